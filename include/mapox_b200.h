@@ -1,0 +1,135 @@
+/* mapox_b200.h - C ABI of libmapox_b200.so: the B200 (sm_100a) hot path of mapox_trainer's
+ * transformer-over-time policy (reference: gabe00122/jaxrl, paths below are relative to its repo root).
+ *
+ * Conventions:
+ *  - every pointer is a DEVICE pointer to caller-owned, row-major, contiguous memory unless a stride is given;
+ *  - bf16 tensors are passed as raw 16-bit words (mpx_bf16); bools arrive as 1-byte PRED (uint8_t);
+ *  - every call only ENQUEUES work on `stream` (a cudaStream_t); nothing synchronises, nothing is allocated
+ *    persistently, all calls are re-entrant and CUDA-graph capturable;
+ *  - return value 0 = MPX_OK, negative = error; mpx_last_error() returns a thread-local message;
+ *  - there is no CPU fallback: on a machine without an sm_100 device every compute call returns MPX_ERR_CUDA.
+ *
+ * The reference has no FFI of its own (it is pure JAX); each entry point cites the reference function whose
+ * device work it replaces.  INTEGRATION.md shows the jax.ffi / ctypes binding for each.
+ */
+#ifndef MAPOX_B200_H_
+#define MAPOX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* mpx_stream_t;
+typedef uint16_t mpx_bf16;
+
+enum { MPX_OK = 0, MPX_ERR_INVALID = -1, MPX_ERR_CUDA = -2, MPX_ERR_UNSUPPORTED = -3 };
+
+const char* mpx_last_error(void);
+int mpx_version(void);
+/* Debug/tuning knobs (tests only). key 0: swap LBO/SBO in MN-major UMMA descriptors. */
+int mpx_debug_set(int key, int value);
+
+/* ---------------------------------------------------------------------------------------------- GAE
+ * Rollout.calculate_advantage, mapox_trainer/rollout.py:128-167 (reverse lax.scan + global normalisation).
+ * rewards (B,T) f32, values (B,T+1) f32, next_terminated (B,T) u8 -> advantages, targets (B,T) f32 (un-normalised)
+ * and stats[0..1] = (sum adv, sum adv^2) in f64 for the normalisation; a multi-GPU caller all-reduces `stats`
+ * before mpx_adv_normalize.  workspace >= mpx_gae_workspace_bytes(B,T). */
+size_t mpx_gae_workspace_bytes(int B, int T);
+int mpx_gae(const float* rewards, const float* values, const uint8_t* next_terminated, int B, int T,
+            float discount, float gae_lambda, float* advantages, float* targets, double* stats,
+            void* workspace, mpx_stream_t stream);
+/* rollout.py:159-162: adv = (adv - mean) / (std + 1e-8), population std, over `count` elements in total. */
+int mpx_adv_normalize(float* advantages, long long n, const double* stats, double count, mpx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------- HL-Gauss
+ * HlGaussValue.get_value, mapox_trainer/values.py:43-45. logits (n,NL) f32, centers (NL) f32 -> value (n) f32. */
+int mpx_hlgauss_value(const float* logits, long long n, int n_logits, const float* centers, float* value,
+                      mpx_stream_t stream);
+/* HlGaussValue.get_loss, values.py:47-63, and its gradient: loss[0] = mean CE; dlogits (n,NL) (nullable) =
+ * grad_scale * d loss / d logits.  supports (NL+1) f32 are the bin edges (values.py:12-19). */
+size_t mpx_hlgauss_loss_workspace_bytes(long long n);
+int mpx_hlgauss_loss(const float* logits, const float* targets, long long n, int n_logits, const float* supports,
+                     float vmin, float vmax, float sigma, float grad_scale, float* loss, float* dlogits,
+                     void* workspace, mpx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------- dense (tcgen05)
+ * nnx.Linear / nnx.LinearGeneral with dtype=bf16 (attention.py:53-92, feed_forward.py:59-71, network.py:228-285):
+ * y = bf16(x @ wt^T) [+ bias -> bf16] [gelu -> bf16] [+ residual -> bf16].  TMA-fed persistent tcgen05 GEMM,
+ * fp32 accumulation in TMEM.  wt is the TRANSPOSED flax kernel: (N,K), row n = output feature n.
+ * The same entry point computes the data gradient of a Linear: dx = linear(dy, wt = kernel as stored (in,out)). */
+typedef struct {
+  const mpx_bf16* x;        long long ldx;    /* (M,K) */
+  const mpx_bf16* wt;       long long ldw;    /* (N,K) */
+  const mpx_bf16* bias;                       /* (N) or NULL */
+  const mpx_bf16* residual; long long ldr;    /* (M,N) or NULL */
+  mpx_bf16* y;              long long ldy;    /* (M,N) or NULL */
+  float* y_f32;             long long ldy32;  /* optional raw fp32 accumulator output (M,N) */
+  int M, N, K;
+  int act;                                    /* 0 none, 1 gelu (tanh approximation, jax.nn.gelu default) */
+} mpx_linear_args;
+int mpx_linear(const mpx_linear_args* a, mpx_stream_t stream);
+
+/* Weight gradient of a Linear: dw (K,N) f32 += x^T (K,M) @ dy (M,N)   (contraction over the M tokens; both
+ * operands are read MN-major straight from their row-major activations - no transposes). dw must be zeroed
+ * (or hold a running sum) by the caller. */
+typedef struct {
+  const mpx_bf16* x;  long long ldx;   /* (M,K) */
+  const mpx_bf16* dy; long long ldy;   /* (M,N) */
+  float* dw;          long long lddw;  /* (K,N) fp32, accumulated with red.add */
+  int M, N, K;
+} mpx_wgrad_args;
+int mpx_linear_wgrad(const mpx_wgrad_args* a, mpx_stream_t stream);
+
+/* q/k/v projections + RoPE (+ KV-cache ring write): AttentionBlock.__call__ attention.py:121-134 and
+ * update_kv_cache :108-114, apply_rope positional_embeddings.py:7-27.
+ * wt_qkv rows: [q heads (Nq*D) | k heads (Nkv*D) | v heads (Nkv*D)], each row = H input features.
+ * Row r uses position pos[r % pos_len] (decode: pos_len = M = B; train: pos_len = T).
+ * If cache_S > 0, k/v are the cache bases (B,S,Nkv,D) and the rows are written at ring slot pos[0] % cache_S
+ * (one scalar for the whole batch, exactly as attention.py:109). head_dim must be 32. */
+typedef struct {
+  const mpx_bf16* x; long long ldx;          /* (M,H) */
+  const mpx_bf16* wt_qkv;                    /* ((Nq+2Nkv)*D, H) */
+  const int32_t* pos; int pos_len;
+  const float* rope_timescale;               /* (D/2) f32: max_wavelength ** (2i/D) */
+  mpx_bf16* q;                               /* (M, Nq*D) */
+  mpx_bf16* k; long long k_row_stride;       /* elements between consecutive rows of k */
+  mpx_bf16* v; long long v_row_stride;
+  int cache_S;
+  int M, H, Nq, Nkv, D;
+} mpx_qkv_rope_args;
+int mpx_qkv_rope(const mpx_qkv_rope_args* a, mpx_stream_t stream);
+
+/* GLU up/gate projections + activation: GLUBlock.__call__ feed_forward.py:73-77:
+ * h = bf16( bf16(gelu(bf16(x@Wup))) * bf16(x@Wgate) ).  wt_ug is (2F,K) packed in 256-row tiles:
+ * rows [256j, 256j+128) = Wup^T rows 128j.., rows [256j+128, 256j+256) = Wgate^T rows 128j.. (F % 128 == 0).
+ * u_save/g_save (nullable, (M,F)) keep the bf16 pre-activations for the backward pass. */
+typedef struct {
+  const mpx_bf16* x; long long ldx;   /* (M,K) */
+  const mpx_bf16* wt_ug;              /* (2F,K) tile-interleaved */
+  mpx_bf16* h;                        /* (M,F) */
+  mpx_bf16* u_save; mpx_bf16* g_save; /* (M,F) or NULL */
+  int M, F, K;
+} mpx_glu_up_args;
+int mpx_glu_up(const mpx_glu_up_args* a, mpx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------- decode attention
+ * Decode branch of AttentionBlock.__call__, attention.py:136-150 (jax.nn.dot_product_attention with
+ * key_value_seq_lengths): one RoPE'd query token per agent against that agent's KV ring cache (already holding
+ * the new token, see mpx_qkv_rope).  kv_len = min(pos[0]+1, S) for every row.  head_dim must be 32. */
+typedef struct {
+  const mpx_bf16* q;        /* (B, Nq*D) */
+  const mpx_bf16* kcache;   /* (B, S, Nkv, D) */
+  const mpx_bf16* vcache;   /* (B, S, Nkv, D) */
+  const int32_t* pos;       /* (B) int32 on device; element 0 is the shared step index */
+  mpx_bf16* out;            /* (B, Nq*D) */
+  int B, S, Nq, Nkv, D;
+} mpx_attn_decode_args;
+int mpx_attn_decode(const mpx_attn_decode_args* a, mpx_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAPOX_B200_H_ */

@@ -1,0 +1,136 @@
+"""Plain-struct view of the reference's config tree (mapox_trainer/config.py) - only the fields the hot path reads.
+
+``from_reference_json`` accepts the reference's own JSON files (config/*.json); the env facts that live in
+mapox (observation components, action count) are parameters because they are not in the JSON.
+``NAMED`` holds the shapes of the five configs BASELINE.json names.
+"""
+
+from __future__ import annotations
+
+import json
+from dataclasses import dataclass, field, replace
+from typing import Optional, Tuple
+
+
+@dataclass(frozen=True)
+class ModelConfig:
+    # TransformerActorCriticConfig (config.py:80-101) + env facts
+    hidden_features: int = 128
+    num_layers: int = 2
+    num_heads: int = 4
+    num_kv_heads: int = 1
+    head_dim: int = 32
+    rope_max_wavelength: float = 10_000.0
+    ffn_size: int = 768
+    value_hidden_dim: Optional[int] = 768
+    value_min: float = -10.0
+    value_max: float = 10.0
+    value_n_logits: int = 51
+    value_sigma: float = 0.10381270166884848
+    obs_type: str = "grid_cnn"
+    cnn_kernels: Tuple[Tuple[int, int], ...] = ((3, 3), (3, 3), (3, 3))
+    cnn_strides: Tuple[Tuple[int, int], ...] = ((2, 2), (1, 1), (1, 1))
+    cnn_channels: Tuple[int, ...] = (16, 32)
+    obs_shape: Tuple[int, ...] = (11, 11, 2)           # (view_w, view_h, K) grid_cnn; (view_w, view_h) grid_flattened
+    obs_max_value: Tuple[int, ...] = (5, 5)            # per-component one-hot sizes (ObservationSpec.max_value)
+    action_dim: int = 8                                # ActionSpec.n
+    task_count: int = 1
+    max_seq_length: int = 512                          # = max_env_steps (train.py:353)
+
+    @property
+    def q_dim(self) -> int:
+        return self.num_heads * self.head_dim
+
+    @property
+    def kv_dim(self) -> int:
+        return self.num_kv_heads * self.head_dim
+
+
+@dataclass(frozen=True)
+class PPOConfig:
+    # PPOConfig (config.py:124-138)
+    epoch_count: int = 1
+    minibatch_count: int = 16
+    vf_coef: float = 0.5392535826611433
+    entropy_coef: float = 0.001
+    entropy_coef_end: float = 0.0
+    vf_clip: float = 0.2827893540340816
+    discount: float = 0.9660902557298033
+    gae_lambda: float = 0.9123716252262187
+    normalize_advantage: bool = True
+
+
+@dataclass(frozen=True)
+class OptimizerConfig:
+    # OptimizerConfig (config.py:112-121)
+    type: str = "muon"
+    learning_rate: float = 0.001
+    weight_decay: float = 0.00010718901435954378
+    eps: float = 1e-8
+    beta1: float = 0.9353521064414686
+    beta2: float = 0.9040155258546868
+    max_norm: float = 0.39644292421090327
+
+
+@dataclass(frozen=True)
+class RunConfig:
+    name: str
+    model: ModelConfig
+    ppo: PPOConfig = field(default_factory=PPOConfig)
+    optimizer: OptimizerConfig = field(default_factory=OptimizerConfig)
+    num_agents: int = 4096        # B = num_envs x agents per env
+    update_steps: int = 5000
+    seed: int = 42
+
+
+def from_reference_json(path: str, *, obs_components: Tuple[int, ...] = (5, 5), action_dim: int = 8,
+                        agents_per_env: Optional[int] = None, task_count: int = 1) -> RunConfig:
+    """Read a reference config/*.json (mapox_trainer/config.py:167-172 load_config) into a RunConfig."""
+    with open(path) as f:
+        j = json.load(f)
+    m = j["learner"]["model"]
+    hist = m["layer"]["history"]
+    enc = m["obs_encoder"]
+    env = j["environment"]
+    val = m["value"]
+    if val["type"] != "hl_gauss":
+        raise ValueError("only the hl_gauss value head is on the B200 path (mse is craftax-only)")
+    model = ModelConfig(
+        hidden_features=m["hidden_features"], num_layers=m["num_layers"], num_heads=hist["num_heads"],
+        num_kv_heads=hist["num_kv_heads"], head_dim=hist["head_dim"],
+        rope_max_wavelength=hist.get("rope_max_wavelength", 10_000.0), ffn_size=m["layer"]["feed_forward"]["size"],
+        value_hidden_dim=m.get("value_hidden_dim"), value_min=val["min"], value_max=val["max"],
+        value_n_logits=val["n_logits"], value_sigma=val["sigma"], obs_type=enc["obs_type"],
+        cnn_kernels=tuple(tuple(k) for k in enc.get("kernels", ())),
+        cnn_strides=tuple(tuple(s) for s in enc.get("strides", ())), cnn_channels=tuple(enc.get("channels", ())),
+        obs_shape=(env.get("view_width", 11), env.get("view_height", 11), len(obs_components)),
+        obs_max_value=tuple(obs_components), action_dim=action_dim, task_count=task_count,
+        max_seq_length=j["max_env_steps"])
+    t = j["learner"]["trainer"]
+    ppo = PPOConfig(epoch_count=t.get("epoch_count", 1), minibatch_count=t.get("minibatch_count", 1),
+                    vf_coef=t.get("vf_coef", 0.05), entropy_coef=t.get("entropy_coef", 0.005),
+                    entropy_coef_end=t.get("entropy_coef_end", 0.0) or 0.0, vf_clip=t.get("vf_clip", 0.2),
+                    discount=t.get("discount", 0.95), gae_lambda=t.get("gae_lambda", 0.95),
+                    normalize_advantage=t.get("normalize_advantage", False))
+    o = j["learner"]["optimizer"]
+    opt = OptimizerConfig(type=o["type"], learning_rate=o["learning_rate"], weight_decay=o["weight_decay"],
+                          eps=o["eps"], beta1=o["beta1"], beta2=o["beta2"], max_norm=o["max_norm"])
+    apn = agents_per_env if agents_per_env is not None else env.get("num_agents", 1)
+    return RunConfig(name=path, model=model, ppo=ppo, optimizer=opt, num_agents=j.get("num_envs", 1) * apn,
+                     update_steps=j["update_steps"], seed=j["seed"] if isinstance(j["seed"], int) else 42)
+
+
+_BASE = ModelConfig()
+NAMED = {
+    # tiny find_return-shaped plumbing config (config/test.json is stale)
+    "test": RunConfig("test", replace(_BASE, max_seq_length=32, obs_shape=(11, 11, 2)), num_agents=16,
+                      ppo=PPOConfig(minibatch_count=2)),
+    "return_2_layers": RunConfig("return_2_layers", _BASE),
+    "return_8_layers": RunConfig("return_8_layers", replace(_BASE, num_layers=8)),
+    "multitask": RunConfig("multitask", replace(_BASE, hidden_features=256, num_layers=16, task_count=4),
+                           ppo=PPOConfig(minibatch_count=32, discount=0.99, gae_lambda=0.91)),
+    "blog_32_layers": RunConfig("blog_32_layers",
+                                replace(_BASE, num_layers=32, obs_type="grid_flattened", obs_shape=(5, 5),
+                                        obs_max_value=(8,)),
+                                ppo=PPOConfig(normalize_advantage=False)),
+}

@@ -1,0 +1,41 @@
+// C-ABI plumbing shared by every entry point: thread-local error string, device queries, debug knobs.
+#include "common.cuh"
+
+namespace mpx {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;
+  }
+  return cached;
+}
+
+extern int g_debug_swap_lbo_sbo;
+
+}  // namespace mpx
+
+extern "C" const char* mpx_last_error(void) { return mpx::g_err; }
+extern "C" int mpx_version(void) { return 100; }
+extern "C" int mpx_debug_set(int key, int value) {
+  if (key == 0) {
+    mpx::g_debug_swap_lbo_sbo = value;
+    return MPX_OK;
+  }
+  mpx::set_error("mpx_debug_set: unknown key %d", key);
+  return MPX_ERR_INVALID;
+}

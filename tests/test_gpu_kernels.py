@@ -1,0 +1,252 @@
+"""GPU parity tests: every C-ABI kernel against the CPU oracle on identical seeded inputs.
+
+Tolerances follow BASELINE.json: bf16 results <= 1e-2 relative, fp32 GAE <= 1e-5, indices bit-exact.
+"""
+
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from jaxrl_b200 import ops as _ops
+    return _ops
+
+
+DEV = "cuda"
+BF16 = torch.bfloat16
+
+
+def _log(msg):
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/probe.log", "a") as f:
+        f.write(msg + "\n")
+
+
+def assert_close_bf16(got, ref, name, rtol=1e-2, abs_floor_frac=4e-3):
+    """|got-ref| <= rtol*|ref| + abs_floor_frac*rms(ref) elementwise (bf16 results)."""
+    got = got.detach().float().cpu()
+    ref = ref.detach().float().cpu()
+    assert got.shape == ref.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    assert torch.isfinite(got).all(), f"{name}: non-finite output"
+    rms = ref.pow(2).mean().sqrt().item() + 1e-12
+    err = (got - ref).abs()
+    tol = rtol * ref.abs() + abs_floor_frac * rms
+    bad = (err > tol).float().mean().item()
+    _log(f"{name}: max_abs_err={err.max().item():.4e} rms_ref={rms:.4e} frac_bad={bad:.3e}")
+    assert bad == 0.0, f"{name}: {bad * 100:.4f}% elements out of tolerance, max err {err.max().item():.4e} (rms {rms:.3e})"
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ---------------------------------------------------------------------------------------------- GAE
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 4), (37, 100), (256, 512), (4096, 512)])
+def test_gae_matches_oracle(ops, B, T):
+    gen = g(B * 1000 + T)
+    r = torch.randn(B, T, generator=gen)
+    v = torch.randn(B, T + 1, generator=gen)
+    term = torch.rand(B, T, generator=gen) < (1.0 / 16)
+    adv_ref, tgt_ref = O.calculate_advantage(r.numpy(), v.numpy(), term.numpy(), 0.9660902557298033,
+                                             0.9123716252262187, False)
+    adv, tgt, stats = ops.gae(r.to(DEV), v.to(DEV), term.to(DEV), 0.9660902557298033, 0.9123716252262187)
+    np.testing.assert_array_equal(tgt.cpu().numpy(), tgt_ref)        # sequential fp32: bit exact
+    np.testing.assert_array_equal(adv.cpu().numpy(), adv_ref)
+    assert abs(stats[0].item() - adv_ref.astype(np.float64).sum()) <= 1e-9 * max(1.0, abs(stats[0].item())) + 1e-6
+    # normalisation
+    adv_n_ref, _ = O.calculate_advantage(r.numpy(), v.numpy(), term.numpy(), 0.9660902557298033,
+                                         0.9123716252262187, True)
+    if B * T > 1:
+        ops.adv_normalize(adv, stats)
+        np.testing.assert_allclose(adv.cpu().numpy(), adv_n_ref, rtol=1e-5, atol=1e-5)
+
+
+def test_gae_known_answers(ops):
+    # reference tests/test_advantage.py:39-61 and :150-163
+    adv, tgt, _ = ops.gae(torch.tensor([[1.0]], device=DEV), torch.tensor([[0.5, 0.8]], device=DEV),
+                          torch.tensor([[False]], device=DEV), 0.99, 0.95)
+    assert abs(tgt.item() - (1.0 + 0.99 * 0.8)) < 1e-5 and abs(adv.item() - (1.0 + 0.99 * 0.8 - 0.5)) < 1e-5
+    r = torch.tensor([[5.0, 10.0, 15.0]], device=DEV)
+    _, tgt, _ = ops.gae(r, torch.tensor([[1.0, 2.0, 3.0, 4.0]], device=DEV),
+                        torch.zeros(1, 3, dtype=torch.bool, device=DEV), 0.0, 0.95)
+    assert torch.allclose(tgt, r, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------- HL-Gauss
+@pytest.mark.parametrize("n,NL,vmin,vmax,sigma", [(7, 51, -10.0, 10.0, 0.1038127), (5000, 51, -10.0, 10.0, 0.1038127),
+                                                  (300, 51, -5.0, 5.0, 0.75), (64, 10, -1.0, 1.0, 0.5)])
+def test_hlgauss(ops, n, NL, vmin, vmax, sigma):
+    gen = g(n + NL)
+    logits = torch.randn(n, NL, generator=gen) * 2.0
+    targets = torch.randn(n, generator=gen) * (vmax - vmin) * 0.4
+    targets[0] = 100.0
+    targets[-1] = -100.0     # clipped (tests/test_values.py:92-98)
+    supports, centers = O.calculate_supports(vmin, vmax, NL)
+    val_ref = O.hlgauss_get_value(logits, centers)
+    val = ops.hlgauss_value(logits.to(DEV), centers.to(DEV))
+    torch.testing.assert_close(val.cpu(), val_ref, rtol=1e-5, atol=1e-5)
+    lg = logits.clone().requires_grad_(True)
+    loss_ref = O.hlgauss_get_loss(lg[None], targets[None], vmin, vmax, sigma)
+    loss_ref.backward()
+    loss, dl = ops.hlgauss_loss(logits.to(DEV), targets.to(DEV), supports.reshape(-1).to(DEV), vmin, vmax, sigma, 1.0)
+    torch.testing.assert_close(loss.cpu()[0], loss_ref.detach(), rtol=2e-5, atol=1e-6)
+    torch.testing.assert_close(dl.cpu(), lg.grad, rtol=1e-4, atol=1e-7)
+    assert torch.isfinite(dl).all()
+
+
+def test_hlgauss_uniform_logits_value_zero(ops):
+    # tests/test_values.py:49-57
+    _, centers = O.calculate_supports(-5.0, 5.0, 51)
+    v = ops.hlgauss_value(torch.zeros(2, 4, 51, device=DEV), centers.to(DEV))
+    assert v.shape == (2, 4) and torch.allclose(v, torch.zeros_like(v), atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------- dense
+def _lin_ref(x, w_t, bias=None, residual=None, act=0):
+    y = O.linear(x, w_t.t().float(), None if bias is None else bias.float())
+    if act == 1:
+        y = O.gelu_tanh(y)
+    if residual is not None:
+        y = (y.float() + residual.float()).to(BF16)
+    return y
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 64), (300, 128, 192), (4096, 128, 128), (1000, 768, 128),
+                                   (4096, 128, 1536), (20000, 128, 768), (77, 128, 51), (513, 192, 128)])
+def test_linear_plain(ops, M, K, N):
+    gen = g(M + K + N)
+    x = (torch.randn(M, K, generator=gen)).to(BF16)
+    wt = (torch.randn(N, K, generator=gen) / math.sqrt(K)).to(BF16)
+    y = ops.linear(x.to(DEV), wt.to(DEV))
+    assert_close_bf16(y, _lin_ref(x, wt), f"linear {M}x{K}x{N}")
+
+
+def test_linear_epilogues(ops):
+    gen = g(11)
+    M, K, N = 1000, 128, 768
+    x = torch.randn(M, K, generator=gen).to(BF16)
+    wt = (torch.randn(N, K, generator=gen) / math.sqrt(K)).to(BF16)
+    bias = (torch.randn(N, generator=gen) * 0.5).to(BF16)
+    y = ops.linear(x.to(DEV), wt.to(DEV), bias=bias.to(DEV), act=1)
+    assert_close_bf16(y, _lin_ref(x, wt, bias=bias, act=1), "linear bias+gelu")
+    M, K, N = 777, 768, 128
+    x = torch.randn(M, K, generator=gen).to(BF16)
+    wt = (torch.randn(N, K, generator=gen) / math.sqrt(K)).to(BF16)
+    res = torch.randn(M, N, generator=gen).to(BF16)
+    y = ops.linear(x.to(DEV), wt.to(DEV), residual=res.to(DEV))
+    assert_close_bf16(y, _lin_ref(x, wt, residual=res), "linear residual")
+    out32 = torch.empty(M, N, dtype=torch.float32, device=DEV)
+    ops.linear(x.to(DEV), wt.to(DEV), out_f32=out32, want_bf16=False)
+    torch.testing.assert_close(out32.cpu(), x.float() @ wt.float().t(), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("M,K,N", [(64, 128, 64), (1000, 128, 192), (131072, 128, 1536), (5000, 768, 128), (333, 128, 128)])
+def test_linear_wgrad(ops, M, K, N):
+    gen = g(M + 3 * K + N)
+    x = torch.randn(M, K, generator=gen).to(BF16)
+    dy = (torch.randn(M, N, generator=gen) * 0.1).to(BF16)
+    ref = (x.double().t() @ dy.double()).float() if M <= 5000 else None
+    xd, dyd = x.to(DEV), dy.to(DEV)
+    if ref is None:
+        ref = (xd.float().t() @ dyd.float()).cpu()
+    from jaxrl_b200._lib import lib
+    results = {}
+    for variant in (0, 1):
+        lib.mpx_debug_set(0, variant)
+        dw = torch.zeros(K, N, dtype=torch.float32, device=DEV)
+        ops.linear_wgrad(xd, dyd, dw)
+        torch.cuda.synchronize()
+        err = (dw.cpu() - ref).abs().max().item()
+        results[variant] = err
+    lib.mpx_debug_set(0, 0)
+    _log(f"wgrad {M}x{K}x{N}: max_abs_err variant0={results[0]:.4e} variant1(swapped)={results[1]:.4e} "
+         f"ref_rms={ref.pow(2).mean().sqrt().item():.4e}")
+    tol = 2e-3 * ref.pow(2).mean().sqrt().item() * math.sqrt(max(M, 64) / 64)
+    assert results[0] <= max(tol, 1e-3), f"wgrad variant0 err {results[0]} (variant1 {results[1]})"
+
+
+def _rope_timescale(D, base=10_000.0):
+    return torch.tensor(base, dtype=torch.float32) ** (2.0 * torch.arange(0, D // 2, dtype=torch.float32) / D)
+
+
+@pytest.mark.parametrize("Nq,Nkv", [(4, 1), (4, 2), (4, 4)])
+def test_qkv_rope_train(ops, Nq, Nkv):
+    gen = g(5 + Nq + Nkv)
+    Bb, T, H, D = 3, 40, 128, 32
+    x = torch.randn(Bb, T, H, generator=gen).to(BF16)
+    wq = torch.randn(H, Nq * D, generator=gen) / math.sqrt(H)
+    wk = torch.randn(H, Nkv * D, generator=gen) / math.sqrt(H)
+    wv = torch.randn(H, Nkv * D, generator=gen) / math.sqrt(H)
+    pos = torch.arange(T, dtype=torch.int32)
+    q_ref = O.apply_rope(O.linear(x, wq).reshape(Bb, T, Nq, D), pos[None], D)
+    k_ref = O.apply_rope(O.linear(x, wk).reshape(Bb, T, Nkv, D), pos[None], D)
+    v_ref = O.linear(x, wv).reshape(Bb, T, Nkv, D)
+    wt = torch.cat([wq, wk, wv], dim=1).t().contiguous().to(BF16)
+    q, k, v = ops.qkv_rope(x.reshape(-1, H).to(DEV), wt.to(DEV), pos.to(DEV), _rope_timescale(D).to(DEV), Nq, Nkv, D)
+    assert_close_bf16(q.reshape(Bb, T, Nq, D), q_ref, "qkv_rope q")
+    assert_close_bf16(k.reshape(Bb, T, Nkv, D), k_ref, "qkv_rope k")
+    assert_close_bf16(v.reshape(Bb, T, Nkv, D), v_ref, "qkv_rope v")
+
+
+@pytest.mark.parametrize("step,S", [(0, 16), (3, 8), (6, 4), (511, 512)])
+def test_qkv_rope_cache_slot(ops, step, S):
+    """Ring write at pos % S (reference tests/test_attention.py:91-121), untouched elsewhere (bit exact)."""
+    gen = g(step + S)
+    Bb, H, D, Nq, Nkv = 5, 128, 32, 4, 1
+    x = torch.randn(Bb, H, generator=gen).to(BF16)
+    w = (torch.randn((Nq + 2 * Nkv) * D, H, generator=gen) / math.sqrt(H)).to(BF16)
+    kc = torch.full((Bb, S, Nkv, D), 7.0, dtype=BF16, device=DEV)
+    vc = torch.full((Bb, S, Nkv, D), -3.0, dtype=BF16, device=DEV)
+    pos = torch.full((Bb,), step, dtype=torch.int32, device=DEV)
+    q, _, _ = ops.qkv_rope(x.to(DEV), w.to(DEV), pos, _rope_timescale(D).to(DEV), Nq, Nkv, D, k=kc, v=vc,
+                           k_row_stride=S * Nkv * D, v_row_stride=S * Nkv * D, cache_S=S)
+    slot = step % S
+    k_ref = O.apply_rope(O.linear(x, w[Nq * D:(Nq + Nkv) * D].t().float()).reshape(Bb, 1, Nkv, D),
+                         torch.full((Bb, 1), step), D)
+    v_ref = O.linear(x, w[(Nq + Nkv) * D:].t().float()).reshape(Bb, 1, Nkv, D)
+    assert_close_bf16(kc[:, slot], k_ref[:, 0], "cache k slot")
+    assert_close_bf16(vc[:, slot], v_ref[:, 0], "cache v slot")
+    mask = torch.ones(S, dtype=torch.bool)
+    mask[slot] = False
+    assert (kc[:, mask] == 7.0).all() and (vc[:, mask] == -3.0).all()
+
+
+def test_glu_up(ops):
+    gen = g(21)
+    M, K, F = 700, 128, 768
+    x = torch.randn(M, K, generator=gen).to(BF16)
+    wu = torch.randn(K, F, generator=gen) / math.sqrt(K)
+    wg = torch.randn(K, F, generator=gen) / math.sqrt(K)
+    up = O.linear(x, wu)
+    gate = O.linear(x, wg)
+    h_ref = (O.gelu_tanh(up).float() * gate.float()).to(BF16)
+    h, u, gg = ops.glu_up(x.to(DEV), ops.pack_glu_weight(wu, wg).to(DEV), F, save=True)
+    assert_close_bf16(u, up, "glu u")
+    assert_close_bf16(gg, gate, "glu g")
+    assert_close_bf16(h, h_ref, "glu h", rtol=2e-2)
+
+
+# ---------------------------------------------------------------------------------------------- decode attention
+@pytest.mark.parametrize("step,S,Nq,Nkv,Bb", [(0, 16, 4, 1, 3), (5, 16, 4, 1, 9), (31, 64, 4, 1, 4), (32, 64, 4, 1, 4),
+                                              (100, 512, 4, 1, 33), (511, 512, 4, 1, 130), (700, 512, 4, 1, 5),
+                                              (77, 128, 4, 2, 6), (40, 64, 4, 4, 3), (9, 32, 8, 1, 2)])
+def test_attn_decode(ops, step, S, Nq, Nkv, Bb):
+    gen = g(step * 7 + S + Nq + Nkv)
+    D = 32
+    q = torch.randn(Bb, Nq, D, generator=gen).to(BF16)
+    kc = torch.randn(Bb, S, Nkv, D, generator=gen).to(BF16)
+    vc = torch.randn(Bb, S, Nkv, D, generator=gen).to(BF16)
+    kv_len = min(step + 1, S)
+    ref = O.dot_product_attention(q[:, None], kc, vc, kv_len=kv_len)[:, 0]
+    pos = torch.full((Bb,), step, dtype=torch.int32, device=DEV)
+    out = ops.attn_decode(q.reshape(Bb, -1).to(DEV), kc.to(DEV), vc.to(DEV), pos, Nq, Nkv, D)
+    assert_close_bf16(out.reshape(Bb, Nq, D), ref, f"attn_decode step={step} S={S} Nkv={Nkv}")
