@@ -39,7 +39,7 @@ int mpx_debug_set(int key, int value);
  * before mpx_adv_normalize.  workspace >= mpx_gae_workspace_bytes(B,T). */
 size_t mpx_gae_workspace_bytes(int B, int T);
 int mpx_gae(const float* rewards, const float* values, const uint8_t* next_terminated, int B, int T,
-            float discount, float gae_lambda, float* advantages, float* targets, double* stats,
+            double discount, double gae_lambda, float* advantages, float* targets, double* stats,
             void* workspace, mpx_stream_t stream);
 /* rollout.py:159-162: adv = (adv - mean) / (std + 1e-8), population std, over `count` elements in total. */
 int mpx_adv_normalize(float* advantages, long long n, const double* stats, double count, mpx_stream_t stream);
@@ -128,6 +128,29 @@ typedef struct {
   int B, S, Nq, Nkv, D;
 } mpx_attn_decode_args;
 int mpx_attn_decode(const mpx_attn_decode_args* a, mpx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------- row-wise ops
+ * flax nnx.RMSNorm (eps 1e-6) as used by TransformerBlock (network.py:158-172) and output_norm (:321):
+ * y = bf16(x32 * (rsqrt(mean(x32^2)+eps) * scale)).  x,y (M,H) bf16, scale (H) f32; H in {128,256,384,512}. */
+int mpx_rmsnorm_fwd(const mpx_bf16* x, const float* scale, float eps, mpx_bf16* y, long long M, int H,
+                    mpx_stream_t stream);
+/* Its transpose: dx = bf16(d/dx) [+ dres, bf16 add: the cotangent of the residual branch]; dscale (H) f32 is
+ * accumulated atomically (nullable). */
+int mpx_rmsnorm_bwd(const mpx_bf16* dy, const mpx_bf16* x, const float* scale, float eps, const mpx_bf16* dres,
+                    mpx_bf16* dx, float* dscale, long long M, int H, mpx_stream_t stream);
+/* Transpose of the GLU activation (feed_forward.py:75-77): dug (M,2F) = [du | dg] from dh, u, g (M,F). */
+int mpx_glu_bwd(const mpx_bf16* dh, const mpx_bf16* u, const mpx_bf16* g, mpx_bf16* dug, long long M, int F,
+                mpx_stream_t stream);
+/* dz = bf16(dy * gelu'(z)) (value_mlp / conv activations, network.py:338, observation.py:93). */
+int mpx_gelu_bwd(const mpx_bf16* dy, const mpx_bf16* z, mpx_bf16* dz, long long n, mpx_stream_t stream);
+/* apply_rope (positional_embeddings.py:7-27) in place on heads [0,nheads) of x (M,ld); inverse=1 applies the
+ * transpose (used for dq, dk).  Row r uses pos[r % pos_len]. */
+int mpx_rope(mpx_bf16* x, long long ld, const int32_t* pos, int pos_len, const float* rope_timescale, long long M,
+             int nheads, int head_dim, int inverse, mpx_stream_t stream);
+/* out (N) f32 += column sums of x (M,ld) bf16 (bias gradients). */
+int mpx_colsum(const mpx_bf16* x, long long ld, long long M, int N, float* out, mpx_stream_t stream);
+/* out = bf16(a + b) (sum of two bf16 cotangents). */
+int mpx_add_bf16(const mpx_bf16* a, const mpx_bf16* b, mpx_bf16* out, long long n, mpx_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -62,7 +62,7 @@ AttnDecodeArgs = _struct("mpx_attn_decode_args", [
 lib.mpx_last_error.restype = C.c_char_p
 lib.mpx_gae_workspace_bytes.restype = C.c_size_t
 lib.mpx_gae_workspace_bytes.argtypes = [C.c_int, C.c_int]
-lib.mpx_gae.argtypes = [c_p, c_p, c_p, C.c_int, C.c_int, C.c_float, C.c_float, c_p, c_p, c_p, c_p, c_p]
+lib.mpx_gae.argtypes = [c_p, c_p, c_p, C.c_int, C.c_int, C.c_double, C.c_double, c_p, c_p, c_p, c_p, c_p]
 lib.mpx_adv_normalize.argtypes = [c_p, c_ll, c_p, C.c_double, c_p]
 lib.mpx_hlgauss_value.argtypes = [c_p, c_ll, C.c_int, c_p, c_p, c_p]
 lib.mpx_hlgauss_loss_workspace_bytes.restype = C.c_size_t
@@ -72,6 +72,13 @@ lib.mpx_hlgauss_loss.argtypes = [c_p, c_p, c_ll, C.c_int, c_p, C.c_float, C.c_fl
 for _name in ("mpx_linear", "mpx_linear_wgrad", "mpx_qkv_rope", "mpx_glu_up", "mpx_attn_decode"):
     getattr(lib, _name).argtypes = [c_p, c_p]
 lib.mpx_debug_set.argtypes = [C.c_int, C.c_int]
+lib.mpx_rmsnorm_fwd.argtypes = [c_p, c_p, C.c_float, c_p, c_ll, C.c_int, c_p]
+lib.mpx_rmsnorm_bwd.argtypes = [c_p, c_p, c_p, C.c_float, c_p, c_p, c_p, c_ll, C.c_int, c_p]
+lib.mpx_glu_bwd.argtypes = [c_p, c_p, c_p, c_p, c_ll, C.c_int, c_p]
+lib.mpx_gelu_bwd.argtypes = [c_p, c_p, c_p, c_ll, c_p]
+lib.mpx_rope.argtypes = [c_p, c_ll, c_p, C.c_int, c_p, c_ll, C.c_int, C.c_int, C.c_int, c_p]
+lib.mpx_colsum.argtypes = [c_p, c_ll, c_ll, C.c_int, c_p, c_p]
+lib.mpx_add_bf16.argtypes = [c_p, c_p, c_p, c_ll, c_p]
 
 
 def check(rc: int, what: str = "") -> None:

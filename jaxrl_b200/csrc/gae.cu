@@ -148,7 +148,7 @@ extern "C" size_t mpx_gae_workspace_bytes(int B, int T) {
 }
 
 extern "C" int mpx_gae(const float* rewards, const float* values, const uint8_t* next_terminated, int B, int T,
-                       float discount, float gae_lambda, float* advantages, float* targets, double* stats,
+                       double discount, double gae_lambda, float* advantages, float* targets, double* stats,
                        void* workspace, mpx_stream_t stream) {
   MPX_REQUIRE(B > 0 && T > 0, "mpx_gae: empty input B=%d T=%d", B, T);
   MPX_REQUIRE(rewards && values && next_terminated && advantages && targets && stats && workspace,
@@ -156,9 +156,11 @@ extern "C" int mpx_gae(const float* rewards, const float* values, const uint8_t*
   const int grid = ceil_div(B, GAE_ROWS);
   double* partials = reinterpret_cast<double*>(workspace);
   // (1 - gae_lambda) is folded in double before the scan, as the python-float expression in rollout.py:138 is.
-  const float one_minus = (float)(1.0 - (double)gae_lambda);
-  gae_scan_kernel<<<grid, GAE_THREADS, 0, (cudaStream_t)stream>>>(rewards, values, next_terminated, B, T, discount,
-                                                                  gae_lambda, one_minus, advantages, targets, partials);
+  // discount / gae_lambda arrive as doubles (python floats in the reference) and are rounded to fp32 once each.
+  const float one_minus = (float)(1.0 - gae_lambda);
+  gae_scan_kernel<<<grid, GAE_THREADS, 0, (cudaStream_t)stream>>>(rewards, values, next_terminated, B, T,
+                                                                  (float)discount, (float)gae_lambda, one_minus,
+                                                                  advantages, targets, partials);
   gae_stats_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, grid, stats);
   return check_launch("mpx_gae");
 }
