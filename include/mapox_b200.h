@@ -53,7 +53,9 @@ int mpx_hlgauss_value(const float* logits, long long n, int n_logits, const floa
 size_t mpx_hlgauss_loss_workspace_bytes(long long n);
 int mpx_hlgauss_loss(const float* logits, const float* targets, long long n, int n_logits, const float* supports,
                      float vmin, float vmax, float sigma, float grad_scale, float* loss, float* dlogits,
-                     void* workspace, mpx_stream_t stream);
+                     mpx_bf16* dlogits_bf16, int ld_bf16, void* workspace, mpx_stream_t stream);
+/* dlogits_bf16 (nullable): the same gradient as bf16 rows of pitch ld_bf16 >= n_logits, zero padded - the
+ * operand layout the tensor-core backward of the value head consumes. */
 
 /* ---------------------------------------------------------------------------------------------- dense (tcgen05)
  * nnx.Linear / nnx.LinearGeneral with dtype=bf16 (attention.py:53-92, feed_forward.py:59-71, network.py:228-285):
@@ -69,6 +71,7 @@ typedef struct {
   float* y_f32;             long long ldy32;  /* optional raw fp32 accumulator output (M,N) */
   int M, N, K;
   int act;                                    /* 0 none, 1 gelu (tanh approximation, jax.nn.gelu default) */
+  mpx_bf16* y_pre;                            /* optional (M,N), pitch ldy: bf16 pre-activation saved for backward */
 } mpx_linear_args;
 int mpx_linear(const mpx_linear_args* a, mpx_stream_t stream);
 
@@ -94,7 +97,7 @@ typedef struct {
   const mpx_bf16* wt_qkv;                    /* ((Nq+2Nkv)*D, H) */
   const int32_t* pos; int pos_len;
   const float* rope_timescale;               /* (D/2) f32: max_wavelength ** (2i/D) */
-  mpx_bf16* q;                               /* (M, Nq*D) */
+  mpx_bf16* q; long long q_row_stride;       /* (M, Nq*D) with row pitch q_row_stride elements */
   mpx_bf16* k; long long k_row_stride;       /* elements between consecutive rows of k */
   mpx_bf16* v; long long v_row_stride;
   int cache_S;
@@ -151,6 +154,118 @@ int mpx_rope(mpx_bf16* x, long long ld, const int32_t* pos, int pos_len, const f
 int mpx_colsum(const mpx_bf16* x, long long ld, long long M, int N, float* out, mpx_stream_t stream);
 /* out = bf16(a + b) (sum of two bf16 cotangents). */
 int mpx_add_bf16(const mpx_bf16* a, const mpx_bf16* b, mpx_bf16* out, long long n, mpx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------- training attention
+ * Training branch of AttentionBlock.__call__, attention.py:151-169 (causal jax.nn.dot_product_attention) over
+ * full trajectory windows.  q (B*T, Nq*D), k/v (B*T, Nkv*D) bf16 already rotated (mpx_qkv_rope), given with row
+ * strides so they may be column slices of one (B*T, (Nq+2Nkv)*D) buffer.  o (B*T, Nq*D) bf16;
+ * lse (B*T, Nq) f32 is saved for the backward pass (log2 units of the scaled scores).  T % 64 == 0, D == 32. */
+typedef struct {
+  const mpx_bf16* q; long long ldq;
+  const mpx_bf16* k; long long ldk;
+  const mpx_bf16* v; long long ldv;
+  mpx_bf16* o;       long long ldo;
+  float* lse;
+  int B, T, Nq, Nkv, D;
+} mpx_attn_train_args;
+int mpx_attn_train_fwd(const mpx_attn_train_args* a, mpx_stream_t stream);
+
+/* Its transpose (what nnx.grad, train.py:236-238, derives): given dout = d loss / d o, writes the cotangents of the
+ * *un-rotated* projections (inverse RoPE applied): dq (B*T, Nq*D), dk, dv (B*T, Nkv*D) bf16 with row strides.
+ * delta (B*T, Nq) f32 and dq_acc (B*T, Nq*D) f32 are caller-provided scratch. */
+typedef struct {
+  const mpx_bf16* q; long long ldq;
+  const mpx_bf16* k; long long ldk;
+  const mpx_bf16* v; long long ldv;
+  const mpx_bf16* o; long long ldo;
+  const mpx_bf16* dout; long long lddo;
+  const float* lse;
+  float* delta;
+  float* dq_acc;
+  mpx_bf16* dq; long long lddq;
+  mpx_bf16* dk; long long lddk;
+  mpx_bf16* dv; long long lddv;
+  const int32_t* pos; int pos_len;
+  const float* rope_timescale;
+  int B, T, Nq, Nkv, D;
+} mpx_attn_train_bwd_args;
+int mpx_attn_train_bwd(const mpx_attn_train_bwd_args* a, mpx_stream_t stream);
+
+/* nnx.Linear with dtype=None on f32(bf16 activations) (the HL-Gauss head, values.py:34/40-41): y (M,N) f32 =
+ * f32(x) @ W + bias with the fp32 weight carried as a bf16 hi/lo pair (wt_hilo (128,K): rows [0,64) = bf16(W^T),
+ * rows [64,128) = bf16(W^T - hi); rows >= N of each half zero).  N <= 64. */
+int mpx_linear_f32w(const mpx_bf16* x, long long ldx, const mpx_bf16* wt_hilo, const float* bias, float* y,
+                    long long ldy, int M, int N, int K, mpx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------- embeds and heads
+ * network.py:303-309: x = obs_emb + reward_encoder(reward) + action_embedder.encode(last_action) [+ task embed],
+ * every term and every sum rounded to bf16.  Tables/kernels are the fp32 parameters. task_ids/task_table nullable. */
+int mpx_embed_combine(const mpx_bf16* obs_emb, const float* reward, const int32_t* last_action,
+                      const int32_t* task_ids, const float* w_reward, const float* b_reward,
+                      const float* action_table, int A, const float* task_table, int n_tasks, mpx_bf16* x,
+                      long long M, int H, mpx_stream_t stream);
+/* Its transpose: accumulates (+=) into the fp32 gradients of reward_encoder.{kernel,bias} and the embedding tables. */
+int mpx_embed_bwd(const mpx_bf16* dx, const float* reward, const int32_t* last_action, const int32_t* task_ids,
+                  int A, int n_tasks, float* d_w_reward, float* d_b_reward, float* d_action_table,
+                  float* d_task_table, long long M, int H, mpx_stream_t stream);
+/* network.py:323-331: tied action logits f32(x) @ table^T (M,A) f32, masked entries = finfo(f32).min. A <= 32. */
+int mpx_policy_logits(const mpx_bf16* x, const float* table, const uint8_t* action_mask, float* logits, long long M,
+                      int H, int A, mpx_stream_t stream);
+/* distrax.Categorical(logits).sample / log_prob (train.py:97-98) as Gumbel arg-max with the noise as an input:
+ * action = argmax(logits + gumbel) (first maximum), log_prob = log_softmax(logits)[action]. */
+int mpx_policy_sample(const float* logits, const float* gumbel, int32_t* action, float* log_prob, long long M, int A,
+                      mpx_stream_t stream);
+/* Counter-based Philox-4x32-10 Gumbel(0,1) noise (the reference draws it from JAX's threefry; the noise source is
+ * outside the parity contract, the arg-max is inside it). */
+int mpx_gumbel_noise(float* out, long long n, unsigned long long seed, unsigned long long stream_id,
+                     const unsigned long long* stream_offset /* device, nullable: added to stream_id */,
+                     mpx_stream_t stream);
+/* Policy part of ppo_loss, train.py:193-212, and its gradient: losses[0] = actor_loss, losses[1] = entropy_loss
+ * (means over M tokens); dlogits (M,A) (nullable) = d(actor_loss + entropy_coef*entropy_loss)/dlogits. */
+size_t mpx_ppo_policy_loss_workspace_bytes(long long M);
+int mpx_ppo_policy_loss(const float* logits, const int32_t* actions, const float* old_log_prob,
+                        const float* advantages, float clip_eps, float entropy_coef,
+                        const float* entropy_coef_dev /* device scalar, nullable: overrides entropy_coef */,
+                        float* losses, float* dlogits, void* workspace, long long M, int A, mpx_stream_t stream);
+/* Transpose of mpx_policy_logits: dx = bf16(dlogits @ table) [+ dx_other, bf16 add]; dtable += dlogits^T @ f32(x). */
+int mpx_policy_head_bwd(const float* dlogits, const mpx_bf16* x, const float* table, const mpx_bf16* dx_other,
+                        mpx_bf16* dx, float* dtable, long long M, int H, int A, mpx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------- obs encoder support
+ * GridCnnObsEncoder (observation.py:84-96) lowered to GEMMs.  obs (M,IH,IW,K) u8 -> one-hot im2col rows
+ * (M*OH*OW, KP) bf16, column (ky*kw+kx)*C + channel, zero padded to KP (multiple of 8). */
+int mpx_obs_onehot_im2col(const uint8_t* obs, mpx_bf16* out, long long M, int IH, int IW, int K,
+                          const int* onehot_sizes /* host array [K] */, int kh, int kw, int sh, int sw, int KP,
+                          mpx_stream_t stream);
+/* NHWC im2col / its transpose for the hidden conv layers (C % 8 == 0, VALID padding). */
+int mpx_im2col(const mpx_bf16* a, mpx_bf16* x, long long M, int IH, int IW, int C, int kh, int kw, int sh, int sw,
+               mpx_stream_t stream);
+int mpx_col2im(const mpx_bf16* dx, mpx_bf16* da, long long M, int IH, int IW, int C, int kh, int kw, int sh, int sw,
+               mpx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------- optimizer
+ * optimizer.py:12-23: optax.adamw(linear_schedule(lr0, 0, total_steps)) then clip_by_global_norm(max_norm) on the
+ * update, over flat fp32 buffers of n elements.  `step` is a device int32 counter (read, then incremented).
+ * grads are multiplied by grad_scale first (1/world_size after a sum all-reduce). */
+size_t mpx_adamw_workspace_bytes(long long n);
+int mpx_adamw_step(float* params, const float* grads, float* mu, float* nu, float* update_scratch, long long n,
+                   int* step, float lr0, float total_steps, float b1, float b2, float eps, float weight_decay,
+                   float max_norm, float grad_scale, float* update_norm_out, void* workspace, mpx_stream_t stream);
+/* fp32 master weights -> bf16 GEMM operand copies. descs is a DEVICE array; each entry casts (and optionally
+ * transposes) a (rows, cols) fp32 block with pitch src_ld into a bf16 destination with pitch dst_ld. */
+typedef struct {
+  const float* src; long long src_ld;
+  mpx_bf16* dst;    long long dst_ld;
+  int rows, cols;
+  int transpose;   /* bit 0: transpose; bit 1: store bf16(w - f32(bf16(w))) (lo half of a hi/lo split) */
+  int _pad;
+} mpx_prep_desc;
+int mpx_prep_weights(const mpx_prep_desc* descs_device, int ndesc, mpx_stream_t stream);
+/* Rollout buffers (rollout.py:11-30) are written time-major (T,B,item) by the decode loop; this produces the
+ * batch-major rows training reads, applying the row permutation of rollout.py:169-181 (perm nullable):
+ * dst[b][t] = src[t][perm[b]]. */
+int mpx_transpose_tb(const void* src, void* dst, const int32_t* perm, int T, int B, int item_bytes,
+                     mpx_stream_t stream);
 
 #ifdef __cplusplus
 }

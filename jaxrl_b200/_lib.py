@@ -7,7 +7,6 @@ raises if the CUDA call fails (e.g. no sm_100 device).
 from __future__ import annotations
 
 import ctypes as C
-import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
@@ -24,13 +23,15 @@ def _load() -> C.CDLL:
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             f"or `make -C {_PKG / 'csrc'}` (nvcc, sm_100a). There is no CPU fallback."
         )
-    return C.CDLL(str(LIB_PATH), mode=os.RTLD_LOCAL if hasattr(os, "RTLD_LOCAL") else C.DEFAULT_MODE)
+    return C.CDLL(str(LIB_PATH))
 
 
 lib = _load()
 
 c_ll = C.c_longlong
 c_p = C.c_void_p
+c_i = C.c_int
+c_f = C.c_float
 
 
 def _struct(name, fields):
@@ -39,46 +40,80 @@ def _struct(name, fields):
 
 LinearArgs = _struct("mpx_linear_args", [
     ("x", c_p), ("ldx", c_ll), ("wt", c_p), ("ldw", c_ll), ("bias", c_p), ("residual", c_p), ("ldr", c_ll),
-    ("y", c_p), ("ldy", c_ll), ("y_f32", c_p), ("ldy32", c_ll), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
-    ("act", C.c_int)])
+    ("y", c_p), ("ldy", c_ll), ("y_f32", c_p), ("ldy32", c_ll), ("M", c_i), ("N", c_i), ("K", c_i),
+    ("act", c_i), ("y_pre", c_p)])
 
 WgradArgs = _struct("mpx_wgrad_args", [
     ("x", c_p), ("ldx", c_ll), ("dy", c_p), ("ldy", c_ll), ("dw", c_p), ("lddw", c_ll),
-    ("M", C.c_int), ("N", C.c_int), ("K", C.c_int)])
+    ("M", c_i), ("N", c_i), ("K", c_i)])
 
 QkvRopeArgs = _struct("mpx_qkv_rope_args", [
-    ("x", c_p), ("ldx", c_ll), ("wt_qkv", c_p), ("pos", c_p), ("pos_len", C.c_int), ("rope_timescale", c_p),
-    ("q", c_p), ("k", c_p), ("k_row_stride", c_ll), ("v", c_p), ("v_row_stride", c_ll), ("cache_S", C.c_int),
-    ("M", C.c_int), ("H", C.c_int), ("Nq", C.c_int), ("Nkv", C.c_int), ("D", C.c_int)])
+    ("x", c_p), ("ldx", c_ll), ("wt_qkv", c_p), ("pos", c_p), ("pos_len", c_i), ("rope_timescale", c_p),
+    ("q", c_p), ("q_row_stride", c_ll), ("k", c_p), ("k_row_stride", c_ll), ("v", c_p), ("v_row_stride", c_ll),
+    ("cache_S", c_i), ("M", c_i), ("H", c_i), ("Nq", c_i), ("Nkv", c_i), ("D", c_i)])
 
 GluUpArgs = _struct("mpx_glu_up_args", [
     ("x", c_p), ("ldx", c_ll), ("wt_ug", c_p), ("h", c_p), ("u_save", c_p), ("g_save", c_p),
-    ("M", C.c_int), ("F", C.c_int), ("K", C.c_int)])
+    ("M", c_i), ("F", c_i), ("K", c_i)])
 
 AttnDecodeArgs = _struct("mpx_attn_decode_args", [
     ("q", c_p), ("kcache", c_p), ("vcache", c_p), ("pos", c_p), ("out", c_p),
-    ("B", C.c_int), ("S", C.c_int), ("Nq", C.c_int), ("Nkv", C.c_int), ("D", C.c_int)])
+    ("B", c_i), ("S", c_i), ("Nq", c_i), ("Nkv", c_i), ("D", c_i)])
+
+AttnTrainArgs = _struct("mpx_attn_train_args", [
+    ("q", c_p), ("ldq", c_ll), ("k", c_p), ("ldk", c_ll), ("v", c_p), ("ldv", c_ll), ("o", c_p), ("ldo", c_ll),
+    ("lse", c_p), ("B", c_i), ("T", c_i), ("Nq", c_i), ("Nkv", c_i), ("D", c_i)])
+
+AttnTrainBwdArgs = _struct("mpx_attn_train_bwd_args", [
+    ("q", c_p), ("ldq", c_ll), ("k", c_p), ("ldk", c_ll), ("v", c_p), ("ldv", c_ll), ("o", c_p), ("ldo", c_ll),
+    ("dout", c_p), ("lddo", c_ll), ("lse", c_p), ("delta", c_p), ("dq_acc", c_p),
+    ("dq", c_p), ("lddq", c_ll), ("dk", c_p), ("lddk", c_ll), ("dv", c_p), ("lddv", c_ll),
+    ("pos", c_p), ("pos_len", c_i), ("rope_timescale", c_p),
+    ("B", c_i), ("T", c_i), ("Nq", c_i), ("Nkv", c_i), ("D", c_i)])
+
+PrepDesc = _struct("mpx_prep_desc", [
+    ("src", c_p), ("src_ld", c_ll), ("dst", c_p), ("dst_ld", c_ll), ("rows", c_i), ("cols", c_i),
+    ("transpose", c_i), ("_pad", c_i)])
 
 lib.mpx_last_error.restype = C.c_char_p
+lib.mpx_debug_set.argtypes = [c_i, c_i]
 lib.mpx_gae_workspace_bytes.restype = C.c_size_t
-lib.mpx_gae_workspace_bytes.argtypes = [C.c_int, C.c_int]
-lib.mpx_gae.argtypes = [c_p, c_p, c_p, C.c_int, C.c_int, C.c_double, C.c_double, c_p, c_p, c_p, c_p, c_p]
+lib.mpx_gae_workspace_bytes.argtypes = [c_i, c_i]
+lib.mpx_gae.argtypes = [c_p, c_p, c_p, c_i, c_i, C.c_double, C.c_double, c_p, c_p, c_p, c_p, c_p]
 lib.mpx_adv_normalize.argtypes = [c_p, c_ll, c_p, C.c_double, c_p]
-lib.mpx_hlgauss_value.argtypes = [c_p, c_ll, C.c_int, c_p, c_p, c_p]
+lib.mpx_hlgauss_value.argtypes = [c_p, c_ll, c_i, c_p, c_p, c_p]
 lib.mpx_hlgauss_loss_workspace_bytes.restype = C.c_size_t
 lib.mpx_hlgauss_loss_workspace_bytes.argtypes = [c_ll]
-lib.mpx_hlgauss_loss.argtypes = [c_p, c_p, c_ll, C.c_int, c_p, C.c_float, C.c_float, C.c_float, C.c_float,
-                                 c_p, c_p, c_p, c_p]
-for _name in ("mpx_linear", "mpx_linear_wgrad", "mpx_qkv_rope", "mpx_glu_up", "mpx_attn_decode"):
+lib.mpx_hlgauss_loss.argtypes = [c_p, c_p, c_ll, c_i, c_p, c_f, c_f, c_f, c_f, c_p, c_p, c_p, c_i, c_p, c_p]
+for _name in ("mpx_linear", "mpx_linear_wgrad", "mpx_qkv_rope", "mpx_glu_up", "mpx_attn_decode",
+              "mpx_attn_train_fwd", "mpx_attn_train_bwd"):
     getattr(lib, _name).argtypes = [c_p, c_p]
-lib.mpx_debug_set.argtypes = [C.c_int, C.c_int]
-lib.mpx_rmsnorm_fwd.argtypes = [c_p, c_p, C.c_float, c_p, c_ll, C.c_int, c_p]
-lib.mpx_rmsnorm_bwd.argtypes = [c_p, c_p, c_p, C.c_float, c_p, c_p, c_p, c_ll, C.c_int, c_p]
-lib.mpx_glu_bwd.argtypes = [c_p, c_p, c_p, c_p, c_ll, C.c_int, c_p]
+lib.mpx_linear_f32w.argtypes = [c_p, c_ll, c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_p]
+lib.mpx_rmsnorm_fwd.argtypes = [c_p, c_p, c_f, c_p, c_ll, c_i, c_p]
+lib.mpx_rmsnorm_bwd.argtypes = [c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_ll, c_i, c_p]
+lib.mpx_glu_bwd.argtypes = [c_p, c_p, c_p, c_p, c_ll, c_i, c_p]
 lib.mpx_gelu_bwd.argtypes = [c_p, c_p, c_p, c_ll, c_p]
-lib.mpx_rope.argtypes = [c_p, c_ll, c_p, C.c_int, c_p, c_ll, C.c_int, C.c_int, C.c_int, c_p]
-lib.mpx_colsum.argtypes = [c_p, c_ll, c_ll, C.c_int, c_p, c_p]
+lib.mpx_rope.argtypes = [c_p, c_ll, c_p, c_i, c_p, c_ll, c_i, c_i, c_i, c_p]
+lib.mpx_colsum.argtypes = [c_p, c_ll, c_ll, c_i, c_p, c_p]
 lib.mpx_add_bf16.argtypes = [c_p, c_p, c_p, c_ll, c_p]
+lib.mpx_embed_combine.argtypes = [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_p, c_ll, c_i, c_p]
+lib.mpx_embed_bwd.argtypes = [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_ll, c_i, c_p]
+lib.mpx_policy_logits.argtypes = [c_p, c_p, c_p, c_p, c_ll, c_i, c_i, c_p]
+lib.mpx_policy_sample.argtypes = [c_p, c_p, c_p, c_p, c_ll, c_i, c_p]
+lib.mpx_gumbel_noise.argtypes = [c_p, c_ll, C.c_ulonglong, C.c_ulonglong, c_p, c_p]
+lib.mpx_ppo_policy_loss_workspace_bytes.restype = C.c_size_t
+lib.mpx_ppo_policy_loss_workspace_bytes.argtypes = [c_ll]
+lib.mpx_ppo_policy_loss.argtypes = [c_p, c_p, c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_p, c_ll, c_i, c_p]
+lib.mpx_policy_head_bwd.argtypes = [c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_i, c_i, c_p]
+lib.mpx_obs_onehot_im2col.argtypes = [c_p, c_p, c_ll, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_p]
+lib.mpx_im2col.argtypes = [c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]
+lib.mpx_col2im.argtypes = [c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]
+lib.mpx_adamw_workspace_bytes.restype = C.c_size_t
+lib.mpx_adamw_workspace_bytes.argtypes = [c_ll]
+lib.mpx_adamw_step.argtypes = [c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_p,
+                               c_p, c_p]
+lib.mpx_prep_weights.argtypes = [c_p, c_i, c_p]
+lib.mpx_transpose_tb.argtypes = [c_p, c_p, c_p, c_i, c_i, c_i, c_p]
 
 
 def check(rc: int, what: str = "") -> None:

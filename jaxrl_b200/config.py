@@ -123,7 +123,7 @@ def from_reference_json(path: str, *, obs_components: Tuple[int, ...] = (5, 5), 
 _BASE = ModelConfig()
 NAMED = {
     # tiny find_return-shaped plumbing config (config/test.json is stale)
-    "test": RunConfig("test", replace(_BASE, max_seq_length=32, obs_shape=(11, 11, 2)), num_agents=16,
+    "test": RunConfig("test", replace(_BASE, max_seq_length=64, obs_shape=(11, 11, 2)), num_agents=16,
                       ppo=PPOConfig(minibatch_count=2)),
     "return_2_layers": RunConfig("return_2_layers", _BASE),
     "return_8_layers": RunConfig("return_8_layers", replace(_BASE, num_layers=8)),

@@ -1,0 +1,146 @@
+// Observation-encoder support: GridCnnObsEncoder (reference mapox_trainer/model/observation.py:36-96) is
+// lowered to the tcgen05 GEMM (mpx_linear / mpx_linear_wgrad) through im2col gathers:
+//   conv1: one-hot(obs) (*) W1  ==  onehot_im2col(obs) [M*OH*OW, kh*kw*C (padded to 8)] . W1^T
+//   conv2: im2col(a1) . W2^T ;  conv3 (3x3 VALID on a 3x3 map) is a plain Linear over the flattened map.
+// The one-hot tensor of mapox.concat_one_hot (observation.py:85-87) is never materialised on its own.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mpx {
+
+struct OneHotSpec {
+  int K;            // observation components per cell
+  int offs[5];      // prefix sums of the per-component one-hot sizes; offs[K] = C (total channels)
+};
+
+// out (M*OH*OW, KP) bf16, KP = round_up(kh*kw*C, 8); one thread per 8 output columns (one 16-byte store).
+__global__ void onehot_im2col_kernel(const uint8_t* __restrict__ obs, __nv_bfloat16* __restrict__ out, long long M,
+                                     int IH, int IW, OneHotSpec spec, int kh, int kw, int sh, int sw, int OH, int OW,
+                                     int KP) {
+  const int C = spec.offs[spec.K];
+  const int pieces = KP / 8;
+  const long long total = M * OH * OW * pieces;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int piece = (int)(i % pieces);
+    long long row = i / pieces;
+    const int ox = (int)(row % OW);
+    const int oy = (int)((row / OW) % OH);
+    const long long m = row / ((long long)OW * OH);
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int col = piece * 8 + e;
+      if (col < kh * kw * C) {
+        const int tap = col / C, ch = col % C;
+        const int ky = tap / kw, kx = tap % kw;
+        int kcomp = 0;
+        while (kcomp + 1 < spec.K && ch >= spec.offs[kcomp + 1]) ++kcomp;
+        const int val = obs[((m * IH + (oy * sh + ky)) * IW + (ox * sw + kx)) * spec.K + kcomp];
+        if (val == ch - spec.offs[kcomp]) w[e >> 1] |= (e & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0
+      }
+    }
+    *reinterpret_cast<uint4*>(out + row * KP + piece * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// NHWC im2col: a (M, IH, IW, C) bf16 -> x (M*OH*OW, kh*kw*C), C % 8 == 0; one thread per 16-byte piece.
+__global__ void im2col_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ x, long long M, int IH,
+                              int IW, int C, int kh, int kw, int sh, int sw, int OH, int OW) {
+  const int cp = C / 8;
+  const long long total = M * OH * OW * kh * kw * cp;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int c8 = (int)(i % cp);
+    long long r = i / cp;
+    const int tap = (int)(r % (kh * kw));
+    r /= (kh * kw);
+    const int ox = (int)(r % OW);
+    const int oy = (int)((r / OW) % OH);
+    const long long m = r / ((long long)OW * OH);
+    const int ky = tap / kw, kx = tap % kw;
+    const uint4 v = *reinterpret_cast<const uint4*>(a + ((m * IH + oy * sh + ky) * IW + ox * sw + kx) * C + c8 * 8);
+    *reinterpret_cast<uint4*>(x + ((m * OH + oy) * OW + ox) * (long long)(kh * kw * C) + tap * C + c8 * 8) = v;
+  }
+}
+
+// Transpose of im2col: da (M, IH, IW, C) = sum of the dx patches covering each cell (fp32 sum, bf16 store).
+__global__ void col2im_kernel(const __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ da, long long M, int IH,
+                              int IW, int C, int kh, int kw, int sh, int sw, int OH, int OW) {
+  const int cp = C / 8;
+  const long long total = M * IH * IW * cp;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int c8 = (int)(i % cp);
+    long long r = i / cp;
+    const int ix = (int)(r % IW);
+    const int iy = (int)((r / IW) % IH);
+    const long long m = r / ((long long)IW * IH);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int ky = 0; ky < kh; ++ky) {
+      const int ny = iy - ky;
+      if (ny < 0 || ny % sh != 0 || ny / sh >= OH) continue;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int nx = ix - kx;
+        if (nx < 0 || nx % sw != 0 || nx / sw >= OW) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(
+            dx + ((m * OH + ny / sh) * OW + nx / sw) * (long long)(kh * kw * C) + (ky * kw + kx) * C + c8 * 8);
+        acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+        acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+      }
+    }
+    *reinterpret_cast<uint4*>(da + ((m * IH + iy) * IW + ix) * C + c8 * 8) =
+        make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
+                   pack_bf16(acc[6], acc[7]));
+  }
+}
+
+static int cv_grid(long long n) {
+  long long g = (n + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace mpx
+
+using namespace mpx;
+
+extern "C" int mpx_obs_onehot_im2col(const uint8_t* obs, mpx_bf16* out, long long M, int IH, int IW, int K,
+                                     const int* onehot_sizes, int kh, int kw, int sh, int sw, int KP,
+                                     mpx_stream_t stream) {
+  MPX_REQUIRE(obs && out && onehot_sizes && M > 0, "mpx_obs_onehot_im2col: bad arguments");
+  MPX_REQUIRE(K >= 1 && K <= 4, "mpx_obs_onehot_im2col: K=%d components unsupported (1..4)", K);
+  OneHotSpec spec;
+  spec.K = K;
+  spec.offs[0] = 0;
+  for (int i = 0; i < K; ++i) spec.offs[i + 1] = spec.offs[i] + onehot_sizes[i];
+  const int C = spec.offs[K];
+  MPX_REQUIRE(KP % 8 == 0 && KP >= kh * kw * C, "mpx_obs_onehot_im2col: KP=%d must be a multiple of 8 >= %d", KP, kh * kw * C);
+  MPX_REQUIRE(IH >= kh && IW >= kw && sh > 0 && sw > 0, "mpx_obs_onehot_im2col: bad geometry");
+  const int OH = (IH - kh) / sh + 1, OW = (IW - kw) / sw + 1;
+  onehot_im2col_kernel<<<cv_grid(M * OH * OW * (KP / 8)), 256, 0, (cudaStream_t)stream>>>(
+      obs, reinterpret_cast<__nv_bfloat16*>(out), M, IH, IW, spec, kh, kw, sh, sw, OH, OW, KP);
+  return check_launch("mpx_obs_onehot_im2col");
+}
+
+extern "C" int mpx_im2col(const mpx_bf16* a, mpx_bf16* x, long long M, int IH, int IW, int C, int kh, int kw, int sh,
+                          int sw, mpx_stream_t stream) {
+  MPX_REQUIRE(a && x && M > 0 && C % 8 == 0 && IH >= kh && IW >= kw && sh > 0 && sw > 0, "mpx_im2col: bad arguments");
+  const int OH = (IH - kh) / sh + 1, OW = (IW - kw) / sw + 1;
+  im2col_kernel<<<cv_grid(M * OH * OW * kh * kw * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<__nv_bfloat16*>(x), M, IH, IW, C, kh, kw, sh, sw, OH, OW);
+  return check_launch("mpx_im2col");
+}
+
+extern "C" int mpx_col2im(const mpx_bf16* dx, mpx_bf16* da, long long M, int IH, int IW, int C, int kh, int kw, int sh,
+                          int sw, mpx_stream_t stream) {
+  MPX_REQUIRE(dx && da && M > 0 && C % 8 == 0 && IH >= kh && IW >= kw && sh > 0 && sw > 0, "mpx_col2im: bad arguments");
+  const int OH = (IH - kh) / sh + 1, OW = (IW - kw) / sw + 1;
+  col2im_kernel<<<cv_grid(M * IH * IW * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(da), M, IH, IW, C, kh, kw, sh, sw, OH, OW);
+  return check_launch("mpx_col2im");
+}

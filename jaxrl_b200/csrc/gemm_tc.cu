@@ -28,7 +28,7 @@ constexpr int STAGES = 4;
 constexpr int GEMM_THREADS = 192;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 
-enum { EPI_STORE = 0, EPI_QKV = 1, EPI_GLU = 2 };
+enum { EPI_STORE = 0, EPI_QKV = 1, EPI_GLU = 2, EPI_PAIRSUM = 3 };
 
 struct GemmParams {
   int M, N, K;
@@ -41,6 +41,8 @@ struct GemmParams {
   float* y_f32;
   long long ldy32;
   int act;
+  __nv_bfloat16* y_pre;      // optional: bf16 pre-activation (after bias), same pitch as y
+  const float* bias_f32;     // EPI_PAIRSUM
   // EPI_QKV
   const int32_t* pos;
   int pos_len;
@@ -48,7 +50,7 @@ struct GemmParams {
   __nv_bfloat16* q;
   __nv_bfloat16* k;
   __nv_bfloat16* v;
-  long long k_row_stride, v_row_stride;
+  long long q_row_stride, k_row_stride, v_row_stride;
   int cache_S, Nq, Nkv;
   // EPI_GLU
   __nv_bfloat16* h;
@@ -118,6 +120,11 @@ __device__ __forceinline__ void epi_store(const GemmParams& p, int row, int col0
     for (int i = 0; i < 32; ++i)
       if (col0 + i < p.N) f[i] = bf16_round(f[i] + __bfloat162float(p.bias[col0 + i]));
   }
+  if (p.y_pre) {
+    __nv_bfloat16* dp = p.y_pre + (long long)row * p.ldy + col0;
+    if (full && ((p.ldy & 7) == 0)) store_bf16x32(dp, f);
+    else for (int i = 0; i < 32 && col0 + i < p.N; ++i) dp[i] = __float2bfloat16_rn(f[i]);
+  }
   if (p.act == 1) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = bf16_round(gelu_tanh(f[i]));
@@ -162,7 +169,7 @@ __device__ __forceinline__ void epi_qkv(const GemmParams& p, int row, int col0, 
     for (int i = 0; i < 32; ++i) f[i] = o[i];
   }
   if (head < p.Nq) {
-    dst = p.q + (long long)row * (p.Nq * 32) + head * 32;
+    dst = p.q + (long long)row * p.q_row_stride + head * 32;
   } else {
     long long slot_off = 0;
     if (p.cache_S > 0) {
@@ -192,6 +199,20 @@ __device__ __forceinline__ void epi_glu(const GemmParams& p, int row, int hcol0,
   if (p.g_save) store_bf16x32(p.g_save + o, gf);
 }
 
+// fp32-weight Linear emulated with a bf16 hi/lo split of the weight: out[j] = acc[j] + acc[64 + j] + bias[j].
+__device__ __forceinline__ void epi_pairsum(const GemmParams& p, int row, int col0, const uint32_t (&hi)[32],
+                                            const uint32_t (&lo)[32]) {
+  if (row >= p.M) return;
+  float* d = p.y_f32 + (long long)row * p.ldy32 + col0;
+  for (int i = 0; i < 32; ++i) {
+    if (col0 + i < p.N) {
+      float v = __uint_as_float(hi[i]) + __uint_as_float(lo[i]);
+      if (p.bias_f32) v += p.bias_f32[col0 + i];
+      d[i] = v;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -211,7 +232,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
   constexpr uint32_t TMEM_COLS = tmem_cols_for(BLOCK_N);
 
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int n_tiles = (EPI == EPI_PAIRSUM) ? 1 : (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
 
@@ -316,6 +337,15 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
           tmem_ld_32x32(t_row + 128 + c, g);
           tmem_ld_wait();
           epi_glu(p, row, n_blk * 128 + c, u, g);
+        }
+      } else if constexpr (EPI == EPI_PAIRSUM) {
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t hi[32], lo[32];
+          tmem_ld_32x32(t_row + c, hi);
+          tmem_ld_32x32(t_row + 64 + c, lo);
+          tmem_ld_wait();
+          epi_pairsum(p, row, c, hi, lo);
         }
       } else {
 #pragma unroll 1
@@ -503,7 +533,7 @@ static int launch_tn(const GemmParams& p, const void* a, long long lda, const vo
   CUtensorMap tm_a, tm_b;
   int rc = make_tmap_bf16_2d(&tm_a, a, p.M, p.K, lda, BLOCK_K, BLOCK_M);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tm_b, bt, p.N, p.K, ldb, BLOCK_K, BLOCK_N);
+  rc = make_tmap_bf16_2d(&tm_b, bt, EPI == EPI_PAIRSUM ? 128 : p.N, p.K, ldb, BLOCK_K, BLOCK_N);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
@@ -515,7 +545,7 @@ static int launch_tn(const GemmParams& p, const void* a, long long lda, const vo
     }
     attr_set = true;
   }
-  const int tiles = ceil_div(p.M, BLOCK_M) * ceil_div(p.N, BLOCK_N);
+  const int tiles = ceil_div(p.M, BLOCK_M) * (EPI == EPI_PAIRSUM ? 1 : ceil_div(p.N, BLOCK_N));
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_tn_kernel<BLOCK_N, EPI><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(p, tm_a, tm_b);
   return check_launch("gemm_tn_kernel");
@@ -569,6 +599,8 @@ extern "C" int mpx_linear(const mpx_linear_args* a, mpx_stream_t stream) {
   p.y_f32 = a->y_f32;
   p.ldy32 = a->ldy32;
   p.act = a->act;
+  p.y_pre = reinterpret_cast<__nv_bfloat16*>(a->y_pre);
+  MPX_REQUIRE(!a->y_pre || a->y, "mpx_linear: y_pre requires y");
   cudaStream_t s = (cudaStream_t)stream;
   if (a->N <= 64) return launch_tn<64, EPI_STORE>(p, a->x, a->ldx, a->wt, a->ldw, s);
   if (a->N <= 128) return launch_tn<128, EPI_STORE>(p, a->x, a->ldx, a->wt, a->ldw, s);
@@ -581,7 +613,7 @@ extern "C" int mpx_linear(const mpx_linear_args* a, mpx_stream_t stream) {
 extern "C" int mpx_linear_wgrad(const mpx_wgrad_args* a, mpx_stream_t stream) {
   MPX_REQUIRE(a && a->x && a->dy && a->dw, "mpx_linear_wgrad: null pointer");
   MPX_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "mpx_linear_wgrad: empty shape");
-  MPX_REQUIRE(a->K % 8 == 0 && a->N % 8 == 0, "mpx_linear_wgrad: K and N must be multiples of 8");
+  MPX_REQUIRE(a->ldx % 8 == 0 && a->ldy % 8 == 0, "mpx_linear_wgrad: ldx and ldy must be multiples of 8");
   cudaStream_t s = (cudaStream_t)stream;
   if (a->N <= 64) return launch_wgrad<64>(a, s);
   if (a->N <= 128) return launch_wgrad<128>(a, s);
@@ -600,9 +632,10 @@ extern "C" int mpx_qkv_rope(const mpx_qkv_rope_args* a, mpx_stream_t stream) {
   p.q = reinterpret_cast<__nv_bfloat16*>(a->q);
   p.k = reinterpret_cast<__nv_bfloat16*>(a->k);
   p.v = reinterpret_cast<__nv_bfloat16*>(a->v);
-  p.k_row_stride = a->k_row_stride; p.v_row_stride = a->v_row_stride;
+  p.q_row_stride = a->q_row_stride; p.k_row_stride = a->k_row_stride; p.v_row_stride = a->v_row_stride;
   p.cache_S = a->cache_S; p.Nq = a->Nq; p.Nkv = a->Nkv;
-  MPX_REQUIRE((a->k_row_stride % 8) == 0 && (a->v_row_stride % 8) == 0, "mpx_qkv_rope: k/v row strides must be multiples of 8");
+  MPX_REQUIRE((a->q_row_stride % 8) == 0 && (a->k_row_stride % 8) == 0 && (a->v_row_stride % 8) == 0,
+              "mpx_qkv_rope: q/k/v row strides must be multiples of 8");
   cudaStream_t s = (cudaStream_t)stream;
   if (N <= 64) return launch_tn<64, EPI_QKV>(p, a->x, a->ldx, a->wt_qkv, a->H, s);
   if (N <= 128) return launch_tn<128, EPI_QKV>(p, a->x, a->ldx, a->wt_qkv, a->H, s);
@@ -619,4 +652,14 @@ extern "C" int mpx_glu_up(const mpx_glu_up_args* a, mpx_stream_t stream) {
   p.u_save = reinterpret_cast<__nv_bfloat16*>(a->u_save);
   p.g_save = reinterpret_cast<__nv_bfloat16*>(a->g_save);
   return launch_tn<256, EPI_GLU>(p, a->x, a->ldx, a->wt_ug, a->K, (cudaStream_t)stream);
+}
+
+extern "C" int mpx_linear_f32w(const mpx_bf16* x, long long ldx, const mpx_bf16* wt_hilo, const float* bias, float* y,
+                               long long ldy, int M, int N, int K, mpx_stream_t stream) {
+  MPX_REQUIRE(x && wt_hilo && y, "mpx_linear_f32w: null pointer");
+  MPX_REQUIRE(M > 0 && K > 0 && N > 0 && N <= 64, "mpx_linear_f32w: N=%d must be in [1,64]", N);
+  GemmParams p = {};
+  p.M = M; p.N = N; p.K = K;
+  p.y_f32 = y; p.ldy32 = ldy; p.bias_f32 = bias;
+  return launch_tn<128, EPI_PAIRSUM>(p, x, ldx, wt_hilo, K, (cudaStream_t)stream);
 }

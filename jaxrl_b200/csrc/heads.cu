@@ -1,0 +1,384 @@
+// Policy / embedding glue around the trunk (reference mapox_trainer/model/network.py:300-343, train.py:97-100,
+// :193-212).  All HBM-bound SIMT kernels:
+//   embed_combine   x = obs_emb + reward_encoder(reward) + action_embedder.encode(last_action) [+ task]  (:303-309)
+//   embed_bwd       its transpose (reward kernel/bias, action/task table gradients)
+//   policy_logits   tied logits f32(x) . table^T, action mask -> finfo(f32).min                          (:323-331)
+//   policy_sample   Gumbel arg-max + log-prob of the sample (distrax.Categorical, train.py:97-98)
+//   gumbel_noise    counter-based (Philox-4x32-10) Gumbel(0,1) noise
+//   ppo_policy_loss clipped-ratio actor loss + entropy bonus and d/dlogits                               (train.py:193-212)
+//   policy_head_bwd cotangent of x and of the tied table from dlogits
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mpx {
+
+constexpr int HD_WARPS = 8;
+constexpr int MAX_A = 32;
+
+// ------------------------------------------------------------------------------------------------ embed
+__global__ void __launch_bounds__(256) embed_combine_kernel(
+    const __nv_bfloat16* __restrict__ obs_emb, const float* __restrict__ reward, const int32_t* __restrict__ last_action,
+    const int32_t* __restrict__ task_ids, const float* __restrict__ w_r, const float* __restrict__ b_r,
+    const float* __restrict__ a_table, int A, const float* __restrict__ t_table, int n_tasks,
+    __nv_bfloat16* __restrict__ x, long long M, int H) {
+  const float sq = bf16_round(sqrtf((float)H));
+  const long long total = M * H;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const long long m = i / H;
+    const int h = (int)(i % H);
+    // reward_encoder: nnx.Linear(1,H) in bf16: bf16(bf16(r) * bf16(w)) then + bf16(b) -> bf16
+    float re = bf16_round(bf16_round(reward[m]) * bf16_round(w_r[h]));
+    re = bf16_round(re + bf16_round(b_r[h]));
+    // Embedder.encode: jnp.take(mode=fill) wraps negatives once, zero-fills out of range; bf16(row) * bf16(sqrt(H))
+    int a = last_action[m];
+    if (a < 0) a += A;
+    float ae = (a >= 0 && a < A) ? bf16_round(a_table[(long long)a * H + h]) : 0.f;
+    ae = bf16_round(ae * sq);
+    float v = bf16_round(__bfloat162float(obs_emb[i]) + re);
+    v = bf16_round(v + ae);
+    if (task_ids && t_table) {
+      int tk = task_ids[m];
+      if (tk < 0) tk += n_tasks;
+      float te = (tk >= 0 && tk < n_tasks) ? bf16_round(t_table[(long long)tk * H + h]) : 0.f;
+      v = bf16_round(v + bf16_round(te * sq));
+    }
+    x[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// Transpose of embed_combine.  Each block reduces `rows_per_block` token rows; thread = feature column.
+// d_wr[h] += sum bf16(r) * dx ; d_br[h] += sum dx ; d_a_table[a][h] += sqrt(H) * dx ; same for tasks.
+__global__ void embed_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const float* __restrict__ reward,
+                                 const int32_t* __restrict__ last_action, const int32_t* __restrict__ task_ids, int A,
+                                 int n_tasks, float* __restrict__ d_wr, float* __restrict__ d_br,
+                                 float* __restrict__ d_a_table, float* __restrict__ d_t_table, long long M, int H,
+                                 int rows_per_block) {
+  extern __shared__ float s_tab[];   // [A + n_tasks][H]
+  const int ntab = A + (d_t_table ? n_tasks : 0);
+  for (int i = threadIdx.x; i < ntab * H; i += blockDim.x) s_tab[i] = 0.f;
+  __syncthreads();
+  const float sq = bf16_round(sqrtf((float)H));
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(M, r0 + (long long)rows_per_block);
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float awr = 0.f, abr = 0.f;
+    for (long long m = r0; m < r1; ++m) {
+      const float g = __bfloat162float(dx[m * H + h]);
+      awr += bf16_round(reward[m]) * g;
+      abr += g;
+      int a = last_action[m];
+      if (a < 0) a += A;
+      if (a >= 0 && a < A) s_tab[a * H + h] += g * sq;     // column h is owned by this thread: no race
+      if (d_t_table) {
+        int tk = task_ids[m];
+        if (tk < 0) tk += n_tasks;
+        if (tk >= 0 && tk < n_tasks) s_tab[(A + tk) * H + h] += g * sq;
+      }
+    }
+    atomicAdd(d_wr + h, awr);
+    atomicAdd(d_br + h, abr);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < A * H; i += blockDim.x)
+    if (s_tab[i] != 0.f) atomicAdd(d_a_table + i, s_tab[i]);
+  if (d_t_table)
+    for (int i = threadIdx.x; i < n_tasks * H; i += blockDim.x)
+      if (s_tab[A * H + i] != 0.f) atomicAdd(d_t_table + i, s_tab[A * H + i]);
+}
+
+// ------------------------------------------------------------------------------------------------ policy logits
+// One warp per token: logits[a] = sum_h f32(x[h]) * table[a][h]; masked entries -> finfo(f32).min.
+__global__ void __launch_bounds__(HD_WARPS * 32) policy_logits_kernel(
+    const __nv_bfloat16* __restrict__ x, const float* __restrict__ table, const uint8_t* __restrict__ mask,
+    float* __restrict__ logits, long long M, int H, int A) {
+  extern __shared__ float s_table[];   // [A][H]
+  for (int i = threadIdx.x; i < A * H; i += blockDim.x) s_table[i] = table[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  long long row = (long long)blockIdx.x * HD_WARPS + (threadIdx.x >> 5);
+  const long long stride = (long long)gridDim.x * HD_WARPS;
+  for (; row < M; row += stride) {
+    float my = 0.f;
+    for (int a = 0; a < A; ++a) {
+      float acc = 0.f;
+      for (int h = lane; h < H; h += 32) acc = fmaf(__bfloat162float(x[row * H + h]), s_table[a * H + h], acc);
+      acc = warp_sum(acc);
+      if (lane == a) my = acc;
+    }
+    if (lane < A) {
+      if (mask && !mask[row * A + lane]) my = -3.4028234663852886e38f;
+      logits[row * A + lane] = my;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ sampling
+// action = argmax_a(logits + gumbel) (first maximum, jnp.argmax), log_prob = log_softmax(logits)[action].
+__global__ void policy_sample_kernel(const float* __restrict__ logits, const float* __restrict__ gumbel,
+                                     int32_t* __restrict__ action, float* __restrict__ log_prob, long long M, int A) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float* l = logits + m * A;
+  const float* gn = gumbel + m * A;
+  float best = -INFINITY, mx = -INFINITY;
+  int bi = 0;
+  for (int a = 0; a < A; ++a) {
+    const float v = l[a] + gn[a];
+    if (v > best) { best = v; bi = a; }
+    mx = fmaxf(mx, l[a]);
+  }
+  float s = 0.f;
+  for (int a = 0; a < A; ++a) s += expf(l[a] - mx);
+  action[m] = bi;
+  log_prob[m] = (l[bi] - mx) - logf(s);
+}
+
+// Philox-4x32-10 counter RNG -> Gumbel(0,1) = -log(-log(u)).  counter = (element index, stream id), key = seed.
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+__global__ void gumbel_noise_kernel(float* __restrict__ out, long long n, unsigned long long seed,
+                                    unsigned long long stream_id, const unsigned long long* __restrict__ stream_off) {
+  if (stream_off) stream_id += stream_off[0];
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i * 4 < n; i += stride) {
+    uint32_t c[4] = {(uint32_t)i, (uint32_t)(i >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i * 4 + k < n) {
+        const float u = ((float)(c[k] >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1)
+        out[i * 4 + k] = -logf(-logf(u));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ PPO policy loss
+// Per token (train.py:193-212, distrax.Categorical log_prob / entropy):
+//   lp = log_softmax(logits); ratio = exp(lp[a] - old_lp); actor = -min(ratio*adv, clip(ratio,1-e,1+e)*adv)
+//   entropy_loss = -H = sum p*lp;  total policy part = mean(actor) + ent_coef * mean(entropy_loss)
+// dlogits = (1/M) * [ g * (onehot(a) - p) + ent_coef * p * (lp + H) ],  g = d actor / d lp[a]
+// partial sums (actor, entropy_loss) per block -> fixed-order finalize (deterministic).
+__global__ void __launch_bounds__(256) ppo_policy_loss_kernel(
+    const float* __restrict__ logits, const int32_t* __restrict__ actions, const float* __restrict__ old_lp,
+    const float* __restrict__ adv, float clip_eps, float ent_coef, const float* __restrict__ ent_coef_dev, float inv_m,
+    float* __restrict__ dlogits, double* __restrict__ partials, long long M, int A) {
+  __shared__ double s_a[256], s_e[256];
+  if (ent_coef_dev) ent_coef = ent_coef_dev[0];
+  double acc_a = 0.0, acc_e = 0.0;
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; m < M; m += stride) {
+    const float* l = logits + m * A;
+    float lp[MAX_A];
+    float mx = -INFINITY;
+    for (int a = 0; a < A; ++a) { lp[a] = l[a]; mx = fmaxf(mx, lp[a]); }
+    float s = 0.f;
+    for (int a = 0; a < A; ++a) s += expf(lp[a] - mx);
+    const float lse = logf(s);
+    float negH = 0.f;
+    for (int a = 0; a < A; ++a) {
+      lp[a] = (lp[a] - mx) - lse;
+      const float p = expf(lp[a]);
+      negH += (p > 0.f) ? p * lp[a] : 0.f;
+    }
+    const int act = actions[m];
+    const float ratio = expf(lp[act] - old_lp[m]);
+    const float ad = adv[m];
+    const float pg1 = ratio * ad;
+    const float rc = fminf(fmaxf(ratio, 1.0f - clip_eps), 1.0f + clip_eps);
+    const float pg2 = rc * ad;
+    acc_a += (double)(-fminf(pg1, pg2));
+    acc_e += (double)negH;
+    // d(-min(pg1,pg2)) / d lp[act]
+    const bool inside = (ratio > 1.0f - clip_eps) && (ratio < 1.0f + clip_eps);
+    float g;
+    if (pg1 < pg2) g = -pg1;                 // unclipped branch selected: d(ratio*adv)/dlp = ratio*adv
+    else if (pg1 > pg2) g = inside ? -pg1 : 0.f;
+    else g = inside ? -pg1 : -0.5f * pg1;    // tie: jnp.minimum splits the cotangent
+    if (dlogits) {
+      for (int a = 0; a < A; ++a) {
+        const float p = expf(lp[a]);
+        const float onehot = (a == act) ? 1.f : 0.f;
+        const float dent = (p > 0.f) ? p * (lp[a] - negH) : 0.f;   // d(sum p lp)/dz = p (lp + H), H = -negH
+        dlogits[m * A + a] = inv_m * (g * (onehot - p) + ent_coef * dent);
+      }
+    }
+  }
+  s_a[threadIdx.x] = acc_a;
+  s_e[threadIdx.x] = acc_e;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      s_a[threadIdx.x] += s_a[threadIdx.x + o];
+      s_e[threadIdx.x] += s_e[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x] = s_a[0];
+    partials[2 * blockIdx.x + 1] = s_e[0];
+  }
+}
+__global__ void ppo_loss_finalize_kernel(const double* __restrict__ partials, int n, double inv_m,
+                                         float* __restrict__ out /* [2]: actor_loss, entropy_loss */) {
+  __shared__ double s0[256], s1[256];
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) { a += partials[2 * i]; b += partials[2 * i + 1]; }
+  s0[threadIdx.x] = a;
+  s1[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { s0[threadIdx.x] += s0[threadIdx.x + o]; s1[threadIdx.x] += s1[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = (float)(s0[0] * inv_m); out[1] = (float)(s1[0] * inv_m); }
+}
+
+// ------------------------------------------------------------------------------------------------ policy head bwd
+// dx[m][h] = bf16( sum_a dlogits[m][a] * table[a][h] ) (+ dx_other in bf16 if given) ;
+// dtable[a][h] += sum_m dlogits[m][a] * f32(x[m][h]).   Masked logits are constants: dlogits is zero there.
+__global__ void policy_head_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ x,
+                                       const float* __restrict__ table, const __nv_bfloat16* __restrict__ dx_other,
+                                       __nv_bfloat16* __restrict__ dx, float* __restrict__ dtable, long long M, int H,
+                                       int A, int rows_per_block) {
+  extern __shared__ float s_buf[];   // [A][H] table, then per-row dlogits [A]
+  float* s_table = s_buf;
+  float* s_dl = s_buf + A * H;
+  for (int i = threadIdx.x; i < A * H; i += blockDim.x) s_table[i] = table[i];
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(M, r0 + (long long)rows_per_block);
+  float dt[MAX_A];
+#pragma unroll
+  for (int a = 0; a < MAX_A; ++a) dt[a] = 0.f;
+  const int h = threadIdx.x;    // blockDim.x == H
+  for (long long m = r0; m < r1; ++m) {
+    __syncthreads();
+    if (threadIdx.x < A) s_dl[threadIdx.x] = dlogits[m * A + threadIdx.x];
+    __syncthreads();
+    const float xv = __bfloat162float(x[m * H + h]);
+    float acc = 0.f;
+#pragma unroll 8
+    for (int a = 0; a < A; ++a) {
+      acc = fmaf(s_dl[a], s_table[a * H + h], acc);
+      dt[a] = fmaf(s_dl[a], xv, dt[a]);
+    }
+    float o = bf16_round(acc);
+    if (dx_other) o += __bfloat162float(dx_other[m * H + h]);
+    dx[m * H + h] = __float2bfloat16_rn(o);
+  }
+  for (int a = 0; a < A; ++a) atomicAdd(dtable + a * H + h, dt[a]);
+}
+
+}  // namespace mpx
+
+using namespace mpx;
+
+static int grid_for(long long n, int per_block, int waves = 16) {
+  long long g = (n + per_block - 1) / per_block;
+  const long long cap = (long long)num_sms() * waves;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+extern "C" int mpx_embed_combine(const mpx_bf16* obs_emb, const float* reward, const int32_t* last_action,
+                                 const int32_t* task_ids, const float* w_reward, const float* b_reward,
+                                 const float* action_table, int A, const float* task_table, int n_tasks, mpx_bf16* x,
+                                 long long M, int H, mpx_stream_t stream) {
+  MPX_REQUIRE(obs_emb && reward && last_action && w_reward && b_reward && action_table && x && M > 0 && H > 0 && A > 0,
+              "mpx_embed_combine: bad arguments");
+  embed_combine_kernel<<<grid_for(M * H, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(obs_emb), reward, last_action, task_ids, w_reward, b_reward, action_table,
+      A, task_table, n_tasks, reinterpret_cast<__nv_bfloat16*>(x), M, H);
+  return check_launch("mpx_embed_combine");
+}
+
+extern "C" int mpx_embed_bwd(const mpx_bf16* dx, const float* reward, const int32_t* last_action,
+                             const int32_t* task_ids, int A, int n_tasks, float* d_w_reward, float* d_b_reward,
+                             float* d_action_table, float* d_task_table, long long M, int H, mpx_stream_t stream) {
+  MPX_REQUIRE(dx && reward && last_action && d_w_reward && d_b_reward && d_action_table && M > 0 && H > 0 && A > 0,
+              "mpx_embed_bwd: bad arguments");
+  MPX_REQUIRE(!d_task_table || task_ids, "mpx_embed_bwd: task table gradient requested without task ids");
+  int rows = (int)((M + (long long)num_sms() * 2 - 1) / ((long long)num_sms() * 2));
+  if (rows < 64) rows = 64;
+  const int grid = (int)((M + rows - 1) / rows);
+  const size_t smem = (size_t)(A + (d_task_table ? n_tasks : 0)) * H * sizeof(float);
+  MPX_REQUIRE(smem <= 48 * 1024, "mpx_embed_bwd: tables too large for shared memory (%zu B)", smem);
+  embed_bwd_kernel<<<grid, H < 256 ? 128 : 256, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dx), reward, last_action, task_ids, A, n_tasks, d_w_reward, d_b_reward,
+      d_action_table, d_task_table, M, H, rows);
+  return check_launch("mpx_embed_bwd");
+}
+
+extern "C" int mpx_policy_logits(const mpx_bf16* x, const float* table, const uint8_t* action_mask, float* logits,
+                                 long long M, int H, int A, mpx_stream_t stream) {
+  MPX_REQUIRE(x && table && logits && M > 0 && H > 0, "mpx_policy_logits: bad arguments");
+  MPX_REQUIRE(A > 0 && A <= MAX_A, "mpx_policy_logits: A=%d not in [1,%d]", A, MAX_A);
+  const size_t smem = (size_t)A * H * sizeof(float);
+  MPX_REQUIRE(smem <= 48 * 1024, "mpx_policy_logits: table too large for shared memory");
+  policy_logits_kernel<<<grid_for(M, HD_WARPS, 8), HD_WARPS * 32, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), table, action_mask, logits, M, H, A);
+  return check_launch("mpx_policy_logits");
+}
+
+extern "C" int mpx_policy_sample(const float* logits, const float* gumbel, int32_t* action, float* log_prob,
+                                 long long M, int A, mpx_stream_t stream) {
+  MPX_REQUIRE(logits && gumbel && action && log_prob && M > 0 && A > 0, "mpx_policy_sample: bad arguments");
+  policy_sample_kernel<<<(int)((M + 127) / 128), 128, 0, (cudaStream_t)stream>>>(logits, gumbel, action, log_prob, M, A);
+  return check_launch("mpx_policy_sample");
+}
+
+extern "C" int mpx_gumbel_noise(float* out, long long n, unsigned long long seed, unsigned long long stream_id,
+                                const unsigned long long* stream_offset, mpx_stream_t stream) {
+  MPX_REQUIRE(out && n > 0, "mpx_gumbel_noise: bad arguments");
+  gumbel_noise_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, stream_id,
+                                                                                    stream_offset);
+  return check_launch("mpx_gumbel_noise");
+}
+
+extern "C" size_t mpx_ppo_policy_loss_workspace_bytes(long long M) {
+  return (size_t)grid_for(M > 0 ? M : 1, 256, 8) * 2 * sizeof(double);
+}
+
+extern "C" int mpx_ppo_policy_loss(const float* logits, const int32_t* actions, const float* old_log_prob,
+                                   const float* advantages, float clip_eps, float entropy_coef,
+                                   const float* entropy_coef_dev, float* losses, float* dlogits, void* workspace,
+                                   long long M, int A, mpx_stream_t stream) {
+  MPX_REQUIRE(logits && actions && old_log_prob && advantages && losses && workspace && M > 0,
+              "mpx_ppo_policy_loss: bad arguments");
+  MPX_REQUIRE(A > 0 && A <= MAX_A, "mpx_ppo_policy_loss: A=%d not in [1,%d]", A, MAX_A);
+  const int grid = grid_for(M, 256, 8);
+  double* partials = reinterpret_cast<double*>(workspace);
+  ppo_policy_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, actions, old_log_prob, advantages, clip_eps,
+                                                                 entropy_coef, entropy_coef_dev, 1.0f / (float)M,
+                                                                 dlogits, partials, M, A);
+  ppo_loss_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, grid, 1.0 / (double)M, losses);
+  return check_launch("mpx_ppo_policy_loss");
+}
+
+extern "C" int mpx_policy_head_bwd(const float* dlogits, const mpx_bf16* x, const float* table, const mpx_bf16* dx_other,
+                                   mpx_bf16* dx, float* dtable, long long M, int H, int A, mpx_stream_t stream) {
+  MPX_REQUIRE(dlogits && x && table && dx && dtable && M > 0, "mpx_policy_head_bwd: bad arguments");
+  MPX_REQUIRE(A > 0 && A <= MAX_A && H >= 32 && H <= 1024, "mpx_policy_head_bwd: unsupported A=%d / H=%d", A, H);
+  int rows = (int)((M + (long long)num_sms() * 4 - 1) / ((long long)num_sms() * 4));
+  if (rows < 16) rows = 16;
+  const int grid = (int)((M + rows - 1) / rows);
+  const size_t smem = ((size_t)A * H + A) * sizeof(float);
+  MPX_REQUIRE(smem <= 48 * 1024, "mpx_policy_head_bwd: table too large for shared memory");
+  policy_head_bwd_kernel<<<grid, H, smem, (cudaStream_t)stream>>>(
+      dlogits, reinterpret_cast<const __nv_bfloat16*>(x), table, reinterpret_cast<const __nv_bfloat16*>(dx_other),
+      reinterpret_cast<__nv_bfloat16*>(dx), dtable, M, H, A, rows);
+  return check_launch("mpx_policy_head_bwd");
+}

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(HLG_WARPS * 32) hlgauss_value_kernel(
 __global__ void __launch_bounds__(HLG_WARPS * 32) hlgauss_loss_kernel(
     const float* __restrict__ logits, const float* __restrict__ targets, long long n, int NL,
     const float* __restrict__ supports, float vmin, float vmax, float sigma, float gscale,
-    float* __restrict__ dlogits, double* __restrict__ partials) {
+    float* __restrict__ dlogits, __nv_bfloat16* __restrict__ dl_bf16, int ld_bf16, double* __restrict__ partials) {
   __shared__ float s_cdf[HLG_WARPS][HLG_MAX_PER_LANE * 32 + 1];
   __shared__ double s_part[HLG_WARPS];
   const int lane = threadIdx.x & 31;
@@ -105,7 +105,11 @@ __global__ void __launch_bounds__(HLG_WARPS * 32) hlgauss_loss_kernel(
       if (j < NL) {
         float lsm = (v[i] - m) - lse;
         l -= p[i] * lsm;
-        if (dlogits) dlogits[row * NL + j] = gscale * (expf(lsm) * psum - p[i]);
+        const float gr = gscale * (expf(lsm) * psum - p[i]);
+        if (dlogits) dlogits[row * NL + j] = gr;
+        if (dl_bf16) dl_bf16[row * ld_bf16 + j] = __float2bfloat16_rn(gr);
+      } else if (dl_bf16 && j < ld_bf16) {
+        dl_bf16[row * ld_bf16 + j] = __float2bfloat16_rn(0.f);
       }
     }
     l = warp_sum(l);
@@ -157,7 +161,10 @@ extern "C" size_t mpx_hlgauss_loss_workspace_bytes(long long n) { return (size_t
 
 extern "C" int mpx_hlgauss_loss(const float* logits, const float* targets, long long n, int n_logits,
                                 const float* supports, float vmin, float vmax, float sigma, float grad_scale,
-                                float* loss, float* dlogits, void* workspace, mpx_stream_t stream) {
+                                float* loss, float* dlogits, mpx_bf16* dlogits_bf16, int ld_bf16, void* workspace,
+                                mpx_stream_t stream) {
+  MPX_REQUIRE(!dlogits_bf16 || (ld_bf16 >= n_logits && ld_bf16 <= HLG_MAX_PER_LANE * 32),
+              "mpx_hlgauss_loss: ld_bf16=%d must be in [n_logits,128]", ld_bf16);
   MPX_REQUIRE(n > 0, "mpx_hlgauss_loss: empty input");
   MPX_REQUIRE(n_logits > 0 && n_logits <= HLG_MAX_PER_LANE * 32, "mpx_hlgauss_loss: n_logits=%d not in [1,128]",
               n_logits);
@@ -166,7 +173,8 @@ extern "C" int mpx_hlgauss_loss(const float* logits, const float* targets, long 
   const int grid = hlg_grid(n);
   double* partials = reinterpret_cast<double*>(workspace);
   hlgauss_loss_kernel<<<grid, HLG_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      logits, targets, n, n_logits, supports, vmin, vmax, sigma, grad_scale / (float)n, dlogits, partials);
+      logits, targets, n, n_logits, supports, vmin, vmax, sigma, grad_scale / (float)n, dlogits,
+      reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), ld_bf16, partials);
   hlgauss_loss_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, grid, 1.0 / (double)n, loss);
   return check_launch("mpx_hlgauss_loss");
 }

@@ -1,0 +1,384 @@
+"""Host-side sequencing of the policy hot path over the C-ABI kernels (no arithmetic happens in python/torch).
+
+Mirrors, call for call, what the reference's TransformerActorCritic.__call__ (network.py:300-343) does in its two
+modes - decode with a KV-cache carry (rollout, train.py:95) and full-window training (ppo_loss, train.py:182) - plus
+the hand-written transpose of the training pass that nnx.grad derives in the reference (train.py:236-238).
+
+All buffers are preallocated workspaces so a decode step / a minibatch step is a fixed launch sequence that can be
+captured into a CUDA graph.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+from types import SimpleNamespace
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib, ops
+from .config import ModelConfig
+from .params import ParamStore, conv_out
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+I32 = torch.int32
+
+
+def _round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+class PolicyEngine:
+    def __init__(self, cfg: ModelConfig, device="cuda", seed: int = 0, params: Optional[ParamStore] = None,
+                 bias_noise: float = 0.0):
+        if cfg.head_dim != 32:
+            raise _lib.MpxError("head_dim must be 32 on the B200 path")
+        if cfg.obs_type != "grid_cnn":
+            raise _lib.MpxError(f"obs_type {cfg.obs_type!r} is not on the B200 path yet (grid_cnn only)")
+        if cfg.value_hidden_dim is None:
+            raise _lib.MpxError("value_hidden_dim=None is not on the B200 path yet")
+        self.cfg = cfg
+        self.dev = torch.device(device)
+        self.p = params if params is not None else ParamStore(cfg, self.dev, seed, bias_noise)
+        H, D = cfg.hidden_features, cfg.head_dim
+        self.H, self.F, self.Vh, self.NL, self.A = H, cfg.ffn_size, cfg.value_hidden_dim, cfg.value_n_logits, cfg.action_dim
+        self.Nq, self.Nkv, self.D = cfg.num_heads, cfg.num_kv_heads, D
+        self.QD, self.KD = self.Nq * D, self.Nkv * D
+        self.QKV = self.QD + 2 * self.KD
+        self.L = cfg.num_layers
+        self.timescale = (torch.tensor(cfg.rope_max_wavelength, dtype=F32)
+                          ** (2.0 * torch.arange(0, D // 2, dtype=F32) / D)).to(self.dev)
+        sup = torch.linspace(cfg.value_min, cfg.value_max, cfg.value_n_logits + 1, dtype=F32)
+        self.supports = sup.to(self.dev)
+        self.centers = ((sup[:-1] + sup[1:]) / 2).to(self.dev)
+        # conv geometry (observation.py:63-82)
+        self.C0 = sum(cfg.obs_max_value)
+        self.conv = []
+        ih, iw, cin = cfg.obs_shape[0], cfg.obs_shape[1], self.C0
+        chans = list(cfg.cnn_channels) + [H]
+        for j, ((kh, kw), (sh, sw), ch) in enumerate(zip(cfg.cnn_kernels, cfg.cnn_strides, chans)):
+            oh, ow = conv_out(ih, kh, sh), conv_out(iw, kw, sw)
+            kp = _round_up(kh * kw * cin, 8)
+            self.conv.append(SimpleNamespace(j=j, ih=ih, iw=iw, cin=cin, kh=kh, kw=kw, sh=sh, sw=sw, oh=oh, ow=ow,
+                                             cout=ch, k=kh * kw * cin, kp=kp))
+            ih, iw, cin = oh, ow, ch
+        if ih != 1 or iw != 1:
+            raise _lib.MpxError("grid_cnn encoder must reduce the view to 1x1 (flatten == hidden_features)")
+        for c in self.conv[1:]:
+            if c.cin % 8 != 0:
+                raise _lib.MpxError("hidden conv channels must be multiples of 8")
+        self._alloc_staged()
+        self.stage_weights()
+
+    # ------------------------------------------------------------------------------------------ staged bf16 weights
+    def _alloc_staged(self):
+        cfg, dev, p = self.cfg, self.dev, self.p
+        H, F, Vh, NL, QD, KD, QKV = self.H, self.F, self.Vh, self.NL, self.QD, self.KD, self.QKV
+        z = lambda *s: torch.zeros(*s, dtype=BF16, device=dev)
+        self.w: Dict[str, torch.Tensor] = {}
+        descs: List[tuple] = []
+
+        def add(src, src_ld, dst, dst_ld, rows, cols, mode):
+            descs.append((src.data_ptr(), src_ld, dst.data_ptr(), dst_ld, rows, cols, mode))
+
+        for i in range(self.L):
+            pre = f"layers.{i}."
+            wq = p[pre + "history.query_proj.kernel"].view(H, QD)
+            wk = p[pre + "history.key_proj.kernel"].view(H, KD)
+            wv = p[pre + "history.value_proj.kernel"].view(H, KD)
+            wo = p[pre + "history.out.kernel"].view(QD, H)
+            wt_qkv, w_qkv = z(QKV, H), z(H, QKV)
+            add(wq, QD, wt_qkv, H, H, QD, 1)
+            add(wk, KD, wt_qkv[QD:], H, H, KD, 1)
+            add(wv, KD, wt_qkv[QD + KD:], H, H, KD, 1)
+            add(wq, QD, w_qkv, QKV, H, QD, 0)
+            add(wk, KD, w_qkv[:, QD:], QKV, H, KD, 0)
+            add(wv, KD, w_qkv[:, QD + KD:], QKV, H, KD, 0)
+            wt_o, w_o = z(H, QD), z(QD, H)
+            add(wo, H, wt_o, QD, QD, H, 1)
+            add(wo, H, w_o, H, QD, H, 0)
+            wu, wg, wd = p[pre + "ffn.up_proj.kernel"], p[pre + "ffn.up_gate.kernel"], p[pre + "ffn.down_proj.kernel"]
+            wt_ug, w_ug = z(2 * F, H), z(H, 2 * F)
+            for j in range(F // 128):     # 256-row tiles: [128 up rows | 128 gate rows]
+                add(wu[:, 128 * j:], F, wt_ug[256 * j:], H, H, 128, 1)
+                add(wg[:, 128 * j:], F, wt_ug[256 * j + 128:], H, H, 128, 1)
+            add(wu, F, w_ug, 2 * F, H, F, 0)
+            add(wg, F, w_ug[:, F:], 2 * F, H, F, 0)
+            wt_d, w_d = z(H, F), z(F, H)
+            add(wd, H, wt_d, F, F, H, 1)
+            add(wd, H, w_d, H, F, H, 0)
+            self.w.update({pre + "wt_qkv": wt_qkv, pre + "w_qkv": w_qkv, pre + "wt_o": wt_o, pre + "w_o": w_o,
+                           pre + "wt_ug": wt_ug, pre + "w_ug": w_ug, pre + "wt_d": wt_d, pre + "w_d": w_d})
+        # value mlp / head
+        wvm = p["value_mlp.kernel"]
+        wt_vm, w_vm, b_vm = z(Vh, H), z(H, Vh), z(Vh)
+        add(wvm, Vh, wt_vm, H, H, Vh, 1)
+        add(wvm, Vh, w_vm, Vh, H, Vh, 0)
+        add(p["value_mlp.bias"].view(1, Vh), Vh, b_vm, Vh, 1, Vh, 0)
+        wvh = p["value_head.dense.kernel"]                     # (Vh, NL) fp32
+        if NL > 64:
+            raise _lib.MpxError("value_n_logits > 64 is not supported by the hi/lo tensor-core value head")
+        wt_vh_hilo, w_vh_pad = z(128, Vh), z(Vh, 64)
+        add(wvh, NL, wt_vh_hilo, Vh, Vh, NL, 1)                 # hi = bf16(W^T)
+        add(wvh, NL, wt_vh_hilo[64:], Vh, Vh, NL, 3)            # lo = bf16(W^T - hi)
+        add(wvh, NL, w_vh_pad, 64, Vh, NL, 0)
+        self.w.update({"wt_vm": wt_vm, "w_vm": w_vm, "b_vm": b_vm, "wt_vh_hilo": wt_vh_hilo, "w_vh_pad": w_vh_pad})
+        # conv layers as GEMMs: kernel (kh,kw,cin,cout) == (k, cout) matrix
+        for c in self.conv:
+            wk_ = p[f"obs_encoder.layers.{c.j}.kernel"].view(c.k, c.cout)
+            wt_c, w_c, b_c = z(c.cout, c.kp), z(c.k, c.cout), z(c.cout)
+            add(wk_, c.cout, wt_c, c.kp, c.k, c.cout, 1)
+            add(wk_, c.cout, w_c, c.cout, c.k, c.cout, 0)
+            add(p[f"obs_encoder.layers.{c.j}.bias"].view(1, c.cout), c.cout, b_c, c.cout, 1, c.cout, 0)
+            self.w.update({f"wt_c{c.j}": wt_c, f"w_c{c.j}": w_c, f"b_c{c.j}": b_c})
+        arr = (_lib.PrepDesc * len(descs))()
+        for n, d in enumerate(descs):
+            arr[n] = _lib.PrepDesc(*d, 0)
+        raw = bytes(arr)
+        self._desc_dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        self._ndesc = len(descs)
+
+    def stage_weights(self):
+        """fp32 master params -> bf16 GEMM operand copies (one launch)."""
+        ops.prep_weights(self._desc_dev, self._ndesc)
+
+    # ------------------------------------------------------------------------------------------ workspaces
+    def _alloc_embed(self, ws, M: int, train: bool):
+        dev = self.dev
+        e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)
+        n = len(self.conv)
+        ws.cx, ws.cz, ws.ca = [], [], []
+        for c in self.conv:
+            rows = M * c.oh * c.ow
+            # the last conv covers the whole remaining map: its im2col is the flattened previous activation
+            ws.cx.append(e(rows, c.kp) if c.j < n - 1 else None)
+            ws.cz.append(e(rows, c.cout) if (train and c.j < n - 1) else None)
+            ws.ca.append(e(rows, c.cout))
+        ws.x0 = e(M, self.H)
+
+    def alloc_decode(self, B: int) -> SimpleNamespace:
+        dev, H = self.dev, self.H
+        ws = SimpleNamespace(B=B)
+        e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)
+        self._alloc_embed(ws, B, train=False)
+        ws.xa, ws.xb, ws.xn = e(B, H), e(B, H), e(B, H)
+        ws.q, ws.ao, ws.h = e(B, self.QD), e(B, self.QD), e(B, self.F)
+        ws.xf, ws.pv = e(B, H), e(B, self.Vh)
+        ws.logits = torch.empty(B, self.A, dtype=F32, device=dev)
+        ws.vlogits = torch.empty(B, self.NL, dtype=F32, device=dev)
+        S = self.cfg.max_seq_length
+        ws.kcache = [torch.zeros(B, S, self.Nkv, self.D, dtype=BF16, device=dev) for _ in range(self.L)]
+        ws.vcache = [torch.zeros(B, S, self.Nkv, self.D, dtype=BF16, device=dev) for _ in range(self.L)]
+        return ws
+
+    def reset_carry(self, ws):
+        """initialize_carry (attention.py:102-106): zero KV ring buffers."""
+        for t in ws.kcache + ws.vcache:
+            t.zero_()
+
+    def alloc_train(self, Bm: int, T: int) -> SimpleNamespace:
+        dev, H, F = self.dev, self.H, self.F
+        M = Bm * T
+        ws = SimpleNamespace(Bm=Bm, T=T, M=M)
+        e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)
+        f = lambda *s: torch.empty(*s, dtype=F32, device=dev)
+        self._alloc_embed(ws, M, train=True)
+        L = self.L
+        ws.x = [ws.x0] + [e(M, H) for _ in range(L)]
+        ws.xn1 = [e(M, H) for _ in range(L)]
+        ws.qkv = [e(M, self.QKV) for _ in range(L)]
+        ws.o = [e(M, self.QD) for _ in range(L)]
+        ws.lse = [f(M, self.Nq) for _ in range(L)]
+        ws.x1 = [e(M, H) for _ in range(L)]
+        ws.xn2 = [e(M, H) for _ in range(L)]
+        ws.h = [e(M, F) for _ in range(L)]
+        ws.u = [e(M, F) for _ in range(L)]
+        ws.g = [e(M, F) for _ in range(L)]
+        ws.xf, ws.zv, ws.pv = e(M, H), e(M, self.Vh), e(M, self.Vh)
+        ws.logits, ws.vlogits = f(M, self.A), f(M, self.NL)
+        ws.pos = torch.arange(T, dtype=I32, device=dev)
+        # backward scratch
+        ws.dlogits = f(M, self.A)
+        ws.dvl = e(M, 64)
+        ws.dpv = e(M, self.Vh)
+        ws.dxa, ws.dxb, ws.dxn = e(M, H), e(M, H), e(M, H)
+        ws.dh, ws.dug = e(M, F), e(M, 2 * F)
+        ws.dqkv, ws.do = e(M, self.QKV), e(M, self.QD)
+        ws.delta, ws.dq_acc = f(M, self.Nq), f(M, self.QD)
+        ws.dca = [e(M * c.oh * c.ow, c.cout) for c in self.conv[:-1]]
+        ws.dcx = [e(M * c.oh * c.ow, c.kp) if c.j > 0 else None for c in self.conv[:-1]]
+        ws.losses = f(4)          # value_loss, actor_loss, entropy_loss, (spare)
+        ws.loss_ws = torch.empty(max(_lib.lib.mpx_hlgauss_loss_workspace_bytes(M),
+                                     _lib.lib.mpx_ppo_policy_loss_workspace_bytes(M)), dtype=torch.uint8, device=dev)
+        return ws
+
+    # ------------------------------------------------------------------------------------------ embed (network.py:303-309)
+    def _embed_fwd(self, ws, M: int, obs, reward, last_action, task_ids, out, train: bool):
+        p, w = self.p, self.w
+        cfg = self.cfg
+        n = len(self.conv)
+        prev = None
+        for c in self.conv:
+            last = c.j == n - 1
+            if c.j == 0:
+                ops.obs_onehot_im2col(obs, ws.cx[0], M, c.ih, c.iw, cfg.obs_max_value, c.kh, c.kw, c.sh, c.sw)
+                xin = ws.cx[0]
+            elif last:
+                xin = prev.view(M, c.kp) if c.kp == c.k else None
+                if xin is None:
+                    raise _lib.MpxError("last conv layer needs kh*kw*cin % 8 == 0")
+            else:
+                ops.im2col(prev, ws.cx[c.j], M, c.ih, c.iw, c.cin, c.kh, c.kw, c.sh, c.sw)
+                xin = ws.cx[c.j]
+            rows = M * c.oh * c.ow
+            ops.linear(xin, w[f"wt_c{c.j}"], bias=w[f"b_c{c.j}"], act=0 if last else 1, out=ws.ca[c.j],
+                       y_pre=ws.cz[c.j] if (train and not last) else None, M=rows)
+            prev = ws.ca[c.j]
+        t_table = p.views.get("task_embedder.embedding_table") if task_ids is not None else None
+        ops.embed_combine(prev, reward, last_action, task_ids if t_table is not None else None,
+                          p["reward_encoder.kernel"], p["reward_encoder.bias"], p["action_embedder.embedding_table"],
+                          t_table, out=out)
+        return out
+
+    def _embed_bwd(self, ws, M: int, dx0, reward, last_action, task_ids):
+        p, w = self.p, self.w
+        gt = p.gviews.get("task_embedder.embedding_table") if task_ids is not None else None
+        ops.embed_bwd(dx0, reward, last_action, task_ids if gt is not None else None, self.A, self.cfg.task_count,
+                      p.g("reward_encoder.kernel"), p.g("reward_encoder.bias"),
+                      p.g("action_embedder.embedding_table"), gt)
+        n = len(self.conv)
+        dy = dx0                      # cotangent of the last conv's output (M, H)
+        for c in reversed(self.conv):
+            last = c.j == n - 1
+            rows = M * c.oh * c.ow
+            if not last:
+                ops.gelu_bwd(dy, ws.cz[c.j], out=dy)          # dz in place
+            ops.colsum(dy, p.g(f"obs_encoder.layers.{c.j}.bias"), M=rows, N=c.cout, ld=c.cout)
+            xin = ws.ca[c.j - 1].view(M, c.kp) if last else ws.cx[c.j]
+            ops.linear_wgrad(xin, dy, p.g(f"obs_encoder.layers.{c.j}.kernel").view(c.k, c.cout), M=rows, K=c.k,
+                             N=c.cout, ldx=c.kp, ldy=c.cout, lddw=c.cout)
+            if c.j == 0:
+                break
+            if last:
+                ops.linear(dy, w[f"w_c{c.j}"], out=ws.dca[c.j - 1].view(M, c.k), M=rows)
+            else:
+                ops.linear(dy, w[f"w_c{c.j}"], out=ws.dcx[c.j], M=rows)
+                ops.col2im(ws.dcx[c.j], ws.dca[c.j - 1], M, c.ih, c.iw, c.cin, c.kh, c.kw, c.sh, c.sw)
+            dy = ws.dca[c.j - 1]
+
+    # ------------------------------------------------------------------------------------------ decode step
+    def decode_step(self, ws, obs, reward, last_action, pos, action_mask=None, task_ids=None):
+        """One rollout step for B agents: TransformerActorCritic.__call__ with carry (network.py:300-343) on
+        add_seq_dim(timestep).  pos is the (B,) int32 device array ts.time.  Leaves action logits in ws.logits
+        and the HL-Gauss logits in ws.vlogits; the KV caches in ws are updated in place."""
+        p, w, B = self.p, self.w, ws.B
+        S = self.cfg.max_seq_length
+        x = self._embed_fwd(ws, B, obs, reward, last_action, task_ids, ws.xa, train=False)
+        other = ws.xb
+        for i in range(self.L):
+            pre = f"layers.{i}."
+            ops.rmsnorm_fwd(x, p[pre + "history_norm.scale"], out=ws.xn)
+            ops.qkv_rope(ws.xn, w[pre + "wt_qkv"], pos, self.timescale, self.Nq, self.Nkv, self.D, q=ws.q,
+                         k=ws.kcache[i], v=ws.vcache[i], k_row_stride=S * self.KD, v_row_stride=S * self.KD,
+                         cache_S=S)
+            ops.attn_decode(ws.q, ws.kcache[i], ws.vcache[i], pos, self.Nq, self.Nkv, self.D, out=ws.ao)
+            ops.linear(ws.ao, w[pre + "wt_o"], residual=x, out=other)
+            x, other = other, x
+            ops.rmsnorm_fwd(x, p[pre + "ffn_norm.scale"], out=ws.xn)
+            ops.glu_up(ws.xn, w[pre + "wt_ug"], self.F, h=ws.h)
+            ops.linear(ws.h, w[pre + "wt_d"], residual=x, out=other)
+            x, other = other, x
+        self._heads_fwd(x, action_mask, ws.xf, ws.logits, ws.pv, None, ws.vlogits)
+        return ws.logits, ws.vlogits
+
+    def _heads_fwd(self, x, action_mask, xf, logits, pv, zv, vlogits):
+        """network.py:321-341."""
+        p, w = self.p, self.w
+        ops.rmsnorm_fwd(x, p["output_norm.scale"], out=xf)
+        ops.policy_logits(xf, p["action_embedder.embedding_table"], action_mask, out=logits)
+        ops.linear(xf, w["wt_vm"], bias=w["b_vm"], act=1, out=pv, y_pre=zv)
+        ops.linear_f32w(pv, w["wt_vh_hilo"], p["value_head.dense.bias"], vlogits, self.NL)
+
+    # ------------------------------------------------------------------------------------------ training forward
+    def forward_train(self, ws, obs, last_rewards, last_actions, action_mask=None, task_ids=None):
+        """Full-window pass (ppo_loss's model call, train.py:180-192): obs (Bm,T,...) u8, positions arange(T)."""
+        p, w, M = self.p, self.w, ws.M
+        x = self._embed_fwd(ws, M, obs, last_rewards, last_actions, task_ids, ws.x[0], train=True)
+        QD, KD, QKV = self.QD, self.KD, self.QKV
+        for i in range(self.L):
+            pre = f"layers.{i}."
+            ops.rmsnorm_fwd(ws.x[i], p[pre + "history_norm.scale"], out=ws.xn1[i])
+            qkv = ws.qkv[i]
+            ops.qkv_rope(ws.xn1[i], w[pre + "wt_qkv"], ws.pos, self.timescale, self.Nq, self.Nkv, self.D,
+                         q=qkv, k=qkv[:, QD:], v=qkv[:, QD + KD:], q_row_stride=QKV, k_row_stride=QKV,
+                         v_row_stride=QKV, pos_len=ws.T)
+            ops.attn_train_fwd(qkv, qkv[:, QD:], qkv[:, QD + KD:], ws.Bm, ws.T, self.Nq, self.Nkv, self.D, QKV, QKV,
+                               QKV, o=ws.o[i], lse=ws.lse[i])
+            ops.linear(ws.o[i], w[pre + "wt_o"], residual=ws.x[i], out=ws.x1[i])
+            ops.rmsnorm_fwd(ws.x1[i], p[pre + "ffn_norm.scale"], out=ws.xn2[i])
+            ops.glu_up(ws.xn2[i], w[pre + "wt_ug"], self.F, save=True, h=ws.h[i], u=ws.u[i], g=ws.g[i])
+            ops.linear(ws.h[i], w[pre + "wt_d"], residual=ws.x1[i], out=ws.x[i + 1])
+        self._heads_fwd(ws.x[self.L], action_mask, ws.xf, ws.logits, ws.pv, ws.zv, ws.vlogits)
+        return ws.vlogits, ws.logits
+
+    # ------------------------------------------------------------------------------------------ loss + backward
+    def loss_and_backward(self, ws, batch: dict, hyp, progress: float, entropy_coef_dev=None):
+        """ppo_loss (train.py:162-222) on the activations left by forward_train, and its full transpose.
+        Gradients are ACCUMULATED into self.p.grad (zero it first).  ws.losses = (value, actor, entropy_loss)."""
+        p, w, M = self.p, self.w, ws.M
+        cfg = self.cfg
+        H, F, QD, KD, QKV, NL, Vh = self.H, self.F, self.QD, self.KD, self.QKV, self.NL, self.Vh
+        ent_coef = hyp.entropy_coef + progress * (hyp.entropy_coef_end - hyp.entropy_coef)
+        # ---- losses and their logits gradients
+        ops.hlgauss_loss(ws.vlogits, batch["targets"], self.supports, cfg.value_min, cfg.value_max, cfg.value_sigma,
+                         grad_scale=hyp.vf_coef, loss=ws.losses[0:1], dlogits_bf16=ws.dvl, ws=ws.loss_ws)
+        ops.ppo_policy_loss(ws.logits, batch["actions"], batch["log_prob"], batch["advantages"], hyp.vf_clip, ent_coef,
+                            losses=ws.losses[1:3], dlogits=ws.dlogits, ws=ws.loss_ws,
+                            entropy_coef_dev=entropy_coef_dev)
+        # ---- value head (values.py:34,40-41) and value MLP (network.py:335-338)
+        ops.linear_wgrad(ws.pv, ws.dvl, p.g("value_head.dense.kernel"), M=M, K=Vh, N=NL, ldx=Vh, ldy=64, lddw=NL)
+        ops.colsum(ws.dvl, p.g("value_head.dense.bias"), M=M, N=NL, ld=64)
+        ops.linear(ws.dvl, w["w_vh_pad"], out=ws.dpv)
+        ops.gelu_bwd(ws.dpv, ws.zv, out=ws.dpv)
+        ops.linear_wgrad(ws.xf, ws.dpv, p.g("value_mlp.kernel"), M=M, K=H, N=Vh, ldx=H, ldy=Vh, lddw=Vh)
+        ops.colsum(ws.dpv, p.g("value_mlp.bias"), M=M, N=Vh, ld=Vh)
+        ops.linear(ws.dpv, w["w_vm"], out=ws.dxn)                      # d xf from the value path
+        # ---- tied policy head (network.py:323) and output norm (:321)
+        ops.policy_head_bwd(ws.dlogits, ws.xf, p["action_embedder.embedding_table"],
+                            p.g("action_embedder.embedding_table"), dx_other=ws.dxn, out=ws.dxa)
+        dx, spare = ws.dxb, ws.dxa
+        ops.rmsnorm_bwd(ws.dxa, ws.x[self.L], p["output_norm.scale"], dscale=p.g("output_norm.scale"), out=dx)
+        # ---- transformer blocks in reverse (network.py:158-172)
+        for i in reversed(range(self.L)):
+            pre = f"layers.{i}."
+            ops.linear(dx, w[pre + "w_d"], out=ws.dh)
+            ops.linear_wgrad(ws.h[i], dx, p.g(pre + "ffn.down_proj.kernel"), M=M, K=F, N=H, ldx=F, ldy=H, lddw=H)
+            ops.glu_bwd(ws.dh, ws.u[i], ws.g[i], out=ws.dug)
+            ops.linear_wgrad(ws.xn2[i], ws.dug, p.g(pre + "ffn.up_proj.kernel"), M=M, K=H, N=F, ldx=H, ldy=2 * F, lddw=F)
+            ops.linear_wgrad(ws.xn2[i], ws.dug[:, F:], p.g(pre + "ffn.up_gate.kernel"), M=M, K=H, N=F, ldx=H,
+                             ldy=2 * F, lddw=F)
+            ops.linear(ws.dug, w[pre + "w_ug"], out=ws.dxn)
+            ops.rmsnorm_bwd(ws.dxn, ws.x1[i], p[pre + "ffn_norm.scale"], dscale=p.g(pre + "ffn_norm.scale"), dres=dx,
+                            out=spare)
+            dx, spare = spare, dx                                       # dx = d x1
+            ops.linear(dx, w[pre + "w_o"], out=ws.do)
+            ops.linear_wgrad(ws.o[i], dx, p.g(pre + "history.out.kernel").view(QD, H), M=M, K=QD, N=H, ldx=QD, ldy=H,
+                             lddw=H)
+            qkv, dqkv = ws.qkv[i], ws.dqkv
+            ops.attn_train_bwd(qkv, qkv[:, QD:], qkv[:, QD + KD:], ws.o[i], ws.do, ws.lse[i], ws.pos, self.timescale,
+                               ws.Bm, ws.T, self.Nq, self.Nkv, self.D, QKV, QKV, QKV, dqkv, dqkv[:, QD:],
+                               dqkv[:, QD + KD:], QKV, QKV, QKV, delta=ws.delta, dq_acc=ws.dq_acc, pos_len=ws.T)
+            ops.linear_wgrad(ws.xn1[i], dqkv, p.g(pre + "history.query_proj.kernel").view(H, QD), M=M, K=H, N=QD,
+                             ldx=H, ldy=QKV, lddw=QD)
+            ops.linear_wgrad(ws.xn1[i], dqkv[:, QD:], p.g(pre + "history.key_proj.kernel").view(H, KD), M=M, K=H,
+                             N=KD, ldx=H, ldy=QKV, lddw=KD)
+            ops.linear_wgrad(ws.xn1[i], dqkv[:, QD + KD:], p.g(pre + "history.value_proj.kernel").view(H, KD), M=M,
+                             K=H, N=KD, ldx=H, ldy=QKV, lddw=KD)
+            ops.linear(dqkv, w[pre + "w_qkv"], out=ws.dxn)
+            ops.rmsnorm_bwd(ws.dxn, ws.x[i], p[pre + "history_norm.scale"], dscale=p.g(pre + "history_norm.scale"),
+                            dres=dx, out=spare)
+            dx, spare = spare, dx                                       # dx = d x[i]
+        self._embed_bwd(ws, M, dx, batch["last_rewards"], batch["last_actions"], batch.get("task_ids"))
+        return ws.losses

@@ -7,7 +7,7 @@ libmapox_b200.so.  All tensors must live on a CUDA device (there is no CPU path)
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional
+from typing import Optional, Sequence
 
 import torch
 
@@ -16,6 +16,7 @@ from ._lib import check, lib, ptr, stream
 
 BF16 = torch.bfloat16
 F32 = torch.float32
+I32 = torch.int32
 
 
 def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
@@ -28,19 +29,25 @@ def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     return t
 
 
+def _u8(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    return t.view(torch.uint8) if t.dtype == torch.bool else t
+
+
 # ------------------------------------------------------------------------------------------------ GAE
-def gae(rewards, values, next_terminated, discount: float, gae_lambda: float):
+def gae(rewards, values, next_terminated, discount: float, gae_lambda: float, adv=None, tgt=None, stats=None,
+        ws=None):
     """-> (advantages, targets, stats[2] f64).  rollout.py:128-157 (before normalisation)."""
     B, T = rewards.shape
     _req(rewards, F32, "rewards"); _req(values, F32, "values")
-    if next_terminated.dtype == torch.bool:
-        next_terminated = next_terminated.view(torch.uint8)
-    _req(next_terminated, torch.uint8, "next_terminated")
+    next_terminated = _req(_u8(next_terminated), torch.uint8, "next_terminated")
     assert values.shape == (B, T + 1)
-    adv = torch.empty_like(rewards)
-    tgt = torch.empty_like(rewards)
-    stats = torch.empty(2, dtype=torch.float64, device=rewards.device)
-    ws = torch.empty(lib.mpx_gae_workspace_bytes(B, T), dtype=torch.uint8, device=rewards.device)
+    adv = torch.empty_like(rewards) if adv is None else adv
+    tgt = torch.empty_like(rewards) if tgt is None else tgt
+    stats = torch.empty(2, dtype=torch.float64, device=rewards.device) if stats is None else stats
+    if ws is None:
+        ws = torch.empty(lib.mpx_gae_workspace_bytes(B, T), dtype=torch.uint8, device=rewards.device)
     check(lib.mpx_gae(ptr(rewards), ptr(values), ptr(next_terminated), B, T, discount, gae_lambda,
                       ptr(adv), ptr(tgt), ptr(stats), ptr(ws), stream()), "mpx_gae")
     return adv, tgt, stats
@@ -56,81 +63,108 @@ def adv_normalize(adv, stats, count: Optional[float] = None):
 
 
 # ------------------------------------------------------------------------------------------------ HL-Gauss
-def hlgauss_value(logits, centers):
+def hlgauss_value(logits, centers, out=None):
     _req(logits, F32, "logits"); _req(centers, F32, "centers")
     NL = logits.shape[-1]
     n = logits.numel() // NL
-    out = torch.empty(logits.shape[:-1], dtype=F32, device=logits.device)
+    out = torch.empty(logits.shape[:-1], dtype=F32, device=logits.device) if out is None else out
     check(lib.mpx_hlgauss_value(ptr(logits), n, NL, ptr(centers), ptr(out), stream()), "mpx_hlgauss_value")
     return out
 
 
-def hlgauss_loss(logits, targets, supports, vmin: float, vmax: float, sigma: float,
-                 grad_scale: float = 1.0, want_grad: bool = True):
-    """-> (loss[1] f32, dlogits or None). values.py:47-63."""
+def hlgauss_loss(logits, targets, supports, vmin: float, vmax: float, sigma: float, grad_scale: float = 1.0,
+                 want_grad: bool = True, loss=None, dlogits=None, dlogits_bf16=None, ws=None):
+    """-> (loss[1] f32, dlogits or None). values.py:47-63.  dlogits_bf16 (n, ld) optional padded bf16 gradient."""
     _req(logits, F32, "logits"); _req(targets, F32, "targets"); _req(supports, F32, "supports")
     NL = logits.shape[-1]
     n = logits.numel() // NL
     assert targets.numel() == n and supports.numel() == NL + 1
-    loss = torch.empty(1, dtype=F32, device=logits.device)
-    dl = torch.empty_like(logits) if want_grad else None
-    ws = torch.empty(lib.mpx_hlgauss_loss_workspace_bytes(n), dtype=torch.uint8, device=logits.device)
+    loss = torch.empty(1, dtype=F32, device=logits.device) if loss is None else loss
+    if dlogits is None and want_grad and dlogits_bf16 is None:
+        dlogits = torch.empty_like(logits)
+    if ws is None:
+        ws = torch.empty(lib.mpx_hlgauss_loss_workspace_bytes(n), dtype=torch.uint8, device=logits.device)
+    ld = 0 if dlogits_bf16 is None else dlogits_bf16.shape[-1]
     check(lib.mpx_hlgauss_loss(ptr(logits), ptr(targets), n, NL, ptr(supports), vmin, vmax, sigma, grad_scale,
-                               ptr(loss), ptr(dl), ptr(ws), stream()), "mpx_hlgauss_loss")
-    return loss, dl
+                               ptr(loss), ptr(dlogits), ptr(dlogits_bf16), ld, ptr(ws), stream()), "mpx_hlgauss_loss")
+    return loss, dlogits
 
 
 # ------------------------------------------------------------------------------------------------ dense
 def linear(x, wt, bias=None, residual=None, act: int = 0, out: Optional[torch.Tensor] = None,
-           out_f32: Optional[torch.Tensor] = None, want_bf16: bool = True):
+           out_f32: Optional[torch.Tensor] = None, want_bf16: bool = True, y_pre=None, M: Optional[int] = None):
     """y = epi(x @ wt^T): x (M,K) bf16, wt (N,K) bf16 (transposed flax kernel)."""
     _req(x, BF16, "x"); _req(wt, BF16, "wt")
-    M, K = x.shape
+    K = x.shape[-1]
+    M = x.numel() // K if M is None else M
     N = wt.shape[0]
     assert wt.shape[1] == K
     if want_bf16 and out is None:
         out = torch.empty(M, N, dtype=BF16, device=x.device)
     a = _lib.LinearArgs(ptr(x), K, ptr(wt), K, ptr(bias), ptr(residual), N, ptr(out), N,
-                        ptr(out_f32), N, M, N, K, act)
+                        ptr(out_f32), N, M, N, K, act, ptr(y_pre))
     check(lib.mpx_linear(C.byref(a), stream()), "mpx_linear")
     return out if want_bf16 else out_f32
 
 
-def linear_wgrad(x, dy, dw):
-    """dw (K,N) f32 += x^T @ dy."""
-    _req(x, BF16, "x"); _req(dy, BF16, "dy"); _req(dw, F32, "dw")
-    M, K = x.shape
-    N = dy.shape[1]
-    assert dy.shape[0] == M and dw.shape == (K, N)
-    a = _lib.WgradArgs(ptr(x), K, ptr(dy), N, ptr(dw), N, M, N, K)
+def linear_wgrad(x, dy, dw, M: Optional[int] = None, K: Optional[int] = None, N: Optional[int] = None,
+                 ldx: Optional[int] = None, ldy: Optional[int] = None, lddw: Optional[int] = None):
+    """dw (K,N) f32 += x^T @ dy.  Column sub-blocks are addressed with explicit pitches (ldx/ldy/lddw)."""
+    _req(dw, F32, "dw")
+    assert x.dtype == BF16 and dy.dtype == BF16 and x.is_cuda and dy.is_cuda
+    ldx = x.shape[-1] if ldx is None else ldx
+    ldy = dy.shape[-1] if ldy is None else ldy
+    K = ldx if K is None else K
+    N = ldy if N is None else N
+    M = x.numel() // x.shape[-1] if M is None else M
+    lddw = dw.shape[-1] if lddw is None else lddw
+    a = _lib.WgradArgs(ptr(x), ldx, ptr(dy), ldy, ptr(dw), lddw, M, N, K)
     check(lib.mpx_linear_wgrad(C.byref(a), stream()), "mpx_linear_wgrad")
     return dw
 
 
+def linear_f32w(x, wt_hilo, bias, out, N: int):
+    """y (M,N) f32 = f32(x) @ W + bias with W carried as a bf16 hi/lo pair (HL-Gauss head)."""
+    _req(x, BF16, "x"); _req(wt_hilo, BF16, "wt_hilo"); _req(out, F32, "out")
+    K = x.shape[-1]
+    M = x.numel() // K
+    check(lib.mpx_linear_f32w(ptr(x), K, ptr(wt_hilo), ptr(bias), ptr(out), out.shape[-1], M, N, K, stream()),
+          "mpx_linear_f32w")
+    return out
+
+
 def qkv_rope(x, wt_qkv, pos, timescale, Nq: int, Nkv: int, D: int, q=None, k=None, v=None,
-             k_row_stride: Optional[int] = None, v_row_stride: Optional[int] = None, cache_S: int = 0):
+             q_row_stride: Optional[int] = None, k_row_stride: Optional[int] = None,
+             v_row_stride: Optional[int] = None, cache_S: int = 0, pos_len: Optional[int] = None):
     """q/k/v projection + RoPE (+ ring-slot write when cache_S > 0).  Returns (q, k, v)."""
-    _req(x, BF16, "x"); _req(wt_qkv, BF16, "wt_qkv"); _req(pos, torch.int32, "pos"); _req(timescale, F32, "timescale")
-    M, H = x.shape
+    _req(x, BF16, "x"); _req(wt_qkv, BF16, "wt_qkv"); _req(timescale, F32, "timescale")
+    assert pos.dtype == I32 and pos.is_cuda
+    H = x.shape[-1]
+    M = x.numel() // H
     if q is None:
         q = torch.empty(M, Nq * D, dtype=BF16, device=x.device)
     if k is None:
         k = torch.empty(M, Nkv * D, dtype=BF16, device=x.device)
         v = torch.empty(M, Nkv * D, dtype=BF16, device=x.device)
-        k_row_stride = v_row_stride = Nkv * D
-    a = _lib.QkvRopeArgs(ptr(x), H, ptr(wt_qkv), ptr(pos), pos.numel(), ptr(timescale), ptr(q), ptr(k),
-                         k_row_stride, ptr(v), v_row_stride, cache_S, M, H, Nq, Nkv, D)
+    q_row_stride = Nq * D if q_row_stride is None else q_row_stride
+    k_row_stride = Nkv * D if k_row_stride is None else k_row_stride
+    v_row_stride = Nkv * D if v_row_stride is None else v_row_stride
+    a = _lib.QkvRopeArgs(ptr(x), H, ptr(wt_qkv), ptr(pos), pos.numel() if pos_len is None else pos_len,
+                         ptr(timescale), ptr(q), q_row_stride, ptr(k), k_row_stride, ptr(v), v_row_stride,
+                         cache_S, M, H, Nq, Nkv, D)
     check(lib.mpx_qkv_rope(C.byref(a), stream()), "mpx_qkv_rope")
     return q, k, v
 
 
-def glu_up(x, wt_ug, F: int, save: bool = False):
+def glu_up(x, wt_ug, F: int, save: bool = False, h=None, u=None, g=None):
     """h = bf16(bf16(gelu(x@Wup)) * bf16(x@Wgate)); optionally also returns the bf16 pre-activations."""
     _req(x, BF16, "x"); _req(wt_ug, BF16, "wt_ug")
-    M, K = x.shape
-    h = torch.empty(M, F, dtype=BF16, device=x.device)
-    u = torch.empty(M, F, dtype=BF16, device=x.device) if save else None
-    g = torch.empty(M, F, dtype=BF16, device=x.device) if save else None
+    K = x.shape[-1]
+    M = x.numel() // K
+    h = torch.empty(M, F, dtype=BF16, device=x.device) if h is None else h
+    if save and u is None:
+        u = torch.empty(M, F, dtype=BF16, device=x.device)
+        g = torch.empty(M, F, dtype=BF16, device=x.device)
     a = _lib.GluUpArgs(ptr(x), K, ptr(wt_ug), ptr(h), ptr(u), ptr(g), M, F, K)
     check(lib.mpx_glu_up(C.byref(a), stream()), "mpx_glu_up")
     return (h, u, g) if save else h
@@ -145,12 +179,199 @@ def pack_glu_weight(w_up: torch.Tensor, w_gate: torch.Tensor) -> torch.Tensor:
     return torch.cat([ut, gt], dim=1).reshape(2 * F, K).to(BF16).contiguous()
 
 
+# ------------------------------------------------------------------------------------------------ row-wise
+def rmsnorm_fwd(x, scale, out=None, eps: float = 1e-6):
+    _req(x, BF16, "x"); _req(scale, F32, "scale")
+    H = x.shape[-1]
+    out = torch.empty_like(x) if out is None else out
+    check(lib.mpx_rmsnorm_fwd(ptr(x), ptr(scale), eps, ptr(out), x.numel() // H, H, stream()), "mpx_rmsnorm_fwd")
+    return out
+
+
+def rmsnorm_bwd(dy, x, scale, dscale=None, dres=None, out=None, eps: float = 1e-6):
+    _req(dy, BF16, "dy"); _req(x, BF16, "x"); _req(scale, F32, "scale")
+    H = x.shape[-1]
+    out = torch.empty_like(x) if out is None else out
+    check(lib.mpx_rmsnorm_bwd(ptr(dy), ptr(x), ptr(scale), eps, ptr(dres), ptr(out), ptr(dscale), x.numel() // H, H,
+                              stream()), "mpx_rmsnorm_bwd")
+    return out
+
+
+def glu_bwd(dh, u, g, out=None):
+    F = dh.shape[-1]
+    M = dh.numel() // F
+    out = torch.empty(M, 2 * F, dtype=BF16, device=dh.device) if out is None else out
+    check(lib.mpx_glu_bwd(ptr(dh), ptr(u), ptr(g), ptr(out), M, F, stream()), "mpx_glu_bwd")
+    return out
+
+
+def gelu_bwd(dy, z, out=None):
+    out = torch.empty_like(dy) if out is None else out
+    check(lib.mpx_gelu_bwd(ptr(dy), ptr(z), ptr(out), dy.numel(), stream()), "mpx_gelu_bwd")
+    return out
+
+
+def rope_(x, ld: int, pos, timescale, M: int, nheads: int, head_dim: int = 32, inverse: bool = False,
+          pos_len: Optional[int] = None):
+    check(lib.mpx_rope(ptr(x), ld, ptr(pos), pos.numel() if pos_len is None else pos_len, ptr(timescale), M, nheads,
+                       head_dim, int(inverse), stream()), "mpx_rope")
+    return x
+
+
+def colsum(x, out, M: Optional[int] = None, N: Optional[int] = None, ld: Optional[int] = None):
+    ld = x.shape[-1] if ld is None else ld
+    N = ld if N is None else N
+    M = x.numel() // x.shape[-1] if M is None else M
+    check(lib.mpx_colsum(ptr(x), ld, M, N, ptr(out), stream()), "mpx_colsum")
+    return out
+
+
+def add_bf16(a, b, out=None):
+    out = torch.empty_like(a) if out is None else out
+    check(lib.mpx_add_bf16(ptr(a), ptr(b), ptr(out), a.numel(), stream()), "mpx_add_bf16")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ attention
 def attn_decode(q, kcache, vcache, pos, Nq: int, Nkv: int, D: int, out=None):
-    _req(q, BF16, "q"); _req(kcache, BF16, "kcache"); _req(vcache, BF16, "vcache"); _req(pos, torch.int32, "pos")
+    _req(q, BF16, "q"); _req(kcache, BF16, "kcache"); _req(vcache, BF16, "vcache")
+    assert pos.dtype == I32 and pos.is_cuda
     B, S = kcache.shape[0], kcache.shape[1]
     if out is None:
         out = torch.empty(B, Nq * D, dtype=BF16, device=q.device)
     a = _lib.AttnDecodeArgs(ptr(q), ptr(kcache), ptr(vcache), ptr(pos), ptr(out), B, S, Nq, Nkv, D)
     check(lib.mpx_attn_decode(C.byref(a), stream()), "mpx_attn_decode")
     return out
+
+
+def attn_train_fwd(q, k, v, B: int, T: int, Nq: int, Nkv: int, D: int, ldq: int, ldk: int, ldv: int, o=None,
+                   lse=None):
+    """q/k/v may be column slices (data_ptr offset views) of one (B*T, ld) buffer."""
+    M = B * T
+    o = torch.empty(M, Nq * D, dtype=BF16, device=q.device) if o is None else o
+    lse = torch.empty(M, Nq, dtype=F32, device=q.device) if lse is None else lse
+    a = _lib.AttnTrainArgs(ptr(q), ldq, ptr(k), ldk, ptr(v), ldv, ptr(o), Nq * D, ptr(lse), B, T, Nq, Nkv, D)
+    check(lib.mpx_attn_train_fwd(C.byref(a), stream()), "mpx_attn_train_fwd")
+    return o, lse
+
+
+def attn_train_bwd(q, k, v, o, dout, lse, pos, timescale, B: int, T: int, Nq: int, Nkv: int, D: int, ldq: int,
+                   ldk: int, ldv: int, dq, dk, dv, lddq: int, lddk: int, lddv: int, delta=None, dq_acc=None,
+                   pos_len: Optional[int] = None):
+    M = B * T
+    delta = torch.empty(M, Nq, dtype=F32, device=q.device) if delta is None else delta
+    dq_acc = torch.empty(M, Nq * D, dtype=F32, device=q.device) if dq_acc is None else dq_acc
+    a = _lib.AttnTrainBwdArgs(ptr(q), ldq, ptr(k), ldk, ptr(v), ldv, ptr(o), Nq * D, ptr(dout), Nq * D, ptr(lse),
+                              ptr(delta), ptr(dq_acc), ptr(dq), lddq, ptr(dk), lddk, ptr(dv), lddv, ptr(pos),
+                              pos.numel() if pos_len is None else pos_len, ptr(timescale), B, T, Nq, Nkv, D)
+    check(lib.mpx_attn_train_bwd(C.byref(a), stream()), "mpx_attn_train_bwd")
+    return dq, dk, dv
+
+
+# ------------------------------------------------------------------------------------------------ embeds / heads
+def embed_combine(obs_emb, reward, last_action, task_ids, w_r, b_r, a_table, t_table, out=None):
+    H = obs_emb.shape[-1]
+    M = obs_emb.numel() // H
+    out = torch.empty_like(obs_emb) if out is None else out
+    check(lib.mpx_embed_combine(ptr(obs_emb), ptr(reward), ptr(last_action), ptr(task_ids), ptr(w_r), ptr(b_r),
+                                ptr(a_table), a_table.shape[0], ptr(t_table),
+                                0 if t_table is None else t_table.shape[0], ptr(out), M, H, stream()),
+          "mpx_embed_combine")
+    return out
+
+
+def embed_bwd(dx, reward, last_action, task_ids, A: int, n_tasks: int, d_wr, d_br, d_a_table, d_t_table):
+    H = dx.shape[-1]
+    M = dx.numel() // H
+    check(lib.mpx_embed_bwd(ptr(dx), ptr(reward), ptr(last_action), ptr(task_ids), A, n_tasks, ptr(d_wr), ptr(d_br),
+                            ptr(d_a_table), ptr(d_t_table), M, H, stream()), "mpx_embed_bwd")
+
+
+def policy_logits(x, table, mask=None, out=None):
+    H = x.shape[-1]
+    M = x.numel() // H
+    A = table.shape[0]
+    out = torch.empty(M, A, dtype=F32, device=x.device) if out is None else out
+    check(lib.mpx_policy_logits(ptr(x), ptr(table), ptr(_u8(mask)), ptr(out), M, H, A, stream()), "mpx_policy_logits")
+    return out
+
+
+def policy_sample(logits, gumbel, action=None, log_prob=None):
+    A = logits.shape[-1]
+    M = logits.numel() // A
+    action = torch.empty(M, dtype=I32, device=logits.device) if action is None else action
+    log_prob = torch.empty(M, dtype=F32, device=logits.device) if log_prob is None else log_prob
+    check(lib.mpx_policy_sample(ptr(logits), ptr(gumbel), ptr(action), ptr(log_prob), M, A, stream()),
+          "mpx_policy_sample")
+    return action, log_prob
+
+
+def gumbel_noise(out, seed: int, stream_id: int, stream_offset=None):
+    check(lib.mpx_gumbel_noise(ptr(out), out.numel(), seed, stream_id, ptr(stream_offset), stream()),
+          "mpx_gumbel_noise")
+    return out
+
+
+def ppo_policy_loss(logits, actions, old_log_prob, advantages, clip_eps: float, entropy_coef: float, losses=None,
+                    dlogits=None, want_grad: bool = True, ws=None, entropy_coef_dev=None):
+    A = logits.shape[-1]
+    M = logits.numel() // A
+    losses = torch.empty(2, dtype=F32, device=logits.device) if losses is None else losses
+    if dlogits is None and want_grad:
+        dlogits = torch.empty_like(logits)
+    if ws is None:
+        ws = torch.empty(lib.mpx_ppo_policy_loss_workspace_bytes(M), dtype=torch.uint8, device=logits.device)
+    check(lib.mpx_ppo_policy_loss(ptr(logits), ptr(actions), ptr(old_log_prob), ptr(advantages), clip_eps,
+                                  entropy_coef, ptr(entropy_coef_dev), ptr(losses), ptr(dlogits), ptr(ws), M, A,
+                                  stream()),
+          "mpx_ppo_policy_loss")
+    return losses, dlogits
+
+
+def policy_head_bwd(dlogits, x, table, dtable, dx_other=None, out=None):
+    H = x.shape[-1]
+    M = x.numel() // H
+    out = torch.empty_like(x) if out is None else out
+    check(lib.mpx_policy_head_bwd(ptr(dlogits), ptr(x), ptr(table), ptr(dx_other), ptr(out), ptr(dtable), M, H,
+                                  table.shape[0], stream()), "mpx_policy_head_bwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ obs encoder
+def obs_onehot_im2col(obs, out, M: int, IH: int, IW: int, sizes: Sequence[int], kh, kw, sh, sw):
+    K = len(sizes)
+    arr = (C.c_int * K)(*sizes)
+    check(lib.mpx_obs_onehot_im2col(ptr(obs), ptr(out), M, IH, IW, K, arr, kh, kw, sh, sw, out.shape[-1], stream()),
+          "mpx_obs_onehot_im2col")
+    return out
+
+
+def im2col(a, out, M: int, IH: int, IW: int, Cc: int, kh, kw, sh, sw):
+    check(lib.mpx_im2col(ptr(a), ptr(out), M, IH, IW, Cc, kh, kw, sh, sw, stream()), "mpx_im2col")
+    return out
+
+
+def col2im(dx, out, M: int, IH: int, IW: int, Cc: int, kh, kw, sh, sw):
+    check(lib.mpx_col2im(ptr(dx), ptr(out), M, IH, IW, Cc, kh, kw, sh, sw, stream()), "mpx_col2im")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ optimizer etc.
+def adamw_step(params, grads, mu, nu, scratch, step, lr0, total_steps, b1, b2, eps, wd, max_norm, grad_scale=1.0,
+               norm_out=None, ws=None):
+    n = params.numel()
+    if ws is None:
+        ws = torch.empty(lib.mpx_adamw_workspace_bytes(n), dtype=torch.uint8, device=params.device)
+    check(lib.mpx_adamw_step(ptr(params), ptr(grads), ptr(mu), ptr(nu), ptr(scratch), n, ptr(step), lr0,
+                             float(total_steps), b1, b2, eps, wd, max_norm, grad_scale, ptr(norm_out), ptr(ws),
+                             stream()), "mpx_adamw_step")
+
+
+def prep_weights(descs_device, ndesc: int):
+    check(lib.mpx_prep_weights(ptr(descs_device), ndesc, stream()), "mpx_prep_weights")
+
+
+def transpose_tb(src, dst, perm, T: int, B: int):
+    item_bytes = src.numel() * src.element_size() // (T * B)
+    check(lib.mpx_transpose_tb(ptr(src), ptr(dst), ptr(perm), T, B, item_bytes, stream()), "mpx_transpose_tb")
+    return dst

@@ -1,0 +1,139 @@
+"""Parameter store: one flat fp32 buffer (+ a flat gradient buffer) with named views that follow the reference's
+nnx pytree paths, so weights can be handed to / from the JAX side by name.
+
+Initialisers restate network.py:39-52,190-193 (glorot-uniform layer kernels, N(0,1)*0.01 embedding tables,
+flax defaults - lecun-normal kernels, zero biases - elsewhere, ones for norm scales).
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Tuple
+
+import torch
+
+from .config import ModelConfig
+
+
+def conv_out(n: int, k: int, s: int) -> int:
+    return (n - k) // s + 1
+
+
+def param_specs(cfg: ModelConfig) -> List[Tuple[str, Tuple[int, ...], str]]:
+    H, D, Nq, Nkv, F = cfg.hidden_features, cfg.head_dim, cfg.num_heads, cfg.num_kv_heads, cfg.ffn_size
+    specs: List[Tuple[str, Tuple[int, ...], str]] = []
+    specs.append(("reward_encoder.kernel", (1, H), "lecun"))
+    specs.append(("reward_encoder.bias", (H,), "zeros"))
+    specs.append(("action_embedder.embedding_table", (cfg.action_dim, H), "embed"))
+    C = sum(cfg.obs_max_value)
+    if cfg.obs_type == "grid_cnn":
+        cin = C
+        chans = list(cfg.cnn_channels) + [H]
+        for j, ((kh, kw), ch) in enumerate(zip(cfg.cnn_kernels, chans)):
+            specs.append((f"obs_encoder.layers.{j}.kernel", (kh, kw, cin, ch), "lecun"))
+            specs.append((f"obs_encoder.layers.{j}.bias", (ch,), "zeros"))
+            cin = ch
+    elif cfg.obs_type == "grid_flattened":
+        specs.append(("obs_encoder.embedding.kernel", (C, 4), "lecun"))
+        specs.append(("obs_encoder.embedding.bias", (4,), "zeros"))
+        specs.append(("obs_encoder.dense.kernel", (4 * cfg.obs_shape[0] * cfg.obs_shape[1], H), "lecun"))
+        specs.append(("obs_encoder.dense.bias", (H,), "zeros"))
+    else:
+        raise ValueError(f"unsupported obs_type {cfg.obs_type}")
+    if cfg.task_count > 1:
+        specs.append(("task_embedder.embedding_table", (cfg.task_count, H), "embed"))
+    for i in range(cfg.num_layers):
+        pre = f"layers.{i}."
+        specs.append((pre + "history_norm.scale", (H,), "ones"))
+        specs.append((pre + "history.key_proj.kernel", (H, Nkv, D), "glorot"))
+        specs.append((pre + "history.value_proj.kernel", (H, Nkv, D), "glorot"))
+        specs.append((pre + "history.query_proj.kernel", (H, Nq, D), "glorot"))
+        specs.append((pre + "history.out.kernel", (Nq, D, H), "glorot_out"))
+        specs.append((pre + "ffn_norm.scale", (H,), "ones"))
+        specs.append((pre + "ffn.up_proj.kernel", (H, F), "glorot"))
+        specs.append((pre + "ffn.up_gate.kernel", (H, F), "glorot"))
+        specs.append((pre + "ffn.down_proj.kernel", (F, H), "glorot"))
+    specs.append(("output_norm.scale", (H,), "ones"))
+    vin = H
+    if cfg.value_hidden_dim is not None:
+        specs.append(("value_mlp.kernel", (H, cfg.value_hidden_dim), "lecun"))
+        specs.append(("value_mlp.bias", (cfg.value_hidden_dim,), "zeros"))
+        vin = cfg.value_hidden_dim
+    specs.append(("value_head.dense.kernel", (vin, cfg.value_n_logits), "lecun"))
+    specs.append(("value_head.dense.bias", (cfg.value_n_logits,), "zeros"))
+    return specs
+
+
+def _init(shape, kind: str, gen: torch.Generator) -> torch.Tensor:
+    if kind == "zeros":
+        return torch.zeros(shape)
+    if kind == "ones":
+        return torch.ones(shape)
+    if kind == "embed":
+        return torch.randn(shape, generator=gen) * 0.01
+    n = 1
+    for s in shape:
+        n *= s
+    if kind == "glorot":          # (in, *out)
+        fan_in, fan_out = shape[0], n // shape[0]
+    elif kind == "glorot_out":    # (*in, out)
+        fan_in, fan_out = n // shape[-1], shape[-1]
+    else:                         # lecun: (*receptive, in, out)
+        fan_in, fan_out = n // shape[-1], shape[-1]
+    if kind.startswith("glorot"):
+        lim = math.sqrt(6.0 / (fan_in + fan_out))
+        return (torch.rand(shape, generator=gen) * 2 - 1) * lim
+    return torch.randn(shape, generator=gen) * math.sqrt(1.0 / fan_in)
+
+
+class ParamStore:
+    ALIGN = 4   # floats (16 bytes): kernels read fp32 params with float4 loads
+
+    def __init__(self, cfg: ModelConfig, device, seed: int = 0, bias_noise: float = 0.0):
+        self.cfg = cfg
+        self.specs = param_specs(cfg)
+        self.offsets: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        off = 0
+        for name, shape, _ in self.specs:
+            n = 1
+            for s in shape:
+                n *= s
+            self.offsets[name] = (off, shape)
+            off += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.numel = off
+        gen = torch.Generator().manual_seed(seed)
+        host = torch.zeros(off, dtype=torch.float32)
+        for name, shape, kind in self.specs:
+            o, _ = self.offsets[name]
+            t = _init(shape, kind, gen)
+            if kind == "zeros" and bias_noise > 0:
+                t = torch.randn(shape, generator=gen) * bias_noise
+            host[o:o + t.numel()] = t.reshape(-1)
+        self.flat = host.to(device)
+        self.grad = torch.zeros_like(self.flat)
+        self.views = {n: self._view(self.flat, n) for n, _, _ in self.specs}
+        self.gviews = {n: self._view(self.grad, n) for n, _, _ in self.specs}
+
+    def _view(self, buf: torch.Tensor, name: str) -> torch.Tensor:
+        o, shape = self.offsets[name]
+        n = 1
+        for s in shape:
+            n *= s
+        return buf[o:o + n].view(shape)
+
+    def __getitem__(self, name: str) -> torch.Tensor:
+        return self.views[name]
+
+    def g(self, name: str) -> torch.Tensor:
+        return self.gviews[name]
+
+    def oracle_dict(self) -> Dict[str, torch.Tensor]:
+        """fp32 CPU copies keyed by the reference pytree path (what the oracle / a JAX checkpoint consumes)."""
+        return {n: v.detach().float().cpu().clone() for n, v in self.views.items()}
+
+    def grad_dict(self) -> Dict[str, torch.Tensor]:
+        return {n: v.detach().float().cpu().clone() for n, v in self.gviews.items()}
+
+    def load_dict(self, d: Dict[str, torch.Tensor]) -> None:
+        for n, v in d.items():
+            self.views[n].copy_(v.to(self.flat.device, torch.float32).reshape(self.views[n].shape))

@@ -1,0 +1,238 @@
+"""PPO update sequencing: rollout -> GAE -> minibatch forward/backward -> optimizer, mirroring the reference's
+`train()` (mapox_trainer/train.py:225-309), `evaluate()` (:42-159) and `Rollout` (rollout.py) call for call, on top
+of the C-ABI kernels.  Environments are replaced by synthetic observations of the named env shapes (north star);
+the environment echoes the sampled action as next_timestep.last_action.
+
+Data-parallel layout (new; the reference is single-device, train.py:312-315 is dead code): each rank owns
+B/world agents end to end - KV caches, rollout buffers, GAE rows and minibatches - with weights replicated; per
+minibatch one gradient all-reduce over NCCL and, once per rollout, an all-reduce of the advantage moments.
+"""
+
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+
+from . import _lib, ops
+from .config import RunConfig
+from .engine import PolicyEngine
+
+BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
+
+
+class SyntheticEnv:
+    """Pre-drawn observation / reward streams with the shapes of the named environment (T+1 steps, B agents).
+    `host=True` keeps them in pinned host memory (the end-to-end path copies one step per decode step)."""
+
+    def __init__(self, cfg, B: int, T: int, device, seed: int = 42, host: bool = False):
+        gen = torch.Generator().manual_seed(seed)
+        vw, vh = cfg.obs_shape[0], cfg.obs_shape[1]
+        comps = [torch.randint(0, n, (T + 1, B, vw, vh), generator=gen, dtype=torch.uint8) for n in cfg.obs_max_value]
+        obs = torch.stack(comps, dim=-1).contiguous()
+        reward = ((torch.rand(T + 1, B, generator=gen) < 0.02).float() * 0.05).contiguous()
+        self.T, self.B = T, B
+        self.obs_host = obs.pin_memory() if host else None
+        self.reward_host = reward.pin_memory() if host else None
+        self.obs = obs.to(device)
+        self.reward = reward.to(device)
+        term = torch.zeros(T + 1, B, dtype=torch.uint8)
+        term[T] = 1                                   # episode ends with the rollout (max_env_steps == T)
+        self.terminated = term.to(device)
+
+
+class PPOTrainer:
+    def __init__(self, run: RunConfig, device="cuda", rank: int = 0, world: int = 1, use_graphs: bool = True,
+                 e2e_host_inputs: bool = False, seed: Optional[int] = None, run_optimizer: bool = True):
+        self.run, self.cfg, self.hyp, self.opt = run, run.model, run.ppo, run.optimizer
+        self.dev = torch.device(device)
+        self.rank, self.world = rank, world
+        self.use_graphs = use_graphs
+        self.e2e = e2e_host_inputs
+        self.run_optimizer = run_optimizer
+        if run.num_agents % world != 0:
+            raise ValueError("num_agents must divide evenly across ranks")
+        self.B = run.num_agents // world
+        self.T = self.cfg.max_seq_length
+        m = self.hyp.minibatch_count
+        if self.B % m != 0:
+            raise ValueError(f"agents per rank ({self.B}) must be a multiple of minibatch_count ({m})")
+        if self.hyp.epoch_count != 1:
+            raise _lib.MpxError("epoch_count > 1 is not implemented on the B200 path yet")
+        self.Bm = self.B // m
+        seed = run.seed if seed is None else seed
+        self.seed = seed
+        self.engine = PolicyEngine(self.cfg, self.dev, seed=seed)          # same seed on every rank: replicated weights
+        self.env = SyntheticEnv(self.cfg, self.B, self.T, self.dev, seed=seed + 1000 * (rank + 1), host=self.e2e)
+        self._alloc()
+        self.rollout_graph = None
+        self.update_graph = None
+
+    # ------------------------------------------------------------------------------------------ buffers
+    def _alloc(self):
+        dev, B, T, cfg = self.dev, self.B, self.T, self.cfg
+        A = cfg.action_dim
+        self.dws = self.engine.alloc_decode(B)
+        self.tws = self.engine.alloc_train(self.Bm, T)
+        f = lambda *s: torch.zeros(*s, dtype=F32, device=dev)
+        r = SimpleNamespace()
+        # time-major rollout buffers (RolloutState, rollout.py:11-30, written one contiguous row per step)
+        r.actions_ext = torch.zeros(T + 1, B, dtype=I32, device=dev)       # row 0 = last_action of the reset step
+        r.log_prob = f(T, B)
+        r.values = f(T + 1, B)
+        r.gumbel = f(B, A)
+        r.pos = torch.arange(T, dtype=I32, device=dev)[:, None].repeat(1, B).contiguous()   # ts.time per step
+        r.obs_stage = torch.empty_like(self.env.obs[0]) if self.e2e else None
+        r.rew_stage = torch.empty_like(self.env.reward[0]) if self.e2e else None
+        self.r = r
+        b = SimpleNamespace()
+        # batch-major (permuted) training view
+        b.obs = torch.empty(B, T, *self.env.obs.shape[2:], dtype=torch.uint8, device=dev)
+        b.actions = torch.empty(B, T, dtype=I32, device=dev)
+        b.last_actions = torch.empty(B, T, dtype=I32, device=dev)
+        b.log_prob, b.rewards, b.last_rewards = f(B, T), f(B, T), f(B, T)
+        b.values = f(B, T + 1)
+        b.next_terminated = torch.empty(B, T, dtype=torch.uint8, device=dev)
+        b.advantages, b.targets = f(B, T), f(B, T)
+        b.stats = torch.zeros(2, dtype=torch.float64, device=dev)
+        b.gae_ws = torch.empty(_lib.lib.mpx_gae_workspace_bytes(B, T), dtype=torch.uint8, device=dev)
+        b.perm = torch.arange(B, dtype=I32, device=dev)
+        self.b = b
+        n = self.engine.p.numel
+        o = SimpleNamespace(mu=f(n), nu=f(n), scratch=f(n), step=torch.zeros(1, dtype=I32, device=dev),
+                            norm=f(1), ws=torch.empty(_lib.lib.mpx_adamw_workspace_bytes(n), dtype=torch.uint8, device=dev))
+        self.o = o
+        self.noise_off = torch.zeros(1, dtype=torch.int64, device=dev)      # Gumbel stream offset, += T per rollout
+        self.ent_coef = torch.full((1,), self.hyp.entropy_coef, dtype=F32, device=dev)
+        self.log_acc = f(4)
+        self.update_idx = 0
+        self.perm_gen = torch.Generator(device=dev).manual_seed(self.seed + 17 + self.rank)
+
+    # ------------------------------------------------------------------------------------------ rollout (evaluate)
+    def _decode(self, t: int, obs, reward, last_action, pos, value_out):
+        eng, r = self.engine, self.r
+        logits, vlogits = eng.decode_step(self.dws, obs, reward, last_action, pos)
+        return logits, vlogits
+
+    def _rollout_body(self):
+        eng, r, env, T = self.engine, self.r, self.env, self.T
+        for t in range(T):
+            if self.e2e:                                    # host -> device copy of this step's inputs (timed)
+                r.obs_stage.copy_(env.obs_host[t], non_blocking=True)
+                r.rew_stage.copy_(env.reward_host[t], non_blocking=True)
+                obs_t, rew_t = r.obs_stage, r.rew_stage
+            else:
+                obs_t, rew_t = env.obs[t], env.reward[t]
+            logits, vlogits = eng.decode_step(self.dws, obs_t, rew_t, r.actions_ext[t], r.pos[t])
+            ops.gumbel_noise(r.gumbel, self.seed, t, self.noise_off)
+            ops.policy_sample(logits, r.gumbel, action=r.actions_ext[t + 1], log_prob=r.log_prob[t])
+            ops.hlgauss_value(vlogits, eng.centers, out=r.values[t])
+        # bootstrap (train.py:142-148): value of the INITIAL timestep with the INITIAL (empty) carry.  Position 0
+        # reads and writes ring slot 0 only, so re-running step 0 on the used caches is equivalent.
+        if self.e2e:
+            r.obs_stage.copy_(env.obs_host[0], non_blocking=True)
+            r.rew_stage.copy_(env.reward_host[0], non_blocking=True)
+            obs0, rew0 = r.obs_stage, r.rew_stage
+        else:
+            obs0, rew0 = env.obs[0], env.reward[0]
+        _, vlogits = eng.decode_step(self.dws, obs0, rew0, r.actions_ext[0], r.pos[0])
+        ops.hlgauss_value(vlogits, eng.centers, out=r.values[T])
+
+    def _postprocess_body(self):
+        """Layout change (+ row permutation, rollout.py:169-181) and calculate_advantage (rollout.py:128-167)."""
+        r, b, env, T, B = self.r, self.b, self.env, self.T, self.B
+        perm = b.perm
+        ops.transpose_tb(env.obs[:T], b.obs, perm, T, B)
+        ops.transpose_tb(r.actions_ext[1:], b.actions, perm, T, B)
+        ops.transpose_tb(r.actions_ext[:T], b.last_actions, perm, T, B)
+        ops.transpose_tb(r.log_prob, b.log_prob, perm, T, B)
+        ops.transpose_tb(env.reward[1:], b.rewards, perm, T, B)
+        ops.transpose_tb(env.reward[:T], b.last_rewards, perm, T, B)
+        ops.transpose_tb(r.values, b.values, perm, T + 1, B)
+        ops.transpose_tb(env.terminated[1:], b.next_terminated, perm, T, B)
+        ops.gae(b.rewards, b.values, b.next_terminated, self.hyp.discount, self.hyp.gae_lambda, adv=b.advantages,
+                tgt=b.targets, stats=b.stats, ws=b.gae_ws)
+
+    def _normalize(self):
+        b = self.b
+        if not self.hyp.normalize_advantage:
+            return
+        count = float(self.B * self.T * self.world)
+        if self.world > 1:
+            torch.distributed.all_reduce(b.stats)
+        ops.adv_normalize(b.advantages.view(-1), b.stats, count)
+
+    # ------------------------------------------------------------------------------------------ update (train.py:249-260)
+    def _minibatch_body(self, i: int):
+        eng, b, tws, Bm = self.engine, self.b, self.tws, self.Bm
+        sl = slice(i * Bm, (i + 1) * Bm)
+        batch = dict(actions=b.actions[sl].reshape(-1), log_prob=b.log_prob[sl].reshape(-1),
+                     advantages=b.advantages[sl].reshape(-1), targets=b.targets[sl].reshape(-1),
+                     last_rewards=b.last_rewards[sl].reshape(-1), last_actions=b.last_actions[sl].reshape(-1))
+        eng.p.grad.zero_()
+        eng.forward_train(tws, b.obs[sl], batch["last_rewards"], batch["last_actions"])
+        eng.loss_and_backward(tws, batch, self.hyp, 0.0, entropy_coef_dev=self.ent_coef)
+        self.log_acc[:3] += tws.losses[:3]
+        if self.world > 1:
+            torch.distributed.all_reduce(eng.p.grad)
+        if self.run_optimizer:
+            o, opt = self.o, self.opt
+            total = self.run.update_steps * self.hyp.minibatch_count * self.hyp.epoch_count
+            ops.adamw_step(eng.p.flat, eng.p.grad, o.mu, o.nu, o.scratch, o.step, opt.learning_rate, total, opt.beta1,
+                           opt.beta2, opt.eps, opt.weight_decay, opt.max_norm, grad_scale=1.0 / self.world,
+                           norm_out=o.norm, ws=o.ws)
+            eng.stage_weights()
+
+    def _update_body(self):
+        for i in range(self.hyp.minibatch_count):
+            self._minibatch_body(i)
+
+    # ------------------------------------------------------------------------------------------ driver
+    def _capture(self, fn):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g
+
+    def warmup(self):
+        """One eager pass (sets kernel attributes, fills caches), then CUDA-graph capture of the three phases."""
+        self._rollout_body()
+        self._postprocess_body()
+        self._normalize()
+        self._update_body()
+        torch.cuda.synchronize()
+        if self.use_graphs:
+            self.rollout_graph = self._capture(self._rollout_body)
+            self.post_graph = self._capture(self._postprocess_body)
+            if self.world == 1:
+                self.update_graph = self._capture(self._update_body)
+            torch.cuda.synchronize()
+        self.log_acc.zero_()
+
+    def train_step(self):
+        """One outer PPO update (train.py:_global_step): returns the device tensor of summed minibatch losses."""
+        progress = self.update_idx / max(1, self.run.update_steps)
+        self.ent_coef.fill_(self.hyp.entropy_coef + progress * (self.hyp.entropy_coef_end - self.hyp.entropy_coef))
+        self.b.perm.copy_(torch.randperm(self.B, generator=self.perm_gen, device=self.dev).to(I32))
+        self.log_acc.zero_()
+        if self.rollout_graph is not None:
+            self.rollout_graph.replay()
+            self.post_graph.replay()
+        else:
+            self._rollout_body()
+            self._postprocess_body()
+        self._normalize()
+        if self.update_graph is not None:
+            self.update_graph.replay()
+        else:
+            self._update_body()
+        self.noise_off += self.T
+        self.update_idx += 1
+        return self.log_acc
+
+    def logs(self) -> dict:
+        """Device -> host read of the averaged minibatch losses (the reference's logger.log sync, train.py:419)."""
+        n = self.hyp.minibatch_count * self.hyp.epoch_count
+        v = (self.log_acc / n).cpu()
+        return dict(value_loss=v[0].item(), actor_loss=v[1].item(), entropy_loss=v[2].item())

@@ -13,6 +13,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import oracle as O  # noqa: E402
+from _util import assert_close_bf16, log as _log, rope_timescale as _rope_timescale  # noqa: E402
 
 
 @pytest.fixture(scope="module")
@@ -23,26 +24,6 @@ def ops():
 
 DEV = "cuda"
 BF16 = torch.bfloat16
-
-
-def _log(msg):
-    os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/probe.log", "a") as f:
-        f.write(msg + "\n")
-
-
-def assert_close_bf16(got, ref, name, rtol=1e-2, abs_floor_frac=4e-3):
-    """|got-ref| <= rtol*|ref| + abs_floor_frac*rms(ref) elementwise (bf16 results)."""
-    got = got.detach().float().cpu()
-    ref = ref.detach().float().cpu()
-    assert got.shape == ref.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
-    assert torch.isfinite(got).all(), f"{name}: non-finite output"
-    rms = ref.pow(2).mean().sqrt().item() + 1e-12
-    err = (got - ref).abs()
-    tol = rtol * ref.abs() + abs_floor_frac * rms
-    bad = (err > tol).float().mean().item()
-    _log(f"{name}: max_abs_err={err.max().item():.4e} rms_ref={rms:.4e} frac_bad={bad:.3e}")
-    assert bad == 0.0, f"{name}: {bad * 100:.4f}% elements out of tolerance, max err {err.max().item():.4e} (rms {rms:.3e})"
 
 
 def g(seed):
@@ -174,10 +155,6 @@ def test_linear_wgrad(ops, M, K, N):
     assert results[0] <= max(tol, 1e-3), f"wgrad variant0 err {results[0]} (variant1 {results[1]})"
 
 
-def _rope_timescale(D, base=10_000.0):
-    return torch.tensor(base, dtype=torch.float32) ** (2.0 * torch.arange(0, D // 2, dtype=torch.float32) / D)
-
-
 @pytest.mark.parametrize("Nq,Nkv", [(4, 1), (4, 2), (4, 4)])
 def test_qkv_rope_train(ops, Nq, Nkv):
     gen = g(5 + Nq + Nkv)
@@ -250,3 +227,119 @@ def test_attn_decode(ops, step, S, Nq, Nkv, Bb):
     pos = torch.full((Bb,), step, dtype=torch.int32, device=DEV)
     out = ops.attn_decode(q.reshape(Bb, -1).to(DEV), kc.to(DEV), vc.to(DEV), pos, Nq, Nkv, D)
     assert_close_bf16(out.reshape(Bb, Nq, D), ref, f"attn_decode step={step} S={S} Nkv={Nkv}")
+
+
+# ---------------------------------------------------------------------------------------------- row-wise / heads
+@pytest.mark.parametrize("M,H", [(5, 128), (1000, 128), (777, 256)])
+def test_rmsnorm_fwd_bwd(ops, M, H):
+    gen = g(M + H)
+    x = torch.randn(M, H, generator=gen).to(BF16)
+    scale = 1.0 + 0.1 * torch.randn(H, generator=gen)
+    y = ops.rmsnorm_fwd(x.to(DEV), scale.to(DEV))
+    assert_close_bf16(y, O.rms_norm(x, scale), f"rmsnorm_fwd {M}x{H}")
+    dy = torch.randn(M, H, generator=gen).to(BF16)
+    dres = torch.randn(M, H, generator=gen).to(BF16)
+    xf = x.float().requires_grad_(True)
+    sf = scale.clone().requires_grad_(True)
+    ms = (xf * xf).mean(-1, keepdim=True)
+    (xf * (torch.rsqrt(ms + 1e-6) * sf) * dy.float()).sum().backward()
+    dscale = torch.zeros(H, dtype=torch.float32, device=DEV)
+    dx = ops.rmsnorm_bwd(dy.to(DEV), x.to(DEV), scale.to(DEV), dscale=dscale, dres=dres.to(DEV))
+    ref_dx = (xf.grad.to(BF16).float() + dres.float()).to(BF16)
+    assert_close_bf16(dx, ref_dx, f"rmsnorm_bwd dx {M}x{H}", rtol=2e-2)
+    torch.testing.assert_close(dscale.cpu(), sf.grad, rtol=2e-3, atol=2e-3 * sf.grad.abs().max().item())
+
+
+def test_glu_bwd_and_gelu_bwd(ops):
+    gen = g(77)
+    M, F = 300, 768
+    u = torch.randn(M, F, generator=gen).to(BF16)
+    gt = torch.randn(M, F, generator=gen).to(BF16)
+    dh = torch.randn(M, F, generator=gen).to(BF16)
+    uf, gf = u.float().requires_grad_(True), gt.float().requires_grad_(True)
+    c = math.sqrt(2.0 / math.pi)
+    a = 0.5 * uf * (1.0 + torch.tanh(c * (uf + 0.044715 * uf ** 3)))
+    (a * gf * dh.float()).sum().backward()
+    dug = ops.glu_bwd(dh.to(DEV), u.to(DEV), gt.to(DEV))
+    assert_close_bf16(dug[:, :F], uf.grad, "glu_bwd du", rtol=3e-2, abs_floor_frac=2e-2)
+    assert_close_bf16(dug[:, F:], gf.grad, "glu_bwd dg", rtol=3e-2, abs_floor_frac=2e-2)
+    z = torch.randn(M, F, generator=gen).to(BF16)
+    zf = z.float().requires_grad_(True)
+    (0.5 * zf * (1.0 + torch.tanh(c * (zf + 0.044715 * zf ** 3))) * dh.float()).sum().backward()
+    dz = ops.gelu_bwd(dh.to(DEV), z.to(DEV))
+    assert_close_bf16(dz, zf.grad, "gelu_bwd", rtol=2e-2, abs_floor_frac=1e-2)
+
+
+def test_rope_inverse_is_transpose(ops):
+    gen = g(5)
+    M, nh, D = 200, 5, 32
+    x = torch.randn(M, nh * D + 32, generator=gen).to(BF16)       # extra 32 untouched columns
+    pos = torch.randint(0, 512, (M,), generator=gen).to(torch.int32)
+    xd = x.clone().to(DEV)
+    ops.rope_(xd, nh * D + 32, pos.to(DEV), _rope_timescale(D).to(DEV), M, nh, D, inverse=False)
+    ref = O.apply_rope(x[:, :nh * D].reshape(M, 1, nh, D), pos[:, None], D).reshape(M, nh * D)
+    assert_close_bf16(xd[:, :nh * D], ref, "rope fwd")
+    assert torch.equal(xd[:, nh * D:].cpu(), x[:, nh * D:])
+    ops.rope_(xd, nh * D + 32, pos.to(DEV), _rope_timescale(D).to(DEV), M, nh, D, inverse=True)
+    assert_close_bf16(xd[:, :nh * D], x[:, :nh * D], "rope inverse(rope(x)) == x", rtol=2e-2, abs_floor_frac=1e-2)
+
+
+def test_policy_logits_and_ppo_loss(ops):
+    gen = g(31)
+    M, H, A = 3000, 128, 6
+    x = torch.randn(M, H, generator=gen).to(BF16)
+    table = torch.randn(A, H, generator=gen) * 0.1
+    mask = torch.rand(M, A, generator=gen) < 0.8
+    mask[:, 0] = True
+    logits = ops.policy_logits(x.to(DEV), table.to(DEV), mask.to(DEV))
+    ref = torch.where(mask, x.float() @ table.t(), torch.tensor(torch.finfo(torch.float32).min))
+    torch.testing.assert_close(logits.cpu(), ref, rtol=1e-4, atol=1e-4)
+    actions = torch.zeros(M, dtype=torch.int32)
+    old_lp = -torch.rand(M, generator=gen) * 2
+    adv = torch.randn(M, generator=gen)
+    lg = ref.clone().requires_grad_(True)
+    lp = O.categorical_log_prob(lg, actions)
+    ratio = torch.exp(lp - old_lp)
+    actor = -torch.minimum(ratio * adv, torch.clamp(ratio, 1 - 0.28, 1 + 0.28) * adv).mean()
+    ent_loss = -O.categorical_entropy(lg).mean()
+    (actor + 0.001 * ent_loss).backward()
+    losses, dl = ops.ppo_policy_loss(logits, actions.to(DEV), old_lp.to(DEV), adv.to(DEV), 0.28, 0.001)
+    torch.testing.assert_close(losses.cpu(), torch.stack([actor.detach(), ent_loss.detach()]), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dl.cpu(), lg.grad, rtol=1e-3, atol=1e-8)
+    # tied-table transpose
+    dtable = torch.zeros(A, H, dtype=torch.float32, device=DEV)
+    dx = ops.policy_head_bwd(dl, x.to(DEV), table.to(DEV), dtable)
+    assert_close_bf16(dx, dl.cpu() @ table, "policy_head_bwd dx", rtol=2e-2, abs_floor_frac=1e-2)
+    torch.testing.assert_close(dtable.cpu(), dl.cpu().t() @ x.float(), rtol=1e-3, atol=1e-6)
+
+
+def test_value_head_hilo(ops):
+    """fp32-weight Linear emulated with a bf16 hi/lo split (values.py:34): ~fp32 accuracy on bf16 activations."""
+    gen = g(41)
+    M, K, N = 500, 768, 51
+    x = torch.randn(M, K, generator=gen).to(BF16)
+    W = torch.randn(K, N, generator=gen) / math.sqrt(K)
+    b = torch.randn(N, generator=gen) * 0.1
+    hi = W.t().to(BF16)
+    lo = (W.t() - hi.float()).to(BF16)
+    wt = torch.zeros(128, K, dtype=BF16)
+    wt[:N] = hi
+    wt[64:64 + N] = lo
+    out = torch.empty(M, N, dtype=torch.float32, device=DEV)
+    ops.linear_f32w(x.to(DEV), wt.to(DEV), b.to(DEV), out, N)
+    ref = x.float() @ W + b
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-4, atol=1e-4)
+
+
+def test_transpose_tb(ops):
+    gen = g(3)
+    T, B = 7, 12
+    src = torch.randint(0, 255, (T, B, 11, 11, 2), generator=gen).to(torch.uint8)
+    perm = torch.randperm(B, generator=gen).to(torch.int32)
+    dst = torch.empty(B, T, 11, 11, 2, dtype=torch.uint8, device=DEV)
+    ops.transpose_tb(src.to(DEV), dst, perm.to(DEV), T, B)
+    assert torch.equal(dst.cpu(), src[:, perm.long()].permute(1, 0, 2, 3, 4))
+    f = torch.randn(T, B, generator=gen)
+    fd = torch.empty(B, T, device=DEV)
+    ops.transpose_tb(f.to(DEV), fd, None, T, B)
+    assert torch.equal(fd.cpu(), f.t())

@@ -1,0 +1,143 @@
+"""GPU parity of the whole policy path (decode rollout, training forward, loss + backward) against the oracle."""
+
+import math
+from dataclasses import replace
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from jaxrl_b200.config import ModelConfig, PPOConfig  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from _util import assert_close_bf16, log as _log  # noqa: E402
+
+DEV = "cuda"
+CFG = ModelConfig(num_layers=2, max_seq_length=64, action_dim=6)
+
+
+def synth(cfg, T, B, seed):
+    gen = torch.Generator().manual_seed(seed)
+    vw, vh, K = cfg.obs_shape
+    obs = torch.stack([torch.randint(0, n, (T + 1, B, vw, vh), generator=gen) for n in cfg.obs_max_value], dim=-1)
+    reward = (torch.rand(T + 1, B, generator=gen) < 0.1).float() * 0.5 + torch.randn(T + 1, B, generator=gen) * 0.05
+    u = torch.rand(T, B, cfg.action_dim, generator=gen).clamp(1e-6, 1 - 1e-6)
+    gumbel = -torch.log(-torch.log(u))
+    mask = torch.rand(T + 1, B, cfg.action_dim, generator=gen) < 0.8
+    mask[..., 0] = True
+    return obs.to(torch.uint8), reward, gumbel, mask
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from jaxrl_b200.engine import PolicyEngine
+    return PolicyEngine(CFG, DEV, seed=3, bias_noise=0.05)
+
+
+def test_policy_sample_bit_exact():
+    """Same logits + same noise => same index (bit exact), log-prob to fp32 tolerance."""
+    from jaxrl_b200 import ops
+    gen = torch.Generator().manual_seed(1)
+    logits = torch.randn(5000, 6, generator=gen) * 3
+    logits[::7, 2] = torch.finfo(torch.float32).min      # masked entries
+    gumbel = -torch.log(-torch.log(torch.rand(5000, 6, generator=gen).clamp(1e-6, 1 - 1e-6)))
+    act, lp = ops.policy_sample(logits.to(DEV), gumbel.to(DEV))
+    ref = O.categorical_sample_gumbel(logits, gumbel)
+    assert torch.equal(act.cpu(), ref)
+    torch.testing.assert_close(lp.cpu(), O.categorical_log_prob(logits, ref), rtol=1e-5, atol=1e-5)
+
+
+def test_decode_rollout_matches_oracle(engine):
+    from jaxrl_b200 import ops
+    cfg, T, B = CFG, 12, 16
+    obs, reward, gumbel, mask = synth(cfg, T, B, 5)
+    p = engine.p.oracle_dict()
+    ref = O.rollout_decode(p, cfg, obs, reward, gumbel, action_mask_seq=mask)
+    ws = engine.alloc_decode(B)
+    engine.reset_carry(ws)
+    obs_d, rew_d, gum_d, mask_d = obs.to(DEV), reward.to(DEV), gumbel.to(DEV), mask.to(DEV)
+    la = torch.zeros(B, dtype=torch.int32, device=DEV)
+    agree = 0
+    for t in range(T):
+        pos = torch.full((B,), t, dtype=torch.int32, device=DEV)
+        logits, vlogits = engine.decode_step(ws, obs_d[t].contiguous(), rew_d[t].contiguous(), la, pos,
+                                             action_mask=mask_d[t].contiguous())
+        act, lp = ops.policy_sample(logits, gum_d[t].contiguous())
+        val = ops.hlgauss_value(vlogits, engine.centers)
+        # recompute the oracle's step-t outputs from its own trajectory (teacher forcing on last_action)
+        agree += (act.cpu() == ref["actions"][:, t]).sum().item()
+        same = act.cpu() == ref["actions"][:, t]
+        torch.testing.assert_close(lp.cpu()[same], ref["log_prob"][:, t][same], rtol=2e-2, atol=2e-2)
+        torch.testing.assert_close(val.cpu(), ref["values"][:, t], rtol=1e-2, atol=2e-2)
+        la = ref["actions"][:, t].to(DEV)
+    frac = agree / (T * B)
+    _log(f"decode rollout: sampled-action agreement {frac:.4f}")
+    assert frac >= 0.97
+    # KV cache contents after T steps
+    for i in range(cfg.num_layers):
+        assert_close_bf16(ws.kcache[i][:, :T], ref["carry"][i].key[:, :T], f"kcache layer {i}", rtol=2e-2)
+        assert_close_bf16(ws.vcache[i][:, :T], ref["carry"][i].value[:, :T], f"vcache layer {i}", rtol=2e-2)
+        assert (ws.kcache[i][:, T:] == 0).all()
+
+
+def _batch(cfg, T, B, seed):
+    obs, reward, gumbel, mask = synth(cfg, T, B, seed)
+    gen = torch.Generator().manual_seed(seed + 100)
+    batch = dict(
+        obs=obs[:T].permute(1, 0, 2, 3, 4).contiguous(), action_mask=mask[:T].permute(1, 0, 2).contiguous(),
+        last_rewards=reward[:T].t().contiguous(),
+        last_actions=torch.randint(0, cfg.action_dim, (B, T), generator=gen).to(torch.int32),
+        actions=torch.zeros(B, T, dtype=torch.int32), terminated=torch.zeros(B, T, dtype=torch.bool),
+        log_prob=-torch.rand(B, T, generator=gen) * 2 - 0.2, advantages=torch.randn(B, T, generator=gen),
+        targets=torch.randn(B, T, generator=gen) * 2)
+    # actions must be unmasked
+    m = batch["action_mask"].float() + 1e-3 * torch.rand(B, T, cfg.action_dim, generator=gen)
+    batch["actions"] = torch.argmax(m * torch.rand(B, T, cfg.action_dim, generator=gen), dim=-1).to(torch.int32)
+    batch["actions"] = torch.where(batch["action_mask"].gather(-1, batch["actions"].long()[..., None])[..., 0],
+                                   batch["actions"], torch.zeros_like(batch["actions"]))
+    return batch
+
+
+def test_train_forward_and_backward_match_oracle(engine):
+    cfg, T, B = CFG, 64, 4
+    hyp = PPOConfig()
+    batch = _batch(cfg, T, B, 9)
+    p = {k: v.clone().requires_grad_(True) for k, v in engine.p.oracle_dict().items()}
+    total, logs = O.ppo_loss(p, cfg, hyp, batch, progress=0.3)
+    total.backward()
+    vl_ref, lg_ref, _ = O.model_forward({k: v.detach() for k, v in p.items()}, cfg,
+                                        O.TimeStep(obs=batch["obs"], time=torch.arange(T, dtype=torch.int32)[None],
+                                                   terminated=batch["terminated"], last_action=batch["last_actions"],
+                                                   reward=batch["last_rewards"], action_mask=batch["action_mask"]))
+    ws = engine.alloc_train(B, T)
+    d = {k: v.to(DEV) for k, v in batch.items()}
+    vlogits, logits = engine.forward_train(ws, d["obs"], d["last_rewards"].reshape(-1), d["last_actions"].reshape(-1),
+                                           action_mask=d["action_mask"])
+    A = cfg.action_dim
+    lg = logits.cpu().reshape(B, T, A)
+    live = batch["action_mask"]
+    assert (lg[~live] == torch.finfo(torch.float32).min).all()
+    assert_close_bf16(lg[live], lg_ref[live], "train logits", rtol=1e-2, abs_floor_frac=2e-2)
+    assert_close_bf16(vlogits.cpu().reshape(B, T, -1), vl_ref, "train vlogits", rtol=1e-2, abs_floor_frac=2e-2)
+    engine.p.grad.zero_()
+    flat = {k: (v.reshape(-1) if v.dim() == 2 and k not in ("obs", "action_mask") else v) for k, v in d.items()}
+    losses = engine.loss_and_backward(ws, flat, hyp, progress=0.3)
+    torch.cuda.synchronize()
+    l = losses.cpu()
+    _log(f"losses gpu value={l[0]:.5f} actor={l[1]:.5f} ent={l[2]:.5f} | ref value={logs['value_loss']:.5f} "
+         f"actor={logs['actor_loss']:.5f} ent={logs['entropy_loss']:.5f}")
+    assert abs(l[0] - logs["value_loss"].item()) <= 2e-2 * abs(logs["value_loss"].item()) + 1e-3
+    assert abs(l[1] - logs["actor_loss"].item()) <= 2e-2 * abs(logs["actor_loss"].item()) + 2e-3
+    assert abs(l[2] - logs["entropy_loss"].item()) <= 2e-2 * abs(logs["entropy_loss"].item()) + 1e-3
+    grads = engine.p.grad_dict()
+    worst = 0.0
+    for name, gref in ((k, v.grad) for k, v in p.items()):
+        gg = grads[name]
+        denom = gref.norm().item() + 1e-8
+        rel = (gg - gref).norm().item() / denom
+        cos = (gg * gref).sum().item() / (gg.norm().item() * gref.norm().item() + 1e-12)
+        _log(f"grad {name}: rel_l2={rel:.4f} cos={cos:.5f} |ref|={denom:.3e}")
+        worst = max(worst, rel)
+        assert cos > 0.99, f"gradient direction mismatch for {name}: cos={cos}"
+        assert rel < 0.1, f"gradient mismatch for {name}: rel l2 {rel}"
