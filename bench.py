@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-agents", type=int, default=None)
+    ap.add_argument("--ncu", action="store_true", help="profiling run: one eager warm pass + ONE eager update, no extras")
     return ap.parse_args()
 
 
@@ -264,6 +265,14 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
+    if args.ncu:
+        trainer = PPOTrainer(run_w, rank=rank, world=world, use_graphs=False)
+        trainer.warmup()
+        torch.cuda.synchronize()
+        trainer.train_step()
+        torch.cuda.synchronize()
+        print(json.dumps({"ncu_run": True, "losses": trainer.logs()}), flush=True)
+        return
     # ---- device-resident arm (value)
     trainer = PPOTrainer(run_w, rank=rank, world=world, use_graphs=not args.no_graphs)
     trainer.warmup()

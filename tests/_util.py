@@ -11,8 +11,11 @@ def log(msg):
         f.write(msg + "\n")
 
 
-def assert_close_bf16(got, ref, name, rtol=1e-2, abs_floor_frac=4e-3):
-    """|got-ref| <= rtol*|ref| + abs_floor_frac*rms(ref) elementwise (bf16 results)."""
+def assert_close_bf16(got, ref, name, rtol=1e-2, abs_floor_frac=4e-3, allow_frac=0.0, max_err_frac=None):
+    """|got-ref| <= rtol*|ref| + abs_floor_frac*rms(ref) elementwise (bf16 results).
+
+    allow_frac: fraction of elements allowed outside that band (bf16 rounding flips upstream of a deep stack);
+    max_err_frac: hard cap on the largest error as a fraction of rms(ref) when allow_frac > 0."""
     got = got.detach().float().cpu()
     ref = ref.detach().float().cpu()
     assert got.shape == ref.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
@@ -22,7 +25,9 @@ def assert_close_bf16(got, ref, name, rtol=1e-2, abs_floor_frac=4e-3):
     tol = rtol * ref.abs() + abs_floor_frac * rms
     bad = (err > tol).float().mean().item()
     log(f"{name}: max_abs_err={err.max().item():.4e} rms_ref={rms:.4e} frac_bad={bad:.3e}")
-    assert bad == 0.0, f"{name}: {bad * 100:.4f}% elements out of tolerance, max err {err.max().item():.4e} (rms {rms:.3e})"
+    assert bad <= allow_frac, f"{name}: {bad * 100:.4f}% elements out of tolerance, max err {err.max().item():.4e} (rms {rms:.3e})"
+    if allow_frac > 0 and max_err_frac is not None:
+        assert err.max().item() <= max_err_frac * rms, f"{name}: max err {err.max().item():.4e} > {max_err_frac} * rms {rms:.3e}"
 
 
 def rope_timescale(D, base=10_000.0):
