@@ -29,7 +29,8 @@ enum { MPX_OK = 0, MPX_ERR_INVALID = -1, MPX_ERR_CUDA = -2, MPX_ERR_UNSUPPORTED 
 
 const char* mpx_last_error(void);
 int mpx_version(void);
-/* Debug/tuning knobs (tests only). key 0: swap LBO/SBO in MN-major UMMA descriptors. */
+/* Debug/tuning knobs (tests only). key 0: swap LBO/SBO in MN-major UMMA descriptors.
+ * key 1: decode attention implementation (0 = mma.sync, default; 1 = SIMT v1). */
 int mpx_debug_set(int key, int value);
 
 /* ---------------------------------------------------------------------------------------------- GAE
@@ -237,6 +238,12 @@ int mpx_policy_head_bwd(const float* dlogits, const mpx_bf16* x, const float* ta
 int mpx_obs_onehot_im2col(const uint8_t* obs, mpx_bf16* out, long long M, int IH, int IW, int K,
                           const int* onehot_sizes /* host array [K] */, int kh, int kw, int sh, int sw, int KP,
                           mpx_stream_t stream);
+/* First conv layer evaluated directly on the uint8 observation (gather-sum of kernel rows selected by the one-hot,
+ * fp32 accumulate == the GEMM on the one-hot rows): a_out (M*OH*OW, cout) = [gelu](bf16(conv) + bias), z_out
+ * (nullable) = the bf16 pre-activation.  w is the bf16 kernel as stored, (kh*kw*C, cout); cout % 8 == 0. */
+int mpx_conv1_onehot_fwd(const uint8_t* obs, const mpx_bf16* w, const mpx_bf16* bias, mpx_bf16* z_out, mpx_bf16* a_out,
+                         long long M, int IH, int IW, int K, const int* onehot_sizes, int kh, int kw, int sh, int sw,
+                         int cout, int apply_gelu, mpx_stream_t stream);
 /* NHWC im2col / its transpose for the hidden conv layers (C % 8 == 0, VALID padding). */
 int mpx_im2col(const mpx_bf16* a, mpx_bf16* x, long long M, int IH, int IW, int C, int kh, int kw, int sh, int sw,
                mpx_stream_t stream);

@@ -26,6 +26,7 @@ int num_sms() {
 }
 
 extern int g_debug_swap_lbo_sbo;
+extern int g_attn_decode_impl;
 
 }  // namespace mpx
 
@@ -34,6 +35,10 @@ extern "C" int mpx_version(void) { return 100; }
 extern "C" int mpx_debug_set(int key, int value) {
   if (key == 0) {
     mpx::g_debug_swap_lbo_sbo = value;
+    return MPX_OK;
+  }
+  if (key == 1) {
+    mpx::g_attn_decode_impl = value;
     return MPX_OK;
   }
   mpx::set_error("mpx_debug_set: unknown key %d", key);

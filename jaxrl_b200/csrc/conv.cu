@@ -13,35 +13,96 @@ struct OneHotSpec {
   int offs[5];      // prefix sums of the per-component one-hot sizes; offs[K] = C (total channels)
 };
 
-// out (M*OH*OW, KP) bf16, KP = round_up(kh*kw*C, 8); one thread per 8 output columns (one 16-byte store).
-__global__ void onehot_im2col_kernel(const uint8_t* __restrict__ obs, __nv_bfloat16* __restrict__ out, long long M,
-                                     int IH, int IW, OneHotSpec spec, int kh, int kw, int sh, int sw, int OH, int OW,
-                                     int KP) {
+// out (M*OH*OW, KP) bf16, KP = round_up(kh*kw*C, 8).  A block builds OHI_ROWS rows in shared memory: zero fill,
+// one 2-byte store per (row, tap, component), then coalesced 16-byte copies out.
+constexpr int OHI_ROWS = 32;
+__global__ void __launch_bounds__(128) onehot_im2col_kernel(const uint8_t* __restrict__ obs, __nv_bfloat16* __restrict__ out,
+                                                            long long rows_total, int IH, int IW, OneHotSpec spec, int kh,
+                                                            int kw, int sh, int sw, int OH, int OW, int KP) {
+  extern __shared__ __align__(16) uint8_t ohi_smem[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(ohi_smem);   // [OHI_ROWS][KP]
   const int C = spec.offs[spec.K];
+  const int taps = kh * kw;
   const int pieces = KP / 8;
-  const long long total = M * OH * OW * pieces;
+  for (long long row0 = (long long)blockIdx.x * OHI_ROWS; row0 < rows_total; row0 += (long long)gridDim.x * OHI_ROWS) {
+    const int nrows = (int)min((long long)OHI_ROWS, rows_total - row0);
+    for (int i = threadIdx.x; i < OHI_ROWS * pieces; i += blockDim.x)
+      reinterpret_cast<uint4*>(tile)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nrows * taps * spec.K; i += blockDim.x) {
+      const int kc = i % spec.K;
+      const int tap = (i / spec.K) % taps;
+      const int r = i / (spec.K * taps);
+      const long long row = row0 + r;
+      const int ox = (int)(row % OW);
+      const int oy = (int)((row / OW) % OH);
+      const long long m = row / ((long long)OW * OH);
+      const int ky = tap / kw, kx = tap % kw;
+      const int val = obs[((m * IH + (oy * sh + ky)) * IW + (ox * sw + kx)) * spec.K + kc];
+      if (val < spec.offs[kc + 1] - spec.offs[kc]) tile[r * KP + tap * C + spec.offs[kc] + val] = __float2bfloat16_rn(1.0f);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nrows * pieces; i += blockDim.x)
+      reinterpret_cast<uint4*>(out + row0 * KP)[i] = reinterpret_cast<const uint4*>(tile)[i];
+    __syncthreads();
+  }
+}
+
+// First conv layer on the one-hot observation WITHOUT materialising it: out[row][c] = sum over (tap, component) of
+// W[tap*C + offs[comp] + obs][c]  (fp32 sum of exact bf16 weights == the GEMM on the one-hot rows), then
+// bf16 round, + bias (bf16), optional pre-activation save, gelu (bf16).  One thread per (row, 8 output channels).
+__global__ void __launch_bounds__(256) conv1_onehot_fwd_kernel(
+    const uint8_t* __restrict__ obs, const __nv_bfloat16* __restrict__ w /* (taps*C, cout) */,
+    const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ z_out, __nv_bfloat16* __restrict__ a_out,
+    long long rows_total, int IH, int IW, OneHotSpec spec, int kh, int kw, int sh, int sw, int OH, int OW, int cout,
+    int apply_gelu) {
+  extern __shared__ __align__(16) uint8_t c1_smem[];
+  __nv_bfloat16* sw_ = reinterpret_cast<__nv_bfloat16*>(c1_smem);
+  const int C = spec.offs[spec.K];
+  const int taps = kh * kw;
+  for (int i = threadIdx.x; i < taps * C * cout / 8; i += blockDim.x)
+    reinterpret_cast<uint4*>(sw_)[i] = reinterpret_cast<const uint4*>(w)[i];
+  __syncthreads();
+  const int cg = cout / 8;
+  const long long total = rows_total * cg;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
-    const int piece = (int)(i % pieces);
-    long long row = i / pieces;
+    const int c8 = (int)(i % cg);
+    const long long row = i / cg;
     const int ox = (int)(row % OW);
     const int oy = (int)((row / OW) % OH);
     const long long m = row / ((long long)OW * OH);
-    uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int col = piece * 8 + e;
-      if (col < kh * kw * C) {
-        const int tap = col / C, ch = col % C;
-        const int ky = tap / kw, kx = tap % kw;
-        int kcomp = 0;
-        while (kcomp + 1 < spec.K && ch >= spec.offs[kcomp + 1]) ++kcomp;
-        const int val = obs[((m * IH + (oy * sh + ky)) * IW + (ox * sw + kx)) * spec.K + kcomp];
-        if (val == ch - spec.offs[kcomp]) w[e >> 1] |= (e & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int ky = 0; ky < kh; ++ky) {
+      for (int kx = 0; kx < kw; ++kx) {
+        const uint8_t* cell = obs + ((m * IH + (oy * sh + ky)) * IW + (ox * sw + kx)) * spec.K;
+        const int tap = ky * kw + kx;
+        for (int kc = 0; kc < spec.K; ++kc) {
+          const int val = cell[kc];
+          if (val < spec.offs[kc + 1] - spec.offs[kc]) {
+            const uint4 wv = *reinterpret_cast<const uint4*>(sw_ + (tap * C + spec.offs[kc] + val) * cout + c8 * 8);
+            acc[0] += bf16_lo(wv.x); acc[1] += bf16_hi(wv.x); acc[2] += bf16_lo(wv.y); acc[3] += bf16_hi(wv.y);
+            acc[4] += bf16_lo(wv.z); acc[5] += bf16_hi(wv.z); acc[6] += bf16_lo(wv.w); acc[7] += bf16_hi(wv.w);
+          }
+        }
       }
     }
-    *reinterpret_cast<uint4*>(out + row * KP + piece * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    const uint4 bv = *reinterpret_cast<const uint4*>(bias + c8 * 8);
+    const float b[8] = {bf16_lo(bv.x), bf16_hi(bv.x), bf16_lo(bv.y), bf16_hi(bv.y),
+                        bf16_lo(bv.z), bf16_hi(bv.z), bf16_lo(bv.w), bf16_hi(bv.w)};
+    float zf[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) zf[e] = bf16_round(bf16_round(acc[e]) + b[e]);
+    if (z_out)
+      *reinterpret_cast<uint4*>(z_out + row * cout + c8 * 8) =
+          make_uint4(pack_bf16(zf[0], zf[1]), pack_bf16(zf[2], zf[3]), pack_bf16(zf[4], zf[5]), pack_bf16(zf[6], zf[7]));
+    if (apply_gelu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) zf[e] = gelu_tanh(zf[e]);
+    }
+    *reinterpret_cast<uint4*>(a_out + row * cout + c8 * 8) =
+        make_uint4(pack_bf16(zf[0], zf[1]), pack_bf16(zf[2], zf[3]), pack_bf16(zf[4], zf[5]), pack_bf16(zf[6], zf[7]));
   }
 }
 
@@ -122,9 +183,37 @@ extern "C" int mpx_obs_onehot_im2col(const uint8_t* obs, mpx_bf16* out, long lon
   MPX_REQUIRE(KP % 8 == 0 && KP >= kh * kw * C, "mpx_obs_onehot_im2col: KP=%d must be a multiple of 8 >= %d", KP, kh * kw * C);
   MPX_REQUIRE(IH >= kh && IW >= kw && sh > 0 && sw > 0, "mpx_obs_onehot_im2col: bad geometry");
   const int OH = (IH - kh) / sh + 1, OW = (IW - kw) / sw + 1;
-  onehot_im2col_kernel<<<cv_grid(M * OH * OW * (KP / 8)), 256, 0, (cudaStream_t)stream>>>(
-      obs, reinterpret_cast<__nv_bfloat16*>(out), M, IH, IW, spec, kh, kw, sh, sw, OH, OW, KP);
+  const long long rows = M * OH * OW;
+  long long g = (rows + OHI_ROWS - 1) / OHI_ROWS;
+  const long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  const size_t smem = (size_t)OHI_ROWS * KP * 2;
+  MPX_REQUIRE(smem <= 48 * 1024, "mpx_obs_onehot_im2col: KP=%d too wide", KP);
+  onehot_im2col_kernel<<<(int)g, 128, smem, (cudaStream_t)stream>>>(obs, reinterpret_cast<__nv_bfloat16*>(out), rows, IH,
+                                                                   IW, spec, kh, kw, sh, sw, OH, OW, KP);
   return check_launch("mpx_obs_onehot_im2col");
+}
+
+extern "C" int mpx_conv1_onehot_fwd(const uint8_t* obs, const mpx_bf16* w, const mpx_bf16* bias, mpx_bf16* z_out,
+                                    mpx_bf16* a_out, long long M, int IH, int IW, int K, const int* onehot_sizes, int kh,
+                                    int kw, int sh, int sw, int cout, int apply_gelu, mpx_stream_t stream) {
+  MPX_REQUIRE(obs && w && bias && a_out && onehot_sizes && M > 0, "mpx_conv1_onehot_fwd: bad arguments");
+  MPX_REQUIRE(K >= 1 && K <= 4 && cout % 8 == 0, "mpx_conv1_onehot_fwd: K=%d / cout=%d unsupported", K, cout);
+  MPX_REQUIRE(IH >= kh && IW >= kw && sh > 0 && sw > 0, "mpx_conv1_onehot_fwd: bad geometry");
+  OneHotSpec spec;
+  spec.K = K;
+  spec.offs[0] = 0;
+  for (int i = 0; i < K; ++i) spec.offs[i + 1] = spec.offs[i] + onehot_sizes[i];
+  const int C = spec.offs[K];
+  const size_t smem = (size_t)kh * kw * C * cout * 2;
+  MPX_REQUIRE(smem <= 48 * 1024 && (kh * kw * C * cout) % 8 == 0, "mpx_conv1_onehot_fwd: kernel too large for shared memory");
+  const int OH = (IH - kh) / sh + 1, OW = (IW - kw) / sw + 1;
+  const long long rows = M * OH * OW;
+  conv1_onehot_fwd_kernel<<<cv_grid(rows * (cout / 8)), 256, smem, (cudaStream_t)stream>>>(
+      obs, reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<const __nv_bfloat16*>(bias),
+      reinterpret_cast<__nv_bfloat16*>(z_out), reinterpret_cast<__nv_bfloat16*>(a_out), rows, IH, IW, spec, kh, kw, sh, sw,
+      OH, OW, cout, apply_gelu);
+  return check_launch("mpx_conv1_onehot_fwd");
 }
 
 extern "C" int mpx_im2col(const mpx_bf16* a, mpx_bf16* x, long long M, int IH, int IW, int C, int kh, int kw, int sh,

@@ -198,14 +198,29 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ x, long long ld, const i
 
 // ------------------------------------------------------------------------------------------------ column sums
 // out[N] (fp32, atomically accumulated) += sum over rows of x (M, ld) bf16 columns [0,N).
-__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long M, int N,
-                              float* __restrict__ out, int rows_per_block) {
+// Block = 256 threads as (256/CW row lanes) x (CW column lanes), CW = 32 or 64 columns per pass; a block owns a
+// strip of rows, every warp reads contiguous column runs; partials meet in shared memory, one atomic per column.
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long M,
+                                                     int N, float* __restrict__ out, int rows_per_block) {
+  __shared__ float s_part[256];
+  const int CW = N >= 64 ? 64 : 32;
+  const int RL = 256 / CW;
+  const int cl = threadIdx.x % CW, rl = threadIdx.x / CW;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = min(M, r0 + (long long)rows_per_block);
-  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+  for (int c0 = 0; c0 < N; c0 += CW) {
+    const int c = c0 + cl;
     float acc = 0.f;
-    for (long long r = r0; r < r1; ++r) acc += __bfloat162float(x[r * ld + c]);
-    atomicAdd(out + c, acc);
+    if (c < N)
+      for (long long r = r0 + rl; r < r1; r += RL) acc += __bfloat162float(x[r * ld + c]);
+    s_part[threadIdx.x] = acc;
+    __syncthreads();
+    if (rl == 0 && c < N) {
+      float t = 0.f;
+      for (int k = 0; k < RL; ++k) t += s_part[k * CW + cl];
+      atomicAdd(out + c, t);
+    }
+    __syncthreads();
   }
 }
 
@@ -303,11 +318,10 @@ extern "C" int mpx_rope(mpx_bf16* x, long long ld, const int32_t* pos, int pos_l
 extern "C" int mpx_colsum(const mpx_bf16* x, long long ld, long long M, int N, float* out, mpx_stream_t stream) {
   MPX_REQUIRE(x && out && M > 0 && N > 0, "mpx_colsum: bad arguments");
   int rows_per_block = (int)((M + (long long)num_sms() * 4 - 1) / ((long long)num_sms() * 4));
-  if (rows_per_block < 32) rows_per_block = 32;
+  if (rows_per_block < 64) rows_per_block = 64;
   const int grid = (int)((M + rows_per_block - 1) / rows_per_block);
-  const int threads = N >= 256 ? 256 : (N >= 128 ? 128 : 64);
-  colsum_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, M, N, out,
-                                                            rows_per_block);
+  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, M, N, out,
+                                                        rows_per_block);
   return check_launch("mpx_colsum");
 }
 

@@ -97,7 +97,14 @@ __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, float (&f
 
 // ------------------------------------------------------------------------------------------------ epilogues
 // Each epilogue thread owns one output row; `acc` holds 32 consecutive fp32 columns starting at `col0`.
-__device__ __forceinline__ void epi_store(const GemmParams& p, int row, int col0, const uint32_t (&acc)[32]) {
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+
+// rpre: this chunk's residual, already in registers (4 x uint4), or nullptr.
+__device__ __forceinline__ void epi_store(const GemmParams& p, int row, int col0, const uint32_t (&acc)[32],
+                                          const uint4* rpre = nullptr) {
   if (row >= p.M || col0 >= p.N) return;
   const bool full = (col0 + 32 <= p.N);
   if (p.y_f32) {
@@ -116,9 +123,17 @@ __device__ __forceinline__ void epi_store(const GemmParams& p, int row, int col0
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = bf16_round(__uint_as_float(acc[i]));
   if (p.bias) {
+    if (full && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+      float b[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (col0 + i < p.N) f[i] = bf16_round(f[i] + __bfloat162float(p.bias[col0 + i]));
+      for (int i = 0; i < 4; ++i) unpack8(reinterpret_cast<const uint4*>(p.bias + col0)[i], b + 8 * i);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = bf16_round(f[i] + b[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) f[i] = bf16_round(f[i] + __bfloat162float(p.bias[col0 + i]));
+    }
   }
   if (p.y_pre) {
     __nv_bfloat16* dp = p.y_pre + (long long)row * p.ldy + col0;
@@ -132,7 +147,13 @@ __device__ __forceinline__ void epi_store(const GemmParams& p, int row, int col0
   const bool vec_ok = full && ((p.ldy & 7) == 0) && (!p.residual || (p.ldr & 7) == 0);
   if (p.residual) {
     const __nv_bfloat16* r = p.residual + (long long)row * p.ldr + col0;
-    if (vec_ok) {
+    if (rpre) {
+      float rf[32];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) unpack8(rpre[i], rf + 8 * i);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = f[i] + rf[i];
+    } else if (vec_ok) {
       float rf[32];
       load_bf16x32(r, rf);
 #pragma unroll
@@ -325,6 +346,18 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
           for (int i = 0; i < 16; ++i) sincosf(pf / p.timescale[i], &sn[i], &cs[i]);
         }
       }
+      // residual rows of this tile are fetched BEFORE waiting for the accumulator (hides the global-load latency)
+      constexpr int kPre = (EPI == EPI_STORE && BLOCK_N <= 128) ? BLOCK_N / 8 : 1;
+      uint4 rpre[kPre];
+      bool have_pre = false;
+      if constexpr (EPI == EPI_STORE && BLOCK_N <= 128) {
+        if (p.residual && p.y && row < p.M && (p.ldr & 7) == 0 && (p.ldy & 7) == 0 && (n_blk + 1) * BLOCK_N <= p.N) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + (long long)row * p.ldr + n_blk * BLOCK_N);
+#pragma unroll
+          for (int i = 0; i < kPre; ++i) rpre[i] = r4[i];
+          have_pre = true;
+        }
+      }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BLOCK_N;
@@ -346,6 +379,14 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
           tmem_ld_32x32(t_row + 64 + c, lo);
           tmem_ld_wait();
           epi_pairsum(p, row, c, hi, lo);
+        }
+      } else if constexpr (EPI == EPI_STORE && BLOCK_N <= 128) {
+#pragma unroll
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t acc[32];
+          tmem_ld_32x32(t_row + c, acc);
+          tmem_ld_wait();
+          epi_store(p, row, n_blk * BLOCK_N + c, acc, have_pre ? &rpre[c / 8] : nullptr);
         }
       } else {
 #pragma unroll 1
@@ -602,12 +643,14 @@ extern "C" int mpx_linear(const mpx_linear_args* a, mpx_stream_t stream) {
   p.y_pre = reinterpret_cast<__nv_bfloat16*>(a->y_pre);
   MPX_REQUIRE(!a->y_pre || a->y, "mpx_linear: y_pre requires y");
   cudaStream_t s = (cudaStream_t)stream;
-  if (a->N <= 64) return launch_tn<64, EPI_STORE>(p, a->x, a->ldx, a->wt, a->ldw, s);
-  if (a->N <= 128) return launch_tn<128, EPI_STORE>(p, a->x, a->ldx, a->wt, a->ldw, s);
-  // wide outputs: 256-column tiles unless that leaves most SMs idle
-  const int tiles256 = ceil_div(a->M, BLOCK_M) * ceil_div(a->N, 256);
-  if (tiles256 >= num_sms() / 2) return launch_tn<256, EPI_STORE>(p, a->x, a->ldx, a->wt, a->ldw, s);
-  return launch_tn<128, EPI_STORE>(p, a->x, a->ldx, a->wt, a->ldw, s);
+  // widest N tile that still gives the machine enough CTAs (small-M decode GEMMs are latency bound: more, narrower
+  // tiles shorten both the K loop's exposed latency and the epilogue)
+  const int mt = ceil_div(a->M, BLOCK_M);
+  const int want = (num_sms() * 3) / 5;
+  if (a->N > 128 && mt * ceil_div(a->N, 256) >= want) return launch_tn<256, EPI_STORE>(p, a->x, a->ldx, a->wt, a->ldw, s);
+  if (a->N > 64 && mt * ceil_div(a->N, 128) >= want) return launch_tn<128, EPI_STORE>(p, a->x, a->ldx, a->wt, a->ldw, s);
+  if (a->N > 32 && mt * ceil_div(a->N, 64) >= want) return launch_tn<64, EPI_STORE>(p, a->x, a->ldx, a->wt, a->ldw, s);
+  return launch_tn<32, EPI_STORE>(p, a->x, a->ldx, a->wt, a->ldw, s);
 }
 
 extern "C" int mpx_linear_wgrad(const mpx_wgrad_args* a, mpx_stream_t stream) {
@@ -637,10 +680,13 @@ extern "C" int mpx_qkv_rope(const mpx_qkv_rope_args* a, mpx_stream_t stream) {
   MPX_REQUIRE((a->q_row_stride % 8) == 0 && (a->k_row_stride % 8) == 0 && (a->v_row_stride % 8) == 0,
               "mpx_qkv_rope: q/k/v row strides must be multiples of 8");
   cudaStream_t s = (cudaStream_t)stream;
-  if (N <= 64) return launch_tn<64, EPI_QKV>(p, a->x, a->ldx, a->wt_qkv, a->H, s);
-  if (N <= 128) return launch_tn<128, EPI_QKV>(p, a->x, a->ldx, a->wt_qkv, a->H, s);
-  if (N <= 192) return launch_tn<192, EPI_QKV>(p, a->x, a->ldx, a->wt_qkv, a->H, s);
-  return launch_tn<256, EPI_QKV>(p, a->x, a->ldx, a->wt_qkv, a->H, s);
+  const int mt = ceil_div(a->M, BLOCK_M);
+  const int want = (num_sms() * 3) / 5;
+  if (N > 192 && mt * ceil_div(N, 256) >= want) return launch_tn<256, EPI_QKV>(p, a->x, a->ldx, a->wt_qkv, a->H, s);
+  if (N > 128 && N <= 192 && mt >= want) return launch_tn<192, EPI_QKV>(p, a->x, a->ldx, a->wt_qkv, a->H, s);
+  if (N > 64 && mt * ceil_div(N, 128) >= want) return launch_tn<128, EPI_QKV>(p, a->x, a->ldx, a->wt_qkv, a->H, s);
+  if (N > 32 && mt * ceil_div(N, 64) >= want) return launch_tn<64, EPI_QKV>(p, a->x, a->ldx, a->wt_qkv, a->H, s);
+  return launch_tn<32, EPI_QKV>(p, a->x, a->ldx, a->wt_qkv, a->H, s);
 }
 
 extern "C" int mpx_glu_up(const mpx_glu_up_args* a, mpx_stream_t stream) {

@@ -250,36 +250,63 @@ __global__ void ppo_loss_finalize_kernel(const double* __restrict__ partials, in
 // ------------------------------------------------------------------------------------------------ policy head bwd
 // dx[m][h] = bf16( sum_a dlogits[m][a] * table[a][h] ) (+ dx_other in bf16 if given) ;
 // dtable[a][h] += sum_m dlogits[m][a] * f32(x[m][h]).   Masked logits are constants: dlogits is zero there.
-__global__ void policy_head_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ x,
-                                       const float* __restrict__ table, const __nv_bfloat16* __restrict__ dx_other,
-                                       __nv_bfloat16* __restrict__ dx, float* __restrict__ dtable, long long M, int H,
-                                       int A, int rows_per_block) {
-  extern __shared__ float s_buf[];   // [A][H] table, then per-row dlogits [A]
+// One warp per token row, lane owns HPL = H/32 feature columns; dtable partials live in registers (AMAX x HPL),
+// meet in shared memory per block, one atomic per table entry per block.
+template <int AMAX, int HPL>
+__global__ void __launch_bounds__(HD_WARPS * 32) policy_head_bwd_kernel(
+    const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ x, const float* __restrict__ table,
+    const __nv_bfloat16* __restrict__ dx_other, __nv_bfloat16* __restrict__ dx, float* __restrict__ dtable, long long M,
+    int A) {
+  constexpr int H = HPL * 32;
+  extern __shared__ float s_buf[];   // [A][H] table, then [A][H] reduction buffer
   float* s_table = s_buf;
-  float* s_dl = s_buf + A * H;
-  for (int i = threadIdx.x; i < A * H; i += blockDim.x) s_table[i] = table[i];
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  const long long r1 = min(M, r0 + (long long)rows_per_block);
-  float dt[MAX_A];
-#pragma unroll
-  for (int a = 0; a < MAX_A; ++a) dt[a] = 0.f;
-  const int h = threadIdx.x;    // blockDim.x == H
-  for (long long m = r0; m < r1; ++m) {
-    __syncthreads();
-    if (threadIdx.x < A) s_dl[threadIdx.x] = dlogits[m * A + threadIdx.x];
-    __syncthreads();
-    const float xv = __bfloat162float(x[m * H + h]);
-    float acc = 0.f;
-#pragma unroll 8
-    for (int a = 0; a < A; ++a) {
-      acc = fmaf(s_dl[a], s_table[a * H + h], acc);
-      dt[a] = fmaf(s_dl[a], xv, dt[a]);
-    }
-    float o = bf16_round(acc);
-    if (dx_other) o += __bfloat162float(dx_other[m * H + h]);
-    dx[m * H + h] = __float2bfloat16_rn(o);
+  float* s_red = s_buf + A * H;
+  for (int i = threadIdx.x; i < A * H; i += blockDim.x) {
+    s_table[i] = table[i];
+    s_red[i] = 0.f;
   }
-  for (int a = 0; a < A; ++a) atomicAdd(dtable + a * H + h, dt[a]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  float dt[AMAX][HPL];
+#pragma unroll
+  for (int a = 0; a < AMAX; ++a)
+#pragma unroll
+    for (int j = 0; j < HPL; ++j) dt[a][j] = 0.f;
+  long long row = (long long)blockIdx.x * HD_WARPS + (threadIdx.x >> 5);
+  const long long stride = (long long)gridDim.x * HD_WARPS;
+  for (; row < M; row += stride) {
+    float xv[HPL], acc[HPL];
+#pragma unroll
+    for (int j = 0; j < HPL; ++j) {
+      xv[j] = __bfloat162float(x[row * H + j * 32 + lane]);
+      acc[j] = 0.f;
+    }
+    const float dl_mine = lane < A ? dlogits[row * A + lane] : 0.f;
+#pragma unroll
+    for (int a = 0; a < AMAX; ++a) {
+      if (a < A) {
+        const float d = __shfl_sync(0xffffffffu, dl_mine, a);
+#pragma unroll
+        for (int j = 0; j < HPL; ++j) {
+          acc[j] = fmaf(d, s_table[a * H + j * 32 + lane], acc[j]);
+          dt[a][j] = fmaf(d, xv[j], dt[a][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < HPL; ++j) {
+      float o = bf16_round(acc[j]);
+      if (dx_other) o += __bfloat162float(dx_other[row * H + j * 32 + lane]);
+      dx[row * H + j * 32 + lane] = __float2bfloat16_rn(o);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < AMAX; ++a)
+    if (a < A)
+#pragma unroll
+      for (int j = 0; j < HPL; ++j) atomicAdd(&s_red[a * H + j * 32 + lane], dt[a][j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < A * H; i += blockDim.x) atomicAdd(dtable + i, s_red[i]);
 }
 
 }  // namespace mpx
@@ -368,17 +395,34 @@ extern "C" int mpx_ppo_policy_loss(const float* logits, const int32_t* actions, 
   return check_launch("mpx_ppo_policy_loss");
 }
 
+template <int AMAX>
+static int launch_phb(const float* dlogits, const __nv_bfloat16* x, const float* table, const __nv_bfloat16* dx_other,
+                      __nv_bfloat16* dx, float* dtable, long long M, int H, int A, cudaStream_t s) {
+  const size_t smem = (size_t)2 * A * H * sizeof(float);
+  if (smem > 48 * 1024) {
+    set_error("mpx_policy_head_bwd: table too large for shared memory");
+    return MPX_ERR_UNSUPPORTED;
+  }
+  long long g = (M + HD_WARPS - 1) / HD_WARPS;
+  const long long cap = (long long)num_sms() * 2;
+  const int grid = (int)(g < cap ? g : cap);
+  switch (H / 32) {
+    case 4: policy_head_bwd_kernel<AMAX, 4><<<grid, HD_WARPS * 32, smem, s>>>(dlogits, x, table, dx_other, dx, dtable, M, A); break;
+    case 8: policy_head_bwd_kernel<AMAX, 8><<<grid, HD_WARPS * 32, smem, s>>>(dlogits, x, table, dx_other, dx, dtable, M, A); break;
+    default: set_error("mpx_policy_head_bwd: H=%d unsupported (128 or 256)", H); return MPX_ERR_UNSUPPORTED;
+  }
+  return check_launch("mpx_policy_head_bwd");
+}
+
 extern "C" int mpx_policy_head_bwd(const float* dlogits, const mpx_bf16* x, const float* table, const mpx_bf16* dx_other,
                                    mpx_bf16* dx, float* dtable, long long M, int H, int A, mpx_stream_t stream) {
   MPX_REQUIRE(dlogits && x && table && dx && dtable && M > 0, "mpx_policy_head_bwd: bad arguments");
-  MPX_REQUIRE(A > 0 && A <= MAX_A && H >= 32 && H <= 1024, "mpx_policy_head_bwd: unsupported A=%d / H=%d", A, H);
-  int rows = (int)((M + (long long)num_sms() * 4 - 1) / ((long long)num_sms() * 4));
-  if (rows < 16) rows = 16;
-  const int grid = (int)((M + rows - 1) / rows);
-  const size_t smem = ((size_t)A * H + A) * sizeof(float);
-  MPX_REQUIRE(smem <= 48 * 1024, "mpx_policy_head_bwd: table too large for shared memory");
-  policy_head_bwd_kernel<<<grid, H, smem, (cudaStream_t)stream>>>(
-      dlogits, reinterpret_cast<const __nv_bfloat16*>(x), table, reinterpret_cast<const __nv_bfloat16*>(dx_other),
-      reinterpret_cast<__nv_bfloat16*>(dx), dtable, M, H, A, rows);
-  return check_launch("mpx_policy_head_bwd");
+  MPX_REQUIRE(A > 0 && A <= MAX_A, "mpx_policy_head_bwd: unsupported A=%d", A);
+  auto X = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto DO = reinterpret_cast<const __nv_bfloat16*>(dx_other);
+  auto DX = reinterpret_cast<__nv_bfloat16*>(dx);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (A <= 8) return launch_phb<8>(dlogits, X, table, DO, DX, dtable, M, H, A, s);
+  if (A <= 16) return launch_phb<16>(dlogits, X, table, DO, DX, dtable, M, H, A, s);
+  return launch_phb<32>(dlogits, X, table, DO, DX, dtable, M, H, A, s);
 }

@@ -152,8 +152,10 @@ class PolicyEngine:
         ws.cx, ws.cz, ws.ca = [], [], []
         for c in self.conv:
             rows = M * c.oh * c.ow
-            # the last conv covers the whole remaining map: its im2col is the flattened previous activation
-            ws.cx.append(e(rows, c.kp) if c.j < n - 1 else None)
+            # the last conv covers the whole remaining map: its im2col is the flattened previous activation;
+            # the first conv reads the uint8 observation directly (its one-hot im2col is only built for the
+            # weight gradient, in training)
+            ws.cx.append(e(rows, c.kp) if (c.j < n - 1 and (c.j > 0 or train)) else None)
             ws.cz.append(e(rows, c.cout) if (train and c.j < n - 1) else None)
             ws.ca.append(e(rows, c.cout))
         ws.x0 = e(M, self.H)
@@ -222,9 +224,13 @@ class PolicyEngine:
         prev = None
         for c in self.conv:
             last = c.j == n - 1
-            if c.j == 0:
-                ops.obs_onehot_im2col(obs, ws.cx[0], M, c.ih, c.iw, cfg.obs_max_value, c.kh, c.kw, c.sh, c.sw)
-                xin = ws.cx[0]
+            if c.j == 0 and not last:
+                ops.conv1_onehot_fwd(obs, w["w_c0"], w["b_c0"], ws.ca[0], M, c.ih, c.iw, cfg.obs_max_value, c.kh, c.kw,
+                                     c.sh, c.sw, c.cout, z_out=ws.cz[0] if train else None, gelu=True)
+                prev = ws.ca[0]
+                continue
+            elif c.j == 0:
+                raise _lib.MpxError("a single-layer grid_cnn encoder is not supported")
             elif last:
                 xin = prev.view(M, c.kp) if c.kp == c.k else None
                 if xin is None:
@@ -242,7 +248,7 @@ class PolicyEngine:
                           t_table, out=out)
         return out
 
-    def _embed_bwd(self, ws, M: int, dx0, reward, last_action, task_ids):
+    def _embed_bwd(self, ws, M: int, dx0, reward, last_action, task_ids, obs):
         p, w = self.p, self.w
         gt = p.gviews.get("task_embedder.embedding_table") if task_ids is not None else None
         ops.embed_bwd(dx0, reward, last_action, task_ids if gt is not None else None, self.A, self.cfg.task_count,
@@ -256,6 +262,8 @@ class PolicyEngine:
             if not last:
                 ops.gelu_bwd(dy, ws.cz[c.j], out=dy)          # dz in place
             ops.colsum(dy, p.g(f"obs_encoder.layers.{c.j}.bias"), M=rows, N=c.cout, ld=c.cout)
+            if c.j == 0:      # one-hot im2col rows are only needed here, for the weight gradient
+                ops.obs_onehot_im2col(obs, ws.cx[0], M, c.ih, c.iw, self.cfg.obs_max_value, c.kh, c.kw, c.sh, c.sw)
             xin = ws.ca[c.j - 1].view(M, c.kp) if last else ws.cx[c.j]
             ops.linear_wgrad(xin, dy, p.g(f"obs_encoder.layers.{c.j}.kernel").view(c.k, c.cout), M=rows, K=c.k,
                              N=c.cout, ldx=c.kp, ldy=c.cout, lddw=c.cout)
@@ -380,5 +388,5 @@ class PolicyEngine:
             ops.rmsnorm_bwd(ws.dxn, ws.x[i], p[pre + "history_norm.scale"], dscale=p.g(pre + "history_norm.scale"),
                             dres=dx, out=spare)
             dx, spare = spare, dx                                       # dx = d x[i]
-        self._embed_bwd(ws, M, dx, batch["last_rewards"], batch["last_actions"], batch.get("task_ids"))
+        self._embed_bwd(ws, M, dx, batch["last_rewards"], batch["last_actions"], batch.get("task_ids"), batch["obs"])
         return ws.losses

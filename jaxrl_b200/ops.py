@@ -346,6 +346,16 @@ def obs_onehot_im2col(obs, out, M: int, IH: int, IW: int, sizes: Sequence[int], 
     return out
 
 
+def conv1_onehot_fwd(obs, w, bias, a_out, M: int, IH: int, IW: int, sizes: Sequence[int], kh, kw, sh, sw, cout: int,
+                     z_out=None, gelu: bool = True):
+    """First conv layer straight from the uint8 observation (no one-hot / im2col materialisation)."""
+    K = len(sizes)
+    arr = (C.c_int * K)(*sizes)
+    check(lib.mpx_conv1_onehot_fwd(ptr(obs), ptr(w), ptr(bias), ptr(z_out), ptr(a_out), M, IH, IW, K, arr, kh, kw, sh,
+                                   sw, cout, int(gelu), stream()), "mpx_conv1_onehot_fwd")
+    return a_out
+
+
 def im2col(a, out, M: int, IH: int, IW: int, Cc: int, kh, kw, sh, sw):
     check(lib.mpx_im2col(ptr(a), ptr(out), M, IH, IW, Cc, kh, kw, sh, sw, stream()), "mpx_im2col")
     return out

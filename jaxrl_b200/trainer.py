@@ -15,7 +15,7 @@ from typing import Optional
 
 import torch
 
-from . import _lib, ops
+from . import _lib, dist as mdist, ops
 from .config import RunConfig
 from .engine import PolicyEngine
 
@@ -64,6 +64,8 @@ class PPOTrainer:
         seed = run.seed if seed is None else seed
         self.seed = seed
         self.engine = PolicyEngine(self.cfg, self.dev, seed=seed)          # same seed on every rank: replicated weights
+        mdist.broadcast_params(self.engine.p.flat)
+        self.engine.stage_weights()
         self.env = SyntheticEnv(self.cfg, self.B, self.T, self.dev, seed=seed + 1000 * (rank + 1), host=self.e2e)
         self._alloc()
         self.rollout_graph = None
@@ -158,9 +160,7 @@ class PPOTrainer:
         b = self.b
         if not self.hyp.normalize_advantage:
             return
-        count = float(self.B * self.T * self.world)
-        if self.world > 1:
-            torch.distributed.all_reduce(b.stats)
+        count = mdist.allreduce_adv_moments(b.stats, self.B * self.T)
         ops.adv_normalize(b.advantages.view(-1), b.stats, count)
 
     # ------------------------------------------------------------------------------------------ update (train.py:249-260)
@@ -169,18 +169,18 @@ class PPOTrainer:
         sl = slice(i * Bm, (i + 1) * Bm)
         batch = dict(actions=b.actions[sl].reshape(-1), log_prob=b.log_prob[sl].reshape(-1),
                      advantages=b.advantages[sl].reshape(-1), targets=b.targets[sl].reshape(-1),
-                     last_rewards=b.last_rewards[sl].reshape(-1), last_actions=b.last_actions[sl].reshape(-1))
+                     last_rewards=b.last_rewards[sl].reshape(-1), last_actions=b.last_actions[sl].reshape(-1),
+                     obs=b.obs[sl])
         eng.p.grad.zero_()
         eng.forward_train(tws, b.obs[sl], batch["last_rewards"], batch["last_actions"])
         eng.loss_and_backward(tws, batch, self.hyp, 0.0, entropy_coef_dev=self.ent_coef)
         self.log_acc[:3] += tws.losses[:3]
-        if self.world > 1:
-            torch.distributed.all_reduce(eng.p.grad)
+        gscale = mdist.allreduce_gradients(eng.p.grad)
         if self.run_optimizer:
             o, opt = self.o, self.opt
             total = self.run.update_steps * self.hyp.minibatch_count * self.hyp.epoch_count
             ops.adamw_step(eng.p.flat, eng.p.grad, o.mu, o.nu, o.scratch, o.step, opt.learning_rate, total, opt.beta1,
-                           opt.beta2, opt.eps, opt.weight_decay, opt.max_norm, grad_scale=1.0 / self.world,
+                           opt.beta2, opt.eps, opt.weight_decay, opt.max_norm, grad_scale=gscale,
                            norm_out=o.norm, ws=o.ws)
             eng.stage_weights()
 

@@ -1,0 +1,85 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic: env sharding + the two collectives give exactly
+the single-device result (global advantage normalisation, mean gradient)."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from jaxrl_b200 import dist as mdist
+from oracle import oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B, T = 8, 16
+        rng = np.random.default_rng(0)
+        r, v = rng.standard_normal((B, T)).astype(np.float32), rng.standard_normal((B, T + 1)).astype(np.float32)
+        term = rng.random((B, T)) < 0.1
+        lo, hi = mdist.shard_bounds(B, rank, world)
+        adv, tgt = O.calculate_advantage(r[lo:hi], v[lo:hi], term[lo:hi], 0.97, 0.9, False)
+        stats = torch.tensor([adv.astype(np.float64).sum(), (adv.astype(np.float64) ** 2).sum()], dtype=torch.float64)
+        count = mdist.allreduce_adv_moments(stats, adv.size)
+        mean = stats[0].item() / count
+        std = (stats[1].item() / count - mean * mean) ** 0.5
+        adv_n = (adv - np.float32(mean)) / (np.float32(std) + np.float32(1e-8))
+        # gradient: local mean-loss gradients, sum all-reduce, scale 1/world == gradient of the global mean
+        w = torch.arange(4, dtype=torch.float32)
+        x = torch.from_numpy(r[lo:hi, :4])
+        g_local = (2 * (x @ w)[:, None] * x).mean(0)           # d/dw mean((x.w)^2) over the shard
+        g = g_local.clone()
+        scale = mdist.allreduce_gradients(g)
+        p = torch.zeros(3) if rank else torch.ones(3)
+        mdist.broadcast_params(p)
+        q.put((rank, lo, hi, adv_n, (g * scale).numpy(), p.numpy(), count))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_env_sharded_collectives_match_single_device():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(rk, world, port, q)) for rk in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    out.sort(key=lambda t: t[0])
+    B, T = 8, 16
+    rng = np.random.default_rng(0)
+    r, v = rng.standard_normal((B, T)).astype(np.float32), rng.standard_normal((B, T + 1)).astype(np.float32)
+    term = rng.random((B, T)) < 0.1
+    ref_adv, _ = O.calculate_advantage(r, v, term, 0.97, 0.9, True)
+    got = np.concatenate([o[3] for o in out], axis=0)
+    np.testing.assert_allclose(got, ref_adv, rtol=1e-5, atol=1e-5)
+    w = torch.arange(4, dtype=torch.float32)
+    x = torch.from_numpy(r[:, :4])
+    g_ref = (2 * (x @ w)[:, None] * x).mean(0).numpy()
+    for o in out:
+        np.testing.assert_allclose(o[4], g_ref, rtol=1e-5, atol=1e-6)
+        np.testing.assert_array_equal(o[5], np.ones(3, np.float32))       # rank-0 weights everywhere
+        assert o[6] == B * T
+    assert (out[0][1], out[0][2], out[1][1], out[1][2]) == (0, 4, 4, 8)
+
+
+def test_shard_bounds_rejects_ragged():
+    with pytest.raises(ValueError):
+        mdist.shard_bounds(10, 0, 4)

@@ -216,7 +216,11 @@ def test_glu_up(ops):
 @pytest.mark.parametrize("step,S,Nq,Nkv,Bb", [(0, 16, 4, 1, 3), (5, 16, 4, 1, 9), (31, 64, 4, 1, 4), (32, 64, 4, 1, 4),
                                               (100, 512, 4, 1, 33), (511, 512, 4, 1, 130), (700, 512, 4, 1, 5),
                                               (77, 128, 4, 2, 6), (40, 64, 4, 4, 3), (9, 32, 8, 1, 2)])
-def test_attn_decode(ops, step, S, Nq, Nkv, Bb):
+@pytest.mark.parametrize("impl", [0, 1])
+def test_attn_decode(ops, step, S, Nq, Nkv, Bb, impl):
+    """impl 0 = mma.sync kernel (default), 1 = SIMT v1; both against the oracle."""
+    from jaxrl_b200._lib import lib
+    lib.mpx_debug_set(1, impl)
     gen = g(step * 7 + S + Nq + Nkv)
     D = 32
     q = torch.randn(Bb, Nq, D, generator=gen).to(BF16)
@@ -225,8 +229,57 @@ def test_attn_decode(ops, step, S, Nq, Nkv, Bb):
     kv_len = min(step + 1, S)
     ref = O.dot_product_attention(q[:, None], kc, vc, kv_len=kv_len)[:, 0]
     pos = torch.full((Bb,), step, dtype=torch.int32, device=DEV)
-    out = ops.attn_decode(q.reshape(Bb, -1).to(DEV), kc.to(DEV), vc.to(DEV), pos, Nq, Nkv, D)
-    assert_close_bf16(out.reshape(Bb, Nq, D), ref, f"attn_decode step={step} S={S} Nkv={Nkv}")
+    try:
+        out = ops.attn_decode(q.reshape(Bb, -1).to(DEV), kc.to(DEV), vc.to(DEV), pos, Nq, Nkv, D)
+        torch.cuda.synchronize()
+    finally:
+        lib.mpx_debug_set(1, 0)
+    assert_close_bf16(out.reshape(Bb, Nq, D), ref, f"attn_decode impl={impl} step={step} S={S} Nkv={Nkv}")
+
+
+def test_attn_decode_full_batch(ops):
+    """Full-size shape (B=4096, S=512): persistent-warp striding covers every agent; bit-for-bit vs the SIMT kernel."""
+    from jaxrl_b200._lib import lib
+    gen = g(99)
+    Bb, S, Nq, Nkv, D, step = 4096, 512, 4, 1, 32, 300
+    q = torch.randn(Bb, Nq * D, generator=gen).to(BF16).to(DEV)
+    kc = torch.randn(Bb, S, Nkv, D, generator=gen).to(BF16).to(DEV)
+    vc = torch.randn(Bb, S, Nkv, D, generator=gen).to(BF16).to(DEV)
+    pos = torch.full((Bb,), step, dtype=torch.int32, device=DEV)
+    outs = []
+    for impl in (0, 1):
+        lib.mpx_debug_set(1, impl)
+        outs.append(ops.attn_decode(q, kc, vc, pos, Nq, Nkv, D).float().cpu())
+    lib.mpx_debug_set(1, 0)
+    ref = O.dot_product_attention(q[:64].cpu().reshape(64, 1, Nq, D), kc[:64].cpu(), vc[:64].cpu(), kv_len=step + 1)[:, 0]
+    assert_close_bf16(outs[0][:64].reshape(64, Nq, D), ref, "attn_decode full batch vs oracle (first 64 agents)")
+    assert_close_bf16(outs[0], outs[1], "attn_decode mma vs simt (all 4096 agents)", rtol=1e-2)
+
+
+def test_conv1_onehot_matches_oracle_conv(ops):
+    gen = g(55)
+    M, IH, IW, sizes, cout = 37, 11, 11, (5, 5), 16
+    obs = torch.stack([torch.randint(0, n, (M, IH, IW), generator=gen) for n in sizes], -1).to(torch.uint8)
+    W = torch.randn(3, 3, sum(sizes), cout, generator=gen) * 0.2
+    b = torch.randn(cout, generator=gen) * 0.1
+    x = O.concat_one_hot(obs, sizes)
+    z_ref = O.conv_valid(x, W, b, (2, 2))
+    a_ref = O.gelu_tanh(z_ref)
+    z = torch.empty(M * 25, cout, dtype=BF16, device=DEV)
+    a = torch.empty(M * 25, cout, dtype=BF16, device=DEV)
+    ops.conv1_onehot_fwd(obs.to(DEV), W.reshape(-1, cout).to(BF16).to(DEV), b.to(BF16).to(DEV), a, M, IH, IW, sizes,
+                         3, 3, 2, 2, cout, z_out=z)
+    assert_close_bf16(z.reshape(M, 5, 5, cout), z_ref, "conv1 onehot z")
+    assert_close_bf16(a.reshape(M, 5, 5, cout), a_ref, "conv1 onehot gelu", rtol=2e-2)
+    # the one-hot im2col rows (used for the weight gradient) reproduce the same conv through the GEMM
+    KP = 96
+    X1 = torch.empty(M * 25, KP, dtype=BF16, device=DEV)
+    ops.obs_onehot_im2col(obs.to(DEV), X1, M, IH, IW, sizes, 3, 3, 2, 2)
+    wt = torch.zeros(cout, KP)
+    wt[:, :90] = W.reshape(90, cout).t()
+    y = ops.linear(X1, wt.to(BF16).to(DEV), bias=b.to(BF16).to(DEV))
+    assert_close_bf16(y.reshape(M, 5, 5, cout), z_ref, "onehot_im2col + GEMM == conv1")
+    assert (X1.float().sum(-1) == 18).all()        # 9 taps x 2 components set exactly one channel each
 
 
 # ---------------------------------------------------------------------------------------------- row-wise / heads

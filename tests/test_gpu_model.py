@@ -130,6 +130,7 @@ def test_train_forward_and_backward_match_oracle(engine):
     torch.testing.assert_close(val, O.hlgauss_get_value(vl_ref, centers), rtol=1e-2, atol=2e-2)
     engine.p.grad.zero_()
     flat = {k: (v.reshape(-1) if v.dim() == 2 and k not in ("obs", "action_mask") else v) for k, v in d.items()}
+    flat["obs"] = d["obs"]
     losses = engine.loss_and_backward(ws, flat, hyp, progress=0.3)
     torch.cuda.synchronize()
     l = losses.cpu()
