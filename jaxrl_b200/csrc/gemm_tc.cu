@@ -165,6 +165,12 @@ __device__ __forceinline__ void epi_store(const GemmParams& p, int row, int col0
   __nv_bfloat16* d = p.y + (long long)row * p.ldy + col0;
   if (vec_ok) {
     store_bf16x32(d, f);
+  } else if ((p.ldy & 7) == 0 && (p.N & 7) == 0) {   // ragged last chunk, still whole 16-byte pieces
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (col0 + 8 * i < p.N)
+        reinterpret_cast<uint4*>(d)[i] = make_uint4(pack_bf16(f[8 * i], f[8 * i + 1]), pack_bf16(f[8 * i + 2], f[8 * i + 3]),
+                                                    pack_bf16(f[8 * i + 4], f[8 * i + 5]), pack_bf16(f[8 * i + 6], f[8 * i + 7]));
   } else {
     for (int i = 0; i < 32 && col0 + i < p.N; ++i) d[i] = __float2bfloat16_rn(f[i]);
   }
