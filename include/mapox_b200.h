@@ -30,7 +30,8 @@ enum { MPX_OK = 0, MPX_ERR_INVALID = -1, MPX_ERR_CUDA = -2, MPX_ERR_UNSUPPORTED 
 const char* mpx_last_error(void);
 int mpx_version(void);
 /* Debug/tuning knobs (tests only). key 0: swap LBO/SBO in MN-major UMMA descriptors.
- * key 1: decode attention implementation (0 = mma.sync, default; 1 = SIMT v1). */
+ * key 1: decode attention implementation (0 = mma.sync online softmax, default; 1 = SIMT exact two-pass;
+ * 2 = mma.sync exact two-pass). */
 int mpx_debug_set(int key, int value);
 
 /* ---------------------------------------------------------------------------------------------- GAE

@@ -424,7 +424,204 @@ __global__ void __launch_bounds__(512) attn_decode_mma_kernel(
   }
 }
 
-int g_attn_decode_impl = 0;   // 0 = mma.sync (default), 1 = SIMT v1 (tests / cross-check)
+// ================================================================================================ v3: online softmax
+// Single pass (flash-decoding): K and V chunks travel together (4 KB per stage, 4 stages -> 12 KB in flight per
+// warp), no score buffer.  Per 32-position chunk: S^T = K.Q^T (mma), running max / rescale in the C-fragment lanes
+// that own heads (2t, 2t+1), P -> bf16, C-layout -> B-layout with movmatrix.trans, O^T += V^T.P^T (mma).
+// Rounds the UN-normalised probabilities to bf16 (like the training kernel and cuDNN's fused SDPA); the exact
+// two-pass kernels above remain selectable (mpx_debug_set(1, 1|2)).
+constexpr int AD3_STAGES = 4;
+constexpr int AD3_STAGE_BYTES = 2 * AD_STAGE_BYTES;   // K chunk then V chunk
+
+__device__ __forceinline__ uint32_t ad_movmatrix_t(uint32_t x) {
+  uint32_t y;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+
+template <int G>
+__global__ void __launch_bounds__(512) attn_decode_online_kernel(
+    const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
+    const __nv_bfloat16* __restrict__ vcache, const int32_t* __restrict__ pos, __nv_bfloat16* __restrict__ out,
+    int B, int S, int Nkv, float scale_log2) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int warps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ring = smem_u32(smem_raw) + warp * (AD3_STAGES * AD3_STAGE_BYTES);
+  const int g = lane >> 2, t = lane & 3, mi = lane >> 3, r8 = lane & 7;
+  const int kv_len = min(pos[0] + 1, S);
+  const int nchunks = (kv_len + AD_CHUNK - 1) / AD_CHUNK;
+  const int Nq = Nkv * G;
+  const size_t row_stride = (size_t)Nkv * 32;
+  const bool head_lane = (2 * t) < G;
+  const bool head1 = (2 * t + 1) < G;
+  const int total = B * Nkv;
+
+  for (int wg = blockIdx.x * warps + warp; wg < total; wg += gridDim.x * warps) {
+    const int b = wg / Nkv, kvh = wg % Nkv;
+    const __nv_bfloat16* kbase = kcache + ((size_t)b * S * Nkv + kvh) * 32;
+    const __nv_bfloat16* vbase = vcache + ((size_t)b * S * Nkv + kvh) * 32;
+    uint32_t qb[2][2];
+    {
+      const __nv_bfloat16* qrow = q + (size_t)b * Nq * 32 + (size_t)kvh * G * 32 + g * 32;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        qb[ks][0] = g < G ? *reinterpret_cast<const uint32_t*>(qrow + 16 * ks + 2 * t) : 0u;
+        qb[ks][1] = g < G ? *reinterpret_cast<const uint32_t*>(qrow + 16 * ks + 8 + 2 * t) : 0u;
+      }
+    }
+    auto issue = [&](int c) {
+      if (c < nchunks) {
+        const uint32_t st = ring + (c % AD3_STAGES) * AD3_STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int pi = lane + 32 * (i & 3);
+          const int r = pi >> 2, j = pi & 3;
+          const int p = c * AD_CHUNK + r;
+          const bool valid = p < kv_len;
+          const __nv_bfloat16* gp = (i < 4 ? kbase : vbase) + (size_t)(valid ? p : 0) * row_stride + j * 8;
+          const uint32_t n = valid ? 16u : 0u;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                       ::"r"(st + (i < 4 ? 0 : AD_STAGE_BYTES) + ad_off64(r, j)), "l"(gp), "r"(n) : "memory");
+        }
+      }
+      cp_async_commit();
+    };
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < AD3_STAGES - 1; ++i) issue(i);
+
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;       // heads 2t, 2t+1 (log2 domain)
+    float oacc[2][4];
+#pragma unroll
+    for (int md = 0; md < 2; ++md) oacc[md][0] = oacc[md][1] = oacc[md][2] = oacc[md][3] = 0.f;
+
+    for (int c = 0; c < nchunks; ++c) {
+      cp_async_wait<AD3_STAGES - 2>();
+      __syncwarp();
+      const uint32_t st = ring + (c % AD3_STAGES) * AD3_STAGE_BYTES;
+      float sacc[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        sacc[mt][0] = sacc[mt][1] = sacc[mt][2] = sacc[mt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t ka[4];
+          ad_ldsm_x4(ka, st + ad_off64(16 * mt + (mi & 1) * 8 + r8, ks * 2 + (mi >> 1)));
+          ad_mma(sacc[mt], ka, qb[ks][0], qb[ks][1]);
+        }
+      }
+      // scale, mask the ragged tail, chunk max over the 32 positions (lanes differing in g)
+      float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int pa = c * AD_CHUNK + 16 * mt + g;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int pp = pa + ((e & 2) ? 8 : 0);
+          float v = sacc[mt][e] * scale_log2;
+          if (pp >= kv_len) v = -INFINITY;
+          sacc[mt][e] = v;
+        }
+        cm0 = fmaxf(cm0, fmaxf(sacc[mt][0], sacc[mt][2]));
+        cm1 = fmaxf(cm1, fmaxf(sacc[mt][1], sacc[mt][3]));
+      }
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, o));
+        cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, o));
+      }
+      const float mn0 = fmaxf(m0, cm0), mn1 = fmaxf(m1, cm1);
+      const float a0 = exp2f(m0 - mn0), a1 = exp2f(m1 - mn1);     // first chunk: exp2(-inf) = 0
+      m0 = mn0; m1 = mn1;
+      l0 *= a0; l1 *= a1;
+#pragma unroll
+      for (int md = 0; md < 2; ++md) {
+        oacc[md][0] *= a0; oacc[md][2] *= a0;
+        oacc[md][1] *= a1; oacc[md][3] *= a1;
+      }
+      // P (bf16), row sums of the ROUNDED values, and the C-layout -> B-layout transposition
+      uint32_t pb[2][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const float p0 = head_lane ? exp2f(sacc[mt][0] - m0) : 0.f, p1 = head1 ? exp2f(sacc[mt][1] - m1) : 0.f;
+        const float p2 = head_lane ? exp2f(sacc[mt][2] - m0) : 0.f, p3 = head1 ? exp2f(sacc[mt][3] - m1) : 0.f;
+        const uint32_t lo = pack_bf16(p0, p1), hi = pack_bf16(p2, p3);     // (pos g | g+8, heads 2t, 2t+1)
+        l0 += bf16_lo(lo) + bf16_lo(hi);
+        l1 += bf16_hi(lo) + bf16_hi(hi);
+        pb[mt][0] = ad_movmatrix_t(lo);                                    // (k = pos 2t,2t+1 ; n = head g)
+        pb[mt][1] = ad_movmatrix_t(hi);                                    // (k = pos 8+2t.. ; n = head g)
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+#pragma unroll
+        for (int md = 0; md < 2; ++md) {
+          uint32_t va[4];
+          ad_ldsm_x4_t(va, st + AD_STAGE_BYTES + ad_off64(16 * j + (mi >> 1) * 8 + r8, 2 * md + (mi & 1)));
+          ad_mma(oacc[md], va, pb[j][0], pb[j][1]);
+        }
+      }
+      __syncwarp();
+      issue(c + AD3_STAGES - 1);
+    }
+    cp_async_wait<0>();
+    // total row sums: partial sums live in the 8 position lanes of each head pair
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      l0 += __shfl_xor_sync(0xffffffffu, l0, o);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+    }
+    if (head_lane) {
+      const float i0 = 1.0f / l0, i1 = head1 ? 1.0f / l1 : 0.f;
+      __nv_bfloat16* orow = out + (size_t)b * Nq * 32 + (size_t)kvh * G * 32;
+#pragma unroll
+      for (int md = 0; md < 2; ++md) {
+        const int d0 = 16 * md + g;
+        orow[(2 * t) * 32 + d0] = __float2bfloat16_rn(oacc[md][0] * i0);
+        orow[(2 * t) * 32 + d0 + 8] = __float2bfloat16_rn(oacc[md][2] * i0);
+        if (head1) {
+          orow[(2 * t + 1) * 32 + d0] = __float2bfloat16_rn(oacc[md][1] * i1);
+          orow[(2 * t + 1) * 32 + d0 + 8] = __float2bfloat16_rn(oacc[md][3] * i1);
+        }
+      }
+    }
+  }
+}
+
+template <int G>
+static int launch_attn_decode_online(const mpx_attn_decode_args* a, cudaStream_t stream) {
+  const size_t per_warp = AD3_STAGES * AD3_STAGE_BYTES;
+  const int wmax = 14;
+  const int total = a->B * a->Nkv, sms = num_sms();
+  int best_w = wmax;
+  double best_eff = -1.0;
+  for (int w = wmax; w >= 8; --w) {
+    const int ctas = ceil_div(total, w) < sms ? ceil_div(total, w) : sms;
+    const int rounds = ceil_div(total, ctas * w);
+    const double eff = (double)total / ((double)sms * rounds * w);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best_w = w; }
+  }
+  const size_t smem = per_warp * best_w;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(attn_decode_online_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(attn_decode_online): %s", cudaGetErrorString(e));
+      return MPX_ERR_CUDA;
+    }
+    attr_smem = smem;
+  }
+  const int grid = ceil_div(total, best_w) < sms ? ceil_div(total, best_w) : sms;
+  const float scale_log2 = (1.0f / sqrtf((float)a->D)) * 1.4426950408889634f;
+  attn_decode_online_kernel<G><<<grid, best_w * 32, smem, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a->q), reinterpret_cast<const __nv_bfloat16*>(a->kcache),
+      reinterpret_cast<const __nv_bfloat16*>(a->vcache), a->pos, reinterpret_cast<__nv_bfloat16*>(a->out), a->B, a->S,
+      a->Nkv, scale_log2);
+  return check_launch("attn_decode_online_kernel");
+}
+
+// 0 = online-softmax mma (default), 1 = SIMT exact two-pass, 2 = mma exact two-pass
+int g_attn_decode_impl = 0;
 
 template <int G>
 static int launch_attn_decode_mma(const mpx_attn_decode_args* a, cudaStream_t stream) {
@@ -502,6 +699,17 @@ extern "C" int mpx_attn_decode(const mpx_attn_decode_args* a, mpx_stream_t strea
   MPX_REQUIRE(a->Nq % a->Nkv == 0, "mpx_attn_decode: Nq=%d not a multiple of Nkv=%d", a->Nq, a->Nkv);
   cudaStream_t s = (cudaStream_t)stream;
   if (g_attn_decode_impl == 0) {
+    switch (a->Nq / a->Nkv) {
+      case 1: return launch_attn_decode_online<1>(a, s);
+      case 2: return launch_attn_decode_online<2>(a, s);
+      case 4: return launch_attn_decode_online<4>(a, s);
+      case 8: return launch_attn_decode_online<8>(a, s);
+      default:
+        set_error("mpx_attn_decode: group size %d unsupported (1,2,4,8)", a->Nq / a->Nkv);
+        return MPX_ERR_UNSUPPORTED;
+    }
+  }
+  if (g_attn_decode_impl == 2) {
     switch (a->Nq / a->Nkv) {
       case 1: return launch_attn_decode_mma<1>(a, s);
       case 2: return launch_attn_decode_mma<2>(a, s);

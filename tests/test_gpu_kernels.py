@@ -216,9 +216,9 @@ def test_glu_up(ops):
 @pytest.mark.parametrize("step,S,Nq,Nkv,Bb", [(0, 16, 4, 1, 3), (5, 16, 4, 1, 9), (31, 64, 4, 1, 4), (32, 64, 4, 1, 4),
                                               (100, 512, 4, 1, 33), (511, 512, 4, 1, 130), (700, 512, 4, 1, 5),
                                               (77, 128, 4, 2, 6), (40, 64, 4, 4, 3), (9, 32, 8, 1, 2)])
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 def test_attn_decode(ops, step, S, Nq, Nkv, Bb, impl):
-    """impl 0 = mma.sync kernel (default), 1 = SIMT v1; both against the oracle."""
+    """impl 0 = mma.sync online softmax (default), 1 = SIMT exact two-pass, 2 = mma.sync exact two-pass."""
     from jaxrl_b200._lib import lib
     lib.mpx_debug_set(1, impl)
     gen = g(step * 7 + S + Nq + Nkv)
@@ -234,7 +234,9 @@ def test_attn_decode(ops, step, S, Nq, Nkv, Bb, impl):
         torch.cuda.synchronize()
     finally:
         lib.mpx_debug_set(1, 0)
-    assert_close_bf16(out.reshape(Bb, Nq, D), ref, f"attn_decode impl={impl} step={step} S={S} Nkv={Nkv}")
+    # the online-softmax kernel rounds un-normalised probabilities (<= 2 bf16 ulps from the XLA arithmetic)
+    assert_close_bf16(out.reshape(Bb, Nq, D), ref, f"attn_decode impl={impl} step={step} S={S} Nkv={Nkv}",
+                      rtol=1.7e-2 if impl == 0 else 1e-2, abs_floor_frac=1e-2 if impl == 0 else 4e-3)
 
 
 def test_attn_decode_full_batch(ops):
@@ -247,13 +249,14 @@ def test_attn_decode_full_batch(ops):
     vc = torch.randn(Bb, S, Nkv, D, generator=gen).to(BF16).to(DEV)
     pos = torch.full((Bb,), step, dtype=torch.int32, device=DEV)
     outs = []
-    for impl in (0, 1):
+    for impl in (0, 1, 2):
         lib.mpx_debug_set(1, impl)
         outs.append(ops.attn_decode(q, kc, vc, pos, Nq, Nkv, D).float().cpu())
     lib.mpx_debug_set(1, 0)
     ref = O.dot_product_attention(q[:64].cpu().reshape(64, 1, Nq, D), kc[:64].cpu(), vc[:64].cpu(), kv_len=step + 1)[:, 0]
-    assert_close_bf16(outs[0][:64].reshape(64, Nq, D), ref, "attn_decode full batch vs oracle (first 64 agents)")
-    assert_close_bf16(outs[0], outs[1], "attn_decode mma vs simt (all 4096 agents)", rtol=1e-2)
+    assert_close_bf16(outs[2][:64].reshape(64, Nq, D), ref, "attn_decode (exact mma) full batch vs oracle (first 64 agents)")
+    assert_close_bf16(outs[2], outs[1], "attn_decode exact mma vs simt (all 4096 agents)", rtol=1e-2)
+    assert_close_bf16(outs[0], outs[1], "attn_decode online mma vs simt (all 4096 agents)", rtol=1.7e-2, abs_floor_frac=1e-2)
 
 
 def test_conv1_onehot_matches_oracle_conv(ops):
