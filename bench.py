@@ -162,7 +162,7 @@ def count_launches(trainer) -> int:
     """Kernel launches of OUR library in one PPO update (counted from the C-ABI calls of one eager pass)."""
     from jaxrl_b200 import _lib
     per_call = {"mpx_gae": 2, "mpx_hlgauss_loss": 2, "mpx_ppo_policy_loss": 2, "mpx_adamw_step": 3,
-                "mpx_attn_train_bwd": 3}
+                "mpx_attn_train_bwd": 3, "mpx_muon_step": 21}
     counts = {"n": 0}
     orig = _lib.check
 
@@ -313,7 +313,7 @@ def main():
                                    f"{run.ppo.minibatch_count} minibatch fwd/bwd + optimizer, L={run.model.num_layers} "
                                    f"H={run.model.hidden_features} GQA {run.model.num_heads}:{run.model.num_kv_heads}",
                        "agents_per_gpu": B, "trajectory": T, "layers": run.model.num_layers,
-                       "parallelism": f"env-sharded dp{world}", "optimizer": "adamw (reference config: muon; see DESIGN.md)",
+                       "parallelism": f"env-sharded dp{world}", "optimizer": run.optimizer.type,
                        "l2": "working set (KV caches + activations, >2 GB) larger than the 126 MB L2; no flush",
                        "cuda_graphs": not args.no_graphs},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,

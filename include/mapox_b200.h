@@ -31,7 +31,8 @@ const char* mpx_last_error(void);
 int mpx_version(void);
 /* Debug/tuning knobs (tests only). key 0: swap LBO/SBO in MN-major UMMA descriptors.
  * key 1: decode attention implementation (0 = mma.sync online softmax, default; 1 = SIMT exact two-pass;
- * 2 = mma.sync exact two-pass). */
+ * 2 = mma.sync exact two-pass).  key 2: training attention forward (0 = tcgen05/TMEM when q,k,v are packed and
+ * Nkv == 1, default; 1 = mma.sync everywhere). */
 int mpx_debug_set(int key, int value);
 
 /* ---------------------------------------------------------------------------------------------- GAE
@@ -259,6 +260,18 @@ size_t mpx_adamw_workspace_bytes(long long n);
 int mpx_adamw_step(float* params, const float* grads, float* mu, float* nu, float* update_scratch, long long n,
                    int* step, float lr0, float total_steps, float b1, float b2, float eps, float weight_decay,
                    float max_norm, float grad_scale, float* update_norm_out, void* workspace, mpx_stream_t stream);
+/* optimizer.py:25-37: optax.contrib.muon (nesterov momentum beta, 5 Newton-Schulz steps in fp32, sqrt(max(1,out/in))
+ * scaling, weight decay, linear LR schedule) for the 2-D matrices described by `mats`, optax.adamw(nesterov=True)
+ * for elements [0, n_adam) of the flat buffers, then clip_by_global_norm(max_norm) on the combined update.
+ * mats: DEVICE array of nmat records {int64 off; int32 rows, cols, r, c, transposed, pad; int64 xoff, aoff}
+ * (r <= c is the orientation Newton-Schulz runs in; xoff/aoff are offsets into the workspaces).
+ * ns_ws: fp32 scratch of 2*x_total + 2*a_total + nmat floats (x_total = sum r*c, a_total = sum r*r). */
+size_t mpx_muon_workspace_bytes(long long n, int nmat);
+int mpx_muon_step(float* params, const float* grads, float* mu, float* nu, float* update_scratch, long long n,
+                  long long n_adam, const void* mats, int nmat, long long x_total, long long a_total, int max_r,
+                  int max_c, float* ns_ws, int* step, float lr0, float total_steps, float adam_b1, float adam_b2,
+                  float eps, float weight_decay, float muon_beta, int ns_steps, float max_norm, float grad_scale,
+                  float* update_norm_out, void* workspace, mpx_stream_t stream);
 /* fp32 master weights -> bf16 GEMM operand copies. descs is a DEVICE array; each entry casts (and optionally
  * transposes) a (rows, cols) fp32 block with pitch src_ld into a bf16 destination with pitch dst_ld. */
 typedef struct {

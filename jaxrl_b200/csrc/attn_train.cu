@@ -437,6 +437,8 @@ static int launch_bwd(const mpx_attn_train_bwd_args* a, cudaStream_t s) {
 
 using namespace mpx;
 
+namespace mpx { int attn_fwd_tc_launch(const mpx_attn_train_args* a, cudaStream_t stream); }
+
 extern "C" int mpx_attn_train_fwd(const mpx_attn_train_args* a, mpx_stream_t stream) {
   MPX_REQUIRE(a && a->q && a->k && a->v && a->o && a->lse, "mpx_attn_train_fwd: null pointer");
   MPX_REQUIRE(a->D == 32, "mpx_attn_train_fwd: head_dim %d unsupported (only 32)", a->D);
@@ -444,6 +446,10 @@ extern "C" int mpx_attn_train_fwd(const mpx_attn_train_args* a, mpx_stream_t str
   MPX_REQUIRE(a->Nkv > 0 && a->Nq % a->Nkv == 0, "mpx_attn_train_fwd: bad head counts");
   MPX_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 2 == 0, "mpx_attn_train_fwd: strides must be multiples of 8");
   cudaStream_t s = (cudaStream_t)stream;
+  {  // tcgen05 / TMEM kernel when q, k, v are one packed (M, Nq*D + 2*D) buffer (Nkv == 1); else mma.sync
+    const int rc = attn_fwd_tc_launch(a, s);
+    if (rc != MPX_ERR_UNSUPPORTED) return rc;
+  }
   switch (a->Nq / a->Nkv) {
     case 1: return launch_fwd<1>(a, s);
     case 2: return launch_fwd<2>(a, s);

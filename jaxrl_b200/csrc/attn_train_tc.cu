@@ -1,0 +1,232 @@
+// PPO-update attention forward on 5th-generation tensor cores: causal GQA flash attention with both contractions
+// (S = Q.K^T and O = P.V) issued as tcgen05.mma, S and O accumulators in TMEM, operands staged by TMA.
+// Restates the training branch of AttentionBlock.__call__ (reference mapox_trainer/model/attention.py:151-169);
+// same arithmetic as attn_fwd_kernel in attn_train.cu (fp32 scores/softmax, un-normalised probabilities rounded to
+// bf16 before P.V, fp32 accumulation, one bf16 rounding of O) and the same lse output for the backward pass.
+//
+// CTA = (batch row b, query head h, 128-query tile qt); 128 threads, thread r owns query row r (= TMEM lane r).
+//   smem:  Q tile   [128 q  x 64 cols] SW128 (cols h*32.. of the (M, Nq*D+2*D) qkv buffer; only 32 are used)
+//          KV tiles [keys   x 64 cols] SW128: each row is [k (32) | v (32)] of one position
+//          P tile   [128 q  x 64 keys] SW128 bf16, written by the softmax threads, A operand of the second MMA
+//   TMEM:  S0 [0,64)  S1 [64,128)  (double buffered: S(kt+1) is computed while softmax(kt) runs)   O [128,192)
+//   MMA1:  S(128x64)  = Q (K-major, K = 32)        . K_tile (K-major)            2 x (M128 N64 K16)
+//   MMA2:  O(128x64) += P (K-major, K = 64 keys)   . [K|V]_tile (MN-major)       4 x (M128 N64 K16)
+//          columns [0,32) of O accumulate P.K (ignored), columns [32,64) accumulate P.V.
+// Requires Nkv == 1 (k and v adjacent in the qkv buffer), head_dim 32, T % 128 == 0.  Other shapes use the
+// mma.sync kernel in attn_train.cu.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.h"
+
+namespace mpx {
+
+constexpr int TC_QT = 128;   // queries per CTA
+constexpr int TC_KT = 64;    // keys per inner tile
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(128, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ o, long long ldo,
+                   float* __restrict__ lse, int T, int Nq, int kv_col, float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nqt = T / TC_QT;
+  const int qt = nqt - 1 - (int)blockIdx.x;      // heavy (late) query tiles first
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int nkt = 2 * (qt + 1);                  // key tiles of 64 visible to this query tile
+  const int nkv_boxes = qt + 1;                  // 128-row TMA boxes of [k|v]
+  uint8_t* sQ = smem;                            // 16 KB
+  uint8_t* sP = smem + 16384;                    // 16 KB
+  uint8_t* sKV = smem + 32768;                   // nkv_boxes * 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + (size_t)nqt * 16384);
+  uint64_t* bar_q = bars;            // Q tile landed
+  uint64_t* bar_kv = bars + 1;       // [nqt] one per [k|v] box
+  uint64_t* bar_s = bars + 1 + 8;    // [2] S buffer written by MMA1
+  uint64_t* bar_o = bars + 1 + 8 + 2;  // MMA2 finished (O updated, P tile free)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const long long tok0 = (long long)b * T;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    mbar_init(bar_q, 1);
+    for (int j = 0; j < nqt; ++j) mbar_init(&bar_kv[j], 1);
+    mbar_init(&bar_s[0], 1);
+    mbar_init(&bar_s[1], 1);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS[2] = {tmem_base, tmem_base + 64};
+  const uint32_t tO = tmem_base + 128;
+
+  constexpr uint32_t idesc1 = umma_idesc_bf16(128, 64, 0, 0);   // Q (K-major) x K (K-major)
+  constexpr uint32_t idesc2 = umma_idesc_bf16(128, 64, 0, 1);   // P (K-major) x [K|V] (MN-major)
+
+  auto issue_mma1 = [&](int kt) {   // S[kt & 1] = Q . K_kt^T     (thread 0 only)
+    const uint32_t a = smem_u32(sQ);
+    const uint32_t bb = smem_u32(sKV) + kt * (TC_KT * 128);
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      umma_bf16(tS[kt & 1], umma_smem_desc_sw128(a + 32 * k, 16, 1024), umma_smem_desc_sw128(bb + 32 * k, 16, 1024),
+                idesc1, k);
+    umma_commit(&bar_s[kt & 1]);
+  };
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, 16384);
+    tma_load_2d(&tm_qkv, bar_q, sQ, head * 32, (int)(tok0 + qt * TC_QT));
+    for (int j = 0; j < nkv_boxes; ++j) {
+      mbar_arrive_expect_tx(&bar_kv[j], 16384);
+      tma_load_2d(&tm_qkv, &bar_kv[j], sKV + j * 16384, kv_col, (int)(tok0 + j * 128));
+    }
+    mbar_wait(bar_q, 0);
+    mbar_wait(&bar_kv[0], 0);
+    tc_fence_after();
+    issue_mma1(0);
+  }
+
+  const int qrow = qt * TC_QT + tid;                       // position of this thread's query in the sequence
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;   // TMEM lane quarter of this warp
+  float m = -INFINITY, l = 0.f;
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    if (tid == 0 && kt + 1 < nkt) {
+      if (((kt + 1) & 1) == 0) mbar_wait(&bar_kv[(kt + 1) >> 1], 0);   // first use of a new [k|v] box
+      tc_fence_after();
+      issue_mma1(kt + 1);
+    }
+    mbar_wait(&bar_s[kt & 1], (kt >> 1) & 1);
+    tc_fence_after();
+    uint32_t sraw[2][32];
+    tmem_ld_32x32(tS[kt & 1] + lane_off, sraw[0]);
+    tmem_ld_32x32(tS[kt & 1] + lane_off + 32, sraw[1]);
+    tmem_ld_wait();
+    float s[64];
+    float mx = -INFINITY;
+    const bool diag = (kt >= 2 * qt);                      // tiles that straddle the causal boundary
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+      float v = __uint_as_float(sraw[j >> 5][j & 31]) * scale_log2;
+      if (diag && kt * TC_KT + j > qrow) v = -INFINITY;
+      s[j] = v;
+      mx = fmaxf(mx, v);
+    }
+    const float mn = fmaxf(m, mx);
+    // rows of the upper half of the last tile see no key at all in it: keep them inert (mn stays finite from kt = 0)
+    const float alpha = exp2f(m - mn);
+    m = mn;
+    l *= alpha;
+    if (kt > 0) {
+      mbar_wait(bar_o, (kt - 1) & 1);                      // MMA2(kt-1) done: O readable, P tile reusable
+      tc_fence_after();
+      if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+        uint32_t ov[32];
+        tmem_ld_32x32(tO + lane_off + 32, ov);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * alpha);
+        tmem_st_32x32(tO + lane_off + 32, ov);
+        tmem_st_wait();
+      }
+    }
+    // P = exp2(s - m) -> bf16, swizzled K-major row of the P tile (128 bytes = 8 x 16-byte pieces)
+    uint8_t* prow = sP + tid * 128;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float p0 = exp2f(s[c * 8 + 2 * e] - m), p1 = exp2f(s[c * 8 + 2 * e + 1] - m);
+        w[e] = pack_bf16(p0, p1);
+        l += bf16_lo(w[e]) + bf16_hi(w[e]);
+      }
+      *reinterpret_cast<uint4*>(prow + ((c ^ (tid & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a = smem_u32(sP);
+      const uint32_t bb = smem_u32(sKV) + kt * (TC_KT * 128);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tO, umma_smem_desc_sw128(a + 32 * k, 16, 1024), umma_smem_desc_sw128(bb + 2048 * k, 8192, 1024),
+                  idesc2, (kt | k) != 0 ? 1u : 0u);
+      umma_commit(bar_o);
+    }
+  }
+  mbar_wait(bar_o, (nkt - 1) & 1);
+  tc_fence_after();
+  uint32_t ov[32];
+  tmem_ld_32x32(tO + lane_off + 32, ov);
+  tmem_ld_wait();
+  const float inv = 1.0f / l;
+  __nv_bfloat16* orow = o + (tok0 + qrow) * ldo + head * 32;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 v;
+    v.x = pack_bf16(__uint_as_float(ov[8 * c + 0]) * inv, __uint_as_float(ov[8 * c + 1]) * inv);
+    v.y = pack_bf16(__uint_as_float(ov[8 * c + 2]) * inv, __uint_as_float(ov[8 * c + 3]) * inv);
+    v.z = pack_bf16(__uint_as_float(ov[8 * c + 4]) * inv, __uint_as_float(ov[8 * c + 5]) * inv);
+    v.w = pack_bf16(__uint_as_float(ov[8 * c + 6]) * inv, __uint_as_float(ov[8 * c + 7]) * inv);
+    reinterpret_cast<uint4*>(orow)[c] = v;
+  }
+  lse[(tok0 + qrow) * Nq + head] = m + log2f(l);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+int g_attn_train_impl = 0;   // 0 = tcgen05 forward when the shape allows (default), 1 = mma.sync everywhere
+
+// Returns MPX_ERR_UNSUPPORTED (without setting an error) when the shape is not covered; the caller falls back.
+int attn_fwd_tc_launch(const mpx_attn_train_args* a, cudaStream_t stream) {
+  const long long QD = (long long)a->Nq * 32;
+  const bool packed = a->Nkv == 1 && a->D == 32 && a->T % TC_QT == 0 && a->T / TC_QT <= 8 && a->ldq == a->ldk &&
+                      a->ldk == a->ldv && a->k == a->q + QD && a->v == a->k + 32 && a->ldq >= QD + 64 &&
+                      (a->ldq % 8) == 0 && (a->ldo % 8) == 0;
+  if (!packed || g_attn_train_impl != 0) return MPX_ERR_UNSUPPORTED;
+  CUtensorMap tm;
+  const long long M = (long long)a->B * a->T;
+  int rc = make_tmap_bf16_2d(&tm, a->q, (uint64_t)M, (uint64_t)a->ldq, (uint64_t)a->ldq, 64, 128);
+  if (rc) return rc;
+  const int nqt = a->T / TC_QT;
+  const size_t smem = 1024 + 32768 + (size_t)nqt * 16384 + 256;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(attn_fwd_tc): %s", cudaGetErrorString(e));
+      return MPX_ERR_CUDA;
+    }
+    attr = smem;
+  }
+  const float scale_log2 = (1.0f / sqrtf((float)a->D)) * 1.4426950408889634f;
+  dim3 grid(nqt, a->Nq, a->B);
+  attn_fwd_tc_kernel<<<grid, 128, smem, stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(a->o), a->ldo, a->lse, a->T, a->Nq,
+                                                 (int)QD, scale_log2);
+  return check_launch("attn_fwd_tc_kernel");
+}
+
+}  // namespace mpx

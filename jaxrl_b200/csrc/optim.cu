@@ -12,12 +12,13 @@ namespace mpx {
 __global__ void __launch_bounds__(256) adamw_update_kernel(
     const float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu, float* __restrict__ nu,
     float* __restrict__ upd, long long n, const int* __restrict__ step, float lr0, float total_steps, float b1, float b2,
-    float eps, float wd, float grad_scale, double* __restrict__ partials) {
+    float eps, float wd, float grad_scale, int nesterov, double* __restrict__ partials) {
   __shared__ double s_sum[256];
   const int t = step[0];
   const float frac = 1.0f - fminf((float)t, total_steps) / total_steps;
   const float lr = lr0 * frac;
   const float bc1 = 1.0f - powf(b1, (float)(t + 1));
+  const float bc1n = 1.0f - powf(b1, (float)(t + 2));
   const float bc2 = 1.0f - powf(b2, (float)(t + 1));
   double acc = 0.0;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -28,7 +29,9 @@ __global__ void __launch_bounds__(256) adamw_update_kernel(
     const float v = b2 * nu[i] + (1.0f - b2) * gi * gi;
     mu[i] = m;
     nu[i] = v;
-    const float u = -lr * ((m / bc1) / (sqrtf(v / bc2) + eps) + wd * p[i]);
+    // optax.scale_by_adam(nesterov=True): mu_hat = b1 * bias_corr(mu, t+2) + (1-b1) * bias_corr(g, t+1)
+    const float mhat = nesterov ? (b1 * (m / bc1n) + (1.0f - b1) * (gi / bc1)) : (m / bc1);
+    const float u = -lr * (mhat / (sqrtf(v / bc2) + eps) + wd * p[i]);
     upd[i] = u;
     acc += (double)u * (double)u;
   }
@@ -142,6 +145,144 @@ __global__ void transpose_tb4_kernel(const uint32_t* __restrict__ src, uint32_t*
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ Muon
+// optax.contrib.muon as chained by the reference (optimizer.py:25-37): matrices labelled "muon" get
+//   mu = beta*mu + (1-beta)*g ; mu_hat = beta*bc(mu, t+2) + (1-beta)*bc(g, t+1)           (nesterov)
+//   X = mu_hat oriented rows <= cols ; X /= (||X||_F + eps) ; 5 x Newton-Schulz: A = X X^T, B = c1 A + c2 A A,
+//   X = c0 X + B X ; update = -lr * ( sqrt(max(1, out/in)) * X + weight_decay * p )
+// everything else goes through AdamW(nesterov=True); clip_by_global_norm then acts on the combined update.
+// Newton-Schulz runs in fp32 (as optax does) on small matrices: batched SIMT GEMM, one grid.z slice per matrix.
+struct MuonMat {
+  long long off;       // offset of the parameter in the flat buffers
+  int rows, cols;      // parameter shape (in, out)
+  int r, c;            // oriented shape, r <= c
+  int transposed;      // 1 if the oriented matrix is the transpose of the parameter
+  int _pad;
+  long long xoff;      // offset of this matrix in the X / X' workspaces (r*c floats)
+  long long aoff;      // offset in the A / B workspaces (r*r floats)
+};
+
+__global__ void __launch_bounds__(256) muon_prepare_kernel(const MuonMat* __restrict__ mats, const float* __restrict__ g,
+                                                           float* __restrict__ mu, float* __restrict__ X,
+                                                           float* __restrict__ norm2, const int* __restrict__ step,
+                                                           float beta, float grad_scale) {
+  __shared__ float s_sum[256];
+  const MuonMat mt = mats[blockIdx.y];
+  const int t = step[0];
+  const float bc1 = 1.0f - powf(beta, (float)(t + 1));
+  const float bc2 = 1.0f - powf(beta, (float)(t + 2));
+  const long long n = (long long)mt.rows * mt.cols;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float gi = g[mt.off + i] * grad_scale;
+    const float m = beta * mu[mt.off + i] + (1.0f - beta) * gi;
+    mu[mt.off + i] = m;
+    const float mh = beta * (m / bc2) + (1.0f - beta) * (gi / bc1);
+    const int pr = (int)(i / mt.cols), pc = (int)(i % mt.cols);
+    const long long xi = mt.transposed ? (long long)pc * mt.c + pr : i;
+    X[mt.xoff + xi] = mh;
+    acc += mh * mh;
+  }
+  s_sum[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(norm2 + blockIdx.y, s_sum[0]);
+}
+
+// Batched C = alpha * A(op) * B + beta * D on row-major fp32 matrices; 64x64 tile, 16-wide k slab, 4x4 per thread.
+// mode 0: C(r,r) = X X^T * inv_norm^2 (first iteration folds the Frobenius normalisation in) ;
+// mode 1: C(r,r) = c2 * A A + c1 * A ; mode 2: C(r,c) = B X * s + c0 * X * s  (s = inv_norm on the first iteration)
+__global__ void __launch_bounds__(256) muon_ns_gemm_kernel(const MuonMat* __restrict__ mats, const float* __restrict__ Xin,
+                                                           float* __restrict__ Xout, float* __restrict__ Abuf,
+                                                           float* __restrict__ Bbuf, const float* __restrict__ norm2,
+                                                           int mode, int first, float c0, float c1, float c2, float eps) {
+  __shared__ float sA[16][64 + 1], sB[16][64 + 1];
+  const MuonMat mt = mats[blockIdx.z];
+  const int r = mt.r, c = mt.c;
+  const int M = r, N = (mode == 2) ? c : r, K = (mode == 0) ? c : r;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  if (m0 >= M || n0 >= N) return;
+  const float* A;  long long lda;      // A[i][k]
+  const float* B;  long long sbk, sbj; // B[k][j] = B[k*sbk + j*sbj]
+  const float* X = Xin + mt.xoff;
+  if (mode == 0) { A = X; lda = c; B = X; sbk = 1; sbj = c; }
+  else if (mode == 1) { A = Abuf + mt.aoff; lda = r; B = Abuf + mt.aoff; sbk = r; sbj = 1; }
+  else { A = Bbuf + mt.aoff; lda = r; B = X; sbk = c; sbj = 1; }
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      const int kk = i % 16, mm = i / 16;
+      sA[kk][mm] = (m0 + mm < M && k0 + kk < K) ? A[(long long)(m0 + mm) * lda + k0 + kk] : 0.f;
+      const int kb = (sbj == 1) ? i / 64 : i % 16, nb = (sbj == 1) ? i % 64 : i / 16;
+      sB[kb][nb] = (n0 + nb < N && k0 + kb < K) ? B[(long long)(k0 + kb) * sbk + (long long)(n0 + nb) * sbj] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sB[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const float inv = first ? 1.0f / (sqrtf(norm2[blockIdx.z]) + eps) : 1.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int mm = m0 + ty * 4 + i;
+    if (mm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int nn = n0 + tx * 4 + j;
+      if (nn >= N) continue;
+      if (mode == 0) Abuf[mt.aoff + (long long)mm * r + nn] = acc[i][j] * inv * inv;
+      else if (mode == 1) Bbuf[mt.aoff + (long long)mm * r + nn] = c2 * acc[i][j] + c1 * A[(long long)mm * r + nn];
+      else Xout[mt.xoff + (long long)mm * c + nn] = (acc[i][j] + c0 * X[(long long)mm * c + nn]) * inv;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) muon_finish_kernel(const MuonMat* __restrict__ mats, const float* __restrict__ X,
+                                                          const float* __restrict__ p, float* __restrict__ upd,
+                                                          const int* __restrict__ step, float lr0, float total_steps,
+                                                          float wd, double* __restrict__ partials) {
+  __shared__ double s_sum[256];
+  const MuonMat mt = mats[blockIdx.y];
+  const int t = step[0];
+  const float lr = lr0 * (1.0f - fminf((float)t, total_steps) / total_steps);
+  const float shape_scale = sqrtf(fmaxf(1.0f, (float)mt.cols / (float)mt.rows));   // sqrt(max(1, fan_out / fan_in))
+  const long long n = (long long)mt.rows * mt.cols;
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int pr = (int)(i / mt.cols), pc = (int)(i % mt.cols);
+    const long long xi = mt.transposed ? (long long)pc * mt.c + pr : i;
+    const float u = -lr * (shape_scale * X[mt.xoff + xi] + wd * p[mt.off + i]);
+    upd[mt.off + i] = u;
+    acc += (double)u * (double)u;
+  }
+  s_sum[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = s_sum[0];
+}
+
 }  // namespace mpx
 
 using namespace mpx;
@@ -177,7 +318,7 @@ extern "C" int mpx_adamw_step(float* params, const float* grads, float* mu, floa
   double* partials = reinterpret_cast<double*>(workspace);
   cudaStream_t s = (cudaStream_t)stream;
   adamw_update_kernel<<<grid, 256, 0, s>>>(params, grads, mu, nu, update_scratch, n, step, lr0, total_steps, b1, b2, eps,
-                                           weight_decay, grad_scale, partials);
+                                           weight_decay, grad_scale, 0, partials);
   apply_update_kernel<<<grid, 256, 0, s>>>(params, update_scratch, n, partials, grid, max_norm, step, update_norm_out);
   step_inc_kernel<<<1, 1, 0, s>>>(step);
   return check_launch("mpx_adamw_step");
@@ -188,4 +329,57 @@ extern "C" int mpx_prep_weights(const mpx_prep_desc* descs_device, int ndesc, mp
   dim3 grid(64, ndesc);
   prep_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(descs_device, ndesc);
   return check_launch("mpx_prep_weights");
+}
+
+// Muon + AdamW(nesterov) partition (optimizer.py:25-37).  Flat buffers of n elements: [0, n_adam) are the AdamW
+// parameters, the matrices described by `mats` (device array of nmat entries, see MuonMat) live in [n_adam, n).
+// ns_ws: fp32 workspace >= 2*sum(r*c) + 2*sum(r*r) + nmat floats.  workspace >= mpx_muon_workspace_bytes(n, nmat).
+extern "C" size_t mpx_muon_workspace_bytes(long long n, int nmat) {
+  return (size_t)(opt_grid(n > 0 ? n : 1) + (size_t)nmat * 8) * sizeof(double);
+}
+
+extern "C" int mpx_muon_step(float* params, const float* grads, float* mu, float* nu, float* update_scratch,
+                             long long n, long long n_adam, const void* mats, int nmat, long long x_total,
+                             long long a_total, int max_r, int max_c, float* ns_ws, int* step, float lr0,
+                             float total_steps, float adam_b1, float adam_b2, float eps, float weight_decay,
+                             float muon_beta, int ns_steps, float max_norm, float grad_scale, float* update_norm_out,
+                             void* workspace, mpx_stream_t stream) {
+  MPX_REQUIRE(params && grads && mu && nu && update_scratch && step && workspace && n > 0, "mpx_muon_step: bad arguments");
+  MPX_REQUIRE(n_adam >= 0 && n_adam <= n && (nmat == 0 || (mats && ns_ws)), "mpx_muon_step: bad partition");
+  MPX_REQUIRE(total_steps > 0.f && ns_steps >= 1, "mpx_muon_step: bad schedule");
+  cudaStream_t s = (cudaStream_t)stream;
+  double* partials = reinterpret_cast<double*>(workspace);
+  const int agrid = n_adam > 0 ? opt_grid(n_adam) : 0;
+  if (n_adam > 0)
+    adamw_update_kernel<<<agrid, 256, 0, s>>>(params, grads, mu, nu, update_scratch, n_adam, step, lr0, total_steps,
+                                              adam_b1, adam_b2, eps, weight_decay, grad_scale, 1, partials);
+  int nparts = agrid;
+  if (nmat > 0) {
+    const MuonMat* mm = reinterpret_cast<const MuonMat*>(mats);
+    float* X0 = ns_ws;
+    float* X1 = X0 + x_total;
+    float* Ab = X1 + x_total;
+    float* Bb = Ab + a_total;
+    float* norm2 = Bb + a_total;
+    cudaMemsetAsync(norm2, 0, (size_t)nmat * sizeof(float), s);
+    muon_prepare_kernel<<<dim3(8, nmat), 256, 0, s>>>(mm, grads, mu, X0, norm2, step, muon_beta, grad_scale);
+    const float c0 = 3.4445f, c1 = -4.7750f, c2 = 2.0315f;
+    float* xin = X0;
+    float* xout = X1;
+    for (int it = 0; it < ns_steps; ++it) {
+      const int first = it == 0;
+      dim3 gA(ceil_div(max_r, 64), ceil_div(max_r, 64), nmat), gX(ceil_div(max_c, 64), ceil_div(max_r, 64), nmat);
+      muon_ns_gemm_kernel<<<gA, 256, 0, s>>>(mm, xin, xout, Ab, Bb, norm2, 0, first, c0, c1, c2, eps);
+      muon_ns_gemm_kernel<<<gA, 256, 0, s>>>(mm, xin, xout, Ab, Bb, norm2, 1, 0, c0, c1, c2, eps);
+      muon_ns_gemm_kernel<<<gX, 256, 0, s>>>(mm, xin, xout, Ab, Bb, norm2, 2, first, c0, c1, c2, eps);
+      float* tmp = xin; xin = xout; xout = tmp;
+    }
+    muon_finish_kernel<<<dim3(8, nmat), 256, 0, s>>>(mm, xin, params, update_scratch, step, lr0, total_steps,
+                                                     weight_decay, partials + agrid);
+    nparts += 8 * nmat;
+  }
+  const int pgrid = opt_grid(n);
+  apply_update_kernel<<<pgrid, 256, 0, s>>>(params, update_scratch, n, partials, nparts, max_norm, step, update_norm_out);
+  step_inc_kernel<<<1, 1, 0, s>>>(step);
+  return check_launch("mpx_muon_step");
 }

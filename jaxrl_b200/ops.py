@@ -377,6 +377,18 @@ def adamw_step(params, grads, mu, nu, scratch, step, lr0, total_steps, b1, b2, e
                              stream()), "mpx_adamw_step")
 
 
+def muon_step(params, grads, mu, nu, scratch, n_adam: int, table, nmat: int, x_total: int, a_total: int, max_r: int,
+              max_c: int, ns_ws, step, lr0, total_steps, b1, b2, eps, wd, max_norm, grad_scale=1.0, muon_beta=0.95,
+              ns_steps=5, norm_out=None, ws=None):
+    """optax.contrib.muon partition (optimizer.py:25-37): Muon on the labelled matrices, AdamW(nesterov) elsewhere."""
+    n = params.numel()
+    if ws is None:
+        ws = torch.empty(lib.mpx_muon_workspace_bytes(n, nmat), dtype=torch.uint8, device=params.device)
+    check(lib.mpx_muon_step(ptr(params), ptr(grads), ptr(mu), ptr(nu), ptr(scratch), n, n_adam, ptr(table), nmat, x_total,
+                            a_total, max_r, max_c, ptr(ns_ws), ptr(step), lr0, float(total_steps), b1, b2, eps, wd,
+                            muon_beta, ns_steps, max_norm, grad_scale, ptr(norm_out), ptr(ws), stream()), "mpx_muon_step")
+
+
 def prep_weights(descs_device, ndesc: int):
     check(lib.mpx_prep_weights(ptr(descs_device), ndesc, stream()), "mpx_prep_weights")
 

@@ -64,6 +64,14 @@ def param_specs(cfg: ModelConfig) -> List[Tuple[str, Tuple[int, ...], str]]:
     return specs
 
 
+MUON_EXCLUDE_TOP = {"value_head", "action_encoder", "reward_encoder", "obs_encoder", "obs_decoder"}   # optimizer.py:42-48
+
+
+def is_muon_param(name: str, shape) -> bool:
+    """muon_dim_numbers_fn (optimizer.py:51-69): 2-D leaves whose top-level module is not excluded."""
+    return len(shape) == 2 and name.split(".")[0] not in MUON_EXCLUDE_TOP
+
+
 def _init(shape, kind: str, gen: torch.Generator) -> torch.Tensor:
     if kind == "zeros":
         return torch.zeros(shape)
@@ -91,16 +99,24 @@ class ParamStore:
 
     def __init__(self, cfg: ModelConfig, device, seed: int = 0, bias_noise: float = 0.0):
         self.cfg = cfg
-        self.specs = param_specs(cfg)
+        specs = param_specs(cfg)
+        # AdamW-labelled leaves first, Muon-labelled matrices last: the optimizer kernels partition the flat buffer
+        self.specs = [sp for sp in specs if not is_muon_param(sp[0], sp[1])] + \
+                     [sp for sp in specs if is_muon_param(sp[0], sp[1])]
         self.offsets: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
         off = 0
+        self.n_adam = None
         for name, shape, _ in self.specs:
+            if self.n_adam is None and is_muon_param(name, shape):
+                self.n_adam = off
             n = 1
             for s in shape:
                 n *= s
             self.offsets[name] = (off, shape)
             off += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.numel = off
+        if self.n_adam is None:
+            self.n_adam = off
         gen = torch.Generator().manual_seed(seed)
         host = torch.zeros(off, dtype=torch.float32)
         for name, shape, kind in self.specs:
@@ -113,6 +129,25 @@ class ParamStore:
         self.grad = torch.zeros_like(self.flat)
         self.views = {n: self._view(self.flat, n) for n, _, _ in self.specs}
         self.gviews = {n: self._view(self.grad, n) for n, _, _ in self.specs}
+
+    def muon_table(self):
+        """-> (device uint8 tensor of MuonMat records, nmat, x_total, a_total, max_r, max_c) for mpx_muon_step."""
+        import struct
+        recs, xoff, aoff, max_r, max_c = [], 0, 0, 1, 1
+        for name, shape, _ in self.specs:
+            if not is_muon_param(name, shape):
+                continue
+            off, _ = self.offsets[name]
+            rows, cols = shape
+            tr = 1 if rows > cols else 0
+            r, c = (cols, rows) if tr else (rows, cols)
+            recs.append(struct.pack("<q6i2q", off, rows, cols, r, c, tr, 0, xoff, aoff))
+            xoff += r * c
+            aoff += r * r
+            max_r, max_c = max(max_r, r), max(max_c, c)
+        raw = b"".join(recs)
+        dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.flat.device) if recs else None
+        return dev, len(recs), xoff, aoff, max_r, max_c
 
     def _view(self, buf: torch.Tensor, name: str) -> torch.Tensor:
         o, shape = self.offsets[name]

@@ -104,6 +104,13 @@ class PPOTrainer:
         n = self.engine.p.numel
         o = SimpleNamespace(mu=f(n), nu=f(n), scratch=f(n), step=torch.zeros(1, dtype=I32, device=dev),
                             norm=f(1), ws=torch.empty(_lib.lib.mpx_adamw_workspace_bytes(n), dtype=torch.uint8, device=dev))
+        if self.opt.type == "muon":
+            tab, nmat, xt, at, mr, mc = self.engine.p.muon_table()
+            o.muon = SimpleNamespace(table=tab, nmat=nmat, x_total=xt, a_total=at, max_r=mr, max_c=mc,
+                                     ns_ws=f(2 * xt + 2 * at + max(nmat, 1)),
+                                     ws=torch.empty(_lib.lib.mpx_muon_workspace_bytes(n, nmat), dtype=torch.uint8, device=dev))
+        elif self.opt.type != "adamw":
+            raise ValueError(f"Unknown optimizer type: {self.opt.type}")
         self.o = o
         self.noise_off = torch.zeros(1, dtype=torch.int64, device=dev)      # Gumbel stream offset, += T per rollout
         self.ent_coef = torch.full((1,), self.hyp.entropy_coef, dtype=F32, device=dev)
@@ -179,9 +186,15 @@ class PPOTrainer:
         if self.run_optimizer:
             o, opt = self.o, self.opt
             total = self.run.update_steps * self.hyp.minibatch_count * self.hyp.epoch_count
-            ops.adamw_step(eng.p.flat, eng.p.grad, o.mu, o.nu, o.scratch, o.step, opt.learning_rate, total, opt.beta1,
-                           opt.beta2, opt.eps, opt.weight_decay, opt.max_norm, grad_scale=gscale,
-                           norm_out=o.norm, ws=o.ws)
+            if opt.type == "muon":        # optimizer.py:25-37 (muon's own eps/beta defaults; adam_b1/b2 from the config)
+                m = o.muon
+                ops.muon_step(eng.p.flat, eng.p.grad, o.mu, o.nu, o.scratch, eng.p.n_adam, m.table, m.nmat, m.x_total,
+                              m.a_total, m.max_r, m.max_c, m.ns_ws, o.step, opt.learning_rate, total, opt.beta1, opt.beta2,
+                              1e-8, opt.weight_decay, opt.max_norm, grad_scale=gscale, norm_out=o.norm, ws=m.ws)
+            else:                         # optimizer.py:12-23
+                ops.adamw_step(eng.p.flat, eng.p.grad, o.mu, o.nu, o.scratch, o.step, opt.learning_rate, total, opt.beta1,
+                               opt.beta2, opt.eps, opt.weight_decay, opt.max_norm, grad_scale=gscale,
+                               norm_out=o.norm, ws=o.ws)
             eng.stage_weights()
 
     def _update_body(self):

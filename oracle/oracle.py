@@ -427,3 +427,51 @@ def rollout_decode(p: dict, cfg, obs_seq: torch.Tensor, reward_seq: torch.Tensor
     res = {k: torch.stack(v, dim=1) for k, v in out.items()}
     res["carry"] = carry
     return res
+
+
+# --------------------------------------------------------------------------- optimizer (parity unpinned)
+def _ns_orthogonalize(x: torch.Tensor, steps: int = 5, eps: float = 1e-8, coeffs=(3.4445, -4.7750, 2.0315)):
+    """optax.contrib orthogonalize_via_newton_schulz for a 2-D matrix (fp32)."""
+    transposed = x.shape[0] > x.shape[1]
+    if transposed:
+        x = x.t()
+    x = x / (torch.linalg.norm(x) + eps)
+    c0, c1, c2 = coeffs
+    for _ in range(steps):
+        a = x @ x.t()
+        b = c1 * a + c2 * (a @ a)
+        x = c0 * x + b @ x
+    return x.t() if transposed else x
+
+
+def optimizer_step(params: dict, grads: dict, state: dict, t: int, cfg, total_steps: int, is_muon, muon_beta=0.95):
+    """One step of create_optimizer (optimizer.py:7-39) restated from optax 0.2.8: muon partition (nesterov momentum,
+    Newton-Schulz, sqrt(max(1,out/in)), decayed weights, linear LR) + adamw(nesterov=True) for the rest when
+    cfg.type == "muon"; plain optax.adamw when "adamw"; then clip_by_global_norm on the UPDATE.  Returns new params.
+    state: {"mu": {...}, "nu": {...}} (zeros initially); t is the 0-based step count."""
+    lr = cfg.learning_rate * (1.0 - min(t, total_steps) / total_steps)
+    upd = {}
+    for k, p in params.items():
+        g = grads[k]
+        if cfg.type == "muon" and is_muon(k, tuple(p.shape)):
+            m = muon_beta * state["mu"][k] + (1 - muon_beta) * g
+            state["mu"][k] = m
+            mh = muon_beta * (m / (1 - muon_beta ** (t + 2))) + (1 - muon_beta) * (g / (1 - muon_beta ** (t + 1)))
+            o = _ns_orthogonalize(mh)
+            o = o * math.sqrt(max(1.0, p.shape[1] / p.shape[0]))
+            upd[k] = -lr * (o + cfg.weight_decay * p)
+        else:
+            b1, b2 = cfg.beta1, cfg.beta2
+            eps = 1e-8 if cfg.type == "muon" else cfg.eps
+            m = b1 * state["mu"][k] + (1 - b1) * g
+            v = b2 * state["nu"][k] + (1 - b2) * g * g
+            state["mu"][k], state["nu"][k] = m, v
+            if cfg.type == "muon":
+                mh = b1 * (m / (1 - b1 ** (t + 2))) + (1 - b1) * (g / (1 - b1 ** (t + 1)))
+            else:
+                mh = m / (1 - b1 ** (t + 1))
+            vh = v / (1 - b2 ** (t + 1))
+            upd[k] = -lr * (mh / (torch.sqrt(vh) + eps) + cfg.weight_decay * p)
+    gn = math.sqrt(sum(float((u.double() ** 2).sum()) for u in upd.values()))
+    scale = cfg.max_norm / gn if gn >= cfg.max_norm else 1.0
+    return {k: params[k] + upd[k] * scale for k in params}, gn

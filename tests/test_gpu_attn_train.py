@@ -14,9 +14,14 @@ DEV = "cuda"
 BF16 = torch.bfloat16
 
 
-@pytest.mark.parametrize("B,T,Nq,Nkv", [(2, 64, 4, 1), (3, 128, 4, 1), (1, 512, 4, 1), (2, 128, 4, 2), (2, 64, 4, 4)])
-def test_attn_train_fwd_bwd(B, T, Nq, Nkv):
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("B,T,Nq,Nkv", [(2, 64, 4, 1), (3, 128, 4, 1), (1, 512, 4, 1), (5, 256, 4, 1), (2, 128, 4, 2),
+                                        (2, 64, 4, 4)])
+def test_attn_train_fwd_bwd(B, T, Nq, Nkv, impl):
+    """impl 0: tcgen05/TMEM forward where the shape allows (Nkv == 1, T % 128 == 0), impl 1: mma.sync forward."""
     from jaxrl_b200 import ops
+    from jaxrl_b200._lib import lib
+    lib.mpx_debug_set(2, impl)
     D = 32
     gen = torch.Generator().manual_seed(B * 100 + T + Nq + Nkv)
     QD, KD = Nq * D, Nkv * D
@@ -34,10 +39,14 @@ def test_attn_train_fwd_bwd(B, T, Nq, Nkv):
     (ref.float() * dout.float()).sum().backward()
 
     qkv = torch.cat([q.reshape(B * T, QD), k.reshape(B * T, KD), v.reshape(B * T, KD)], dim=1).detach().to(DEV).contiguous()
-    o, lse = ops.attn_train_fwd(qkv, qkv[:, QD:], qkv[:, QD + KD:], B, T, Nq, Nkv, D, QKV, QKV, QKV)
+    try:
+        o, lse = ops.attn_train_fwd(qkv, qkv[:, QD:], qkv[:, QD + KD:], B, T, Nq, Nkv, D, QKV, QKV, QKV)
+        torch.cuda.synchronize()
+    finally:
+        lib.mpx_debug_set(2, 0)
     # flash-style online softmax rounds the UN-normalised probabilities to bf16 (as cuDNN's fused SDPA, the
     # reference's GPU implementation, does); the XLA path rounds after normalising -> up to 2 bf16 ulps apart.
-    assert_close_bf16(o.reshape(B, T, Nq, D), ref, f"attn_train_fwd B{B} T{T} kv{Nkv}", rtol=1.7e-2, abs_floor_frac=1e-2,
+    assert_close_bf16(o.reshape(B, T, Nq, D), ref, f"attn_train_fwd impl{impl} B{B} T{T} kv{Nkv}", rtol=1.7e-2, abs_floor_frac=1e-2,
                       allow_frac=5e-4, max_err_frac=0.25)
     dqkv = torch.zeros(B * T, QKV, dtype=BF16, device=DEV)
     ops.attn_train_bwd(qkv, qkv[:, QD:], qkv[:, QD + KD:], o, dout.reshape(B * T, QD).to(DEV).contiguous(), lse,

@@ -150,3 +150,49 @@ def test_train_forward_and_backward_match_oracle(engine):
         worst = max(worst, rel)
         assert cos > 0.99, f"gradient direction mismatch for {name}: cos={cos}"
         assert rel < 0.1, f"gradient mismatch for {name}: rel l2 {rel}"
+
+
+@pytest.mark.parametrize("opt_type", ["muon", "adamw"])
+def test_optimizer_step_matches_oracle(opt_type):
+    """Muon partition / AdamW + post-clip (optimizer.py:7-39) on the flat buffers vs the torch restatement."""
+    from jaxrl_b200 import _lib, ops
+    from jaxrl_b200.config import OptimizerConfig
+    from jaxrl_b200.params import ParamStore, is_muon_param
+    cfg = replace(CFG, num_layers=1)
+    ps = ParamStore(cfg, DEV, seed=11, bias_noise=0.02)
+    ocfg = OptimizerConfig(type=opt_type)
+    gen = torch.Generator().manual_seed(2)
+    n = ps.numel
+    z = lambda: torch.zeros(n, device=DEV)
+    mu, nu, scratch = z(), z(), z()
+    step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    norm = torch.zeros(1, device=DEV)
+    params = ps.oracle_dict()
+    state = {"mu": {k: torch.zeros_like(v) for k, v in params.items()}, "nu": {k: torch.zeros_like(v) for k, v in params.items()}}
+    total = 100
+    if opt_type == "muon":
+        tab, nmat, xt, at, mr, mc = ps.muon_table()
+        ns_ws = torch.zeros(2 * xt + 2 * at + nmat, device=DEV)
+    for t in range(3):
+        grads = {k: torch.randn(v.shape, generator=gen) * 0.01 for k, v in params.items()}
+        ps.grad.zero_()
+        for k, gview in ps.gviews.items():
+            gview.copy_(grads[k].to(DEV))
+        if opt_type == "muon":
+            ops.muon_step(ps.flat, ps.grad, mu, nu, scratch, ps.n_adam, tab, nmat, xt, at, mr, mc, ns_ws, step,
+                          ocfg.learning_rate, total, ocfg.beta1, ocfg.beta2, 1e-8, ocfg.weight_decay, ocfg.max_norm,
+                          norm_out=norm)
+        else:
+            ops.adamw_step(ps.flat, ps.grad, mu, nu, scratch, step, ocfg.learning_rate, total, ocfg.beta1, ocfg.beta2,
+                           ocfg.eps, ocfg.weight_decay, ocfg.max_norm, norm_out=norm)
+        new_params, gn = O.optimizer_step(params, grads, state, t, ocfg, total, is_muon_param)
+        got = ps.oracle_dict()
+        assert abs(norm.item() - gn) <= 2e-3 * gn, f"update norm {norm.item()} vs {gn}"
+        for k in params:
+            d_ref = new_params[k] - params[k]
+            d_got = got[k] - params[k]
+            rel = (d_got - d_ref).norm().item() / (d_ref.norm().item() + 1e-12)
+            assert rel < 5e-3, f"{opt_type} step {t} {k}: update rel err {rel}"
+        params = new_params
+        ps.load_dict(params)            # keep both sides on identical weights
+    assert step.item() == 3
