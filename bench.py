@@ -227,7 +227,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     # weak scaling: B agents per GPU fixed (the config's 4096), total = world * B
     run_w = replace(run, num_agents=run.num_agents * world)
     B, T = run.num_agents, run.model.max_seq_length
@@ -276,7 +277,7 @@ def main():
     # ---- device-resident arm (value)
     trainer = PPOTrainer(run_w, rank=rank, world=world, use_graphs=not args.no_graphs)
     trainer.warmup()
-    launches = count_launches(trainer) if rank == 0 else 0
+    launches = count_launches(trainer)      # every rank: the pass contains the collectives of one update
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -285,6 +286,7 @@ def main():
     logs = trainer.logs()
     value = world * B * T * args.steps / secs
     roof = decode_attention_roofline(trainer, peaks) if rank == 0 else None
+    phases = trainer.timed_phases()
     del trainer
     torch.cuda.empty_cache()
 
@@ -317,7 +319,7 @@ def main():
                        "l2": "working set (KV caches + activations, >2 GB) larger than the 126 MB L2; no flush",
                        "cuda_graphs": not args.no_graphs},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
-            "roofline": roof, "cpu_baseline": cb, "losses": logs,
+            "roofline": roof, "cpu_baseline": cb, "losses": logs, "phases_ms": phases,
             "published_reference": "3.8M+ steps/s on 1x RTX 5090 (README.md:10), other hardware",
         }
         print(json.dumps(line), flush=True)

@@ -121,6 +121,12 @@ typedef struct {
 } mpx_glu_up_args;
 int mpx_glu_up(const mpx_glu_up_args* a, mpx_stream_t stream);
 
+/* Whole GLU block + residual in one kernel (feed_forward.py:73-78 and the residual add of network.py:167-170):
+ * out = bf16(residual + bf16(h @ Wdown)), h = bf16(bf16(gelu(bf16(x@Wup))) * bf16(x@Wgate)); h stays on chip.
+ * wt_ug64 is (2F,H) packed in 128-row tiles [64 up rows | 64 gate rows]; wt_d is Wdown^T (H,F).  H must be 128. */
+int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const mpx_bf16* wt_d, const mpx_bf16* residual,
+                  mpx_bf16* out, int M, int H, int F, mpx_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------- decode attention
  * Decode branch of AttentionBlock.__call__, attention.py:136-150 (jax.nn.dot_product_attention with
  * key_value_seq_lengths): one RoPE'd query token per agent against that agent's KV ring cache (already holding

@@ -89,6 +89,7 @@ for _name in ("mpx_linear", "mpx_linear_wgrad", "mpx_qkv_rope", "mpx_glu_up", "m
               "mpx_attn_train_fwd", "mpx_attn_train_bwd"):
     getattr(lib, _name).argtypes = [c_p, c_p]
 lib.mpx_linear_f32w.argtypes = [c_p, c_ll, c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_p]
+lib.mpx_glu_fused.argtypes = [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p]
 lib.mpx_rmsnorm_fwd.argtypes = [c_p, c_p, c_f, c_p, c_ll, c_i, c_p]
 lib.mpx_rmsnorm_bwd.argtypes = [c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_ll, c_i, c_p]
 lib.mpx_glu_bwd.argtypes = [c_p, c_p, c_p, c_p, c_ll, c_i, c_p]

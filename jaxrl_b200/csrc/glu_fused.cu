@@ -1,0 +1,287 @@
+// Fused GLU feed-forward block (reference GLUBlock.__call__, mapox_trainer/model/feed_forward.py:73-78, plus the
+// residual add of TransformerBlock, network.py:167-170):
+//     out = bf16( residual + bf16( bf16( bf16(gelu(bf16(x@Wup))) * bf16(x@Wgate) ) @ Wdown ) )
+// in ONE kernel: the (M, F) hidden activation never leaves the SM.  Two chained tcgen05 GEMMs per 64-wide chunk of
+// the hidden dimension (FlashAttention-style): MMA1 writes [u_c | g_c] (128 x 128 fp32) to TMEM, the epilogue warps
+// turn it into the bf16 h_c tile in shared memory (SW128 K-major, the A operand of MMA2), MMA2 accumulates
+// h_c @ Wdown_c^T into a second TMEM accumulator.  MMA1 of chunk c+1 overlaps the activation math of chunk c.
+//
+// Roles (192 threads): warp 0 TMA producer (x tile + weight ring), warp 1 MMA issuer / TMEM owner, warps 2-5
+// activation + output epilogue (thread = row).  H (model width) must be 128; F % 64 == 0.
+// Used by the rollout decode step, where the unfused pair (mpx_glu_up + mpx_linear) is launch/latency bound.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.h"
+
+namespace mpx {
+
+constexpr int GF_STAGES = 6;
+constexpr int GF_STAGE_BYTES = 16384;   // [128 rows x 64 cols] bf16, SW128
+
+struct GluFusedParams {
+  int M, F;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out;
+};
+
+__global__ void __launch_bounds__(192, 1)
+glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_x,
+                 const __grid_constant__ CUtensorMap tm_wug, const __grid_constant__ CUtensorMap tm_wd) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sX = smem;                         // 2 x 16 KB: x tile, K blocks 0 and 1
+  uint8_t* sH = smem + 32768;                 // 2 x 16 KB: h chunk double buffer
+  uint8_t* sW = smem + 65536;                 // GF_STAGES x 16 KB weight ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + GF_STAGES * GF_STAGE_BYTES);
+  uint64_t* w_full = bars;                    // [GF_STAGES]
+  uint64_t* w_empty = bars + GF_STAGES;       // [GF_STAGES]
+  uint64_t* x_full = bars + 2 * GF_STAGES;
+  uint64_t* x_empty = x_full + 1;
+  uint64_t* ug_full = x_full + 2;             // [2]
+  uint64_t* ug_empty = x_full + 4;            // [2]
+  uint64_t* h_full = x_full + 6;              // [2]
+  uint64_t* h_empty = x_full + 8;             // [2]
+  uint64_t* d_full = x_full + 10;
+  uint64_t* d_empty = x_full + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks = p.F / 64;
+  const int m_tiles = (p.M + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_wug);
+    tma_prefetch_desc(&tm_wd);
+    for (int s = 0; s < GF_STAGES; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    mbar_init(x_full, 1);
+    mbar_init(x_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&ug_full[b], 1);
+      mbar_init(&ug_empty[b], 4);
+      mbar_init(&h_full[b], 4);
+      mbar_init(&h_empty[b], 1);
+    }
+    mbar_init(d_full, 1);
+    mbar_init(d_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tUG[2] = {tmem_base, tmem_base + 128};
+  const uint32_t tD = tmem_base + 256;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t wphase = 0, xphase = 0;
+      auto load_w = [&](const CUtensorMap* tm, int c0, int c1) {
+        mbar_wait(&w_empty[stage], wphase ^ 1);
+        mbar_arrive_expect_tx(&w_full[stage], GF_STAGE_BYTES);
+        tma_load_2d(tm, &w_full[stage], sW + stage * GF_STAGE_BYTES, c0, c1);
+        if (++stage == GF_STAGES) { stage = 0; wphase ^= 1; }
+      };
+      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+        mbar_wait(x_empty, xphase ^ 1);
+        mbar_arrive_expect_tx(x_full, 32768);
+        tma_load_2d(&tm_x, x_full, sX, 0, tile * 128);
+        tma_load_2d(&tm_x, x_full, sX + 16384, 64, tile * 128);
+        xphase ^= 1;
+        // weight order == MMA issue order: UG_0, then for each c: UG_{c+1} (if any), D_c
+        load_w(&tm_wug, 0, 0);
+        load_w(&tm_wug, 64, 0);
+        for (int c = 0; c < nchunks; ++c) {
+          if (c + 1 < nchunks) {
+            load_w(&tm_wug, 0, (c + 1) * 128);
+            load_w(&tm_wug, 64, (c + 1) * 128);
+          }
+          load_w(&tm_wd, c * 64, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+      int stage = 0;
+      uint32_t wphase = 0, xphase = 0, dphase = 0;
+      uint32_t ug_ph[2] = {0, 0}, h_ph[2] = {0, 0};
+      auto mma1 = [&](int c, bool last) {     // [u_c | g_c] = x . Wug_c^T
+        const int b = c & 1;
+        mbar_wait(&ug_empty[b], ug_ph[b] ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < 2; ++kb) {
+          mbar_wait(&w_full[stage], wphase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(sX + kb * 16384);
+          const uint32_t sb = smem_u32(sW + stage * GF_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tUG[b], umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024),
+                      idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&w_empty[stage]);
+          if (++stage == GF_STAGES) { stage = 0; wphase ^= 1; }
+        }
+        umma_commit(&ug_full[b]);
+        if (last) umma_commit(x_empty);
+        ug_ph[b] ^= 1;
+      };
+      auto mma2 = [&](int c, bool last) {     // acc_d += h_c . Wd_c^T
+        const int b = c & 1;
+        mbar_wait(&h_full[b], h_ph[b]);
+        h_ph[b] ^= 1;
+        mbar_wait(&w_full[stage], wphase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(sH + b * 16384);
+        const uint32_t sb = smem_u32(sW + stage * GF_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tD, umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024), idesc,
+                    (c | k) != 0 ? 1u : 0u);
+        umma_commit(&w_empty[stage]);
+        if (++stage == GF_STAGES) { stage = 0; wphase ^= 1; }
+        umma_commit(&h_empty[b]);
+        if (last) umma_commit(d_full);
+      };
+      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+        mbar_wait(x_full, xphase);
+        xphase ^= 1;
+        mbar_wait(d_empty, dphase ^ 1);       // previous tile's output accumulator has been drained
+        dphase ^= 1;
+        tc_fence_after();
+        mma1(0, nchunks == 1);
+        for (int c = 0; c < nchunks; ++c) {
+          if (c + 1 < nchunks) mma1(c + 1, c + 2 == nchunks);
+          mma2(c, c + 1 == nchunks);
+        }
+      }
+    }
+  } else {
+    // ================================ activation / output warps ================================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                       // row within the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    uint32_t ug_ph[2] = {0, 0}, h_ph[2] = {0, 0}, dphase = 0;
+    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+      const long long row = (long long)tile * 128 + r;
+      uint4 res[16];
+      if (row < p.M) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + row * 128);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) res[i] = r4[i];
+      }
+      for (int c = 0; c < nchunks; ++c) {
+        const int b = c & 1;
+        mbar_wait(&ug_full[b], ug_ph[b]);
+        ug_ph[b] ^= 1;
+        tc_fence_after();
+        uint32_t u0[32], u1[32], g0[32], g1[32];
+        tmem_ld_32x32(tUG[b] + lane_off, u0);
+        tmem_ld_32x32(tUG[b] + lane_off + 32, u1);
+        tmem_ld_32x32(tUG[b] + lane_off + 64, g0);
+        tmem_ld_32x32(tUG[b] + lane_off + 96, g1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ug_empty[b]);
+        uint32_t hw[32];                                       // 64 bf16 = this row's h chunk
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float ua = bf16_round(__uint_as_float(u0[2 * i])), ub = bf16_round(__uint_as_float(u0[2 * i + 1]));
+          const float ga = bf16_round(__uint_as_float(g0[2 * i])), gb = bf16_round(__uint_as_float(g0[2 * i + 1]));
+          hw[i] = pack_bf16(bf16_round(gelu_tanh(ua)) * ga, bf16_round(gelu_tanh(ub)) * gb);
+          const float uc = bf16_round(__uint_as_float(u1[2 * i])), ud = bf16_round(__uint_as_float(u1[2 * i + 1]));
+          const float gc = bf16_round(__uint_as_float(g1[2 * i])), gd = bf16_round(__uint_as_float(g1[2 * i + 1]));
+          hw[16 + i] = pack_bf16(bf16_round(gelu_tanh(uc)) * gc, bf16_round(gelu_tanh(ud)) * gd);
+        }
+        mbar_wait(&h_empty[b], h_ph[b] ^ 1);                   // MMA2 of chunk c-2 no longer reads this buffer
+        h_ph[b] ^= 1;
+        uint8_t* hrow = sH + b * 16384 + r * 128;
+#pragma unroll
+        for (int pc = 0; pc < 8; ++pc)
+          *reinterpret_cast<uint4*>(hrow + ((pc ^ (r & 7)) << 4)) =
+              make_uint4(hw[4 * pc], hw[4 * pc + 1], hw[4 * pc + 2], hw[4 * pc + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&h_full[b]);
+      }
+      // output: bf16(acc) + residual -> bf16
+      mbar_wait(d_full, dphase);
+      dphase ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t acc[32];
+        tmem_ld_32x32(tD + lane_off + 32 * cc, acc);
+        tmem_ld_wait();
+        if (row < p.M) {
+          uint4* o4 = reinterpret_cast<uint4*>(p.out + row * 128 + 32 * cc);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 rv = res[4 * cc + i];
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float y0 = bf16_round(__uint_as_float(acc[8 * i + 2 * e])), y1 = bf16_round(__uint_as_float(acc[8 * i + 2 * e + 1]));
+              ow[e] = pack_bf16(y0 + bf16_lo(rw[e]), y1 + bf16_hi(rw[e]));
+            }
+            o4[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace mpx
+
+using namespace mpx;
+
+extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const mpx_bf16* wt_d, const mpx_bf16* residual,
+                             mpx_bf16* out, int M, int H, int F, mpx_stream_t stream) {
+  MPX_REQUIRE(x && wt_ug64 && wt_d && residual && out && M > 0, "mpx_glu_fused: bad arguments");
+  MPX_REQUIRE(H == 128, "mpx_glu_fused: hidden_features=%d unsupported (128 only; use mpx_glu_up + mpx_linear)", H);
+  MPX_REQUIRE(F > 0 && F % 64 == 0, "mpx_glu_fused: F=%d must be a positive multiple of 64", F);
+  CUtensorMap tm_x, tm_wug, tm_wd;
+  int rc = make_tmap_bf16_2d(&tm_x, x, M, H, H, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tm_wug, wt_ug64, 2 * F, H, H, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tm_wd, wt_d, H, F, F, 64, 128);
+  if (rc) return rc;
+  const int smem = 1024 + 65536 + GF_STAGES * GF_STAGE_BYTES + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(glu_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(glu_fused): %s", cudaGetErrorString(e));
+      return MPX_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  GluFusedParams p;
+  p.M = M; p.F = F;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  const int tiles = ceil_div(M, 128);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  glu_fused_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(p, tm_x, tm_wug, tm_wd);
+  return check_launch("glu_fused_kernel");
+}

@@ -48,6 +48,7 @@ class PolicyEngine:
         self.QD, self.KD = self.Nq * D, self.Nkv * D
         self.QKV = self.QD + 2 * self.KD
         self.L = cfg.num_layers
+        self.fused_glu = (H == 128 and cfg.ffn_size % 64 == 0)     # decode path: one kernel per GLU block
         self.timescale = (torch.tensor(cfg.rope_max_wavelength, dtype=F32)
                           ** (2.0 * torch.arange(0, D // 2, dtype=F32) / D)).to(self.dev)
         sup = torch.linspace(cfg.value_min, cfg.value_max, cfg.value_n_logits + 1, dtype=F32)
@@ -106,6 +107,11 @@ class PolicyEngine:
                 add(wg[:, 128 * j:], F, wt_ug[256 * j + 128:], H, H, 128, 1)
             add(wu, F, w_ug, 2 * F, H, F, 0)
             add(wg, F, w_ug[:, F:], 2 * F, H, F, 0)
+            wt_ug64 = z(2 * F, H)                                  # 128-row tiles [64 up | 64 gate] (fused decode GLU)
+            for j in range(F // 64):
+                add(wu[:, 64 * j:], F, wt_ug64[128 * j:], H, H, 64, 1)
+                add(wg[:, 64 * j:], F, wt_ug64[128 * j + 64:], H, H, 64, 1)
+            self.w[pre + "wt_ug64"] = wt_ug64
             wt_d, w_d = z(H, F), z(F, H)
             add(wd, H, wt_d, F, F, H, 1)
             add(wd, H, w_d, H, F, H, 0)
@@ -295,8 +301,11 @@ class PolicyEngine:
             ops.linear(ws.ao, w[pre + "wt_o"], residual=x, out=other)
             x, other = other, x
             ops.rmsnorm_fwd(x, p[pre + "ffn_norm.scale"], out=ws.xn)
-            ops.glu_up(ws.xn, w[pre + "wt_ug"], self.F, h=ws.h)
-            ops.linear(ws.h, w[pre + "wt_d"], residual=x, out=other)
+            if self.fused_glu:
+                ops.glu_fused(ws.xn, w[pre + "wt_ug64"], w[pre + "wt_d"], x, other, self.F)
+            else:
+                ops.glu_up(ws.xn, w[pre + "wt_ug"], self.F, h=ws.h)
+                ops.linear(ws.h, w[pre + "wt_d"], residual=x, out=other)
             x, other = other, x
         self._heads_fwd(x, action_mask, ws.xf, ws.logits, ws.pv, None, ws.vlogits)
         return ws.logits, ws.vlogits

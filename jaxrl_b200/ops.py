@@ -170,6 +170,25 @@ def glu_up(x, wt_ug, F: int, save: bool = False, h=None, u=None, g=None):
     return (h, u, g) if save else h
 
 
+def glu_fused(x, wt_ug64, wt_d, residual, out, F: int):
+    """out = residual + down(gelu(up(x)) * gate(x)) in one kernel (H = 128)."""
+    _req(x, BF16, "x"); _req(wt_ug64, BF16, "wt_ug64"); _req(wt_d, BF16, "wt_d"); _req(residual, BF16, "residual")
+    H = x.shape[-1]
+    M = x.numel() // H
+    check(lib.mpx_glu_fused(ptr(x), ptr(wt_ug64), ptr(wt_d), ptr(residual), ptr(out), M, H, F, stream()),
+          "mpx_glu_fused")
+    return out
+
+
+def pack_glu_weight64(w_up: torch.Tensor, w_gate: torch.Tensor) -> torch.Tensor:
+    """(K,F) flax kernels -> (2F,K) bf16, 128-row tiles [64 up rows | 64 gate rows] (see mpx_glu_fused)."""
+    K, F = w_up.shape
+    assert F % 64 == 0
+    ut = w_up.t().reshape(F // 64, 64, K)
+    gt = w_gate.t().reshape(F // 64, 64, K)
+    return torch.cat([ut, gt], dim=1).reshape(2 * F, K).to(BF16).contiguous()
+
+
 def pack_glu_weight(w_up: torch.Tensor, w_gate: torch.Tensor) -> torch.Tensor:
     """(K,F) flax kernels -> (2F,K) bf16, 256-row tiles [128 up rows | 128 gate rows] (see mpx_glu_up)."""
     K, F = w_up.shape

@@ -244,6 +244,33 @@ class PPOTrainer:
         self.update_idx += 1
         return self.log_acc
 
+    def timed_phases(self) -> dict:
+        """One update with CUDA events between the phases (ms): rollout / layout+GAE / minibatch updates."""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        self.log_acc.zero_()
+        ev[0].record()
+        if self.rollout_graph is not None:
+            self.rollout_graph.replay()
+        else:
+            self._rollout_body()
+        ev[1].record()
+        if self.rollout_graph is not None:
+            self.post_graph.replay()
+        else:
+            self._postprocess_body()
+        self._normalize()
+        ev[2].record()
+        if self.update_graph is not None:
+            self.update_graph.replay()
+        else:
+            self._update_body()
+        ev[3].record()
+        torch.cuda.synchronize()
+        self.noise_off += self.T
+        self.update_idx += 1
+        return {"rollout_ms": ev[0].elapsed_time(ev[1]), "gae_layout_ms": ev[1].elapsed_time(ev[2]),
+                "update_ms": ev[2].elapsed_time(ev[3])}
+
     def logs(self) -> dict:
         """Device -> host read of the averaged minibatch losses (the reference's logger.log sync, train.py:419)."""
         n = self.hyp.minibatch_count * self.hyp.epoch_count

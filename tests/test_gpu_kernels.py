@@ -399,3 +399,21 @@ def test_transpose_tb(ops):
     fd = torch.empty(B, T, device=DEV)
     ops.transpose_tb(f.to(DEV), fd, None, T, B)
     assert torch.equal(fd.cpu(), f.t())
+
+
+@pytest.mark.parametrize("M", [77, 4096, 20000])
+def test_glu_fused(ops, M):
+    """Fused GLU block + residual (h stays on chip) vs the oracle GLUBlock."""
+    gen = g(M)
+    K, F = 128, 768
+    x = torch.randn(M, K, generator=gen).to(BF16)
+    res = torch.randn(M, K, generator=gen).to(BF16)
+    wu = torch.randn(K, F, generator=gen) / math.sqrt(K)
+    wg = torch.randn(K, F, generator=gen) / math.sqrt(K)
+    wd = torch.randn(F, K, generator=gen) / math.sqrt(F)
+    pdict = {"f.up_proj.kernel": wu, "f.up_gate.kernel": wg, "f.down_proj.kernel": wd}
+    ref = (O.glu_block(pdict, "f.", x).float() + res.float()).to(BF16)
+    out = torch.empty(M, K, dtype=BF16, device=DEV)
+    ops.glu_fused(x.to(DEV), ops.pack_glu_weight64(wu, wg).to(DEV), wd.t().contiguous().to(BF16).to(DEV), res.to(DEV), out, F)
+    torch.cuda.synchronize()
+    assert_close_bf16(out, ref, f"glu_fused M={M}", rtol=1e-2, abs_floor_frac=1e-2, allow_frac=1e-3, max_err_frac=0.1)
