@@ -193,19 +193,25 @@ __global__ void __launch_bounds__(256) muon_prepare_kernel(const MuonMat* __rest
   if (threadIdx.x == 0) atomicAdd(norm2 + blockIdx.y, s_sum[0]);
 }
 
-// Batched C = alpha * A(op) * B + beta * D on row-major fp32 matrices; 64x64 tile, 16-wide k slab, 4x4 per thread.
-// mode 0: C(r,r) = X X^T * inv_norm^2 (first iteration folds the Frobenius normalisation in) ;
-// mode 1: C(r,r) = c2 * A A + c1 * A ; mode 2: C(r,c) = B X * s + c0 * X * s  (s = inv_norm on the first iteration)
+// Batched Newton-Schulz GEMMs on row-major fp32 matrices; 64x64 tile, 16-wide k slab, 4x4 per thread, float4 smem reads.
+// mode 0: A(r,r) += X X^T * inv_norm^2 over a 128-wide K split (A zeroed by the host; split-K keeps all SMs busy;
+//         the first iteration folds the Frobenius normalisation in) ;
+// mode 1: B(r,r) = c2 * A A + c1 * A ; mode 2: X'(r,c) = (B X + c0 * X) * s  (s = inv_norm on the first iteration)
+constexpr int NS_KSPLIT = 128;
 __global__ void __launch_bounds__(256) muon_ns_gemm_kernel(const MuonMat* __restrict__ mats, const float* __restrict__ Xin,
                                                            float* __restrict__ Xout, float* __restrict__ Abuf,
                                                            float* __restrict__ Bbuf, const float* __restrict__ norm2,
-                                                           int mode, int first, float c0, float c1, float c2, float eps) {
-  __shared__ float sA[16][64 + 1], sB[16][64 + 1];
+                                                           int mode, int first, int ntiles_n, float c0, float c1, float c2,
+                                                           float eps) {
+  __shared__ __align__(16) float sA[16][68], sB[16][68];
   const MuonMat mt = mats[blockIdx.z];
   const int r = mt.r, c = mt.c;
   const int M = r, N = (mode == 2) ? c : r, K = (mode == 0) ? c : r;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  if (m0 >= M || n0 >= N) return;
+  const int nt = blockIdx.x % ntiles_n, ks = blockIdx.x / ntiles_n;     // ks > 0 only in mode 0
+  const int m0 = blockIdx.y * 64, n0 = nt * 64;
+  const int kbeg = (mode == 0) ? ks * NS_KSPLIT : 0;
+  const int kend = (mode == 0) ? min(K, kbeg + NS_KSPLIT) : K;
+  if (m0 >= M || n0 >= N || kbeg >= K) return;
   const float* A;  long long lda;      // A[i][k]
   const float* B;  long long sbk, sbj; // B[k][j] = B[k*sbk + j*sbj]
   const float* X = Xin + mt.xoff;
@@ -218,21 +224,19 @@ __global__ void __launch_bounds__(256) muon_ns_gemm_kernel(const MuonMat* __rest
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
     for (int i = threadIdx.x; i < 16 * 64; i += 256) {
       const int kk = i % 16, mm = i / 16;
-      sA[kk][mm] = (m0 + mm < M && k0 + kk < K) ? A[(long long)(m0 + mm) * lda + k0 + kk] : 0.f;
+      sA[kk][mm] = (m0 + mm < M && k0 + kk < kend) ? A[(long long)(m0 + mm) * lda + k0 + kk] : 0.f;
       const int kb = (sbj == 1) ? i / 64 : i % 16, nb = (sbj == 1) ? i % 64 : i / 16;
-      sB[kb][nb] = (n0 + nb < N && k0 + kb < K) ? B[(long long)(k0 + kb) * sbk + (long long)(n0 + nb) * sbj] : 0.f;
+      sB[kb][nb] = (n0 + nb < N && k0 + kb < kend) ? B[(long long)(k0 + kb) * sbk + (long long)(n0 + nb) * sbj] : 0.f;
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = sB[kk][tx * 4 + j];
+      const float4 av = *reinterpret_cast<const float4*>(&sA[kk][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&sB[kk][tx * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(256) muon_ns_gemm_kernel(const MuonMat* __rest
     for (int j = 0; j < 4; ++j) {
       const int nn = n0 + tx * 4 + j;
       if (nn >= N) continue;
-      if (mode == 0) Abuf[mt.aoff + (long long)mm * r + nn] = acc[i][j] * inv * inv;
+      if (mode == 0) atomicAdd(&Abuf[mt.aoff + (long long)mm * r + nn], acc[i][j] * inv * inv);
       else if (mode == 1) Bbuf[mt.aoff + (long long)mm * r + nn] = c2 * acc[i][j] + c1 * A[(long long)mm * r + nn];
       else Xout[mt.xoff + (long long)mm * c + nn] = (acc[i][j] + c0 * X[(long long)mm * c + nn]) * inv;
     }
@@ -368,10 +372,11 @@ extern "C" int mpx_muon_step(float* params, const float* grads, float* mu, float
     float* xout = X1;
     for (int it = 0; it < ns_steps; ++it) {
       const int first = it == 0;
-      dim3 gA(ceil_div(max_r, 64), ceil_div(max_r, 64), nmat), gX(ceil_div(max_c, 64), ceil_div(max_r, 64), nmat);
-      muon_ns_gemm_kernel<<<gA, 256, 0, s>>>(mm, xin, xout, Ab, Bb, norm2, 0, first, c0, c1, c2, eps);
-      muon_ns_gemm_kernel<<<gA, 256, 0, s>>>(mm, xin, xout, Ab, Bb, norm2, 1, 0, c0, c1, c2, eps);
-      muon_ns_gemm_kernel<<<gX, 256, 0, s>>>(mm, xin, xout, Ab, Bb, norm2, 2, first, c0, c1, c2, eps);
+      const int tr = ceil_div(max_r, 64), tc = ceil_div(max_c, 64), nks = ceil_div(max_c, NS_KSPLIT);
+      cudaMemsetAsync(Ab, 0, (size_t)a_total * sizeof(float), s);
+      muon_ns_gemm_kernel<<<dim3(tr * nks, tr, nmat), 256, 0, s>>>(mm, xin, xout, Ab, Bb, norm2, 0, first, tr, c0, c1, c2, eps);
+      muon_ns_gemm_kernel<<<dim3(tr, tr, nmat), 256, 0, s>>>(mm, xin, xout, Ab, Bb, norm2, 1, 0, tr, c0, c1, c2, eps);
+      muon_ns_gemm_kernel<<<dim3(tc, tr, nmat), 256, 0, s>>>(mm, xin, xout, Ab, Bb, norm2, 2, first, tc, c0, c1, c2, eps);
       float* tmp = xin; xin = xout; xout = tmp;
     }
     muon_finish_kernel<<<dim3(8, nmat), 256, 0, s>>>(mm, xin, params, update_scratch, step, lr0, total_steps,

@@ -256,7 +256,8 @@ def test_attn_decode_full_batch(ops):
     ref = O.dot_product_attention(q[:64].cpu().reshape(64, 1, Nq, D), kc[:64].cpu(), vc[:64].cpu(), kv_len=step + 1)[:, 0]
     assert_close_bf16(outs[2][:64].reshape(64, Nq, D), ref, "attn_decode (exact mma) full batch vs oracle (first 64 agents)")
     assert_close_bf16(outs[2], outs[1], "attn_decode exact mma vs simt (all 4096 agents)", rtol=1e-2)
-    assert_close_bf16(outs[0], outs[1], "attn_decode online mma vs simt (all 4096 agents)", rtol=1.7e-2, abs_floor_frac=1e-2)
+    assert_close_bf16(outs[0], outs[1], "attn_decode online mma vs simt (all 4096 agents)", rtol=1.7e-2, abs_floor_frac=1e-2,
+                      allow_frac=1e-4, max_err_frac=0.1)
 
 
 def test_conv1_onehot_matches_oracle_conv(ops):

@@ -76,8 +76,11 @@ def test_decode_rollout_matches_oracle(engine):
     assert frac >= 0.97
     # KV cache contents after T steps
     for i in range(cfg.num_layers):
-        assert_close_bf16(ws.kcache[i][:, :T], ref["carry"][i].key[:, :T], f"kcache layer {i}", rtol=2e-2)
-        assert_close_bf16(ws.vcache[i][:, :T], ref["carry"][i].value[:, :T], f"vcache layer {i}", rtol=2e-2)
+        # layer > 0 caches sit downstream of bf16 rounding flips in the layer below (online-softmax attention,
+        # fused GLU): band = 2% relative + 1% of the tensor rms, a few per cent of entries may sit just outside
+        kw = dict(rtol=2e-2, abs_floor_frac=1e-2, allow_frac=2e-2 if i > 0 else 0.0, max_err_frac=5e-2)
+        assert_close_bf16(ws.kcache[i][:, :T], ref["carry"][i].key[:, :T], f"kcache layer {i}", **kw)
+        assert_close_bf16(ws.vcache[i][:, :T], ref["carry"][i].value[:, :T], f"vcache layer {i}", **kw)
         assert (ws.kcache[i][:, T:] == 0).all()
 
 
