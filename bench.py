@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-agents", type=int, default=None)
     ap.add_argument("--ncu", action="store_true", help="profiling run: one eager warm pass + ONE eager update, no extras")
+    ap.add_argument("--ncu-decode-step", action="store_true", help="profiling run: one decode step (t=300) between profiler start/stop")
+    ap.add_argument("--ncu-minibatch", action="store_true",
+                    help="profiling run: eager warm pass, then ONE training minibatch (fwd+bwd+optimizer) between NVTX-free markers")
     return ap.parse_args()
 
 
@@ -266,6 +269,31 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
+    if args.ncu_decode_step:
+        trainer = PPOTrainer(run_w, rank=rank, world=world, use_graphs=False)
+        trainer.warmup()
+        from jaxrl_b200 import ops as _ops
+        t, r, env, eng = 300, trainer.r, trainer.env, trainer.engine
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        logits, vlogits = eng.decode_step(trainer.dws, env.obs[t], env.reward[t], r.actions_ext[t], r.pos[t])
+        _ops.gumbel_noise(r.gumbel, trainer.seed, t, trainer.noise_off)
+        _ops.policy_sample(logits, r.gumbel, action=r.actions_ext[t + 1], log_prob=r.log_prob[t])
+        _ops.hlgauss_value(vlogits, eng.centers, out=r.values[t])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"ncu_decode_step": True}), flush=True)
+        return
+    if args.ncu_minibatch:
+        trainer = PPOTrainer(run_w, rank=rank, world=world, use_graphs=False)
+        trainer.warmup()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        trainer._minibatch_body(1)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"ncu_minibatch": True}), flush=True)
+        return
     if args.ncu:
         trainer = PPOTrainer(run_w, rank=rank, world=world, use_graphs=False)
         trainer.warmup()

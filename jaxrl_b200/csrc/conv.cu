@@ -13,38 +13,51 @@ struct OneHotSpec {
   int offs[5];      // prefix sums of the per-component one-hot sizes; offs[K] = C (total channels)
 };
 
-// out (M*OH*OW, KP) bf16, KP = round_up(kh*kw*C, 8).  A block builds OHI_ROWS rows in shared memory: zero fill,
-// one 2-byte store per (row, tap, component), then coalesced 16-byte copies out.
-constexpr int OHI_ROWS = 32;
-__global__ void __launch_bounds__(128) onehot_im2col_kernel(const uint8_t* __restrict__ obs, __nv_bfloat16* __restrict__ out,
+// out (M*OH*OW, KP) bf16, KP = round_up(kh*kw*C, 8) <= 256.  One warp per output row: lane i < taps*K loads the
+// observation byte of item i = (tap, component); lane p < KP/8 owns the 16-byte piece p of the row and knows, from
+// row-independent metadata computed once, which item and which value turn each of its 8 columns on.  Per row:
+// one byte load, 8 shuffles + compares, one coalesced 16-byte store per piece.
+__global__ void __launch_bounds__(256) onehot_im2col_kernel(const uint8_t* __restrict__ obs, __nv_bfloat16* __restrict__ out,
                                                             long long rows_total, int IH, int IW, OneHotSpec spec, int kh,
                                                             int kw, int sh, int sw, int OH, int OW, int KP) {
-  extern __shared__ __align__(16) uint8_t ohi_smem[];
-  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(ohi_smem);   // [OHI_ROWS][KP]
+  const int lane = threadIdx.x & 31;
   const int C = spec.offs[spec.K];
   const int taps = kh * kw;
-  const int pieces = KP / 8;
-  for (long long row0 = (long long)blockIdx.x * OHI_ROWS; row0 < rows_total; row0 += (long long)gridDim.x * OHI_ROWS) {
-    const int nrows = (int)min((long long)OHI_ROWS, rows_total - row0);
-    for (int i = threadIdx.x; i < OHI_ROWS * pieces; i += blockDim.x)
-      reinterpret_cast<uint4*>(tile)[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < nrows * taps * spec.K; i += blockDim.x) {
-      const int kc = i % spec.K;
-      const int tap = (i / spec.K) % taps;
-      const int r = i / (spec.K * taps);
-      const long long row = row0 + r;
-      const int ox = (int)(row % OW);
-      const int oy = (int)((row / OW) % OH);
-      const long long m = row / ((long long)OW * OH);
-      const int ky = tap / kw, kx = tap % kw;
-      const int val = obs[((m * IH + (oy * sh + ky)) * IW + (ox * sw + kx)) * spec.K + kc];
-      if (val < spec.offs[kc + 1] - spec.offs[kc]) tile[r * KP + tap * C + spec.offs[kc] + val] = __float2bfloat16_rn(1.0f);
+  const int nitems = taps * spec.K;             // <= 32 (checked by the host)
+  const int pieces = KP / 8;                    // <= 32
+  // item owned by this lane: cell offset inside the receptive field
+  const int it_tap = lane / spec.K, it_k = lane % spec.K;
+  const int it_off = ((it_tap / kw) * IW + (it_tap % kw)) * spec.K + it_k;
+  // columns owned by this lane: source item lane and the value that lights the column (-1 = never)
+  int src[8], want[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int col = lane * 8 + e;
+    src[e] = 0;
+    want[e] = -1;
+    if (lane < pieces && col < taps * C) {
+      const int tap = col / C, ch = col % C;
+      int kc = 0;
+      while (kc + 1 < spec.K && ch >= spec.offs[kc + 1]) ++kc;
+      src[e] = tap * spec.K + kc;
+      want[e] = ch - spec.offs[kc];
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nrows * pieces; i += blockDim.x)
-      reinterpret_cast<uint4*>(out + row0 * KP)[i] = reinterpret_cast<const uint4*>(tile)[i];
-    __syncthreads();
+  }
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long stride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (; row < rows_total; row += stride) {
+    const int ox = (int)(row % OW);
+    const int oy = (int)((row / OW) % OH);
+    const long long m = row / ((long long)OW * OH);
+    const uint8_t* cell0 = obs + ((m * IH + oy * sh) * IW + ox * sw) * spec.K;
+    const int val = lane < nitems ? cell0[it_off] : 255;
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int v = __shfl_sync(0xffffffffu, val, src[e]);
+      if (v == want[e]) w[e >> 1] |= (e & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0
+    }
+    if (lane < pieces) *reinterpret_cast<uint4*>(out + row * KP + lane * 8) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -184,13 +197,13 @@ extern "C" int mpx_obs_onehot_im2col(const uint8_t* obs, mpx_bf16* out, long lon
   MPX_REQUIRE(IH >= kh && IW >= kw && sh > 0 && sw > 0, "mpx_obs_onehot_im2col: bad geometry");
   const int OH = (IH - kh) / sh + 1, OW = (IW - kw) / sw + 1;
   const long long rows = M * OH * OW;
-  long long g = (rows + OHI_ROWS - 1) / OHI_ROWS;
+  MPX_REQUIRE(kh * kw * K <= 32 && KP <= 256, "mpx_obs_onehot_im2col: receptive field too large (kh*kw*K=%d, KP=%d)",
+              kh * kw * K, KP);
+  long long g = (rows + 7) / 8;
   const long long cap = (long long)num_sms() * 16;
   if (g > cap) g = cap;
-  const size_t smem = (size_t)OHI_ROWS * KP * 2;
-  MPX_REQUIRE(smem <= 48 * 1024, "mpx_obs_onehot_im2col: KP=%d too wide", KP);
-  onehot_im2col_kernel<<<(int)g, 128, smem, (cudaStream_t)stream>>>(obs, reinterpret_cast<__nv_bfloat16*>(out), rows, IH,
-                                                                   IW, spec, kh, kw, sh, sw, OH, OW, KP);
+  onehot_im2col_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(obs, reinterpret_cast<__nv_bfloat16*>(out), rows, IH, IW,
+                                                               spec, kh, kw, sh, sw, OH, OW, KP);
   return check_launch("mpx_obs_onehot_im2col");
 }
 
