@@ -32,7 +32,7 @@ int mpx_version(void);
 /* Debug/tuning knobs (tests only). key 0: swap LBO/SBO in MN-major UMMA descriptors.
  * key 1: decode attention implementation (0 = mma.sync online softmax, default; 1 = SIMT exact two-pass;
  * 2 = mma.sync exact two-pass).  key 2: training attention forward (0 = tcgen05/TMEM when q,k,v are packed and
- * Nkv == 1, default; 1 = mma.sync everywhere). */
+ * Nkv == 1, default; 1 = mma.sync everywhere).  key 3: mpx_glu_fused cluster size (0 = auto; 1, 2 or 4 = force). */
 int mpx_debug_set(int key, int value);
 
 /* ---------------------------------------------------------------------------------------------- GAE
@@ -84,9 +84,12 @@ int mpx_linear(const mpx_linear_args* a, mpx_stream_t stream);
 typedef struct {
   const mpx_bf16* x;  long long ldx;   /* (M,K) */
   const mpx_bf16* dy; long long ldy;   /* (M,N) */
-  float* dw;          long long lddw;  /* (K,N) fp32, accumulated with red.add */
+  float* dw;          long long lddw;  /* (K,N) fp32, accumulated (+=) */
   int M, N, K;
+  void* workspace; size_t workspace_bytes;   /* optional: >= mpx_linear_wgrad_workspace_bytes(M,N,K) makes the split-K
+                                                reduction a deterministic two-pass sum; otherwise red.add atomics */
 } mpx_wgrad_args;
+size_t mpx_linear_wgrad_workspace_bytes(int M, int N, int K);
 int mpx_linear_wgrad(const mpx_wgrad_args* a, mpx_stream_t stream);
 
 /* q/k/v projections + RoPE (+ KV-cache ring write): AttentionBlock.__call__ attention.py:121-134 and

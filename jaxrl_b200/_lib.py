@@ -45,7 +45,7 @@ LinearArgs = _struct("mpx_linear_args", [
 
 WgradArgs = _struct("mpx_wgrad_args", [
     ("x", c_p), ("ldx", c_ll), ("dy", c_p), ("ldy", c_ll), ("dw", c_p), ("lddw", c_ll),
-    ("M", c_i), ("N", c_i), ("K", c_i)])
+    ("M", c_i), ("N", c_i), ("K", c_i), ("workspace", c_p), ("workspace_bytes", C.c_size_t)])
 
 QkvRopeArgs = _struct("mpx_qkv_rope_args", [
     ("x", c_p), ("ldx", c_ll), ("wt_qkv", c_p), ("pos", c_p), ("pos_len", c_i), ("rope_timescale", c_p),
@@ -88,6 +88,8 @@ lib.mpx_hlgauss_loss.argtypes = [c_p, c_p, c_ll, c_i, c_p, c_f, c_f, c_f, c_f, c
 for _name in ("mpx_linear", "mpx_linear_wgrad", "mpx_qkv_rope", "mpx_glu_up", "mpx_attn_decode",
               "mpx_attn_train_fwd", "mpx_attn_train_bwd"):
     getattr(lib, _name).argtypes = [c_p, c_p]
+lib.mpx_linear_wgrad_workspace_bytes.restype = C.c_size_t
+lib.mpx_linear_wgrad_workspace_bytes.argtypes = [c_i, c_i, c_i]
 lib.mpx_linear_f32w.argtypes = [c_p, c_ll, c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_p]
 lib.mpx_glu_fused.argtypes = [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p]
 lib.mpx_rmsnorm_fwd.argtypes = [c_p, c_p, c_f, c_p, c_ll, c_i, c_p]

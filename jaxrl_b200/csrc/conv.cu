@@ -43,12 +43,12 @@ __global__ void __launch_bounds__(256) onehot_im2col_kernel(const uint8_t* __res
       want[e] = ch - spec.offs[kc];
     }
   }
-  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long stride = (long long)gridDim.x * (blockDim.x >> 5);
-  for (; row < rows_total; row += stride) {
-    const int ox = (int)(row % OW);
-    const int oy = (int)((row / OW) % OH);
-    const long long m = row / ((long long)OW * OH);
+  const unsigned nrows = (unsigned)rows_total;                         // host guarantees < 2^31: 32-bit index math
+  const unsigned stride = gridDim.x * (blockDim.x >> 5);
+  for (unsigned row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < nrows; row += stride) {
+    const int ox = (int)(row % (unsigned)OW);
+    const int oy = (int)((row / (unsigned)OW) % (unsigned)OH);
+    const long long m = row / (unsigned)(OW * OH);
     const uint8_t* cell0 = obs + ((m * IH + oy * sh) * IW + ox * sw) * spec.K;
     const int val = lane < nitems ? cell0[it_off] : 255;
     uint32_t w[4] = {0, 0, 0, 0};
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) onehot_im2col_kernel(const uint8_t* __res
       const int v = __shfl_sync(0xffffffffu, val, src[e]);
       if (v == want[e]) w[e >> 1] |= (e & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0
     }
-    if (lane < pieces) *reinterpret_cast<uint4*>(out + row * KP + lane * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    if (lane < pieces) *reinterpret_cast<uint4*>(out + (long long)row * KP + lane * 8) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -77,15 +77,14 @@ __global__ void __launch_bounds__(256) conv1_onehot_fwd_kernel(
     reinterpret_cast<uint4*>(sw_)[i] = reinterpret_cast<const uint4*>(w)[i];
   __syncthreads();
   const int cg = cout / 8;
-  const long long total = rows_total * cg;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < total; i += stride) {
-    const int c8 = (int)(i % cg);
-    const long long row = i / cg;
-    const int ox = (int)(row % OW);
-    const int oy = (int)((row / OW) % OH);
-    const long long m = row / ((long long)OW * OH);
+  const unsigned total = (unsigned)(rows_total * cg);                // host guarantees < 2^31: 32-bit index math
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c8 = (int)(i % (unsigned)cg);
+    const unsigned row = i / (unsigned)cg;
+    const int ox = (int)(row % (unsigned)OW);
+    const int oy = (int)((row / (unsigned)OW) % (unsigned)OH);
+    const long long m = row / (unsigned)(OW * OH);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int ky = 0; ky < kh; ++ky) {
       for (int kx = 0; kx < kw; ++kx) {
@@ -108,13 +107,13 @@ __global__ void __launch_bounds__(256) conv1_onehot_fwd_kernel(
 #pragma unroll
     for (int e = 0; e < 8; ++e) zf[e] = bf16_round(bf16_round(acc[e]) + b[e]);
     if (z_out)
-      *reinterpret_cast<uint4*>(z_out + row * cout + c8 * 8) =
+      *reinterpret_cast<uint4*>(z_out + (long long)row * cout + c8 * 8) =
           make_uint4(pack_bf16(zf[0], zf[1]), pack_bf16(zf[2], zf[3]), pack_bf16(zf[4], zf[5]), pack_bf16(zf[6], zf[7]));
     if (apply_gelu) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) zf[e] = gelu_tanh(zf[e]);
     }
-    *reinterpret_cast<uint4*>(a_out + row * cout + c8 * 8) =
+    *reinterpret_cast<uint4*>(a_out + (long long)row * cout + c8 * 8) =
         make_uint4(pack_bf16(zf[0], zf[1]), pack_bf16(zf[2], zf[3]), pack_bf16(zf[4], zf[5]), pack_bf16(zf[6], zf[7]));
   }
 }
@@ -123,17 +122,16 @@ __global__ void __launch_bounds__(256) conv1_onehot_fwd_kernel(
 __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ x, long long M, int IH,
                               int IW, int C, int kh, int kw, int sh, int sw, int OH, int OW) {
   const int cp = C / 8;
-  const long long total = M * OH * OW * kh * kw * cp;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < total; i += stride) {
-    const int c8 = (int)(i % cp);
-    long long r = i / cp;
-    const int tap = (int)(r % (kh * kw));
-    r /= (kh * kw);
-    const int ox = (int)(r % OW);
-    const int oy = (int)((r / OW) % OH);
-    const long long m = r / ((long long)OW * OH);
+  const unsigned total = (unsigned)(M * OH * OW * kh * kw * cp);     // host guarantees < 2^31
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c8 = (int)(i % (unsigned)cp);
+    unsigned r = i / (unsigned)cp;
+    const int tap = (int)(r % (unsigned)(kh * kw));
+    r /= (unsigned)(kh * kw);
+    const int ox = (int)(r % (unsigned)OW);
+    const int oy = (int)((r / (unsigned)OW) % (unsigned)OH);
+    const long long m = r / (unsigned)(OW * OH);
     const int ky = tap / kw, kx = tap % kw;
     const uint4 v = *reinterpret_cast<const uint4*>(a + ((m * IH + oy * sh + ky) * IW + ox * sw + kx) * C + c8 * 8);
     *reinterpret_cast<uint4*>(x + ((m * OH + oy) * OW + ox) * (long long)(kh * kw * C) + tap * C + c8 * 8) = v;
@@ -144,15 +142,14 @@ __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16
 __global__ void col2im_kernel(const __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ da, long long M, int IH,
                               int IW, int C, int kh, int kw, int sh, int sw, int OH, int OW) {
   const int cp = C / 8;
-  const long long total = M * IH * IW * cp;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < total; i += stride) {
-    const int c8 = (int)(i % cp);
-    long long r = i / cp;
-    const int ix = (int)(r % IW);
-    const int iy = (int)((r / IW) % IH);
-    const long long m = r / ((long long)IW * IH);
+  const unsigned total = (unsigned)(M * IH * IW * cp);                 // host guarantees < 2^31
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c8 = (int)(i % (unsigned)cp);
+    unsigned r = i / (unsigned)cp;
+    const int ix = (int)(r % (unsigned)IW);
+    const int iy = (int)((r / (unsigned)IW) % (unsigned)IH);
+    const long long m = r / (unsigned)(IW * IH);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int ky = 0; ky < kh; ++ky) {
       const int ny = iy - ky;
@@ -199,6 +196,7 @@ extern "C" int mpx_obs_onehot_im2col(const uint8_t* obs, mpx_bf16* out, long lon
   const long long rows = M * OH * OW;
   MPX_REQUIRE(kh * kw * K <= 32 && KP <= 256, "mpx_obs_onehot_im2col: receptive field too large (kh*kw*K=%d, KP=%d)",
               kh * kw * K, KP);
+  MPX_REQUIRE(rows < (1LL << 31), "mpx_obs_onehot_im2col: too many rows for 32-bit indexing");
   long long g = (rows + 7) / 8;
   const long long cap = (long long)num_sms() * 16;
   if (g > cap) g = cap;
@@ -222,6 +220,7 @@ extern "C" int mpx_conv1_onehot_fwd(const uint8_t* obs, const mpx_bf16* w, const
   MPX_REQUIRE(smem <= 48 * 1024 && (kh * kw * C * cout) % 8 == 0, "mpx_conv1_onehot_fwd: kernel too large for shared memory");
   const int OH = (IH - kh) / sh + 1, OW = (IW - kw) / sw + 1;
   const long long rows = M * OH * OW;
+  MPX_REQUIRE(rows * (cout / 8) < (1LL << 31), "mpx_conv1_onehot_fwd: too many rows for 32-bit indexing");
   conv1_onehot_fwd_kernel<<<cv_grid(rows * (cout / 8)), 256, smem, (cudaStream_t)stream>>>(
       obs, reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<const __nv_bfloat16*>(bias),
       reinterpret_cast<__nv_bfloat16*>(z_out), reinterpret_cast<__nv_bfloat16*>(a_out), rows, IH, IW, spec, kh, kw, sh, sw,
@@ -233,6 +232,7 @@ extern "C" int mpx_im2col(const mpx_bf16* a, mpx_bf16* x, long long M, int IH, i
                           int sw, mpx_stream_t stream) {
   MPX_REQUIRE(a && x && M > 0 && C % 8 == 0 && IH >= kh && IW >= kw && sh > 0 && sw > 0, "mpx_im2col: bad arguments");
   const int OH = (IH - kh) / sh + 1, OW = (IW - kw) / sw + 1;
+  MPX_REQUIRE(M * OH * OW * kh * kw * (C / 8) < (1LL << 31), "mpx_im2col: too many elements for 32-bit indexing");
   im2col_kernel<<<cv_grid(M * OH * OW * kh * kw * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<__nv_bfloat16*>(x), M, IH, IW, C, kh, kw, sh, sw, OH, OW);
   return check_launch("mpx_im2col");
@@ -241,6 +241,7 @@ extern "C" int mpx_im2col(const mpx_bf16* a, mpx_bf16* x, long long M, int IH, i
 extern "C" int mpx_col2im(const mpx_bf16* dx, mpx_bf16* da, long long M, int IH, int IW, int C, int kh, int kw, int sh,
                           int sw, mpx_stream_t stream) {
   MPX_REQUIRE(dx && da && M > 0 && C % 8 == 0 && IH >= kh && IW >= kw && sh > 0 && sw > 0, "mpx_col2im: bad arguments");
+  MPX_REQUIRE(M * IH * IW * (C / 8) < (1LL << 31), "mpx_col2im: too many elements for 32-bit indexing");
   const int OH = (IH - kh) / sh + 1, OW = (IW - kw) / sw + 1;
   col2im_kernel<<<cv_grid(M * IH * IW * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(da), M, IH, IW, C, kh, kw, sh, sw, OH, OW);

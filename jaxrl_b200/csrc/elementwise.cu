@@ -128,12 +128,12 @@ __global__ void __launch_bounds__(EW_WARPS * 32) rmsnorm_bwd_kernel(
 // dug is (M, 2F): [du | dg].
 __global__ void glu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ u,
                                const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ dug, long long M, int F) {
-  const long long n4 = M * (F / 4);
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < n4; i += stride) {
-    const long long row = i / (F / 4);
-    const int c = (int)(i % (F / 4)) * 4;
+  const unsigned n4 = (unsigned)(M * (F / 4));                         // host guarantees < 2^31
+  const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned f4 = (unsigned)(F / 4);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const long long row = i / f4;
+    const int c = (int)(i % f4) * 4;
     float dhv[4], uv[4], gv[4], du[4], dg[4];
     ld4(dh + row * F + c, dhv);
     ld4(u + row * F + c, uv);
@@ -198,27 +198,43 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ x, long long ld, const i
 
 // ------------------------------------------------------------------------------------------------ column sums
 // out[N] (fp32, atomically accumulated) += sum over rows of x (M, ld) bf16 columns [0,N).
-// Block = 256 threads as (256/CW row lanes) x (CW column lanes), CW = 32 or 64 columns per pass; a block owns a
-// strip of rows, every warp reads contiguous column runs; partials meet in shared memory, one atomic per column.
+// Thread = 8 consecutive columns (one 16-byte load per row); a block owns a strip of rows, its 256 threads cover
+// (256 / ceil(N/8)) row lanes; partials meet in shared memory, one atomic per column per block.
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long M,
                                                      int N, float* __restrict__ out, int rows_per_block) {
-  __shared__ float s_part[256];
-  const int CW = N >= 64 ? 64 : 32;
-  const int RL = 256 / CW;
-  const int cl = threadIdx.x % CW, rl = threadIdx.x / CW;
+  __shared__ float s_part[256 * 8];
+  const int groups = (N + 7) / 8;                    // 16-byte column groups
+  const int gpp = groups < 256 ? groups : 256;       // groups handled per pass
+  const int RL = 256 / gpp;                          // row lanes
+  const int gl = threadIdx.x % gpp, rl = threadIdx.x / gpp;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = min(M, r0 + (long long)rows_per_block);
-  for (int c0 = 0; c0 < N; c0 += CW) {
-    const int c = c0 + cl;
-    float acc = 0.f;
-    if (c < N)
-      for (long long r = r0 + rl; r < r1; r += RL) acc += __bfloat162float(x[r * ld + c]);
-    s_part[threadIdx.x] = acc;
+  for (int g0 = 0; g0 < groups; g0 += gpp) {
+    const int c = (g0 + gl) * 8;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (rl < RL && c < N) {
+      if (c + 8 <= N) {
+        for (long long r = r0 + rl; r < r1; r += RL) {
+          const uint4 v = *reinterpret_cast<const uint4*>(x + r * ld + c);
+          acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+          acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+        }
+      } else {
+        for (long long r = r0 + rl; r < r1; r += RL)
+          for (int e = 0; e < 8 && c + e < N; ++e) acc[e] += __bfloat162float(x[r * ld + c + e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_part[threadIdx.x * 8 + e] = acc[e];
     __syncthreads();
-    if (rl == 0 && c < N) {
-      float t = 0.f;
-      for (int k = 0; k < RL; ++k) t += s_part[k * CW + cl];
-      atomicAdd(out + c, t);
+    for (int j = threadIdx.x; j < gpp * 8; j += 256) {
+      const int gg = j / 8, e = j % 8;
+      const int col = (g0 + gg) * 8 + e;
+      if (col < N) {
+        float t = 0.f;
+        for (int k = 0; k < RL; ++k) t += s_part[(k * gpp + gg) * 8 + e];
+        atomicAdd(out + col, t);
+      }
     }
     __syncthreads();
   }
@@ -292,6 +308,7 @@ extern "C" int mpx_rmsnorm_bwd(const mpx_bf16* dy, const mpx_bf16* x, const floa
 extern "C" int mpx_glu_bwd(const mpx_bf16* dh, const mpx_bf16* u, const mpx_bf16* g, mpx_bf16* dug, long long M,
                            int F, mpx_stream_t stream) {
   MPX_REQUIRE(dh && u && g && dug && M > 0 && F > 0 && F % 4 == 0, "mpx_glu_bwd: bad arguments");
+  MPX_REQUIRE(M * (F / 4) < (1LL << 31), "mpx_glu_bwd: too many elements for 32-bit indexing");
   glu_bwd_kernel<<<ew_grid(M * (F / 4), 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dh), reinterpret_cast<const __nv_bfloat16*>(u),
       reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<__nv_bfloat16*>(dug), M, F);
@@ -317,6 +334,7 @@ extern "C" int mpx_rope(mpx_bf16* x, long long ld, const int32_t* pos, int pos_l
 
 extern "C" int mpx_colsum(const mpx_bf16* x, long long ld, long long M, int N, float* out, mpx_stream_t stream) {
   MPX_REQUIRE(x && out && M > 0 && N > 0, "mpx_colsum: bad arguments");
+  MPX_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "mpx_colsum: x must be 16-byte aligned with ld %% 8 == 0");
   int rows_per_block = (int)((M + (long long)num_sms() * 4 - 1) / ((long long)num_sms() * 4));
   if (rows_per_block < 64) rows_per_block = 64;
   const int grid = (int)((M + rows_per_block - 1) / rows_per_block);

@@ -4,8 +4,9 @@
 //   wgrad           :  dW[K,N] += X[M,K]^T . dY[M,N]        both operands MN-major (read straight from the
 //                                                           row-major activations), SWIZZLE_128B, split over M
 //
-// Structure (one CTA per SM, 192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc),
-// warps 2-5 = epilogue (TMEM -> registers -> fused epilogue -> global).  4-stage smem ring (full/empty
+// Structure (one CTA per SM, 320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc),
+// warps 2-9 = epilogue (TMEM -> registers -> fused epilogue -> global; two warps per TMEM lane quarter, each
+// taking every other 32-column chunk, so math-heavy epilogues are not limited to one warp per SM sub-partition).  4-stage smem ring (full/empty
 // mbarriers) and 2 TMEM accumulator stages (tmem_full/tmem_empty) so the epilogue of tile i overlaps the MMAs
 // of tile i+1.  Tile = 128 x BLOCK_N, BLOCK_K = 64 bf16 = one 128-byte swizzle atom.
 //
@@ -25,7 +26,8 @@ int g_debug_swap_lbo_sbo = 0;
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int STAGES = 4;
-constexpr int GEMM_THREADS = 192;
+constexpr int WGRAD_THREADS = 192;  // weight-gradient kernel: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int GEMM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 
 enum { EPI_STORE = 0, EPI_QKV = 1, EPI_GLU = 2, EPI_PAIRSUM = 3 };
@@ -272,7 +274,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 4);
+      mbar_init(&tempty[s], 8);
     }
     fence_barrier_init();
   }
@@ -337,6 +339,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
   } else {
     // ================================ epilogue warps ================================
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;        // which of the two warps of this quarter: takes chunks with (c/32)&1 == half
     const int row_in_tile = quarter * 32 + lane;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -353,14 +356,19 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
         }
       }
       // residual rows of this tile are fetched BEFORE waiting for the accumulator (hides the global-load latency)
-      constexpr int kPre = (EPI == EPI_STORE && BLOCK_N <= 128) ? BLOCK_N / 8 : 1;
+      constexpr int kMine = (BLOCK_N / 32 + 1) / 2;                  // 32-column chunks owned by this warp (at most)
+      constexpr int kPre = (EPI == EPI_STORE && BLOCK_N <= 128) ? kMine * 4 : 1;
       uint4 rpre[kPre];
       bool have_pre = false;
       if constexpr (EPI == EPI_STORE && BLOCK_N <= 128) {
         if (p.residual && p.y && row < p.M && (p.ldr & 7) == 0 && (p.ldy & 7) == 0 && (n_blk + 1) * BLOCK_N <= p.N) {
           const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + (long long)row * p.ldr + n_blk * BLOCK_N);
 #pragma unroll
-          for (int i = 0; i < kPre; ++i) rpre[i] = r4[i];
+          for (int j = 0; j < kMine; ++j)
+            if ((2 * j + half) * 32 < BLOCK_N) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) rpre[4 * j + i] = r4[(2 * j + half) * 4 + i];
+            }
           have_pre = true;
         }
       }
@@ -370,7 +378,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
       if constexpr (EPI == EPI_GLU) {
         static_assert(EPI != EPI_GLU || BLOCK_N == 256, "GLU tile is 128 up + 128 gate columns");
 #pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
+        for (int c = 32 * half; c < 128; c += 64) {
           uint32_t u[32], g[32];
           tmem_ld_32x32(t_row + c, u);
           tmem_ld_32x32(t_row + 128 + c, g);
@@ -378,8 +386,8 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
           epi_glu(p, row, n_blk * 128 + c, u, g);
         }
       } else if constexpr (EPI == EPI_PAIRSUM) {
-#pragma unroll 1
-        for (int c = 0; c < 64; c += 32) {
+        {
+          const int c = 32 * half;
           uint32_t hi[32], lo[32];
           tmem_ld_32x32(t_row + c, hi);
           tmem_ld_32x32(t_row + 64 + c, lo);
@@ -388,15 +396,18 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
         }
       } else if constexpr (EPI == EPI_STORE && BLOCK_N <= 128) {
 #pragma unroll
-        for (int c = 0; c < BLOCK_N; c += 32) {
-          uint32_t acc[32];
-          tmem_ld_32x32(t_row + c, acc);
-          tmem_ld_wait();
-          epi_store(p, row, n_blk * BLOCK_N + c, acc, have_pre ? &rpre[c / 8] : nullptr);
+        for (int j = 0; j < kMine; ++j) {
+          const int c = (2 * j + half) * 32;
+          if (c < BLOCK_N) {
+            uint32_t acc[32];
+            tmem_ld_32x32(t_row + c, acc);
+            tmem_ld_wait();
+            epi_store(p, row, n_blk * BLOCK_N + c, acc, have_pre ? &rpre[4 * j] : nullptr);
+          }
         }
       } else {
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
+        for (int c = 32 * half; c < BLOCK_N; c += 64) {
           uint32_t acc[32];
           tmem_ld_32x32(t_row + c, acc);
           tmem_ld_wait();
@@ -419,9 +430,10 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
 // chunk of the M tokens, 64 tokens per stage.  A = X^T and B = dY^T are MN-major: the smem tile of a stage is
 // [64 tokens][64 features] x (features/64) boxes, each box 8 KB with the 128-byte swizzle.
 template <int WG_N>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_wgrad_kernel(int M, int N, int K, float* __restrict__ dw, long long lddw, int tokens_per_cta, int swap_lbo_sbo,
-                  const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy) {
+__global__ void __launch_bounds__(WGRAD_THREADS, 1)
+gemm_wgrad_kernel(int M, int N, int K, float* __restrict__ dw, long long lddw, float* __restrict__ partial,
+                  int tokens_per_cta, int swap_lbo_sbo, const __grid_constant__ CUtensorMap tm_x,
+                  const __grid_constant__ CUtensorMap tm_dy) {
   constexpr int A_BYTES = 2 * 8192;            // 128 features = 2 boxes
   constexpr int B_BYTES = (WG_N / 64) * 8192;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -516,7 +528,17 @@ gemm_wgrad_kernel(int M, int N, int K, float* __restrict__ dw, long long lddw, i
       uint32_t acc[32];
       tmem_ld_32x32(t_row + c, acc);
       tmem_ld_wait();
-      if (krow < K && num_it > 0) {
+      if (partial) {
+        // split-K partial tile -> workspace [split][K_pad][N_pad] (plain stores; reduced in fixed order afterwards)
+        const long long kp = (long long)gridDim.x * 128, np = (long long)gridDim.y * WG_N;
+        float4* d4 = reinterpret_cast<float4*>(partial + ((long long)blockIdx.z * kp + (k_blk * 128 + quarter * 32 + lane)) * np +
+                                               n_blk * WG_N + c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          d4[i] = num_it > 0 ? make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]),
+                                           __uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3]))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else if (krow < K && num_it > 0) {
         float* d = dw + (long long)krow * lddw + n_blk * WG_N + c;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
@@ -527,6 +549,28 @@ gemm_wgrad_kernel(int M, int N, int K, float* __restrict__ dw, long long lddw, i
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// dw[k][n] += sum over splits of partial[s][k][n]   (fixed summation order: deterministic)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int kp, int np,
+                                                           float* __restrict__ dw, long long lddw, int K, int N) {
+  const int n4 = np / 4;
+  const int total = K * n4;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    const int k = i / n4, n = (i % n4) * 4;
+    if (n >= N) continue;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* p = partial + (long long)k * np + n;
+    for (int s = 0; s < splits; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(p + (long long)s * kp * np);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    float* d = dw + (long long)k * lddw + n;
+    d[0] += a.x;
+    if (n + 1 < N) d[1] += a.y;
+    if (n + 2 < N) d[2] += a.z;
+    if (n + 3 < N) d[3] += a.w;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -623,8 +667,16 @@ static int launch_wgrad(const mpx_wgrad_args* a, cudaStream_t stream) {
   if (tokens_per_cta < 64) tokens_per_cta = 64;
   splits = ceil_div(a->M, tokens_per_cta);
   dim3 grid(kb, nb, splits);
-  gemm_wgrad_kernel<WG_N><<<grid, GEMM_THREADS, SMEM, stream>>>(a->M, a->N, a->K, a->dw, a->lddw, tokens_per_cta,
+  const size_t need = (size_t)splits * kb * 128 * nb * WG_N * sizeof(float);
+  float* partial = (a->workspace && a->workspace_bytes >= need && splits > 1) ? reinterpret_cast<float*>(a->workspace) : nullptr;
+  gemm_wgrad_kernel<WG_N><<<grid, WGRAD_THREADS, SMEM, stream>>>(a->M, a->N, a->K, a->dw, a->lddw, partial, tokens_per_cta,
                                                                g_debug_swap_lbo_sbo, tm_x, tm_dy);
+  if (partial) {
+    const int total = a->K * (nb * WG_N / 4);
+    int rg = ceil_div(total, 256);
+    if (rg > num_sms() * 8) rg = num_sms() * 8;
+    wgrad_reduce_kernel<<<rg, 256, 0, stream>>>(partial, splits, kb * 128, nb * WG_N, a->dw, a->lddw, a->K, a->N);
+  }
   return check_launch("gemm_wgrad_kernel");
 }
 
@@ -652,11 +704,21 @@ extern "C" int mpx_linear(const mpx_linear_args* a, mpx_stream_t stream) {
   // widest N tile that still gives the machine enough CTAs (small-M decode GEMMs are latency bound: more, narrower
   // tiles shorten both the K loop's exposed latency and the epilogue)
   const int mt = ceil_div(a->M, BLOCK_M);
-  const int want = (num_sms() * 3) / 5;
+  const int want = num_sms();
   if (a->N > 128 && mt * ceil_div(a->N, 256) >= want) return launch_tn<256, EPI_STORE>(p, a->x, a->ldx, a->wt, a->ldw, s);
   if (a->N > 64 && mt * ceil_div(a->N, 128) >= want) return launch_tn<128, EPI_STORE>(p, a->x, a->ldx, a->wt, a->ldw, s);
   if (a->N > 32 && mt * ceil_div(a->N, 64) >= want) return launch_tn<64, EPI_STORE>(p, a->x, a->ldx, a->wt, a->ldw, s);
   return launch_tn<32, EPI_STORE>(p, a->x, a->ldx, a->wt, a->ldw, s);
+}
+
+extern "C" size_t mpx_linear_wgrad_workspace_bytes(int M, int N, int K) {
+  const int wg_n = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  const int kb = ceil_div(K, 128), nb = ceil_div(N, wg_n);
+  int splits = ceil_div(2 * num_sms(), kb * nb);
+  int tokens_per_cta = ceil_div(ceil_div(M, splits), 64) * 64;
+  if (tokens_per_cta < 64) tokens_per_cta = 64;
+  splits = ceil_div(M, tokens_per_cta);
+  return (size_t)splits * kb * 128 * nb * wg_n * sizeof(float);
 }
 
 extern "C" int mpx_linear_wgrad(const mpx_wgrad_args* a, mpx_stream_t stream) {

@@ -6,9 +6,15 @@
 // turn it into the bf16 h_c tile in shared memory (SW128 K-major, the A operand of MMA2), MMA2 accumulates
 // h_c @ Wdown_c^T into a second TMEM accumulator.  MMA1 of chunk c+1 overlaps the activation math of chunk c.
 //
-// Roles (192 threads): warp 0 TMA producer (x tile + weight ring), warp 1 MMA issuer / TMEM owner, warps 2-5
-// activation + output epilogue (thread = row).  H (model width) must be 128; F % 64 == 0.
-// Used by the rollout decode step, where the unfused pair (mpx_glu_up + mpx_linear) is launch/latency bound.
+// Roles (320 threads): warp 0 TMA producer (x tile + weight ring), warp 1 MMA issuer / TMEM owner, warps 2-9
+// activation + output epilogue (two warps per TMEM lane quarter; thread = row, each warp half of the columns).
+// H (model width) must be 128; F % 64 == 0.
+//
+// Rollout batches are small (M = agents, 32 row tiles at 4096 agents), so one CTA per row tile would leave most
+// of the 148 SMs idle while each CTA walks a serial MMA1 -> activation -> MMA2 chain over all F/64 chunks.  The
+// kernel therefore runs as a thread-block cluster of CL CTAs per row tile: CTA k of the cluster owns chunks
+// [k*F/64/CL, (k+1)*F/64/CL), leaves its fp32 partial of the output tile in its own shared memory, and the CL
+// partials are summed over distributed shared memory - CTA k finishes output columns [k*128/CL, (k+1)*128/CL).
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tmap.h"
@@ -17,6 +23,11 @@ namespace mpx {
 
 constexpr int GF_STAGES = 6;
 constexpr int GF_STAGE_BYTES = 16384;   // [128 rows x 64 cols] bf16, SW128
+constexpr int GF_THREADS = 320;
+constexpr int GF_EPI_WARPS = 8;
+constexpr int GF_PART_BYTES = 65536;    // fp32 partial of the 128 x 128 output tile, [32 float4 columns][128 rows]
+
+int g_glu_fused_cluster = 0;   // mpx_debug_set(3, v): 0 = auto, 1/2/4 = force that cluster size (tests)
 
 struct GluFusedParams {
   int M, F;
@@ -24,15 +35,18 @@ struct GluFusedParams {
   __nv_bfloat16* out;
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(GF_THREADS, 1)
 glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_x,
                  const __grid_constant__ CUtensorMap tm_wug, const __grid_constant__ CUtensorMap tm_wd) {
   extern __shared__ uint8_t smem_raw[];
+  // the dynamic window starts at the same shared::cta offset in every CTA of the cluster, so the aligned
+  // carve-up below is identical across the cluster (mapa relies on that)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sX = smem;                         // 2 x 16 KB: x tile, K blocks 0 and 1
   uint8_t* sH = smem + 32768;                 // 2 x 16 KB: h chunk double buffer
   uint8_t* sW = smem + 65536;                 // GF_STAGES x 16 KB weight ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + GF_STAGES * GF_STAGE_BYTES);
+  uint8_t* sP = sW + GF_STAGES * GF_STAGE_BYTES;   // fp32 partial (cluster reduction staging)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + GF_PART_BYTES);
   uint64_t* w_full = bars;                    // [GF_STAGES]
   uint64_t* w_empty = bars + GF_STAGES;       // [GF_STAGES]
   uint64_t* x_full = bars + 2 * GF_STAGES;
@@ -43,10 +57,14 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
   uint64_t* h_empty = x_full + 8;             // [2]
   uint64_t* d_full = x_full + 10;
   uint64_t* d_empty = x_full + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 12);
+  uint64_t* part_full = x_full + 12;          // all partials of the cluster written (remote arrivals)
+  uint64_t* part_empty = x_full + 13;         // all readers of MY partial done (remote arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nchunks = p.F / 64;
+  const int ncta = (int)cluster_nctarank(), krank = (int)cluster_ctarank();
+  const int nchunks = p.F / 64 / ncta;        // chunks of the hidden dimension owned by this CTA
+  const int chunk0 = krank * nchunks;
   const int m_tiles = (p.M + 127) / 128;
 
   if (threadIdx.x == 0) {
@@ -61,12 +79,14 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
     mbar_init(x_empty, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&ug_full[b], 1);
-      mbar_init(&ug_empty[b], 4);
-      mbar_init(&h_full[b], 4);
+      mbar_init(&ug_empty[b], GF_EPI_WARPS);
+      mbar_init(&h_full[b], GF_EPI_WARPS);
       mbar_init(&h_empty[b], 1);
     }
     mbar_init(d_full, 1);
-    mbar_init(d_empty, 4);
+    mbar_init(d_empty, GF_EPI_WARPS);
+    mbar_init(part_full, GF_EPI_WARPS * ncta);
+    mbar_init(part_empty, GF_EPI_WARPS * ncta);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -75,6 +95,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
   }
   tc_fence_before();
   __syncthreads();
+  if (ncta > 1) cluster_sync_all();            // remote CTAs' barriers are initialised before anyone arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tUG[2] = {tmem_base, tmem_base + 128};
@@ -91,21 +112,21 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         tma_load_2d(tm, &w_full[stage], sW + stage * GF_STAGE_BYTES, c0, c1);
         if (++stage == GF_STAGES) { stage = 0; wphase ^= 1; }
       };
-      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.y; tile < m_tiles; tile += gridDim.y) {
         mbar_wait(x_empty, xphase ^ 1);
         mbar_arrive_expect_tx(x_full, 32768);
         tma_load_2d(&tm_x, x_full, sX, 0, tile * 128);
         tma_load_2d(&tm_x, x_full, sX + 16384, 64, tile * 128);
         xphase ^= 1;
         // weight order == MMA issue order: UG_0, then for each c: UG_{c+1} (if any), D_c
-        load_w(&tm_wug, 0, 0);
-        load_w(&tm_wug, 64, 0);
+        load_w(&tm_wug, 0, chunk0 * 128);
+        load_w(&tm_wug, 64, chunk0 * 128);
         for (int c = 0; c < nchunks; ++c) {
           if (c + 1 < nchunks) {
-            load_w(&tm_wug, 0, (c + 1) * 128);
-            load_w(&tm_wug, 64, (c + 1) * 128);
+            load_w(&tm_wug, 0, (chunk0 + c + 1) * 128);
+            load_w(&tm_wug, 64, (chunk0 + c + 1) * 128);
           }
-          load_w(&tm_wd, c * 64, 0);
+          load_w(&tm_wd, (chunk0 + c) * 64, 0);
         }
       }
     }
@@ -153,7 +174,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         umma_commit(&h_empty[b]);
         if (last) umma_commit(d_full);
       };
-      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.y; tile < m_tiles; tile += gridDim.y) {
         mbar_wait(x_full, xphase);
         xphase ^= 1;
         mbar_wait(d_empty, dphase ^ 1);       // previous tile's output accumulator has been drained
@@ -169,84 +190,139 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
   } else {
     // ================================ activation / output warps ================================
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;                        // which 32 of the chunk's 64 hidden columns
     const int r = quarter * 32 + lane;                       // row within the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    uint32_t ug_ph[2] = {0, 0}, h_ph[2] = {0, 0}, dphase = 0;
-    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+    uint32_t ug_ph[2] = {0, 0}, h_ph[2] = {0, 0}, dphase = 0, pf_phase = 0, pe_phase = 0;
+    // output columns this thread finishes: single CTA -> its half of the row; cluster -> its half of the CTA's slice
+    const int slice = 128 / ncta;                            // 128, 64 or 32 columns per CTA
+    const int ocol0 = krank * slice + half * (slice / 2);
+    const int ncol4 = slice / 8;                             // float4 groups (of 4 columns) per thread: 16, 8 or 4
+    for (int tile = blockIdx.y; tile < m_tiles; tile += gridDim.y) {
       const long long row = (long long)tile * 128 + r;
-      uint4 res[16];
-      if (row < p.M) {
-        const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + row * 128);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) res[i] = r4[i];
-      }
       for (int c = 0; c < nchunks; ++c) {
         const int b = c & 1;
         mbar_wait(&ug_full[b], ug_ph[b]);
         ug_ph[b] ^= 1;
         tc_fence_after();
-        uint32_t u0[32], u1[32], g0[32], g1[32];
-        tmem_ld_32x32(tUG[b] + lane_off, u0);
-        tmem_ld_32x32(tUG[b] + lane_off + 32, u1);
-        tmem_ld_32x32(tUG[b] + lane_off + 64, g0);
-        tmem_ld_32x32(tUG[b] + lane_off + 96, g1);
+        uint32_t u[32], g[32];
+        tmem_ld_32x32(tUG[b] + lane_off + 32 * half, u);
+        tmem_ld_32x32(tUG[b] + lane_off + 64 + 32 * half, g);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ug_empty[b]);
-        uint32_t hw[32];                                       // 64 bf16 = this row's h chunk
+        uint32_t hw[16];                                       // 32 bf16 = this warp's half of the row's h chunk
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float ua = bf16_round(__uint_as_float(u0[2 * i])), ub = bf16_round(__uint_as_float(u0[2 * i + 1]));
-          const float ga = bf16_round(__uint_as_float(g0[2 * i])), gb = bf16_round(__uint_as_float(g0[2 * i + 1]));
+          const float ua = bf16_round(__uint_as_float(u[2 * i])), ub = bf16_round(__uint_as_float(u[2 * i + 1]));
+          const float ga = bf16_round(__uint_as_float(g[2 * i])), gb = bf16_round(__uint_as_float(g[2 * i + 1]));
           hw[i] = pack_bf16(bf16_round(gelu_tanh(ua)) * ga, bf16_round(gelu_tanh(ub)) * gb);
-          const float uc = bf16_round(__uint_as_float(u1[2 * i])), ud = bf16_round(__uint_as_float(u1[2 * i + 1]));
-          const float gc = bf16_round(__uint_as_float(g1[2 * i])), gd = bf16_round(__uint_as_float(g1[2 * i + 1]));
-          hw[16 + i] = pack_bf16(bf16_round(gelu_tanh(uc)) * gc, bf16_round(gelu_tanh(ud)) * gd);
         }
         mbar_wait(&h_empty[b], h_ph[b] ^ 1);                   // MMA2 of chunk c-2 no longer reads this buffer
         h_ph[b] ^= 1;
         uint8_t* hrow = sH + b * 16384 + r * 128;
 #pragma unroll
-        for (int pc = 0; pc < 8; ++pc)
+        for (int i = 0; i < 4; ++i) {
+          const int pc = 4 * half + i;
           *reinterpret_cast<uint4*>(hrow + ((pc ^ (r & 7)) << 4)) =
-              make_uint4(hw[4 * pc], hw[4 * pc + 1], hw[4 * pc + 2], hw[4 * pc + 3]);
+              make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&h_full[b]);
       }
-      // output: bf16(acc) + residual -> bf16
       mbar_wait(d_full, dphase);
       dphase ^= 1;
       tc_fence_after();
+      if (ncta == 1) {
+        // output: bf16(acc) + residual -> bf16, straight from TMEM
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t acc[32];
-        tmem_ld_32x32(tD + lane_off + 32 * cc, acc);
-        tmem_ld_wait();
-        if (row < p.M) {
-          uint4* o4 = reinterpret_cast<uint4*>(p.out + row * 128 + 32 * cc);
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t acc[32];
+          tmem_ld_32x32(tD + lane_off + 64 * half + 32 * cc, acc);
+          tmem_ld_wait();
+          if (row < p.M) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + row * 128 + 64 * half + 32 * cc);
+            uint4* o4 = reinterpret_cast<uint4*>(p.out + row * 128 + 64 * half + 32 * cc);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint4 rv = res[4 * cc + i];
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-            uint32_t ow[4];
+            for (int i = 0; i < 4; ++i) {
+              const uint4 rv = r4[i];
+              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+              uint32_t ow[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float y0 = bf16_round(__uint_as_float(acc[8 * i + 2 * e])), y1 = bf16_round(__uint_as_float(acc[8 * i + 2 * e + 1]));
-              ow[e] = pack_bf16(y0 + bf16_lo(rw[e]), y1 + bf16_hi(rw[e]));
+              for (int e = 0; e < 4; ++e) {
+                const float y0 = bf16_round(__uint_as_float(acc[8 * i + 2 * e]));
+                const float y1 = bf16_round(__uint_as_float(acc[8 * i + 2 * e + 1]));
+                ow[e] = pack_bf16(y0 + bf16_lo(rw[e]), y1 + bf16_hi(rw[e]));
+              }
+              o4[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }
-            o4[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d_empty);
+      } else {
+        // 1. stage my fp32 partial: [float4 column group c4][row] so that a warp touches 512 contiguous bytes
+        mbar_wait_cluster(part_empty, pe_phase ^ 1);           // readers of the previous tile's partial are done
+        pe_phase ^= 1;
+        float4* stage4 = reinterpret_cast<float4*>(sP);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t acc[32];
+          tmem_ld_32x32(tD + lane_off + 64 * half + 32 * cc, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            stage4[(16 * half + 8 * cc + i) * 128 + r] =
+                make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]),
+                            __uint_as_float(acc[4 * i + 3]));
+        }
+        tc_fence_before();
+        fence_acq_rel_cluster();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(d_empty);                                // TMEM accumulator drained
+          const uint32_t pf = smem_u32(part_full);
+          for (int j = 0; j < ncta; ++j) mbar_arrive_cluster(mapa_u32(pf, j));
+        }
+        // 2. sum the CL partials of my column slice in CTA-rank order, add the residual, store
+        mbar_wait_cluster(part_full, pf_phase);
+        pf_phase ^= 1;
+        const uint32_t sp = smem_u32(sP);
+#pragma unroll 1
+        for (int i = 0; i < ncol4; i += 2) {                   // 8 output columns per iteration
+          float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+          const uint32_t off0 = (uint32_t)(((ocol0 >> 2) + i) * 128 + r) * 16u;
+          for (int j = 0; j < ncta; ++j) {
+            const uint32_t base = mapa_u32(sp, j);
+            const float4 a = ld_dsmem_f4(base + off0), bb = ld_dsmem_f4(base + off0 + 128 * 16);
+            s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+            s1.x += bb.x; s1.y += bb.y; s1.z += bb.z; s1.w += bb.w;
+          }
+          if (row < p.M) {
+            const long long o = row * 128 + ocol0 + 4 * i;
+            const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + o);
+            uint4 ov;
+            ov.x = pack_bf16(bf16_round(s0.x) + bf16_lo(rv.x), bf16_round(s0.y) + bf16_hi(rv.x));
+            ov.y = pack_bf16(bf16_round(s0.z) + bf16_lo(rv.y), bf16_round(s0.w) + bf16_hi(rv.y));
+            ov.z = pack_bf16(bf16_round(s1.x) + bf16_lo(rv.z), bf16_round(s1.y) + bf16_hi(rv.z));
+            ov.w = pack_bf16(bf16_round(s1.z) + bf16_lo(rv.w), bf16_round(s1.w) + bf16_hi(rv.w));
+            *reinterpret_cast<uint4*>(p.out + o) = ov;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t pe = smem_u32(part_empty);
+          for (int j = 0; j < ncta; ++j) mbar_arrive_cluster(mapa_u32(pe, j));
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(d_empty);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (ncta > 1) cluster_sync_all();            // nobody exits while a peer may still read its partial
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -266,7 +342,7 @@ extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const m
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_wd, wt_d, H, F, F, 64, 128);
   if (rc) return rc;
-  const int smem = 1024 + 65536 + GF_STAGES * GF_STAGE_BYTES + 256;
+  const int smem = 1024 + 65536 + GF_STAGES * GF_STAGE_BYTES + GF_PART_BYTES + 256;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(glu_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -281,7 +357,31 @@ extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const m
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   const int tiles = ceil_div(M, 128);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  glu_fused_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(p, tm_x, tm_wug, tm_wd);
+  const int nchunks = F / 64;
+  // largest cluster (split of the hidden dimension) that still fits one wave
+  int cl = 1;
+  if (nchunks % 4 == 0 && tiles * 4 <= num_sms()) cl = 4;
+  else if (nchunks % 2 == 0 && tiles * 2 <= num_sms()) cl = 2;
+  if (g_glu_fused_cluster == 1 || ((g_glu_fused_cluster == 2 || g_glu_fused_cluster == 4) && nchunks % g_glu_fused_cluster == 0))
+    cl = g_glu_fused_cluster;
+  int gy = num_sms() / cl;
+  if (gy > tiles) gy = tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cl, gy, 1);
+  cfg.blockDim = dim3(GF_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, glu_fused_kernel, p, tm_x, tm_wug, tm_wd);
+  if (le != cudaSuccess) {
+    set_error("cudaLaunchKernelEx(glu_fused, cluster %d): %s", cl, cudaGetErrorString(le));
+    return MPX_ERR_CUDA;
+  }
   return check_launch("glu_fused_kernel");
 }

@@ -22,12 +22,11 @@ __global__ void __launch_bounds__(256) embed_combine_kernel(
     const float* __restrict__ a_table, int A, const float* __restrict__ t_table, int n_tasks,
     __nv_bfloat16* __restrict__ x, long long M, int H) {
   const float sq = bf16_round(sqrtf((float)H));
-  const long long total = M * H;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < total; i += stride) {
-    const long long m = i / H;
-    const int h = (int)(i % H);
+  const unsigned total = (unsigned)(M * H);                           // host guarantees < 2^31
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const unsigned m = i / (unsigned)H;
+    const int h = (int)(i % (unsigned)H);
     // reward_encoder: nnx.Linear(1,H) in bf16: bf16(bf16(r) * bf16(w)) then + bf16(b) -> bf16
     float re = bf16_round(bf16_round(reward[m]) * bf16_round(w_r[h]));
     re = bf16_round(re + bf16_round(b_r[h]));
@@ -64,17 +63,29 @@ __global__ void embed_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const flo
   const long long r1 = min(M, r0 + (long long)rows_per_block);
   for (int h = threadIdx.x; h < H; h += blockDim.x) {
     float awr = 0.f, abr = 0.f;
-    for (long long m = r0; m < r1; ++m) {
-      const float g = __bfloat162float(dx[m * H + h]);
-      awr += bf16_round(reward[m]) * g;
-      abr += g;
-      int a = last_action[m];
-      if (a < 0) a += A;
-      if (a >= 0 && a < A) s_tab[a * H + h] += g * sq;     // column h is owned by this thread: no race
-      if (d_t_table) {
-        int tk = task_ids[m];
-        if (tk < 0) tk += n_tasks;
-        if (tk >= 0 && tk < n_tasks) s_tab[(A + tk) * H + h] += g * sq;
+    for (long long m0 = r0; m0 < r1; m0 += 8) {
+      float gv[8], rv[8];
+      int av[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {                          // independent loads first (memory-level parallelism)
+        const long long m = m0 + u < r1 ? m0 + u : r1 - 1;
+        gv[u] = m0 + u < r1 ? __bfloat162float(dx[m * H + h]) : 0.f;
+        rv[u] = reward[m];
+        av[u] = last_action[m];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float g = gv[u];
+        awr += bf16_round(rv[u]) * g;
+        abr += g;
+        int a = av[u];
+        if (a < 0) a += A;
+        if (a >= 0 && a < A) s_tab[a * H + h] += g * sq;   // column h is owned by this thread: no race
+        if (d_t_table && m0 + u < r1) {
+          int tk = task_ids[m0 + u];
+          if (tk < 0) tk += n_tasks;
+          if (tk >= 0 && tk < n_tasks) s_tab[(A + tk) * H + h] += g * sq;
+        }
       }
     }
     atomicAdd(d_wr + h, awr);
@@ -89,7 +100,9 @@ __global__ void embed_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const flo
 }
 
 // ------------------------------------------------------------------------------------------------ policy logits
-// One warp per token: logits[a] = sum_h f32(x[h]) * table[a][h]; masked entries -> finfo(f32).min.
+// 8 lanes per token (4 tokens per warp): logits[a] = sum_h f32(x[h]) * table[a][h]; masked entries -> finfo(f32).min.
+// Each lane owns H/8 consecutive features (16-byte loads); the A partial sums are reduced over the 8 lanes with 3
+// xor-shuffles each.
 __global__ void __launch_bounds__(HD_WARPS * 32) policy_logits_kernel(
     const __nv_bfloat16* __restrict__ x, const float* __restrict__ table, const uint8_t* __restrict__ mask,
     float* __restrict__ logits, long long M, int H, int A) {
@@ -97,19 +110,47 @@ __global__ void __launch_bounds__(HD_WARPS * 32) policy_logits_kernel(
   for (int i = threadIdx.x; i < A * H; i += blockDim.x) s_table[i] = table[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  long long row = (long long)blockIdx.x * HD_WARPS + (threadIdx.x >> 5);
-  const long long stride = (long long)gridDim.x * HD_WARPS;
-  for (; row < M; row += stride) {
-    float my = 0.f;
-    for (int a = 0; a < A; ++a) {
-      float acc = 0.f;
-      for (int h = lane; h < H; h += 32) acc = fmaf(__bfloat162float(x[row * H + h]), s_table[a * H + h], acc);
-      acc = warp_sum(acc);
-      if (lane == a) my = acc;
+  const int sub = lane & 7, rsel = lane >> 3;
+  const int per = H / 8;                                               // features per lane (multiple of 8)
+  long long row = ((long long)blockIdx.x * HD_WARPS + (threadIdx.x >> 5)) * 4 + rsel;
+  const long long stride = (long long)gridDim.x * HD_WARPS * 4;
+  for (long long base = row - rsel; base < M; base += stride) {
+    row = base + rsel;
+    float part[MAX_A];
+#pragma unroll
+    for (int a = 0; a < MAX_A; ++a) part[a] = 0.f;
+    if (row < M) {
+      for (int c = 0; c < per; c += 8) {
+        const uint4 v = *reinterpret_cast<const uint4*>(x + row * H + sub * per + c);
+        const float xf[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
+                             bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+#pragma unroll
+        for (int a = 0; a < MAX_A; ++a) {
+          if (a < A) {
+            const float* tr = s_table + a * H + sub * per + c;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) part[a] = fmaf(xf[e], tr[e], part[a]);
+          }
+        }
+      }
     }
-    if (lane < A) {
-      if (mask && !mask[row * A + lane]) my = -3.4028234663852886e38f;
-      logits[row * A + lane] = my;
+#pragma unroll
+    for (int a = 0; a < MAX_A; ++a) {
+      if (a < A) {
+        part[a] += __shfl_xor_sync(0xffffffffu, part[a], 1);
+        part[a] += __shfl_xor_sync(0xffffffffu, part[a], 2);
+        part[a] += __shfl_xor_sync(0xffffffffu, part[a], 4);
+      }
+    }
+    if (row < M) {
+#pragma unroll
+      for (int a = 0; a < MAX_A; ++a) {
+        if (a < A && (a & 7) == sub) {
+          float v = part[a];
+          if (mask && !mask[row * A + a]) v = -3.4028234663852886e38f;
+          logits[row * A + a] = v;
+        }
+      }
     }
   }
 }
@@ -326,6 +367,7 @@ extern "C" int mpx_embed_combine(const mpx_bf16* obs_emb, const float* reward, c
                                  long long M, int H, mpx_stream_t stream) {
   MPX_REQUIRE(obs_emb && reward && last_action && w_reward && b_reward && action_table && x && M > 0 && H > 0 && A > 0,
               "mpx_embed_combine: bad arguments");
+  MPX_REQUIRE(M * H < (1LL << 31), "mpx_embed_combine: too many elements for 32-bit indexing");
   embed_combine_kernel<<<grid_for(M * H, 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(obs_emb), reward, last_action, task_ids, w_reward, b_reward, action_table,
       A, task_table, n_tasks, reinterpret_cast<__nv_bfloat16*>(x), M, H);
@@ -338,7 +380,7 @@ extern "C" int mpx_embed_bwd(const mpx_bf16* dx, const float* reward, const int3
   MPX_REQUIRE(dx && reward && last_action && d_w_reward && d_b_reward && d_action_table && M > 0 && H > 0 && A > 0,
               "mpx_embed_bwd: bad arguments");
   MPX_REQUIRE(!d_task_table || task_ids, "mpx_embed_bwd: task table gradient requested without task ids");
-  int rows = (int)((M + (long long)num_sms() * 2 - 1) / ((long long)num_sms() * 2));
+  int rows = (int)((M + (long long)num_sms() * 8 - 1) / ((long long)num_sms() * 8));
   if (rows < 64) rows = 64;
   const int grid = (int)((M + rows - 1) / rows);
   const size_t smem = (size_t)(A + (d_task_table ? n_tasks : 0)) * H * sizeof(float);
@@ -353,9 +395,10 @@ extern "C" int mpx_policy_logits(const mpx_bf16* x, const float* table, const ui
                                  long long M, int H, int A, mpx_stream_t stream) {
   MPX_REQUIRE(x && table && logits && M > 0 && H > 0, "mpx_policy_logits: bad arguments");
   MPX_REQUIRE(A > 0 && A <= MAX_A, "mpx_policy_logits: A=%d not in [1,%d]", A, MAX_A);
+  MPX_REQUIRE(H % 64 == 0, "mpx_policy_logits: H=%d must be a multiple of 64", H);
   const size_t smem = (size_t)A * H * sizeof(float);
   MPX_REQUIRE(smem <= 48 * 1024, "mpx_policy_logits: table too large for shared memory");
-  policy_logits_kernel<<<grid_for(M, HD_WARPS, 8), HD_WARPS * 32, smem, (cudaStream_t)stream>>>(
+  policy_logits_kernel<<<grid_for(M, HD_WARPS * 4, 8), HD_WARPS * 32, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), table, action_mask, logits, M, H, A);
   return check_launch("mpx_policy_logits");
 }
@@ -404,7 +447,7 @@ static int launch_phb(const float* dlogits, const __nv_bfloat16* x, const float*
     return MPX_ERR_UNSUPPORTED;
   }
   long long g = (M + HD_WARPS - 1) / HD_WARPS;
-  const long long cap = (long long)num_sms() * 2;
+  const long long cap = (long long)num_sms() * 6;
   const int grid = (int)(g < cap ? g : cap);
   switch (H / 32) {
     case 4: policy_head_bwd_kernel<AMAX, 4><<<grid, HD_WARPS * 32, smem, s>>>(dlogits, x, table, dx_other, dx, dtable, M, A); break;

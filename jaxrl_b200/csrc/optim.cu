@@ -172,15 +172,15 @@ __global__ void __launch_bounds__(256) muon_prepare_kernel(const MuonMat* __rest
   const int t = step[0];
   const float bc1 = 1.0f - powf(beta, (float)(t + 1));
   const float bc2 = 1.0f - powf(beta, (float)(t + 2));
-  const long long n = (long long)mt.rows * mt.cols;
+  const unsigned n = (unsigned)(mt.rows * mt.cols);
   float acc = 0.f;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+  for (unsigned i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
     const float gi = g[mt.off + i] * grad_scale;
     const float m = beta * mu[mt.off + i] + (1.0f - beta) * gi;
     mu[mt.off + i] = m;
     const float mh = beta * (m / bc2) + (1.0f - beta) * (gi / bc1);
-    const int pr = (int)(i / mt.cols), pc = (int)(i % mt.cols);
-    const long long xi = mt.transposed ? (long long)pc * mt.c + pr : i;
+    const int pr = (int)(i / (unsigned)mt.cols), pc = (int)(i % (unsigned)mt.cols);
+    const long long xi = mt.transposed ? (long long)pc * mt.c + pr : (long long)i;
     X[mt.xoff + xi] = mh;
     acc += mh * mh;
   }
@@ -224,14 +224,29 @@ __global__ void __launch_bounds__(256) muon_ns_gemm_kernel(const MuonMat* __rest
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = kbeg; k0 < kend; k0 += 16) {
-    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+  // software pipeline: the next k slab's global loads are in flight (registers) while the current slab is multiplied
+  float pa[4], pb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = threadIdx.x + q * 256;
       const int kk = i % 16, mm = i / 16;
-      sA[kk][mm] = (m0 + mm < M && k0 + kk < kend) ? A[(long long)(m0 + mm) * lda + k0 + kk] : 0.f;
+      pa[q] = (m0 + mm < M && k0 + kk < kend) ? A[(long long)(m0 + mm) * lda + k0 + kk] : 0.f;
       const int kb = (sbj == 1) ? i / 64 : i % 16, nb = (sbj == 1) ? i % 64 : i / 16;
-      sB[kb][nb] = (n0 + nb < N && k0 + kb < kend) ? B[(long long)(k0 + kb) * sbk + (long long)(n0 + nb) * sbj] : 0.f;
+      pb[q] = (n0 + nb < N && k0 + kb < kend) ? B[(long long)(k0 + kb) * sbk + (long long)(n0 + nb) * sbj] : 0.f;
+    }
+  };
+  fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = threadIdx.x + q * 256;
+      sA[i % 16][i / 16] = pa[q];
+      if (sbj == 1) sB[i / 64][i % 64] = pb[q];
+      else sB[i % 16][i / 16] = pb[q];
     }
     __syncthreads();
+    if (k0 + 16 < kend) fetch(k0 + 16);
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
       const float4 av = *reinterpret_cast<const float4*>(&sA[kk][ty * 4]);
@@ -269,11 +284,11 @@ __global__ void __launch_bounds__(256) muon_finish_kernel(const MuonMat* __restr
   const int t = step[0];
   const float lr = lr0 * (1.0f - fminf((float)t, total_steps) / total_steps);
   const float shape_scale = sqrtf(fmaxf(1.0f, (float)mt.cols / (float)mt.rows));   // sqrt(max(1, fan_out / fan_in))
-  const long long n = (long long)mt.rows * mt.cols;
+  const unsigned n = (unsigned)(mt.rows * mt.cols);
   double acc = 0.0;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-    const int pr = (int)(i / mt.cols), pc = (int)(i % mt.cols);
-    const long long xi = mt.transposed ? (long long)pc * mt.c + pr : i;
+  for (unsigned i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const int pr = (int)(i / (unsigned)mt.cols), pc = (int)(i % (unsigned)mt.cols);
+    const long long xi = mt.transposed ? (long long)pc * mt.c + pr : (long long)i;
     const float u = -lr * (shape_scale * X[mt.xoff + xi] + wd * p[mt.off + i]);
     upd[mt.off + i] = u;
     acc += (double)u * (double)u;
@@ -339,7 +354,7 @@ extern "C" int mpx_prep_weights(const mpx_prep_desc* descs_device, int ndesc, mp
 // parameters, the matrices described by `mats` (device array of nmat entries, see MuonMat) live in [n_adam, n).
 // ns_ws: fp32 workspace >= 2*sum(r*c) + 2*sum(r*r) + nmat floats.  workspace >= mpx_muon_workspace_bytes(n, nmat).
 extern "C" size_t mpx_muon_workspace_bytes(long long n, int nmat) {
-  return (size_t)(opt_grid(n > 0 ? n : 1) + (size_t)nmat * 8) * sizeof(double);
+  return (size_t)(opt_grid(n > 0 ? n : 1) + (size_t)nmat * 32) * sizeof(double);
 }
 
 extern "C" int mpx_muon_step(float* params, const float* grads, float* mu, float* nu, float* update_scratch,
@@ -366,7 +381,7 @@ extern "C" int mpx_muon_step(float* params, const float* grads, float* mu, float
     float* Bb = Ab + a_total;
     float* norm2 = Bb + a_total;
     cudaMemsetAsync(norm2, 0, (size_t)nmat * sizeof(float), s);
-    muon_prepare_kernel<<<dim3(8, nmat), 256, 0, s>>>(mm, grads, mu, X0, norm2, step, muon_beta, grad_scale);
+    muon_prepare_kernel<<<dim3(32, nmat), 256, 0, s>>>(mm, grads, mu, X0, norm2, step, muon_beta, grad_scale);
     const float c0 = 3.4445f, c1 = -4.7750f, c2 = 2.0315f;
     float* xin = X0;
     float* xout = X1;
@@ -379,9 +394,9 @@ extern "C" int mpx_muon_step(float* params, const float* grads, float* mu, float
       muon_ns_gemm_kernel<<<dim3(tc, tr, nmat), 256, 0, s>>>(mm, xin, xout, Ab, Bb, norm2, 2, first, tc, c0, c1, c2, eps);
       float* tmp = xin; xin = xout; xout = tmp;
     }
-    muon_finish_kernel<<<dim3(8, nmat), 256, 0, s>>>(mm, xin, params, update_scratch, step, lr0, total_steps,
+    muon_finish_kernel<<<dim3(32, nmat), 256, 0, s>>>(mm, xin, params, update_scratch, step, lr0, total_steps,
                                                      weight_decay, partials + agrid);
-    nparts += 8 * nmat;
+    nparts += 32 * nmat;
   }
   const int pgrid = opt_grid(n);
   apply_update_kernel<<<pgrid, 256, 0, s>>>(params, update_scratch, n, partials, nparts, max_norm, step, update_norm_out);

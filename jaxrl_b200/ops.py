@@ -107,8 +107,21 @@ def linear(x, wt, bias=None, residual=None, act: int = 0, out: Optional[torch.Te
     return out if want_bf16 else out_f32
 
 
+_WGRAD_WS = {}
+
+
+def wgrad_workspace(device, nbytes: int = 96 << 20) -> torch.Tensor:
+    """Shared scratch for the deterministic split-K reduction of mpx_linear_wgrad (one per device)."""
+    key = (torch.device(device).index or 0)
+    ws = _WGRAD_WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _WGRAD_WS[key] = ws
+    return ws
+
+
 def linear_wgrad(x, dy, dw, M: Optional[int] = None, K: Optional[int] = None, N: Optional[int] = None,
-                 ldx: Optional[int] = None, ldy: Optional[int] = None, lddw: Optional[int] = None):
+                 ldx: Optional[int] = None, ldy: Optional[int] = None, lddw: Optional[int] = None, ws=None):
     """dw (K,N) f32 += x^T @ dy.  Column sub-blocks are addressed with explicit pitches (ldx/ldy/lddw)."""
     _req(dw, F32, "dw")
     assert x.dtype == BF16 and dy.dtype == BF16 and x.is_cuda and dy.is_cuda
@@ -118,7 +131,9 @@ def linear_wgrad(x, dy, dw, M: Optional[int] = None, K: Optional[int] = None, N:
     N = ldy if N is None else N
     M = x.numel() // x.shape[-1] if M is None else M
     lddw = dw.shape[-1] if lddw is None else lddw
-    a = _lib.WgradArgs(ptr(x), ldx, ptr(dy), ldy, ptr(dw), lddw, M, N, K)
+    if ws is None:
+        ws = wgrad_workspace(dw.device)
+    a = _lib.WgradArgs(ptr(x), ldx, ptr(dy), ldy, ptr(dw), lddw, M, N, K, ptr(ws), ws.numel())
     check(lib.mpx_linear_wgrad(C.byref(a), stream()), "mpx_linear_wgrad")
     return dw
 

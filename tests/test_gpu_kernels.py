@@ -402,11 +402,14 @@ def test_transpose_tb(ops):
     assert torch.equal(fd.cpu(), f.t())
 
 
-@pytest.mark.parametrize("M", [77, 4096, 20000])
-def test_glu_fused(ops, M):
-    """Fused GLU block + residual (h stays on chip) vs the oracle GLUBlock."""
-    gen = g(M)
-    K, F = 128, 768
+@pytest.mark.parametrize("M,F,cluster", [(77, 768, 0), (4096, 768, 0), (4096, 768, 1), (4096, 768, 2), (1000, 512, 4),
+                                         (5000, 768, 4), (20000, 768, 0), (20000, 640, 2), (300, 192, 0)])
+def test_glu_fused(ops, M, F, cluster):
+    """Fused GLU block + residual (h stays on chip) vs the oracle GLUBlock; every cluster split of the hidden
+    dimension (partials summed over distributed shared memory) and the persistent multi-tile loop."""
+    from jaxrl_b200._lib import lib
+    gen = g(M + F + cluster)
+    K = 128
     x = torch.randn(M, K, generator=gen).to(BF16)
     res = torch.randn(M, K, generator=gen).to(BF16)
     wu = torch.randn(K, F, generator=gen) / math.sqrt(K)
@@ -415,6 +418,11 @@ def test_glu_fused(ops, M):
     pdict = {"f.up_proj.kernel": wu, "f.up_gate.kernel": wg, "f.down_proj.kernel": wd}
     ref = (O.glu_block(pdict, "f.", x).float() + res.float()).to(BF16)
     out = torch.empty(M, K, dtype=BF16, device=DEV)
-    ops.glu_fused(x.to(DEV), ops.pack_glu_weight64(wu, wg).to(DEV), wd.t().contiguous().to(BF16).to(DEV), res.to(DEV), out, F)
-    torch.cuda.synchronize()
-    assert_close_bf16(out, ref, f"glu_fused M={M}", rtol=1e-2, abs_floor_frac=1e-2, allow_frac=1e-3, max_err_frac=0.1)
+    lib.mpx_debug_set(3, cluster)
+    try:
+        ops.glu_fused(x.to(DEV), ops.pack_glu_weight64(wu, wg).to(DEV), wd.t().contiguous().to(BF16).to(DEV), res.to(DEV), out, F)
+        torch.cuda.synchronize()
+    finally:
+        lib.mpx_debug_set(3, 0)
+    assert_close_bf16(out, ref, f"glu_fused M={M} F={F} cl={cluster}", rtol=1e-2, abs_floor_frac=1e-2, allow_frac=1e-3,
+                      max_err_frac=0.1)
