@@ -70,7 +70,8 @@ struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // + barriers + 1 KB alignment slack
+  static constexpr int XPOSE_OFFSET = BAR_OFFSET + 256;   // 2 KB per epilogue warp: row-per-lane <-> coalesced transposes
+  static constexpr int TOTAL = XPOSE_OFFSET + 8 * 2048 + 1024;   // + 1 KB alignment slack
 };
 
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&f)[32]) {
@@ -97,6 +98,59 @@ __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, float (&f
   }
 }
 
+
+// ---- row-per-lane <-> coalesced re-layout of a 32-row x 32-column bf16 tile through a 2 KB per-warp smem buffer.
+// The epilogue holds one output ROW per lane (TMEM lane == row).  Writing that straight to global memory makes
+// every warp store touch 32 different 128-byte lines with 16 bytes each, and the L1 tag stage (one line per cycle)
+// becomes the bottleneck of epilogue-heavy GEMMs.  After the transpose, lane = (row r8, 16-byte piece j): one warp
+// store covers 8 rows x 64 contiguous bytes.  The XOR swizzle keeps both smem phases bank-conflict free.
+__device__ __forceinline__ void pack_row(const float (&f)[32], uint4 (&v)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    v[i] = make_uint4(pack_bf16(f[8 * i + 0], f[8 * i + 1]), pack_bf16(f[8 * i + 2], f[8 * i + 3]),
+                      pack_bf16(f[8 * i + 4], f[8 * i + 5]), pack_bf16(f[8 * i + 6], f[8 * i + 7]));
+}
+// tile: global address of (first row of the warp, first column of the chunk); rows_valid in [0, 32].
+__device__ __forceinline__ void warp_store_tile(uint8_t* xp, __nv_bfloat16* tile, long long ld, int rows_valid,
+                                                const uint4 (&v)[4], int lane) {
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(xp + lane * 64 + ((j ^ sw) << 4)) = v[j];
+  __syncwarp();
+  const int r8 = lane >> 2, j = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int R = 8 * i + r8;
+    const uint4 x = *reinterpret_cast<const uint4*>(xp + R * 64 + ((j ^ ((R >> 1) & 3)) << 4));
+    if (R < rows_valid) *reinterpret_cast<uint4*>(tile + (long long)R * ld + j * 8) = x;
+  }
+  __syncwarp();
+}
+// coalesced global read of the warp's 32 x 32 tile into registers (lane = (r8, j) layout) ...
+__device__ __forceinline__ void warp_fetch_tile(const __nv_bfloat16* tile, long long ld, int rows_valid, uint4 (&c)[4],
+                                                int lane) {
+  const int r8 = lane >> 2, j = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int R = 8 * i + r8;
+    c[i] = (R < rows_valid) ? *reinterpret_cast<const uint4*>(tile + (long long)R * ld + j * 8) : make_uint4(0, 0, 0, 0);
+  }
+}
+// ... and its conversion to one row per lane
+__device__ __forceinline__ void warp_rows_from_fetched(uint8_t* xp, const uint4 (&c)[4], uint4 (&v)[4], int lane) {
+  const int r8 = lane >> 2, j = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int R = 8 * i + r8;
+    *reinterpret_cast<uint4*>(xp + R * 64 + ((j ^ ((R >> 1) & 3)) << 4)) = c[i];
+  }
+  __syncwarp();
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) v[jj] = *reinterpret_cast<const uint4*>(xp + lane * 64 + ((jj ^ sw) << 4));
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------ epilogues
 // Each epilogue thread owns one output row; `acc` holds 32 consecutive fp32 columns starting at `col0`.
 __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
@@ -104,12 +158,15 @@ __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
   f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
 }
 
-// rpre: this chunk's residual, already in registers (4 x uint4), or nullptr.
-__device__ __forceinline__ void epi_store(const GemmParams& p, int row, int col0, const uint32_t (&acc)[32],
-                                          const uint4* rpre = nullptr) {
-  if (row >= p.M || col0 >= p.N) return;
+// Warp-cooperative: every lane of the warp must call (rows beyond M are masked inside).  row0 = first row of the warp,
+// rpre: this chunk's residual already fetched with warp_fetch_tile (when use_pre).
+__device__ __forceinline__ void epi_store(const GemmParams& p, int row0, int lane, int col0, const uint32_t (&acc)[32],
+                                          uint8_t* xp, const uint4 (&rpre)[4], bool use_pre) {
+  if (row0 >= p.M || col0 >= p.N) return;                 // warp-uniform
+  const int row = row0 + lane;
+  const int rows_valid = min(32, p.M - row0);
   const bool full = (col0 + 32 <= p.N);
-  if (p.y_f32) {
+  if (p.y_f32 && row < p.M) {
     float* d = p.y_f32 + (long long)row * p.ldy32 + col0;
     if (full && ((p.ldy32 & 3) == 0)) {
 #pragma unroll
@@ -137,56 +194,70 @@ __device__ __forceinline__ void epi_store(const GemmParams& p, int row, int col0
         if (col0 + i < p.N) f[i] = bf16_round(f[i] + __bfloat162float(p.bias[col0 + i]));
     }
   }
+  // 16-byte pieces everywhere: pitches are multiples of 8 elements and the bases 16-byte aligned
+  const bool vec_y = full && ((p.ldy & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
   if (p.y_pre) {
-    __nv_bfloat16* dp = p.y_pre + (long long)row * p.ldy + col0;
-    if (full && ((p.ldy & 7) == 0)) store_bf16x32(dp, f);
-    else for (int i = 0; i < 32 && col0 + i < p.N; ++i) dp[i] = __float2bfloat16_rn(f[i]);
+    if (vec_y && ((reinterpret_cast<uintptr_t>(p.y_pre) & 15) == 0)) {
+      uint4 v[4];
+      pack_row(f, v);
+      warp_store_tile(xp, p.y_pre + (long long)row0 * p.ldy + col0, p.ldy, rows_valid, v, lane);
+    } else if (row < p.M) {
+      __nv_bfloat16* dp = p.y_pre + (long long)row * p.ldy + col0;
+      for (int i = 0; i < 32 && col0 + i < p.N; ++i) dp[i] = __float2bfloat16_rn(f[i]);
+    }
   }
   if (p.act == 1) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = bf16_round(gelu_tanh(f[i]));
   }
-  const bool vec_ok = full && ((p.ldy & 7) == 0) && (!p.residual || (p.ldr & 7) == 0);
   if (p.residual) {
-    const __nv_bfloat16* r = p.residual + (long long)row * p.ldr + col0;
-    if (rpre) {
+    const bool vec_r = full && ((p.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+    if (use_pre || vec_r) {
+      uint4 c[4], v[4];
+      if (use_pre) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[i] = rpre[i];
+      } else {
+        warp_fetch_tile(p.residual + (long long)row0 * p.ldr + col0, p.ldr, rows_valid, c, lane);
+      }
+      warp_rows_from_fetched(xp, c, v, lane);
       float rf[32];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) unpack8(rpre[i], rf + 8 * i);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = f[i] + rf[i];
-    } else if (vec_ok) {
-      float rf[32];
-      load_bf16x32(r, rf);
+      for (int i = 0; i < 4; ++i) unpack8(v[i], rf + 8 * i);
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] = f[i] + rf[i];   // rounded to bf16 by the store
-    } else {
+    } else if (row < p.M) {
+      const __nv_bfloat16* r = p.residual + (long long)row * p.ldr + col0;
       for (int i = 0; i < 32 && col0 + i < p.N; ++i) f[i] = f[i] + __bfloat162float(r[i]);
     }
   }
-  __nv_bfloat16* d = p.y + (long long)row * p.ldy + col0;
-  if (vec_ok) {
-    store_bf16x32(d, f);
-  } else if ((p.ldy & 7) == 0 && (p.N & 7) == 0) {   // ragged last chunk, still whole 16-byte pieces
+  if (vec_y) {
+    uint4 v[4];
+    pack_row(f, v);
+    warp_store_tile(xp, p.y + (long long)row0 * p.ldy + col0, p.ldy, rows_valid, v, lane);
+  } else if (row < p.M) {
+    __nv_bfloat16* d = p.y + (long long)row * p.ldy + col0;
+    if ((p.ldy & 7) == 0 && (p.N & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0)) {   // ragged last chunk
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (col0 + 8 * i < p.N)
-        reinterpret_cast<uint4*>(d)[i] = make_uint4(pack_bf16(f[8 * i], f[8 * i + 1]), pack_bf16(f[8 * i + 2], f[8 * i + 3]),
-                                                    pack_bf16(f[8 * i + 4], f[8 * i + 5]), pack_bf16(f[8 * i + 6], f[8 * i + 7]));
-  } else {
-    for (int i = 0; i < 32 && col0 + i < p.N; ++i) d[i] = __float2bfloat16_rn(f[i]);
+      for (int i = 0; i < 4; ++i)
+        if (col0 + 8 * i < p.N)
+          reinterpret_cast<uint4*>(d)[i] = make_uint4(pack_bf16(f[8 * i], f[8 * i + 1]), pack_bf16(f[8 * i + 2], f[8 * i + 3]),
+                                                      pack_bf16(f[8 * i + 4], f[8 * i + 5]), pack_bf16(f[8 * i + 6], f[8 * i + 7]));
+    } else {
+      for (int i = 0; i < 32 && col0 + i < p.N; ++i) d[i] = __float2bfloat16_rn(f[i]);
+    }
   }
 }
 
-// One 32-column chunk == one attention head (head_dim 32).
-__device__ __forceinline__ void epi_qkv(const GemmParams& p, int row, int col0, const uint32_t (&acc)[32],
-                                        const float (&sn)[16], const float (&cs)[16]) {
-  if (row >= p.M || col0 >= p.N) return;
+// One 32-column chunk == one attention head (head_dim 32).  Warp-cooperative like epi_store.
+__device__ __forceinline__ void epi_qkv(const GemmParams& p, int row0, int lane, int col0, const uint32_t (&acc)[32],
+                                        const float (&sn)[16], const float (&cs)[16], uint8_t* xp) {
+  if (row0 >= p.M || col0 >= p.N) return;
+  const int rows_valid = min(32, p.M - row0);
   const int head = col0 >> 5;
   float f[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = bf16_round(__uint_as_float(acc[i]));   // projection output is bf16
-  __nv_bfloat16* dst;
   if (head < p.Nq + p.Nkv) {
     float o[32];
 #pragma unroll
@@ -197,8 +268,11 @@ __device__ __forceinline__ void epi_qkv(const GemmParams& p, int row, int col0, 
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = o[i];
   }
+  __nv_bfloat16* dst;
+  long long ld;
   if (head < p.Nq) {
-    dst = p.q + (long long)row * p.q_row_stride + head * 32;
+    dst = p.q + (long long)row0 * p.q_row_stride + head * 32;
+    ld = p.q_row_stride;
   } else {
     long long slot_off = 0;
     if (p.cache_S > 0) {
@@ -206,15 +280,27 @@ __device__ __forceinline__ void epi_qkv(const GemmParams& p, int row, int col0, 
       if (p0 < 0) p0 += p.cache_S;
       slot_off = (long long)p0 * (p.Nkv * 32);
     }
-    if (head < p.Nq + p.Nkv) dst = p.k + (long long)row * p.k_row_stride + slot_off + (head - p.Nq) * 32;
-    else dst = p.v + (long long)row * p.v_row_stride + slot_off + (head - p.Nq - p.Nkv) * 32;
+    if (head < p.Nq + p.Nkv) {
+      dst = p.k + (long long)row0 * p.k_row_stride + slot_off + (head - p.Nq) * 32;
+      ld = p.k_row_stride;
+    } else {
+      dst = p.v + (long long)row0 * p.v_row_stride + slot_off + (head - p.Nq - p.Nkv) * 32;
+      ld = p.v_row_stride;
+    }
   }
-  store_bf16x32(dst, f);
+  uint4 v[4];
+  pack_row(f, v);
+  if ((ld & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    warp_store_tile(xp, dst, ld, rows_valid, v, lane);
+  } else if (lane < rows_valid) {
+    store_bf16x32(dst + (long long)lane * ld, f);
+  }
 }
 
-__device__ __forceinline__ void epi_glu(const GemmParams& p, int row, int hcol0, const uint32_t (&u)[32],
-                                        const uint32_t (&g)[32]) {
-  if (row >= p.M || hcol0 >= p.F) return;
+__device__ __forceinline__ void epi_glu(const GemmParams& p, int row0, int lane, int hcol0, const uint32_t (&u)[32],
+                                        const uint32_t (&g)[32], uint8_t* xp) {
+  if (row0 >= p.M || hcol0 >= p.F) return;
+  const int rows_valid = min(32, p.M - row0);
   float uf[32], gf[32], hf[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
@@ -222,10 +308,18 @@ __device__ __forceinline__ void epi_glu(const GemmParams& p, int row, int hcol0,
     gf[i] = bf16_round(__uint_as_float(g[i]));
     hf[i] = bf16_round(gelu_tanh(uf[i])) * gf[i];
   }
-  const long long o = (long long)row * p.F + hcol0;
-  store_bf16x32(p.h + o, hf);
-  if (p.u_save) store_bf16x32(p.u_save + o, uf);
-  if (p.g_save) store_bf16x32(p.g_save + o, gf);
+  const long long o = (long long)row0 * p.F + hcol0;
+  uint4 v[4];
+  pack_row(hf, v);
+  warp_store_tile(xp, p.h + o, p.F, rows_valid, v, lane);
+  if (p.u_save) {
+    pack_row(uf, v);
+    warp_store_tile(xp, p.u_save + o, p.F, rows_valid, v, lane);
+  }
+  if (p.g_save) {
+    pack_row(gf, v);
+    warp_store_tile(xp, p.g_save + o, p.F, rows_valid, v, lane);
+  }
 }
 
 // fp32-weight Linear emulated with a bf16 hi/lo split of the weight: out[j] = acc[j] + acc[64 + j] + bias[j].
@@ -341,12 +435,14 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;        // which of the two warps of this quarter: takes chunks with (c/32)&1 == half
     const int row_in_tile = quarter * 32 + lane;
+    uint8_t* xp = smem + L::XPOSE_OFFSET + (warp - 2) * 2048;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int row = m_blk * BLOCK_M + row_in_tile;
+      const int row0 = m_blk * BLOCK_M + quarter * 32;      // first row of this warp
+      const int row = row0 + lane;
       float sn[16], cs[16];
       if constexpr (EPI == EPI_QKV) {
         if (row < p.M) {
@@ -357,18 +453,18 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
       }
       // residual rows of this tile are fetched BEFORE waiting for the accumulator (hides the global-load latency)
       constexpr int kMine = (BLOCK_N / 32 + 1) / 2;                  // 32-column chunks owned by this warp (at most)
-      constexpr int kPre = (EPI == EPI_STORE && BLOCK_N <= 128) ? kMine * 4 : 1;
-      uint4 rpre[kPre];
+      constexpr int kPre = (EPI == EPI_STORE && BLOCK_N <= 128) ? kMine : 1;
+      uint4 rpre[kPre][4];
       bool have_pre = false;
       if constexpr (EPI == EPI_STORE && BLOCK_N <= 128) {
-        if (p.residual && p.y && row < p.M && (p.ldr & 7) == 0 && (p.ldy & 7) == 0 && (n_blk + 1) * BLOCK_N <= p.N) {
-          const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + (long long)row * p.ldr + n_blk * BLOCK_N);
+        if (p.residual && p.y && row0 < p.M && (p.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0 &&
+            (n_blk + 1) * BLOCK_N <= p.N) {
+          const int rows_valid = min(32, p.M - row0);
 #pragma unroll
           for (int j = 0; j < kMine; ++j)
-            if ((2 * j + half) * 32 < BLOCK_N) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) rpre[4 * j + i] = r4[(2 * j + half) * 4 + i];
-            }
+            if ((2 * j + half) * 32 < BLOCK_N)
+              warp_fetch_tile(p.residual + (long long)row0 * p.ldr + n_blk * BLOCK_N + (2 * j + half) * 32, p.ldr,
+                              rows_valid, rpre[j], lane);
           have_pre = true;
         }
       }
@@ -383,7 +479,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
           tmem_ld_32x32(t_row + c, u);
           tmem_ld_32x32(t_row + 128 + c, g);
           tmem_ld_wait();
-          epi_glu(p, row, n_blk * 128 + c, u, g);
+          epi_glu(p, row0, lane, n_blk * 128 + c, u, g, xp);
         }
       } else if constexpr (EPI == EPI_PAIRSUM) {
         {
@@ -402,7 +498,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
             uint32_t acc[32];
             tmem_ld_32x32(t_row + c, acc);
             tmem_ld_wait();
-            epi_store(p, row, n_blk * BLOCK_N + c, acc, have_pre ? &rpre[4 * j] : nullptr);
+            epi_store(p, row0, lane, n_blk * BLOCK_N + c, acc, xp, rpre[j], have_pre);
           }
         }
       } else {
@@ -411,8 +507,8 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
           uint32_t acc[32];
           tmem_ld_32x32(t_row + c, acc);
           tmem_ld_wait();
-          if constexpr (EPI == EPI_QKV) epi_qkv(p, row, n_blk * BLOCK_N + c, acc, sn, cs);
-          else epi_store(p, row, n_blk * BLOCK_N + c, acc);
+          if constexpr (EPI == EPI_QKV) epi_qkv(p, row0, lane, n_blk * BLOCK_N + c, acc, sn, cs, xp);
+          else epi_store(p, row0, lane, n_blk * BLOCK_N + c, acc, xp, rpre[0], false);
         }
       }
       tc_fence_before();
@@ -552,24 +648,51 @@ gemm_wgrad_kernel(int M, int N, int K, float* __restrict__ dw, long long lddw, f
 }
 
 // dw[k][n] += sum over splits of partial[s][k][n]   (fixed summation order: deterministic)
+// Block = 8 warps: each warp owns a strided subset of the splits for the same 32 float4 (512 contiguous bytes), with
+// four independent loads in flight; the 8 per-warp sums are combined through shared memory in warp order.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int kp, int np,
                                                            float* __restrict__ dw, long long lddw, int K, int N) {
+  __shared__ float4 s_part[8][32];
   const int n4 = np / 4;
   const int total = K * n4;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
-    const int k = i / n4, n = (i % n4) * 4;
-    if (n >= N) continue;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long split_stride = (long long)kp * np;
+  for (int base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {
+    const int i = base + lane;
+    const bool live = i < total;
+    const int k = live ? i / n4 : 0, n = live ? (i % n4) * 4 : 0;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* p = partial + (long long)k * np + n;
-    for (int s = 0; s < splits; ++s) {
-      const float4 v = *reinterpret_cast<const float4*>(p + (long long)s * kp * np);
-      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    if (live && n < N) {
+      const float* p = partial + (long long)k * np + n;
+      int s = warp;
+      for (; s + 24 < splits; s += 32) {
+        const float4 v0 = *reinterpret_cast<const float4*>(p + (long long)s * split_stride);
+        const float4 v1 = *reinterpret_cast<const float4*>(p + (long long)(s + 8) * split_stride);
+        const float4 v2 = *reinterpret_cast<const float4*>(p + (long long)(s + 16) * split_stride);
+        const float4 v3 = *reinterpret_cast<const float4*>(p + (long long)(s + 24) * split_stride);
+        a.x += (v0.x + v1.x) + (v2.x + v3.x); a.y += (v0.y + v1.y) + (v2.y + v3.y);
+        a.z += (v0.z + v1.z) + (v2.z + v3.z); a.w += (v0.w + v1.w) + (v2.w + v3.w);
+      }
+      for (; s < splits; s += 8) {
+        const float4 v = *reinterpret_cast<const float4*>(p + (long long)s * split_stride);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
     }
-    float* d = dw + (long long)k * lddw + n;
-    d[0] += a.x;
-    if (n + 1 < N) d[1] += a.y;
-    if (n + 2 < N) d[2] += a.z;
-    if (n + 3 < N) d[3] += a.w;
+    s_part[warp][lane] = a;
+    __syncthreads();
+    if (warp == 0 && live && n < N) {
+#pragma unroll
+      for (int w = 1; w < 8; ++w) {
+        const float4 v = s_part[w][lane];
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      float* d = dw + (long long)k * lddw + n;
+      d[0] += a.x;
+      if (n + 1 < N) d[1] += a.y;
+      if (n + 2 < N) d[2] += a.z;
+      if (n + 3 < N) d[3] += a.w;
+    }
+    __syncthreads();
   }
 }
 
@@ -673,7 +796,7 @@ static int launch_wgrad(const mpx_wgrad_args* a, cudaStream_t stream) {
                                                                g_debug_swap_lbo_sbo, tm_x, tm_dy);
   if (partial) {
     const int total = a->K * (nb * WG_N / 4);
-    int rg = ceil_div(total, 256);
+    int rg = ceil_div(total, 32);
     if (rg > num_sms() * 8) rg = num_sms() * 8;
     wgrad_reduce_kernel<<<rg, 256, 0, stream>>>(partial, splits, kb * 128, nb * WG_N, a->dw, a->lddw, a->K, a->N);
   }
