@@ -13,7 +13,7 @@ python bench.py --ncu-minibatch > gpurun_out/plain_mb.log 2>&1 && \
 timeout 600 ncu --metrics $M --clock-control none --profile-from-start off --csv --log-file gpurun_out/mb_metrics_t11.csv python bench.py --ncu-minibatch > gpurun_out/ncu_mb.log 2>&1
 echo "ncu mb exit $?" >> gpurun_out/t11.log
 timeout 900 ncu --set full --import-source on --clock-control none --profile-from-start off --kernel-name-base demangled \
-  -k 'regex:gemm_tn_kernel<\(int\)(256|128), \(int\)(0|2)>' -c 8 -f -o gpurun_out/gemm_full_t11 python bench.py --ncu-minibatch > gpurun_out/ncu_gemm_full.log 2>&1
+  -k 'regex:.*gemm_tn_kernel<(256|128), (0|2)>.*' -c 8 -f -o gpurun_out/gemm_full_t11 python bench.py --ncu-minibatch > gpurun_out/ncu_gemm_full.log 2>&1
 echo "ncu gemm full exit $?" >> gpurun_out/t11.log
 ls -la gpurun_out/*.ncu-rep >> gpurun_out/t11.log 2>&1
 cat gpurun_out/t11.log
