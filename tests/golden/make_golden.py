@@ -114,7 +114,7 @@ def oracle_rope_attention():
         o = O.dot_product_attention(q, kc, vc, kv_len=kv_len)
         outs[f"decode_out_len{kv_len}"] = o.float().numpy()
     # causal training attention (attention.py:151-169)
-    T = 40
+    T = 64
     qt = torch.randn(2, T, Nq, D, generator=g).to(torch.bfloat16)
     kt = torch.randn(2, T, Nkv, D, generator=g).to(torch.bfloat16)
     vt = torch.randn(2, T, Nkv, D, generator=g).to(torch.bfloat16)
