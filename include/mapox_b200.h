@@ -32,7 +32,8 @@ int mpx_version(void);
 /* Debug/tuning knobs (tests only). key 0: swap LBO/SBO in MN-major UMMA descriptors.
  * key 1: decode attention implementation (0 = mma.sync online softmax, default; 1 = SIMT exact two-pass;
  * 2 = mma.sync exact two-pass).  key 2: training attention forward (0 = tcgen05/TMEM when q,k,v are packed and
- * Nkv == 1, default; 1 = mma.sync everywhere).  key 3: mpx_glu_fused cluster size (0 = auto; 1, 2 or 4 = force). */
+ * Nkv == 1, default; 1 = mma.sync everywhere).  key 3: mpx_glu_fused cluster size (0 = auto; 1, 2 or 4 = force).
+ * key 4: mpx_value_head_fused cluster size, same values. */
 int mpx_debug_set(int key, int value);
 
 /* ---------------------------------------------------------------------------------------------- GAE
@@ -129,6 +130,16 @@ int mpx_glu_up(const mpx_glu_up_args* a, mpx_stream_t stream);
  * wt_ug64 is (2F,H) packed in 128-row tiles [64 up rows | 64 gate rows]; wt_d is Wdown^T (H,F).  H must be 128. */
 int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const mpx_bf16* wt_d, const mpx_bf16* residual,
                   mpx_bf16* out, int M, int H, int F, mpx_stream_t stream);
+
+/* Whole value path of a rollout step in one kernel (network.py:321,335-341 + values.py:40-45):
+ * value = sum softmax(f32(pv) @ Wvh + b_vh) * centers, pv = bf16(gelu(bf16(bf16(xf @ Wvm) + b_vm))),
+ * xf = RMSNorm(x; norm_scale, eps) when norm_scale != NULL, else xf = x (rows already normalised).
+ * wt_vm is Wvm^T (Vh,H) bf16, wt_vh_hilo the (128,Vh) bf16 [hi rows 0..63 | lo rows 64..127] split of Wvh^T
+ * (see mpx_prep_weights), b_vm (Vh) bf16, b_vh/centers (NL) f32.  value (M) f32; vlogits (M,NL) f32 is optional.
+ * H must be 128, Vh a multiple of 64, NL <= 64. */
+int mpx_value_head_fused(const mpx_bf16* x, const float* norm_scale, float eps, const mpx_bf16* wt_vm,
+                         const mpx_bf16* b_vm, const mpx_bf16* wt_vh_hilo, const float* b_vh, const float* centers,
+                         float* value, float* vlogits, int M, int H, int Vh, int NL, mpx_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------- decode attention
  * Decode branch of AttentionBlock.__call__, attention.py:136-150 (jax.nn.dot_product_attention with

@@ -29,6 +29,7 @@ extern int g_debug_swap_lbo_sbo;
 extern int g_attn_decode_impl;
 extern int g_attn_train_impl;
 extern int g_glu_fused_cluster;
+extern int g_value_fused_cluster;
 
 }  // namespace mpx
 
@@ -49,6 +50,10 @@ extern "C" int mpx_debug_set(int key, int value) {
   }
   if (key == 3) {
     mpx::g_glu_fused_cluster = value;
+    return MPX_OK;
+  }
+  if (key == 4) {
+    mpx::g_value_fused_cluster = value;
     return MPX_OK;
   }
   mpx::set_error("mpx_debug_set: unknown key %d", key);

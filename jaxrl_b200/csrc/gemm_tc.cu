@@ -104,24 +104,20 @@ __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, float (&f
 // every warp store touch 32 different 128-byte lines with 16 bytes each, and the L1 tag stage (one line per cycle)
 // becomes the bottleneck of epilogue-heavy GEMMs.  After the transpose, lane = (row r8, 16-byte piece j): one warp
 // store covers 8 rows x 64 contiguous bytes.  The XOR swizzle keeps both smem phases bank-conflict free.
-__device__ __forceinline__ void pack_row(const float (&f)[32], uint4 (&v)[4]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    v[i] = make_uint4(pack_bf16(f[8 * i + 0], f[8 * i + 1]), pack_bf16(f[8 * i + 2], f[8 * i + 3]),
-                      pack_bf16(f[8 * i + 4], f[8 * i + 5]), pack_bf16(f[8 * i + 6], f[8 * i + 7]));
-}
-// tile: global address of (first row of the warp, first column of the chunk); rows_valid in [0, 32].
-__device__ __forceinline__ void warp_store_tile(uint8_t* xp, __nv_bfloat16* tile, long long ld, int rows_valid,
-                                                const uint4 (&v)[4], int lane) {
+// tile: global address of (first row of the warp, first column of the chunk); rows_valid in [0, 32];
+// xp: shared-space address of this warp's 2 KB transpose buffer; v: this lane's row as 16 packed bf16 pairs.
+__device__ __forceinline__ void warp_store_tile(uint32_t xp, __nv_bfloat16* tile, long long ld, int rows_valid,
+                                                const uint32_t (&w)[16], int lane) {
   const int sw = (lane >> 1) & 3;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(xp + lane * 64 + ((j ^ sw) << 4)) = v[j];
+  for (int j = 0; j < 4; ++j)
+    sts_v4(xp + lane * 64 + ((j ^ sw) << 4), make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]));
   __syncwarp();
   const int r8 = lane >> 2, j = lane & 3;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int R = 8 * i + r8;
-    const uint4 x = *reinterpret_cast<const uint4*>(xp + R * 64 + ((j ^ ((R >> 1) & 3)) << 4));
+    const uint4 x = lds_v4(xp + R * 64 + ((j ^ ((R >> 1) & 3)) << 4));
     if (R < rows_valid) *reinterpret_cast<uint4*>(tile + (long long)R * ld + j * 8) = x;
   }
   __syncwarp();
@@ -136,18 +132,21 @@ __device__ __forceinline__ void warp_fetch_tile(const __nv_bfloat16* tile, long 
     c[i] = (R < rows_valid) ? *reinterpret_cast<const uint4*>(tile + (long long)R * ld + j * 8) : make_uint4(0, 0, 0, 0);
   }
 }
-// ... and its conversion to one row per lane
-__device__ __forceinline__ void warp_rows_from_fetched(uint8_t* xp, const uint4 (&c)[4], uint4 (&v)[4], int lane) {
+// ... and its conversion to one row per lane (16 packed bf16 pairs)
+__device__ __forceinline__ void warp_rows_from_fetched(uint32_t xp, const uint4 (&c)[4], uint32_t (&w)[16], int lane) {
   const int r8 = lane >> 2, j = lane & 3;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int R = 8 * i + r8;
-    *reinterpret_cast<uint4*>(xp + R * 64 + ((j ^ ((R >> 1) & 3)) << 4)) = c[i];
+    sts_v4(xp + R * 64 + ((j ^ ((R >> 1) & 3)) << 4), c[i]);
   }
   __syncwarp();
   const int sw = (lane >> 1) & 3;
 #pragma unroll
-  for (int jj = 0; jj < 4; ++jj) v[jj] = *reinterpret_cast<const uint4*>(xp + lane * 64 + ((jj ^ sw) << 4));
+  for (int jj = 0; jj < 4; ++jj) {
+    const uint4 v = lds_v4(xp + lane * 64 + ((jj ^ sw) << 4));
+    w[4 * jj] = v.x; w[4 * jj + 1] = v.y; w[4 * jj + 2] = v.z; w[4 * jj + 3] = v.w;
+  }
   __syncwarp();
 }
 
@@ -160,8 +159,9 @@ __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
 
 // Warp-cooperative: every lane of the warp must call (rows beyond M are masked inside).  row0 = first row of the warp,
 // rpre: this chunk's residual already fetched with warp_fetch_tile (when use_pre).
+// Values are carried as packed bf16 pairs between the rounding points (one F2FP per pair).
 __device__ __forceinline__ void epi_store(const GemmParams& p, int row0, int lane, int col0, const uint32_t (&acc)[32],
-                                          uint8_t* xp, const uint4 (&rpre)[4], bool use_pre) {
+                                          uint32_t xp, const uint4 (&rpre)[4], bool use_pre) {
   if (row0 >= p.M || col0 >= p.N) return;                 // warp-uniform
   const int row = row0 + lane;
   const int rows_valid = min(32, p.M - row0);
@@ -178,86 +178,95 @@ __device__ __forceinline__ void epi_store(const GemmParams& p, int row0, int lan
     }
   }
   if (!p.y) return;
-  float f[32];
+  uint32_t w[16];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) f[i] = bf16_round(__uint_as_float(acc[i]));
+  for (int i = 0; i < 16; ++i) w[i] = pack_bf16(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
   if (p.bias) {
     if (full && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
-      float b[32];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) unpack8(reinterpret_cast<const uint4*>(p.bias + col0)[i], b + 8 * i);
+      for (int i = 0; i < 4; ++i) {
+        const uint4 bv = reinterpret_cast<const uint4*>(p.bias + col0)[i];
+        const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = bf16_round(f[i] + b[i]);
+        for (int e = 0; e < 4; ++e)
+          w[4 * i + e] = pack_bf16(bf16_lo(w[4 * i + e]) + bf16_lo(bw[e]), bf16_hi(w[4 * i + e]) + bf16_hi(bw[e]));
+      }
     } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (col0 + i < p.N) f[i] = bf16_round(f[i] + __bfloat162float(p.bias[col0 + i]));
+      for (int i = 0; i < 16; ++i) {
+        const float b0 = (col0 + 2 * i < p.N) ? __bfloat162float(p.bias[col0 + 2 * i]) : 0.f;
+        const float b1 = (col0 + 2 * i + 1 < p.N) ? __bfloat162float(p.bias[col0 + 2 * i + 1]) : 0.f;
+        w[i] = pack_bf16(bf16_lo(w[i]) + b0, bf16_hi(w[i]) + b1);
+      }
     }
   }
   // 16-byte pieces everywhere: pitches are multiples of 8 elements and the bases 16-byte aligned
   const bool vec_y = full && ((p.ldy & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
   if (p.y_pre) {
     if (vec_y && ((reinterpret_cast<uintptr_t>(p.y_pre) & 15) == 0)) {
-      uint4 v[4];
-      pack_row(f, v);
-      warp_store_tile(xp, p.y_pre + (long long)row0 * p.ldy + col0, p.ldy, rows_valid, v, lane);
+      warp_store_tile(xp, p.y_pre + (long long)row0 * p.ldy + col0, p.ldy, rows_valid, w, lane);
     } else if (row < p.M) {
       __nv_bfloat16* dp = p.y_pre + (long long)row * p.ldy + col0;
-      for (int i = 0; i < 32 && col0 + i < p.N; ++i) dp[i] = __float2bfloat16_rn(f[i]);
+      for (int i = 0; i < 32 && col0 + i < p.N; ++i)
+        dp[i] = __ushort_as_bfloat16((unsigned short)((i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu)));
     }
   }
   if (p.act == 1) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = bf16_round(gelu_tanh(f[i]));
+    for (int i = 0; i < 16; ++i) w[i] = pack_bf16(gelu_tanh(bf16_lo(w[i])), gelu_tanh(bf16_hi(w[i])));
   }
   if (p.residual) {
     const bool vec_r = full && ((p.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
     if (use_pre || vec_r) {
-      uint4 c[4], v[4];
+      uint4 c[4];
+      uint32_t rw[16];
       if (use_pre) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) c[i] = rpre[i];
       } else {
         warp_fetch_tile(p.residual + (long long)row0 * p.ldr + col0, p.ldr, rows_valid, c, lane);
       }
-      warp_rows_from_fetched(xp, c, v, lane);
-      float rf[32];
+      warp_rows_from_fetched(xp, c, rw, lane);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) unpack8(v[i], rf + 8 * i);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = f[i] + rf[i];   // rounded to bf16 by the store
+      for (int i = 0; i < 16; ++i) w[i] = pack_bf16(bf16_lo(w[i]) + bf16_lo(rw[i]), bf16_hi(w[i]) + bf16_hi(rw[i]));
     } else if (row < p.M) {
       const __nv_bfloat16* r = p.residual + (long long)row * p.ldr + col0;
-      for (int i = 0; i < 32 && col0 + i < p.N; ++i) f[i] = f[i] + __bfloat162float(r[i]);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float r0 = (col0 + 2 * i < p.N) ? __bfloat162float(r[2 * i]) : 0.f;
+        const float r1 = (col0 + 2 * i + 1 < p.N) ? __bfloat162float(r[2 * i + 1]) : 0.f;
+        w[i] = pack_bf16(bf16_lo(w[i]) + r0, bf16_hi(w[i]) + r1);
+      }
     }
   }
   if (vec_y) {
-    uint4 v[4];
-    pack_row(f, v);
-    warp_store_tile(xp, p.y + (long long)row0 * p.ldy + col0, p.ldy, rows_valid, v, lane);
+    warp_store_tile(xp, p.y + (long long)row0 * p.ldy + col0, p.ldy, rows_valid, w, lane);
   } else if (row < p.M) {
     __nv_bfloat16* d = p.y + (long long)row * p.ldy + col0;
     if ((p.ldy & 7) == 0 && (p.N & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0)) {   // ragged last chunk
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        if (col0 + 8 * i < p.N)
-          reinterpret_cast<uint4*>(d)[i] = make_uint4(pack_bf16(f[8 * i], f[8 * i + 1]), pack_bf16(f[8 * i + 2], f[8 * i + 3]),
-                                                      pack_bf16(f[8 * i + 4], f[8 * i + 5]), pack_bf16(f[8 * i + 6], f[8 * i + 7]));
+        if (col0 + 8 * i < p.N) reinterpret_cast<uint4*>(d)[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
     } else {
-      for (int i = 0; i < 32 && col0 + i < p.N; ++i) d[i] = __float2bfloat16_rn(f[i]);
+      for (int i = 0; i < 32 && col0 + i < p.N; ++i)
+        d[i] = __ushort_as_bfloat16((unsigned short)((i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu)));
     }
   }
 }
 
 // One 32-column chunk == one attention head (head_dim 32).  Warp-cooperative like epi_store.
 __device__ __forceinline__ void epi_qkv(const GemmParams& p, int row0, int lane, int col0, const uint32_t (&acc)[32],
-                                        const float (&sn)[16], const float (&cs)[16], uint8_t* xp) {
+                                        const float (&sn)[16], const float (&cs)[16], uint32_t xp) {
   if (row0 >= p.M || col0 >= p.N) return;
   const int rows_valid = min(32, p.M - row0);
   const int head = col0 >> 5;
   float f[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) f[i] = bf16_round(__uint_as_float(acc[i]));   // projection output is bf16
+  for (int i = 0; i < 32; i += 2) {                        // projection output is bf16
+    f[i] = __uint_as_float(acc[i]);
+    f[i + 1] = __uint_as_float(acc[i + 1]);
+    bf16_round2(f[i], f[i + 1]);
+  }
   if (head < p.Nq + p.Nkv) {
     float o[32];
 #pragma unroll
@@ -288,38 +297,32 @@ __device__ __forceinline__ void epi_qkv(const GemmParams& p, int row0, int lane,
       ld = p.v_row_stride;
     }
   }
-  uint4 v[4];
-  pack_row(f, v);
+  uint32_t w[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
   if ((ld & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-    warp_store_tile(xp, dst, ld, rows_valid, v, lane);
+    warp_store_tile(xp, dst, ld, rows_valid, w, lane);
   } else if (lane < rows_valid) {
     store_bf16x32(dst + (long long)lane * ld, f);
   }
 }
 
 __device__ __forceinline__ void epi_glu(const GemmParams& p, int row0, int lane, int hcol0, const uint32_t (&u)[32],
-                                        const uint32_t (&g)[32], uint8_t* xp) {
+                                        const uint32_t (&g)[32], uint32_t xp) {
   if (row0 >= p.M || hcol0 >= p.F) return;
   const int rows_valid = min(32, p.M - row0);
-  float uf[32], gf[32], hf[32];
+  uint32_t uw[16], gw[16], hw[16];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    uf[i] = bf16_round(__uint_as_float(u[i]));
-    gf[i] = bf16_round(__uint_as_float(g[i]));
-    hf[i] = bf16_round(gelu_tanh(uf[i])) * gf[i];
+  for (int i = 0; i < 16; ++i) {
+    uw[i] = pack_bf16(__uint_as_float(u[2 * i]), __uint_as_float(u[2 * i + 1]));
+    gw[i] = pack_bf16(__uint_as_float(g[2 * i]), __uint_as_float(g[2 * i + 1]));
+    const uint32_t aw = pack_bf16(gelu_tanh(bf16_lo(uw[i])), gelu_tanh(bf16_hi(uw[i])));
+    hw[i] = pack_bf16(bf16_lo(aw) * bf16_lo(gw[i]), bf16_hi(aw) * bf16_hi(gw[i]));
   }
   const long long o = (long long)row0 * p.F + hcol0;
-  uint4 v[4];
-  pack_row(hf, v);
-  warp_store_tile(xp, p.h + o, p.F, rows_valid, v, lane);
-  if (p.u_save) {
-    pack_row(uf, v);
-    warp_store_tile(xp, p.u_save + o, p.F, rows_valid, v, lane);
-  }
-  if (p.g_save) {
-    pack_row(gf, v);
-    warp_store_tile(xp, p.g_save + o, p.F, rows_valid, v, lane);
-  }
+  warp_store_tile(xp, p.h + o, p.F, rows_valid, hw, lane);
+  if (p.u_save) warp_store_tile(xp, p.u_save + o, p.F, rows_valid, uw, lane);
+  if (p.g_save) warp_store_tile(xp, p.g_save + o, p.F, rows_valid, gw, lane);
 }
 
 // fp32-weight Linear emulated with a bf16 hi/lo split of the weight: out[j] = acc[j] + acc[64 + j] + bias[j].
@@ -435,7 +438,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;        // which of the two warps of this quarter: takes chunks with (c/32)&1 == half
     const int row_in_tile = quarter * 32 + lane;
-    uint8_t* xp = smem + L::XPOSE_OFFSET + (warp - 2) * 2048;
+    const uint32_t xp = smem_u32(smem + L::XPOSE_OFFSET + (warp - 2) * 2048);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;

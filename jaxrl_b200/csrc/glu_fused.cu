@@ -215,9 +215,10 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         uint32_t hw[16];                                       // 32 bf16 = this warp's half of the row's h chunk
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float ua = bf16_round(__uint_as_float(u[2 * i])), ub = bf16_round(__uint_as_float(u[2 * i + 1]));
-          const float ga = bf16_round(__uint_as_float(g[2 * i])), gb = bf16_round(__uint_as_float(g[2 * i + 1]));
-          hw[i] = pack_bf16(bf16_round(gelu_tanh(ua)) * ga, bf16_round(gelu_tanh(ub)) * gb);
+          const uint32_t uw = pack_bf16(__uint_as_float(u[2 * i]), __uint_as_float(u[2 * i + 1]));
+          const uint32_t gw = pack_bf16(__uint_as_float(g[2 * i]), __uint_as_float(g[2 * i + 1]));
+          const uint32_t aw = pack_bf16(gelu_tanh(bf16_lo(uw)), gelu_tanh(bf16_hi(uw)));
+          hw[i] = pack_bf16(bf16_lo(aw) * bf16_lo(gw), bf16_hi(aw) * bf16_hi(gw));
         }
         mbar_wait(&h_empty[b], h_ph[b] ^ 1);                   // MMA2 of chunk c-2 no longer reads this buffer
         h_ph[b] ^= 1;

@@ -1,0 +1,453 @@
+// Fused value path of the rollout step (TransformerActorCritic.__call__, mapox_trainer/model/network.py:321,335-341,
+// and HlGaussValue.get_value, values.py:40-45):
+//     xf      = RMSNorm(x)                              (optional: skipped when the caller passes normalised rows)
+//     pv      = bf16(gelu(bf16(bf16(xf @ Wvm) + b_vm)))  (value MLP, H -> Vh)
+//     vlogits = f32(pv) @ Wvh + b_vh                     (fp32 Linear, Vh -> NL; Wvh carried as a bf16 hi/lo pair)
+//     value   = sum softmax(vlogits) * centers
+// in ONE kernel: the (M, Vh) hidden activation and the logits never leave the SM.  Same skeleton as glu_fused.cu:
+// two chained tcgen05 GEMMs per 64-wide chunk of Vh (MMA1 -> TMEM -> bias+gelu in registers -> bf16 smem tile ->
+// MMA2 accumulating [hi | lo] logits in TMEM), and a thread-block cluster splits the Vh chunks of one 128-row tile
+// over CL CTAs so that small rollout batches still fill the machine; the CL fp32 partials are summed over
+// distributed shared memory, CTA k finishing rows [k*128/CL, (k+1)*128/CL) of the tile (softmax needs whole rows).
+//
+// Roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, warps 2-9 activation + epilogue
+// (two warps per TMEM lane quarter; thread = row, each warp half of the chunk's columns).  H must be 128, Vh % 64 == 0,
+// NL <= 64.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.h"
+
+namespace mpx {
+
+constexpr int VF_STAGES = 4;
+constexpr int VF_STAGE_BYTES = 16384;
+constexpr int VF_THREADS = 320;
+constexpr int VF_EPI_WARPS = 8;
+
+int g_value_fused_cluster = 0;   // mpx_debug_set(4, v): 0 = auto, 1/2/4 = force that cluster size (tests)
+
+struct ValueFusedParams {
+  int M, Vh, NL;
+  const float* norm_scale;        // (128) or null
+  float eps;
+  const __nv_bfloat16* b_vm;      // (Vh)
+  const float* b_vh;              // (NL)
+  const float* centers;           // (NL)
+  float* value;                   // (M)
+  float* vlogits;                 // (M, NL) or null
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(VF_THREADS, 1)
+value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap tm_x,
+                   const __grid_constant__ CUtensorMap tm_wvm, const __grid_constant__ CUtensorMap tm_whl) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sX = smem;                         // 2 x 16 KB: x tile, K blocks 0 and 1
+  uint8_t* sH = smem + 32768;                 // 2 x 16 KB: pv chunk double buffer
+  uint8_t* sW = smem + 65536;                 // VF_STAGES x 16 KB weight ring
+  uint8_t* sP = sW + VF_STAGES * VF_STAGE_BYTES;   // 32 KB: fp32 partial logits [16 float4 columns][128 rows]
+  uint8_t* sR = sP + 32768;                   // 8 KB: summed logits of one 32-row group [16 float4 columns][32 rows]
+  float* sSq = reinterpret_cast<float*>(sR + 8192);   // 2 x 128 partial sums of squares (RMSNorm prologue)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sR + 8192 + 1024);
+  uint64_t* w_full = bars;                    // [VF_STAGES]
+  uint64_t* w_empty = bars + VF_STAGES;       // [VF_STAGES]
+  uint64_t* x_full = bars + 2 * VF_STAGES;
+  uint64_t* x_empty = x_full + 1;
+  uint64_t* xn_ready = x_full + 2;
+  uint64_t* z_full = x_full + 3;              // [2]
+  uint64_t* z_empty = x_full + 5;             // [2]
+  uint64_t* h_full = x_full + 7;              // [2]
+  uint64_t* h_empty = x_full + 9;             // [2]
+  uint64_t* d_full = x_full + 11;
+  uint64_t* d_empty = x_full + 12;
+  uint64_t* part_full = x_full + 13;
+  uint64_t* part_empty = x_full + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ncta = (int)cluster_nctarank(), krank = (int)cluster_ctarank();
+  const int nchunks = p.Vh / 64 / ncta;
+  const int chunk0 = krank * nchunks;
+  const int m_tiles = (p.M + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_wvm);
+    tma_prefetch_desc(&tm_whl);
+    for (int s = 0; s < VF_STAGES; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    mbar_init(x_full, 1);
+    mbar_init(x_empty, 1);
+    mbar_init(xn_ready, VF_EPI_WARPS);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&z_full[b], 1);
+      mbar_init(&z_empty[b], VF_EPI_WARPS);
+      mbar_init(&h_full[b], VF_EPI_WARPS);
+      mbar_init(&h_empty[b], 1);
+    }
+    mbar_init(d_full, 1);
+    mbar_init(d_empty, VF_EPI_WARPS);
+    mbar_init(part_full, VF_EPI_WARPS * ncta);
+    mbar_init(part_empty, VF_EPI_WARPS * ncta);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (ncta > 1) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tZ[2] = {tmem_base, tmem_base + 64};
+  const uint32_t tD = tmem_base + 128;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t wphase = 0, xphase = 0;
+      auto load_vm = [&](int chunk) {           // Wvm^T rows [chunk*64, +64), both K blocks: 2 x 8 KB
+        mbar_wait(&w_empty[stage], wphase ^ 1);
+        mbar_arrive_expect_tx(&w_full[stage], VF_STAGE_BYTES);
+        tma_load_2d(&tm_wvm, &w_full[stage], sW + stage * VF_STAGE_BYTES, 0, chunk * 64);
+        tma_load_2d(&tm_wvm, &w_full[stage], sW + stage * VF_STAGE_BYTES + 8192, 64, chunk * 64);
+        if (++stage == VF_STAGES) { stage = 0; wphase ^= 1; }
+      };
+      auto load_hl = [&](int chunk) {           // [hi | lo] rows 0..127, Vh columns [chunk*64, +64): 16 KB
+        mbar_wait(&w_empty[stage], wphase ^ 1);
+        mbar_arrive_expect_tx(&w_full[stage], VF_STAGE_BYTES);
+        tma_load_2d(&tm_whl, &w_full[stage], sW + stage * VF_STAGE_BYTES, chunk * 64, 0);
+        if (++stage == VF_STAGES) { stage = 0; wphase ^= 1; }
+      };
+      for (int tile = blockIdx.y; tile < m_tiles; tile += gridDim.y) {
+        mbar_wait(x_empty, xphase ^ 1);
+        mbar_arrive_expect_tx(x_full, 32768);
+        tma_load_2d(&tm_x, x_full, sX, 0, tile * 128);
+        tma_load_2d(&tm_x, x_full, sX + 16384, 64, tile * 128);
+        xphase ^= 1;
+        load_vm(chunk0);
+        for (int c = 0; c < nchunks; ++c) {
+          if (c + 1 < nchunks) load_vm(chunk0 + c + 1);
+          load_hl(chunk0 + c);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = umma_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc2 = umma_idesc_bf16(128, 128, 0, 0);
+      int stage = 0;
+      uint32_t wphase = 0, xnphase = 0, dphase = 0;
+      uint32_t z_ph[2] = {0, 0}, h_ph[2] = {0, 0};
+      auto mma1 = [&](int c, bool last) {     // z_c (128 x 64) = xf . Wvm_c^T
+        const int b = c & 1;
+        mbar_wait(&z_empty[b], z_ph[b] ^ 1);
+        mbar_wait(&w_full[stage], wphase);
+        tc_fence_after();
+        const uint32_t sb = smem_u32(sW + stage * VF_STAGE_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint32_t sa = smem_u32(sX + kb * 16384);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tZ[b], umma_smem_desc_sw128(sa + 32 * k, 16, 1024),
+                      umma_smem_desc_sw128(sb + kb * 8192 + 32 * k, 16, 1024), idesc1, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&w_empty[stage]);
+        if (++stage == VF_STAGES) { stage = 0; wphase ^= 1; }
+        umma_commit(&z_full[b]);
+        if (last) umma_commit(x_empty);
+        z_ph[b] ^= 1;
+      };
+      auto mma2 = [&](int c, bool last) {     // [hi | lo] += pv_c . Whl_c^T
+        const int b = c & 1;
+        mbar_wait(&h_full[b], h_ph[b]);
+        h_ph[b] ^= 1;
+        mbar_wait(&w_full[stage], wphase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(sH + b * 16384);
+        const uint32_t sb = smem_u32(sW + stage * VF_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tD, umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024), idesc2,
+                    (c | k) != 0 ? 1u : 0u);
+        umma_commit(&w_empty[stage]);
+        if (++stage == VF_STAGES) { stage = 0; wphase ^= 1; }
+        umma_commit(&h_empty[b]);
+        if (last) umma_commit(d_full);
+      };
+      for (int tile = blockIdx.y; tile < m_tiles; tile += gridDim.y) {
+        mbar_wait(xn_ready, xnphase);          // x tile landed and (optionally) normalised in place
+        xnphase ^= 1;
+        mbar_wait(d_empty, dphase ^ 1);
+        dphase ^= 1;
+        tc_fence_after();
+        mma1(0, nchunks == 1);
+        for (int c = 0; c < nchunks; ++c) {
+          if (c + 1 < nchunks) mma1(c + 1, c + 2 == nchunks);
+          mma2(c, c + 1 == nchunks);
+        }
+      }
+    }
+  } else {
+    // ================================ activation / epilogue warps ================================
+    const int ew = warp - 2;                                 // 0..7
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    const int r = quarter * 32 + lane;                       // row within the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    uint32_t z_ph[2] = {0, 0}, h_ph[2] = {0, 0}, dphase = 0, pf_phase = 0, pe_phase = 0, xphase = 0;
+    for (int tile = blockIdx.y; tile < m_tiles; tile += gridDim.y) {
+      // ---- RMSNorm prologue on the x tile, in place in the swizzled smem layout (this warp: K block `half`)
+      mbar_wait(x_full, xphase);
+      xphase ^= 1;
+      if (p.norm_scale) {
+        uint8_t* xrow = sX + half * 16384 + r * 128;
+        uint4 xv[8];
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          xv[c] = *reinterpret_cast<const uint4*>(xrow + ((c ^ (r & 7)) << 4));
+          const uint32_t w4[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = bf16_lo(w4[e]), b = bf16_hi(w4[e]);
+            ss += a * a + b * b;
+          }
+        }
+        sSq[half * 128 + r] = ss;
+        named_bar_sync(1, VF_EPI_WARPS * 32);
+        const float inv = rsqrtf((sSq[r] + sSq[128 + r]) * (1.0f / 128.0f) + p.eps);
+        const float4* sc4 = reinterpret_cast<const float4*>(p.norm_scale + half * 64);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1];
+          uint4 o;
+          o.x = pack_bf16(bf16_lo(xv[c].x) * inv * s0.x, bf16_hi(xv[c].x) * inv * s0.y);
+          o.y = pack_bf16(bf16_lo(xv[c].y) * inv * s0.z, bf16_hi(xv[c].y) * inv * s0.w);
+          o.z = pack_bf16(bf16_lo(xv[c].z) * inv * s1.x, bf16_hi(xv[c].z) * inv * s1.y);
+          o.w = pack_bf16(bf16_lo(xv[c].w) * inv * s1.z, bf16_hi(xv[c].w) * inv * s1.w);
+          *reinterpret_cast<uint4*>(xrow + ((c ^ (r & 7)) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, VF_EPI_WARPS * 32);                 // sSq may be rewritten by the next tile
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(xn_ready);
+
+      // ---- value MLP chunks: bias + gelu on the MMA1 accumulator, bf16 tile for MMA2
+      for (int c = 0; c < nchunks; ++c) {
+        const int b = c & 1;
+        mbar_wait(&z_full[b], z_ph[b]);
+        z_ph[b] ^= 1;
+        tc_fence_after();
+        uint32_t z[32];
+        tmem_ld_32x32(tZ[b] + lane_off + 32 * half, z);
+        const uint4* b4 = reinterpret_cast<const uint4*>(p.b_vm + (chunk0 + c) * 64 + 32 * half);
+        uint4 bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bv[i] = b4[i];
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&z_empty[b]);
+        uint32_t hw[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t bw[4] = {bv[i].x, bv[i].y, bv[i].z, bv[i].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t zw = pack_bf16(__uint_as_float(z[8 * i + 2 * e]), __uint_as_float(z[8 * i + 2 * e + 1]));
+            const uint32_t zb = pack_bf16(bf16_lo(zw) + bf16_lo(bw[e]), bf16_hi(zw) + bf16_hi(bw[e]));
+            hw[4 * i + e] = pack_bf16(gelu_tanh(bf16_lo(zb)), gelu_tanh(bf16_hi(zb)));
+          }
+        }
+        mbar_wait(&h_empty[b], h_ph[b] ^ 1);
+        h_ph[b] ^= 1;
+        uint8_t* hrow = sH + b * 16384 + r * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int pc = 4 * half + i;
+          *reinterpret_cast<uint4*>(hrow + ((pc ^ (r & 7)) << 4)) =
+              make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&h_full[b]);
+      }
+
+      // ---- logits: stage hi + lo partial (fp32) for the cluster reduction
+      mbar_wait(d_full, dphase);
+      dphase ^= 1;
+      tc_fence_after();
+      mbar_wait_cluster(part_empty, pe_phase ^ 1);
+      pe_phase ^= 1;
+      float4* stage4 = reinterpret_cast<float4*>(sP);
+      {
+        uint32_t hi[32], lo[32];
+        tmem_ld_32x32(tD + lane_off + 32 * half, hi);
+        tmem_ld_32x32(tD + lane_off + 64 + 32 * half, lo);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          stage4[(8 * half + i) * 128 + r] =
+              make_float4(__uint_as_float(hi[4 * i]) + __uint_as_float(lo[4 * i]),
+                          __uint_as_float(hi[4 * i + 1]) + __uint_as_float(lo[4 * i + 1]),
+                          __uint_as_float(hi[4 * i + 2]) + __uint_as_float(lo[4 * i + 2]),
+                          __uint_as_float(hi[4 * i + 3]) + __uint_as_float(lo[4 * i + 3]));
+      }
+      tc_fence_before();
+      fence_acq_rel_cluster();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(d_empty);
+        const uint32_t pf = smem_u32(part_full);
+        for (int j = 0; j < ncta; ++j) mbar_arrive_cluster(mapa_u32(pf, j));
+      }
+      mbar_wait_cluster(part_full, pf_phase);
+      pf_phase ^= 1;
+      // ---- this CTA finishes row groups [krank*4/ncta, (krank+1)*4/ncta) of the tile (32 rows each)
+      const uint32_t sp = smem_u32(sP);
+      float4* rbuf = reinterpret_cast<float4*>(sR);
+      const int groups = 4 / ncta;
+      for (int gi = 0; gi < groups; ++gi) {
+        const int rg = krank * groups + gi;
+        // warp ew sums float4 columns 2*ew and 2*ew+1 over the cluster, lane = row of the group
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c4 = 2 * ew + q;
+          float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+          const uint32_t off = (uint32_t)(c4 * 128 + rg * 32 + lane) * 16u;
+          for (int j = 0; j < ncta; ++j) {
+            const float4 a = ld_dsmem_f4(mapa_u32(sp, j) + off);
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+          }
+          rbuf[c4 * 32 + lane] = s;
+        }
+        named_bar_sync(1, VF_EPI_WARPS * 32);
+        if (ew == (gi & 7)) {
+          const long long row = (long long)tile * 128 + rg * 32 + lane;
+          float m = -INFINITY;
+          float lg[64];
+#pragma unroll
+          for (int c4 = 0; c4 < 16; ++c4) {
+            const float4 v = rbuf[c4 * 32 + lane];
+            lg[4 * c4] = v.x; lg[4 * c4 + 1] = v.y; lg[4 * c4 + 2] = v.z; lg[4 * c4 + 3] = v.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            if (j < p.NL) {
+              lg[j] += p.b_vh[j];
+              m = fmaxf(m, lg[j]);
+            }
+          }
+          float s = 0.f, sc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            if (j < p.NL) {
+              const float e = expf(lg[j] - m);
+              s += e;
+              sc += e * p.centers[j];
+            }
+          }
+          if (row < p.M) {
+            p.value[row] = sc / s;
+            if (p.vlogits) {
+#pragma unroll
+              for (int j = 0; j < 64; ++j)
+                if (j < p.NL) p.vlogits[row * p.NL + j] = lg[j];
+            }
+          }
+        }
+        named_bar_sync(1, VF_EPI_WARPS * 32);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t pe = smem_u32(part_empty);
+        for (int j = 0; j < ncta; ++j) mbar_arrive_cluster(mapa_u32(pe, j));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (ncta > 1) cluster_sync_all();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace mpx
+
+using namespace mpx;
+
+extern "C" int mpx_value_head_fused(const mpx_bf16* x, const float* norm_scale, float eps, const mpx_bf16* wt_vm,
+                                    const mpx_bf16* b_vm, const mpx_bf16* wt_vh_hilo, const float* b_vh,
+                                    const float* centers, float* value, float* vlogits, int M, int H, int Vh, int NL,
+                                    mpx_stream_t stream) {
+  MPX_REQUIRE(x && wt_vm && b_vm && wt_vh_hilo && b_vh && centers && value && M > 0, "mpx_value_head_fused: bad arguments");
+  MPX_REQUIRE(H == 128, "mpx_value_head_fused: hidden_features=%d unsupported (128 only; use mpx_linear + mpx_linear_f32w)", H);
+  MPX_REQUIRE(Vh > 0 && Vh % 64 == 0, "mpx_value_head_fused: value_hidden_dim=%d must be a positive multiple of 64", Vh);
+  MPX_REQUIRE(NL > 0 && NL <= 64, "mpx_value_head_fused: n_logits=%d not in [1,64]", NL);
+  MPX_REQUIRE((reinterpret_cast<uintptr_t>(b_vm) & 15) == 0 && (!norm_scale || (reinterpret_cast<uintptr_t>(norm_scale) & 15) == 0),
+              "mpx_value_head_fused: b_vm / norm_scale must be 16-byte aligned");
+  CUtensorMap tm_x, tm_wvm, tm_whl;
+  int rc = make_tmap_bf16_2d(&tm_x, x, M, H, H, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tm_wvm, wt_vm, Vh, H, H, 64, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tm_whl, wt_vh_hilo, 128, Vh, Vh, 64, 128);
+  if (rc) return rc;
+  const int smem = 1024 + 65536 + VF_STAGES * VF_STAGE_BYTES + 32768 + 8192 + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(value_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(value_fused): %s", cudaGetErrorString(e));
+      return MPX_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  ValueFusedParams p;
+  p.M = M; p.Vh = Vh; p.NL = NL;
+  p.norm_scale = norm_scale;
+  p.eps = eps;
+  p.b_vm = reinterpret_cast<const __nv_bfloat16*>(b_vm);
+  p.b_vh = b_vh;
+  p.centers = centers;
+  p.value = value;
+  p.vlogits = vlogits;
+  const int tiles = ceil_div(M, 128);
+  const int nchunks = Vh / 64;
+  int cl = 1;
+  if (nchunks % 4 == 0 && tiles * 4 <= num_sms()) cl = 4;
+  else if (nchunks % 2 == 0 && tiles * 2 <= num_sms()) cl = 2;
+  if (g_value_fused_cluster == 1 || ((g_value_fused_cluster == 2 || g_value_fused_cluster == 4) && nchunks % g_value_fused_cluster == 0))
+    cl = g_value_fused_cluster;
+  int gy = num_sms() / cl;
+  if (gy > tiles) gy = tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cl, gy, 1);
+  cfg.blockDim = dim3(VF_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, value_fused_kernel, p, tm_x, tm_wvm, tm_whl);
+  if (le != cudaSuccess) {
+    set_error("cudaLaunchKernelEx(value_fused, cluster %d): %s", cl, cudaGetErrorString(le));
+    return MPX_ERR_CUDA;
+  }
+  return check_launch("value_fused_kernel");
+}

@@ -49,6 +49,8 @@ class PolicyEngine:
         self.QKV = self.QD + 2 * self.KD
         self.L = cfg.num_layers
         self.fused_glu = (H == 128 and cfg.ffn_size % 64 == 0)     # decode path: one kernel per GLU block
+        self.fused_value = (H == 128 and cfg.value_hidden_dim is not None and cfg.value_hidden_dim % 64 == 0
+                            and cfg.value_n_logits <= 64)           # decode path: one kernel for the value path
         self.timescale = (torch.tensor(cfg.rope_max_wavelength, dtype=F32)
                           ** (2.0 * torch.arange(0, D // 2, dtype=F32) / D)).to(self.dev)
         sup = torch.linspace(cfg.value_min, cfg.value_max, cfg.value_n_logits + 1, dtype=F32)
@@ -283,10 +285,11 @@ class PolicyEngine:
             dy = ws.dca[c.j - 1]
 
     # ------------------------------------------------------------------------------------------ decode step
-    def decode_step(self, ws, obs, reward, last_action, pos, action_mask=None, task_ids=None):
+    def decode_step(self, ws, obs, reward, last_action, pos, action_mask=None, task_ids=None, value_out=None):
         """One rollout step for B agents: TransformerActorCritic.__call__ with carry (network.py:300-343) on
         add_seq_dim(timestep).  pos is the (B,) int32 device array ts.time.  Leaves action logits in ws.logits
-        and the HL-Gauss logits in ws.vlogits; the KV caches in ws are updated in place."""
+        and the HL-Gauss logits in ws.vlogits; the KV caches in ws are updated in place.  value_out (B,) f32, when
+        given, receives HlGaussValue.get_value of those logits (values.py:43-45; fused with the value path)."""
         p, w, B = self.p, self.w, ws.B
         S = self.cfg.max_seq_length
         x = self._embed_fwd(ws, B, obs, reward, last_action, task_ids, ws.xa, train=False)
@@ -307,7 +310,15 @@ class PolicyEngine:
                 ops.glu_up(ws.xn, w[pre + "wt_ug"], self.F, h=ws.h)
                 ops.linear(ws.h, w[pre + "wt_d"], residual=x, out=other)
             x, other = other, x
+        if value_out is not None and self.fused_value:
+            ops.rmsnorm_fwd(x, p["output_norm.scale"], out=ws.xf)
+            ops.policy_logits(ws.xf, p["action_embedder.embedding_table"], action_mask, out=ws.logits)
+            ops.value_head_fused(ws.xf, w["wt_vm"], w["b_vm"], w["wt_vh_hilo"], p["value_head.dense.bias"], self.centers,
+                                 value_out, vlogits=ws.vlogits)
+            return ws.logits, ws.vlogits
         self._heads_fwd(x, action_mask, ws.xf, ws.logits, ws.pv, None, ws.vlogits)
+        if value_out is not None:
+            ops.hlgauss_value(ws.vlogits, self.centers, out=value_out)
         return ws.logits, ws.vlogits
 
     def _heads_fwd(self, x, action_mask, xf, logits, pv, zv, vlogits):

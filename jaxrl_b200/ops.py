@@ -195,6 +195,21 @@ def glu_fused(x, wt_ug64, wt_d, residual, out, F: int):
     return out
 
 
+def value_head_fused(x, wt_vm, b_vm, wt_vh_hilo, b_vh, centers, value, vlogits=None, norm_scale=None,
+                     eps: float = 1e-6):
+    """value = HL-Gauss expectation of the value head on gelu(value_mlp(x)) in one kernel (H = 128)."""
+    _req(x, BF16, "x"); _req(wt_vm, BF16, "wt_vm"); _req(b_vm, BF16, "b_vm"); _req(wt_vh_hilo, BF16, "wt_vh_hilo")
+    _req(b_vh, F32, "b_vh"); _req(centers, F32, "centers"); _req(value, F32, "value")
+    H = x.shape[-1]
+    M = x.numel() // H
+    Vh = wt_vm.shape[0]
+    NL = centers.numel()
+    check(lib.mpx_value_head_fused(ptr(x), ptr(norm_scale), eps, ptr(wt_vm), ptr(b_vm), ptr(wt_vh_hilo), ptr(b_vh),
+                                   ptr(centers), ptr(value), ptr(vlogits), M, H, Vh, NL, stream()),
+          "mpx_value_head_fused")
+    return value
+
+
 def pack_glu_weight64(w_up: torch.Tensor, w_gate: torch.Tensor) -> torch.Tensor:
     """(K,F) flax kernels -> (2F,K) bf16, 128-row tiles [64 up rows | 64 gate rows] (see mpx_glu_fused)."""
     K, F = w_up.shape

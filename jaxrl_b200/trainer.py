@@ -119,11 +119,6 @@ class PPOTrainer:
         self.perm_gen = torch.Generator(device=dev).manual_seed(self.seed + 17 + self.rank)
 
     # ------------------------------------------------------------------------------------------ rollout (evaluate)
-    def _decode(self, t: int, obs, reward, last_action, pos, value_out):
-        eng, r = self.engine, self.r
-        logits, vlogits = eng.decode_step(self.dws, obs, reward, last_action, pos)
-        return logits, vlogits
-
     def _rollout_body(self):
         eng, r, env, T = self.engine, self.r, self.env, self.T
         for t in range(T):
@@ -133,10 +128,9 @@ class PPOTrainer:
                 obs_t, rew_t = r.obs_stage, r.rew_stage
             else:
                 obs_t, rew_t = env.obs[t], env.reward[t]
-            logits, vlogits = eng.decode_step(self.dws, obs_t, rew_t, r.actions_ext[t], r.pos[t])
+            logits, _ = eng.decode_step(self.dws, obs_t, rew_t, r.actions_ext[t], r.pos[t], value_out=r.values[t])
             ops.gumbel_noise(r.gumbel, self.seed, t, self.noise_off)
             ops.policy_sample(logits, r.gumbel, action=r.actions_ext[t + 1], log_prob=r.log_prob[t])
-            ops.hlgauss_value(vlogits, eng.centers, out=r.values[t])
         # bootstrap (train.py:142-148): value of the INITIAL timestep with the INITIAL (empty) carry.  Position 0
         # reads and writes ring slot 0 only, so re-running step 0 on the used caches is equivalent.
         if self.e2e:
@@ -145,8 +139,7 @@ class PPOTrainer:
             obs0, rew0 = r.obs_stage, r.rew_stage
         else:
             obs0, rew0 = env.obs[0], env.reward[0]
-        _, vlogits = eng.decode_step(self.dws, obs0, rew0, r.actions_ext[0], r.pos[0])
-        ops.hlgauss_value(vlogits, eng.centers, out=r.values[T])
+        eng.decode_step(self.dws, obs0, rew0, r.actions_ext[0], r.pos[0], value_out=r.values[T])
 
     def _postprocess_body(self):
         """Layout change (+ row permutation, rollout.py:169-181) and calculate_advantage (rollout.py:128-167)."""

@@ -128,11 +128,11 @@ def oracle_rope_attention():
 def oracle_model():
     """Tiny trunk forward (network.py:300-343): logits, value logits and value on a seeded 2-layer model."""
     from jaxrl_b200.params import ParamStore
-    cfg = ModelConfig(num_layers=2, max_seq_length=16, action_dim=6)
+    cfg = ModelConfig(num_layers=2, max_seq_length=64, action_dim=6)
     store = ParamStore(cfg, "cpu", seed=3, bias_noise=0.05)
     p = store.oracle_dict()
     g = torch.Generator().manual_seed(19)
-    B, T = 3, 10
+    B, T = 2, 64      # the training attention kernels take windows that are multiples of 64
     vw, vh, K = cfg.obs_shape
     obs = torch.stack([torch.randint(0, n, (B, T, vw, vh), generator=g) for n in cfg.obs_max_value], dim=-1).to(torch.uint8)
     reward = torch.randn(B, T, generator=g) * 0.1

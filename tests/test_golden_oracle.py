@@ -78,7 +78,7 @@ def test_oracle_model_frozen():
     from jaxrl_b200.config import ModelConfig
     from jaxrl_b200.params import ParamStore
     z = load("oracle_model.npz")
-    cfg = ModelConfig(num_layers=2, max_seq_length=16, action_dim=6)
+    cfg = ModelConfig(num_layers=2, max_seq_length=64, action_dim=6)
     p = ParamStore(cfg, "cpu", seed=int(z["seed"][0]), bias_noise=float(z["bias_noise"][0])).oracle_dict()
     B, T = z["reward"].shape
     ts = O.TimeStep(obs=torch.from_numpy(z["obs"]), time=torch.arange(T, dtype=torch.int32)[None],

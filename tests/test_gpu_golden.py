@@ -117,7 +117,7 @@ def test_model_forward_fixture(ops):
     from jaxrl_b200.config import ModelConfig
     from jaxrl_b200.engine import PolicyEngine
     z = load("oracle_model.npz")
-    cfg = ModelConfig(num_layers=2, max_seq_length=16, action_dim=6)
+    cfg = ModelConfig(num_layers=2, max_seq_length=64, action_dim=6)
     eng = PolicyEngine(cfg, DEV, seed=int(z["seed"][0]), bias_noise=float(z["bias_noise"][0]))
     B, T = z["reward"].shape
     ws = eng.alloc_train(B, T)

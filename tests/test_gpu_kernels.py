@@ -426,3 +426,44 @@ def test_glu_fused(ops, M, F, cluster):
         lib.mpx_debug_set(3, 0)
     assert_close_bf16(out, ref, f"glu_fused M={M} F={F} cl={cluster}", rtol=1e-2, abs_floor_frac=1e-2, allow_frac=1e-3,
                       max_err_frac=0.1)
+
+
+@pytest.mark.parametrize("M,Vh,NL,cluster,norm", [(77, 768, 51, 0, False), (4096, 768, 51, 0, True), (4096, 768, 51, 1, False),
+                                                  (4096, 768, 51, 2, True), (1000, 256, 51, 4, True), (20000, 768, 51, 0, False),
+                                                  (20000, 768, 51, 4, True), (300, 192, 10, 0, True), (129, 64, 64, 0, False)])
+def test_value_head_fused(ops, M, Vh, NL, cluster, norm):
+    """Fused value path (RMSNorm -> value MLP + gelu -> fp32 value head -> HL-Gauss expectation) vs the oracle."""
+    from jaxrl_b200._lib import lib
+    gen = g(M + Vh + NL + cluster)
+    H = 128
+    x = torch.randn(M, H, generator=gen).to(BF16)
+    scale = 1.0 + 0.1 * torch.randn(H, generator=gen)
+    wvm = torch.randn(H, Vh, generator=gen) / math.sqrt(H)
+    bvm = torch.randn(Vh, generator=gen) * 0.1
+    wvh = torch.randn(Vh, NL, generator=gen) / math.sqrt(Vh)
+    bvh = torch.randn(NL, generator=gen) * 0.1
+    _, centers = O.calculate_supports(-10.0, 10.0, NL)
+    xf = O.rms_norm(x, scale) if norm else x
+    pv = O.gelu_tanh(O.linear(xf, wvm, bvm))
+    vl_ref = O.linear(pv, wvh, bvh, dtype=None)
+    val_ref = O.hlgauss_get_value(vl_ref, centers)
+    wt_vm = wvm.t().contiguous().to(BF16)
+    hi = wvh.t().contiguous().to(BF16)
+    lo = (wvh.t().contiguous() - hi.float()).to(BF16)
+    hilo = torch.zeros(128, Vh, dtype=BF16)
+    hilo[:NL] = hi
+    hilo[64:64 + NL] = lo
+    value = torch.empty(M, dtype=torch.float32, device=DEV)
+    vlogits = torch.empty(M, NL, dtype=torch.float32, device=DEV)
+    lib.mpx_debug_set(4, cluster)
+    try:
+        ops.value_head_fused(x.to(DEV), wt_vm.to(DEV), bvm.to(BF16).to(DEV), hilo.to(DEV), bvh.to(DEV), centers.to(DEV),
+                             value, vlogits=vlogits, norm_scale=scale.to(DEV) if norm else None)
+        torch.cuda.synchronize()
+    finally:
+        lib.mpx_debug_set(4, 0)
+    assert_close_bf16(vlogits, vl_ref, f"value_head_fused vlogits M={M} Vh={Vh} cl={cluster} norm={norm}", rtol=1e-2,
+                      abs_floor_frac=2e-2, allow_frac=2e-3, max_err_frac=0.1)
+    torch.testing.assert_close(value.cpu(), val_ref, rtol=1e-2, atol=3e-2)
+    # internal consistency: value == get_value(vlogits) to fp32 accuracy
+    torch.testing.assert_close(value.cpu(), O.hlgauss_get_value(vlogits.cpu(), centers), rtol=1e-5, atol=1e-5)

@@ -61,10 +61,12 @@ def test_decode_rollout_matches_oracle(engine):
     agree = 0
     for t in range(T):
         pos = torch.full((B,), t, dtype=torch.int32, device=DEV)
+        val = torch.empty(B, dtype=torch.float32, device=DEV)
         logits, vlogits = engine.decode_step(ws, obs_d[t].contiguous(), rew_d[t].contiguous(), la, pos,
-                                             action_mask=mask_d[t].contiguous())
+                                             action_mask=mask_d[t].contiguous(), value_out=val)   # fused value path
         act, lp = ops.policy_sample(logits, gum_d[t].contiguous())
-        val = ops.hlgauss_value(vlogits, engine.centers)
+        # the fused kernel's value must agree with get_value of the logits it reports
+        torch.testing.assert_close(val, ops.hlgauss_value(vlogits, engine.centers), rtol=1e-5, atol=1e-5)
         # recompute the oracle's step-t outputs from its own trajectory (teacher forcing on last_action)
         agree += (act.cpu() == ref["actions"][:, t]).sum().item()
         same = act.cpu() == ref["actions"][:, t]
