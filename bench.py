@@ -276,10 +276,9 @@ def main():
         t, r, env, eng = 300, trainer.r, trainer.env, trainer.engine
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        logits, _ = eng.decode_step(trainer.dws, env.obs[t], env.reward[t], r.actions_ext[t], r.pos[t],
-                                    value_out=r.values[t])
-        _ops.gumbel_noise(r.gumbel, trainer.seed, t, trainer.noise_off)
-        _ops.policy_sample(logits, r.gumbel, action=r.actions_ext[t + 1], log_prob=r.log_prob[t])
+        eng.decode_step(trainer.dws, env.obs[t], env.reward[t], r.actions_ext[t], r.pos[t], value_out=r.values[t],
+                        sample=dict(action=r.actions_ext[t + 1], log_prob=r.log_prob[t], seed=trainer.seed, stream_id=t,
+                                    stream_offset=trainer.noise_off, want_logits=False))
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         print(json.dumps({"ncu_decode_step": True}), flush=True)

@@ -238,6 +238,16 @@ int mpx_policy_logits(const mpx_bf16* x, const float* table, const uint8_t* acti
  * action = argmax(logits + gumbel) (first maximum), log_prob = log_softmax(logits)[action]. */
 int mpx_policy_sample(const float* logits, const float* gumbel, int32_t* action, float* log_prob, long long M, int A,
                       mpx_stream_t stream);
+/* The rollout step's whole policy path in one kernel (network.py:321-333, train.py:97-98): xf = RMSNorm(x) when
+ * norm_scale != NULL (else x is used as is), logits = f32(xf) @ table^T, mask, action = argmax(logits + gumbel),
+ * log_prob = log_softmax(logits)[action].  gumbel_in (M,A) overrides the built-in Philox draw (which is the one
+ * mpx_gumbel_noise(seed, stream_id + *stream_offset) produces for an (M,A) buffer).  logits_out (M,A) and xf_out (M,H)
+ * are optional outputs. */
+int mpx_policy_head_sample(const mpx_bf16* x, const float* norm_scale, float eps, const float* table,
+                           const uint8_t* action_mask, const float* gumbel_in, unsigned long long seed,
+                           unsigned long long stream_id, const unsigned long long* stream_offset, float* logits_out,
+                           mpx_bf16* xf_out, int32_t* action, float* log_prob, long long M, int H, int A,
+                           mpx_stream_t stream);
 /* Counter-based Philox-4x32-10 Gumbel(0,1) noise (the reference draws it from JAX's threefry; the noise source is
  * outside the parity contract, the arg-max is inside it). */
 int mpx_gumbel_noise(float* out, long long n, unsigned long long seed, unsigned long long stream_id,

@@ -206,6 +206,133 @@ __global__ void gumbel_noise_kernel(float* __restrict__ out, long long n, unsign
   }
 }
 
+// ------------------------------------------------------------------------------------------------ fused policy head
+// Rollout-step policy path in one kernel (network.py:321-333 + train.py:97-98): optional output RMSNorm, tied action
+// logits, mask, Gumbel arg-max sample and its log-probability.  8 lanes per token as in policy_logits_kernel; after the
+// xor-reduction every lane of the group holds all A logits, lane `sub` then owns actions {sub, sub+8, ...} for the noise
+// draw (same Philox counters as gumbel_noise_kernel: element index = row*A + a), the arg-max and the log-sum-exp.
+constexpr int PH_MAX_PER = 32;   // features per lane: H <= 256
+__global__ void __launch_bounds__(HD_WARPS * 32) policy_head_sample_kernel(
+    const __nv_bfloat16* __restrict__ x, const float* __restrict__ norm_scale, float eps, const float* __restrict__ table,
+    const uint8_t* __restrict__ mask, const float* __restrict__ gumbel_in, unsigned long long seed,
+    unsigned long long stream_id, const unsigned long long* __restrict__ stream_off, float* __restrict__ logits_out,
+    __nv_bfloat16* __restrict__ xf_out, int32_t* __restrict__ action, float* __restrict__ log_prob, long long M, int H,
+    int A) {
+  extern __shared__ float s_table[];   // [A][H]
+  for (int i = threadIdx.x; i < A * H; i += blockDim.x) s_table[i] = table[i];
+  __syncthreads();
+  if (stream_off) stream_id += stream_off[0];
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & 7, rsel = lane >> 3;
+  const int per = H / 8;
+  const long long stride = (long long)gridDim.x * HD_WARPS * 4;
+  for (long long base = ((long long)blockIdx.x * HD_WARPS + (threadIdx.x >> 5)) * 4; base < M; base += stride) {
+    const long long row = base + rsel;
+    const bool live = row < M;
+    float xv[PH_MAX_PER];
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < PH_MAX_PER; c += 8) {
+      if (c < per) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (live) v = *reinterpret_cast<const uint4*>(x + row * H + sub * per + c);
+        xv[c] = bf16_lo(v.x); xv[c + 1] = bf16_hi(v.x); xv[c + 2] = bf16_lo(v.y); xv[c + 3] = bf16_hi(v.y);
+        xv[c + 4] = bf16_lo(v.z); xv[c + 5] = bf16_hi(v.z); xv[c + 6] = bf16_lo(v.w); xv[c + 7] = bf16_hi(v.w);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss = fmaf(xv[c + e], xv[c + e], ss);
+      }
+    }
+    if (norm_scale) {     // nnx.RMSNorm: fp32 statistics, result rounded to bf16
+      ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+      const float inv = rsqrtf(ss / (float)H + eps);
+#pragma unroll
+      for (int c = 0; c < PH_MAX_PER; c += 8) {
+        if (c < per) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            w[e >> 1] = pack_bf16(xv[c + e] * inv * norm_scale[sub * per + c + e],
+                                  xv[c + e + 1] * inv * norm_scale[sub * per + c + e + 1]);
+            xv[c + e] = bf16_lo(w[e >> 1]);
+            xv[c + e + 1] = bf16_hi(w[e >> 1]);
+          }
+          if (xf_out && live) *reinterpret_cast<uint4*>(xf_out + row * H + sub * per + c) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+    float part[MAX_A];
+#pragma unroll
+    for (int a = 0; a < MAX_A; ++a) {
+      part[a] = 0.f;
+      if (a < A) {
+        const float* tr = s_table + a * H + sub * per;
+#pragma unroll
+        for (int c = 0; c < PH_MAX_PER; ++c)
+          if (c < per) part[a] = fmaf(xv[c], tr[c], part[a]);
+        part[a] += __shfl_xor_sync(0xffffffffu, part[a], 1);
+        part[a] += __shfl_xor_sync(0xffffffffu, part[a], 2);
+        part[a] += __shfl_xor_sync(0xffffffffu, part[a], 4);
+      }
+    }
+    // this lane's actions: masked logit, noise, local arg-max / max
+    float best = -INFINITY, mx = -INFINITY, mine[MAX_A / 8];
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int q = 0; q < MAX_A / 8; ++q) {
+      const int a = sub + 8 * q;
+      mine[q] = -INFINITY;
+      if (a < A && live) {
+        float l = part[a];
+        if (mask && !mask[row * A + a]) l = -3.4028234663852886e38f;
+        mine[q] = l;
+        if (logits_out) logits_out[row * A + a] = l;
+        float gn;
+        if (gumbel_in) {
+          gn = gumbel_in[row * A + a];
+        } else {
+          const unsigned long long e = (unsigned long long)row * A + a;
+          const unsigned long long i = e >> 2;
+          uint32_t c[4] = {(uint32_t)i, (uint32_t)(i >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32)};
+          philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+          const uint32_t r = (e & 3) == 0 ? c[0] : (e & 3) == 1 ? c[1] : (e & 3) == 2 ? c[2] : c[3];
+          const float u = ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f);
+          gn = -logf(-logf(u));
+        }
+        const float v = l + gn;
+        if (v > best) { best = v; bi = a; }      // ascending a within the lane: keeps the first maximum
+        mx = fmaxf(mx, l);
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    float se = 0.f, lbi = 0.f;
+#pragma unroll
+    for (int q = 0; q < MAX_A / 8; ++q) {
+      const int a = sub + 8 * q;
+      if (a < A && live) {
+        se += expf(mine[q] - mx);
+        if (a == bi) lbi = mine[q];
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      se += __shfl_xor_sync(0xffffffffu, se, o);
+      lbi += __shfl_xor_sync(0xffffffffu, lbi, o);
+    }
+    if (live && sub == 0) {
+      action[row] = bi;
+      log_prob[row] = (lbi - mx) - logf(se);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ PPO policy loss
 // Per token (train.py:193-212, distrax.Categorical log_prob / entropy):
 //   lp = log_softmax(logits); ratio = exp(lp[a] - old_lp); actor = -min(ratio*adv, clip(ratio,1-e,1+e)*adv)
@@ -468,4 +595,21 @@ extern "C" int mpx_policy_head_bwd(const float* dlogits, const mpx_bf16* x, cons
   if (A <= 8) return launch_phb<8>(dlogits, X, table, DO, DX, dtable, M, H, A, s);
   if (A <= 16) return launch_phb<16>(dlogits, X, table, DO, DX, dtable, M, H, A, s);
   return launch_phb<32>(dlogits, X, table, DO, DX, dtable, M, H, A, s);
+}
+
+extern "C" int mpx_policy_head_sample(const mpx_bf16* x, const float* norm_scale, float eps, const float* table,
+                                      const uint8_t* action_mask, const float* gumbel_in, unsigned long long seed,
+                                      unsigned long long stream_id, const unsigned long long* stream_offset,
+                                      float* logits_out, mpx_bf16* xf_out, int32_t* action, float* log_prob, long long M,
+                                      int H, int A, mpx_stream_t stream) {
+  MPX_REQUIRE(x && table && action && log_prob && M > 0, "mpx_policy_head_sample: bad arguments");
+  MPX_REQUIRE(A > 0 && A <= MAX_A, "mpx_policy_head_sample: A=%d not in [1,%d]", A, MAX_A);
+  MPX_REQUIRE(H % 64 == 0 && H <= 8 * PH_MAX_PER, "mpx_policy_head_sample: H=%d must be a multiple of 64, <= %d", H,
+              8 * PH_MAX_PER);
+  const size_t smem = (size_t)A * H * sizeof(float);
+  MPX_REQUIRE(smem <= 48 * 1024, "mpx_policy_head_sample: table too large for shared memory");
+  policy_head_sample_kernel<<<grid_for(M, HD_WARPS * 4, 8), HD_WARPS * 32, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), norm_scale, eps, table, action_mask, gumbel_in, seed, stream_id,
+      stream_offset, logits_out, reinterpret_cast<__nv_bfloat16*>(xf_out), action, log_prob, M, H, A);
+  return check_launch("mpx_policy_head_sample");
 }

@@ -285,11 +285,14 @@ class PolicyEngine:
             dy = ws.dca[c.j - 1]
 
     # ------------------------------------------------------------------------------------------ decode step
-    def decode_step(self, ws, obs, reward, last_action, pos, action_mask=None, task_ids=None, value_out=None):
+    def decode_step(self, ws, obs, reward, last_action, pos, action_mask=None, task_ids=None, value_out=None,
+                    sample=None):
         """One rollout step for B agents: TransformerActorCritic.__call__ with carry (network.py:300-343) on
         add_seq_dim(timestep).  pos is the (B,) int32 device array ts.time.  Leaves action logits in ws.logits
         and the HL-Gauss logits in ws.vlogits; the KV caches in ws are updated in place.  value_out (B,) f32, when
-        given, receives HlGaussValue.get_value of those logits (values.py:43-45; fused with the value path)."""
+        given, receives HlGaussValue.get_value of those logits (values.py:43-45; fused with the value path).
+        sample = dict(action=(B,) i32, log_prob=(B,) f32, seed=, stream_id=, stream_offset=, [gumbel_in=],
+        [want_logits=True]) draws the action inside the policy-head kernel (sample_actions, network.py:345-351)."""
         p, w, B = self.p, self.w, ws.B
         S = self.cfg.max_seq_length
         x = self._embed_fwd(ws, B, obs, reward, last_action, task_ids, ws.xa, train=False)
@@ -311,14 +314,28 @@ class PolicyEngine:
                 ops.linear(ws.h, w[pre + "wt_d"], residual=x, out=other)
             x, other = other, x
         if value_out is not None and self.fused_value:
-            ops.rmsnorm_fwd(x, p["output_norm.scale"], out=ws.xf)
-            ops.policy_logits(ws.xf, p["action_embedder.embedding_table"], action_mask, out=ws.logits)
-            ops.value_head_fused(ws.xf, w["wt_vm"], w["b_vm"], w["wt_vh_hilo"], p["value_head.dense.bias"], self.centers,
-                                 value_out, vlogits=ws.vlogits)
+            # both head kernels apply output_norm themselves: no normalised copy of x is materialised
+            if sample is not None:
+                ops.policy_head_sample(x, p["action_embedder.embedding_table"], sample["action"], sample["log_prob"],
+                                       seed=sample.get("seed", 0), stream_id=sample.get("stream_id", 0),
+                                       stream_offset=sample.get("stream_offset"), mask=action_mask,
+                                       gumbel_in=sample.get("gumbel_in"), norm_scale=p["output_norm.scale"],
+                                       logits_out=ws.logits if sample.get("want_logits", True) else None)
+            else:
+                ops.rmsnorm_fwd(x, p["output_norm.scale"], out=ws.xf)
+                ops.policy_logits(ws.xf, p["action_embedder.embedding_table"], action_mask, out=ws.logits)
+            ops.value_head_fused(x, w["wt_vm"], w["b_vm"], w["wt_vh_hilo"], p["value_head.dense.bias"], self.centers,
+                                 value_out, vlogits=ws.vlogits, norm_scale=p["output_norm.scale"])
             return ws.logits, ws.vlogits
         self._heads_fwd(x, action_mask, ws.xf, ws.logits, ws.pv, None, ws.vlogits)
         if value_out is not None:
             ops.hlgauss_value(ws.vlogits, self.centers, out=value_out)
+        if sample is not None:
+            gum = sample.get("gumbel_in")
+            if gum is None:
+                gum = ops.gumbel_noise(torch.empty_like(ws.logits), sample.get("seed", 0), sample.get("stream_id", 0),
+                                       sample.get("stream_offset"))
+            ops.policy_sample(ws.logits, gum, action=sample["action"], log_prob=sample["log_prob"])
         return ws.logits, ws.vlogits
 
     def _heads_fwd(self, x, action_mask, xf, logits, pv, zv, vlogits):

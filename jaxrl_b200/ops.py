@@ -355,6 +355,19 @@ def policy_sample(logits, gumbel, action=None, log_prob=None):
     return action, log_prob
 
 
+def policy_head_sample(x, table, action, log_prob, seed: int = 0, stream_id: int = 0, stream_offset=None, mask=None,
+                       gumbel_in=None, norm_scale=None, eps: float = 1e-6, logits_out=None, xf_out=None):
+    """Fused rollout policy path: (RMSNorm) -> tied logits -> mask -> Gumbel arg-max -> log-prob."""
+    _req(x, BF16, "x"); _req(table, F32, "table"); _req(action, I32, "action"); _req(log_prob, F32, "log_prob")
+    H = x.shape[-1]
+    M = x.numel() // H
+    A = table.shape[0]
+    check(lib.mpx_policy_head_sample(ptr(x), ptr(norm_scale), eps, ptr(table), ptr(_u8(mask)), ptr(gumbel_in), seed,
+                                     stream_id, ptr(stream_offset), ptr(logits_out), ptr(xf_out), ptr(action),
+                                     ptr(log_prob), M, H, A, stream()), "mpx_policy_head_sample")
+    return action, log_prob
+
+
 def gumbel_noise(out, seed: int, stream_id: int, stream_offset=None):
     check(lib.mpx_gumbel_noise(ptr(out), out.numel(), seed, stream_id, ptr(stream_offset), stream()),
           "mpx_gumbel_noise")

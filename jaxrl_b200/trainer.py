@@ -128,9 +128,9 @@ class PPOTrainer:
                 obs_t, rew_t = r.obs_stage, r.rew_stage
             else:
                 obs_t, rew_t = env.obs[t], env.reward[t]
-            logits, _ = eng.decode_step(self.dws, obs_t, rew_t, r.actions_ext[t], r.pos[t], value_out=r.values[t])
-            ops.gumbel_noise(r.gumbel, self.seed, t, self.noise_off)
-            ops.policy_sample(logits, r.gumbel, action=r.actions_ext[t + 1], log_prob=r.log_prob[t])
+            eng.decode_step(self.dws, obs_t, rew_t, r.actions_ext[t], r.pos[t], value_out=r.values[t],
+                            sample=dict(action=r.actions_ext[t + 1], log_prob=r.log_prob[t], seed=self.seed, stream_id=t,
+                                        stream_offset=self.noise_off, want_logits=False))
         # bootstrap (train.py:142-148): value of the INITIAL timestep with the INITIAL (empty) carry.  Position 0
         # reads and writes ring slot 0 only, so re-running step 0 on the used caches is equivalent.
         if self.e2e:

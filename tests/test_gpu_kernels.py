@@ -467,3 +467,45 @@ def test_value_head_fused(ops, M, Vh, NL, cluster, norm):
     torch.testing.assert_close(value.cpu(), val_ref, rtol=1e-2, atol=3e-2)
     # internal consistency: value == get_value(vlogits) to fp32 accuracy
     torch.testing.assert_close(value.cpu(), O.hlgauss_get_value(vlogits.cpu(), centers), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("M,H,A,norm", [(4096, 128, 6, True), (777, 128, 8, False), (3000, 256, 19, True), (5, 64, 1, True)])
+def test_policy_head_sample_fused(ops, M, H, A, norm):
+    """Fused (RMSNorm ->) logits -> mask -> Gumbel arg-max -> log-prob vs the separate kernels and the oracle."""
+    gen = g(M + H + A)
+    x = torch.randn(M, H, generator=gen).to(BF16)
+    scale = 1.0 + 0.1 * torch.randn(H, generator=gen)
+    table = torch.randn(A, H, generator=gen) * 0.1
+    mask = torch.rand(M, A, generator=gen) < 0.8
+    mask[:, 0] = True
+    xd, td, md = x.to(DEV), table.to(DEV), mask.to(DEV)
+    xf_ref = O.rms_norm(x, scale) if norm else x
+    ref_logits = torch.where(mask, xf_ref.float() @ table.t(), torch.tensor(torch.finfo(torch.float32).min))
+    # (1) caller-provided noise: same arg-max as the oracle wherever the top-2 margin is not a rounding tie
+    gum = -torch.log(-torch.log(torch.rand(M, A, generator=gen).clamp(1e-6, 1 - 1e-6)))
+    act = torch.empty(M, dtype=torch.int32, device=DEV)
+    lp = torch.empty(M, dtype=torch.float32, device=DEV)
+    logits = torch.empty(M, A, dtype=torch.float32, device=DEV)
+    xf = torch.empty(M, H, dtype=BF16, device=DEV)
+    ops.policy_head_sample(xd, td, act, lp, mask=md, gumbel_in=gum.to(DEV), norm_scale=scale.to(DEV) if norm else None,
+                           logits_out=logits, xf_out=xf if norm else None)
+    torch.cuda.synchronize()
+    live = mask
+    torch.testing.assert_close(logits.cpu()[live], ref_logits[live], rtol=1e-2, atol=2e-2)
+    assert (logits.cpu()[~live] == torch.finfo(torch.float32).min).all()
+    if norm:
+        assert_close_bf16(xf, xf_ref, "policy_head_sample xf")
+    # exact self-consistency: the action is the arg-max of the kernel's own logits + the given noise
+    own = O.categorical_sample_gumbel(logits.cpu(), gum)
+    assert torch.equal(act.cpu(), own)
+    torch.testing.assert_close(lp.cpu(), O.categorical_log_prob(logits.cpu(), own), rtol=1e-5, atol=1e-5)
+    # (2) built-in Philox noise == mpx_gumbel_noise with the same (seed, stream) + mpx_policy_sample
+    off = torch.tensor([3], dtype=torch.int64, device=DEV)
+    act2 = torch.empty_like(act)
+    lp2 = torch.empty_like(lp)
+    ops.policy_head_sample(xd, td, act2, lp2, seed=1234, stream_id=7, stream_offset=off, mask=md,
+                           norm_scale=scale.to(DEV) if norm else None)
+    noise = ops.gumbel_noise(torch.empty(M, A, dtype=torch.float32, device=DEV), 1234, 7, off)
+    act3, lp3 = ops.policy_sample(logits, noise)
+    assert torch.equal(act2, act3)
+    torch.testing.assert_close(lp2, lp3, rtol=1e-6, atol=1e-6)
