@@ -33,7 +33,8 @@ int mpx_version(void);
  * key 1: decode attention implementation (0 = mma.sync online softmax, default; 1 = SIMT exact two-pass;
  * 2 = mma.sync exact two-pass).  key 2: training attention forward (0 = tcgen05/TMEM when q,k,v are packed and
  * Nkv == 1, default; 1 = mma.sync everywhere).  key 3: mpx_glu_fused cluster size (0 = auto; 1, 2 or 4 = force).
- * key 4: mpx_value_head_fused cluster size, same values. */
+ * key 4: mpx_value_head_fused cluster size, same values.  key 5: swap LBO/SBO in mpx_obs_embed_fused's no-swizzle
+ * UMMA descriptors (bring-up). */
 int mpx_debug_set(int key, int value);
 
 /* ---------------------------------------------------------------------------------------------- GAE
@@ -231,6 +232,17 @@ int mpx_embed_combine(const mpx_bf16* obs_emb, const float* reward, const int32_
 int mpx_embed_bwd(const mpx_bf16* dx, const float* reward, const int32_t* last_action, const int32_t* task_ids,
                   int A, int n_tasks, float* d_w_reward, float* d_b_reward, float* d_action_table,
                   float* d_task_table, long long M, int H, mpx_stream_t stream);
+/* Rollout-step observation encoder + input embedding in one kernel (observation.py:84-96 + network.py:303-309) for the
+ * standard geometry: (M,11,11,K) uint8 view, one-hot sizes[K] (sum <= 20), conv 3x3/2 -> 16, gelu, conv 3x3/1 -> 32, gelu,
+ * conv 3x3/1 -> H = 128, then x = obs_emb + reward_encoder(reward) + embed(last_action) (+ embed(task)).
+ * w1 (9*C,16) bf16 rows = (tap, one-hot channel); wt2 (32,144) and wt3 (128,288) are the transposed kernels with
+ * K index = tap*cin + c (the layouts mpx_prep_weights produces for mpx_linear); biases bf16; embedding tables fp32 as
+ * in mpx_embed_combine.  obs_emb (M,H) is an optional copy of the encoder output before the embedding sum. */
+int mpx_obs_embed_fused(const uint8_t* obs, const int* sizes, int K, const mpx_bf16* w1, const mpx_bf16* b1,
+                        const mpx_bf16* wt2, const mpx_bf16* b2, const mpx_bf16* wt3, const mpx_bf16* b3,
+                        const float* reward, const int32_t* last_action, const int32_t* task_ids, const float* w_reward,
+                        const float* b_reward, const float* action_table, int A, const float* task_table, int n_tasks,
+                        mpx_bf16* x, mpx_bf16* obs_emb, long long M, int IH, int IW, int H, mpx_stream_t stream);
 /* network.py:323-331: tied action logits f32(x) @ table^T (M,A) f32, masked entries = finfo(f32).min. A <= 32. */
 int mpx_policy_logits(const mpx_bf16* x, const float* table, const uint8_t* action_mask, float* logits, long long M,
                       int H, int A, mpx_stream_t stream);

@@ -30,6 +30,7 @@ extern int g_attn_decode_impl;
 extern int g_attn_train_impl;
 extern int g_glu_fused_cluster;
 extern int g_value_fused_cluster;
+extern int g_obs_fused_swap;
 
 }  // namespace mpx
 
@@ -54,6 +55,10 @@ extern "C" int mpx_debug_set(int key, int value) {
   }
   if (key == 4) {
     mpx::g_value_fused_cluster = value;
+    return MPX_OK;
+  }
+  if (key == 5) {
+    mpx::g_obs_fused_swap = value;
     return MPX_OK;
   }
   mpx::set_error("mpx_debug_set: unknown key %d", key);

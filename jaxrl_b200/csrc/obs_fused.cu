@@ -1,0 +1,395 @@
+// Fused observation encoder + input embedding of the rollout step (reference GridCnnObsEncoder.__call__,
+// mapox_trainer/model/observation.py:84-96, and the embedding sum of TransformerActorCritic.__call__,
+// network.py:303-309) for the standard geometry: 11x11xK uint8 view -> one-hot -> conv 3x3/2 (16) -> gelu ->
+// conv 3x3/1 (32) -> gelu -> conv 3x3/1 (H = 128) -> + reward / last-action / task embeddings.
+//
+// One CTA per tile of 32 agents; nothing but the uint8 observation is read from and nothing but the (B, H) bf16
+// embedding is written to HBM:
+//   conv1  one-hot convolution == a gather-sum of weight rows (SIMT, 8 worker warps), result a1 (25 positions x 16 ch)
+//          written to shared memory directly in the tcgen05 no-swizzle K-major core-matrix layout;
+//   conv2  27 tcgen05.mma (M128 N32 K16): for output row py, tap (ky,kx): D[py] += A(q) . W2[tap], where the A
+//          operand is simply the a1 tile of input position q = (py+ky)*5 + kx - rows 0..95 of the MMA are
+//          (px, agent) because consecutive px are consecutive q tiles; no im2col copy exists anywhere;
+//   conv3  the 3x3 map flattened is a Linear with K = 288: 18 tcgen05.mma (M128 N128 K16) on a2 (bias+gelu epilogue
+//          of conv2, written by the worker warps in core-matrix layout); only rows 0..31 of the tile are agents.
+// The weights are re-laid into core-matrix images in shared memory once per CTA with cp.async.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mpx {
+
+int g_obs_fused_swap = 0;   // mpx_debug_set(5, 1): swap LBO/SBO of the no-swizzle descriptors (bring-up knob)
+
+constexpr int OF_AG = 32;              // agents per tile
+constexpr int OF_WORKERS = 8;          // worker warps
+constexpr int OF_THREADS = (OF_WORKERS + 1) * 32;
+constexpr int OF_IH = 11, OF_IW = 11, OF_P1 = 5, OF_C1 = 16, OF_C2 = 32, OF_H = 128;
+constexpr int OF_K3 = 9 * OF_C2;       // 288
+constexpr int OF_MAXC = 20;            // one-hot channels supported
+constexpr int OF_MAXK = 4;             // observation components per cell
+
+constexpr int OF_A1_BYTES = 26 * 1024;                 // 25 position tiles [32 agents x 16 ch] + 1 tile of slack
+constexpr int OF_A2_BYTES = 16 * (OF_K3 / 8) * 128;    // 128 rows x 576 B = 73728
+constexpr int OF_W3_BYTES = 16 * (OF_K3 / 8) * 128;    // 128 n x 576 B
+constexpr int OF_W2_BYTES = 9 * 1024;
+constexpr int OF_W1_BYTES = 9 * OF_MAXC * OF_C1 * 2;   // 5760
+constexpr int OF_OBS_BYTES = OF_AG * OF_IH * OF_IW * OF_MAXK;   // 15488
+constexpr int OF_SMEM = OF_A1_BYTES + OF_A2_BYTES + OF_W3_BYTES + OF_W2_BYTES + OF_W1_BYTES + 512 + OF_OBS_BYTES + 128 + 1024;
+
+struct ObsFusedParams {
+  const uint8_t* obs;             // (M, 11, 11, K)
+  int K, C;                       // components per cell, total one-hot channels
+  int offs[OF_MAXK + 1];
+  const __nv_bfloat16* w1;        // (9*C, 16) bf16
+  const __nv_bfloat16* wt2;       // (32, 144) bf16, K index = tap*16 + cin
+  const __nv_bfloat16* wt3;       // (128, 288) bf16, K index = pos*32 + cin
+  const __nv_bfloat16* b1;
+  const __nv_bfloat16* b2;
+  const __nv_bfloat16* b3;
+  const float* reward;            // (M)
+  const int32_t* last_action;     // (M)
+  const int32_t* task_ids;        // (M) or null
+  const float* w_r;               // (H)
+  const float* b_r;               // (H)
+  const float* a_table;           // (A, H)
+  int A;
+  const float* t_table;           // (n_tasks, H) or null
+  int n_tasks;
+  __nv_bfloat16* x;               // (M, H)
+  __nv_bfloat16* obs_emb;         // (M, H) or null: conv3 output before the embedding sum (tests)
+  long long M;
+  int swap;
+};
+
+__device__ __forceinline__ uint64_t umma_smem_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;                                                  // layout type 0: no swizzle
+}
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void of_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA1 = smem;
+  uint8_t* sA2 = sA1 + OF_A1_BYTES;
+  uint8_t* sW3 = sA2 + OF_A2_BYTES;
+  uint8_t* sW2 = sW3 + OF_W3_BYTES;
+  uint8_t* sW1 = sW2 + OF_W2_BYTES;
+  __nv_bfloat16* sB = reinterpret_cast<__nv_bfloat16*>(sW1 + OF_W1_BYTES);     // b1[16] b2[32] b3[128]
+  uint8_t* sObs = reinterpret_cast<uint8_t*>(sB) + 512;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sObs + OF_OBS_BYTES);
+  uint64_t* a1_ready = bars;
+  uint64_t* c2_full = bars + 1;
+  uint64_t* a2_ready = bars + 2;
+  uint64_t* c3_full = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* sOut = reinterpret_cast<float*>(sA1);               // conv3 accumulator staging, aliases a1 (dead by then)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tid = threadIdx.x;
+  const int n_tiles = (int)((p.M + OF_AG - 1) / OF_AG);
+  const int cell_bytes = OF_IH * OF_IW * p.K;
+
+  if (tid == 0) {
+    mbar_init(a1_ready, OF_WORKERS);
+    mbar_init(c2_full, 1);
+    mbar_init(a2_ready, OF_WORKERS);
+    mbar_init(c3_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == OF_WORKERS) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  // ---- weight images (once per CTA): 16-byte pieces of the K-major bf16 matrices -> core-matrix layout
+  {
+    const uint32_t w3 = smem_u32(sW3), w2 = smem_u32(sW2), w1 = smem_u32(sW1), sb = smem_u32(sB);
+    for (int i = tid; i < OF_H * (OF_K3 / 8); i += OF_THREADS) {          // wt3 (128, 288): piece (n, kk)
+      const int n = i / (OF_K3 / 8), kk = i % (OF_K3 / 8);
+      cp_async16(w3 + (n >> 3) * ((OF_K3 / 8) * 128) + kk * 128 + (n & 7) * 16, p.wt3 + (long long)n * OF_K3 + kk * 8);
+    }
+    for (int i = tid; i < OF_C2 * 18; i += OF_THREADS) {                  // wt2 (32, 144): piece (n, kk), tap = kk / 2
+      const int n = i / 18, kk = i % 18;
+      cp_async16(w2 + (kk >> 1) * 1024 + (n >> 3) * 256 + (kk & 1) * 128 + (n & 7) * 16, p.wt2 + n * 144 + kk * 8);
+    }
+    for (int i = tid; i < 9 * p.C * 2; i += OF_THREADS) cp_async16(w1 + i * 16, p.w1 + i * 8);
+    if (tid < 2) cp_async16(sb + tid * 16, p.b1 + tid * 8);
+    else if (tid < 6) cp_async16(sb + 32 + (tid - 2) * 16, p.b2 + (tid - 2) * 8);
+    else if (tid < 22) cp_async16(sb + 96 + (tid - 6) * 16, p.b3 + (tid - 6) * 8);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tD2 = tmem_base;            // 3 x 32 columns
+  const uint32_t tD3 = tmem_base + 128;      // 128 columns
+  const uint32_t lboA = p.swap ? 256u : 128u, sboA1 = p.swap ? 128u : 256u;
+  const uint32_t sbo3 = (OF_K3 / 8) * 128;   // 4608
+
+  if (warp == OF_WORKERS) {
+    // ================================ MMA issuer ================================
+    cp_async_wait_all();
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      constexpr uint32_t idesc2 = umma_idesc_bf16(128, OF_C2, 0, 0);
+      constexpr uint32_t idesc3 = umma_idesc_bf16(128, OF_H, 0, 0);
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        mbar_wait(a1_ready, ph);
+        tc_fence_after();
+        const uint32_t a1 = smem_u32(sA1), w2 = smem_u32(sW2);
+#pragma unroll 1
+        for (int j = 0; j < 3; ++j) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int q0 = (j + tap / 3) * OF_P1 + (tap % 3);
+            umma_bf16(tD2 + j * OF_C2, umma_smem_desc_nosw(a1 + q0 * 1024, lboA, sboA1),
+                      umma_smem_desc_nosw(w2 + tap * 1024, lboA, sboA1), idesc2, tap != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(c2_full);
+        mbar_wait(a2_ready, ph);
+        tc_fence_after();
+        const uint32_t a2 = smem_u32(sA2), w3 = smem_u32(sW3);
+#pragma unroll
+        for (int s = 0; s < OF_K3 / 16; ++s)
+          umma_bf16(tD3, umma_smem_desc_nosw(a2 + s * 256, p.swap ? sbo3 : 128u, p.swap ? 128u : sbo3),
+                    umma_smem_desc_nosw(w3 + s * 256, p.swap ? sbo3 : 128u, p.swap ? 128u : sbo3), idesc3, s != 0 ? 1u : 0u);
+        umma_commit(c3_full);
+        ph ^= 1;
+      }
+    }
+  } else {
+    // ================================ worker warps ================================
+    const int wtid = tid;                                   // 0..255
+    const int quarter = warp & 3, chalf = warp >> 2;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const float sqH = bf16_round(sqrtf((float)OF_H));
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long m0 = (long long)tile * OF_AG;
+      const int nag = (int)min((long long)OF_AG, p.M - m0);
+      // ---- observation tile -> smem (contiguous bytes)
+      {
+        const int nbytes = nag * cell_bytes;
+        const uint8_t* src = p.obs + m0 * cell_bytes;
+        if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+          const int nw = nbytes >> 2;
+          for (int i = wtid; i < nw; i += OF_WORKERS * 32)
+            reinterpret_cast<uint32_t*>(sObs)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+          for (int i = (nw << 2) + wtid; i < nbytes; i += OF_WORKERS * 32) sObs[i] = src[i];
+        } else {
+          for (int i = wtid; i < nbytes; i += OF_WORKERS * 32) sObs[i] = src[i];
+        }
+      }
+      if (tile == blockIdx.x) cp_async_wait_all();          // this thread's share of the weight images has landed
+      of_bar_sync(1, OF_WORKERS * 32);
+      // ---- conv1: gather-sum over (tap, component), bias, gelu -> a1 in core-matrix layout
+      for (int t = wtid; t < OF_AG * 25 * 2; t += OF_WORKERS * 32) {
+        const int ag = t & 31, half = (t >> 5) & 1, q = t >> 6;
+        const int oy = q / OF_P1, ox = q % OF_P1;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const uint8_t* cell0 = sObs + ag * cell_bytes + ((oy * 2) * OF_IW + ox * 2) * p.K;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint8_t* cell = cell0 + ((tap / 3) * OF_IW + (tap % 3)) * p.K;
+          for (int kc = 0; kc < p.K; ++kc) {
+            const int val = cell[kc];
+            if (ag < nag && val < p.offs[kc + 1] - p.offs[kc]) {
+              const uint4 wv = *reinterpret_cast<const uint4*>(sW1 + ((tap * p.C + p.offs[kc] + val) * OF_C1 + half * 8) * 2);
+              acc[0] += bf16_lo(wv.x); acc[1] += bf16_hi(wv.x); acc[2] += bf16_lo(wv.y); acc[3] += bf16_hi(wv.y);
+              acc[4] += bf16_lo(wv.z); acc[5] += bf16_hi(wv.z); acc[6] += bf16_lo(wv.w); acc[7] += bf16_hi(wv.w);
+            }
+          }
+        }
+        const uint4 bv = *reinterpret_cast<const uint4*>(sB + half * 8);
+        const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t zw = pack_bf16(acc[2 * e], acc[2 * e + 1]);
+          const uint32_t zb = pack_bf16(bf16_lo(zw) + bf16_lo(bw[e]), bf16_hi(zw) + bf16_hi(bw[e]));
+          o[e] = pack_bf16(gelu_tanh(bf16_lo(zb)), gelu_tanh(bf16_hi(zb)));
+        }
+        *reinterpret_cast<uint4*>(sA1 + q * 1024 + (ag >> 3) * 256 + half * 128 + (ag & 7) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a1_ready);
+      // ---- conv2 epilogue: rows (px = quarter, agent = lane), this warp's 16 of the 32 channels -> a2
+      mbar_wait(c2_full, ph);
+      tc_fence_after();
+      if (quarter < 3) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          uint32_t d[16];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]),
+                "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
+              : "r"(tD2 + lane_off + j * OF_C2 + chalf * 16)
+              : "memory");
+          tmem_ld_wait();
+          const uint4* b4 = reinterpret_cast<const uint4*>(sB + 16 + chalf * 16);
+          const int pos = 3 * j + quarter;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const uint4 bv = b4[hh];
+            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t zw = pack_bf16(__uint_as_float(d[8 * hh + 2 * e]), __uint_as_float(d[8 * hh + 2 * e + 1]));
+              const uint32_t zb = pack_bf16(bf16_lo(zw) + bf16_lo(bw[e]), bf16_hi(zw) + bf16_hi(bw[e]));
+              o[e] = pack_bf16(gelu_tanh(bf16_lo(zb)), gelu_tanh(bf16_hi(zb)));
+            }
+            const int kk = pos * 4 + chalf * 2 + hh;        // 8-wide K core matrix index: k = pos*32 + chalf*16 + hh*8
+            *reinterpret_cast<uint4*>(sA2 + (lane >> 3) * sbo3 + kk * 128 + (lane & 7) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a2_ready);
+      // ---- conv3 accumulator (TMEM lanes 0..31 = agents) -> fp32 staging
+      mbar_wait(c3_full, ph);
+      tc_fence_after();
+      if (quarter == 0) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t acc[32];
+          tmem_ld_32x32(tD3 + chalf * 64 + cc * 32, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(sOut + lane * OF_H + chalf * 64 + cc * 32 + 4 * (i ^ (lane & 7))) =
+                make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]),
+                            __uint_as_float(acc[4 * i + 3]));
+        }
+        tc_fence_before();
+      }
+      of_bar_sync(1, OF_WORKERS * 32);
+      // ---- bias + embedding sum (network.py:303-309): thread = (agent, 16 columns)
+      {
+        const int ag = wtid >> 3, cg = wtid & 7;
+        const long long m = m0 + ag;
+        if (ag < nag) {
+          const float rw = bf16_round(p.reward[m]);
+          int a = p.last_action[m];
+          if (a < 0) a += p.A;
+          const bool a_ok = (a >= 0 && a < p.A);
+          int tk = -1;
+          if (p.task_ids && p.t_table) {
+            tk = p.task_ids[m];
+            if (tk < 0) tk += p.n_tasks;
+            if (tk >= p.n_tasks) tk = -1;
+          }
+          uint32_t ow[8], ew[8];
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const int c4 = cg * 4 + i4;                        // float4 index within the row
+            const int blk = c4 >> 3, i = c4 & 7;               // 32-column block, piece inside it (swizzled)
+            const float4 v = *reinterpret_cast<const float4*>(sOut + ag * OF_H + blk * 32 + 4 * (i ^ (ag & 7)));
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            float res[4], emb[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int h = c4 * 4 + e;
+              const float oe = bf16_round(bf16_round(vv[e]) + __bfloat162float(sB[48 + h]));      // conv3 + bias
+              emb[e] = oe;
+              float re = bf16_round(rw * bf16_round(p.w_r[h]));
+              re = bf16_round(re + bf16_round(p.b_r[h]));
+              float ae = a_ok ? bf16_round(p.a_table[(long long)a * OF_H + h]) : 0.f;
+              ae = bf16_round(ae * sqH);
+              float x = bf16_round(oe + re);
+              x = bf16_round(x + ae);
+              if (p.task_ids && p.t_table) {
+                const float te = tk >= 0 ? bf16_round(p.t_table[(long long)tk * OF_H + h]) : 0.f;
+                x = bf16_round(x + bf16_round(te * sqH));
+              }
+              res[e] = x;
+            }
+            ow[2 * i4] = pack_bf16(res[0], res[1]); ow[2 * i4 + 1] = pack_bf16(res[2], res[3]);
+            ew[2 * i4] = pack_bf16(emb[0], emb[1]); ew[2 * i4 + 1] = pack_bf16(emb[2], emb[3]);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(p.x + m * OF_H + cg * 16);
+          dst[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          dst[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+          if (p.obs_emb) {
+            uint4* de = reinterpret_cast<uint4*>(p.obs_emb + m * OF_H + cg * 16);
+            de[0] = make_uint4(ew[0], ew[1], ew[2], ew[3]);
+            de[1] = make_uint4(ew[4], ew[5], ew[6], ew[7]);
+          }
+        }
+      }
+      of_bar_sync(1, OF_WORKERS * 32);                       // sOut (aliasing a1) and sObs are free for the next tile
+      ph ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == OF_WORKERS) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace mpx
+
+using namespace mpx;
+
+extern "C" int mpx_obs_embed_fused(const uint8_t* obs, const int* sizes, int K, const mpx_bf16* w1, const mpx_bf16* b1,
+                                   const mpx_bf16* wt2, const mpx_bf16* b2, const mpx_bf16* wt3, const mpx_bf16* b3,
+                                   const float* reward, const int32_t* last_action, const int32_t* task_ids,
+                                   const float* w_reward, const float* b_reward, const float* action_table, int A,
+                                   const float* task_table, int n_tasks, mpx_bf16* x, mpx_bf16* obs_emb, long long M,
+                                   int IH, int IW, int H, mpx_stream_t stream) {
+  MPX_REQUIRE(obs && sizes && w1 && b1 && wt2 && b2 && wt3 && b3 && reward && last_action && w_reward && b_reward &&
+                  action_table && x && M > 0 && A > 0,
+              "mpx_obs_embed_fused: bad arguments");
+  MPX_REQUIRE(IH == OF_IH && IW == OF_IW && H == OF_H, "mpx_obs_embed_fused: only the 11x11 view / H=128 geometry is fused");
+  MPX_REQUIRE(K >= 1 && K <= OF_MAXK, "mpx_obs_embed_fused: K=%d components unsupported", K);
+  ObsFusedParams p;
+  p.obs = obs; p.K = K;
+  p.offs[0] = 0;
+  for (int i = 0; i < K; ++i) {
+    MPX_REQUIRE(sizes[i] > 0, "mpx_obs_embed_fused: bad one-hot size");
+    p.offs[i + 1] = p.offs[i] + sizes[i];
+  }
+  for (int i = K + 1; i <= OF_MAXK; ++i) p.offs[i] = p.offs[K];
+  p.C = p.offs[K];
+  MPX_REQUIRE(p.C <= OF_MAXC, "mpx_obs_embed_fused: %d one-hot channels > %d", p.C, OF_MAXC);
+  p.w1 = reinterpret_cast<const __nv_bfloat16*>(w1);
+  p.wt2 = reinterpret_cast<const __nv_bfloat16*>(wt2);
+  p.wt3 = reinterpret_cast<const __nv_bfloat16*>(wt3);
+  p.b1 = reinterpret_cast<const __nv_bfloat16*>(b1);
+  p.b2 = reinterpret_cast<const __nv_bfloat16*>(b2);
+  p.b3 = reinterpret_cast<const __nv_bfloat16*>(b3);
+  p.reward = reward; p.last_action = last_action; p.task_ids = task_ids;
+  p.w_r = w_reward; p.b_r = b_reward; p.a_table = action_table; p.A = A;
+  p.t_table = task_table; p.n_tasks = n_tasks;
+  p.x = reinterpret_cast<__nv_bfloat16*>(x);
+  p.obs_emb = reinterpret_cast<__nv_bfloat16*>(obs_emb);
+  p.M = M;
+  p.swap = g_obs_fused_swap;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(obs_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OF_SMEM);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(obs_fused): %s", cudaGetErrorString(e));
+      return MPX_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const long long tiles = (M + OF_AG - 1) / OF_AG;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  obs_fused_kernel<<<grid, OF_THREADS, OF_SMEM, (cudaStream_t)stream>>>(p);
+  return check_launch("obs_fused_kernel");
+}

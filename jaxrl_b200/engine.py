@@ -72,6 +72,12 @@ class PolicyEngine:
         for c in self.conv[1:]:
             if c.cin % 8 != 0:
                 raise _lib.MpxError("hidden conv channels must be multiples of 8")
+        # rollout path: the standard geometry (11x11 view, 3x3/2 -> 16, 3x3/1 -> 32, 3x3/1 -> 128) runs as one kernel
+        self.fused_obs = (H == 128 and tuple(cfg.obs_shape[:2]) == (11, 11) and len(self.conv) == 3
+                          and all((c.kh, c.kw) == (3, 3) for c in self.conv)
+                          and [(c.sh, c.sw) for c in self.conv] == [(2, 2), (1, 1), (1, 1)]
+                          and [c.cout for c in self.conv] == [16, 32, 128] and self.C0 <= 20
+                          and len(cfg.obs_max_value) <= 4)
         self._alloc_staged()
         self.stage_weights()
 
@@ -229,6 +235,13 @@ class PolicyEngine:
         p, w = self.p, self.w
         cfg = self.cfg
         n = len(self.conv)
+        if not train and self.fused_obs:          # rollout: encoder + embedding sum in one kernel, nothing saved
+            t_table = p.views.get("task_embedder.embedding_table") if task_ids is not None else None
+            c0 = self.conv[0]
+            return ops.obs_embed_fused(obs, cfg.obs_max_value, w["w_c0"], w["b_c0"], w["wt_c1"], w["b_c1"], w["wt_c2"],
+                                       w["b_c2"], reward, last_action, task_ids if t_table is not None else None,
+                                       p["reward_encoder.kernel"], p["reward_encoder.bias"],
+                                       p["action_embedder.embedding_table"], t_table, out, M, c0.ih, c0.iw)
         prev = None
         for c in self.conv:
             last = c.j == n - 1

@@ -509,3 +509,50 @@ def test_policy_head_sample_fused(ops, M, H, A, norm):
     act3, lp3 = ops.policy_sample(logits, noise)
     assert torch.equal(act2, act3)
     torch.testing.assert_close(lp2, lp3, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("M,sizes,tasks", [(32, (5, 5), 0), (4096, (5, 5), 0), (77, (3, 7, 2), 3), (9000, (5, 5), 0)])
+def test_obs_embed_fused(ops, M, sizes, tasks):
+    """Fused observation encoder (one-hot conv gather + two tcgen05 convolutions on no-swizzle operands) + embedding sum
+    vs the oracle obs_encoder / model_embed."""
+    from jaxrl_b200.config import ModelConfig
+    gen = g(M + len(sizes) + tasks)
+    K, C, H, A = len(sizes), sum(sizes), 128, 6
+    cfg = ModelConfig(obs_shape=(11, 11, K), obs_max_value=tuple(sizes), action_dim=A, task_count=max(tasks, 1))
+    obs = torch.stack([torch.randint(0, n, (M, 11, 11), generator=gen) for n in sizes], -1).to(torch.uint8)
+    p = {"obs_encoder.layers.0.kernel": torch.randn(3, 3, C, 16, generator=gen) * 0.3,
+         "obs_encoder.layers.0.bias": torch.randn(16, generator=gen) * 0.1,
+         "obs_encoder.layers.1.kernel": torch.randn(3, 3, 16, 32, generator=gen) / 12.0,
+         "obs_encoder.layers.1.bias": torch.randn(32, generator=gen) * 0.1,
+         "obs_encoder.layers.2.kernel": torch.randn(3, 3, 32, H, generator=gen) / 17.0,
+         "obs_encoder.layers.2.bias": torch.randn(H, generator=gen) * 0.1,
+         "reward_encoder.kernel": torch.randn(1, H, generator=gen), "reward_encoder.bias": torch.randn(H, generator=gen) * 0.1,
+         "action_embedder.embedding_table": torch.randn(A, H, generator=gen) * 0.1}
+    if tasks:
+        p["task_embedder.embedding_table"] = torch.randn(tasks, H, generator=gen) * 0.1
+    reward = torch.randn(M, generator=gen)
+    la = torch.randint(-1, A, (M,), generator=gen).to(torch.int32)
+    tk = torch.randint(0, tasks, (M,), generator=gen).to(torch.int32) if tasks else None
+    emb_ref = O.obs_encoder(p, cfg, obs)
+    ts = O.TimeStep(obs=obs[:, None], time=torch.zeros(M, 1, dtype=torch.int32), terminated=torch.zeros(M, 1, dtype=torch.bool),
+                    last_action=la[:, None], reward=reward[:, None], action_mask=None, task_ids=None if tk is None else tk[:, None])
+    x_ref = O.model_embed(p, cfg, ts)[:, 0]
+    d = lambda t: t.to(DEV)
+    b = lambda t: t.to(BF16).to(DEV)
+    w1 = b(p["obs_encoder.layers.0.kernel"].reshape(9 * C, 16))
+    wt2 = b(p["obs_encoder.layers.1.kernel"].reshape(144, 32).t().contiguous())
+    wt3 = b(p["obs_encoder.layers.2.kernel"].reshape(288, H).t().contiguous())
+    out = torch.empty(M, H, dtype=BF16, device=DEV)
+    emb = torch.empty(M, H, dtype=BF16, device=DEV)
+    import os
+    from jaxrl_b200._lib import lib
+    lib.mpx_debug_set(5, int(os.environ.get("MPX_OBS_SWAP", "0")))      # bring-up knob (descriptor LBO/SBO order)
+    ops.obs_embed_fused(d(obs), sizes, w1, b(p["obs_encoder.layers.0.bias"]), wt2, b(p["obs_encoder.layers.1.bias"]), wt3,
+                        b(p["obs_encoder.layers.2.bias"]), d(reward), d(la), None if tk is None else d(tk),
+                        d(p["reward_encoder.kernel"].reshape(-1)), d(p["reward_encoder.bias"]),
+                        d(p["action_embedder.embedding_table"]), d(p["task_embedder.embedding_table"]) if tasks else None,
+                        out, M, 11, 11, obs_emb=emb)
+    torch.cuda.synchronize()
+    assert_close_bf16(emb, emb_ref, f"obs_embed_fused encoder output M={M}", rtol=1e-2, abs_floor_frac=1e-2, allow_frac=2e-3,
+                      max_err_frac=0.1)
+    assert_close_bf16(out, x_ref, f"obs_embed_fused x M={M}", rtol=1e-2, abs_floor_frac=1e-2, allow_frac=2e-3, max_err_frac=0.1)
