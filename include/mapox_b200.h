@@ -128,9 +128,11 @@ int mpx_glu_up(const mpx_glu_up_args* a, mpx_stream_t stream);
 
 /* Whole GLU block + residual in one kernel (feed_forward.py:73-78 and the residual add of network.py:167-170):
  * out = bf16(residual + bf16(h @ Wdown)), h = bf16(bf16(gelu(bf16(x@Wup))) * bf16(x@Wgate)); h stays on chip.
- * wt_ug64 is (2F,H) packed in 128-row tiles [64 up rows | 64 gate rows]; wt_d is Wdown^T (H,F).  H must be 128. */
+ * wt_ug64 is (2F,H) packed in 128-row tiles [64 up rows | 64 gate rows]; wt_d is Wdown^T (H,F).  H must be 128.
+ * norm_scale (H) f32, when not NULL, applies RMSNorm(x; scale, eps) to the rows first (network.py:167: ffn_norm), so
+ * the caller passes the un-normalised residual stream as both x and residual. */
 int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const mpx_bf16* wt_d, const mpx_bf16* residual,
-                  mpx_bf16* out, int M, int H, int F, mpx_stream_t stream);
+                  mpx_bf16* out, int M, int H, int F, const float* norm_scale, float eps, mpx_stream_t stream);
 
 /* Whole value path of a rollout step in one kernel (network.py:321,335-341 + values.py:40-45):
  * value = sum softmax(f32(pv) @ Wvh + b_vh) * centers, pv = bf16(gelu(bf16(bf16(xf @ Wvm) + b_vm))),

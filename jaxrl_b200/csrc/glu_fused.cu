@@ -33,7 +33,13 @@ struct GluFusedParams {
   int M, F;
   const __nv_bfloat16* residual;
   __nv_bfloat16* out;
+  const float* norm_scale;        // (128) fp32: RMSNorm applied to the x tile in shared memory before MMA1; or null
+  float eps;
 };
+
+__device__ __forceinline__ void gf_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 __global__ void __launch_bounds__(GF_THREADS, 1)
 glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_x,
@@ -59,7 +65,9 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
   uint64_t* d_empty = x_full + 11;
   uint64_t* part_full = x_full + 12;          // all partials of the cluster written (remote arrivals)
   uint64_t* part_empty = x_full + 13;         // all readers of MY partial done (remote arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 14);
+  uint64_t* xn_ready = x_full + 14;           // x tile landed and (optionally) normalised in place
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 15);
+  float* sSq = reinterpret_cast<float*>(x_full + 16);   // 2 x 128 partial sums of squares (RMSNorm prologue)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ncta = (int)cluster_nctarank(), krank = (int)cluster_ctarank();
@@ -87,6 +95,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
     mbar_init(d_empty, GF_EPI_WARPS);
     mbar_init(part_full, GF_EPI_WARPS * ncta);
     mbar_init(part_empty, GF_EPI_WARPS * ncta);
+    mbar_init(xn_ready, GF_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -175,7 +184,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         if (last) umma_commit(d_full);
       };
       for (int tile = blockIdx.y; tile < m_tiles; tile += gridDim.y) {
-        mbar_wait(x_full, xphase);
+        mbar_wait(xn_ready, xphase);
         xphase ^= 1;
         mbar_wait(d_empty, dphase ^ 1);       // previous tile's output accumulator has been drained
         dphase ^= 1;
@@ -193,13 +202,49 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
     const int half = (warp - 2) >> 2;                        // which 32 of the chunk's 64 hidden columns
     const int r = quarter * 32 + lane;                       // row within the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    uint32_t ug_ph[2] = {0, 0}, h_ph[2] = {0, 0}, dphase = 0, pf_phase = 0, pe_phase = 0;
+    uint32_t ug_ph[2] = {0, 0}, h_ph[2] = {0, 0}, dphase = 0, pf_phase = 0, pe_phase = 0, xphase = 0;
     // output columns this thread finishes: single CTA -> its half of the row; cluster -> its half of the CTA's slice
     const int slice = 128 / ncta;                            // 128, 64 or 32 columns per CTA
     const int ocol0 = krank * slice + half * (slice / 2);
     const int ncol4 = slice / 8;                             // float4 groups (of 4 columns) per thread: 16, 8 or 4
     for (int tile = blockIdx.y; tile < m_tiles; tile += gridDim.y) {
       const long long row = (long long)tile * 128 + r;
+      // ---- optional RMSNorm of the x tile, in place in the swizzled layout (this warp: K block `half` of its rows)
+      mbar_wait(x_full, xphase);
+      xphase ^= 1;
+      if (p.norm_scale) {
+        uint8_t* xrow = sX + half * 16384 + r * 128;
+        uint4 xv[8];
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          xv[c] = *reinterpret_cast<const uint4*>(xrow + ((c ^ (r & 7)) << 4));
+          const uint32_t w4[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = bf16_lo(w4[e]), bb = bf16_hi(w4[e]);
+            ss += a * a + bb * bb;
+          }
+        }
+        sSq[half * 128 + r] = ss;
+        gf_bar_sync(1, GF_EPI_WARPS * 32);
+        const float inv = rsqrtf((sSq[r] + sSq[128 + r]) * (1.0f / 128.0f) + p.eps);
+        const float4* sc4 = reinterpret_cast<const float4*>(p.norm_scale + half * 64);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1];
+          uint4 o;
+          o.x = pack_bf16(bf16_lo(xv[c].x) * inv * s0.x, bf16_hi(xv[c].x) * inv * s0.y);
+          o.y = pack_bf16(bf16_lo(xv[c].y) * inv * s0.z, bf16_hi(xv[c].y) * inv * s0.w);
+          o.z = pack_bf16(bf16_lo(xv[c].z) * inv * s1.x, bf16_hi(xv[c].z) * inv * s1.y);
+          o.w = pack_bf16(bf16_lo(xv[c].w) * inv * s1.z, bf16_hi(xv[c].w) * inv * s1.w);
+          *reinterpret_cast<uint4*>(xrow + ((c ^ (r & 7)) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        gf_bar_sync(1, GF_EPI_WARPS * 32);                     // sSq may be rewritten by the next tile
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(xn_ready);
       for (int c = 0; c < nchunks; ++c) {
         const int b = c & 1;
         mbar_wait(&ug_full[b], ug_ph[b]);
@@ -332,7 +377,8 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
 using namespace mpx;
 
 extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const mpx_bf16* wt_d, const mpx_bf16* residual,
-                             mpx_bf16* out, int M, int H, int F, mpx_stream_t stream) {
+                             mpx_bf16* out, int M, int H, int F, const float* norm_scale, float eps,
+                             mpx_stream_t stream) {
   MPX_REQUIRE(x && wt_ug64 && wt_d && residual && out && M > 0, "mpx_glu_fused: bad arguments");
   MPX_REQUIRE(H == 128, "mpx_glu_fused: hidden_features=%d unsupported (128 only; use mpx_glu_up + mpx_linear)", H);
   MPX_REQUIRE(F > 0 && F % 64 == 0, "mpx_glu_fused: F=%d must be a positive multiple of 64", F);
@@ -343,7 +389,7 @@ extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const m
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_wd, wt_d, H, F, F, 64, 128);
   if (rc) return rc;
-  const int smem = 1024 + 65536 + GF_STAGES * GF_STAGE_BYTES + GF_PART_BYTES + 256;
+  const int smem = 1024 + 65536 + GF_STAGES * GF_STAGE_BYTES + GF_PART_BYTES + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(glu_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -357,6 +403,9 @@ extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const m
   p.M = M; p.F = F;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.norm_scale = norm_scale;
+  p.eps = eps;
+  MPX_REQUIRE(!norm_scale || (reinterpret_cast<uintptr_t>(norm_scale) & 15) == 0, "mpx_glu_fused: norm_scale must be 16-byte aligned");
   const int tiles = ceil_div(M, 128);
   const int nchunks = F / 64;
   // largest cluster (split of the hidden dimension) that still fits one wave

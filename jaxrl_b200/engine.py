@@ -319,10 +319,11 @@ class PolicyEngine:
             ops.attn_decode(ws.q, ws.kcache[i], ws.vcache[i], pos, self.Nq, self.Nkv, self.D, out=ws.ao)
             ops.linear(ws.ao, w[pre + "wt_o"], residual=x, out=other)
             x, other = other, x
-            ops.rmsnorm_fwd(x, p[pre + "ffn_norm.scale"], out=ws.xn)
-            if self.fused_glu:
-                ops.glu_fused(ws.xn, w[pre + "wt_ug64"], w[pre + "wt_d"], x, other, self.F)
+            if self.fused_glu:                                # ffn_norm is applied inside the kernel
+                ops.glu_fused(x, w[pre + "wt_ug64"], w[pre + "wt_d"], x, other, self.F,
+                              norm_scale=p[pre + "ffn_norm.scale"])
             else:
+                ops.rmsnorm_fwd(x, p[pre + "ffn_norm.scale"], out=ws.xn)
                 ops.glu_up(ws.xn, w[pre + "wt_ug"], self.F, h=ws.h)
                 ops.linear(ws.h, w[pre + "wt_d"], residual=x, out=other)
             x, other = other, x

@@ -402,9 +402,10 @@ def test_transpose_tb(ops):
     assert torch.equal(fd.cpu(), f.t())
 
 
+@pytest.mark.parametrize("norm", [False, True])
 @pytest.mark.parametrize("M,F,cluster", [(77, 768, 0), (4096, 768, 0), (4096, 768, 1), (4096, 768, 2), (1000, 512, 4),
                                          (5000, 768, 4), (20000, 768, 0), (20000, 640, 2), (300, 192, 0)])
-def test_glu_fused(ops, M, F, cluster):
+def test_glu_fused(ops, M, F, cluster, norm):
     """Fused GLU block + residual (h stays on chip) vs the oracle GLUBlock; every cluster split of the hidden
     dimension (partials summed over distributed shared memory) and the persistent multi-tile loop."""
     from jaxrl_b200._lib import lib
@@ -416,11 +417,14 @@ def test_glu_fused(ops, M, F, cluster):
     wg = torch.randn(K, F, generator=gen) / math.sqrt(K)
     wd = torch.randn(F, K, generator=gen) / math.sqrt(F)
     pdict = {"f.up_proj.kernel": wu, "f.up_gate.kernel": wg, "f.down_proj.kernel": wd}
-    ref = (O.glu_block(pdict, "f.", x).float() + res.float()).to(BF16)
+    scale = 1.0 + 0.1 * torch.randn(K, generator=gen)
+    xin = O.rms_norm(x, scale) if norm else x
+    ref = (O.glu_block(pdict, "f.", xin).float() + res.float()).to(BF16)
     out = torch.empty(M, K, dtype=BF16, device=DEV)
     lib.mpx_debug_set(3, cluster)
     try:
-        ops.glu_fused(x.to(DEV), ops.pack_glu_weight64(wu, wg).to(DEV), wd.t().contiguous().to(BF16).to(DEV), res.to(DEV), out, F)
+        ops.glu_fused(x.to(DEV), ops.pack_glu_weight64(wu, wg).to(DEV), wd.t().contiguous().to(BF16).to(DEV), res.to(DEV), out, F,
+                      norm_scale=scale.to(DEV) if norm else None)
         torch.cuda.synchronize()
     finally:
         lib.mpx_debug_set(3, 0)
