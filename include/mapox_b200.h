@@ -235,16 +235,20 @@ int mpx_embed_bwd(const mpx_bf16* dx, const float* reward, const int32_t* last_a
                   int A, int n_tasks, float* d_w_reward, float* d_b_reward, float* d_action_table,
                   float* d_task_table, long long M, int H, mpx_stream_t stream);
 /* Rollout-step observation encoder + input embedding in one kernel (observation.py:84-96 + network.py:303-309) for the
- * standard geometry: (M,11,11,K) uint8 view, one-hot sizes[K] (sum <= 20), conv 3x3/2 -> 16, gelu, conv 3x3/1 -> 32, gelu,
- * conv 3x3/1 -> H = 128, then x = obs_emb + reward_encoder(reward) + embed(last_action) (+ embed(task)).
- * w1 (9*C,16) bf16 rows = (tap, one-hot channel); wt2 (32,144) and wt3 (128,288) are the transposed kernels with
- * K index = tap*cin + c (the layouts mpx_prep_weights produces for mpx_linear); biases bf16; embedding tables fp32 as
- * in mpx_embed_combine.  obs_emb (M,H) is an optional copy of the encoder output before the embedding sum. */
-int mpx_obs_embed_fused(const uint8_t* obs, const int* sizes, int K, const mpx_bf16* w1, const mpx_bf16* b1,
-                        const mpx_bf16* wt2, const mpx_bf16* b2, const mpx_bf16* wt3, const mpx_bf16* b3,
-                        const float* reward, const int32_t* last_action, const int32_t* task_ids, const float* w_reward,
-                        const float* b_reward, const float* action_table, int A, const float* task_table, int n_tasks,
-                        mpx_bf16* x, mpx_bf16* obs_emb, long long M, int IH, int IW, int H, mpx_stream_t stream);
+ * standard geometry: (M,11,11,K) uint8 view, one-hot sizes[K] with prod(sizes[k]+1) <= 48, conv 3x3/2 -> 16, gelu,
+ * conv 3x3/1 -> 32, gelu, conv 3x3/1 -> H = 128, then x = obs_emb + reward_encoder(reward) + embed(last_action)
+ * (+ embed(task)).  The kernel reads the encoder weights from an IMAGE (mpx_obs_fused_image_bytes() bytes, 16-byte
+ * aligned) that mpx_obs_fused_prep builds - once per weight update - from w1 (9*C,16) bf16 rows = (tap, one-hot
+ * channel), wt2 (32,144) and wt3 (128,288) (the transposed kernels, K index = tap*cin + c, as mpx_prep_weights lays
+ * them out for mpx_linear) and the bf16 biases.  Embedding tables are fp32 as in mpx_embed_combine.  obs_emb (M,H) is
+ * an optional copy of the encoder output before the embedding sum. */
+size_t mpx_obs_fused_image_bytes(void);
+int mpx_obs_fused_prep(const int* sizes, int K, const mpx_bf16* w1, const mpx_bf16* b1, const mpx_bf16* wt2,
+                       const mpx_bf16* b2, const mpx_bf16* wt3, const mpx_bf16* b3, void* image, mpx_stream_t stream);
+int mpx_obs_embed_fused(const uint8_t* obs, const int* sizes, int K, const void* image, const float* reward,
+                        const int32_t* last_action, const int32_t* task_ids, const float* w_reward, const float* b_reward,
+                        const float* action_table, int A, const float* task_table, int n_tasks, mpx_bf16* x,
+                        mpx_bf16* obs_emb, long long M, int IH, int IW, int H, mpx_stream_t stream);
 /* network.py:323-331: tied action logits f32(x) @ table^T (M,A) f32, masked entries = finfo(f32).min. A <= 32. */
 int mpx_policy_logits(const mpx_bf16* x, const float* table, const uint8_t* action_mask, float* logits, long long M,
                       int H, int A, mpx_stream_t stream);

@@ -105,8 +105,11 @@ lib.mpx_embed_bwd.argtypes = [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, 
 lib.mpx_policy_logits.argtypes = [c_p, c_p, c_p, c_p, c_ll, c_i, c_i, c_p]
 lib.mpx_policy_sample.argtypes = [c_p, c_p, c_p, c_p, c_ll, c_i, c_p]
 lib.mpx_gumbel_noise.argtypes = [c_p, c_ll, C.c_ulonglong, C.c_ulonglong, c_p, c_p]
-lib.mpx_obs_embed_fused.argtypes = [c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_i,
-                                    c_p, c_p, c_ll, c_i, c_i, c_i, c_p]
+lib.mpx_obs_fused_image_bytes.restype = C.c_size_t
+lib.mpx_obs_fused_image_bytes.argtypes = []
+lib.mpx_obs_fused_prep.argtypes = [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]
+lib.mpx_obs_embed_fused.argtypes = [c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_p, c_p, c_ll, c_i, c_i,
+                                    c_i, c_p]
 lib.mpx_policy_head_sample.argtypes = [c_p, c_p, C.c_float, c_p, c_p, c_p, C.c_ulonglong, C.c_ulonglong, c_p, c_p, c_p, c_p,
                                        c_p, c_ll, c_i, c_i, c_p]
 lib.mpx_ppo_policy_loss_workspace_bytes.restype = C.c_size_t

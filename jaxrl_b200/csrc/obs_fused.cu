@@ -12,7 +12,10 @@
 //          (px, agent) because consecutive px are consecutive q tiles; no im2col copy exists anywhere;
 //   conv3  the 3x3 map flattened is a Linear with K = 288: 18 tcgen05.mma (M128 N128 K16) on a2 (bias+gelu epilogue
 //          of conv2, written by the worker warps in core-matrix layout); only rows 0..31 of the tile are agents.
-// The weights are re-laid into core-matrix images in shared memory once per CTA with cp.async.
+// conv1's per-cell lookups use a JOINT table: one code per cell combines all K components (an extra code per component
+// stands for an out-of-range value = all-zero one-hot), so a 3x3 receptive field costs 9 lookups of a 16-channel fp32 row.
+// The joint table and the core-matrix images of W2 / W3 are built once per weight update by obs_fused_prep_kernel into
+// one contiguous device buffer, which each CTA pulls into shared memory with a single bulk copy.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -25,27 +28,26 @@ constexpr int OF_WORKERS = 8;          // worker warps
 constexpr int OF_THREADS = (OF_WORKERS + 1) * 32;
 constexpr int OF_IH = 11, OF_IW = 11, OF_P1 = 5, OF_C1 = 16, OF_C2 = 32, OF_H = 128;
 constexpr int OF_K3 = 9 * OF_C2;       // 288
-constexpr int OF_MAXC = 20;            // one-hot channels supported
 constexpr int OF_MAXK = 4;             // observation components per cell
 
 constexpr int OF_A1_BYTES = 26 * 1024;                 // 25 position tiles [32 agents x 16 ch] + 1 tile of slack
 constexpr int OF_A2_BYTES = 16 * (OF_K3 / 8) * 128;    // 128 rows x 576 B = 73728
 constexpr int OF_W3_BYTES = 16 * (OF_K3 / 8) * 128;    // 128 n x 576 B
 constexpr int OF_W2_BYTES = 9 * 1024;
-constexpr int OF_W1_BYTES = 9 * OF_MAXC * OF_C1 * 2;   // 5760
+constexpr int OF_MAXJ = 48;                            // joint one-hot codes per cell (product of (size_k + 1))
+constexpr int OF_T1_BYTES = 9 * OF_MAXJ * OF_C1 * 4;   // conv1 joint table, fp32: 27648
+constexpr int OF_BIAS_BYTES = 512;                     // b1[16] b2[32] b3[128] bf16
+constexpr int OF_IMG_BYTES = OF_W3_BYTES + OF_W2_BYTES + OF_T1_BYTES + OF_BIAS_BYTES;   // one bulk copy
 constexpr int OF_OBS_BYTES = OF_AG * OF_IH * OF_IW * OF_MAXK;   // 15488
-constexpr int OF_SMEM = OF_A1_BYTES + OF_A2_BYTES + OF_W3_BYTES + OF_W2_BYTES + OF_W1_BYTES + 512 + OF_OBS_BYTES + 128 + 1024;
+constexpr int OF_SMEM = OF_A1_BYTES + OF_A2_BYTES + OF_IMG_BYTES + OF_OBS_BYTES + 128 + 1024;
 
 struct ObsFusedParams {
   const uint8_t* obs;             // (M, 11, 11, K)
-  int K, C;                       // components per cell, total one-hot channels
-  int offs[OF_MAXK + 1];
-  const __nv_bfloat16* w1;        // (9*C, 16) bf16
-  const __nv_bfloat16* wt2;       // (32, 144) bf16, K index = tap*16 + cin
-  const __nv_bfloat16* wt3;       // (128, 288) bf16, K index = pos*32 + cin
-  const __nv_bfloat16* b1;
-  const __nv_bfloat16* b2;
-  const __nv_bfloat16* b3;
+  int K;                          // components per cell
+  int NJ;                         // joint codes per cell = prod(sizes[k] + 1)
+  int sizes[OF_MAXK];             // one-hot size per component
+  int radix[OF_MAXK];             // joint code = sum_k min(val_k, sizes[k]) * radix[k]
+  const uint8_t* image;           // OF_IMG_BYTES, built by obs_fused_prep_kernel
   const float* reward;            // (M)
   const int32_t* last_action;     // (M)
   const int32_t* task_ids;        // (M) or null
@@ -69,28 +71,66 @@ __device__ __forceinline__ uint64_t umma_smem_desc_nosw(uint32_t smem_addr, uint
   d |= (uint64_t)1 << 46;
   return d;                                                  // layout type 0: no swizzle
 }
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void of_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Image layout (bytes): [W3 core-matrix image 73728][W2 tap images 9216][conv1 joint table fp32 27648][biases bf16 512]
+//   W3: element (n, k) at (n/8)*4608 + (k/8)*128 + (n%8)*16 + (k%8)*2        (k = pos*32 + cin)
+//   W2: element (tap, n, c) at tap*1024 + (n/8)*256 + (c/8)*128 + (n%8)*16 + (c%8)*2
+//   T1: [tap][code][16] fp32 = sum over components k with digit_k < sizes[k] of W1[tap*C + off_k + digit_k][:]
+__global__ void __launch_bounds__(256) obs_fused_prep_kernel(const __nv_bfloat16* __restrict__ w1, const __nv_bfloat16* __restrict__ b1,
+                                                             const __nv_bfloat16* __restrict__ wt2, const __nv_bfloat16* __restrict__ b2,
+                                                             const __nv_bfloat16* __restrict__ wt3, const __nv_bfloat16* __restrict__ b3,
+                                                             ObsFusedParams p, uint8_t* __restrict__ image) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+  uint4* img4 = reinterpret_cast<uint4*>(image);
+  for (int i = tid; i < OF_H * (OF_K3 / 8); i += nthr) {                  // wt3 (128, 288): 16-byte piece (n, kk)
+    const int n = i / (OF_K3 / 8), kk = i % (OF_K3 / 8);
+    img4[((n >> 3) * ((OF_K3 / 8) * 128) + kk * 128 + (n & 7) * 16) >> 4] =
+        *reinterpret_cast<const uint4*>(wt3 + (long long)n * OF_K3 + kk * 8);
+  }
+  for (int i = tid; i < OF_C2 * 18; i += nthr) {                          // wt2 (32, 144): piece (n, kk), tap = kk / 2
+    const int n = i / 18, kk = i % 18;
+    img4[(OF_W3_BYTES + (kk >> 1) * 1024 + (n >> 3) * 256 + (kk & 1) * 128 + (n & 7) * 16) >> 4] =
+        *reinterpret_cast<const uint4*>(wt2 + n * 144 + kk * 8);
+  }
+  float* t1 = reinterpret_cast<float*>(image + OF_W3_BYTES + OF_W2_BYTES);
+  int C = 0;
+  for (int k = 0; k < p.K; ++k) C += p.sizes[k];
+  for (int i = tid; i < 9 * p.NJ * OF_C1; i += nthr) {
+    const int ch = i % OF_C1, code = (i / OF_C1) % p.NJ, tap = i / (OF_C1 * p.NJ);
+    float acc = 0.f;
+    int off = 0, rem = code;
+    for (int k = 0; k < p.K; ++k) {
+      const int digit = rem % (p.sizes[k] + 1);
+      rem /= (p.sizes[k] + 1);
+      if (digit < p.sizes[k]) acc += __bfloat162float(w1[(tap * C + off + digit) * OF_C1 + ch]);
+      off += p.sizes[k];
+    }
+    t1[i] = acc;
+  }
+  __nv_bfloat16* bb = reinterpret_cast<__nv_bfloat16*>(image + OF_W3_BYTES + OF_W2_BYTES + OF_T1_BYTES);
+  for (int i = tid; i < OF_C1 + OF_C2 + OF_H; i += nthr)
+    bb[i] = i < OF_C1 ? b1[i] : i < OF_C1 + OF_C2 ? b2[i - OF_C1] : b3[i - OF_C1 - OF_C2];
+}
 
 __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA1 = smem;
   uint8_t* sA2 = sA1 + OF_A1_BYTES;
-  uint8_t* sW3 = sA2 + OF_A2_BYTES;
+  uint8_t* sImg = sA2 + OF_A2_BYTES;
+  uint8_t* sW3 = sImg;
   uint8_t* sW2 = sW3 + OF_W3_BYTES;
-  uint8_t* sW1 = sW2 + OF_W2_BYTES;
-  __nv_bfloat16* sB = reinterpret_cast<__nv_bfloat16*>(sW1 + OF_W1_BYTES);     // b1[16] b2[32] b3[128]
-  uint8_t* sObs = reinterpret_cast<uint8_t*>(sB) + 512;
+  const float* sT1 = reinterpret_cast<const float*>(sW2 + OF_W2_BYTES);
+  const __nv_bfloat16* sB = reinterpret_cast<const __nv_bfloat16*>(sW2 + OF_W2_BYTES + OF_T1_BYTES);   // b1[16] b2[32] b3[128]
+  uint8_t* sObs = sImg + OF_IMG_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sObs + OF_OBS_BYTES);
   uint64_t* a1_ready = bars;
   uint64_t* c2_full = bars + 1;
   uint64_t* a2_ready = bars + 2;
   uint64_t* c3_full = bars + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* img_full = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
   float* sOut = reinterpret_cast<float*>(sA1);               // conv3 accumulator staging, aliases a1 (dead by then)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -103,27 +143,14 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
     mbar_init(c2_full, 1);
     mbar_init(a2_ready, OF_WORKERS);
     mbar_init(c3_full, 1);
+    mbar_init(img_full, 1);
     fence_barrier_init();
+    mbar_arrive_expect_tx(img_full, OF_IMG_BYTES);           // weights + tables: one bulk copy per CTA
+    bulk_load_1d(sImg, p.image, OF_IMG_BYTES, img_full);
   }
   if (warp == OF_WORKERS) {
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
-  }
-  // ---- weight images (once per CTA): 16-byte pieces of the K-major bf16 matrices -> core-matrix layout
-  {
-    const uint32_t w3 = smem_u32(sW3), w2 = smem_u32(sW2), w1 = smem_u32(sW1), sb = smem_u32(sB);
-    for (int i = tid; i < OF_H * (OF_K3 / 8); i += OF_THREADS) {          // wt3 (128, 288): piece (n, kk)
-      const int n = i / (OF_K3 / 8), kk = i % (OF_K3 / 8);
-      cp_async16(w3 + (n >> 3) * ((OF_K3 / 8) * 128) + kk * 128 + (n & 7) * 16, p.wt3 + (long long)n * OF_K3 + kk * 8);
-    }
-    for (int i = tid; i < OF_C2 * 18; i += OF_THREADS) {                  // wt2 (32, 144): piece (n, kk), tap = kk / 2
-      const int n = i / 18, kk = i % 18;
-      cp_async16(w2 + (kk >> 1) * 1024 + (n >> 3) * 256 + (kk & 1) * 128 + (n & 7) * 16, p.wt2 + n * 144 + kk * 8);
-    }
-    for (int i = tid; i < 9 * p.C * 2; i += OF_THREADS) cp_async16(w1 + i * 16, p.w1 + i * 8);
-    if (tid < 2) cp_async16(sb + tid * 16, p.b1 + tid * 8);
-    else if (tid < 6) cp_async16(sb + 32 + (tid - 2) * 16, p.b2 + (tid - 2) * 8);
-    else if (tid < 22) cp_async16(sb + 96 + (tid - 6) * 16, p.b3 + (tid - 6) * 8);
   }
   tc_fence_before();
   __syncthreads();
@@ -136,13 +163,11 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
 
   if (warp == OF_WORKERS) {
     // ================================ MMA issuer ================================
-    cp_async_wait_all();
-    fence_proxy_async_smem();
-    __syncwarp();
     if (lane == 0) {
       constexpr uint32_t idesc2 = umma_idesc_bf16(128, OF_C2, 0, 0);
       constexpr uint32_t idesc3 = umma_idesc_bf16(128, OF_H, 0, 0);
       uint32_t ph = 0;
+      mbar_wait(img_full, 0);
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         mbar_wait(a1_ready, ph);
         tc_fence_after();
@@ -182,45 +207,52 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
       {
         const int nbytes = nag * cell_bytes;
         const uint8_t* src = p.obs + m0 * cell_bytes;
-        if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
-          const int nw = nbytes >> 2;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+          const int nw = nbytes >> 4;
           for (int i = wtid; i < nw; i += OF_WORKERS * 32)
-            reinterpret_cast<uint32_t*>(sObs)[i] = reinterpret_cast<const uint32_t*>(src)[i];
-          for (int i = (nw << 2) + wtid; i < nbytes; i += OF_WORKERS * 32) sObs[i] = src[i];
+            reinterpret_cast<uint4*>(sObs)[i] = reinterpret_cast<const uint4*>(src)[i];
+          for (int i = (nw << 4) + wtid; i < nbytes; i += OF_WORKERS * 32) sObs[i] = src[i];
         } else {
           for (int i = wtid; i < nbytes; i += OF_WORKERS * 32) sObs[i] = src[i];
         }
       }
-      if (tile == blockIdx.x) cp_async_wait_all();          // this thread's share of the weight images has landed
+      if (tile == (int)blockIdx.x) mbar_wait(img_full, 0);   // tables and weights have landed
       of_bar_sync(1, OF_WORKERS * 32);
-      // ---- conv1: gather-sum over (tap, component), bias, gelu -> a1 in core-matrix layout
-      for (int t = wtid; t < OF_AG * 25 * 2; t += OF_WORKERS * 32) {
-        const int ag = t & 31, half = (t >> 5) & 1, q = t >> 6;
+      // ---- conv1: 9 joint-table lookups per (agent, output position), bias, gelu -> a1 in core-matrix layout
+      for (int t = wtid; t < OF_AG * 25; t += OF_WORKERS * 32) {
+        const int ag = t & 31, q = t >> 5;
         const int oy = q / OF_P1, ox = q % OF_P1;
-        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        const uint8_t* cell0 = sObs + ag * cell_bytes + ((oy * 2) * OF_IW + ox * 2) * p.K;
+        float acc[16];
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const uint8_t* cell = cell0 + ((tap / 3) * OF_IW + (tap % 3)) * p.K;
-          for (int kc = 0; kc < p.K; ++kc) {
-            const int val = cell[kc];
-            if (ag < nag && val < p.offs[kc + 1] - p.offs[kc]) {
-              const uint4 wv = *reinterpret_cast<const uint4*>(sW1 + ((tap * p.C + p.offs[kc] + val) * OF_C1 + half * 8) * 2);
-              acc[0] += bf16_lo(wv.x); acc[1] += bf16_hi(wv.x); acc[2] += bf16_lo(wv.y); acc[3] += bf16_hi(wv.y);
-              acc[4] += bf16_lo(wv.z); acc[5] += bf16_hi(wv.z); acc[6] += bf16_lo(wv.w); acc[7] += bf16_hi(wv.w);
+        for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+        const uint8_t* cell0 = sObs + ag * cell_bytes + ((oy * 2) * OF_IW + ox * 2) * p.K;
+        if (ag < nag) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint8_t* cell = cell0 + ((tap / 3) * OF_IW + (tap % 3)) * p.K;
+            int code = 0;
+            for (int kc = 0; kc < p.K; ++kc) code += min((int)cell[kc], p.sizes[kc]) * p.radix[kc];
+            const float4* row = reinterpret_cast<const float4*>(sT1 + (tap * p.NJ + code) * OF_C1);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const float4 w = row[v];
+              acc[4 * v] += w.x; acc[4 * v + 1] += w.y; acc[4 * v + 2] += w.z; acc[4 * v + 3] += w.w;
             }
           }
         }
-        const uint4 bv = *reinterpret_cast<const uint4*>(sB + half * 8);
-        const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-        uint32_t o[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t zw = pack_bf16(acc[2 * e], acc[2 * e + 1]);
-          const uint32_t zb = pack_bf16(bf16_lo(zw) + bf16_lo(bw[e]), bf16_hi(zw) + bf16_hi(bw[e]));
-          o[e] = pack_bf16(gelu_tanh(bf16_lo(zb)), gelu_tanh(bf16_hi(zb)));
+        for (int half = 0; half < 2; ++half) {
+          const uint4 bv = *reinterpret_cast<const uint4*>(sB + half * 8);
+          const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t zw = pack_bf16(acc[8 * half + 2 * e], acc[8 * half + 2 * e + 1]);
+            const uint32_t zb = pack_bf16(bf16_lo(zw) + bf16_lo(bw[e]), bf16_hi(zw) + bf16_hi(bw[e]));
+            o[e] = pack_bf16(gelu_tanh(bf16_lo(zb)), gelu_tanh(bf16_hi(zb)));
+          }
+          *reinterpret_cast<uint4*>(sA1 + q * 1024 + (ag >> 3) * 256 + half * 128 + (ag & 7) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
         }
-        *reinterpret_cast<uint4*>(sA1 + q * 1024 + (ag >> 3) * 256 + half * 128 + (ag & 7) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -345,33 +377,57 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
 
 using namespace mpx;
 
-extern "C" int mpx_obs_embed_fused(const uint8_t* obs, const int* sizes, int K, const mpx_bf16* w1, const mpx_bf16* b1,
-                                   const mpx_bf16* wt2, const mpx_bf16* b2, const mpx_bf16* wt3, const mpx_bf16* b3,
-                                   const float* reward, const int32_t* last_action, const int32_t* task_ids,
-                                   const float* w_reward, const float* b_reward, const float* action_table, int A,
-                                   const float* task_table, int n_tasks, mpx_bf16* x, mpx_bf16* obs_emb, long long M,
-                                   int IH, int IW, int H, mpx_stream_t stream) {
-  MPX_REQUIRE(obs && sizes && w1 && b1 && wt2 && b2 && wt3 && b3 && reward && last_action && w_reward && b_reward &&
-                  action_table && x && M > 0 && A > 0,
+static int of_fill_spec(ObsFusedParams& p, const int* sizes, int K) {
+  MPX_REQUIRE(sizes && K >= 1 && K <= OF_MAXK, "mpx_obs_embed_fused: K=%d components unsupported", K);
+  p.K = K;
+  int nj = 1;
+  for (int i = 0; i < OF_MAXK; ++i) {
+    p.sizes[i] = i < K ? sizes[i] : 0;
+    p.radix[i] = i < K ? nj : 0;
+    if (i < K) {
+      MPX_REQUIRE(sizes[i] > 0 && sizes[i] < 255, "mpx_obs_embed_fused: bad one-hot size %d", sizes[i]);
+      nj *= sizes[i] + 1;
+    }
+  }
+  MPX_REQUIRE(nj <= OF_MAXJ, "mpx_obs_embed_fused: %d joint one-hot codes per cell > %d (use the unfused encoder)", nj, OF_MAXJ);
+  p.NJ = nj;
+  return MPX_OK;
+}
+
+extern "C" size_t mpx_obs_fused_image_bytes(void) { return (size_t)OF_IMG_BYTES; }
+
+extern "C" int mpx_obs_fused_prep(const int* sizes, int K, const mpx_bf16* w1, const mpx_bf16* b1, const mpx_bf16* wt2,
+                                  const mpx_bf16* b2, const mpx_bf16* wt3, const mpx_bf16* b3, void* image,
+                                  mpx_stream_t stream) {
+  MPX_REQUIRE(w1 && b1 && wt2 && b2 && wt3 && b3 && image, "mpx_obs_fused_prep: null pointer");
+  MPX_REQUIRE((reinterpret_cast<uintptr_t>(image) & 15) == 0 && (reinterpret_cast<uintptr_t>(wt2) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(wt3) & 15) == 0,
+              "mpx_obs_fused_prep: image / wt2 / wt3 must be 16-byte aligned");
+  ObsFusedParams p = {};
+  int rc = of_fill_spec(p, sizes, K);
+  if (rc) return rc;
+  obs_fused_prep_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(w1), reinterpret_cast<const __nv_bfloat16*>(b1),
+      reinterpret_cast<const __nv_bfloat16*>(wt2), reinterpret_cast<const __nv_bfloat16*>(b2),
+      reinterpret_cast<const __nv_bfloat16*>(wt3), reinterpret_cast<const __nv_bfloat16*>(b3), p,
+      reinterpret_cast<uint8_t*>(image));
+  return check_launch("obs_fused_prep_kernel");
+}
+
+extern "C" int mpx_obs_embed_fused(const uint8_t* obs, const int* sizes, int K, const void* image, const float* reward,
+                                   const int32_t* last_action, const int32_t* task_ids, const float* w_reward,
+                                   const float* b_reward, const float* action_table, int A, const float* task_table,
+                                   int n_tasks, mpx_bf16* x, mpx_bf16* obs_emb, long long M, int IH, int IW, int H,
+                                   mpx_stream_t stream) {
+  MPX_REQUIRE(obs && image && reward && last_action && w_reward && b_reward && action_table && x && M > 0 && A > 0,
               "mpx_obs_embed_fused: bad arguments");
   MPX_REQUIRE(IH == OF_IH && IW == OF_IW && H == OF_H, "mpx_obs_embed_fused: only the 11x11 view / H=128 geometry is fused");
-  MPX_REQUIRE(K >= 1 && K <= OF_MAXK, "mpx_obs_embed_fused: K=%d components unsupported", K);
-  ObsFusedParams p;
-  p.obs = obs; p.K = K;
-  p.offs[0] = 0;
-  for (int i = 0; i < K; ++i) {
-    MPX_REQUIRE(sizes[i] > 0, "mpx_obs_embed_fused: bad one-hot size");
-    p.offs[i + 1] = p.offs[i] + sizes[i];
-  }
-  for (int i = K + 1; i <= OF_MAXK; ++i) p.offs[i] = p.offs[K];
-  p.C = p.offs[K];
-  MPX_REQUIRE(p.C <= OF_MAXC, "mpx_obs_embed_fused: %d one-hot channels > %d", p.C, OF_MAXC);
-  p.w1 = reinterpret_cast<const __nv_bfloat16*>(w1);
-  p.wt2 = reinterpret_cast<const __nv_bfloat16*>(wt2);
-  p.wt3 = reinterpret_cast<const __nv_bfloat16*>(wt3);
-  p.b1 = reinterpret_cast<const __nv_bfloat16*>(b1);
-  p.b2 = reinterpret_cast<const __nv_bfloat16*>(b2);
-  p.b3 = reinterpret_cast<const __nv_bfloat16*>(b3);
+  MPX_REQUIRE((reinterpret_cast<uintptr_t>(image) & 15) == 0, "mpx_obs_embed_fused: image must be 16-byte aligned");
+  ObsFusedParams p = {};
+  int rc = of_fill_spec(p, sizes, K);
+  if (rc) return rc;
+  p.obs = obs;
+  p.image = reinterpret_cast<const uint8_t*>(image);
   p.reward = reward; p.last_action = last_action; p.task_ids = task_ids;
   p.w_r = w_reward; p.b_r = b_reward; p.a_table = action_table; p.A = A;
   p.t_table = task_table; p.n_tasks = n_tasks;

@@ -76,8 +76,9 @@ class PolicyEngine:
         self.fused_obs = (H == 128 and tuple(cfg.obs_shape[:2]) == (11, 11) and len(self.conv) == 3
                           and all((c.kh, c.kw) == (3, 3) for c in self.conv)
                           and [(c.sh, c.sw) for c in self.conv] == [(2, 2), (1, 1), (1, 1)]
-                          and [c.cout for c in self.conv] == [16, 32, 128] and self.C0 <= 20
-                          and len(cfg.obs_max_value) <= 4)
+                          and [c.cout for c in self.conv] == [16, 32, 128] and len(cfg.obs_max_value) <= 4
+                          and math.prod(n + 1 for n in cfg.obs_max_value) <= 48)
+        self.obs_image = ops.obs_fused_image(self.dev) if self.fused_obs else None
         self._alloc_staged()
         self.stage_weights()
 
@@ -154,9 +155,18 @@ class PolicyEngine:
         self._desc_dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
         self._ndesc = len(descs)
 
-    def stage_weights(self):
-        """fp32 master params -> bf16 GEMM operand copies (one launch)."""
+    def stage_weights(self, rollout: bool = True):
+        """fp32 master params -> bf16 GEMM operand copies (one launch).  rollout=True also rebuilds the weight image of
+        the fused observation encoder, which only the rollout path reads (so once per update is enough)."""
         ops.prep_weights(self._desc_dev, self._ndesc)
+        if rollout:
+            self.stage_rollout_weights()
+
+    def stage_rollout_weights(self):
+        if self.fused_obs:
+            w = self.w
+            ops.obs_fused_prep(self.cfg.obs_max_value, w["w_c0"], w["b_c0"], w["wt_c1"], w["b_c1"], w["wt_c2"], w["b_c2"],
+                               self.obs_image)
 
     # ------------------------------------------------------------------------------------------ workspaces
     def _alloc_embed(self, ws, M: int, train: bool):
@@ -238,10 +248,10 @@ class PolicyEngine:
         if not train and self.fused_obs:          # rollout: encoder + embedding sum in one kernel, nothing saved
             t_table = p.views.get("task_embedder.embedding_table") if task_ids is not None else None
             c0 = self.conv[0]
-            return ops.obs_embed_fused(obs, cfg.obs_max_value, w["w_c0"], w["b_c0"], w["wt_c1"], w["b_c1"], w["wt_c2"],
-                                       w["b_c2"], reward, last_action, task_ids if t_table is not None else None,
-                                       p["reward_encoder.kernel"], p["reward_encoder.bias"],
-                                       p["action_embedder.embedding_table"], t_table, out, M, c0.ih, c0.iw)
+            return ops.obs_embed_fused(obs, cfg.obs_max_value, self.obs_image, reward, last_action,
+                                       task_ids if t_table is not None else None, p["reward_encoder.kernel"],
+                                       p["reward_encoder.bias"], p["action_embedder.embedding_table"], t_table, out, M,
+                                       c0.ih, c0.iw)
         prev = None
         for c in self.conv:
             last = c.j == n - 1

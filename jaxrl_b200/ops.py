@@ -418,17 +418,31 @@ def conv1_onehot_fwd(obs, w, bias, a_out, M: int, IH: int, IW: int, sizes: Seque
     return a_out
 
 
-def obs_embed_fused(obs, sizes: Sequence[int], w1, b1, wt2, b2, wt3, b3, reward, last_action, task_ids, w_r, b_r,
-                    a_table, t_table, out, M: int, IH: int, IW: int, obs_emb=None):
+def obs_fused_image(device) -> torch.Tensor:
+    """Device buffer for the fused observation encoder's weight image (see mpx_obs_fused_prep)."""
+    return torch.empty(lib.mpx_obs_fused_image_bytes(), dtype=torch.uint8, device=device)
+
+
+def obs_fused_prep(sizes: Sequence[int], w1, b1, wt2, b2, wt3, b3, image):
+    _req(w1, BF16, "w1"); _req(wt2, BF16, "wt2"); _req(wt3, BF16, "wt3"); _req(image, torch.uint8, "image")
+    K = len(sizes)
+    arr = (C.c_int * K)(*sizes)
+    check(lib.mpx_obs_fused_prep(arr, K, ptr(w1), ptr(b1), ptr(wt2), ptr(b2), ptr(wt3), ptr(b3), ptr(image), stream()),
+          "mpx_obs_fused_prep")
+    return image
+
+
+def obs_embed_fused(obs, sizes: Sequence[int], image, reward, last_action, task_ids, w_r, b_r, a_table, t_table, out,
+                    M: int, IH: int, IW: int, obs_emb=None):
     """Whole observation encoder + input embedding sum of a rollout step in one kernel (standard 11x11 geometry)."""
-    _req(out, BF16, "out"); _req(w1, BF16, "w1"); _req(wt2, BF16, "wt2"); _req(wt3, BF16, "wt3")
+    _req(out, BF16, "out"); _req(image, torch.uint8, "image")
     K = len(sizes)
     arr = (C.c_int * K)(*sizes)
     H = out.shape[-1]
-    check(lib.mpx_obs_embed_fused(ptr(obs), arr, K, ptr(w1), ptr(b1), ptr(wt2), ptr(b2), ptr(wt3), ptr(b3), ptr(reward),
-                                  ptr(last_action), ptr(task_ids), ptr(w_r), ptr(b_r), ptr(a_table), a_table.shape[0],
-                                  ptr(t_table), 0 if t_table is None else t_table.shape[0], ptr(out), ptr(obs_emb), M, IH,
-                                  IW, H, stream()), "mpx_obs_embed_fused")
+    check(lib.mpx_obs_embed_fused(ptr(obs), arr, K, ptr(image), ptr(reward), ptr(last_action), ptr(task_ids), ptr(w_r),
+                                  ptr(b_r), ptr(a_table), a_table.shape[0], ptr(t_table),
+                                  0 if t_table is None else t_table.shape[0], ptr(out), ptr(obs_emb), M, IH, IW, H,
+                                  stream()), "mpx_obs_embed_fused")
     return out
 
 

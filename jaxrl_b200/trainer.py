@@ -121,6 +121,7 @@ class PPOTrainer:
     # ------------------------------------------------------------------------------------------ rollout (evaluate)
     def _rollout_body(self):
         eng, r, env, T = self.engine, self.r, self.env, self.T
+        eng.stage_rollout_weights()                         # weights are fixed for the whole rollout
         for t in range(T):
             if self.e2e:                                    # host -> device copy of this step's inputs (timed)
                 r.obs_stage.copy_(env.obs_host[t], non_blocking=True)
@@ -188,7 +189,7 @@ class PPOTrainer:
                 ops.adamw_step(eng.p.flat, eng.p.grad, o.mu, o.nu, o.scratch, o.step, opt.learning_rate, total, opt.beta1,
                                opt.beta2, opt.eps, opt.weight_decay, opt.max_norm, grad_scale=gscale,
                                norm_out=o.norm, ws=o.ws)
-            eng.stage_weights()
+            eng.stage_weights(rollout=False)
 
     def _update_body(self):
         for i in range(self.hyp.minibatch_count):

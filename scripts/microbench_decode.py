@@ -18,6 +18,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--agents", type=int, default=4096)
 ap.add_argument("--pos", type=int, default=300)
 ap.add_argument("--reps", type=int, default=50)
+ap.add_argument("--only", default=None, help="substring: run matching variants 3x without graphs (for ncu) and exit")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 run = NAMED["return_2_layers"]
@@ -81,6 +82,13 @@ variants = {
     "decode_step (whole)": lambda: eng.decode_step(ws, obs, reward, la, pos, value_out=value,
                                                    sample=dict(action=act, log_prob=lp, seed=1, stream_id=2, want_logits=False)),
 }
+if args.only:
+    for name, fn in variants.items():
+        if args.only in name:
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+    sys.exit(0)
 out = {}
 for name, fn in variants.items():
     fn()

@@ -515,7 +515,7 @@ def test_policy_head_sample_fused(ops, M, H, A, norm):
     torch.testing.assert_close(lp2, lp3, rtol=1e-6, atol=1e-6)
 
 
-@pytest.mark.parametrize("M,sizes,tasks", [(32, (5, 5), 0), (4096, (5, 5), 0), (77, (3, 7, 2), 3), (9000, (5, 5), 0)])
+@pytest.mark.parametrize("M,sizes,tasks", [(32, (5, 5), 0), (4096, (5, 5), 0), (77, (3, 2, 2), 3), (9000, (5, 5), 0), (50, (6,), 0)])
 def test_obs_embed_fused(ops, M, sizes, tasks):
     """Fused observation encoder (one-hot conv gather + two tcgen05 convolutions on no-swizzle operands) + embedding sum
     vs the oracle obs_encoder / model_embed."""
@@ -551,8 +551,9 @@ def test_obs_embed_fused(ops, M, sizes, tasks):
     import os
     from jaxrl_b200._lib import lib
     lib.mpx_debug_set(5, int(os.environ.get("MPX_OBS_SWAP", "0")))      # bring-up knob (descriptor LBO/SBO order)
-    ops.obs_embed_fused(d(obs), sizes, w1, b(p["obs_encoder.layers.0.bias"]), wt2, b(p["obs_encoder.layers.1.bias"]), wt3,
-                        b(p["obs_encoder.layers.2.bias"]), d(reward), d(la), None if tk is None else d(tk),
+    image = ops.obs_fused_prep(sizes, w1, b(p["obs_encoder.layers.0.bias"]), wt2, b(p["obs_encoder.layers.1.bias"]), wt3,
+                               b(p["obs_encoder.layers.2.bias"]), ops.obs_fused_image(DEV))
+    ops.obs_embed_fused(d(obs), sizes, image, d(reward), d(la), None if tk is None else d(tk),
                         d(p["reward_encoder.kernel"].reshape(-1)), d(p["reward_encoder.bias"]),
                         d(p["action_embedder.embedding_table"]), d(p["task_embedder.embedding_table"]) if tasks else None,
                         out, M, 11, 11, obs_emb=emb)
