@@ -36,6 +36,9 @@ int mpx_version(void);
  * key 4: mpx_value_head_fused cluster size, same values.  key 5: swap LBO/SBO in mpx_obs_embed_fused's no-swizzle
  * UMMA descriptors (bring-up). */
 int mpx_debug_set(int key, int value);
+/* Bring-up aid: device buffer of >= 32 uint64 slots in which CTA 0 of the fused rollout kernels records %globaltimer at
+ * its phase boundaries (NULL switches it off, the default). */
+int mpx_debug_set_stamps(void* device_buffer);
 
 /* ---------------------------------------------------------------------------------------------- GAE
  * Rollout.calculate_advantage, mapox_trainer/rollout.py:128-167 (reverse lax.scan + global normalisation).

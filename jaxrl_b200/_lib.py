@@ -77,6 +77,7 @@ PrepDesc = _struct("mpx_prep_desc", [
 
 lib.mpx_last_error.restype = C.c_char_p
 lib.mpx_debug_set.argtypes = [c_i, c_i]
+lib.mpx_debug_set_stamps.argtypes = [c_p]
 lib.mpx_gae_workspace_bytes.restype = C.c_size_t
 lib.mpx_gae_workspace_bytes.argtypes = [c_i, c_i]
 lib.mpx_gae.argtypes = [c_p, c_p, c_p, c_i, c_i, C.c_double, C.c_double, c_p, c_p, c_p, c_p, c_p]

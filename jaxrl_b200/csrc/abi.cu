@@ -25,6 +25,7 @@ int num_sms() {
   return cached;
 }
 
+unsigned long long* g_dbg_stamps = nullptr;
 extern int g_debug_swap_lbo_sbo;
 extern int g_attn_decode_impl;
 extern int g_attn_train_impl;
@@ -36,6 +37,10 @@ extern int g_obs_fused_swap;
 
 extern "C" const char* mpx_last_error(void) { return mpx::g_err; }
 extern "C" int mpx_version(void) { return 100; }
+extern "C" int mpx_debug_set_stamps(void* device_buffer) {
+  mpx::g_dbg_stamps = reinterpret_cast<unsigned long long*>(device_buffer);
+  return MPX_OK;
+}
 extern "C" int mpx_debug_set(int key, int value) {
   if (key == 0) {
     mpx::g_debug_swap_lbo_sbo = value;

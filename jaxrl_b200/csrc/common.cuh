@@ -32,4 +32,17 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 int num_sms();   // abi.cu (cached cudaDevAttrMultiProcessorCount of the current device)
 
+// Bring-up aid: mpx_debug_set_stamps(ptr) hands the fused kernels a device buffer of 64-bit slots; CTA 0 then records
+// %globaltimer (ns) at its phase boundaries.  NULL (the default) compiles to one predicated-off branch per stamp.
+extern unsigned long long* g_dbg_stamps;
+#ifdef __CUDACC__
+__device__ __forceinline__ void dbg_stamp(unsigned long long* buf, int slot) {
+  if (buf) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    buf[slot] = t;
+  }
+}
+#endif
+
 }  // namespace mpx

@@ -35,6 +35,7 @@ struct GluFusedParams {
   __nv_bfloat16* out;
   const float* norm_scale;        // (128) fp32: RMSNorm applied to the x tile in shared memory before MMA1; or null
   float eps;
+  unsigned long long* dbg;
 };
 
 __device__ __forceinline__ void gf_bar_sync(int id, int nthreads) {
@@ -75,6 +76,8 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
   const int chunk0 = krank * nchunks;
   const int m_tiles = (p.M + 127) / 128;
 
+  unsigned long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) ? p.dbg : nullptr;   // warp 2 lane 0
+  dbg_stamp(dbg, 0);
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_wug);
@@ -106,6 +109,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
   __syncthreads();
   if (ncta > 1) cluster_sync_all();            // remote CTAs' barriers are initialised before anyone arrives on them
   tc_fence_after();
+  dbg_stamp(dbg, 1);
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tUG[2] = {tmem_base, tmem_base + 128};
   const uint32_t tD = tmem_base + 256;
@@ -212,6 +216,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
       // ---- optional RMSNorm of the x tile, in place in the swizzled layout (this warp: K block `half` of its rows)
       mbar_wait(x_full, xphase);
       xphase ^= 1;
+      dbg_stamp(dbg, 2);
       if (p.norm_scale) {
         uint8_t* xrow = sX + half * 16384 + r * 128;
         uint4 xv[8];
@@ -244,12 +249,14 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         gf_bar_sync(1, GF_EPI_WARPS * 32);                     // sSq may be rewritten by the next tile
       }
       __syncwarp();
+      dbg_stamp(dbg, 3);
       if (lane == 0) mbar_arrive(xn_ready);
       for (int c = 0; c < nchunks; ++c) {
         const int b = c & 1;
         mbar_wait(&ug_full[b], ug_ph[b]);
         ug_ph[b] ^= 1;
         tc_fence_after();
+        dbg_stamp(dbg, 4 + 2 * c);
         uint32_t u[32], g[32];
         tmem_ld_32x32(tUG[b] + lane_off + 32 * half, u);
         tmem_ld_32x32(tUG[b] + lane_off + 64 + 32 * half, g);
@@ -276,11 +283,13 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         }
         fence_proxy_async_smem();
         __syncwarp();
+        dbg_stamp(dbg, 5 + 2 * c);
         if (lane == 0) mbar_arrive(&h_full[b]);
       }
       mbar_wait(d_full, dphase);
       dphase ^= 1;
       tc_fence_after();
+      dbg_stamp(dbg, 20);
       if (ncta == 1) {
         // output: bf16(acc) + residual -> bf16, straight from TMEM
 #pragma unroll
@@ -334,8 +343,10 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
           for (int j = 0; j < ncta; ++j) mbar_arrive_cluster(mapa_u32(pf, j));
         }
         // 2. sum the CL partials of my column slice in CTA-rank order, add the residual, store
+        dbg_stamp(dbg, 21);
         mbar_wait_cluster(part_full, pf_phase);
         pf_phase ^= 1;
+        dbg_stamp(dbg, 22);
         const uint32_t sp = smem_u32(sP);
 #pragma unroll 1
         for (int i = 0; i < ncol4; i += 2) {                   // 8 output columns per iteration
@@ -359,6 +370,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
           }
         }
         __syncwarp();
+        dbg_stamp(dbg, 23);
         if (lane == 0) {
           const uint32_t pe = smem_u32(part_empty);
           for (int j = 0; j < ncta; ++j) mbar_arrive_cluster(mapa_u32(pe, j));
@@ -369,6 +381,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
   tc_fence_before();
   __syncthreads();
   if (ncta > 1) cluster_sync_all();            // nobody exits while a peer may still read its partial
+  dbg_stamp(dbg, 24);
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -405,6 +418,7 @@ extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const m
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.norm_scale = norm_scale;
   p.eps = eps;
+  p.dbg = g_dbg_stamps;
   MPX_REQUIRE(!norm_scale || (reinterpret_cast<uintptr_t>(norm_scale) & 15) == 0, "mpx_glu_fused: norm_scale must be 16-byte aligned");
   const int tiles = ceil_div(M, 128);
   const int nchunks = F / 64;

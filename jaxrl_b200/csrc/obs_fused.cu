@@ -61,6 +61,7 @@ struct ObsFusedParams {
   __nv_bfloat16* obs_emb;         // (M, H) or null: conv3 output before the embedding sum (tests)
   long long M;
   int swap;
+  unsigned long long* dbg;
 };
 
 __device__ __forceinline__ uint64_t umma_smem_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -138,6 +139,8 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
   const int n_tiles = (int)((p.M + OF_AG - 1) / OF_AG);
   const int cell_bytes = OF_IH * OF_IW * p.K;
 
+  unsigned long long* dbg = (blockIdx.x == 0 && tid == 0) ? p.dbg : nullptr;
+  dbg_stamp(dbg, 0);
   if (tid == 0) {
     mbar_init(a1_ready, OF_WORKERS);
     mbar_init(c2_full, 1);
@@ -155,6 +158,7 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  dbg_stamp(dbg, 1);
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tD2 = tmem_base;            // 3 x 32 columns
   const uint32_t tD3 = tmem_base + 128;      // 128 columns
@@ -216,8 +220,10 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
           for (int i = wtid; i < nbytes; i += OF_WORKERS * 32) sObs[i] = src[i];
         }
       }
+      dbg_stamp(dbg, 2);
       if (tile == (int)blockIdx.x) mbar_wait(img_full, 0);   // tables and weights have landed
       of_bar_sync(1, OF_WORKERS * 32);
+      dbg_stamp(dbg, 3);
       // ---- conv1: 9 joint-table lookups per (agent, output position), bias, gelu -> a1 in core-matrix layout
       for (int t = wtid; t < OF_AG * 25; t += OF_WORKERS * 32) {
         const int ag = t & 31, q = t >> 5;
@@ -256,10 +262,12 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
       }
       fence_proxy_async_smem();
       __syncwarp();
+      dbg_stamp(dbg, 4);
       if (lane == 0) mbar_arrive(a1_ready);
       // ---- conv2 epilogue: rows (px = quarter, agent = lane), this warp's 16 of the 32 channels -> a2
       mbar_wait(c2_full, ph);
       tc_fence_after();
+      dbg_stamp(dbg, 5);
       if (quarter < 3) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
@@ -292,10 +300,12 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
+      dbg_stamp(dbg, 6);
       if (lane == 0) mbar_arrive(a2_ready);
       // ---- conv3 accumulator (TMEM lanes 0..31 = agents) -> fp32 staging
       mbar_wait(c3_full, ph);
       tc_fence_after();
+      dbg_stamp(dbg, 7);
       if (quarter == 0) {
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
@@ -311,6 +321,7 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
         tc_fence_before();
       }
       of_bar_sync(1, OF_WORKERS * 32);
+      dbg_stamp(dbg, 8);
       // ---- bias + embedding sum (network.py:303-309): thread = (agent, 16 columns)
       {
         const int ag = wtid >> 3, cg = wtid & 7;
@@ -365,6 +376,7 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
         }
       }
       of_bar_sync(1, OF_WORKERS * 32);                       // sOut (aliasing a1) and sObs are free for the next tile
+      dbg_stamp(dbg, 9);
       ph ^= 1;
     }
   }
@@ -435,6 +447,7 @@ extern "C" int mpx_obs_embed_fused(const uint8_t* obs, const int* sizes, int K, 
   p.obs_emb = reinterpret_cast<__nv_bfloat16*>(obs_emb);
   p.M = M;
   p.swap = g_obs_fused_swap;
+  p.dbg = g_dbg_stamps;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(obs_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OF_SMEM);

@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Phase timeline (CTA 0, %globaltimer) of the fused rollout kernels - bring-up aid, see mpx_debug_set_stamps."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from jaxrl_b200 import ops  # noqa: E402
+from jaxrl_b200._lib import lib  # noqa: E402
+from jaxrl_b200.config import NAMED  # noqa: E402
+from jaxrl_b200.engine import PolicyEngine  # noqa: E402
+
+dev = torch.device("cuda:0")
+cfg = NAMED["return_2_layers"].model
+eng = PolicyEngine(cfg, dev, seed=0)
+B = 4096
+ws = eng.alloc_decode(B)
+eng.reset_carry(ws)
+gen = torch.Generator(device=dev).manual_seed(0)
+vw, vh, K = cfg.obs_shape
+obs = torch.stack([torch.randint(0, n, (B, vw, vh), generator=gen, device=dev) for n in cfg.obs_max_value], -1).to(torch.uint8)
+reward = torch.randn(B, device=dev, generator=gen)
+la = torch.randint(0, cfg.action_dim, (B,), device=dev, generator=gen).to(torch.int32)
+x = torch.randn(B, eng.H, device=dev, generator=gen).to(torch.bfloat16)
+x2 = torch.empty_like(x)
+p, w = eng.p, eng.w
+pre = "layers.0."
+stamps = torch.zeros(64, dtype=torch.int64, device=dev)
+
+
+def timeline(name, fn, labels):
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    stamps.zero_()
+    lib.mpx_debug_set_stamps(stamps.data_ptr())
+    fn()
+    torch.cuda.synchronize()
+    lib.mpx_debug_set_stamps(None)
+    s = stamps.cpu().tolist()
+    t0 = s[0]
+    print(f"--- {name}")
+    for i, v in enumerate(s):
+        if v:
+            print(f"   slot {i:2d}  +{(v - t0) / 1e3:7.2f} us  {labels.get(i, '')}")
+
+
+timeline("obs_fused", lambda: eng._embed_fwd(ws, B, obs, reward, la, None, ws.xa, train=False),
+         {0: "start", 1: "setup done (barriers, tmem alloc)", 2: "obs tile in smem", 3: "image landed + sync", 4: "conv1 gather done",
+          5: "conv2 MMAs done", 6: "conv2 epilogue done", 7: "conv3 MMAs done", 8: "staging synced", 9: "embedding sum stored"})
+timeline("glu_fused (norm)", lambda: ops.glu_fused(x, w[pre + "wt_ug64"], w[pre + "wt_d"], x, x2, eng.F,
+                                                   norm_scale=p[pre + "ffn_norm.scale"]),
+         {0: "start", 1: "setup done (barriers, tmem, cluster sync)", 2: "x tile landed", 3: "norm done", 4: "ug0 ready", 5: "h0 written",
+          6: "ug1 ready", 7: "h1 written", 8: "ug2 ready", 9: "h2 written", 20: "D ready", 21: "partial staged", 22: "all partials in",
+          23: "output stored", 24: "exit sync"})
