@@ -69,6 +69,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
   uint64_t* xn_ready = x_full + 14;           // x tile landed and (optionally) normalised in place
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 15);
   float* sSq = reinterpret_cast<float*>(x_full + 16);   // 2 x 128 partial sums of squares (RMSNorm prologue)
+  float* sScale = sSq + 256;                            // norm scale (128)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ncta = (int)cluster_nctarank(), krank = (int)cluster_ctarank();
@@ -105,6 +106,8 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  if (p.norm_scale && threadIdx.x >= 64 && threadIdx.x < 96)
+    reinterpret_cast<float4*>(sScale)[threadIdx.x - 64] = reinterpret_cast<const float4*>(p.norm_scale)[threadIdx.x - 64];
   tc_fence_before();
   __syncthreads();
   if (ncta > 1) cluster_sync_all();            // remote CTAs' barriers are initialised before anyone arrives on them
@@ -218,12 +221,12 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
       xphase ^= 1;
       dbg_stamp(dbg, 2);
       if (p.norm_scale) {
-        uint8_t* xrow = sX + half * 16384 + r * 128;
+        const uint32_t xrow = smem_u32(sX + half * 16384 + r * 128);
         uint4 xv[8];
         float ss = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          xv[c] = *reinterpret_cast<const uint4*>(xrow + ((c ^ (r & 7)) << 4));
+          xv[c] = lds_v4(xrow + ((c ^ (r & 7)) << 4));
           const uint32_t w4[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -234,7 +237,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         sSq[half * 128 + r] = ss;
         gf_bar_sync(1, GF_EPI_WARPS * 32);
         const float inv = rsqrtf((sSq[r] + sSq[128 + r]) * (1.0f / 128.0f) + p.eps);
-        const float4* sc4 = reinterpret_cast<const float4*>(p.norm_scale + half * 64);
+        const float4* sc4 = reinterpret_cast<const float4*>(sScale + half * 64);      // same address for the whole warp
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1];
@@ -243,7 +246,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
           o.y = pack_bf16(bf16_lo(xv[c].y) * inv * s0.z, bf16_hi(xv[c].y) * inv * s0.w);
           o.z = pack_bf16(bf16_lo(xv[c].z) * inv * s1.x, bf16_hi(xv[c].z) * inv * s1.y);
           o.w = pack_bf16(bf16_lo(xv[c].w) * inv * s1.z, bf16_hi(xv[c].w) * inv * s1.w);
-          *reinterpret_cast<uint4*>(xrow + ((c ^ (r & 7)) << 4)) = o;
+          sts_v4(xrow + ((c ^ (r & 7)) << 4), o);
         }
         fence_proxy_async_smem();
         gf_bar_sync(1, GF_EPI_WARPS * 32);                     // sSq may be rewritten by the next tile
@@ -274,12 +277,11 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         }
         mbar_wait(&h_empty[b], h_ph[b] ^ 1);                   // MMA2 of chunk c-2 no longer reads this buffer
         h_ph[b] ^= 1;
-        uint8_t* hrow = sH + b * 16384 + r * 128;
+        const uint32_t hrow = smem_u32(sH + b * 16384 + r * 128);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int pc = 4 * half + i;
-          *reinterpret_cast<uint4*>(hrow + ((pc ^ (r & 7)) << 4)) =
-              make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+          sts_v4(hrow + ((pc ^ (r & 7)) << 4), make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]));
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -322,22 +324,28 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         // 1. stage my fp32 partial: [float4 column group c4][row] so that a warp touches 512 contiguous bytes
         mbar_wait_cluster(part_empty, pe_phase ^ 1);           // readers of the previous tile's partial are done
         pe_phase ^= 1;
-        float4* stage4 = reinterpret_cast<float4*>(sP);
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t acc[32];
-          tmem_ld_32x32(tD + lane_off + 64 * half + 32 * cc, acc);
+        const uint32_t stage = smem_u32(sP);
+        // residual of my output slice: in flight while the partials are exchanged
+        uint4 rres[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (ncta == 4 && row < p.M) {
+          rres[0] = *reinterpret_cast<const uint4*>(p.residual + row * 128 + ocol0);
+          rres[1] = *reinterpret_cast<const uint4*>(p.residual + row * 128 + ocol0 + 8);
+        }
+        {
+          uint32_t acc0[32], acc1[32];
+          tmem_ld_32x32(tD + lane_off + 64 * half, acc0);
+          tmem_ld_32x32(tD + lane_off + 64 * half + 32, acc1);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            stage4[(16 * half + 8 * cc + i) * 128 + r] =
-                make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]),
-                            __uint_as_float(acc[4 * i + 3]));
+          for (int i = 0; i < 8; ++i) {
+            sts_v4(stage + (uint32_t)((16 * half + i) * 128 + r) * 16u, make_uint4(acc0[4 * i], acc0[4 * i + 1], acc0[4 * i + 2], acc0[4 * i + 3]));
+            sts_v4(stage + (uint32_t)((16 * half + 8 + i) * 128 + r) * 16u, make_uint4(acc1[4 * i], acc1[4 * i + 1], acc1[4 * i + 2], acc1[4 * i + 3]));
+          }
         }
         tc_fence_before();
-        fence_acq_rel_cluster();
         __syncwarp();
         if (lane == 0) {
+          fence_acq_rel_cluster();                             // the warp's staged rows (ordered by the syncwarp) -> cluster scope
           mbar_arrive(d_empty);                                // TMEM accumulator drained
           const uint32_t pf = smem_u32(part_full);
           for (int j = 0; j < ncta; ++j) mbar_arrive_cluster(mapa_u32(pf, j));
@@ -348,19 +356,32 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         pf_phase ^= 1;
         dbg_stamp(dbg, 22);
         const uint32_t sp = smem_u32(sP);
-#pragma unroll 1
-        for (int i = 0; i < ncol4; i += 2) {                   // 8 output columns per iteration
-          float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+        uint32_t pbase[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pbase[j] = mapa_u32(sp, j < ncta ? j : 0);
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {                       // 8 output columns per iteration (ncol4 = 4 or 8)
+          if (i >= ncol4) break;
           const uint32_t off0 = (uint32_t)(((ocol0 >> 2) + i) * 128 + r) * 16u;
-          for (int j = 0; j < ncta; ++j) {
-            const uint32_t base = mapa_u32(sp, j);
-            const float4 a = ld_dsmem_f4(base + off0), bb = ld_dsmem_f4(base + off0 + 128 * 16);
-            s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
-            s1.x += bb.x; s1.y += bb.y; s1.z += bb.z; s1.w += bb.w;
+          float4 a[4], bb[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                        // all remote loads in flight before the first add
+            if (j < ncta) {
+              a[j] = ld_dsmem_f4(pbase[j] + off0);
+              bb[j] = ld_dsmem_f4(pbase[j] + off0 + 128 * 16);
+            }
+          }
+          float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < ncta) {
+              s0.x += a[j].x; s0.y += a[j].y; s0.z += a[j].z; s0.w += a[j].w;
+              s1.x += bb[j].x; s1.y += bb[j].y; s1.z += bb[j].z; s1.w += bb[j].w;
+            }
           }
           if (row < p.M) {
             const long long o = row * 128 + ocol0 + 4 * i;
-            const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + o);
+            const uint4 rv = (ncta == 4) ? rres[(i >> 1) & 1] : *reinterpret_cast<const uint4*>(p.residual + o);
             uint4 ov;
             ov.x = pack_bf16(bf16_round(s0.x) + bf16_lo(rv.x), bf16_round(s0.y) + bf16_hi(rv.x));
             ov.y = pack_bf16(bf16_round(s0.z) + bf16_lo(rv.y), bf16_round(s0.w) + bf16_hi(rv.y));
@@ -377,10 +398,12 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         }
       }
     }
+    // nobody exits while a peer may still read its partial: wait until every reader of MY last partial has signalled
+    // (cheaper than a full cluster barrier; peers' barriers I arrive on stay alive for the same reason)
+    if (ncta > 1) mbar_wait_cluster(part_empty, pe_phase ^ 1);
   }
   tc_fence_before();
   __syncthreads();
-  if (ncta > 1) cluster_sync_all();            // nobody exits while a peer may still read its partial
   dbg_stamp(dbg, 24);
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
@@ -402,7 +425,7 @@ extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const m
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_wd, wt_d, H, F, F, 64, 128);
   if (rc) return rc;
-  const int smem = 1024 + 65536 + GF_STAGES * GF_STAGE_BYTES + GF_PART_BYTES + 256 + 1024;
+  const int smem = 1024 + 65536 + GF_STAGES * GF_STAGE_BYTES + GF_PART_BYTES + 256 + 1024 + 512;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(glu_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -35,11 +35,18 @@ constexpr int OF_A2_BYTES = 16 * (OF_K3 / 8) * 128;    // 128 rows x 576 B = 737
 constexpr int OF_W3_BYTES = 16 * (OF_K3 / 8) * 128;    // 128 n x 576 B
 constexpr int OF_W2_BYTES = 9 * 1024;
 constexpr int OF_MAXJ = 48;                            // joint one-hot codes per cell (product of (size_k + 1))
-constexpr int OF_T1_BYTES = 9 * OF_MAXJ * OF_C1 * 4;   // conv1 joint table, fp32: 27648
+constexpr int OF_T1_BYTES = 9 * OF_MAXJ * 2 * OF_C1 * 4;   // conv1 joint table, fp32, two bank-disjoint copies: 55296
 constexpr int OF_BIAS_BYTES = 512;                     // b1[16] b2[32] b3[128] bf16
 constexpr int OF_IMG_BYTES = OF_W3_BYTES + OF_W2_BYTES + OF_T1_BYTES + OF_BIAS_BYTES;   // one bulk copy
 constexpr int OF_OBS_BYTES = OF_AG * OF_IH * OF_IW * OF_MAXK;   // 15488
-constexpr int OF_SMEM = OF_A1_BYTES + OF_A2_BYTES + OF_IMG_BYTES + OF_OBS_BYTES + 128 + 1024;
+constexpr int OF_CODE_BYTES = OF_AG * OF_IH * OF_IW;            // 3872: one joint code per cell
+// Only rows 0..31 of the conv3 A operand are agents; the other 96 rows of the M=128 MMA are don't-care, so a1, the
+// observation tile and the codes live inside that part of the a2 region (row groups 4..15).
+constexpr int OF_A1_OFF = 4 * (OF_K3 / 8) * 128;                // 18432
+constexpr int OF_OBS_OFF = OF_A1_OFF + OF_A1_BYTES;             // 45056
+constexpr int OF_CODE_OFF = OF_OBS_OFF + OF_OBS_BYTES;          // 60544
+static_assert(OF_CODE_OFF + OF_CODE_BYTES <= OF_A2_BYTES, "aliased buffers must fit in the unused a2 rows");
+constexpr int OF_SMEM = OF_A2_BYTES + OF_IMG_BYTES + 128 + 1024;
 
 struct ObsFusedParams {
   const uint8_t* obs;             // (M, 11, 11, K)
@@ -77,7 +84,8 @@ __device__ __forceinline__ void of_bar_sync(int id, int n) { asm volatile("bar.s
 // Image layout (bytes): [W3 core-matrix image 73728][W2 tap images 9216][conv1 joint table fp32 27648][biases bf16 512]
 //   W3: element (n, k) at (n/8)*4608 + (k/8)*128 + (n%8)*16 + (k%8)*2        (k = pos*32 + cin)
 //   W2: element (tap, n, c) at tap*1024 + (n/8)*256 + (c/8)*128 + (n%8)*16 + (c%8)*2
-//   T1: [tap][code][16] fp32 = sum over components k with digit_k < sizes[k] of W1[tap*C + off_k + digit_k][:]
+//   T1: [tap][code][copy 0|1][16] fp32 = sum over components k with digit_k < sizes[k] of W1[tap*C + off_k + digit_k][:]
+//       (row pitch 128 B: copy 0 sits in banks 0-15, copy 1 in banks 16-31, so two lookups never collide)
 __global__ void __launch_bounds__(256) obs_fused_prep_kernel(const __nv_bfloat16* __restrict__ w1, const __nv_bfloat16* __restrict__ b1,
                                                              const __nv_bfloat16* __restrict__ wt2, const __nv_bfloat16* __restrict__ b2,
                                                              const __nv_bfloat16* __restrict__ wt3, const __nv_bfloat16* __restrict__ b3,
@@ -107,7 +115,8 @@ __global__ void __launch_bounds__(256) obs_fused_prep_kernel(const __nv_bfloat16
       if (digit < p.sizes[k]) acc += __bfloat162float(w1[(tap * C + off + digit) * OF_C1 + ch]);
       off += p.sizes[k];
     }
-    t1[i] = acc;
+    t1[((tap * p.NJ + code) * 2) * OF_C1 + ch] = acc;
+    t1[((tap * p.NJ + code) * 2 + 1) * OF_C1 + ch] = acc;
   }
   __nv_bfloat16* bb = reinterpret_cast<__nv_bfloat16*>(image + OF_W3_BYTES + OF_W2_BYTES + OF_T1_BYTES);
   for (int i = tid; i < OF_C1 + OF_C2 + OF_H; i += nthr)
@@ -117,15 +126,16 @@ __global__ void __launch_bounds__(256) obs_fused_prep_kernel(const __nv_bfloat16
 __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA1 = smem;
-  uint8_t* sA2 = sA1 + OF_A1_BYTES;
+  uint8_t* sA2 = smem;
+  uint8_t* sA1 = sA2 + OF_A1_OFF;
   uint8_t* sImg = sA2 + OF_A2_BYTES;
   uint8_t* sW3 = sImg;
   uint8_t* sW2 = sW3 + OF_W3_BYTES;
   const float* sT1 = reinterpret_cast<const float*>(sW2 + OF_W2_BYTES);
   const __nv_bfloat16* sB = reinterpret_cast<const __nv_bfloat16*>(sW2 + OF_W2_BYTES + OF_T1_BYTES);   // b1[16] b2[32] b3[128]
-  uint8_t* sObs = sImg + OF_IMG_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sObs + OF_OBS_BYTES);
+  uint8_t* sObs = sA2 + OF_OBS_OFF;
+  uint8_t* sCode = sA2 + OF_CODE_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sImg + OF_IMG_BYTES);
   uint64_t* a1_ready = bars;
   uint64_t* c2_full = bars + 1;
   uint64_t* a2_ready = bars + 2;
@@ -204,9 +214,46 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const float sqH = bf16_round(sqrtf((float)OF_H));
     uint32_t ph = 0;
+    // embedding-sum role of this thread: (agent eag, columns [16*ecg, +16)); reward encoder weights are tile-invariant
+    const int eag = wtid >> 3, ecg = wtid & 7;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long m0 = (long long)tile * OF_AG;
       const int nag = (int)min((long long)OF_AG, p.M - m0);
+      // ---- this thread's embedding addends (network.py:304-309), in flight while the encoder runs
+      uint32_t re_w[8], ae_w[8], te_w[8];
+      {
+        const long long m = m0 + eag;
+        float rw = 0.f;
+        int a = -1, tk = -1;
+        if (eag < nag) {
+          rw = bf16_round(p.reward[m]);
+          a = p.last_action[m];
+          if (a < 0) a += p.A;
+          if (a >= p.A) a = -1;
+          if (p.task_ids && p.t_table) {
+            tk = p.task_ids[m];
+            if (tk < 0) tk += p.n_tasks;
+            if (tk >= p.n_tasks) tk = -1;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 av = make_float4(0.f, 0.f, 0.f, 0.f), tv = av;
+          if (a >= 0) av = reinterpret_cast<const float4*>(p.a_table + (long long)a * OF_H + ecg * 16)[i];
+          if (tk >= 0) tv = reinterpret_cast<const float4*>(p.t_table + (long long)tk * OF_H + ecg * 16)[i];
+          const float4 wv = reinterpret_cast<const float4*>(p.w_r + ecg * 16)[i], bq = reinterpret_cast<const float4*>(p.b_r + ecg * 16)[i];
+          const float avv[4] = {av.x, av.y, av.z, av.w}, tvv[4] = {tv.x, tv.y, tv.z, tv.w};
+          const float wr[4] = {bf16_round(wv.x), bf16_round(wv.y), bf16_round(wv.z), bf16_round(wv.w)};
+          const float br[4] = {bf16_round(bq.x), bf16_round(bq.y), bf16_round(bq.z), bf16_round(bq.w)};
+#pragma unroll
+          for (int e = 0; e < 4; e += 2) {
+            const int h = 4 * i + e;
+            re_w[h >> 1] = pack_bf16(bf16_round(rw * wr[e]) + br[e], bf16_round(rw * wr[e + 1]) + br[e + 1]);
+            ae_w[h >> 1] = pack_bf16(bf16_round(avv[e]) * sqH, bf16_round(avv[e + 1]) * sqH);
+            te_w[h >> 1] = pack_bf16(bf16_round(tvv[e]) * sqH, bf16_round(tvv[e + 1]) * sqH);
+          }
+        }
+      }
       // ---- observation tile -> smem (contiguous bytes)
       {
         const int nbytes = nag * cell_bytes;
@@ -220,44 +267,44 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
           for (int i = wtid; i < nbytes; i += OF_WORKERS * 32) sObs[i] = src[i];
         }
       }
+      of_bar_sync(1, OF_WORKERS * 32);
       dbg_stamp(dbg, 2);
+      // ---- one joint code per cell: sum_k min(value_k, size_k) * radix_k  (size_k = "out of range" digit)
+      for (int i = wtid; i < nag * OF_IH * OF_IW; i += OF_WORKERS * 32) {
+        const uint8_t* cell = sObs + i * p.K;
+        int code = 0;
+        for (int kc = 0; kc < p.K; ++kc) code += min((int)cell[kc], p.sizes[kc]) * p.radix[kc];
+        sCode[i] = (uint8_t)code;
+      }
       if (tile == (int)blockIdx.x) mbar_wait(img_full, 0);   // tables and weights have landed
       of_bar_sync(1, OF_WORKERS * 32);
       dbg_stamp(dbg, 3);
-      // ---- conv1: 9 joint-table lookups per (agent, output position), bias, gelu -> a1 in core-matrix layout
-      for (int t = wtid; t < OF_AG * 25; t += OF_WORKERS * 32) {
-        const int ag = t & 31, q = t >> 5;
-        const int oy = q / OF_P1, ox = q % OF_P1;
-        float acc[16];
+      // ---- conv1: lane = (task tsub of 8, channel quad v); 9 conflict-free float4 lookups per task
+      {
+        const int tsub = lane >> 2, v = lane & 3;
+        const float* tbase = sT1 + (tsub & 1) * OF_C1 + 4 * v;
+        const uint2 bv = *reinterpret_cast<const uint2*>(sB + 4 * v);
+        for (int g = warp; g < OF_AG * 25 / 8; g += OF_WORKERS) {
+          const int task = g * 8 + tsub;
+          const int ag = task & 31, q = task >> 5;
+          const int oy = q / OF_P1, ox = q % OF_P1;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ag < nag) {
+            const uint8_t* c0 = sCode + ag * (OF_IH * OF_IW) + (oy * 2) * OF_IW + ox * 2;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) acc[e] = 0.f;
-        const uint8_t* cell0 = sObs + ag * cell_bytes + ((oy * 2) * OF_IW + ox * 2) * p.K;
-        if (ag < nag) {
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint8_t* cell = cell0 + ((tap / 3) * OF_IW + (tap % 3)) * p.K;
-            int code = 0;
-            for (int kc = 0; kc < p.K; ++kc) code += min((int)cell[kc], p.sizes[kc]) * p.radix[kc];
-            const float4* row = reinterpret_cast<const float4*>(sT1 + (tap * p.NJ + code) * OF_C1);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              const float4 w = row[v];
-              acc[4 * v] += w.x; acc[4 * v + 1] += w.y; acc[4 * v + 2] += w.z; acc[4 * v + 3] += w.w;
+            for (int tap = 0; tap < 9; ++tap) {
+              const int code = c0[(tap / 3) * OF_IW + (tap % 3)];
+              const float4 w = *reinterpret_cast<const float4*>(tbase + (tap * p.NJ + code) * (2 * OF_C1));
+              acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
             }
           }
-        }
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint4 bv = *reinterpret_cast<const uint4*>(sB + half * 8);
-          const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-          uint32_t o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const uint32_t zw = pack_bf16(acc[8 * half + 2 * e], acc[8 * half + 2 * e + 1]);
-            const uint32_t zb = pack_bf16(bf16_lo(zw) + bf16_lo(bw[e]), bf16_hi(zw) + bf16_hi(bw[e]));
-            o[e] = pack_bf16(gelu_tanh(bf16_lo(zb)), gelu_tanh(bf16_hi(zb)));
-          }
-          *reinterpret_cast<uint4*>(sA1 + q * 1024 + (ag >> 3) * 256 + half * 128 + (ag & 7) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+          const uint32_t z0 = pack_bf16(acc.x, acc.y), z1 = pack_bf16(acc.z, acc.w);
+          const uint32_t y0 = pack_bf16(bf16_lo(z0) + bf16_lo(bv.x), bf16_hi(z0) + bf16_hi(bv.x));
+          const uint32_t y1 = pack_bf16(bf16_lo(z1) + bf16_lo(bv.y), bf16_hi(z1) + bf16_hi(bv.y));
+          uint2 o;
+          o.x = pack_bf16(gelu_tanh(bf16_lo(y0)), gelu_tanh(bf16_hi(y0)));
+          o.y = pack_bf16(gelu_tanh(bf16_lo(y1)), gelu_tanh(bf16_hi(y1)));
+          *reinterpret_cast<uint2*>(sA1 + q * 1024 + (ag >> 3) * 256 + (v >> 1) * 128 + (ag & 7) * 16 + (v & 1) * 8) = o;
         }
       }
       fence_proxy_async_smem();
@@ -322,57 +369,37 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
       }
       of_bar_sync(1, OF_WORKERS * 32);
       dbg_stamp(dbg, 8);
-      // ---- bias + embedding sum (network.py:303-309): thread = (agent, 16 columns)
-      {
-        const int ag = wtid >> 3, cg = wtid & 7;
-        const long long m = m0 + ag;
-        if (ag < nag) {
-          const float rw = bf16_round(p.reward[m]);
-          int a = p.last_action[m];
-          if (a < 0) a += p.A;
-          const bool a_ok = (a >= 0 && a < p.A);
-          int tk = -1;
+      // ---- bias + embedding sum (network.py:303-309): thread = (agent eag, 16 columns)
+      if (eag < nag) {
+        const long long m = m0 + eag;
+        uint32_t ow[8], ew[8];
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int c4 = ecg * 4 + i4;                         // float4 index within the row
+          const int blk = c4 >> 3, i = c4 & 7;                 // 32-column block, piece inside it (swizzled)
+          const float4 vq = *reinterpret_cast<const float4*>(sOut + eag * OF_H + blk * 32 + 4 * (i ^ (eag & 7)));
+          const uint2 b3 = *reinterpret_cast<const uint2*>(sB + 48 + c4 * 4);
+          const uint32_t c0 = pack_bf16(vq.x, vq.y), c1 = pack_bf16(vq.z, vq.w);              // conv3 output -> bf16
+          const uint32_t e0 = pack_bf16(bf16_lo(c0) + bf16_lo(b3.x), bf16_hi(c0) + bf16_hi(b3.x));   // + bias
+          const uint32_t e1 = pack_bf16(bf16_lo(c1) + bf16_lo(b3.y), bf16_hi(c1) + bf16_hi(b3.y));
+          ew[2 * i4] = e0; ew[2 * i4 + 1] = e1;
+          uint32_t x0 = pack_bf16(bf16_lo(e0) + bf16_lo(re_w[2 * i4]), bf16_hi(e0) + bf16_hi(re_w[2 * i4]));
+          uint32_t x1 = pack_bf16(bf16_lo(e1) + bf16_lo(re_w[2 * i4 + 1]), bf16_hi(e1) + bf16_hi(re_w[2 * i4 + 1]));
+          x0 = pack_bf16(bf16_lo(x0) + bf16_lo(ae_w[2 * i4]), bf16_hi(x0) + bf16_hi(ae_w[2 * i4]));
+          x1 = pack_bf16(bf16_lo(x1) + bf16_lo(ae_w[2 * i4 + 1]), bf16_hi(x1) + bf16_hi(ae_w[2 * i4 + 1]));
           if (p.task_ids && p.t_table) {
-            tk = p.task_ids[m];
-            if (tk < 0) tk += p.n_tasks;
-            if (tk >= p.n_tasks) tk = -1;
+            x0 = pack_bf16(bf16_lo(x0) + bf16_lo(te_w[2 * i4]), bf16_hi(x0) + bf16_hi(te_w[2 * i4]));
+            x1 = pack_bf16(bf16_lo(x1) + bf16_lo(te_w[2 * i4 + 1]), bf16_hi(x1) + bf16_hi(te_w[2 * i4 + 1]));
           }
-          uint32_t ow[8], ew[8];
-#pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const int c4 = cg * 4 + i4;                        // float4 index within the row
-            const int blk = c4 >> 3, i = c4 & 7;               // 32-column block, piece inside it (swizzled)
-            const float4 v = *reinterpret_cast<const float4*>(sOut + ag * OF_H + blk * 32 + 4 * (i ^ (ag & 7)));
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-            float res[4], emb[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int h = c4 * 4 + e;
-              const float oe = bf16_round(bf16_round(vv[e]) + __bfloat162float(sB[48 + h]));      // conv3 + bias
-              emb[e] = oe;
-              float re = bf16_round(rw * bf16_round(p.w_r[h]));
-              re = bf16_round(re + bf16_round(p.b_r[h]));
-              float ae = a_ok ? bf16_round(p.a_table[(long long)a * OF_H + h]) : 0.f;
-              ae = bf16_round(ae * sqH);
-              float x = bf16_round(oe + re);
-              x = bf16_round(x + ae);
-              if (p.task_ids && p.t_table) {
-                const float te = tk >= 0 ? bf16_round(p.t_table[(long long)tk * OF_H + h]) : 0.f;
-                x = bf16_round(x + bf16_round(te * sqH));
-              }
-              res[e] = x;
-            }
-            ow[2 * i4] = pack_bf16(res[0], res[1]); ow[2 * i4 + 1] = pack_bf16(res[2], res[3]);
-            ew[2 * i4] = pack_bf16(emb[0], emb[1]); ew[2 * i4 + 1] = pack_bf16(emb[2], emb[3]);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(p.x + m * OF_H + cg * 16);
-          dst[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-          dst[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
-          if (p.obs_emb) {
-            uint4* de = reinterpret_cast<uint4*>(p.obs_emb + m * OF_H + cg * 16);
-            de[0] = make_uint4(ew[0], ew[1], ew[2], ew[3]);
-            de[1] = make_uint4(ew[4], ew[5], ew[6], ew[7]);
-          }
+          ow[2 * i4] = x0; ow[2 * i4 + 1] = x1;
+        }
+        uint4* dst = reinterpret_cast<uint4*>(p.x + m * OF_H + ecg * 16);
+        dst[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        dst[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+        if (p.obs_emb) {
+          uint4* de = reinterpret_cast<uint4*>(p.obs_emb + m * OF_H + ecg * 16);
+          de[0] = make_uint4(ew[0], ew[1], ew[2], ew[3]);
+          de[1] = make_uint4(ew[4], ew[5], ew[6], ew[7]);
         }
       }
       of_bar_sync(1, OF_WORKERS * 32);                       // sOut (aliasing a1) and sObs are free for the next tile

@@ -35,6 +35,7 @@ struct ValueFusedParams {
   const float* centers;           // (NL)
   float* value;                   // (M)
   float* vlogits;                 // (M, NL) or null
+  unsigned long long* dbg;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -52,7 +53,10 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
   uint8_t* sP = sW + VF_STAGES * VF_STAGE_BYTES;   // 32 KB: fp32 partial logits [16 float4 columns][128 rows]
   uint8_t* sR = sP + 32768;                   // 8 KB: summed logits of one 32-row group [16 float4 columns][32 rows]
   float* sSq = reinterpret_cast<float*>(sR + 8192);   // 2 x 128 partial sums of squares (RMSNorm prologue)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sR + 8192 + 1024);
+  float* sScale = sSq + 256;                          // norm scale (128)
+  float* sBvh = sScale + 128;                         // value head bias (64)
+  float* sCen = sBvh + 64;                            // bin centres (64)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sR + 8192 + 2048);
   uint64_t* w_full = bars;                    // [VF_STAGES]
   uint64_t* w_empty = bars + VF_STAGES;       // [VF_STAGES]
   uint64_t* x_full = bars + 2 * VF_STAGES;
@@ -101,10 +105,21 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 192) {
+    const int i = threadIdx.x - 64;
+    if (p.norm_scale) sScale[i] = p.norm_scale[i];
+    if (i < 64) {
+      sBvh[i] = i < p.NL ? p.b_vh[i] : 0.f;
+      sCen[i] = i < p.NL ? p.centers[i] : 0.f;
+    }
+  }
+  unsigned long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) ? p.dbg : nullptr;   // warp 2 lane 0
+  dbg_stamp(dbg, 0);
   tc_fence_before();
   __syncthreads();
   if (ncta > 1) cluster_sync_all();
   tc_fence_after();
+  dbg_stamp(dbg, 1);
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tZ[2] = {tmem_base, tmem_base + 64};
   const uint32_t tD = tmem_base + 128;
@@ -210,13 +225,14 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
       // ---- RMSNorm prologue on the x tile, in place in the swizzled smem layout (this warp: K block `half`)
       mbar_wait(x_full, xphase);
       xphase ^= 1;
+      dbg_stamp(dbg, 2);
       if (p.norm_scale) {
-        uint8_t* xrow = sX + half * 16384 + r * 128;
+        const uint32_t xrow = smem_u32(sX + half * 16384 + r * 128);
         uint4 xv[8];
         float ss = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          xv[c] = *reinterpret_cast<const uint4*>(xrow + ((c ^ (r & 7)) << 4));
+          xv[c] = lds_v4(xrow + ((c ^ (r & 7)) << 4));
           const uint32_t w4[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -227,7 +243,7 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
         sSq[half * 128 + r] = ss;
         named_bar_sync(1, VF_EPI_WARPS * 32);
         const float inv = rsqrtf((sSq[r] + sSq[128 + r]) * (1.0f / 128.0f) + p.eps);
-        const float4* sc4 = reinterpret_cast<const float4*>(p.norm_scale + half * 64);
+        const float4* sc4 = reinterpret_cast<const float4*>(sScale + half * 64);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1];
@@ -236,12 +252,13 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
           o.y = pack_bf16(bf16_lo(xv[c].y) * inv * s0.z, bf16_hi(xv[c].y) * inv * s0.w);
           o.z = pack_bf16(bf16_lo(xv[c].z) * inv * s1.x, bf16_hi(xv[c].z) * inv * s1.y);
           o.w = pack_bf16(bf16_lo(xv[c].w) * inv * s1.z, bf16_hi(xv[c].w) * inv * s1.w);
-          *reinterpret_cast<uint4*>(xrow + ((c ^ (r & 7)) << 4)) = o;
+          sts_v4(xrow + ((c ^ (r & 7)) << 4), o);
         }
         fence_proxy_async_smem();
         named_bar_sync(1, VF_EPI_WARPS * 32);                 // sSq may be rewritten by the next tile
       }
       __syncwarp();
+      dbg_stamp(dbg, 3);
       if (lane == 0) mbar_arrive(xn_ready);
 
       // ---- value MLP chunks: bias + gelu on the MMA1 accumulator, bf16 tile for MMA2
@@ -250,6 +267,7 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
         mbar_wait(&z_full[b], z_ph[b]);
         z_ph[b] ^= 1;
         tc_fence_after();
+        dbg_stamp(dbg, 4 + 2 * c);
         uint32_t z[32];
         tmem_ld_32x32(tZ[b] + lane_off + 32 * half, z);
         const uint4* b4 = reinterpret_cast<const uint4*>(p.b_vm + (chunk0 + c) * 64 + 32 * half);
@@ -273,15 +291,15 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
         }
         mbar_wait(&h_empty[b], h_ph[b] ^ 1);
         h_ph[b] ^= 1;
-        uint8_t* hrow = sH + b * 16384 + r * 128;
+        const uint32_t hrow = smem_u32(sH + b * 16384 + r * 128);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int pc = 4 * half + i;
-          *reinterpret_cast<uint4*>(hrow + ((pc ^ (r & 7)) << 4)) =
-              make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+          sts_v4(hrow + ((pc ^ (r & 7)) << 4), make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]));
         }
         fence_proxy_async_smem();
         __syncwarp();
+        dbg_stamp(dbg, 5 + 2 * c);
         if (lane == 0) mbar_arrive(&h_full[b]);
       }
 
@@ -289,9 +307,10 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
       mbar_wait(d_full, dphase);
       dphase ^= 1;
       tc_fence_after();
+      dbg_stamp(dbg, 20);
       mbar_wait_cluster(part_empty, pe_phase ^ 1);
       pe_phase ^= 1;
-      float4* stage4 = reinterpret_cast<float4*>(sP);
+      const uint32_t stage = smem_u32(sP);
       {
         uint32_t hi[32], lo[32];
         tmem_ld_32x32(tD + lane_off + 32 * half, hi);
@@ -299,22 +318,24 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          stage4[(8 * half + i) * 128 + r] =
-              make_float4(__uint_as_float(hi[4 * i]) + __uint_as_float(lo[4 * i]),
-                          __uint_as_float(hi[4 * i + 1]) + __uint_as_float(lo[4 * i + 1]),
-                          __uint_as_float(hi[4 * i + 2]) + __uint_as_float(lo[4 * i + 2]),
-                          __uint_as_float(hi[4 * i + 3]) + __uint_as_float(lo[4 * i + 3]));
+          sts_v4(stage + (uint32_t)((8 * half + i) * 128 + r) * 16u,
+                 make_uint4(__float_as_uint(__uint_as_float(hi[4 * i]) + __uint_as_float(lo[4 * i])),
+                            __float_as_uint(__uint_as_float(hi[4 * i + 1]) + __uint_as_float(lo[4 * i + 1])),
+                            __float_as_uint(__uint_as_float(hi[4 * i + 2]) + __uint_as_float(lo[4 * i + 2])),
+                            __float_as_uint(__uint_as_float(hi[4 * i + 3]) + __uint_as_float(lo[4 * i + 3]))));
       }
       tc_fence_before();
-      fence_acq_rel_cluster();
       __syncwarp();
+      dbg_stamp(dbg, 21);
       if (lane == 0) {
+        fence_acq_rel_cluster();                             // the warp's staged rows (ordered by the syncwarp) -> cluster scope
         mbar_arrive(d_empty);
         const uint32_t pf = smem_u32(part_full);
         for (int j = 0; j < ncta; ++j) mbar_arrive_cluster(mapa_u32(pf, j));
       }
       mbar_wait_cluster(part_full, pf_phase);
       pf_phase ^= 1;
+      dbg_stamp(dbg, 22);
       // ---- this CTA finishes row groups [krank*4/ncta, (krank+1)*4/ncta) of the tile (32 rows each)
       const uint32_t sp = smem_u32(sP);
       float4* rbuf = reinterpret_cast<float4*>(sR);
@@ -323,17 +344,26 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
         const int rg = krank * groups + gi;
         // warp ew sums float4 columns 2*ew and 2*ew+1 over the cluster, lane = row of the group
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int c4 = 2 * ew + q;
-          float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-          const uint32_t off = (uint32_t)(c4 * 128 + rg * 32 + lane) * 16u;
-          for (int j = 0; j < ncta; ++j) {
-            const float4 a = ld_dsmem_f4(mapa_u32(sp, j) + off);
-            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        {
+          float4 a[2][4];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {                        // all remote loads in flight before the first add
+            const uint32_t off = (uint32_t)((2 * ew + q) * 128 + rg * 32 + lane) * 16u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < ncta) a[q][j] = ld_dsmem_f4(mapa_u32(sp, j) + off);
           }
-          rbuf[c4 * 32 + lane] = s;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < ncta) { s.x += a[q][j].x; s.y += a[q][j].y; s.z += a[q][j].z; s.w += a[q][j].w; }
+            rbuf[(2 * ew + q) * 32 + lane] = s;
+          }
         }
         named_bar_sync(1, VF_EPI_WARPS * 32);
+        dbg_stamp(dbg, 23);
         if (ew == (gi & 7)) {
           const long long row = (long long)tile * 128 + rg * 32 + lane;
           float m = -INFINITY;
@@ -346,7 +376,7 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
 #pragma unroll
           for (int j = 0; j < 64; ++j) {
             if (j < p.NL) {
-              lg[j] += p.b_vh[j];
+              lg[j] += sBvh[j];
               m = fmaxf(m, lg[j]);
             }
           }
@@ -354,9 +384,9 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
 #pragma unroll
           for (int j = 0; j < 64; ++j) {
             if (j < p.NL) {
-              const float e = expf(lg[j] - m);
+              const float e = __expf(lg[j] - m);
               s += e;
-              sc += e * p.centers[j];
+              sc += e * sCen[j];
             }
           }
           if (row < p.M) {
@@ -371,15 +401,18 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
         named_bar_sync(1, VF_EPI_WARPS * 32);
       }
       __syncwarp();
+      dbg_stamp(dbg, 24);
       if (lane == 0) {
         const uint32_t pe = smem_u32(part_empty);
         for (int j = 0; j < ncta; ++j) mbar_arrive_cluster(mapa_u32(pe, j));
       }
     }
+    // nobody exits while a peer may still read its partial (see glu_fused.cu)
+    if (ncta > 1) mbar_wait_cluster(part_empty, pe_phase ^ 1);
   }
   tc_fence_before();
   __syncthreads();
-  if (ncta > 1) cluster_sync_all();
+  dbg_stamp(dbg, 25);
   if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
@@ -404,7 +437,7 @@ extern "C" int mpx_value_head_fused(const mpx_bf16* x, const float* norm_scale, 
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_whl, wt_vh_hilo, 128, Vh, Vh, 64, 128);
   if (rc) return rc;
-  const int smem = 1024 + 65536 + VF_STAGES * VF_STAGE_BYTES + 32768 + 8192 + 1024 + 256;
+  const int smem = 1024 + 65536 + VF_STAGES * VF_STAGE_BYTES + 32768 + 8192 + 2048 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(value_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -423,6 +456,7 @@ extern "C" int mpx_value_head_fused(const mpx_bf16* x, const float* norm_scale, 
   p.centers = centers;
   p.value = value;
   p.vlogits = vlogits;
+  p.dbg = g_dbg_stamps;
   const int tiles = ceil_div(M, 128);
   const int nchunks = Vh / 64;
   int cl = 1;

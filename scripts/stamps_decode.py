@@ -47,10 +47,17 @@ def timeline(name, fn, labels):
 
 
 timeline("obs_fused", lambda: eng._embed_fwd(ws, B, obs, reward, la, None, ws.xa, train=False),
-         {0: "start", 1: "setup done (barriers, tmem alloc)", 2: "obs tile in smem", 3: "image landed + sync", 4: "conv1 gather done",
+         {0: "start", 1: "setup done (barriers, tmem alloc)", 2: "obs tile in smem", 3: "codes done, image landed", 4: "conv1 gather done",
           5: "conv2 MMAs done", 6: "conv2 epilogue done", 7: "conv3 MMAs done", 8: "staging synced", 9: "embedding sum stored"})
 timeline("glu_fused (norm)", lambda: ops.glu_fused(x, w[pre + "wt_ug64"], w[pre + "wt_d"], x, x2, eng.F,
                                                    norm_scale=p[pre + "ffn_norm.scale"]),
          {0: "start", 1: "setup done (barriers, tmem, cluster sync)", 2: "x tile landed", 3: "norm done", 4: "ug0 ready", 5: "h0 written",
           6: "ug1 ready", 7: "h1 written", 8: "ug2 ready", 9: "h2 written", 20: "D ready", 21: "partial staged", 22: "all partials in",
           23: "output stored", 24: "exit sync"})
+value = torch.empty(B, dtype=torch.float32, device=dev)
+timeline("value_head_fused (norm)", lambda: ops.value_head_fused(x, w["wt_vm"], w["b_vm"], w["wt_vh_hilo"], p["value_head.dense.bias"],
+                                                               eng.centers, value, vlogits=ws.vlogits,
+                                                               norm_scale=p["output_norm.scale"]),
+         {0: "start", 1: "setup done", 2: "x tile landed", 3: "norm done", 4: "z0 ready", 5: "h0 written", 6: "z1 ready", 7: "h1 written",
+          8: "z2 ready", 9: "h2 written", 20: "D ready", 21: "partial staged", 22: "all partials in", 23: "row group summed",
+          24: "values stored", 25: "exit"})
