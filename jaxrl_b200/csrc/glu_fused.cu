@@ -97,7 +97,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
     }
     mbar_init(d_full, 1);
     mbar_init(d_empty, GF_EPI_WARPS);
-    mbar_init(part_full, GF_EPI_WARPS * ncta);
+    mbar_init(part_full, 1);                   // one arrive.expect_tx per tile; the pushed bytes complete it
     mbar_init(part_empty, GF_EPI_WARPS * ncta);
     mbar_init(xn_ready, GF_EPI_WARPS);
     fence_barrier_init();
@@ -216,6 +216,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
     const int ncol4 = slice / 8;                             // float4 groups (of 4 columns) per thread: 16, 8 or 4
     for (int tile = blockIdx.y; tile < m_tiles; tile += gridDim.y) {
       const long long row = (long long)tile * 128 + r;
+      if (ncta > 1 && warp == 2 && lane == 0) mbar_arrive_expect_tx(part_full, GF_PART_BYTES);   // 128 rows x slice x 4 B x CL
       // ---- optional RMSNorm of the x tile, in place in the swizzled layout (this warp: K block `half` of its rows)
       mbar_wait(x_full, xphase);
       xphase ^= 1;
@@ -321,10 +322,14 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         __syncwarp();
         if (lane == 0) mbar_arrive(d_empty);
       } else {
-        // 1. stage my fp32 partial: [float4 column group c4][row] so that a warp touches 512 contiguous bytes
-        mbar_wait_cluster(part_empty, pe_phase ^ 1);           // readers of the previous tile's partial are done
+        // 1. PUSH my fp32 partial to its owners: CTA j finishes output columns [j*slice, (j+1)*slice) and receives, from
+        //    every CTA of the cluster, those columns into recv[src][c4 local][row] (st.async: the data itself completes
+        //    the owner's transaction barrier - no fences, no acknowledgement on the critical path)
+        const bool last_tile = tile + (int)gridDim.y >= m_tiles;
+        mbar_wait_cluster(part_empty, pe_phase ^ 1);           // owners have consumed the previous tile (multi-tile only)
         pe_phase ^= 1;
-        const uint32_t stage = smem_u32(sP);
+        const uint32_t sp = smem_u32(sP);
+        const int per_owner = slice / 4;                       // float4 column groups per owner: 8 (CL 4) or 16 (CL 2)
         // residual of my output slice: in flight while the partials are exchanged
         uint4 rres[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
         if (ncta == 4 && row < p.M) {
@@ -336,47 +341,36 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
           tmem_ld_32x32(tD + lane_off + 64 * half, acc0);
           tmem_ld_32x32(tD + lane_off + 64 * half + 32, acc1);
           tmem_ld_wait();
+          const uint32_t pf = smem_u32(part_full);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            sts_v4(stage + (uint32_t)((16 * half + i) * 128 + r) * 16u, make_uint4(acc0[4 * i], acc0[4 * i + 1], acc0[4 * i + 2], acc0[4 * i + 3]));
-            sts_v4(stage + (uint32_t)((16 * half + 8 + i) * 128 + r) * 16u, make_uint4(acc1[4 * i], acc1[4 * i + 1], acc1[4 * i + 2], acc1[4 * i + 3]));
+          for (int i = 0; i < 16; ++i) {
+            const int c4 = 16 * half + i;                      // float4 column group of the full 128-column row
+            const int owner = c4 / per_owner, c4l = c4 % per_owner;
+            const uint32_t dst = sp + (uint32_t)((krank * per_owner + c4l) * 128 + r) * 16u;
+            const uint32_t* a4 = (i < 8) ? &acc0[4 * i] : &acc1[4 * (i - 8)];
+            st_async_v4(mapa_u32(dst, owner), make_uint4(a4[0], a4[1], a4[2], a4[3]), mapa_u32(pf, owner));
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          fence_acq_rel_cluster();                             // the warp's staged rows (ordered by the syncwarp) -> cluster scope
-          mbar_arrive(d_empty);                                // TMEM accumulator drained
-          const uint32_t pf = smem_u32(part_full);
-          for (int j = 0; j < ncta; ++j) mbar_arrive_cluster(mapa_u32(pf, j));
-        }
-        // 2. sum the CL partials of my column slice in CTA-rank order, add the residual, store
+        if (lane == 0) mbar_arrive(d_empty);                   // TMEM accumulator drained
         dbg_stamp(dbg, 21);
+        // 2. all CL partials of my slice have landed in MY shared memory: sum in CTA-rank order, add the residual, store
         mbar_wait_cluster(part_full, pf_phase);
         pf_phase ^= 1;
         dbg_stamp(dbg, 22);
-        const uint32_t sp = smem_u32(sP);
-        uint32_t pbase[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pbase[j] = mapa_u32(sp, j < ncta ? j : 0);
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {                       // 8 output columns per iteration (ncol4 = 4 or 8)
           if (i >= ncol4) break;
-          const uint32_t off0 = (uint32_t)(((ocol0 >> 2) + i) * 128 + r) * 16u;
-          float4 a[4], bb[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {                        // all remote loads in flight before the first add
-            if (j < ncta) {
-              a[j] = ld_dsmem_f4(pbase[j] + off0);
-              bb[j] = ld_dsmem_f4(pbase[j] + off0 + 128 * 16);
-            }
-          }
+          const int c4l = half * ncol4 + i;                    // my first float4 group inside the slice
           float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             if (j < ncta) {
-              s0.x += a[j].x; s0.y += a[j].y; s0.z += a[j].z; s0.w += a[j].w;
-              s1.x += bb[j].x; s1.y += bb[j].y; s1.z += bb[j].z; s1.w += bb[j].w;
+              const uint4 a = lds_v4(sp + (uint32_t)((j * per_owner + c4l) * 128 + r) * 16u);
+              const uint4 bb = lds_v4(sp + (uint32_t)((j * per_owner + c4l + 1) * 128 + r) * 16u);
+              s0.x += __uint_as_float(a.x); s0.y += __uint_as_float(a.y); s0.z += __uint_as_float(a.z); s0.w += __uint_as_float(a.w);
+              s1.x += __uint_as_float(bb.x); s1.y += __uint_as_float(bb.y); s1.z += __uint_as_float(bb.z); s1.w += __uint_as_float(bb.w);
             }
           }
           if (row < p.M) {
@@ -392,15 +386,14 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         }
         __syncwarp();
         dbg_stamp(dbg, 23);
-        if (lane == 0) {
+        if (lane == 0 && !last_tile) {                         // my receive buffer may be overwritten by the next tile
           const uint32_t pe = smem_u32(part_empty);
           for (int j = 0; j < ncta; ++j) mbar_arrive_cluster(mapa_u32(pe, j));
         }
       }
     }
-    // nobody exits while a peer may still read its partial: wait until every reader of MY last partial has signalled
-    // (cheaper than a full cluster barrier; peers' barriers I arrive on stay alive for the same reason)
-    if (ncta > 1) mbar_wait_cluster(part_empty, pe_phase ^ 1);
+    // Exit protocol: a CTA leaves only after ITS receive barrier completed (all pushes into its shared memory have
+    // landed) and nobody signals part_empty after the last tile, so no peer touches an exited CTA.
   }
   tc_fence_before();
   __syncthreads();

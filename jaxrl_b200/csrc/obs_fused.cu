@@ -219,6 +219,19 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long m0 = (long long)tile * OF_AG;
       const int nag = (int)min((long long)OF_AG, p.M - m0);
+      // ---- observation tile -> smem (contiguous bytes)
+      {
+        const int nbytes = nag * cell_bytes;
+        const uint8_t* src = p.obs + m0 * cell_bytes;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+          const int nw = nbytes >> 4;
+          for (int i = wtid; i < nw; i += OF_WORKERS * 32)
+            reinterpret_cast<uint4*>(sObs)[i] = reinterpret_cast<const uint4*>(src)[i];
+          for (int i = (nw << 4) + wtid; i < nbytes; i += OF_WORKERS * 32) sObs[i] = src[i];
+        } else {
+          for (int i = wtid; i < nbytes; i += OF_WORKERS * 32) sObs[i] = src[i];
+        }
+      }
       // ---- this thread's embedding addends (network.py:304-309), in flight while the encoder runs
       uint32_t re_w[8], ae_w[8], te_w[8];
       {
@@ -254,27 +267,30 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
           }
         }
       }
-      // ---- observation tile -> smem (contiguous bytes)
-      {
-        const int nbytes = nag * cell_bytes;
-        const uint8_t* src = p.obs + m0 * cell_bytes;
-        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-          const int nw = nbytes >> 4;
-          for (int i = wtid; i < nw; i += OF_WORKERS * 32)
-            reinterpret_cast<uint4*>(sObs)[i] = reinterpret_cast<const uint4*>(src)[i];
-          for (int i = (nw << 4) + wtid; i < nbytes; i += OF_WORKERS * 32) sObs[i] = src[i];
-        } else {
-          for (int i = wtid; i < nbytes; i += OF_WORKERS * 32) sObs[i] = src[i];
-        }
-      }
       of_bar_sync(1, OF_WORKERS * 32);
       dbg_stamp(dbg, 2);
-      // ---- one joint code per cell: sum_k min(value_k, size_k) * radix_k  (size_k = "out of range" digit)
-      for (int i = wtid; i < nag * OF_IH * OF_IW; i += OF_WORKERS * 32) {
-        const uint8_t* cell = sObs + i * p.K;
-        int code = 0;
-        for (int kc = 0; kc < p.K; ++kc) code += min((int)cell[kc], p.sizes[kc]) * p.radix[kc];
-        sCode[i] = (uint8_t)code;
+      // ---- one joint code per cell: sum_k min(value_k, size_k) * radix_k  (size_k = "out of range" digit); 4 cells / thread
+      {
+        const int ncell = nag * OF_IH * OF_IW;
+        const int K = p.K;
+        const int s0 = p.sizes[0], s1 = p.sizes[1], s2 = p.sizes[2], s3 = p.sizes[3];
+        const int r1 = p.radix[1], r2 = p.radix[2], r3 = p.radix[3];
+        for (int i4 = wtid; i4 * 4 < ncell; i4 += OF_WORKERS * 32) {
+          uint32_t packed = 0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = i4 * 4 + e;
+            if (i < ncell) {
+              const uint8_t* cell = sObs + i * K;
+              int code = min((int)cell[0], s0);
+              if (K > 1) code += min((int)cell[1], s1) * r1;
+              if (K > 2) code += min((int)cell[2], s2) * r2;
+              if (K > 3) code += min((int)cell[3], s3) * r3;
+              packed |= (uint32_t)code << (8 * e);
+            }
+          }
+          reinterpret_cast<uint32_t*>(sCode)[i4] = packed;
+        }
       }
       if (tile == (int)blockIdx.x) mbar_wait(img_full, 0);   // tables and weights have landed
       of_bar_sync(1, OF_WORKERS * 32);
@@ -284,27 +300,40 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
         const int tsub = lane >> 2, v = lane & 3;
         const float* tbase = sT1 + (tsub & 1) * OF_C1 + 4 * v;
         const uint2 bv = *reinterpret_cast<const uint2*>(sB + 4 * v);
-        for (int g = warp; g < OF_AG * 25 / 8; g += OF_WORKERS) {
-          const int task = g * 8 + tsub;
-          const int ag = task & 31, q = task >> 5;
-          const int oy = q / OF_P1, ox = q % OF_P1;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ag < nag) {
-            const uint8_t* c0 = sCode + ag * (OF_IH * OF_IW) + (oy * 2) * OF_IW + ox * 2;
+        for (int g0 = warp; g0 < OF_AG * 25 / 8; g0 += 2 * OF_WORKERS) {      // two task groups in flight per iteration
+          float4 acc[2];
+          int agq[2][2];
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const int code = c0[(tap / 3) * OF_IW + (tap % 3)];
-              const float4 w = *reinterpret_cast<const float4*>(tbase + (tap * p.NJ + code) * (2 * OF_C1));
-              acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+          for (int u = 0; u < 2; ++u) {
+            const int g = g0 + u * OF_WORKERS;
+            const int task = g * 8 + tsub;
+            const int ag = task & 31, q = task >> 5;
+            agq[u][0] = ag; agq[u][1] = q;
+            acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g < OF_AG * 25 / 8 && ag < nag) {
+              const int oy = q / OF_P1, ox = q % OF_P1;
+              const uint8_t* c0 = sCode + ag * (OF_IH * OF_IW) + (oy * 2) * OF_IW + ox * 2;
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const int code = c0[(tap / 3) * OF_IW + (tap % 3)];
+                const float4 w = *reinterpret_cast<const float4*>(tbase + (tap * p.NJ + code) * (2 * OF_C1));
+                acc[u].x += w.x; acc[u].y += w.y; acc[u].z += w.z; acc[u].w += w.w;
+              }
             }
           }
-          const uint32_t z0 = pack_bf16(acc.x, acc.y), z1 = pack_bf16(acc.z, acc.w);
-          const uint32_t y0 = pack_bf16(bf16_lo(z0) + bf16_lo(bv.x), bf16_hi(z0) + bf16_hi(bv.x));
-          const uint32_t y1 = pack_bf16(bf16_lo(z1) + bf16_lo(bv.y), bf16_hi(z1) + bf16_hi(bv.y));
-          uint2 o;
-          o.x = pack_bf16(gelu_tanh(bf16_lo(y0)), gelu_tanh(bf16_hi(y0)));
-          o.y = pack_bf16(gelu_tanh(bf16_lo(y1)), gelu_tanh(bf16_hi(y1)));
-          *reinterpret_cast<uint2*>(sA1 + q * 1024 + (ag >> 3) * 256 + (v >> 1) * 128 + (ag & 7) * 16 + (v & 1) * 8) = o;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (g0 + u * OF_WORKERS < OF_AG * 25 / 8) {
+              const int ag = agq[u][0], q = agq[u][1];
+              const uint32_t z0 = pack_bf16(acc[u].x, acc[u].y), z1 = pack_bf16(acc[u].z, acc[u].w);
+              const uint32_t y0 = pack_bf16(bf16_lo(z0) + bf16_lo(bv.x), bf16_hi(z0) + bf16_hi(bv.x));
+              const uint32_t y1 = pack_bf16(bf16_lo(z1) + bf16_lo(bv.y), bf16_hi(z1) + bf16_hi(bv.y));
+              uint2 o;
+              o.x = pack_bf16(gelu_tanh(bf16_lo(y0)), gelu_tanh(bf16_hi(y0)));
+              o.y = pack_bf16(gelu_tanh(bf16_lo(y1)), gelu_tanh(bf16_hi(y1)));
+              *reinterpret_cast<uint2*>(sA1 + q * 1024 + (ag >> 3) * 256 + (v >> 1) * 128 + (ag & 7) * 16 + (v & 1) * 8) = o;
+            }
+          }
         }
       }
       fence_proxy_async_smem();

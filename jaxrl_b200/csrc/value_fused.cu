@@ -97,7 +97,7 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
     }
     mbar_init(d_full, 1);
     mbar_init(d_empty, VF_EPI_WARPS);
-    mbar_init(part_full, VF_EPI_WARPS * ncta);
+    mbar_init(part_full, 1);                   // one arrive.expect_tx per tile; the pushed bytes complete it
     mbar_init(part_empty, VF_EPI_WARPS * ncta);
     fence_barrier_init();
   }
@@ -222,6 +222,7 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     uint32_t z_ph[2] = {0, 0}, h_ph[2] = {0, 0}, dphase = 0, pf_phase = 0, pe_phase = 0, xphase = 0;
     for (int tile = blockIdx.y; tile < m_tiles; tile += gridDim.y) {
+      if (ew == 0 && lane == 0) mbar_arrive_expect_tx(part_full, 32768);   // CL x (128/CL) rows x 64 logits x 4 B
       // ---- RMSNorm prologue on the x tile, in place in the swizzled smem layout (this warp: K block `half`)
       mbar_wait(x_full, xphase);
       xphase ^= 1;
@@ -303,112 +304,107 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
         if (lane == 0) mbar_arrive(&h_full[b]);
       }
 
-      // ---- logits: stage hi + lo partial (fp32) for the cluster reduction
+      // ---- logits: PUSH the hi + lo partial (fp32) of each row to the CTA that finishes it (rows [j*R, (j+1)*R),
+      //      R = 128/CL), into recv[src][row][16 float4 columns, XOR-swizzled by row]; the data completes the owner's
+      //      transaction barrier (st.async), so no fence / acknowledgement sits on the critical path
       mbar_wait(d_full, dphase);
       dphase ^= 1;
       tc_fence_after();
       dbg_stamp(dbg, 20);
-      mbar_wait_cluster(part_empty, pe_phase ^ 1);
+      const bool last_tile = tile + (int)gridDim.y >= m_tiles;
+      mbar_wait_cluster(part_empty, pe_phase ^ 1);           // owners have consumed the previous tile (multi-tile only)
       pe_phase ^= 1;
-      const uint32_t stage = smem_u32(sP);
+      const uint32_t sp = smem_u32(sP);
+      const int R = 128 / ncta;                              // rows finished per CTA
       {
         uint32_t hi[32], lo[32];
         tmem_ld_32x32(tD + lane_off + 32 * half, hi);
         tmem_ld_32x32(tD + lane_off + 64 + 32 * half, lo);
         tmem_ld_wait();
+        const int owner = r / R, rl = r % R;
+        const uint32_t dst = mapa_u32(sp + (uint32_t)((krank * R + rl) * 16) * 16u, owner);
+        const uint32_t bar = mapa_u32(smem_u32(part_full), owner);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          sts_v4(stage + (uint32_t)((8 * half + i) * 128 + r) * 16u,
-                 make_uint4(__float_as_uint(__uint_as_float(hi[4 * i]) + __uint_as_float(lo[4 * i])),
-                            __float_as_uint(__uint_as_float(hi[4 * i + 1]) + __uint_as_float(lo[4 * i + 1])),
-                            __float_as_uint(__uint_as_float(hi[4 * i + 2]) + __uint_as_float(lo[4 * i + 2])),
-                            __float_as_uint(__uint_as_float(hi[4 * i + 3]) + __uint_as_float(lo[4 * i + 3]))));
+        for (int i = 0; i < 8; ++i) {
+          const int c4 = (8 * half + i) ^ ((rl & 7) << 1);
+          st_async_v4(dst + c4 * 16,
+                      make_uint4(__float_as_uint(__uint_as_float(hi[4 * i]) + __uint_as_float(lo[4 * i])),
+                                 __float_as_uint(__uint_as_float(hi[4 * i + 1]) + __uint_as_float(lo[4 * i + 1])),
+                                 __float_as_uint(__uint_as_float(hi[4 * i + 2]) + __uint_as_float(lo[4 * i + 2])),
+                                 __float_as_uint(__uint_as_float(hi[4 * i + 3]) + __uint_as_float(lo[4 * i + 3]))),
+                      bar);
+        }
       }
       tc_fence_before();
       __syncwarp();
       dbg_stamp(dbg, 21);
-      if (lane == 0) {
-        fence_acq_rel_cluster();                             // the warp's staged rows (ordered by the syncwarp) -> cluster scope
-        mbar_arrive(d_empty);
-        const uint32_t pf = smem_u32(part_full);
-        for (int j = 0; j < ncta; ++j) mbar_arrive_cluster(mapa_u32(pf, j));
-      }
+      if (lane == 0) mbar_arrive(d_empty);
       mbar_wait_cluster(part_full, pf_phase);
       pf_phase ^= 1;
       dbg_stamp(dbg, 22);
-      // ---- this CTA finishes row groups [krank*4/ncta, (krank+1)*4/ncta) of the tile (32 rows each)
-      const uint32_t sp = smem_u32(sP);
-      float4* rbuf = reinterpret_cast<float4*>(sR);
-      const int groups = 4 / ncta;
-      for (int gi = 0; gi < groups; ++gi) {
-        const int rg = krank * groups + gi;
-        // warp ew sums float4 columns 2*ew and 2*ew+1 over the cluster, lane = row of the group
+      // ---- my R rows: 8 lanes per row, lane `sub` owns logits [8*sub, 8*sub+8); bias, softmax, expectation
+      {
+        const int sub = lane & 7;
+        for (int rl = ew * 4 + (lane >> 3); rl < R; rl += VF_EPI_WARPS * 4) {
+          float lg[8];
+          {
+            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+            const int c4 = (2 * sub) ^ ((rl & 7) << 1);
 #pragma unroll
-        {
-          float4 a[2][4];
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {                        // all remote loads in flight before the first add
-            const uint32_t off = (uint32_t)((2 * ew + q) * 128 + rg * 32 + lane) * 16u;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j < ncta) a[q][j] = ld_dsmem_f4(mapa_u32(sp, j) + off);
+            for (int j = 0; j < 4; ++j) {
+              if (j < ncta) {
+                const uint4 a = lds_v4(sp + (uint32_t)((j * R + rl) * 16 + c4) * 16u);
+                const uint4 bq = lds_v4(sp + (uint32_t)((j * R + rl) * 16 + c4 + 1) * 16u);
+                s0.x += __uint_as_float(a.x); s0.y += __uint_as_float(a.y); s0.z += __uint_as_float(a.z); s0.w += __uint_as_float(a.w);
+                s1.x += __uint_as_float(bq.x); s1.y += __uint_as_float(bq.y); s1.z += __uint_as_float(bq.z); s1.w += __uint_as_float(bq.w);
+              }
+            }
+            lg[0] = s0.x; lg[1] = s0.y; lg[2] = s0.z; lg[3] = s0.w; lg[4] = s1.x; lg[5] = s1.y; lg[6] = s1.z; lg[7] = s1.w;
           }
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j < ncta) { s.x += a[q][j].x; s.y += a[q][j].y; s.z += a[q][j].z; s.w += a[q][j].w; }
-            rbuf[(2 * ew + q) * 32 + lane] = s;
-          }
-        }
-        named_bar_sync(1, VF_EPI_WARPS * 32);
-        dbg_stamp(dbg, 23);
-        if (ew == (gi & 7)) {
-          const long long row = (long long)tile * 128 + rg * 32 + lane;
           float m = -INFINITY;
-          float lg[64];
 #pragma unroll
-          for (int c4 = 0; c4 < 16; ++c4) {
-            const float4 v = rbuf[c4 * 32 + lane];
-            lg[4 * c4] = v.x; lg[4 * c4 + 1] = v.y; lg[4 * c4 + 2] = v.z; lg[4 * c4 + 3] = v.w;
+          for (int e = 0; e < 8; ++e) {
+            const int j = 8 * sub + e;
+            lg[e] = (j < p.NL) ? lg[e] + sBvh[j] : -INFINITY;
+            m = fmaxf(m, lg[e]);
           }
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+          float se = 0.f, sc = 0.f;
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
+          for (int e = 0; e < 8; ++e) {
+            const int j = 8 * sub + e;
             if (j < p.NL) {
-              lg[j] += sBvh[j];
-              m = fmaxf(m, lg[j]);
+              const float ex = __expf(lg[e] - m);
+              se += ex;
+              sc = fmaf(ex, sCen[j], sc);
             }
           }
-          float s = 0.f, sc = 0.f;
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            if (j < p.NL) {
-              const float e = __expf(lg[j] - m);
-              s += e;
-              sc += e * sCen[j];
-            }
+          for (int o = 1; o < 8; o <<= 1) {
+            se += __shfl_xor_sync(0xffffffffu, se, o);
+            sc += __shfl_xor_sync(0xffffffffu, sc, o);
           }
+          const long long row = (long long)tile * 128 + krank * R + rl;
           if (row < p.M) {
-            p.value[row] = sc / s;
+            if (sub == 0) p.value[row] = sc / se;
             if (p.vlogits) {
 #pragma unroll
-              for (int j = 0; j < 64; ++j)
-                if (j < p.NL) p.vlogits[row * p.NL + j] = lg[j];
+              for (int e = 0; e < 8; ++e)
+                if (8 * sub + e < p.NL) p.vlogits[row * p.NL + 8 * sub + e] = lg[e];
             }
           }
         }
-        named_bar_sync(1, VF_EPI_WARPS * 32);
       }
       __syncwarp();
       dbg_stamp(dbg, 24);
-      if (lane == 0) {
+      if (lane == 0 && !last_tile) {                         // my receive buffer may be overwritten by the next tile
         const uint32_t pe = smem_u32(part_empty);
         for (int j = 0; j < ncta; ++j) mbar_arrive_cluster(mapa_u32(pe, j));
       }
     }
-    // nobody exits while a peer may still read its partial (see glu_fused.cu)
-    if (ncta > 1) mbar_wait_cluster(part_empty, pe_phase ^ 1);
+    // exit protocol as in glu_fused.cu: my receive barrier completed, nobody signals after the last tile
   }
   tc_fence_before();
   __syncthreads();
