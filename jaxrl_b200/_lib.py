@@ -7,6 +7,7 @@ raises if the CUDA call fails (e.g. no sm_100 device).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
@@ -147,3 +148,7 @@ def ptr(t) -> int | None:
 def stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+# Tuning knob for A/B runs: MPX_PDL=0 launches the rollout-chain kernels without programmatic dependent launch.
+if os.environ.get("MPX_PDL") is not None:
+    lib.mpx_debug_set(6, int(os.environ["MPX_PDL"]))

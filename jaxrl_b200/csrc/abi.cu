@@ -26,6 +26,7 @@ int num_sms() {
 }
 
 unsigned long long* g_dbg_stamps = nullptr;
+int g_use_pdl = 1;
 extern int g_debug_swap_lbo_sbo;
 extern int g_attn_decode_impl;
 extern int g_attn_train_impl;
@@ -64,6 +65,10 @@ extern "C" int mpx_debug_set(int key, int value) {
   }
   if (key == 5) {
     mpx::g_obs_fused_swap = value;
+    return MPX_OK;
+  }
+  if (key == 6) {
+    mpx::g_use_pdl = value;
     return MPX_OK;
   }
   mpx::set_error("mpx_debug_set: unknown key %d", key);

@@ -449,6 +449,8 @@ __global__ void __launch_bounds__(512) attn_decode_online_kernel(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ring = smem_u32(smem_raw) + warp * (AD3_STAGES * AD3_STAGE_BYTES);
   const int g = lane >> 2, t = lane & 3, mi = lane >> 3, r8 = lane & 7;
+  griddep_launch();
+  griddep_wait();                              // q, the KV ring and pos are written by the previous kernels
   const int kv_len = min(pos[0] + 1, S);
   const int nchunks = (kv_len + AD_CHUNK - 1) / AD_CHUNK;
   const int Nq = Nkv * G;
@@ -613,10 +615,14 @@ static int launch_attn_decode_online(const mpx_attn_decode_args* a, cudaStream_t
   }
   const int grid = ceil_div(total, best_w) < sms ? ceil_div(total, best_w) : sms;
   const float scale_log2 = (1.0f / sqrtf((float)a->D)) * 1.4426950408889634f;
-  attn_decode_online_kernel<G><<<grid, best_w * 32, smem, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(a->q), reinterpret_cast<const __nv_bfloat16*>(a->kcache),
-      reinterpret_cast<const __nv_bfloat16*>(a->vcache), a->pos, reinterpret_cast<__nv_bfloat16*>(a->out), a->B, a->S,
-      a->Nkv, scale_log2);
+  cudaError_t le = launch_ex(attn_decode_online_kernel<G>, dim3(grid), dim3(best_w * 32), smem, stream, 1, true,
+                             reinterpret_cast<const __nv_bfloat16*>(a->q), reinterpret_cast<const __nv_bfloat16*>(a->kcache),
+                             reinterpret_cast<const __nv_bfloat16*>(a->vcache), a->pos,
+                             reinterpret_cast<__nv_bfloat16*>(a->out), a->B, a->S, a->Nkv, scale_log2);
+  if (le != cudaSuccess) {
+    set_error("launch attn_decode_online_kernel: %s", cudaGetErrorString(le));
+    return MPX_ERR_CUDA;
+  }
   return check_launch("attn_decode_online_kernel");
 }
 

@@ -32,6 +32,37 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 int num_sms();   // abi.cu (cached cudaDevAttrMultiProcessorCount of the current device)
 
+// Launch with optional thread-block cluster (x dimension) and programmatic dependent launch (see ptx.cuh).
+extern int g_use_pdl;   // mpx_debug_set(6, 0|1); default 1
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             int cluster_x, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl && g_use_pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // Bring-up aid: mpx_debug_set_stamps(ptr) hands the fused kernels a device buffer of 64-bit slots; CTA 0 then records
 // %globaltimer (ns) at its phase boundaries.  NULL (the default) compiles to one predicated-off branch per stamp.
 extern unsigned long long* g_dbg_stamps;

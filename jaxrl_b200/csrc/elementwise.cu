@@ -30,6 +30,8 @@ __global__ void __launch_bounds__(EW_WARPS * 32) rmsnorm_fwd_kernel(
   const int lane = threadIdx.x & 31;
   long long row = (long long)blockIdx.x * EW_WARPS + (threadIdx.x >> 5);
   const long long stride = (long long)gridDim.x * EW_WARPS;
+  griddep_launch();
+  griddep_wait();
   for (; row < M; row += stride) {
     float v[ITERS][4];
     float ss = 0.f;
@@ -275,10 +277,10 @@ extern "C" int mpx_rmsnorm_fwd(const mpx_bf16* x, const float* scale, float eps,
   auto Y = reinterpret_cast<__nv_bfloat16*>(y);
   cudaStream_t s = (cudaStream_t)stream;
   switch (H / 128) {
-    case 1: rmsnorm_fwd_kernel<1><<<grid, EW_WARPS * 32, 0, s>>>(X, scale, eps, Y, M, H); break;
-    case 2: rmsnorm_fwd_kernel<2><<<grid, EW_WARPS * 32, 0, s>>>(X, scale, eps, Y, M, H); break;
-    case 3: rmsnorm_fwd_kernel<3><<<grid, EW_WARPS * 32, 0, s>>>(X, scale, eps, Y, M, H); break;
-    default: rmsnorm_fwd_kernel<4><<<grid, EW_WARPS * 32, 0, s>>>(X, scale, eps, Y, M, H); break;
+    case 1: launch_ex(rmsnorm_fwd_kernel<1>, dim3(grid), dim3(EW_WARPS * 32), 0, s, 1, true, X, scale, eps, Y, M, H); break;
+    case 2: launch_ex(rmsnorm_fwd_kernel<2>, dim3(grid), dim3(EW_WARPS * 32), 0, s, 1, true, X, scale, eps, Y, M, H); break;
+    case 3: launch_ex(rmsnorm_fwd_kernel<3>, dim3(grid), dim3(EW_WARPS * 32), 0, s, 1, true, X, scale, eps, Y, M, H); break;
+    default: launch_ex(rmsnorm_fwd_kernel<4>, dim3(grid), dim3(EW_WARPS * 32), 0, s, 1, true, X, scale, eps, Y, M, H); break;
   }
   return check_launch("mpx_rmsnorm_fwd");
 }

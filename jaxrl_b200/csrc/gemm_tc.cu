@@ -362,6 +362,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
 
+  griddep_launch();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
@@ -382,6 +383,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_wait();                              // operands / residual / positions may come from the previous kernel
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -764,7 +766,11 @@ static int launch_tn(const GemmParams& p, const void* a, long long lda, const vo
   }
   const int tiles = ceil_div(p.M, BLOCK_M) * (EPI == EPI_PAIRSUM ? 1 : ceil_div(p.N, BLOCK_N));
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tn_kernel<BLOCK_N, EPI><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(p, tm_a, tm_b);
+  cudaError_t le = launch_ex(gemm_tn_kernel<BLOCK_N, EPI>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, 1, true, p, tm_a, tm_b);
+  if (le != cudaSuccess) {
+    set_error("launch gemm_tn_kernel: %s", cudaGetErrorString(le));
+    return MPX_ERR_CUDA;
+  }
   return check_launch("gemm_tn_kernel");
 }
 

@@ -79,6 +79,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
 
   unsigned long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) ? p.dbg : nullptr;   // warp 2 lane 0
   dbg_stamp(dbg, 0);
+  griddep_launch();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_wug);
@@ -106,6 +107,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  griddep_wait();                              // everything read from global memory below may come from earlier kernels
   if (p.norm_scale && threadIdx.x >= 64 && threadIdx.x < 96)
     reinterpret_cast<float4*>(sScale)[threadIdx.x - 64] = reinterpret_cast<const float4*>(p.norm_scale)[threadIdx.x - 64];
   tc_fence_before();
@@ -326,7 +328,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         //    every CTA of the cluster, those columns into recv[src][c4 local][row] (st.async: the data itself completes
         //    the owner's transaction barrier - no fences, no acknowledgement on the critical path)
         const bool last_tile = tile + (int)gridDim.y >= m_tiles;
-        mbar_wait_cluster(part_empty, pe_phase ^ 1);           // owners have consumed the previous tile (multi-tile only)
+        if (tile != (int)blockIdx.y) mbar_wait_cluster(part_empty, pe_phase ^ 1);   // owners consumed the previous tile
         pe_phase ^= 1;
         const uint32_t sp = smem_u32(sP);
         const int per_owner = slice / 4;                       // float4 column groups per owner: 8 (CL 4) or 16 (CL 2)
@@ -356,7 +358,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         if (lane == 0) mbar_arrive(d_empty);                   // TMEM accumulator drained
         dbg_stamp(dbg, 21);
         // 2. all CL partials of my slice have landed in MY shared memory: sum in CTA-rank order, add the residual, store
-        mbar_wait_cluster(part_full, pf_phase);
+        mbar_wait(part_full, pf_phase);                        // async-proxy completion, like a TMA load
         pf_phase ^= 1;
         dbg_stamp(dbg, 22);
 #pragma unroll
@@ -446,19 +448,7 @@ extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const m
     cl = g_glu_fused_cluster;
   int gy = num_sms() / cl;
   if (gy > tiles) gy = tiles;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cl, gy, 1);
-  cfg.blockDim = dim3(GF_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cl;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, glu_fused_kernel, p, tm_x, tm_wug, tm_wd);
+  cudaError_t le = launch_ex(glu_fused_kernel, dim3(cl, gy, 1), dim3(GF_THREADS), smem, (cudaStream_t)stream, cl, true, p, tm_x, tm_wug, tm_wd);
   if (le != cudaSuccess) {
     set_error("cudaLaunchKernelEx(glu_fused, cluster %d): %s", cl, cudaGetErrorString(le));
     return MPX_ERR_CUDA;

@@ -219,6 +219,8 @@ __global__ void __launch_bounds__(HD_WARPS * 32) policy_head_sample_kernel(
     __nv_bfloat16* __restrict__ xf_out, int32_t* __restrict__ action, float* __restrict__ log_prob, long long M, int H,
     int A) {
   extern __shared__ float s_table[];   // [A][H]
+  griddep_launch();
+  griddep_wait();
   for (int i = threadIdx.x; i < A * H; i += blockDim.x) s_table[i] = table[i];
   __syncthreads();
   if (stream_off) stream_id += stream_off[0];
@@ -608,8 +610,13 @@ extern "C" int mpx_policy_head_sample(const mpx_bf16* x, const float* norm_scale
               8 * PH_MAX_PER);
   const size_t smem = (size_t)A * H * sizeof(float);
   MPX_REQUIRE(smem <= 48 * 1024, "mpx_policy_head_sample: table too large for shared memory");
-  policy_head_sample_kernel<<<grid_for(M, HD_WARPS * 4, 8), HD_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), norm_scale, eps, table, action_mask, gumbel_in, seed, stream_id,
-      stream_offset, logits_out, reinterpret_cast<__nv_bfloat16*>(xf_out), action, log_prob, M, H, A);
+  cudaError_t le = launch_ex(policy_head_sample_kernel, dim3(grid_for(M, HD_WARPS * 4, 8)), dim3(HD_WARPS * 32), smem,
+                             (cudaStream_t)stream, 1, true, reinterpret_cast<const __nv_bfloat16*>(x), norm_scale, eps, table,
+                             action_mask, gumbel_in, seed, stream_id, stream_offset, logits_out,
+                             reinterpret_cast<__nv_bfloat16*>(xf_out), action, log_prob, M, H, A);
+  if (le != cudaSuccess) {
+    set_error("launch policy_head_sample_kernel: %s", cudaGetErrorString(le));
+    return MPX_ERR_CUDA;
+  }
   return check_launch("mpx_policy_head_sample");
 }

@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
 
   unsigned long long* dbg = (blockIdx.x == 0 && tid == 0) ? p.dbg : nullptr;
   dbg_stamp(dbg, 0);
+  griddep_launch();
   if (tid == 0) {
     mbar_init(a1_ready, OF_WORKERS);
     mbar_init(c2_full, 1);
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
     mbar_init(c3_full, 1);
     mbar_init(img_full, 1);
     fence_barrier_init();
+    griddep_wait();                                          // the image may have been rebuilt by the previous kernel
     mbar_arrive_expect_tx(img_full, OF_IMG_BYTES);           // weights + tables: one bulk copy per CTA
     bulk_load_1d(sImg, p.image, OF_IMG_BYTES, img_full);
   }
@@ -216,9 +218,20 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
     uint32_t ph = 0;
     // embedding-sum role of this thread: (agent eag, columns [16*ecg, +16)); reward encoder weights are tile-invariant
     const int eag = wtid >> 3, ecg = wtid & 7;
+    griddep_wait();                                          // observations / rewards / actions come from earlier kernels
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long m0 = (long long)tile * OF_AG;
       const int nag = (int)min((long long)OF_AG, p.M - m0);
+      // ---- this thread's embedding inputs (network.py:304-309): scalars first, so the table rows can be requested
+      //      as soon as the observation tile is on its way
+      float e_rw = 0.f;
+      int e_a = -1, e_tk = -1;
+      if (eag < nag) {
+        const long long m = m0 + eag;
+        e_rw = p.reward[m];
+        e_a = p.last_action[m];
+        if (p.task_ids && p.t_table) e_tk = p.task_ids[m];
+      }
       // ---- observation tile -> smem (contiguous bytes)
       {
         const int nbytes = nag * cell_bytes;
@@ -235,16 +248,12 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
       // ---- this thread's embedding addends (network.py:304-309), in flight while the encoder runs
       uint32_t re_w[8], ae_w[8], te_w[8];
       {
-        const long long m = m0 + eag;
-        float rw = 0.f;
-        int a = -1, tk = -1;
+        const float rw = bf16_round(e_rw);
+        int a = e_a, tk = e_tk;
         if (eag < nag) {
-          rw = bf16_round(p.reward[m]);
-          a = p.last_action[m];
           if (a < 0) a += p.A;
           if (a >= p.A) a = -1;
           if (p.task_ids && p.t_table) {
-            tk = p.task_ids[m];
             if (tk < 0) tk += p.n_tasks;
             if (tk >= p.n_tasks) tk = -1;
           }
@@ -515,6 +524,10 @@ extern "C" int mpx_obs_embed_fused(const uint8_t* obs, const int* sizes, int K, 
   }
   const long long tiles = (M + OF_AG - 1) / OF_AG;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  obs_fused_kernel<<<grid, OF_THREADS, OF_SMEM, (cudaStream_t)stream>>>(p);
+  cudaError_t le = launch_ex(obs_fused_kernel, dim3(grid), dim3(OF_THREADS), OF_SMEM, (cudaStream_t)stream, 1, true, p);
+  if (le != cudaSuccess) {
+    set_error("launch obs_fused_kernel: %s", cudaGetErrorString(le));
+    return MPX_ERR_CUDA;
+  }
   return check_launch("obs_fused_kernel");
 }

@@ -78,6 +78,7 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
   const int chunk0 = krank * nchunks;
   const int m_tiles = (p.M + 127) / 128;
 
+  griddep_launch();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_wvm);
@@ -105,6 +106,7 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
+  griddep_wait();                              // everything read from global memory below may come from earlier kernels
   if (threadIdx.x >= 64 && threadIdx.x < 192) {
     const int i = threadIdx.x - 64;
     if (p.norm_scale) sScale[i] = p.norm_scale[i];
@@ -312,7 +314,7 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
       tc_fence_after();
       dbg_stamp(dbg, 20);
       const bool last_tile = tile + (int)gridDim.y >= m_tiles;
-      mbar_wait_cluster(part_empty, pe_phase ^ 1);           // owners have consumed the previous tile (multi-tile only)
+      if (tile != (int)blockIdx.y) mbar_wait_cluster(part_empty, pe_phase ^ 1);   // owners consumed the previous tile
       pe_phase ^= 1;
       const uint32_t sp = smem_u32(sP);
       const int R = 128 / ncta;                              // rows finished per CTA
@@ -339,7 +341,7 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
       __syncwarp();
       dbg_stamp(dbg, 21);
       if (lane == 0) mbar_arrive(d_empty);
-      mbar_wait_cluster(part_full, pf_phase);
+      mbar_wait(part_full, pf_phase);                        // async-proxy completion, like a TMA load
       pf_phase ^= 1;
       dbg_stamp(dbg, 22);
       // ---- my R rows: 8 lanes per row, lane `sub` owns logits [8*sub, 8*sub+8); bias, softmax, expectation
@@ -462,19 +464,7 @@ extern "C" int mpx_value_head_fused(const mpx_bf16* x, const float* norm_scale, 
     cl = g_value_fused_cluster;
   int gy = num_sms() / cl;
   if (gy > tiles) gy = tiles;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cl, gy, 1);
-  cfg.blockDim = dim3(VF_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cl;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, value_fused_kernel, p, tm_x, tm_wvm, tm_whl);
+  cudaError_t le = launch_ex(value_fused_kernel, dim3(cl, gy, 1), dim3(VF_THREADS), smem, (cudaStream_t)stream, cl, true, p, tm_x, tm_wvm, tm_whl);
   if (le != cudaSuccess) {
     set_error("cudaLaunchKernelEx(value_fused, cluster %d): %s", cl, cudaGetErrorString(le));
     return MPX_ERR_CUDA;
