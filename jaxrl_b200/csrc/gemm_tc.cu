@@ -766,7 +766,7 @@ static int launch_tn(const GemmParams& p, const void* a, long long lda, const vo
   }
   const int tiles = ceil_div(p.M, BLOCK_M) * (EPI == EPI_PAIRSUM ? 1 : ceil_div(p.N, BLOCK_N));
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  cudaError_t le = launch_ex(gemm_tn_kernel<BLOCK_N, EPI>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, 1, true, p, tm_a, tm_b);
+  cudaError_t le = launch_ex(gemm_tn_kernel<BLOCK_N, EPI>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, 0, true, p, tm_a, tm_b);
   if (le != cudaSuccess) {
     set_error("launch gemm_tn_kernel: %s", cudaGetErrorString(le));
     return MPX_ERR_CUDA;
