@@ -252,6 +252,13 @@ int mpx_obs_embed_fused(const uint8_t* obs, const int* sizes, int K, const void*
                         const int32_t* last_action, const int32_t* task_ids, const float* w_reward, const float* b_reward,
                         const float* action_table, int A, const float* task_table, int n_tasks, mpx_bf16* x,
                         mpx_bf16* obs_emb, long long M, int IH, int IW, int H, mpx_stream_t stream);
+/* Weight gradient of the first observation conv without materialising the one-hot im2col matrix:
+ * dw ((kh*kw*C), cout) f32 += onehot_im2col(obs)^T @ dz, dz (M*OH*OW, cout) bf16 contiguous.  The one-hot operand
+ * tiles are generated in shared memory from the uint8 observation.  kh*kw*C <= 128, kh*kw*K <= 32, cout <= 64. */
+size_t mpx_conv1_onehot_wgrad_workspace_bytes(long long M, int IH, int IW, int kh, int kw, int sh, int sw);
+int mpx_conv1_onehot_wgrad(const uint8_t* obs, const mpx_bf16* dz, float* dw, long long M, int IH, int IW, int K,
+                           const int* sizes, int kh, int kw, int sh, int sw, int cout, void* workspace,
+                           size_t workspace_bytes, mpx_stream_t stream);
 /* network.py:323-331: tied action logits f32(x) @ table^T (M,A) f32, masked entries = finfo(f32).min. A <= 32. */
 int mpx_policy_logits(const mpx_bf16* x, const float* table, const uint8_t* action_mask, float* logits, long long M,
                       int H, int A, mpx_stream_t stream);

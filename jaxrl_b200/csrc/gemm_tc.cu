@@ -701,6 +701,154 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------ one-hot wgrad
+// Weight gradient of the first observation conv (reference GridCnnObsEncoder, observation.py:66-96, through autodiff):
+//   dW1[(tap, channel c)][ch] += sum over output rows (agent-step m, position q) of onehot(obs)[row][(tap, c)] * dz1[row][ch]
+// i.e. the same X^T . dY contraction as gemm_wgrad_kernel, except that X (the one-hot im2col matrix, 566 MB per
+// minibatch if materialised) is never written to memory: four builder warps generate each [64 rows][128 features]
+// operand tile straight into shared memory in the MN-major SW128 layout the MMA reads (zeros + at most taps*K ones per
+// row) from the uint8 observation, while warp 0 streams the matching dz1 tile with TMA.
+struct OneHotWgradParams {
+  const uint8_t* obs;      // (M, IH, IW, K)
+  long long rows;          // M * OH * OW
+  int IH, IW, OH, OW, K, C, kh, kw, sh, sw;
+  int offs[5];             // prefix sums of the one-hot sizes
+  float* partial;          // [splits][128][64]
+  int rows_per_cta;        // multiple of 64
+};
+
+__global__ void __launch_bounds__(WGRAD_THREADS, 1)
+onehot_wgrad_kernel(const OneHotWgradParams p, const __grid_constant__ CUtensorMap tm_dy) {
+  constexpr int A_BYTES = 2 * 8192, B_BYTES = 8192, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = (long long)blockIdx.x * p.rows_per_cta;
+  const long long row1 = min(p.rows, row0 + p.rows_per_cta);
+  const int num_it = row1 > row0 ? (int)((row1 - row0 + 63) / 64) : 0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_dy);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1 + 4);          // TMA producer (expect_tx) + 4 builder warps
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&tfull[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < num_it; ++it) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], B_BYTES);
+        // rows past row1 but < rows belong to the next CTA: their one-hot rows are built as zeros, so they add nothing
+        tma_load_2d(&tm_dy, &full[stage], smem + stage * STAGE_BYTES + A_BYTES, 0, (int)(row0 + (long long)it * 64));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < num_it; ++it) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base, umma_smem_desc_sw128(sa + k * 2048, 8192, 1024), umma_smem_desc_sw128(sb + k * 2048, 8192, 1024),
+                    idesc, (it | k) != 0 ? 1u : 0u);
+        umma_commit(&empty[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tfull[0]);
+    }
+  } else {
+    // ---- builders: thread = (row of the stage tl, 64-feature box)
+    const int tb = threadIdx.x - 64;
+    const int tl = tb & 63, box = tb >> 6;
+    const int taps = p.kh * p.kw;
+    const int ohw = p.OH * p.OW;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < num_it; ++it) {
+      const long long row = row0 + (long long)it * 64 + tl;
+      // the row's receptive field: taps * K bytes -> feature indices (registers), before the stage is free
+      int feat[32];
+      int nfeat = 0;
+      if (row < row1) {
+        const long long m = row / ohw;
+        const int q = (int)(row % ohw);
+        const int oy = q / p.OW, ox = q % p.OW;
+        const uint8_t* cell0 = p.obs + ((m * p.IH + oy * p.sh) * p.IW + ox * p.sw) * p.K;
+        for (int tap = 0; tap < taps; ++tap) {
+          const uint8_t* cell = cell0 + ((tap / p.kw) * p.IW + (tap % p.kw)) * p.K;
+          for (int kc = 0; kc < p.K; ++kc) {
+            const int val = __ldg(cell + kc);
+            const int f = tap * p.C + p.offs[kc] + val;
+            if (val < p.offs[kc + 1] - p.offs[kc] && (f >> 6) == box && nfeat < 32) feat[nfeat++] = f & 63;
+          }
+        }
+      }
+      mbar_wait(&empty[stage], phase ^ 1);
+      const uint32_t rowaddr = smem_u32(smem + stage * STAGE_BYTES + box * 8192 + tl * 128);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) sts_v4(rowaddr + c * 16, make_uint4(0, 0, 0, 0));
+      for (int i = 0; i < nfeat; ++i) {
+        const int f = feat[i];
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(rowaddr + ((((f >> 3) ^ (tl & 7)) << 4) + (f & 7) * 2)), "h"((unsigned short)0x3F80) : "memory");
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[stage]);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+    // ---- epilogue: TMEM (128 features x 64 columns) -> partial[split][128][64]
+    const int quarter = warp & 3;
+    if (num_it > 0) {
+      mbar_wait(&tfull[0], 0);
+      tc_fence_after();
+    }
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < 64; c += 32) {
+      uint32_t acc[32];
+      if (num_it > 0) {
+        tmem_ld_32x32(t_row + c, acc);
+        tmem_ld_wait();
+      }
+      float4* d4 = reinterpret_cast<float4*>(p.partial + ((long long)blockIdx.x * 128 + quarter * 32 + lane) * 64 + c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        d4[i] = num_it > 0 ? make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]),
+                                         __uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3]))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 64);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -908,4 +1056,58 @@ extern "C" int mpx_linear_f32w(const mpx_bf16* x, long long ldx, const mpx_bf16*
   p.M = M; p.N = N; p.K = K;
   p.y_f32 = y; p.ldy32 = ldy; p.bias_f32 = bias;
   return launch_tn<128, EPI_PAIRSUM>(p, x, ldx, wt_hilo, K, (cudaStream_t)stream);
+}
+
+static int onehot_wgrad_splits(long long rows, int* rows_per_cta) {
+  int splits = 2 * num_sms();
+  long long per = ((rows + splits - 1) / splits + 63) / 64 * 64;
+  if (per < 64) per = 64;
+  *rows_per_cta = (int)per;
+  return (int)((rows + per - 1) / per);
+}
+
+extern "C" size_t mpx_conv1_onehot_wgrad_workspace_bytes(long long M, int IH, int IW, int kh, int kw, int sh, int sw) {
+  const int OH = (IH - kh) / sh + 1, OW = (IW - kw) / sw + 1;
+  int per;
+  const int splits = onehot_wgrad_splits(M * OH * OW, &per);
+  return (size_t)splits * 128 * 64 * sizeof(float);
+}
+
+extern "C" int mpx_conv1_onehot_wgrad(const uint8_t* obs, const mpx_bf16* dz, float* dw, long long M, int IH, int IW, int K,
+                                      const int* sizes, int kh, int kw, int sh, int sw, int cout, void* workspace,
+                                      size_t workspace_bytes, mpx_stream_t stream) {
+  MPX_REQUIRE(obs && dz && dw && sizes && workspace && M > 0, "mpx_conv1_onehot_wgrad: bad arguments");
+  MPX_REQUIRE(K >= 1 && K <= 4 && kh * kw * K <= 32, "mpx_conv1_onehot_wgrad: K=%d / %dx%d taps unsupported", K, kh, kw);
+  MPX_REQUIRE(cout > 0 && cout <= 64 && cout % 8 == 0, "mpx_conv1_onehot_wgrad: cout=%d must be a multiple of 8, <= 64", cout);
+  OneHotWgradParams p = {};
+  p.obs = obs; p.IH = IH; p.IW = IW; p.K = K; p.kh = kh; p.kw = kw; p.sh = sh; p.sw = sw;
+  p.OH = (IH - kh) / sh + 1; p.OW = (IW - kw) / sw + 1;
+  p.offs[0] = 0;
+  for (int i = 0; i < 4; ++i) p.offs[i + 1] = p.offs[i] + (i < K ? sizes[i] : 0);
+  p.C = p.offs[K];
+  MPX_REQUIRE(kh * kw * p.C <= 128, "mpx_conv1_onehot_wgrad: %d one-hot features > 128", kh * kw * p.C);
+  p.rows = M * p.OH * p.OW;
+  MPX_REQUIRE(p.rows < (1LL << 31), "mpx_conv1_onehot_wgrad: too many rows");
+  const int splits = onehot_wgrad_splits(p.rows, &p.rows_per_cta);
+  MPX_REQUIRE(workspace_bytes >= (size_t)splits * 128 * 64 * sizeof(float), "mpx_conv1_onehot_wgrad: workspace too small");
+  p.partial = reinterpret_cast<float*>(workspace);
+  CUtensorMap tm_dy;
+  int rc = make_tmap_bf16_2d(&tm_dy, dz, p.rows, cout, cout, 64, 64);
+  if (rc) return rc;
+  constexpr int SMEM = STAGES * (3 * 8192) + 256 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(onehot_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(onehot_wgrad): %s", cudaGetErrorString(e));
+      return MPX_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  onehot_wgrad_kernel<<<splits, WGRAD_THREADS, SMEM, s>>>(p, tm_dy);
+  const int feats = kh * kw * p.C;
+  int rg = ceil_div(feats * 16, 32);
+  wgrad_reduce_kernel<<<rg, 256, 0, s>>>(p.partial, splits, 128, 64, dw, cout, feats, cout);
+  return check_launch("onehot_wgrad_kernel");
 }

@@ -79,6 +79,9 @@ class PolicyEngine:
                           and [c.cout for c in self.conv] == [16, 32, 128] and len(cfg.obs_max_value) <= 4
                           and math.prod(n + 1 for n in cfg.obs_max_value) <= 48)
         self.obs_image = ops.obs_fused_image(self.dev) if self.fused_obs else None
+        c0 = self.conv[0]
+        self.onehot_wgrad = (c0.k <= 128 and c0.kh * c0.kw * len(cfg.obs_max_value) <= 32 and c0.cout <= 64
+                             and c0.cout % 8 == 0 and len(cfg.obs_max_value) <= 4)
         self._alloc_staged()
         self.stage_weights()
 
@@ -293,6 +296,10 @@ class PolicyEngine:
             if not last:
                 ops.gelu_bwd(dy, ws.cz[c.j], out=dy)          # dz in place
             ops.colsum(dy, p.g(f"obs_encoder.layers.{c.j}.bias"), M=rows, N=c.cout, ld=c.cout)
+            if c.j == 0 and self.onehot_wgrad:     # one-hot operand tiles are generated inside the wgrad kernel
+                ops.conv1_onehot_wgrad(obs, dy, p.g("obs_encoder.layers.0.kernel").view(c.k, c.cout), M, c.ih, c.iw,
+                                       self.cfg.obs_max_value, c.kh, c.kw, c.sh, c.sw, c.cout)
+                break
             if c.j == 0:      # one-hot im2col rows are only needed here, for the weight gradient
                 ops.obs_onehot_im2col(obs, ws.cx[0], M, c.ih, c.iw, self.cfg.obs_max_value, c.kh, c.kw, c.sh, c.sw)
             xin = ws.ca[c.j - 1].view(M, c.kp) if last else ws.cx[c.j]

@@ -418,6 +418,21 @@ def conv1_onehot_fwd(obs, w, bias, a_out, M: int, IH: int, IW: int, sizes: Seque
     return a_out
 
 
+def conv1_onehot_wgrad(obs, dz, dw, M: int, IH: int, IW: int, sizes: Sequence[int], kh, kw, sh, sw, cout: int, ws=None):
+    """dw (kh*kw*C, cout) f32 += onehot_im2col(obs)^T @ dz without materialising the one-hot rows."""
+    _req(dz, BF16, "dz"); _req(dw, F32, "dw")
+    K = len(sizes)
+    arr = (C.c_int * K)(*sizes)
+    need = lib.mpx_conv1_onehot_wgrad_workspace_bytes(M, IH, IW, kh, kw, sh, sw)
+    if ws is None:
+        ws = wgrad_workspace(dz.device)
+    if ws.numel() * ws.element_size() < need:
+        raise _lib.MpxError(f"conv1_onehot_wgrad: workspace of {need} bytes required")
+    check(lib.mpx_conv1_onehot_wgrad(ptr(obs), ptr(dz), ptr(dw), M, IH, IW, K, arr, kh, kw, sh, sw, cout, ptr(ws),
+                                     ws.numel() * ws.element_size(), stream()), "mpx_conv1_onehot_wgrad")
+    return dw
+
+
 def obs_fused_image(device) -> torch.Tensor:
     """Device buffer for the fused observation encoder's weight image (see mpx_obs_fused_prep)."""
     return torch.empty(lib.mpx_obs_fused_image_bytes(), dtype=torch.uint8, device=device)

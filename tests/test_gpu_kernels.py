@@ -561,3 +561,22 @@ def test_obs_embed_fused(ops, M, sizes, tasks):
     assert_close_bf16(emb, emb_ref, f"obs_embed_fused encoder output M={M}", rtol=1e-2, abs_floor_frac=1e-2, allow_frac=2e-3,
                       max_err_frac=0.1)
     assert_close_bf16(out, x_ref, f"obs_embed_fused x M={M}", rtol=1e-2, abs_floor_frac=1e-2, allow_frac=2e-3, max_err_frac=0.1)
+
+
+@pytest.mark.parametrize("M,sizes", [(37, (5, 5)), (3000, (5, 5)), (500, (3, 2, 2)), (64, (6,))])
+def test_conv1_onehot_wgrad(ops, M, sizes):
+    """dW1 += onehot_im2col(obs)^T @ dz with the one-hot operand generated in shared memory, vs the materialised
+    one-hot GEMM in fp64 (bf16 inputs, fp32 accumulation: exact up to summation order)."""
+    gen = g(M + len(sizes))
+    IH = IW = 11
+    C, cout = sum(sizes), 16
+    obs = torch.stack([torch.randint(0, n, (M, IH, IW), generator=gen) for n in sizes], -1).to(torch.uint8)
+    dz = (torch.randn(M * 25, cout, generator=gen)).to(BF16)
+    x = O.concat_one_hot(obs, sizes).float()                                  # (M, 11, 11, C)
+    cols = torch.nn.functional.unfold(x.permute(0, 3, 1, 2), kernel_size=3, stride=2)   # (M, C*9, 25), index c*9 + tap
+    cols = cols.reshape(M, C, 9, 25).permute(0, 3, 2, 1).reshape(M * 25, 9 * C)         # rows (m, q), features (tap, c)
+    ref = cols.double().t() @ dz.double()
+    dw = torch.full((9 * C, cout), 0.5, dtype=torch.float32, device=DEV)    # accumulates into existing values
+    ops.conv1_onehot_wgrad(obs.to(DEV), dz.to(DEV), dw, M, IH, IW, sizes, 3, 3, 2, 2, cout)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dw.cpu().double() - 0.5, ref, rtol=1e-4, atol=1e-3 * max(1.0, math.sqrt(M)))
