@@ -717,7 +717,12 @@ struct OneHotWgradParams {
   int rows_per_cta;        // multiple of 64
 };
 
-__global__ void __launch_bounds__(WGRAD_THREADS, 1)
+constexpr int OHW_BUILDERS = 8;                              // builder warps
+constexpr int OHW_THREADS = 64 + OHW_BUILDERS * 32;
+
+// KC = observation components per cell; the receptive field is 3x3 (9 taps).
+template <int KC>
+__global__ void __launch_bounds__(OHW_THREADS, 1)
 onehot_wgrad_kernel(const OneHotWgradParams p, const __grid_constant__ CUtensorMap tm_dy) {
   constexpr int A_BYTES = 2 * 8192, B_BYTES = 8192, STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -736,7 +741,7 @@ onehot_wgrad_kernel(const OneHotWgradParams p, const __grid_constant__ CUtensorM
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_dy);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1 + 4);          // TMA producer (expect_tx) + 4 builder warps
+      mbar_init(&full[s], 1 + OHW_BUILDERS);   // TMA producer (expect_tx) + builder warps
       mbar_init(&empty[s], 1);
     }
     mbar_init(&tfull[0], 1);
@@ -783,65 +788,96 @@ onehot_wgrad_kernel(const OneHotWgradParams p, const __grid_constant__ CUtensorM
       umma_commit(&tfull[0]);
     }
   } else {
-    // ---- builders: thread = (row of the stage tl, 64-feature box)
+    // ---- builders: thread = (row of the stage tl, 64-feature box, half): zero-fills 4 of the 8 chunks of its box
+    //      row and turns on the ones of taps [5*half, 5*half+5) that fall into its box.  The observation bytes of the
+    //      NEXT stage are requested before this stage is written, so their latency overlaps the stores.
     const int tb = threadIdx.x - 64;
-    const int tl = tb & 63, box = tb >> 6;
-    const int taps = p.kh * p.kw;
+    const int tl = tb & 63, box = (tb >> 7) & 1, half = (tb >> 6) & 1;
+    const int tap0 = half * 5, tap1 = half ? 9 : 5;
     const int ohw = p.OH * p.OW;
     int stage = 0;
     uint32_t phase = 0;
-    for (int it = 0; it < num_it; ++it) {
+    uint32_t cur[5], nxt[5];
+    auto fetch = [&](int it, uint32_t (&dst)[5]) {
       const long long row = row0 + (long long)it * 64 + tl;
-      // the row's receptive field: taps * K bytes -> feature indices (registers), before the stage is free
-      int feat[32];
-      int nfeat = 0;
-      if (row < row1) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) dst[i] = 0xFFFFFFFFu;        // "out of range" for every component: no ones
+      if (it < num_it && row < row1) {
         const long long m = row / ohw;
         const int q = (int)(row % ohw);
         const int oy = q / p.OW, ox = q % p.OW;
-        const uint8_t* cell0 = p.obs + ((m * p.IH + oy * p.sh) * p.IW + ox * p.sw) * p.K;
-        for (int tap = 0; tap < taps; ++tap) {
-          const uint8_t* cell = cell0 + ((tap / p.kw) * p.IW + (tap % p.kw)) * p.K;
-          for (int kc = 0; kc < p.K; ++kc) {
-            const int val = __ldg(cell + kc);
-            const int f = tap * p.C + p.offs[kc] + val;
-            if (val < p.offs[kc + 1] - p.offs[kc] && (f >> 6) == box && nfeat < 32) feat[nfeat++] = f & 63;
+        const uint8_t* cell0 = p.obs + ((m * p.IH + oy * p.sh) * p.IW + ox * p.sw) * KC;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const int tap = tap0 + i;
+          if (tap < tap1) {
+            const uint8_t* cell = cell0 + ((tap / 3) * p.IW + (tap % 3)) * KC;
+            uint32_t v = 0;
+            if (KC == 2) {
+              v = *reinterpret_cast<const unsigned short*>(cell);   // cells are 2-byte aligned when KC == 2
+            } else if (KC == 4) {
+              v = *reinterpret_cast<const uint32_t*>(cell);
+            } else {
+#pragma unroll
+              for (int kc = 0; kc < KC; ++kc) v |= (uint32_t)cell[kc] << (8 * kc);
+            }
+            dst[i] = v;
           }
         }
       }
+    };
+    fetch(0, cur);
+    for (int it = 0; it < num_it; ++it) {
+      fetch(it + 1, nxt);
       mbar_wait(&empty[stage], phase ^ 1);
       const uint32_t rowaddr = smem_u32(smem + stage * STAGE_BYTES + box * 8192 + tl * 128);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) sts_v4(rowaddr + c * 16, make_uint4(0, 0, 0, 0));
-      for (int i = 0; i < nfeat; ++i) {
-        const int f = feat[i];
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(rowaddr + ((((f >> 3) ^ (tl & 7)) << 4) + (f & 7) * 2)), "h"((unsigned short)0x3F80) : "memory");
+      for (int c = 0; c < 4; ++c) sts_v4(rowaddr + (((4 * half + c) ^ (tl & 7)) << 4), make_uint4(0, 0, 0, 0));
+      // the partner thread (other half) zero-fills the other 4 chunks: both must be done before any one is set
+      asm volatile("bar.sync 1, %0;" ::"r"(OHW_BUILDERS * 32) : "memory");
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int tap = tap0 + i;
+        if (tap < tap1) {
+#pragma unroll
+          for (int kc = 0; kc < KC; ++kc) {
+            const int val = (cur[i] >> (8 * kc)) & 255;
+            const int f = tap * p.C + p.offs[kc] + val;
+            if (val < p.offs[kc + 1] - p.offs[kc] && (f >> 6) == box)
+              asm volatile("st.shared.u16 [%0], %1;" ::"r"(rowaddr + ((((f & 63) >> 3) ^ (tl & 7)) << 4) + (f & 7) * 2),
+                           "h"((unsigned short)0x3F80) : "memory");
+          }
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[stage]);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
-    }
-    // ---- epilogue: TMEM (128 features x 64 columns) -> partial[split][128][64]
-    const int quarter = warp & 3;
-    if (num_it > 0) {
-      mbar_wait(&tfull[0], 0);
-      tc_fence_after();
-    }
-    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-    for (int c = 0; c < 64; c += 32) {
-      uint32_t acc[32];
-      if (num_it > 0) {
-        tmem_ld_32x32(t_row + c, acc);
-        tmem_ld_wait();
-      }
-      float4* d4 = reinterpret_cast<float4*>(p.partial + ((long long)blockIdx.x * 128 + quarter * 32 + lane) * 64 + c);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        d4[i] = num_it > 0 ? make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]),
-                                         __uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3]))
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 5; ++i) cur[i] = nxt[i];
+    }
+    // ---- epilogue (warps 2-5): TMEM (128 features x 64 columns) -> partial[split][128][64]
+    if (warp < 6) {
+      const int quarter = warp & 3;
+      if (num_it > 0) {
+        mbar_wait(&tfull[0], 0);
+        tc_fence_after();
+      }
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t acc[32];
+        if (num_it > 0) {
+          tmem_ld_32x32(t_row + c, acc);
+          tmem_ld_wait();
+        }
+        float4* d4 = reinterpret_cast<float4*>(p.partial + ((long long)blockIdx.x * 128 + quarter * 32 + lane) * 64 + c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          d4[i] = num_it > 0 ? make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]),
+                                           __uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3]))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   }
   tc_fence_before();
@@ -1077,7 +1113,9 @@ extern "C" int mpx_conv1_onehot_wgrad(const uint8_t* obs, const mpx_bf16* dz, fl
                                       const int* sizes, int kh, int kw, int sh, int sw, int cout, void* workspace,
                                       size_t workspace_bytes, mpx_stream_t stream) {
   MPX_REQUIRE(obs && dz && dw && sizes && workspace && M > 0, "mpx_conv1_onehot_wgrad: bad arguments");
-  MPX_REQUIRE(K >= 1 && K <= 4 && kh * kw * K <= 32, "mpx_conv1_onehot_wgrad: K=%d / %dx%d taps unsupported", K, kh, kw);
+  MPX_REQUIRE(K >= 1 && K <= 4 && kh == 3 && kw == 3, "mpx_conv1_onehot_wgrad: K=%d / %dx%d taps unsupported (3x3, K <= 4)", K, kh, kw);
+  MPX_REQUIRE(K != 2 || (reinterpret_cast<uintptr_t>(obs) & 1) == 0, "mpx_conv1_onehot_wgrad: obs must be 2-byte aligned for K=2");
+  MPX_REQUIRE(K != 4 || (reinterpret_cast<uintptr_t>(obs) & 3) == 0, "mpx_conv1_onehot_wgrad: obs must be 4-byte aligned for K=4");
   MPX_REQUIRE(cout > 0 && cout <= 64 && cout % 8 == 0, "mpx_conv1_onehot_wgrad: cout=%d must be a multiple of 8, <= 64", cout);
   OneHotWgradParams p = {};
   p.obs = obs; p.IH = IH; p.IW = IW; p.K = K; p.kh = kh; p.kw = kw; p.sh = sh; p.sw = sw;
@@ -1097,7 +1135,10 @@ extern "C" int mpx_conv1_onehot_wgrad(const uint8_t* obs, const mpx_bf16* dz, fl
   constexpr int SMEM = STAGES * (3 * 8192) + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(onehot_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(onehot_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(onehot_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(onehot_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(onehot_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(onehot_wgrad): %s", cudaGetErrorString(e));
       return MPX_ERR_CUDA;
@@ -1105,7 +1146,12 @@ extern "C" int mpx_conv1_onehot_wgrad(const uint8_t* obs, const mpx_bf16* dz, fl
     attr_set = true;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  onehot_wgrad_kernel<<<splits, WGRAD_THREADS, SMEM, s>>>(p, tm_dy);
+  switch (K) {
+    case 1: onehot_wgrad_kernel<1><<<splits, OHW_THREADS, SMEM, s>>>(p, tm_dy); break;
+    case 2: onehot_wgrad_kernel<2><<<splits, OHW_THREADS, SMEM, s>>>(p, tm_dy); break;
+    case 3: onehot_wgrad_kernel<3><<<splits, OHW_THREADS, SMEM, s>>>(p, tm_dy); break;
+    default: onehot_wgrad_kernel<4><<<splits, OHW_THREADS, SMEM, s>>>(p, tm_dy); break;
+  }
   const int feats = kh * kw * p.C;
   int rg = ceil_div(feats * 16, 32);
   wgrad_reduce_kernel<<<rg, 256, 0, s>>>(p.partial, splits, 128, 64, dw, cout, feats, cout);
