@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from types import SimpleNamespace
 from typing import Dict, List, Optional
 
@@ -79,6 +80,8 @@ class PolicyEngine:
                           and [c.cout for c in self.conv] == [16, 32, 128] and len(cfg.obs_max_value) <= 4
                           and math.prod(n + 1 for n in cfg.obs_max_value) <= 48)
         self.obs_image = ops.obs_fused_image(self.dev) if self.fused_obs else None
+        self.overlap_wgrad = os.environ.get("MPX_WGRAD_OVERLAP", "1") != "0"
+        self.side = torch.cuda.Stream(device=self.dev) if (self.overlap_wgrad and self.dev.type == "cuda") else None
         c0 = self.conv[0]
         self.onehot_wgrad = (c0.k <= 128 and c0.kh * c0.kw * len(cfg.obs_max_value) <= 32 and c0.cout <= 64
                              and c0.cout % 8 == 0 and len(cfg.obs_max_value) <= 4)
@@ -399,6 +402,32 @@ class PolicyEngine:
         self._heads_fwd(ws.x[self.L], action_mask, ws.xf, ws.logits, ws.pv, ws.zv, ws.vlogits)
         return ws.vlogits, ws.logits
 
+    # ------------------------------------------------------------------------------------------ side stream
+    # Weight-gradient GEMMs only feed the optimizer, so they run on a second stream next to the data-gradient chain
+    # (HBM-bound wgrads overlap the compute-bound attention backward and the epilogue-bound dgrad GEMMs).  They share
+    # one split-K workspace, which the side stream's program order protects.  Every buffer a pending wgrad reads is
+    # guarded by an event the main stream waits on before the next kernel that overwrites it.
+    def _side_run(self, fn):
+        """Enqueue fn on the side stream, ordered after everything already on the current stream; returns an event
+        recorded on the side stream after fn."""
+        if not self.overlap_wgrad:
+            fn()
+            return None
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            fn()
+            done = torch.cuda.Event()
+            done.record(self.side)
+        return done
+
+    @staticmethod
+    def _wait(ev):
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
     # ------------------------------------------------------------------------------------------ loss + backward
     def loss_and_backward(self, ws, batch: dict, hyp, progress: float, entropy_coef_dev=None):
         """ppo_loss (train.py:162-222) on the activations left by forward_train, and its full transpose.
@@ -414,11 +443,13 @@ class PolicyEngine:
                             losses=ws.losses[1:3], dlogits=ws.dlogits, ws=ws.loss_ws,
                             entropy_coef_dev=entropy_coef_dev)
         # ---- value head (values.py:34,40-41) and value MLP (network.py:335-338)
-        ops.linear_wgrad(ws.pv, ws.dvl, p.g("value_head.dense.kernel"), M=M, K=Vh, N=NL, ldx=Vh, ldy=64, lddw=NL)
+        self._side_run(lambda: ops.linear_wgrad(ws.pv, ws.dvl, p.g("value_head.dense.kernel"), M=M, K=Vh, N=NL, ldx=Vh,
+                                                ldy=64, lddw=NL))             # dvl / dpv are not rewritten in this pass
         ops.colsum(ws.dvl, p.g("value_head.dense.bias"), M=M, N=NL, ld=64)
         ops.linear(ws.dvl, w["w_vh_pad"], out=ws.dpv)
         ops.gelu_bwd(ws.dpv, ws.zv, out=ws.dpv)
-        ops.linear_wgrad(ws.xf, ws.dpv, p.g("value_mlp.kernel"), M=M, K=H, N=Vh, ldx=H, ldy=Vh, lddw=Vh)
+        self._side_run(lambda: ops.linear_wgrad(ws.xf, ws.dpv, p.g("value_mlp.kernel"), M=M, K=H, N=Vh, ldx=H, ldy=Vh,
+                                                lddw=Vh))
         ops.colsum(ws.dpv, p.g("value_mlp.bias"), M=M, N=Vh, ld=Vh)
         ops.linear(ws.dpv, w["w_vm"], out=ws.dxn)                      # d xf from the value path
         # ---- tied policy head (network.py:323) and output norm (:321)
@@ -427,34 +458,51 @@ class PolicyEngine:
         dx, spare = ws.dxb, ws.dxa
         ops.rmsnorm_bwd(ws.dxa, ws.x[self.L], p["output_norm.scale"], dscale=p.g("output_norm.scale"), out=dx)
         # ---- transformer blocks in reverse (network.py:158-172)
+        ev_updown = ev_out = ev_qkv = None          # side-stream completion of the previous layer's wgrads
         for i in reversed(range(self.L)):
             pre = f"layers.{i}."
+            dx_in = dx
             ops.linear(dx, w[pre + "w_d"], out=ws.dh)
-            ops.linear_wgrad(ws.h[i], dx, p.g(pre + "ffn.down_proj.kernel"), M=M, K=F, N=H, ldx=F, ldy=H, lddw=H)
+            ev_down = self._side_run(lambda: ops.linear_wgrad(ws.h[i], dx_in, p.g(pre + "ffn.down_proj.kernel"), M=M, K=F,
+                                                              N=H, ldx=F, ldy=H, lddw=H))
+            self._wait(ev_updown)                    # dug is still being read by the previous layer's up/gate wgrads
             ops.glu_bwd(ws.dh, ws.u[i], ws.g[i], out=ws.dug)
-            ops.linear_wgrad(ws.xn2[i], ws.dug, p.g(pre + "ffn.up_proj.kernel"), M=M, K=H, N=F, ldx=H, ldy=2 * F, lddw=F)
-            ops.linear_wgrad(ws.xn2[i], ws.dug[:, F:], p.g(pre + "ffn.up_gate.kernel"), M=M, K=H, N=F, ldx=H,
-                             ldy=2 * F, lddw=F)
+
+            def _wg_updown(i=i, pre=pre):
+                ops.linear_wgrad(ws.xn2[i], ws.dug, p.g(pre + "ffn.up_proj.kernel"), M=M, K=H, N=F, ldx=H, ldy=2 * F,
+                                 lddw=F)
+                ops.linear_wgrad(ws.xn2[i], ws.dug[:, F:], p.g(pre + "ffn.up_gate.kernel"), M=M, K=H, N=F, ldx=H,
+                                 ldy=2 * F, lddw=F)
+            ev_updown = self._side_run(_wg_updown)
             ops.linear(ws.dug, w[pre + "w_ug"], out=ws.dxn)
+            self._wait(ev_out)                       # `spare` was the d x1 the previous layer's out-proj wgrad reads
             ops.rmsnorm_bwd(ws.dxn, ws.x1[i], p[pre + "ffn_norm.scale"], dscale=p.g(pre + "ffn_norm.scale"), dres=dx,
                             out=spare)
             dx, spare = spare, dx                                       # dx = d x1
+            dx_mid = dx
             ops.linear(dx, w[pre + "w_o"], out=ws.do)
-            ops.linear_wgrad(ws.o[i], dx, p.g(pre + "history.out.kernel").view(QD, H), M=M, K=QD, N=H, ldx=QD, ldy=H,
-                             lddw=H)
+            ev_out = self._side_run(lambda: ops.linear_wgrad(ws.o[i], dx_mid, p.g(pre + "history.out.kernel").view(QD, H),
+                                                             M=M, K=QD, N=H, ldx=QD, ldy=H, lddw=H))
             qkv, dqkv = ws.qkv[i], ws.dqkv
+            self._wait(ev_qkv)                       # dqkv is still being read by the previous layer's q/k/v wgrads
             ops.attn_train_bwd(qkv, qkv[:, QD:], qkv[:, QD + KD:], ws.o[i], ws.do, ws.lse[i], ws.pos, self.timescale,
                                ws.Bm, ws.T, self.Nq, self.Nkv, self.D, QKV, QKV, QKV, dqkv, dqkv[:, QD:],
                                dqkv[:, QD + KD:], QKV, QKV, QKV, delta=ws.delta, dq_acc=ws.dq_acc, pos_len=ws.T)
-            ops.linear_wgrad(ws.xn1[i], dqkv, p.g(pre + "history.query_proj.kernel").view(H, QD), M=M, K=H, N=QD,
-                             ldx=H, ldy=QKV, lddw=QD)
-            ops.linear_wgrad(ws.xn1[i], dqkv[:, QD:], p.g(pre + "history.key_proj.kernel").view(H, KD), M=M, K=H,
-                             N=KD, ldx=H, ldy=QKV, lddw=KD)
-            ops.linear_wgrad(ws.xn1[i], dqkv[:, QD + KD:], p.g(pre + "history.value_proj.kernel").view(H, KD), M=M,
-                             K=H, N=KD, ldx=H, ldy=QKV, lddw=KD)
+
+            def _wg_qkv(i=i, pre=pre, dqkv=dqkv):
+                ops.linear_wgrad(ws.xn1[i], dqkv, p.g(pre + "history.query_proj.kernel").view(H, QD), M=M, K=H, N=QD,
+                                 ldx=H, ldy=QKV, lddw=QD)
+                ops.linear_wgrad(ws.xn1[i], dqkv[:, QD:], p.g(pre + "history.key_proj.kernel").view(H, KD), M=M, K=H,
+                                 N=KD, ldx=H, ldy=QKV, lddw=KD)
+                ops.linear_wgrad(ws.xn1[i], dqkv[:, QD + KD:], p.g(pre + "history.value_proj.kernel").view(H, KD), M=M,
+                                 K=H, N=KD, ldx=H, ldy=QKV, lddw=KD)
+            ev_qkv = self._side_run(_wg_qkv)
             ops.linear(dqkv, w[pre + "w_qkv"], out=ws.dxn)
+            self._wait(ev_down)                      # `spare` is the d x[i+1] this layer's down-proj wgrad reads
             ops.rmsnorm_bwd(ws.dxn, ws.x[i], p[pre + "history_norm.scale"], dscale=p.g(pre + "history_norm.scale"),
                             dres=dx, out=spare)
             dx, spare = spare, dx                                       # dx = d x[i]
+        # the embedding backward uses the same split-K workspace and overwrites `spare`: join the side stream first
+        self._wait(ev_qkv)
         self._embed_bwd(ws, M, dx, batch["last_rewards"], batch["last_actions"], batch.get("task_ids"), batch["obs"])
         return ws.losses
