@@ -118,6 +118,124 @@ __global__ void __launch_bounds__(256) conv1_onehot_fwd_kernel(
   }
 }
 
+// Same layer for the standard geometry (11x11 view, 3x3 stride 2 -> 5x5, 16 output channels), restructured around
+// shared memory like the rollout encoder (obs_fused.cu): per tile of 32 agent-steps the observation bytes are turned
+// into ONE joint code per cell (all K components; digit size_k = out of range), and each output position costs 9
+// conflict-free float4 lookups per channel quad in a joint fp32 table (two bank-disjoint copies) instead of 18 bf16
+// row gathers + unpacking.  Lane = (task of 8, channel quad); tasks run q-fastest so the z / a rows a warp writes are
+// contiguous.
+constexpr int C1J_AG = 32, C1J_MAXJ = 48, C1J_MAXK = 4;
+struct Conv1JointSpec {
+  int K, NJ, C;
+  int sizes[C1J_MAXK], radix[C1J_MAXK], offs[C1J_MAXK + 1];
+};
+__global__ void __launch_bounds__(256) conv1_onehot_joint_kernel(
+    const uint8_t* __restrict__ obs, const __nv_bfloat16* __restrict__ w /* (9*C, 16) */,
+    const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ z_out, __nv_bfloat16* __restrict__ a_out,
+    long long M, Conv1JointSpec spec, int apply_gelu) {
+  extern __shared__ __align__(16) uint8_t cj_smem[];
+  float* sT = reinterpret_cast<float*>(cj_smem);                        // [9][NJ][2 copies][16]
+  uint8_t* sObs = cj_smem + 9 * spec.NJ * 2 * 16 * 4;                   // 32 x 121 x K bytes
+  uint8_t* sCode = sObs + C1J_AG * 121 * C1J_MAXK;                      // 32 x 121 bytes
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // ---- joint table: entry (tap, code, ch) = sum over components with digit_k < size_k of W[tap*C + off_k + digit_k][ch]
+  for (int i = tid; i < 9 * spec.NJ * 16; i += 256) {
+    const int ch = i & 15, code = (i >> 4) % spec.NJ, tap = (i >> 4) / spec.NJ;
+    float acc = 0.f;
+    int rem = code;
+    for (int k = 0; k < spec.K; ++k) {
+      const int digit = rem % (spec.sizes[k] + 1);
+      rem /= (spec.sizes[k] + 1);
+      if (digit < spec.sizes[k]) acc += __bfloat162float(w[(tap * spec.C + spec.offs[k] + digit) * 16 + ch]);
+    }
+    sT[((tap * spec.NJ + code) * 2) * 16 + ch] = acc;
+    sT[((tap * spec.NJ + code) * 2 + 1) * 16 + ch] = acc;
+  }
+  const int cell_bytes = 121 * spec.K;
+  const int tsub = lane >> 2, v = lane & 3;
+  const float* tbase = sT + (tsub & 1) * 16 + 4 * v;
+  const uint2 bv = *reinterpret_cast<const uint2*>(bias + 4 * v);
+  const long long n_tiles = (M + C1J_AG - 1) / C1J_AG;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long m0 = tile * C1J_AG;
+    const int nag = (int)min((long long)C1J_AG, M - m0);
+    __syncthreads();                                                    // previous tile fully consumed (and table built)
+    {
+      const int nbytes = nag * cell_bytes;
+      const uint8_t* src = obs + m0 * cell_bytes;
+      if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const int nw = nbytes >> 4;
+        for (int i = tid; i < nw; i += 256) reinterpret_cast<uint4*>(sObs)[i] = reinterpret_cast<const uint4*>(src)[i];
+        for (int i = (nw << 4) + tid; i < nbytes; i += 256) sObs[i] = src[i];
+      } else {
+        for (int i = tid; i < nbytes; i += 256) sObs[i] = src[i];
+      }
+    }
+    __syncthreads();
+    {
+      const int ncell = nag * 121;
+      const int K = spec.K;
+      const int s0 = spec.sizes[0], s1 = spec.sizes[1], s2 = spec.sizes[2], s3 = spec.sizes[3];
+      const int r1 = spec.radix[1], r2 = spec.radix[2], r3 = spec.radix[3];
+      for (int i4 = tid; i4 * 4 < ncell; i4 += 256) {
+        uint32_t packed = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = i4 * 4 + e;
+          if (i < ncell) {
+            const uint8_t* cell = sObs + i * K;
+            int code = min((int)cell[0], s0);
+            if (K > 1) code += min((int)cell[1], s1) * r1;
+            if (K > 2) code += min((int)cell[2], s2) * r2;
+            if (K > 3) code += min((int)cell[3], s3) * r3;
+            packed |= (uint32_t)code << (8 * e);
+          }
+        }
+        reinterpret_cast<uint32_t*>(sCode)[i4] = packed;
+      }
+    }
+    __syncthreads();
+    for (int g0 = warp; g0 < C1J_AG * 25 / 8; g0 += 16) {                // two task groups in flight per iteration
+      float4 acc[2];
+      int task[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int g = g0 + 8 * u;
+        task[u] = g * 8 + tsub;
+        const int ag = task[u] / 25, q = task[u] % 25;
+        acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g < C1J_AG * 25 / 8 && ag < nag) {
+          const uint8_t* c0 = sCode + ag * 121 + (q / 5) * 22 + (q % 5) * 2;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int code = c0[(tap / 3) * 11 + (tap % 3)];
+            const float4 wv = *reinterpret_cast<const float4*>(tbase + (tap * spec.NJ + code) * 32);
+            acc[u].x += wv.x; acc[u].y += wv.y; acc[u].z += wv.z; acc[u].w += wv.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int ag = task[u] / 25;
+        if (g0 + 8 * u < C1J_AG * 25 / 8 && ag < nag) {
+          const uint32_t z0 = pack_bf16(acc[u].x, acc[u].y), z1 = pack_bf16(acc[u].z, acc[u].w);
+          uint2 zz;
+          zz.x = pack_bf16(bf16_lo(z0) + bf16_lo(bv.x), bf16_hi(z0) + bf16_hi(bv.x));
+          zz.y = pack_bf16(bf16_lo(z1) + bf16_lo(bv.y), bf16_hi(z1) + bf16_hi(bv.y));
+          const long long o = (m0 * 25 + task[u]) * 16 + 4 * v;         // row = (m0 + ag)*25 + q == m0*25 + task
+          if (z_out) *reinterpret_cast<uint2*>(z_out + o) = zz;
+          uint2 aa = zz;
+          if (apply_gelu) {
+            aa.x = pack_bf16(gelu_tanh(bf16_lo(zz.x)), gelu_tanh(bf16_hi(zz.x)));
+            aa.y = pack_bf16(gelu_tanh(bf16_lo(zz.y)), gelu_tanh(bf16_hi(zz.y)));
+          }
+          *reinterpret_cast<uint2*>(a_out + o) = aa;
+        }
+      }
+    }
+  }
+}
+
 // NHWC im2col: a (M, IH, IW, C) bf16 -> x (M*OH*OW, kh*kw*C), C % 8 == 0; one thread per 16-byte piece.
 __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ x, long long M, int IH,
                               int IW, int C, int kh, int kw, int sh, int sw, int OH, int OW) {
@@ -221,6 +339,42 @@ extern "C" int mpx_conv1_onehot_fwd(const uint8_t* obs, const mpx_bf16* w, const
   const int OH = (IH - kh) / sh + 1, OW = (IW - kw) / sw + 1;
   const long long rows = M * OH * OW;
   MPX_REQUIRE(rows * (cout / 8) < (1LL << 31), "mpx_conv1_onehot_fwd: too many rows for 32-bit indexing");
+  {
+    // standard geometry: shared-memory joint-table kernel
+    int nj = 1;
+    for (int i = 0; i < K; ++i) nj *= onehot_sizes[i] + 1;
+    if (IH == 11 && IW == 11 && kh == 3 && kw == 3 && sh == 2 && sw == 2 && cout == 16 && nj <= C1J_MAXJ &&
+        (reinterpret_cast<uintptr_t>(a_out) & 7) == 0 && (!z_out || (reinterpret_cast<uintptr_t>(z_out) & 7) == 0) &&
+        (reinterpret_cast<uintptr_t>(bias) & 7) == 0) {
+      Conv1JointSpec js = {};
+      js.K = K; js.NJ = nj; js.C = C;
+      int radix = 1;
+      for (int i = 0; i < C1J_MAXK; ++i) {
+        js.sizes[i] = i < K ? onehot_sizes[i] : 0;
+        js.radix[i] = i < K ? radix : 0;
+        js.offs[i] = spec.offs[i < K ? i : K];
+        if (i < K) radix *= onehot_sizes[i] + 1;
+      }
+      js.offs[C1J_MAXK] = C;
+      const int jsmem = 9 * nj * 2 * 16 * 4 + C1J_AG * 121 * C1J_MAXK + C1J_AG * 121 + 16;
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv1_onehot_joint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e != cudaSuccess) {
+          set_error("cudaFuncSetAttribute(conv1_onehot_joint): %s", cudaGetErrorString(e));
+          return MPX_ERR_CUDA;
+        }
+        attr_set = true;
+      }
+      const long long tiles = (M + C1J_AG - 1) / C1J_AG;
+      long long grid = (long long)num_sms() * 3;
+      if (grid > tiles) grid = tiles;
+      conv1_onehot_joint_kernel<<<(int)grid, 256, jsmem, (cudaStream_t)stream>>>(
+          obs, reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<const __nv_bfloat16*>(bias),
+          reinterpret_cast<__nv_bfloat16*>(z_out), reinterpret_cast<__nv_bfloat16*>(a_out), M, js, apply_gelu);
+      return check_launch("mpx_conv1_onehot_fwd(joint)");
+    }
+  }
   conv1_onehot_fwd_kernel<<<cv_grid(rows * (cout / 8)), 256, smem, (cudaStream_t)stream>>>(
       obs, reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<const __nv_bfloat16*>(bias),
       reinterpret_cast<__nv_bfloat16*>(z_out), reinterpret_cast<__nv_bfloat16*>(a_out), rows, IH, IW, spec, kh, kw, sh, sw,
