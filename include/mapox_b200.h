@@ -133,9 +133,13 @@ int mpx_glu_up(const mpx_glu_up_args* a, mpx_stream_t stream);
  * out = bf16(residual + bf16(h @ Wdown)), h = bf16(bf16(gelu(bf16(x@Wup))) * bf16(x@Wgate)); h stays on chip.
  * wt_ug64 is (2F,H) packed in 128-row tiles [64 up rows | 64 gate rows]; wt_d is Wdown^T (H,F).  H must be 128.
  * norm_scale (H) f32, when not NULL, applies RMSNorm(x; scale, eps) to the rows first (network.py:167: ffn_norm), so
- * the caller passes the un-normalised residual stream as both x and residual. */
+ * the caller passes the un-normalised residual stream as both x and residual.
+ * wt_o (H,H) = Wo^T, when not NULL (requires norm_scale), folds the attention output projection and its residual add
+ * (network.py:163-165) in front: x is then the attention output and the kernel computes
+ * x1 = residual + x @ Wo, out = x1 + GLU(RMSNorm(x1)); x1 never leaves shared memory. */
 int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const mpx_bf16* wt_d, const mpx_bf16* residual,
-                  mpx_bf16* out, int M, int H, int F, const float* norm_scale, float eps, mpx_stream_t stream);
+                  mpx_bf16* out, int M, int H, int F, const float* norm_scale, float eps, const mpx_bf16* wt_o,
+                  mpx_stream_t stream);
 
 /* Whole value path of a rollout step in one kernel (network.py:321,335-341 + values.py:40-45):
  * value = sum softmax(f32(pv) @ Wvh + b_vh) * centers, pv = bf16(gelu(bf16(bf16(xf @ Wvm) + b_vm))),

@@ -21,7 +21,7 @@
 
 namespace mpx {
 
-constexpr int GF_STAGES = 6;
+constexpr int GF_STAGES = 4;
 constexpr int GF_STAGE_BYTES = 16384;   // [128 rows x 64 cols] bf16, SW128
 constexpr int GF_THREADS = 320;
 constexpr int GF_EPI_WARPS = 8;
@@ -35,6 +35,7 @@ struct GluFusedParams {
   __nv_bfloat16* out;
   const float* norm_scale;        // (128) fp32: RMSNorm applied to the x tile in shared memory before MMA1; or null
   float eps;
+  int proj;                       // 1: x is the attention output; x1 = residual + x @ Wo^T is formed first
   unsigned long long* dbg;
 };
 
@@ -44,7 +45,8 @@ __device__ __forceinline__ void gf_bar_sync(int id, int nthreads) {
 
 __global__ void __launch_bounds__(GF_THREADS, 1)
 glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_x,
-                 const __grid_constant__ CUtensorMap tm_wug, const __grid_constant__ CUtensorMap tm_wd) {
+                 const __grid_constant__ CUtensorMap tm_wug, const __grid_constant__ CUtensorMap tm_wd,
+                 const __grid_constant__ CUtensorMap tm_wo) {
   extern __shared__ uint8_t smem_raw[];
   // the dynamic window starts at the same shared::cta offset in every CTA of the cluster, so the aligned
   // carve-up below is identical across the cluster (mapa relies on that)
@@ -53,7 +55,8 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
   uint8_t* sH = smem + 32768;                 // 2 x 16 KB: h chunk double buffer
   uint8_t* sW = smem + 65536;                 // GF_STAGES x 16 KB weight ring
   uint8_t* sP = sW + GF_STAGES * GF_STAGE_BYTES;   // fp32 partial (cluster reduction staging)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + GF_PART_BYTES);
+  uint8_t* sX1 = sP + GF_PART_BYTES;          // 32 KB: x1 rows (bf16, 256 B each, 16-byte chunks XOR-swizzled by row) [proj]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX1 + 32768);
   uint64_t* w_full = bars;                    // [GF_STAGES]
   uint64_t* w_empty = bars + GF_STAGES;       // [GF_STAGES]
   uint64_t* x_full = bars + 2 * GF_STAGES;
@@ -67,8 +70,9 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
   uint64_t* part_full = x_full + 12;          // all partials of the cluster written (remote arrivals)
   uint64_t* part_empty = x_full + 13;         // all readers of MY partial done (remote arrivals)
   uint64_t* xn_ready = x_full + 14;           // x tile landed and (optionally) normalised in place
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 15);
-  float* sSq = reinterpret_cast<float*>(x_full + 16);   // 2 x 128 partial sums of squares (RMSNorm prologue)
+  uint64_t* d0_full = x_full + 15;            // [proj] x @ Wo^T accumulated in the tD columns
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 16);
+  float* sSq = reinterpret_cast<float*>(x_full + 18);   // 2 x 128 partial sums of squares (RMSNorm prologue)
   float* sScale = sSq + 256;                            // norm scale (128)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -84,6 +88,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_wug);
     tma_prefetch_desc(&tm_wd);
+    if (p.proj) tma_prefetch_desc(&tm_wo);
     for (int s = 0; s < GF_STAGES; ++s) {
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
@@ -101,6 +106,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
     mbar_init(part_full, 1);                   // one arrive.expect_tx per tile; the pushed bytes complete it
     mbar_init(part_empty, GF_EPI_WARPS * ncta);
     mbar_init(xn_ready, GF_EPI_WARPS);
+    mbar_init(d0_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -136,7 +142,11 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         tma_load_2d(&tm_x, x_full, sX, 0, tile * 128);
         tma_load_2d(&tm_x, x_full, sX + 16384, 64, tile * 128);
         xphase ^= 1;
-        // weight order == MMA issue order: UG_0, then for each c: UG_{c+1} (if any), D_c
+        // weight order == MMA issue order: [Wo K blocks], UG_0, then for each c: UG_{c+1} (if any), D_c
+        if (p.proj) {
+          load_w(&tm_wo, 0, 0);
+          load_w(&tm_wo, 64, 0);
+        }
         load_w(&tm_wug, 0, chunk0 * 128);
         load_w(&tm_wug, 64, chunk0 * 128);
         for (int c = 0; c < nchunks; ++c) {
@@ -193,9 +203,28 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         if (last) umma_commit(d_full);
       };
       for (int tile = blockIdx.y; tile < m_tiles; tile += gridDim.y) {
+        if (p.proj) {
+          // x1 accumulator = ao . Wo^T in the tD columns (free: the previous tile's output has been drained)
+          mbar_wait(x_full, xphase);
+          mbar_wait(d_empty, dphase ^ 1);
+          tc_fence_after();
+          for (int kb = 0; kb < 2; ++kb) {
+            mbar_wait(&w_full[stage], wphase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(sX + kb * 16384);
+            const uint32_t sb = smem_u32(sW + stage * GF_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tD, umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024),
+                        idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&w_empty[stage]);
+            if (++stage == GF_STAGES) { stage = 0; wphase ^= 1; }
+          }
+          umma_commit(d0_full);
+        }
         mbar_wait(xn_ready, xphase);
         xphase ^= 1;
-        mbar_wait(d_empty, dphase ^ 1);       // previous tile's output accumulator has been drained
+        if (!p.proj) mbar_wait(d_empty, dphase ^ 1);   // previous tile's output accumulator has been drained
         dphase ^= 1;
         tc_fence_after();
         mma1(0, nchunks == 1);
@@ -220,6 +249,56 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
       const long long row = (long long)tile * 128 + r;
       if (ncta > 1 && warp == 2 && lane == 0) mbar_arrive_expect_tx(part_full, GF_PART_BYTES);   // 128 rows x slice x 4 B x CL
       // ---- optional RMSNorm of the x tile, in place in the swizzled layout (this warp: K block `half` of its rows)
+      if (p.proj) {
+        // ---- x1 = bf16(bf16(ao @ Wo) + x): kept in smem for the final residual; RMSNorm(x1) becomes the MMA1 operand
+        if (tile != (int)blockIdx.y) gf_bar_sync(1, GF_EPI_WARPS * 32);   // every reader of the previous tile's x1 rows is done
+        uint4 rx[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          rx[c] = row < p.M ? *reinterpret_cast<const uint4*>(p.residual + row * 128 + 64 * half + 8 * c) : make_uint4(0, 0, 0, 0);
+        mbar_wait(d0_full, xphase);
+        tc_fence_after();
+        dbg_stamp(dbg, 2);
+        uint32_t a0[32], a1[32];
+        tmem_ld_32x32(tD + lane_off + 64 * half, a0);
+        tmem_ld_32x32(tD + lane_off + 64 * half + 32, a1);
+        tmem_ld_wait();
+        tc_fence_before();
+        uint32_t xw[32];
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const uint32_t* acc = i < 16 ? a0 : a1;
+          const int j = i & 15;
+          const uint32_t yw = pack_bf16(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+          const uint32_t rw = (i & 3) == 0 ? rx[i >> 2].x : (i & 3) == 1 ? rx[i >> 2].y : (i & 3) == 2 ? rx[i >> 2].z : rx[i >> 2].w;
+          xw[i] = pack_bf16(bf16_lo(yw) + bf16_lo(rw), bf16_hi(yw) + bf16_hi(rw));
+          const float a = bf16_lo(xw[i]), b2 = bf16_hi(xw[i]);
+          ss += a * a + b2 * b2;
+        }
+        const uint32_t x1row = smem_u32(sX1 + r * 256);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          sts_v4(x1row + (((8 * half + c) ^ (r & 7)) << 4), make_uint4(xw[4 * c], xw[4 * c + 1], xw[4 * c + 2], xw[4 * c + 3]));
+        sSq[half * 128 + r] = ss;
+        gf_bar_sync(1, GF_EPI_WARPS * 32);
+        const float inv = rsqrtf((sSq[r] + sSq[128 + r]) * (1.0f / 128.0f) + p.eps);
+        const float4* sc4 = reinterpret_cast<const float4*>(sScale + half * 64);
+        const uint32_t xrow = smem_u32(sX + half * 16384 + r * 128);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1];
+          uint4 o;
+          o.x = pack_bf16(bf16_lo(xw[4 * c]) * inv * s0.x, bf16_hi(xw[4 * c]) * inv * s0.y);
+          o.y = pack_bf16(bf16_lo(xw[4 * c + 1]) * inv * s0.z, bf16_hi(xw[4 * c + 1]) * inv * s0.w);
+          o.z = pack_bf16(bf16_lo(xw[4 * c + 2]) * inv * s1.x, bf16_hi(xw[4 * c + 2]) * inv * s1.y);
+          o.w = pack_bf16(bf16_lo(xw[4 * c + 3]) * inv * s1.z, bf16_hi(xw[4 * c + 3]) * inv * s1.w);
+          sts_v4(xrow + ((c ^ (r & 7)) << 4), o);
+        }
+        fence_proxy_async_smem();
+        gf_bar_sync(1, GF_EPI_WARPS * 32);                     // sSq / sX1 complete for every row
+        xphase ^= 1;
+      } else {
       mbar_wait(x_full, xphase);
       xphase ^= 1;
       dbg_stamp(dbg, 2);
@@ -253,6 +332,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         }
         fence_proxy_async_smem();
         gf_bar_sync(1, GF_EPI_WARPS * 32);                     // sSq may be rewritten by the next tile
+      }
       }
       __syncwarp();
       dbg_stamp(dbg, 3);
@@ -307,7 +387,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
             uint4* o4 = reinterpret_cast<uint4*>(p.out + row * 128 + 64 * half + 32 * cc);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const uint4 rv = r4[i];
+              const uint4 rv = p.proj ? lds_v4(smem_u32(sX1 + r * 256) + (((8 * half + 4 * cc + i) ^ (r & 7)) << 4)) : r4[i];
               const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
               uint32_t ow[4];
 #pragma unroll
@@ -334,7 +414,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         const int per_owner = slice / 4;                       // float4 column groups per owner: 8 (CL 4) or 16 (CL 2)
         // residual of my output slice: in flight while the partials are exchanged
         uint4 rres[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (ncta == 4 && row < p.M) {
+        if (ncta == 4 && row < p.M && !p.proj) {
           rres[0] = *reinterpret_cast<const uint4*>(p.residual + row * 128 + ocol0);
           rres[1] = *reinterpret_cast<const uint4*>(p.residual + row * 128 + ocol0 + 8);
         }
@@ -377,7 +457,8 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
           }
           if (row < p.M) {
             const long long o = row * 128 + ocol0 + 4 * i;
-            const uint4 rv = (ncta == 4) ? rres[(i >> 1) & 1] : *reinterpret_cast<const uint4*>(p.residual + o);
+            const uint4 rv = p.proj ? lds_v4(smem_u32(sX1 + r * 256) + ((((ocol0 + 4 * i) >> 3) ^ (r & 7)) << 4))
+                                    : (ncta == 4) ? rres[(i >> 1) & 1] : *reinterpret_cast<const uint4*>(p.residual + o);
             uint4 ov;
             ov.x = pack_bf16(bf16_round(s0.x) + bf16_lo(rv.x), bf16_round(s0.y) + bf16_hi(rv.x));
             ov.y = pack_bf16(bf16_round(s0.z) + bf16_lo(rv.y), bf16_round(s0.w) + bf16_hi(rv.y));
@@ -408,19 +489,22 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
 using namespace mpx;
 
 extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const mpx_bf16* wt_d, const mpx_bf16* residual,
-                             mpx_bf16* out, int M, int H, int F, const float* norm_scale, float eps,
+                             mpx_bf16* out, int M, int H, int F, const float* norm_scale, float eps, const mpx_bf16* wt_o,
                              mpx_stream_t stream) {
   MPX_REQUIRE(x && wt_ug64 && wt_d && residual && out && M > 0, "mpx_glu_fused: bad arguments");
   MPX_REQUIRE(H == 128, "mpx_glu_fused: hidden_features=%d unsupported (128 only; use mpx_glu_up + mpx_linear)", H);
   MPX_REQUIRE(F > 0 && F % 64 == 0, "mpx_glu_fused: F=%d must be a positive multiple of 64", F);
-  CUtensorMap tm_x, tm_wug, tm_wd;
+  MPX_REQUIRE(!wt_o || norm_scale, "mpx_glu_fused: the projection prologue needs norm_scale");
+  CUtensorMap tm_x, tm_wug, tm_wd, tm_wo;
   int rc = make_tmap_bf16_2d(&tm_x, x, M, H, H, 64, 128);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_wug, wt_ug64, 2 * F, H, H, 64, 128);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_wd, wt_d, H, F, F, 64, 128);
   if (rc) return rc;
-  const int smem = 1024 + 65536 + GF_STAGES * GF_STAGE_BYTES + GF_PART_BYTES + 256 + 1024 + 512;
+  rc = make_tmap_bf16_2d(&tm_wo, wt_o ? wt_o : wt_d, H, H, wt_o ? H : F, 64, 128);
+  if (rc) return rc;
+  const int smem = 1024 + 65536 + GF_STAGES * GF_STAGE_BYTES + GF_PART_BYTES + 32768 + 256 + 1024 + 512;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(glu_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -436,6 +520,7 @@ extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const m
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.norm_scale = norm_scale;
   p.eps = eps;
+  p.proj = wt_o ? 1 : 0;
   p.dbg = g_dbg_stamps;
   MPX_REQUIRE(!norm_scale || (reinterpret_cast<uintptr_t>(norm_scale) & 15) == 0, "mpx_glu_fused: norm_scale must be 16-byte aligned");
   const int tiles = ceil_div(M, 128);
@@ -448,7 +533,7 @@ extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const m
     cl = g_glu_fused_cluster;
   int gy = num_sms() / cl;
   if (gy > tiles) gy = tiles;
-  cudaError_t le = launch_ex(glu_fused_kernel, dim3(cl, gy, 1), dim3(GF_THREADS), smem, (cudaStream_t)stream, cl, true, p, tm_x, tm_wug, tm_wd);
+  cudaError_t le = launch_ex(glu_fused_kernel, dim3(cl, gy, 1), dim3(GF_THREADS), smem, (cudaStream_t)stream, cl, true, p, tm_x, tm_wug, tm_wd, tm_wo);
   if (le != cudaSuccess) {
     set_error("cudaLaunchKernelEx(glu_fused, cluster %d): %s", cl, cudaGetErrorString(le));
     return MPX_ERR_CUDA;

@@ -337,6 +337,12 @@ class PolicyEngine:
                          k=ws.kcache[i], v=ws.vcache[i], k_row_stride=S * self.KD, v_row_stride=S * self.KD,
                          cache_S=S)
             ops.attn_decode(ws.q, ws.kcache[i], ws.vcache[i], pos, self.Nq, self.Nkv, self.D, out=ws.ao)
+            if self.fused_glu and self.QD == 128:
+                # out projection + residual, ffn_norm, GLU and its residual in ONE kernel (x1 stays in shared memory)
+                ops.glu_fused(ws.ao, w[pre + "wt_ug64"], w[pre + "wt_d"], x, other, self.F,
+                              norm_scale=p[pre + "ffn_norm.scale"], wt_o=w[pre + "wt_o"])
+                x, other = other, x
+                continue
             ops.linear(ws.ao, w[pre + "wt_o"], residual=x, out=other)
             x, other = other, x
             if self.fused_glu:                                # ffn_norm is applied inside the kernel

@@ -185,13 +185,14 @@ def glu_up(x, wt_ug, F: int, save: bool = False, h=None, u=None, g=None):
     return (h, u, g) if save else h
 
 
-def glu_fused(x, wt_ug64, wt_d, residual, out, F: int, norm_scale=None, eps: float = 1e-6):
-    """out = residual + down(gelu(up(xn)) * gate(xn)) in one kernel (H = 128); xn = RMSNorm(x) when norm_scale is given."""
+def glu_fused(x, wt_ug64, wt_d, residual, out, F: int, norm_scale=None, eps: float = 1e-6, wt_o=None):
+    """out = residual + down(gelu(up(xn)) * gate(xn)) in one kernel (H = 128); xn = RMSNorm(x) when norm_scale is given.
+    With wt_o (Wo^T): x is the attention output, x1 = residual + x @ Wo, out = x1 + GLU(RMSNorm(x1))."""
     _req(x, BF16, "x"); _req(wt_ug64, BF16, "wt_ug64"); _req(wt_d, BF16, "wt_d"); _req(residual, BF16, "residual")
     H = x.shape[-1]
     M = x.numel() // H
     check(lib.mpx_glu_fused(ptr(x), ptr(wt_ug64), ptr(wt_d), ptr(residual), ptr(out), M, H, F, ptr(norm_scale), eps,
-                            stream()), "mpx_glu_fused")
+                            ptr(wt_o), stream()), "mpx_glu_fused")
     return out
 
 

@@ -580,3 +580,32 @@ def test_conv1_onehot_wgrad(ops, M, sizes):
     ops.conv1_onehot_wgrad(obs.to(DEV), dz.to(DEV), dw, M, IH, IW, sizes, 3, 3, 2, 2, cout)
     torch.cuda.synchronize()
     torch.testing.assert_close(dw.cpu().double() - 0.5, ref, rtol=1e-4, atol=1e-3 * max(1.0, math.sqrt(M)))
+
+
+@pytest.mark.parametrize("M,F,cluster", [(77, 768, 0), (4096, 768, 0), (4096, 768, 1), (4096, 768, 2), (20000, 768, 0),
+                                         (20000, 512, 4), (300, 192, 0)])
+def test_glu_fused_with_out_projection(ops, M, F, cluster):
+    """Attention output projection + residual + ffn_norm + GLU + residual in one kernel vs the oracle block tail."""
+    from jaxrl_b200._lib import lib
+    gen = g(M + F + cluster + 7)
+    H = 128
+    ao = torch.randn(M, H, generator=gen).to(BF16)
+    x = torch.randn(M, H, generator=gen).to(BF16)
+    wo = torch.randn(H, H, generator=gen) / math.sqrt(H)            # (in = heads*dim, out = H)
+    wu = torch.randn(H, F, generator=gen) / math.sqrt(H)
+    wg = torch.randn(H, F, generator=gen) / math.sqrt(H)
+    wd = torch.randn(F, H, generator=gen) / math.sqrt(F)
+    scale = 1.0 + 0.1 * torch.randn(H, generator=gen)
+    x1 = (O.linear(ao, wo).float() + x.float()).to(BF16)
+    pdict = {"f.up_proj.kernel": wu, "f.up_gate.kernel": wg, "f.down_proj.kernel": wd}
+    ref = (O.glu_block(pdict, "f.", O.rms_norm(x1, scale)).float() + x1.float()).to(BF16)
+    out = torch.empty(M, H, dtype=BF16, device=DEV)
+    lib.mpx_debug_set(3, cluster)
+    try:
+        ops.glu_fused(ao.to(DEV), ops.pack_glu_weight64(wu, wg).to(DEV), wd.t().contiguous().to(BF16).to(DEV), x.to(DEV), out, F,
+                      norm_scale=scale.to(DEV), wt_o=wo.t().contiguous().to(BF16).to(DEV))
+        torch.cuda.synchronize()
+    finally:
+        lib.mpx_debug_set(3, 0)
+    assert_close_bf16(out, ref, f"glu_fused+proj M={M} F={F} cl={cluster}", rtol=1e-2, abs_floor_frac=1e-2, allow_frac=2e-3,
+                      max_err_frac=0.1)
