@@ -308,11 +308,12 @@ int mpx_obs_onehot_im2col(const uint8_t* obs, mpx_bf16* out, long long M, int IH
 int mpx_conv1_onehot_fwd(const uint8_t* obs, const mpx_bf16* w, const mpx_bf16* bias, mpx_bf16* z_out, mpx_bf16* a_out,
                          long long M, int IH, int IW, int K, const int* onehot_sizes, int kh, int kw, int sh, int sw,
                          int cout, int apply_gelu, mpx_stream_t stream);
-/* NHWC im2col / its transpose for the hidden conv layers (C % 8 == 0, VALID padding). */
+/* NHWC im2col / its transpose for the hidden conv layers (C % 8 == 0, VALID padding).  mpx_col2im's optional z
+ * (M,IH,IW,C) folds the activation transpose of the layer below into the same pass: da = bf16(bf16(sum) * gelu'(z)). */
 int mpx_im2col(const mpx_bf16* a, mpx_bf16* x, long long M, int IH, int IW, int C, int kh, int kw, int sh, int sw,
                mpx_stream_t stream);
 int mpx_col2im(const mpx_bf16* dx, mpx_bf16* da, long long M, int IH, int IW, int C, int kh, int kw, int sh, int sw,
-               mpx_stream_t stream);
+               const mpx_bf16* z, mpx_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------- optimizer
  * optimizer.py:12-23: optax.adamw(linear_schedule(lr0, 0, total_steps)) then clip_by_global_norm(max_norm) on the

@@ -124,7 +124,7 @@ lib.mpx_policy_head_bwd.argtypes = [c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_i, c_i
 lib.mpx_obs_onehot_im2col.argtypes = [c_p, c_p, c_ll, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_p]
 lib.mpx_conv1_onehot_fwd.argtypes = [c_p, c_p, c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p]
 lib.mpx_im2col.argtypes = [c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]
-lib.mpx_col2im.argtypes = [c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]
+lib.mpx_col2im.argtypes = [c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]
 lib.mpx_adamw_workspace_bytes.restype = C.c_size_t
 lib.mpx_adamw_workspace_bytes.argtypes = [c_ll]
 lib.mpx_adamw_step.argtypes = [c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_p,

@@ -257,11 +257,17 @@ __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16
 }
 
 // Transpose of im2col: da (M, IH, IW, C) = sum of the dx patches covering each cell (fp32 sum, bf16 store).
-__global__ void col2im_kernel(const __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ da, long long M, int IH,
-                              int IW, int C, int kh, int kw, int sh, int sw, int OH, int OW) {
+// z (same shape as da, nullable): also applies the activation transpose dz = bf16(da * gelu'(z)) in the same pass.
+// KH/KW/SH/SW > 0: compile-time geometry (unrolled, predicated loads); 0: runtime geometry.
+template <int KH, int KW, int SH, int SW>
+__global__ void __launch_bounds__(256) col2im_kernel(const __nv_bfloat16* __restrict__ dx, const __nv_bfloat16* __restrict__ z,
+                                                     __nv_bfloat16* __restrict__ da, long long M, int IH, int IW, int C,
+                                                     int kh_, int kw_, int sh_, int sw_, int OH, int OW) {
+  const int kh = KH > 0 ? KH : kh_, kw = KW > 0 ? KW : kw_, sh = SH > 0 ? SH : sh_, sw = SW > 0 ? SW : sw_;
   const int cp = C / 8;
   const unsigned total = (unsigned)(M * IH * IW * cp);                 // host guarantees < 2^31
   const unsigned stride = gridDim.x * blockDim.x;
+  const int patch = kh * kw * C;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int c8 = (int)(i % (unsigned)cp);
     unsigned r = i / (unsigned)cp;
@@ -269,21 +275,48 @@ __global__ void col2im_kernel(const __nv_bfloat16* __restrict__ dx, __nv_bfloat1
     const int iy = (int)((r / (unsigned)IW) % (unsigned)IH);
     const long long m = r / (unsigned)(IW * IH);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int ky = 0; ky < kh; ++ky) {
-      const int ny = iy - ky;
-      if (ny < 0 || ny % sh != 0 || ny / sh >= OH) continue;
-      for (int kx = 0; kx < kw; ++kx) {
-        const int nx = ix - kx;
-        if (nx < 0 || nx % sw != 0 || nx / sw >= OW) continue;
-        const uint4 v = *reinterpret_cast<const uint4*>(
-            dx + ((m * OH + ny / sh) * OW + nx / sw) * (long long)(kh * kw * C) + (ky * kw + kx) * C + c8 * 8);
-        acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
-        acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+    const __nv_bfloat16* base = dx + m * OH * OW * (long long)patch + c8 * 8;
+    if (KH > 0) {
+      uint4 v[KH > 0 ? KH * KW : 1];
+#pragma unroll
+      for (int ky = 0; ky < (KH > 0 ? KH : 1); ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < (KW > 0 ? KW : 1); ++kx) {
+          const int ny = iy - ky, nx = ix - kx;
+          const bool ok = ny >= 0 && nx >= 0 && (SH == 1 || ny % sh == 0) && (SW == 1 || nx % sw == 0) && ny / sh < OH && nx / sw < OW;
+          v[ky * (KW > 0 ? KW : 1) + kx] = ok ? *reinterpret_cast<const uint4*>(base + ((ny / sh) * OW + nx / sw) * patch + (ky * kw + kx) * C)
+                                               : make_uint4(0, 0, 0, 0);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < (KH > 0 ? KH * KW : 1); ++t) {
+        acc[0] += bf16_lo(v[t].x); acc[1] += bf16_hi(v[t].x); acc[2] += bf16_lo(v[t].y); acc[3] += bf16_hi(v[t].y);
+        acc[4] += bf16_lo(v[t].z); acc[5] += bf16_hi(v[t].z); acc[6] += bf16_lo(v[t].w); acc[7] += bf16_hi(v[t].w);
+      }
+    } else {
+      for (int ky = 0; ky < kh; ++ky) {
+        const int ny = iy - ky;
+        if (ny < 0 || ny % sh != 0 || ny / sh >= OH) continue;
+        for (int kx = 0; kx < kw; ++kx) {
+          const int nx = ix - kx;
+          if (nx < 0 || nx % sw != 0 || nx / sw >= OW) continue;
+          const uint4 v = *reinterpret_cast<const uint4*>(base + ((ny / sh) * OW + nx / sw) * patch + (ky * kw + kx) * C);
+          acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+          acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+        }
       }
     }
-    *reinterpret_cast<uint4*>(da + ((m * IH + iy) * IW + ix) * C + c8 * 8) =
-        make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
-                   pack_bf16(acc[6], acc[7]));
+    const long long o = ((m * IH + iy) * IW + ix) * C + c8 * 8;
+    uint4 out = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
+                           pack_bf16(acc[6], acc[7]));
+    if (z) {
+      const uint4 zv = *reinterpret_cast<const uint4*>(z + o);
+      out.x = pack_bf16(bf16_lo(out.x) * gelu_tanh_grad(bf16_lo(zv.x)), bf16_hi(out.x) * gelu_tanh_grad(bf16_hi(zv.x)));
+      out.y = pack_bf16(bf16_lo(out.y) * gelu_tanh_grad(bf16_lo(zv.y)), bf16_hi(out.y) * gelu_tanh_grad(bf16_hi(zv.y)));
+      out.z = pack_bf16(bf16_lo(out.z) * gelu_tanh_grad(bf16_lo(zv.z)), bf16_hi(out.z) * gelu_tanh_grad(bf16_hi(zv.z)));
+      out.w = pack_bf16(bf16_lo(out.w) * gelu_tanh_grad(bf16_lo(zv.w)), bf16_hi(out.w) * gelu_tanh_grad(bf16_hi(zv.w)));
+    }
+    *reinterpret_cast<uint4*>(da + o) = out;
   }
 }
 
@@ -393,11 +426,18 @@ extern "C" int mpx_im2col(const mpx_bf16* a, mpx_bf16* x, long long M, int IH, i
 }
 
 extern "C" int mpx_col2im(const mpx_bf16* dx, mpx_bf16* da, long long M, int IH, int IW, int C, int kh, int kw, int sh,
-                          int sw, mpx_stream_t stream) {
+                          int sw, const mpx_bf16* z, mpx_stream_t stream) {
   MPX_REQUIRE(dx && da && M > 0 && C % 8 == 0 && IH >= kh && IW >= kw && sh > 0 && sw > 0, "mpx_col2im: bad arguments");
   MPX_REQUIRE(M * IH * IW * (C / 8) < (1LL << 31), "mpx_col2im: too many elements for 32-bit indexing");
   const int OH = (IH - kh) / sh + 1, OW = (IW - kw) / sw + 1;
-  col2im_kernel<<<cv_grid(M * IH * IW * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(da), M, IH, IW, C, kh, kw, sh, sw, OH, OW);
+  const int grid = cv_grid(M * IH * IW * (C / 8));
+  if (kh == 3 && kw == 3 && sh == 1 && sw == 1)
+    col2im_kernel<3, 3, 1, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(z),
+        reinterpret_cast<__nv_bfloat16*>(da), M, IH, IW, C, kh, kw, sh, sw, OH, OW);
+  else
+    col2im_kernel<0, 0, 0, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(z),
+        reinterpret_cast<__nv_bfloat16*>(da), M, IH, IW, C, kh, kw, sh, sw, OH, OW);
   return check_launch("mpx_col2im");
 }

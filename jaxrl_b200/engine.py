@@ -293,11 +293,13 @@ class PolicyEngine:
                       p.g("action_embedder.embedding_table"), gt)
         n = len(self.conv)
         dy = dx0                      # cotangent of the last conv's output (M, H)
+        fused_gelu = False
         for c in reversed(self.conv):
             last = c.j == n - 1
             rows = M * c.oh * c.ow
-            if not last:
+            if not last and not fused_gelu:
                 ops.gelu_bwd(dy, ws.cz[c.j], out=dy)          # dz in place
+            fused_gelu = False
             ops.colsum(dy, p.g(f"obs_encoder.layers.{c.j}.bias"), M=rows, N=c.cout, ld=c.cout)
             if c.j == 0 and self.onehot_wgrad:     # one-hot operand tiles are generated inside the wgrad kernel
                 ops.conv1_onehot_wgrad(obs, dy, p.g("obs_encoder.layers.0.kernel").view(c.k, c.cout), M, c.ih, c.iw,
@@ -314,7 +316,9 @@ class PolicyEngine:
                 ops.linear(dy, w[f"w_c{c.j}"], out=ws.dca[c.j - 1].view(M, c.k), M=rows)
             else:
                 ops.linear(dy, w[f"w_c{c.j}"], out=ws.dcx[c.j], M=rows)
-                ops.col2im(ws.dcx[c.j], ws.dca[c.j - 1], M, c.ih, c.iw, c.cin, c.kh, c.kw, c.sh, c.sw)
+                # the layer below is never the last one: its gelu transpose rides along with the scatter-sum
+                ops.col2im(ws.dcx[c.j], ws.dca[c.j - 1], M, c.ih, c.iw, c.cin, c.kh, c.kw, c.sh, c.sw, z=ws.cz[c.j - 1])
+                fused_gelu = True
             dy = ws.dca[c.j - 1]
 
     # ------------------------------------------------------------------------------------------ decode step

@@ -467,8 +467,9 @@ def im2col(a, out, M: int, IH: int, IW: int, Cc: int, kh, kw, sh, sw):
     return out
 
 
-def col2im(dx, out, M: int, IH: int, IW: int, Cc: int, kh, kw, sh, sw):
-    check(lib.mpx_col2im(ptr(dx), ptr(out), M, IH, IW, Cc, kh, kw, sh, sw, stream()), "mpx_col2im")
+def col2im(dx, out, M: int, IH: int, IW: int, Cc: int, kh, kw, sh, sw, z=None):
+    """Transpose of im2col; with z also the gelu transpose of the layer below: out = bf16(bf16(sum) * gelu'(z))."""
+    check(lib.mpx_col2im(ptr(dx), ptr(out), M, IH, IW, Cc, kh, kw, sh, sw, ptr(z), stream()), "mpx_col2im")
     return out
 
 

@@ -609,3 +609,25 @@ def test_glu_fused_with_out_projection(ops, M, F, cluster):
         lib.mpx_debug_set(3, 0)
     assert_close_bf16(out, ref, f"glu_fused+proj M={M} F={F} cl={cluster}", rtol=1e-2, abs_floor_frac=1e-2, allow_frac=2e-3,
                       max_err_frac=0.1)
+
+
+@pytest.mark.parametrize("geom", [(5, 5, 16, 3, 3, 1, 1), (11, 11, 8, 3, 3, 2, 2), (6, 7, 8, 2, 3, 1, 2)])
+@pytest.mark.parametrize("with_z", [False, True])
+def test_col2im(ops, geom, with_z):
+    """Transpose of im2col (scatter-sum of patches), optionally fused with the gelu transpose of the layer below."""
+    IH, IW, C, kh, kw, sh, sw = geom
+    gen = g(sum(geom) + with_z)
+    M = 300
+    OH, OW = (IH - kh) // sh + 1, (IW - kw) // sw + 1
+    dx = torch.randn(M * OH * OW, kh * kw * C, generator=gen).to(BF16)
+    z = torch.randn(M, IH, IW, C, generator=gen).to(BF16)
+    # reference: fold (fp32 sum) -> bf16 -> * gelu'(z) -> bf16
+    cols = dx.float().reshape(M, OH * OW, kh * kw, C).permute(0, 3, 2, 1).reshape(M, C * kh * kw, OH * OW)
+    ref = torch.nn.functional.fold(cols, (IH, IW), (kh, kw), stride=(sh, sw)).permute(0, 2, 3, 1).to(BF16)
+    if with_z:
+        zf = z.float().requires_grad_(True)
+        O.gelu_tanh(zf).sum().backward()
+        ref = (ref.float() * zf.grad).to(BF16)
+    out = torch.empty(M, IH, IW, C, dtype=BF16, device=DEV)
+    ops.col2im(dx.to(DEV), out, M, IH, IW, C, kh, kw, sh, sw, z=z.to(DEV) if with_z else None)
+    assert_close_bf16(out, ref, f"col2im {geom} z={with_z}", rtol=1e-2, abs_floor_frac=4e-3)
