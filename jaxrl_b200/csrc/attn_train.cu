@@ -174,18 +174,29 @@ __global__ void __launch_bounds__(G * 128) attn_fwd_kernel(
 
 // ================================================================================================ backward
 // delta[token, head] = sum_d dO * O  (fp32)
+// 4 lanes per (token, head): 16-byte loads, two xor-shuffles.
 __global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo,
                                       const __nv_bfloat16* __restrict__ o, long long ldo, float* __restrict__ delta,
                                       long long M, int Nq) {
   const int lane = threadIdx.x & 31;
-  long long idx = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long stride = (long long)gridDim.x * (blockDim.x >> 5);
-  for (; idx < M * Nq; idx += stride) {
-    const long long tok = idx / Nq;
-    const int h = (int)(idx % Nq);
-    const float a = __bfloat162float(dout[tok * lddo + h * 32 + lane]) * __bfloat162float(o[tok * ldo + h * 32 + lane]);
-    const float ssum = warp_sum(a);
-    if (lane == 0) delta[idx] = ssum;
+  const int piece = lane & 3;
+  const long long total = M * Nq;
+  long long idx = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8 + (lane >> 2);
+  const long long stride = (long long)gridDim.x * (blockDim.x >> 5) * 8;
+  for (long long base = idx - (lane >> 2); base < total; base += stride, idx += stride) {
+    float a = 0.f;
+    if (idx < total) {
+      const long long tok = idx / Nq;
+      const int h = (int)(idx % Nq);
+      const uint4 dv = *reinterpret_cast<const uint4*>(dout + tok * lddo + h * 32 + piece * 8);
+      const uint4 ov = *reinterpret_cast<const uint4*>(o + tok * ldo + h * 32 + piece * 8);
+      a = bf16_lo(dv.x) * bf16_lo(ov.x) + bf16_hi(dv.x) * bf16_hi(ov.x) + bf16_lo(dv.y) * bf16_lo(ov.y) +
+          bf16_hi(dv.y) * bf16_hi(ov.y) + bf16_lo(dv.z) * bf16_lo(ov.z) + bf16_hi(dv.z) * bf16_hi(ov.z) +
+          bf16_lo(dv.w) * bf16_lo(ov.w) + bf16_hi(dv.w) * bf16_hi(ov.w);
+    }
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    if (piece == 0 && idx < total) delta[idx] = a;
   }
 }
 
@@ -415,7 +426,7 @@ static int launch_bwd(const mpx_attn_train_bwd_args* a, cudaStream_t s) {
     set_error("cudaMemsetAsync(dq_acc): %s", cudaGetErrorString(e));
     return MPX_ERR_CUDA;
   }
-  long long nw = M * a->Nq;
+  long long nw = (M * a->Nq + 7) / 8;   // warps: 8 (token, head) pairs each
   int dgrid = (int)((nw + 7) / 8 < (long long)num_sms() * 16 ? (nw + 7) / 8 : (long long)num_sms() * 16);
   attn_bwd_delta_kernel<<<dgrid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(a->dout), a->lddo,
                                               reinterpret_cast<const __nv_bfloat16*>(a->o), a->ldo, a->delta, M, a->Nq);
@@ -462,6 +473,9 @@ extern "C" int mpx_attn_train_bwd(const mpx_attn_train_bwd_args* a, mpx_stream_t
   MPX_REQUIRE(a && a->q && a->k && a->v && a->o && a->dout && a->lse && a->delta && a->dq_acc && a->dq && a->dk && a->dv &&
                   a->pos && a->rope_timescale, "mpx_attn_train_bwd: null pointer");
   MPX_REQUIRE(a->D == 32, "mpx_attn_train_bwd: head_dim %d unsupported (only 32)", a->D);
+  MPX_REQUIRE(a->lddo % 8 == 0 && a->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(a->dout) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(a->o) & 15) == 0,
+              "mpx_attn_train_bwd: o / dout must be 16-byte aligned with pitches that are multiples of 8");
   MPX_REQUIRE(a->B > 0 && a->T > 0 && a->T % AT_TILE == 0, "mpx_attn_train_bwd: T=%d must be a positive multiple of 64", a->T);
   MPX_REQUIRE(a->Nkv > 0 && a->Nq % a->Nkv == 0 && a->pos_len > 0, "mpx_attn_train_bwd: bad head counts");
   cudaStream_t s = (cudaStream_t)stream;

@@ -125,6 +125,88 @@ __global__ void __launch_bounds__(EW_WARPS * 32) rmsnorm_bwd_kernel(
   }
 }
 
+// H == 128 specialisation: 16 lanes per row with 16-byte accesses (two rows per warp instruction) and two row pairs in
+// flight per iteration - the generic kernel above is latency bound at this width (8-byte accesses, one row per warp).
+__global__ void __launch_bounds__(EW_WARPS * 32) rmsnorm_bwd128_kernel(
+    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
+    float eps, const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ dscale,
+    long long M) {
+  __shared__ float s_ds[EW_WARPS * 2][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & 15, rsel = lane >> 4;
+  float sc[8];
+  {
+    const float4 a = reinterpret_cast<const float4*>(scale + sub * 8)[0], b = reinterpret_cast<const float4*>(scale + sub * 8)[1];
+    sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
+  }
+  float ds[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long stride = (long long)gridDim.x * EW_WARPS * 4;
+  for (long long base = ((long long)blockIdx.x * EW_WARPS + warp) * 4; base < M; base += stride) {
+    uint4 xq[2], gq[2], rq[2];
+    bool live[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long row = base + 2 * u + rsel;
+      live[u] = row < M;
+      xq[u] = gq[u] = rq[u] = make_uint4(0, 0, 0, 0);
+      if (live[u]) {
+        xq[u] = *reinterpret_cast<const uint4*>(x + row * 128 + sub * 8);
+        gq[u] = *reinterpret_cast<const uint4*>(dy + row * 128 + sub * 8);
+        if (dres) rq[u] = *reinterpret_cast<const uint4*>(dres + row * 128 + sub * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t xw[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w}, gw[4] = {gq[u].x, gq[u].y, gq[u].z, gq[u].w};
+      const uint32_t rw[4] = {rq[u].x, rq[u].y, rq[u].z, rq[u].w};
+      float xv[8], gv[8], a[8];
+      float ss = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        xv[2 * e] = bf16_lo(xw[e]); xv[2 * e + 1] = bf16_hi(xw[e]);
+        gv[2 * e] = bf16_lo(gw[e]); gv[2 * e + 1] = bf16_hi(gw[e]);
+        ss += xv[2 * e] * xv[2 * e] + xv[2 * e + 1] * xv[2 * e + 1];
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rstd = rsqrtf(ss * (1.0f / 128.0f) + eps);
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        a[i] = gv[i] * sc[i];
+        dot += a[i] * xv[i];
+        ds[i] += gv[i] * xv[i] * rstd;
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      const float c = rstd * rstd * rstd * dot * (1.0f / 128.0f);
+      uint32_t ow[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float o0 = rstd * a[2 * e] - xv[2 * e] * c, o1 = rstd * a[2 * e + 1] - xv[2 * e + 1] * c;
+        if (dres) {
+          const uint32_t t = pack_bf16(o0, o1);
+          o0 = bf16_lo(t) + bf16_lo(rw[e]);
+          o1 = bf16_hi(t) + bf16_hi(rw[e]);
+        }
+        ow[e] = pack_bf16(o0, o1);
+      }
+      if (live[u]) *reinterpret_cast<uint4*>(dx + (base + 2 * u + rsel) * 128 + sub * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+  }
+  if (dscale) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_ds[warp * 2 + rsel][sub * 8 + i] = ds[i];
+    __syncthreads();
+    for (int j = threadIdx.x; j < 128; j += EW_WARPS * 32) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < EW_WARPS * 2; ++w) t += s_ds[w][j];
+      atomicAdd(dscale + j, t);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ GLU backward
 // forward: a = bf16(gelu(u)); h = bf16(a * g).  backward: dg = bf16(dh * a); du = bf16(bf16(dh * g) * gelu'(u)).
 // dug is (M, 2F): [du | dg].
@@ -216,7 +298,18 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (rl < RL && c < N) {
       if (c + 8 <= N) {
-        for (long long r = r0 + rl; r < r1; r += RL) {
+        long long r = r0 + rl;
+        for (; r + 3LL * RL < r1; r += 4LL * RL) {          // four independent 16-byte loads in flight
+          uint4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(x + (r + (long long)u * RL) * ld + c);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc[0] += bf16_lo(v[u].x); acc[1] += bf16_hi(v[u].x); acc[2] += bf16_lo(v[u].y); acc[3] += bf16_hi(v[u].y);
+            acc[4] += bf16_lo(v[u].z); acc[5] += bf16_hi(v[u].z); acc[6] += bf16_lo(v[u].w); acc[7] += bf16_hi(v[u].w);
+          }
+        }
+        for (; r < r1; r += RL) {
           const uint4 v = *reinterpret_cast<const uint4*>(x + r * ld + c);
           acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
           acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
@@ -298,6 +391,14 @@ extern "C" int mpx_rmsnorm_bwd(const mpx_bf16* dy, const mpx_bf16* x, const floa
   auto DR = reinterpret_cast<const __nv_bfloat16*>(dres);
   auto DX = reinterpret_cast<__nv_bfloat16*>(dx);
   cudaStream_t s = (cudaStream_t)stream;
+  if (H == 128 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dx) & 15) == 0 && (!dres || (reinterpret_cast<uintptr_t>(dres) & 15) == 0) &&
+      (reinterpret_cast<uintptr_t>(scale) & 15) == 0) {
+    long long g4 = (M + EW_WARPS * 4 - 1) / (EW_WARPS * 4);
+    const int grid4 = (int)(g4 < cap ? g4 : cap);
+    rmsnorm_bwd128_kernel<<<grid4, EW_WARPS * 32, 0, s>>>(DY, X, scale, eps, DR, DX, dscale, M);
+    return check_launch("mpx_rmsnorm_bwd");
+  }
   switch (H / 128) {
     case 1: rmsnorm_bwd_kernel<1><<<grid, EW_WARPS * 32, 0, s>>>(DY, X, scale, eps, DR, DX, dscale, M, H); break;
     case 2: rmsnorm_bwd_kernel<2><<<grid, EW_WARPS * 32, 0, s>>>(DY, X, scale, eps, DR, DX, dscale, M, H); break;
