@@ -188,16 +188,17 @@ def decode_attention_roofline(trainer, peaks):
     launching stream; achieved = algorithmic KV bytes per launch / average launch duration."""
     import torch
     from jaxrl_b200 import ops
-    eng, ws, r = trainer.engine, trainer.dws, trainer.r
-    T, B, L = trainer.T, trainer.B, eng.L
+    eng, r = trainer.engine, trainer.r
+    ws = trainer.dws if trainer.n_chains == 1 else trainer.dws_chain[0]   # the launch shape the rollout really uses
+    T, B, L = trainer.T, ws.B, eng.L
     for t in range(0, T, 64):
-        ops.attn_decode(ws.q, ws.kcache[0], ws.vcache[0], r.pos[t], eng.Nq, eng.Nkv, eng.D, out=ws.ao)
+        ops.attn_decode(ws.q, ws.kcache[0], ws.vcache[0], r.pos[t][:B], eng.Nq, eng.Nkv, eng.D, out=ws.ao)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for t in range(T):
         i = t % L
-        ops.attn_decode(ws.q, ws.kcache[i], ws.vcache[i], r.pos[t], eng.Nq, eng.Nkv, eng.D, out=ws.ao)
+        ops.attn_decode(ws.q, ws.kcache[i], ws.vcache[i], r.pos[t][:B], eng.Nq, eng.Nkv, eng.D, out=ws.ao)
     e1.record()
     torch.cuda.synchronize()
     avg_s = e0.elapsed_time(e1) * 1e-3 / T
@@ -209,7 +210,7 @@ def decode_attention_roofline(trainer, peaks):
     peak = peaks.get("hbm_gbs", 6650.0)
     return {"kernel": "attn_decode_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": None, "avg_launch_us": avg_s * 1e6,
-            "algorithmic_bytes_per_launch": per_launch,
+            "algorithmic_bytes_per_launch": per_launch, "agents_per_launch": B,
             "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"}
 
 
@@ -276,9 +277,12 @@ def main():
         t, r, env, eng = 300, trainer.r, trainer.env, trainer.engine
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        eng.decode_step(trainer.dws, env.obs[t], env.reward[t], r.actions_ext[t], r.pos[t], value_out=r.values[t],
-                        sample=dict(action=r.actions_ext[t + 1], log_prob=r.log_prob[t], seed=trainer.seed, stream_id=t,
-                                    stream_offset=trainer.noise_off, want_logits=False))
+        dws = trainer.dws if trainer.n_chains == 1 else trainer.dws_chain[0]
+        rows = slice(0, dws.B)
+        eng.decode_step(dws, env.obs[t][rows], env.reward[t][rows], r.actions_ext[t][rows], r.pos[t][rows],
+                        value_out=r.values[t][rows],
+                        sample=dict(action=r.actions_ext[t + 1][rows], log_prob=r.log_prob[t][rows], seed=trainer.seed,
+                                    stream_id=t, stream_offset=trainer.noise_off, want_logits=False))
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         print(json.dumps({"ncu_decode_step": True}), flush=True)

@@ -10,6 +10,8 @@ minibatch one gradient all-reduce over NCCL and, once per rollout, an all-reduce
 
 from __future__ import annotations
 
+import os
+
 from types import SimpleNamespace
 from typing import Optional
 
@@ -75,7 +77,16 @@ class PPOTrainer:
     def _alloc(self):
         dev, B, T, cfg = self.dev, self.B, self.T, self.cfg
         A = cfg.action_dim
-        self.dws = self.engine.alloc_decode(B)
+        # Rollout chains: agents are independent during the rollout, so the batch is split into `n_chains` row ranges
+        # whose decode-step chains run on separate streams inside the same CUDA graph - the latency-bound kernels of
+        # one chain fill the SMs that the other chain leaves idle (the HBM-bound attention kernels still alternate).
+        self.n_chains = int(os.environ.get("MPX_ROLLOUT_CHAINS", "2"))
+        if self.n_chains < 1 or B % (self.n_chains * 128) != 0:
+            self.n_chains = 1
+        self.Bc = B // self.n_chains
+        self.dws = self.engine.alloc_decode(B) if self.n_chains == 1 else None
+        self.dws_chain = [self.engine.alloc_decode(self.Bc) for _ in range(self.n_chains)] if self.n_chains > 1 else []
+        self.chain_streams = [torch.cuda.Stream(device=dev) for _ in range(self.n_chains - 1)]
         self.tws = self.engine.alloc_train(self.Bm, T)
         f = lambda *s: torch.zeros(*s, dtype=F32, device=dev)
         r = SimpleNamespace()
@@ -119,28 +130,49 @@ class PPOTrainer:
         self.perm_gen = torch.Generator(device=dev).manual_seed(self.seed + 17 + self.rank)
 
     # ------------------------------------------------------------------------------------------ rollout (evaluate)
-    def _rollout_body(self):
+    def _rollout_chain(self, ws, rows: slice, seed: int):
+        """The T decode steps (+ bootstrap value) of the agents in `rows` (evaluate(), train.py:42-159)."""
         eng, r, env, T = self.engine, self.r, self.env, self.T
-        eng.stage_rollout_weights()                         # weights are fixed for the whole rollout
         for t in range(T):
             if self.e2e:                                    # host -> device copy of this step's inputs (timed)
-                r.obs_stage.copy_(env.obs_host[t], non_blocking=True)
-                r.rew_stage.copy_(env.reward_host[t], non_blocking=True)
-                obs_t, rew_t = r.obs_stage, r.rew_stage
+                r.obs_stage[rows].copy_(env.obs_host[t][rows], non_blocking=True)
+                r.rew_stage[rows].copy_(env.reward_host[t][rows], non_blocking=True)
+                obs_t, rew_t = r.obs_stage[rows], r.rew_stage[rows]
             else:
-                obs_t, rew_t = env.obs[t], env.reward[t]
-            eng.decode_step(self.dws, obs_t, rew_t, r.actions_ext[t], r.pos[t], value_out=r.values[t],
-                            sample=dict(action=r.actions_ext[t + 1], log_prob=r.log_prob[t], seed=self.seed, stream_id=t,
-                                        stream_offset=self.noise_off, want_logits=False))
+                obs_t, rew_t = env.obs[t][rows], env.reward[t][rows]
+            eng.decode_step(ws, obs_t, rew_t, r.actions_ext[t][rows], r.pos[t][rows], value_out=r.values[t][rows],
+                            sample=dict(action=r.actions_ext[t + 1][rows], log_prob=r.log_prob[t][rows], seed=seed,
+                                        stream_id=t, stream_offset=self.noise_off, want_logits=False))
         # bootstrap (train.py:142-148): value of the INITIAL timestep with the INITIAL (empty) carry.  Position 0
         # reads and writes ring slot 0 only, so re-running step 0 on the used caches is equivalent.
         if self.e2e:
-            r.obs_stage.copy_(env.obs_host[0], non_blocking=True)
-            r.rew_stage.copy_(env.reward_host[0], non_blocking=True)
-            obs0, rew0 = r.obs_stage, r.rew_stage
+            r.obs_stage[rows].copy_(env.obs_host[0][rows], non_blocking=True)
+            r.rew_stage[rows].copy_(env.reward_host[0][rows], non_blocking=True)
+            obs0, rew0 = r.obs_stage[rows], r.rew_stage[rows]
         else:
-            obs0, rew0 = env.obs[0], env.reward[0]
-        eng.decode_step(self.dws, obs0, rew0, r.actions_ext[0], r.pos[0], value_out=r.values[T])
+            obs0, rew0 = env.obs[0][rows], env.reward[0][rows]
+        eng.decode_step(ws, obs0, rew0, r.actions_ext[0][rows], r.pos[0][rows], value_out=r.values[T][rows])
+
+    def _rollout_body(self):
+        self.engine.stage_rollout_weights()                 # weights are fixed for the whole rollout
+        if self.n_chains == 1:
+            self._rollout_chain(self.dws, slice(0, self.B), self.seed)
+            return
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        joins = []
+        for c in range(1, self.n_chains):
+            st = self.chain_streams[c - 1]
+            with torch.cuda.stream(st):
+                st.wait_event(fork)
+                self._rollout_chain(self.dws_chain[c], slice(c * self.Bc, (c + 1) * self.Bc), self.seed + 7919 * c)
+                ev = torch.cuda.Event()
+                ev.record(st)
+                joins.append(ev)
+        self._rollout_chain(self.dws_chain[0], slice(0, self.Bc), self.seed)
+        for ev in joins:
+            main.wait_event(ev)
 
     def _postprocess_body(self):
         """Layout change (+ row permutation, rollout.py:169-181) and calculate_advantage (rollout.py:128-167)."""
