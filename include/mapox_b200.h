@@ -263,6 +263,14 @@ size_t mpx_conv1_onehot_wgrad_workspace_bytes(long long M, int IH, int IW, int k
 int mpx_conv1_onehot_wgrad(const uint8_t* obs, const mpx_bf16* dz, float* dw, long long M, int IH, int IW, int K,
                            const int* sizes, int kh, int kw, int sh, int sw, int cout, void* workspace,
                            size_t workspace_bytes, mpx_stream_t stream);
+/* FlattenedObsEncoder (observation.py:98-145), first half: one_hot(obs) -> Linear(C,4) per cell as a table lookup.
+ * obs (M, cells) uint8, w (C,4) / bias (4) fp32 master params, out (M, KP) bf16 with KP = round_up(4*cells, 8)
+ * (pad columns zeroed); the dense half is an mpx_linear on out.  mpx_flat_embed_bwd is the transpose:
+ * dw (C,4) += per-class sums of dflat (M,KP), dbias (4) += column sums. */
+int mpx_flat_embed_fwd(const uint8_t* obs, const float* w, const float* bias, mpx_bf16* out, long long M, int cells, int C,
+                       int KP, mpx_stream_t stream);
+int mpx_flat_embed_bwd(const uint8_t* obs, const mpx_bf16* dflat, float* dw, float* dbias, long long M, int cells, int C,
+                       int KP, mpx_stream_t stream);
 /* network.py:323-331: tied action logits f32(x) @ table^T (M,A) f32, masked entries = finfo(f32).min. A <= 32. */
 int mpx_policy_logits(const mpx_bf16* x, const float* table, const uint8_t* action_mask, float* logits, long long M,
                       int H, int A, mpx_stream_t stream);

@@ -110,6 +110,8 @@ lib.mpx_gumbel_noise.argtypes = [c_p, c_ll, C.c_ulonglong, C.c_ulonglong, c_p, c
 lib.mpx_conv1_onehot_wgrad_workspace_bytes.restype = C.c_size_t
 lib.mpx_conv1_onehot_wgrad_workspace_bytes.argtypes = [c_ll, c_i, c_i, c_i, c_i, c_i, c_i]
 lib.mpx_conv1_onehot_wgrad.argtypes = [c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_p, C.c_size_t, c_p]
+lib.mpx_flat_embed_fwd.argtypes = [c_p, c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_p]
+lib.mpx_flat_embed_bwd.argtypes = [c_p, c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_p]
 lib.mpx_obs_fused_image_bytes.restype = C.c_size_t
 lib.mpx_obs_fused_image_bytes.argtypes = []
 lib.mpx_obs_fused_prep.argtypes = [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]

@@ -320,6 +320,68 @@ __global__ void __launch_bounds__(256) col2im_kernel(const __nv_bfloat16* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------ flattened encoder
+// FlattenedObsEncoder (reference observation.py:98-145): one_hot(obs) -> Linear(C, 4) per cell -> flatten -> Linear.
+// The per-cell Linear on a one-hot row is a lookup: e[j] = bf16( bf16(W[obs][j]) + bf16(b[j]) ); an out-of-range
+// value is the all-zero one-hot (bias only).  out (M, KP) bf16, KP = round_up(cells*4, 8), pad columns zeroed.
+__global__ void flat_embed_fwd_kernel(const uint8_t* __restrict__ obs, const float* __restrict__ w,
+                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, long long M,
+                                      int cells, int C, int KP) {
+  const int per_row = KP / 4;                                         // 4-column groups per output row
+  const unsigned total = (unsigned)(M * per_row);                    // host guarantees < 2^31
+  const float b0 = bf16_round(bias[0]), b1 = bf16_round(bias[1]), b2 = bf16_round(bias[2]), b3 = bf16_round(bias[3]);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned m = i / (unsigned)per_row;
+    const int cell = (int)(i % (unsigned)per_row);
+    uint2 o = make_uint2(0u, 0u);
+    if (cell < cells) {
+      const int c = obs[(long long)m * cells + cell];
+      float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+      if (c < C) {
+        const float4 wv = *reinterpret_cast<const float4*>(w + c * 4);
+        e0 = bf16_round(wv.x); e1 = bf16_round(wv.y); e2 = bf16_round(wv.z); e3 = bf16_round(wv.w);
+      }
+      o.x = pack_bf16(e0 + b0, e1 + b1);
+      o.y = pack_bf16(e2 + b2, e3 + b3);
+    }
+    *reinterpret_cast<uint2*>(out + (long long)m * KP + cell * 4) = o;
+  }
+}
+
+// Transpose: dW[c][j] += sum over (token, cell) with obs == c of dflat[token][cell*4 + j]; db[j] += sum over all.
+// Per-block shared accumulators (C*4 + 4 floats), then one global atomic per entry per block.
+__global__ void __launch_bounds__(256) flat_embed_bwd_kernel(const uint8_t* __restrict__ obs,
+                                                             const __nv_bfloat16* __restrict__ dflat,
+                                                             float* __restrict__ dw, float* __restrict__ db, long long M,
+                                                             int cells, int C, int KP) {
+  extern __shared__ float s_acc[];                                    // [C][4] + [4]
+  for (int i = threadIdx.x; i < C * 4 + 4; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const unsigned total = (unsigned)(M * cells);
+  float bl[4] = {0.f, 0.f, 0.f, 0.f};
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned m = i / (unsigned)cells;
+    const int cell = (int)(i % (unsigned)cells);
+    const uint2 v = *reinterpret_cast<const uint2*>(dflat + (long long)m * KP + cell * 4);
+    const float d[4] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y)};
+    const int c = obs[i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bl[j] += d[j];
+      if (c < C) atomicAdd(&s_acc[c * 4 + j], d[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float t = warp_sum(bl[j]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[C * 4 + j], t);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 4; i += blockDim.x)
+    if (s_acc[i] != 0.f) atomicAdd(dw + i, s_acc[i]);
+  if (threadIdx.x < 4) atomicAdd(db + threadIdx.x, s_acc[C * 4 + threadIdx.x]);
+}
+
 static int cv_grid(long long n) {
   long long g = (n + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
@@ -440,4 +502,28 @@ extern "C" int mpx_col2im(const mpx_bf16* dx, mpx_bf16* da, long long M, int IH,
         reinterpret_cast<const __nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(z),
         reinterpret_cast<__nv_bfloat16*>(da), M, IH, IW, C, kh, kw, sh, sw, OH, OW);
   return check_launch("mpx_col2im");
+}
+
+extern "C" int mpx_flat_embed_fwd(const uint8_t* obs, const float* w, const float* bias, mpx_bf16* out, long long M,
+                                  int cells, int C, int KP, mpx_stream_t stream) {
+  MPX_REQUIRE(obs && w && bias && out && M > 0 && cells > 0 && C > 0, "mpx_flat_embed_fwd: bad arguments");
+  MPX_REQUIRE(KP % 8 == 0 && KP >= cells * 4, "mpx_flat_embed_fwd: KP=%d must be a multiple of 8 >= 4*cells", KP);
+  MPX_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0, "mpx_flat_embed_fwd: embedding kernel must be 16-byte aligned");
+  MPX_REQUIRE(M * (KP / 4) < (1LL << 31), "mpx_flat_embed_fwd: too many elements for 32-bit indexing");
+  flat_embed_fwd_kernel<<<cv_grid(M * (KP / 4)), 256, 0, (cudaStream_t)stream>>>(
+      obs, w, bias, reinterpret_cast<__nv_bfloat16*>(out), M, cells, C, KP);
+  return check_launch("mpx_flat_embed_fwd");
+}
+
+extern "C" int mpx_flat_embed_bwd(const uint8_t* obs, const mpx_bf16* dflat, float* dw, float* dbias, long long M, int cells,
+                                  int C, int KP, mpx_stream_t stream) {
+  MPX_REQUIRE(obs && dflat && dw && dbias && M > 0 && cells > 0 && C > 0, "mpx_flat_embed_bwd: bad arguments");
+  MPX_REQUIRE(KP % 8 == 0 && KP >= cells * 4 && C <= 1024, "mpx_flat_embed_bwd: bad KP / C");
+  MPX_REQUIRE(M * cells < (1LL << 31), "mpx_flat_embed_bwd: too many elements for 32-bit indexing");
+  long long g = (M * cells + 255) / 256;
+  const long long cap = (long long)num_sms() * 4;                    // bounds the global atomics
+  if (g > cap) g = cap;
+  flat_embed_bwd_kernel<<<(int)g, 256, (C * 4 + 4) * sizeof(float), (cudaStream_t)stream>>>(
+      obs, reinterpret_cast<const __nv_bfloat16*>(dflat), dw, dbias, M, cells, C, KP);
+  return check_launch("mpx_flat_embed_bwd");
 }

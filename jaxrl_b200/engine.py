@@ -60,21 +60,28 @@ class PolicyEngine:
         # conv geometry (observation.py:63-82)
         self.C0 = sum(cfg.obs_max_value)
         self.conv = []
+        self.flat = cfg.obs_type == "grid_flattened"            # FlattenedObsEncoder (observation.py:98-145)
+        if self.flat:
+            self.cells = cfg.obs_shape[0] * cfg.obs_shape[1]
+            self.fk = 4 * self.cells                             # dense in_features (embed_features = 4)
+            self.fkp = _round_up(self.fk, 8)
+        elif cfg.obs_type != "grid_cnn":
+            raise _lib.MpxError(f"obs_type {cfg.obs_type!r} is not on the B200 path")
         ih, iw, cin = cfg.obs_shape[0], cfg.obs_shape[1], self.C0
         chans = list(cfg.cnn_channels) + [H]
-        for j, ((kh, kw), (sh, sw), ch) in enumerate(zip(cfg.cnn_kernels, cfg.cnn_strides, chans)):
+        for j, ((kh, kw), (sh, sw), ch) in enumerate(zip(cfg.cnn_kernels, cfg.cnn_strides, chans) if not self.flat else ()):
             oh, ow = conv_out(ih, kh, sh), conv_out(iw, kw, sw)
             kp = _round_up(kh * kw * cin, 8)
             self.conv.append(SimpleNamespace(j=j, ih=ih, iw=iw, cin=cin, kh=kh, kw=kw, sh=sh, sw=sw, oh=oh, ow=ow,
                                              cout=ch, k=kh * kw * cin, kp=kp))
             ih, iw, cin = oh, ow, ch
-        if ih != 1 or iw != 1:
+        if not self.flat and (ih != 1 or iw != 1):
             raise _lib.MpxError("grid_cnn encoder must reduce the view to 1x1 (flatten == hidden_features)")
         for c in self.conv[1:]:
             if c.cin % 8 != 0:
                 raise _lib.MpxError("hidden conv channels must be multiples of 8")
         # rollout path: the standard geometry (11x11 view, 3x3/2 -> 16, 3x3/1 -> 32, 3x3/1 -> 128) runs as one kernel
-        self.fused_obs = (H == 128 and tuple(cfg.obs_shape[:2]) == (11, 11) and len(self.conv) == 3
+        self.fused_obs = (not self.flat and H == 128 and tuple(cfg.obs_shape[:2]) == (11, 11) and len(self.conv) == 3
                           and all((c.kh, c.kw) == (3, 3) for c in self.conv)
                           and [(c.sh, c.sw) for c in self.conv] == [(2, 2), (1, 1), (1, 1)]
                           and [c.cout for c in self.conv] == [16, 32, 128] and len(cfg.obs_max_value) <= 4
@@ -82,8 +89,8 @@ class PolicyEngine:
         self.obs_image = ops.obs_fused_image(self.dev) if self.fused_obs else None
         self.overlap_wgrad = os.environ.get("MPX_WGRAD_OVERLAP", "1") != "0"
         self.side = torch.cuda.Stream(device=self.dev) if (self.overlap_wgrad and self.dev.type == "cuda") else None
-        c0 = self.conv[0]
-        self.onehot_wgrad = (c0.k <= 128 and c0.kh * c0.kw * len(cfg.obs_max_value) <= 32 and c0.cout <= 64
+        c0 = self.conv[0] if self.conv else None
+        self.onehot_wgrad = (c0 is not None and c0.k <= 128 and (c0.kh, c0.kw) == (3, 3) and c0.cout <= 64
                              and c0.cout % 8 == 0 and len(cfg.obs_max_value) <= 4)
         self._alloc_staged()
         self.stage_weights()
@@ -154,6 +161,13 @@ class PolicyEngine:
             add(wk_, c.cout, w_c, c.cout, c.k, c.cout, 0)
             add(p[f"obs_encoder.layers.{c.j}.bias"].view(1, c.cout), c.cout, b_c, c.cout, 1, c.cout, 0)
             self.w.update({f"wt_c{c.j}": wt_c, f"w_c{c.j}": w_c, f"b_c{c.j}": b_c})
+        if self.flat:                                           # dense half of FlattenedObsEncoder: (4*cells, H) kernel
+            wfd = p["obs_encoder.dense.kernel"]
+            wt_fd, w_fd, b_fd = z(H, self.fkp), z(self.fkp, H), z(H)   # K padded to a multiple of 8 with zeros
+            add(wfd, H, wt_fd, self.fkp, self.fk, H, 1)
+            add(wfd, H, w_fd, H, self.fk, H, 0)
+            add(p["obs_encoder.dense.bias"].view(1, H), H, b_fd, H, 1, H, 0)
+            self.w.update({"wt_fd": wt_fd, "w_fd": w_fd, "b_fd": b_fd})
         arr = (_lib.PrepDesc * len(descs))()
         for n, d in enumerate(descs):
             arr[n] = _lib.PrepDesc(*d, 0)
@@ -180,6 +194,10 @@ class PolicyEngine:
         e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)
         n = len(self.conv)
         ws.cx, ws.cz, ws.ca = [], [], []
+        if self.flat:
+            ws.fe = e(M, self.fkp)                                # flattened cell embeddings (dense input)
+            ws.oe = e(M, self.H)                                  # encoder output
+            ws.dfe = e(M, self.fkp) if train else None
         for c in self.conv:
             rows = M * c.oh * c.ow
             # the last conv covers the whole remaining map: its im2col is the flattened previous activation;
@@ -251,6 +269,14 @@ class PolicyEngine:
         p, w = self.p, self.w
         cfg = self.cfg
         n = len(self.conv)
+        if self.flat:
+            ops.flat_embed_fwd(obs, p["obs_encoder.embedding.kernel"], p["obs_encoder.embedding.bias"], ws.fe, M, self.cells)
+            ops.linear(ws.fe, w["wt_fd"], bias=w["b_fd"], out=ws.oe)
+            t_table = p.views.get("task_embedder.embedding_table") if task_ids is not None else None
+            ops.embed_combine(ws.oe, reward, last_action, task_ids if t_table is not None else None,
+                              p["reward_encoder.kernel"], p["reward_encoder.bias"], p["action_embedder.embedding_table"],
+                              t_table, out=out)
+            return out
         if not train and self.fused_obs:          # rollout: encoder + embedding sum in one kernel, nothing saved
             t_table = p.views.get("task_embedder.embedding_table") if task_ids is not None else None
             c0 = self.conv[0]
@@ -291,6 +317,14 @@ class PolicyEngine:
         ops.embed_bwd(dx0, reward, last_action, task_ids if gt is not None else None, self.A, self.cfg.task_count,
                       p.g("reward_encoder.kernel"), p.g("reward_encoder.bias"),
                       p.g("action_embedder.embedding_table"), gt)
+        if self.flat:
+            ops.colsum(dx0, p.g("obs_encoder.dense.bias"), M=M, N=self.H, ld=self.H)
+            ops.linear_wgrad(ws.fe, dx0, p.g("obs_encoder.dense.kernel"), M=M, K=self.fk, N=self.H, ldx=self.fkp,
+                             ldy=self.H, lddw=self.H)
+            ops.linear(dx0, w["w_fd"], out=ws.dfe)
+            ops.flat_embed_bwd(obs, ws.dfe, p.g("obs_encoder.embedding.kernel"), p.g("obs_encoder.embedding.bias"), M,
+                               self.cells)
+            return
         n = len(self.conv)
         dy = dx0                      # cotangent of the last conv's output (M, H)
         fused_gelu = False

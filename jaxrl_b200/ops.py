@@ -434,6 +434,20 @@ def conv1_onehot_wgrad(obs, dz, dw, M: int, IH: int, IW: int, sizes: Sequence[in
     return dw
 
 
+def flat_embed_fwd(obs, w, bias, out, M: int, cells: int):
+    """FlattenedObsEncoder embedding lookup: out (M, KP) bf16."""
+    _req(w, F32, "w"); _req(bias, F32, "bias"); _req(out, BF16, "out")
+    check(lib.mpx_flat_embed_fwd(ptr(obs), ptr(w), ptr(bias), ptr(out), M, cells, w.shape[0], out.shape[-1], stream()),
+          "mpx_flat_embed_fwd")
+    return out
+
+
+def flat_embed_bwd(obs, dflat, dw, dbias, M: int, cells: int):
+    _req(dflat, BF16, "dflat"); _req(dw, F32, "dw"); _req(dbias, F32, "dbias")
+    check(lib.mpx_flat_embed_bwd(ptr(obs), ptr(dflat), ptr(dw), ptr(dbias), M, cells, dw.shape[0], dflat.shape[-1],
+                                 stream()), "mpx_flat_embed_bwd")
+
+
 def obs_fused_image(device) -> torch.Tensor:
     """Device buffer for the fused observation encoder's weight image (see mpx_obs_fused_prep)."""
     return torch.empty(lib.mpx_obs_fused_image_bytes(), dtype=torch.uint8, device=device)

@@ -32,7 +32,8 @@ class SyntheticEnv:
         gen = torch.Generator().manual_seed(seed)
         vw, vh = cfg.obs_shape[0], cfg.obs_shape[1]
         comps = [torch.randint(0, n, (T + 1, B, vw, vh), generator=gen, dtype=torch.uint8) for n in cfg.obs_max_value]
-        obs = torch.stack(comps, dim=-1).contiguous()
+        # grid_cnn: (…, vw, vh, K) components; grid_flattened: one class id per cell, (…, vw, vh)
+        obs = comps[0].contiguous() if cfg.obs_type == "grid_flattened" else torch.stack(comps, dim=-1).contiguous()
         reward = ((torch.rand(T + 1, B, generator=gen) < 0.02).float() * 0.05).contiguous()
         self.T, self.B = T, B
         self.obs_host = obs.pin_memory() if host else None

@@ -201,3 +201,57 @@ def test_optimizer_step_matches_oracle(opt_type):
         params = new_params
         ps.load_dict(params)            # keep both sides on identical weights
     assert step.item() == 3
+
+
+def test_flattened_encoder_forward_backward_match_oracle():
+    """grid_flattened observation encoder (FlattenedObsEncoder, observation.py:98-145; the blog_32_layers config):
+    training forward, losses and every gradient vs the oracle, plus a few decode steps."""
+    from jaxrl_b200 import ops
+    from jaxrl_b200.engine import PolicyEngine
+    cfg = replace(CFG, obs_type="grid_flattened", obs_shape=(5, 5), obs_max_value=(8,), num_layers=1)
+    eng = PolicyEngine(cfg, DEV, seed=5, bias_noise=0.05)
+    T, B = 64, 4
+    hyp = PPOConfig()
+    gen = torch.Generator().manual_seed(21)
+    batch = dict(
+        obs=torch.randint(0, 8, (B, T, 5, 5), generator=gen).to(torch.uint8),
+        action_mask=torch.ones(B, T, cfg.action_dim, dtype=torch.bool),
+        last_rewards=torch.randn(B, T, generator=gen) * 0.1,
+        last_actions=torch.randint(0, cfg.action_dim, (B, T), generator=gen).to(torch.int32),
+        actions=torch.randint(0, cfg.action_dim, (B, T), generator=gen).to(torch.int32),
+        terminated=torch.zeros(B, T, dtype=torch.bool),
+        log_prob=-torch.rand(B, T, generator=gen) * 2 - 0.2, advantages=torch.randn(B, T, generator=gen),
+        targets=torch.randn(B, T, generator=gen) * 2)
+    p = {k: v.clone().requires_grad_(True) for k, v in eng.p.oracle_dict().items()}
+    total, logs = O.ppo_loss(p, cfg, hyp, batch, progress=0.0)
+    total.backward()
+    ws = eng.alloc_train(B, T)
+    d = {k: v.to(DEV) for k, v in batch.items()}
+    eng.forward_train(ws, d["obs"], d["last_rewards"].reshape(-1), d["last_actions"].reshape(-1), action_mask=d["action_mask"])
+    eng.p.grad.zero_()
+    flat = {k: (v.reshape(-1) if v.dim() == 2 and k not in ("obs", "action_mask") else v) for k, v in d.items()}
+    flat["obs"] = d["obs"]
+    losses = eng.loss_and_backward(ws, flat, hyp, progress=0.0)
+    torch.cuda.synchronize()
+    l = losses.cpu()
+    assert abs(l[0] - logs["value_loss"].item()) <= 2e-2 * abs(logs["value_loss"].item()) + 1e-3
+    assert abs(l[1] - logs["actor_loss"].item()) <= 2e-2 * abs(logs["actor_loss"].item()) + 2e-3
+    grads = eng.p.grad_dict()
+    for name, gref in ((k, v.grad) for k, v in p.items()):
+        gg = grads[name]
+        rel = (gg - gref).norm().item() / (gref.norm().item() + 1e-8)
+        cos = (gg * gref).sum().item() / (gg.norm().item() * gref.norm().item() + 1e-12)
+        _log(f"flat-encoder grad {name}: rel_l2={rel:.4f} cos={cos:.5f}")
+        assert cos > 0.99 and rel < 0.1, f"gradient mismatch for {name}: rel {rel} cos {cos}"
+    # decode: embedding of the first step equals the training embedding of token 0 of each row
+    dws = eng.alloc_decode(B)
+    eng.reset_carry(dws)
+    pos = torch.zeros(B, dtype=torch.int32, device=DEV)
+    logits, vlogits = eng.decode_step(dws, d["obs"][:, 0].contiguous(), d["last_rewards"][:, 0].contiguous(),
+                                      d["last_actions"][:, 0].contiguous(), pos)
+    vl_ref, lg_ref, _ = O.model_forward({k: v.detach() for k, v in p.items()}, cfg,
+                                        O.TimeStep(obs=batch["obs"][:, :1], time=torch.zeros(1, 1, dtype=torch.int32),
+                                                   terminated=batch["terminated"][:, :1], last_action=batch["last_actions"][:, :1],
+                                                   reward=batch["last_rewards"][:, :1], action_mask=None))
+    assert_close_bf16(logits.cpu(), lg_ref[:, 0], "flat-encoder decode logits", rtol=1e-2, abs_floor_frac=2e-2, allow_frac=5e-3,
+                      max_err_frac=6e-2)
