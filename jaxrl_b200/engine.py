@@ -36,8 +36,8 @@ class PolicyEngine:
                  bias_noise: float = 0.0):
         if cfg.head_dim != 32:
             raise _lib.MpxError("head_dim must be 32 on the B200 path")
-        if cfg.obs_type != "grid_cnn":
-            raise _lib.MpxError(f"obs_type {cfg.obs_type!r} is not on the B200 path yet (grid_cnn only)")
+        if cfg.obs_type not in ("grid_cnn", "grid_flattened"):
+            raise _lib.MpxError(f"obs_type {cfg.obs_type!r} is not on the B200 path (grid_cnn / grid_flattened)")
         if cfg.value_hidden_dim is None:
             raise _lib.MpxError("value_hidden_dim=None is not on the B200 path yet")
         self.cfg = cfg
