@@ -208,8 +208,16 @@ def decode_attention_roofline(trainer, peaks):
     per_launch = B * (kv_bytes + io_bytes)
     achieved = per_launch / avg_s / 1e9
     peak = peaks.get("hbm_gbs", 6650.0)
-    return {"kernel": "attn_decode_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "avg_launch_us": avg_s * 1e6,
+    # DRAM traffic per launch: ncu measured (read + write) / algorithmic bytes for this kernel at one position
+    # (profiles/r01_attn_decode_traffic.json); scaled to the average launch of the rollout, like `achieved`.
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_attn_decode_traffic.json")))
+        traffic = tj["ratio"] * per_launch
+    except Exception:
+        pass
+    return {"kernel": "attn_decode_online_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "avg_launch_us": avg_s * 1e6,
             "algorithmic_bytes_per_launch": per_launch, "agents_per_launch": B,
             "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"}
 
