@@ -38,7 +38,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ o, long long ldo,
-                   float* __restrict__ lse, int T, int Nq, int kv_col, float scale_log2) {
+                   float* __restrict__ lse, int T, int Nq, int kv_col, float scale_log2, unsigned long long* dbg_buf) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nqt = T / TC_QT;
@@ -58,6 +58,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const long long tok0 = (long long)b * T;
+  unsigned long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 32) ? dbg_buf : nullptr;
+  dbg_stamp(dbg, 0);
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -75,6 +77,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  dbg_stamp(dbg, 1);
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS[2] = {tmem_base, tmem_base + 64};
   const uint32_t tO = tmem_base + 128;
@@ -117,6 +120,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
     }
     mbar_wait(&bar_s[kt & 1], (kt >> 1) & 1);
     tc_fence_after();
+    if (kt < 8) dbg_stamp(dbg, 2 + 3 * kt);
     uint32_t sraw[2][32];
     tmem_ld_32x32(tS[kt & 1] + lane_off, sraw[0]);
     tmem_ld_32x32(tS[kt & 1] + lane_off + 32, sraw[1]);
@@ -139,6 +143,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
     if (kt > 0) {
       mbar_wait(bar_o, (kt - 1) & 1);                      // MMA2(kt-1) done: O readable, P tile reusable
       tc_fence_after();
+      if (kt < 8) dbg_stamp(dbg, 3 + 3 * kt);
       if (__any_sync(0xffffffffu, alpha != 1.0f)) {
         uint32_t ov[32];
         tmem_ld_32x32(tO + lane_off + 32, ov);
@@ -165,6 +170,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+    if (kt < 8) dbg_stamp(dbg, 4 + 3 * kt);
     if (tid == 0) {
       tc_fence_after();
       const uint32_t a = smem_u32(sP);
@@ -193,6 +199,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
     reinterpret_cast<uint4*>(orow)[c] = v;
   }
   lse[(tok0 + qrow) * Nq + head] = m + log2f(l);
+  dbg_stamp(dbg, 30);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 256);
@@ -225,7 +232,7 @@ int attn_fwd_tc_launch(const mpx_attn_train_args* a, cudaStream_t stream) {
   const float scale_log2 = (1.0f / sqrtf((float)a->D)) * 1.4426950408889634f;
   dim3 grid(nqt, a->Nq, a->B);
   attn_fwd_tc_kernel<<<grid, 128, smem, stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(a->o), a->ldo, a->lse, a->T, a->Nq,
-                                                 (int)QD, scale_log2);
+                                                 (int)QD, scale_log2, g_dbg_stamps);
   return check_launch("attn_fwd_tc_kernel");
 }
 

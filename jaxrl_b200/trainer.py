@@ -97,8 +97,10 @@ class PPOTrainer:
         r.values = f(T + 1, B)
         r.gumbel = f(B, A)
         r.pos = torch.arange(T, dtype=I32, device=dev)[:, None].repeat(1, B).contiguous()   # ts.time per step
-        r.obs_stage = torch.empty_like(self.env.obs[0]) if self.e2e else None
-        r.rew_stage = torch.empty_like(self.env.reward[0]) if self.e2e else None
+        # end-to-end mode: double-buffered device staging of the per-step host inputs
+        r.obs_stage = [torch.empty_like(self.env.obs[0]) for _ in range(2)] if self.e2e else None
+        r.rew_stage = [torch.empty_like(self.env.reward[0]) for _ in range(2)] if self.e2e else None
+        self.copy_stream = torch.cuda.Stream(device=dev) if self.e2e else None
         self.r = r
         b = SimpleNamespace()
         # batch-major (permuted) training view
@@ -132,27 +134,50 @@ class PPOTrainer:
 
     # ------------------------------------------------------------------------------------------ rollout (evaluate)
     def _rollout_chain(self, ws, rows: slice, seed: int):
-        """The T decode steps (+ bootstrap value) of the agents in `rows` (evaluate(), train.py:42-159)."""
+        """The T decode steps (+ bootstrap value) of the agents in `rows` (evaluate(), train.py:42-159).
+        End-to-end mode: every step's observations / rewards come from pinned host memory; the copy of step t+1 runs
+        on a copy stream into the other half of a double buffer while step t computes."""
         eng, r, env, T = self.engine, self.r, self.env, self.T
-        for t in range(T):
-            if self.e2e:                                    # host -> device copy of this step's inputs (timed)
-                r.obs_stage[rows].copy_(env.obs_host[t][rows], non_blocking=True)
-                r.rew_stage[rows].copy_(env.reward_host[t][rows], non_blocking=True)
-                obs_t, rew_t = r.obs_stage[rows], r.rew_stage[rows]
+        e2e = self.e2e
+        if e2e:
+            main = torch.cuda.current_stream()
+            cs = self.copy_stream
+            ready = [None, None]          # copy of the step using buffer b has landed (recorded on the copy stream)
+            done = [None, None]           # the step that read buffer b has been enqueued completely (main stream)
+            start = torch.cuda.Event()
+            start.record(main)
+
+            def fetch(t_src: int, b: int):
+                with torch.cuda.stream(cs):
+                    cs.wait_event(done[b] if done[b] is not None else start)
+                    r.obs_stage[b][rows].copy_(env.obs_host[t_src][rows], non_blocking=True)
+                    r.rew_stage[b][rows].copy_(env.reward_host[t_src][rows], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                    ready[b] = ev
+            fetch(0, 0)
+        for t in range(T + 1):
+            # step T is the bootstrap (train.py:142-148): value of the INITIAL timestep with the INITIAL (empty) carry.
+            # Position 0 reads and writes ring slot 0 only, so re-running step 0 on the used caches is equivalent.
+            src = t if t < T else 0
+            if e2e:
+                b = t & 1
+                if t < T:
+                    fetch(t + 1 if t + 1 < T else 0, b ^ 1)
+                main.wait_event(ready[b])
+                obs_t, rew_t = r.obs_stage[b][rows], r.rew_stage[b][rows]
             else:
-                obs_t, rew_t = env.obs[t][rows], env.reward[t][rows]
-            eng.decode_step(ws, obs_t, rew_t, r.actions_ext[t][rows], r.pos[t][rows], value_out=r.values[t][rows],
-                            sample=dict(action=r.actions_ext[t + 1][rows], log_prob=r.log_prob[t][rows], seed=seed,
-                                        stream_id=t, stream_offset=self.noise_off, want_logits=False))
-        # bootstrap (train.py:142-148): value of the INITIAL timestep with the INITIAL (empty) carry.  Position 0
-        # reads and writes ring slot 0 only, so re-running step 0 on the used caches is equivalent.
-        if self.e2e:
-            r.obs_stage[rows].copy_(env.obs_host[0][rows], non_blocking=True)
-            r.rew_stage[rows].copy_(env.reward_host[0][rows], non_blocking=True)
-            obs0, rew0 = r.obs_stage[rows], r.rew_stage[rows]
-        else:
-            obs0, rew0 = env.obs[0][rows], env.reward[0][rows]
-        eng.decode_step(ws, obs0, rew0, r.actions_ext[0][rows], r.pos[0][rows], value_out=r.values[T][rows])
+                obs_t, rew_t = env.obs[src][rows], env.reward[src][rows]
+            if t < T:
+                eng.decode_step(ws, obs_t, rew_t, r.actions_ext[t][rows], r.pos[t][rows], value_out=r.values[t][rows],
+                                sample=dict(action=r.actions_ext[t + 1][rows], log_prob=r.log_prob[t][rows], seed=seed,
+                                            stream_id=t, stream_offset=self.noise_off, want_logits=False))
+            else:
+                eng.decode_step(ws, obs_t, rew_t, r.actions_ext[0][rows], r.pos[0][rows], value_out=r.values[T][rows])
+            if e2e:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                done[b] = ev
 
     def _rollout_body(self):
         self.engine.stage_rollout_weights()                 # weights are fixed for the whole rollout

@@ -61,3 +61,18 @@ timeline("value_head_fused (norm)", lambda: ops.value_head_fused(x, w["wt_vm"], 
          {0: "start", 1: "setup done", 2: "x tile landed", 3: "norm done", 4: "z0 ready", 5: "h0 written", 6: "z1 ready", 7: "h1 written",
           8: "z2 ready", 9: "h2 written", 20: "D ready", 21: "partial staged", 22: "all partials in", 23: "row group summed",
           24: "values stored", 25: "exit"})
+
+# training attention forward (tcgen05): CTA 0 = (last query tile, head 0, batch row 0): 8 key tiles
+Bm, T = 256, 512
+qkv = torch.randn(Bm * T, eng.QKV, device=dev, generator=gen).to(torch.bfloat16)
+o = torch.empty(Bm * T, eng.QD, dtype=torch.bfloat16, device=dev)
+lse = torch.empty(Bm * T, eng.Nq, dtype=torch.float32, device=dev)
+QD, KD = eng.QD, eng.KD
+lab = {0: "start", 1: "setup done", 30: "O / lse stored"}
+for kt in range(8):
+    lab[2 + 3 * kt] = f"S{kt} ready"
+    lab[3 + 3 * kt] = f"MMA2({kt - 1}) done (P free)"
+    lab[4 + 3 * kt] = f"P{kt} written + sync"
+timeline("attn_fwd_tc (query tile 3, 8 key tiles)",
+         lambda: ops.attn_train_fwd(qkv, qkv[:, QD:], qkv[:, QD + KD:], Bm, T, eng.Nq, eng.Nkv, eng.D, eng.QKV, eng.QKV, eng.QKV,
+                                    o=o, lse=lse), lab)
