@@ -19,23 +19,24 @@ def _rollout_state(tr):
 
 @pytest.mark.parametrize("graphs", [False, True])
 def test_trainer_modes_agree(graphs):
+    """Frozen parameters (no optimizer): the host-fed and the device-resident rollout of every update must be
+    bit-identical - this is what catches an ordering bug between the copy stream and the decode chain."""
     from jaxrl_b200.trainer import PPOTrainer
     run = NAMED["test"]
-    a = PPOTrainer(run, use_graphs=graphs, seed=7)
-    b = PPOTrainer(run, use_graphs=graphs, seed=7, e2e_host_inputs=True)
+    a = PPOTrainer(run, use_graphs=graphs, seed=7, run_optimizer=False)
+    b = PPOTrainer(run, use_graphs=graphs, seed=7, e2e_host_inputs=True, run_optimizer=False)
     a.warmup()
     b.warmup()
-    for _ in range(2):
+    for _ in range(3):
         a.train_step()
         b.train_step()
-    torch.cuda.synchronize()
-    for x, y in zip(_rollout_state(a), _rollout_state(b)):
-        assert torch.equal(x, y), "host-fed (copy stream) and device-resident rollouts diverged"
+        torch.cuda.synchronize()
+        for x, y in zip(_rollout_state(a), _rollout_state(b)):
+            assert torch.equal(x, y), "host-fed (copy stream) and device-resident rollouts diverged"
     la, lb = a.logs(), b.logs()
     for k in la:
-        assert abs(la[k] - lb[k]) <= 1e-6 * max(1.0, abs(la[k])), (k, la[k], lb[k])
+        assert abs(la[k] - lb[k]) <= 1e-5 * max(1.0, abs(la[k])), (k, la[k], lb[k])
         assert torch.isfinite(torch.tensor(la[k]))
-    assert torch.equal(a.engine.p.flat, b.engine.p.flat)
 
 
 def test_trainer_updates_parameters_and_is_deterministic():
@@ -52,9 +53,10 @@ def test_trainer_updates_parameters_and_is_deterministic():
         assert not torch.equal(p0, t.engine.p.flat)
         assert torch.isfinite(t.engine.p.flat).all()
         outs.append((t.engine.p.flat.clone(), t.r.actions_ext.clone()))
-    # same seeds, same kernels: only the fp32 atomics of a few bias / scale gradients may reorder between runs
-    assert (outs[0][1] == outs[1][1]).float().mean().item() >= 0.99
-    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=0, atol=1e-4)
+    # same seeds, same kernels: only the fp32 atomics of a few bias / scale gradients may reorder between runs (Muon's
+    # orthogonalisation amplifies such last-bit differences on small-gradient matrices, hence the loose band)
+    assert (outs[0][1] == outs[1][1]).float().mean().item() >= 0.98
+    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=0, atol=2e-3)
 
 
 def test_rollout_chains_match_single_chain():
