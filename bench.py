@@ -309,8 +309,10 @@ def main():
         trainer = PPOTrainer(run_w, rank=rank, world=world, use_graphs=False)
         trainer.warmup()
         torch.cuda.synchronize()
+        torch.cuda.profiler.start()          # `ncu --profile-from-start off`: exactly one PPO update (= one bench step)
         trainer.train_step()
         torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
         print(json.dumps({"ncu_run": True, "losses": trainer.logs()}), flush=True)
         return
     # ---- device-resident arm (value)
