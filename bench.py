@@ -112,7 +112,8 @@ def cpu_baseline(run, agents: int, steps: int = 1, warmup: int = 0):
     gen = torch.Generator().manual_seed(0)
     p = {name: _init(shape, kind, gen) for name, shape, kind in param_specs(cfg)}
     vw, vh = cfg.obs_shape[0], cfg.obs_shape[1]
-    obs = torch.stack([torch.randint(0, n, (T + 1, agents, vw, vh), generator=gen) for n in cfg.obs_max_value], -1).to(torch.uint8)
+    comps = [torch.randint(0, n, (T + 1, agents, vw, vh), generator=gen) for n in cfg.obs_max_value]
+    obs = (comps[0] if cfg.obs_type == "grid_flattened" else torch.stack(comps, -1)).to(torch.uint8)
     reward = (torch.rand(T + 1, agents, generator=gen) < 0.02).float() * 0.05
     u = torch.rand(T, agents, cfg.action_dim, generator=gen).clamp(1e-6, 1 - 1e-6)
     gumbel = -torch.log(-torch.log(u))
@@ -130,7 +131,7 @@ def cpu_baseline(run, agents: int, steps: int = 1, warmup: int = 0):
         bm = agents // m
         for i in range(m):
             sl = slice(i * bm, (i + 1) * bm)
-            batch = dict(obs=obs[:T].permute(1, 0, 2, 3, 4)[sl], action_mask=None, actions=ro["actions"][sl],
+            batch = dict(obs=obs[:T].transpose(0, 1)[sl], action_mask=None, actions=ro["actions"][sl],
                          last_actions=ro["last_actions"][sl], last_rewards=ro["last_rewards"][sl],
                          terminated=torch.zeros(bm, T, dtype=torch.bool), log_prob=ro["log_prob"][sl],
                          advantages=adv[sl], targets=tgt[sl])
