@@ -270,8 +270,8 @@ class PPOTrainer:
         if self.use_graphs:
             self.rollout_graph = self._capture(self._rollout_body)
             self.post_graph = self._capture(self._postprocess_body)
-            # world > 1: the update contains NCCL all-reduces; capturing them is opt-in (MPX_GRAPH_NCCL=1)
-            if self.world == 1 or os.environ.get("MPX_GRAPH_NCCL", "0") == "1":
+            # world > 1: the update graph then contains the NCCL gradient all-reduces (MPX_GRAPH_NCCL=0 keeps it eager)
+            if self.world == 1 or os.environ.get("MPX_GRAPH_NCCL", "1") == "1":
                 self.update_graph = self._capture(self._update_body)
             torch.cuda.synchronize()
         self.log_acc.zero_()
