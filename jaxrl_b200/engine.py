@@ -357,13 +357,15 @@ class PolicyEngine:
 
     # ------------------------------------------------------------------------------------------ decode step
     def decode_step(self, ws, obs, reward, last_action, pos, action_mask=None, task_ids=None, value_out=None,
-                    sample=None):
+                    sample=None, hidden_out=None):
         """One rollout step for B agents: TransformerActorCritic.__call__ with carry (network.py:300-343) on
         add_seq_dim(timestep).  pos is the (B,) int32 device array ts.time.  Leaves action logits in ws.logits
         and the HL-Gauss logits in ws.vlogits; the KV caches in ws are updated in place.  value_out (B,) f32, when
         given, receives HlGaussValue.get_value of those logits (values.py:43-45; fused with the value path).
         sample = dict(action=(B,) i32, log_prob=(B,) f32, seed=, stream_id=, stream_offset=, [gumbel_in=],
-        [want_logits=True]) draws the action inside the policy-head kernel (sample_actions, network.py:345-351)."""
+        [want_logits=True]) draws the action inside the policy-head kernel (sample_actions, network.py:345-351).
+        hidden_out (B,H) bf16: the trunk output x is left there and the value path is NOT run - the caller evaluates
+        it later for many steps at once with values_from_hidden (the value is not an input of the next step)."""
         p, w, B = self.p, self.w, ws.B
         S = self.cfg.max_seq_length
         x = self._embed_fwd(ws, B, obs, reward, last_action, task_ids, ws.xa, train=False)
@@ -375,6 +377,8 @@ class PolicyEngine:
                          k=ws.kcache[i], v=ws.vcache[i], k_row_stride=S * self.KD, v_row_stride=S * self.KD,
                          cache_S=S)
             ops.attn_decode(ws.q, ws.kcache[i], ws.vcache[i], pos, self.Nq, self.Nkv, self.D, out=ws.ao)
+            if hidden_out is not None and i == self.L - 1:
+                other = hidden_out                            # the block's output goes straight to the caller's buffer
             if self.fused_glu and self.QD == 128:
                 # out projection + residual, ffn_norm, GLU and its residual in ONE kernel (x1 stays in shared memory)
                 ops.glu_fused(ws.ao, w[pre + "wt_ug64"], w[pre + "wt_d"], x, other, self.F,
@@ -391,6 +395,14 @@ class PolicyEngine:
                 ops.glu_up(ws.xn, w[pre + "wt_ug"], self.F, h=ws.h)
                 ops.linear(ws.h, w[pre + "wt_d"], residual=x, out=other)
             x, other = other, x
+        if hidden_out is not None:
+            if sample is not None:
+                ops.policy_head_sample(x, p["action_embedder.embedding_table"], sample["action"], sample["log_prob"],
+                                       seed=sample.get("seed", 0), stream_id=sample.get("stream_id", 0),
+                                       stream_offset=sample.get("stream_offset"), mask=action_mask,
+                                       gumbel_in=sample.get("gumbel_in"), norm_scale=p["output_norm.scale"],
+                                       logits_out=ws.logits if sample.get("want_logits", True) else None)
+            return ws.logits, None
         if value_out is not None and self.fused_value:
             # both head kernels apply output_norm themselves: no normalised copy of x is materialised
             if sample is not None:
@@ -415,6 +427,15 @@ class PolicyEngine:
                                        sample.get("stream_offset"))
             ops.policy_sample(ws.logits, gum, action=sample["action"], log_prob=sample["log_prob"])
         return ws.logits, ws.vlogits
+
+    def values_from_hidden(self, hidden, value_out):
+        """HlGaussValue.get_value(value_head(gelu(value_mlp(output_norm(x))))) (network.py:321,335-341, values.py:40-45)
+        for any number of trunk outputs at once: hidden (M,H) bf16 -> value_out (M,) f32.  Requires the fused kernel."""
+        if not self.fused_value:
+            raise _lib.MpxError("values_from_hidden needs the fused value path (H == 128)")
+        p, w = self.p, self.w
+        ops.value_head_fused(hidden, w["wt_vm"], w["b_vm"], w["wt_vh_hilo"], p["value_head.dense.bias"], self.centers,
+                             value_out, norm_scale=p["output_norm.scale"])
 
     def _heads_fwd(self, x, action_mask, xf, logits, pv, zv, vlogits):
         """network.py:321-341."""

@@ -97,6 +97,10 @@ class PPOTrainer:
         r.values = f(T + 1, B)
         r.gumbel = f(B, A)
         r.pos = torch.arange(T, dtype=I32, device=dev)[:, None].repeat(1, B).contiguous()   # ts.time per step
+        # The value of step t is not an input of step t+1: the rollout only keeps the trunk output of every step and
+        # evaluates the value path ONCE for all (T+1)*B rows afterwards (same arithmetic, off the per-step chain).
+        self.defer_value = self.engine.fused_value and os.environ.get("MPX_DEFER_VALUE", "1") == "1"
+        r.hidden = torch.empty(T + 1, B, cfg.hidden_features, dtype=torch.bfloat16, device=dev) if self.defer_value else None
         # end-to-end mode: double-buffered device staging of the per-step host inputs
         r.obs_stage = [torch.empty_like(self.env.obs[0]) for _ in range(2)] if self.e2e else None
         r.rew_stage = [torch.empty_like(self.env.reward[0]) for _ in range(2)] if self.e2e else None
@@ -168,12 +172,14 @@ class PPOTrainer:
                 obs_t, rew_t = r.obs_stage[b][rows], r.rew_stage[b][rows]
             else:
                 obs_t, rew_t = env.obs[src][rows], env.reward[src][rows]
+            hid = r.hidden[t][rows] if self.defer_value else None
+            val = None if self.defer_value else r.values[t][rows]
             if t < T:
-                eng.decode_step(ws, obs_t, rew_t, r.actions_ext[t][rows], r.pos[t][rows], value_out=r.values[t][rows],
+                eng.decode_step(ws, obs_t, rew_t, r.actions_ext[t][rows], r.pos[t][rows], value_out=val, hidden_out=hid,
                                 sample=dict(action=r.actions_ext[t + 1][rows], log_prob=r.log_prob[t][rows], seed=seed,
                                             stream_id=t, stream_offset=self.noise_off, want_logits=False))
             else:
-                eng.decode_step(ws, obs_t, rew_t, r.actions_ext[0][rows], r.pos[0][rows], value_out=r.values[T][rows])
+                eng.decode_step(ws, obs_t, rew_t, r.actions_ext[0][rows], r.pos[0][rows], value_out=val, hidden_out=hid)
             if e2e:
                 ev = torch.cuda.Event()
                 ev.record(main)
@@ -183,6 +189,7 @@ class PPOTrainer:
         self.engine.stage_rollout_weights()                 # weights are fixed for the whole rollout
         if self.n_chains == 1:
             self._rollout_chain(self.dws, slice(0, self.B), self.seed)
+            self._deferred_values()
             return
         main = torch.cuda.current_stream()
         fork = torch.cuda.Event()
@@ -199,6 +206,12 @@ class PPOTrainer:
         self._rollout_chain(self.dws_chain[0], slice(0, self.Bc), self.seed)
         for ev in joins:
             main.wait_event(ev)
+        self._deferred_values()
+
+    def _deferred_values(self):
+        if self.defer_value:
+            r = self.r
+            self.engine.values_from_hidden(r.hidden.view(-1, r.hidden.shape[-1]), r.values.view(-1))
 
     def _postprocess_body(self):
         """Layout change (+ row permutation, rollout.py:169-181) and calculate_advantage (rollout.py:128-167)."""
