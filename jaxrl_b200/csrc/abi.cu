@@ -33,6 +33,7 @@ extern int g_attn_train_impl;
 extern int g_glu_fused_cluster;
 extern int g_value_fused_cluster;
 extern int g_obs_fused_swap;
+extern int g_gemm_dbg_mode;
 
 }  // namespace mpx
 
@@ -69,6 +70,10 @@ extern "C" int mpx_debug_set(int key, int value) {
   }
   if (key == 6) {
     mpx::g_use_pdl = value;
+    return MPX_OK;
+  }
+  if (key == 7) {
+    mpx::g_gemm_dbg_mode = value;
     return MPX_OK;
   }
   mpx::set_error("mpx_debug_set: unknown key %d", key);

@@ -22,6 +22,7 @@
 namespace mpx {
 
 int g_debug_swap_lbo_sbo = 0;
+int g_gemm_dbg_mode = 0;
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
@@ -45,6 +46,7 @@ struct GemmParams {
   int act;
   __nv_bfloat16* y_pre;      // optional: bf16 pre-activation (after bias), same pitch as y
   const float* bias_f32;     // EPI_PAIRSUM
+  int dbg_mode;              // mpx_debug_set(7, v) experiments: 1 = epilogue without global stores, 2 = no epilogue work
   // EPI_QKV
   const int32_t* pos;
   int pos_len;
@@ -164,7 +166,7 @@ __device__ __forceinline__ void epi_store(const GemmParams& p, int row0, int lan
                                           uint32_t xp, const uint4 (&rpre)[4], bool use_pre) {
   if (row0 >= p.M || col0 >= p.N) return;                 // warp-uniform
   const int row = row0 + lane;
-  const int rows_valid = min(32, p.M - row0);
+  const int rows_valid = (p.dbg_mode & 1) ? 0 : min(32, p.M - row0);
   const bool full = (col0 + 32 <= p.N);
   if (p.y_f32 && row < p.M) {
     float* d = p.y_f32 + (long long)row * p.ldy32 + col0;
@@ -310,7 +312,7 @@ __device__ __forceinline__ void epi_qkv(const GemmParams& p, int row0, int lane,
 __device__ __forceinline__ void epi_glu(const GemmParams& p, int row0, int lane, int hcol0, const uint32_t (&u)[32],
                                         const uint32_t (&g)[32], uint32_t xp) {
   if (row0 >= p.M || hcol0 >= p.F) return;
-  const int rows_valid = min(32, p.M - row0);
+  const int rows_valid = (p.dbg_mode & 1) ? 0 : min(32, p.M - row0);
   uint32_t uw[16], gw[16], hw[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -484,7 +486,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
           tmem_ld_32x32(t_row + c, u);
           tmem_ld_32x32(t_row + 128 + c, g);
           tmem_ld_wait();
-          epi_glu(p, row0, lane, n_blk * 128 + c, u, g, xp);
+          if (!(p.dbg_mode & 2)) epi_glu(p, row0, lane, n_blk * 128 + c, u, g, xp);
         }
       } else if constexpr (EPI == EPI_PAIRSUM) {
         {
@@ -503,7 +505,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
             uint32_t acc[32];
             tmem_ld_32x32(t_row + c, acc);
             tmem_ld_wait();
-            epi_store(p, row0, lane, n_blk * BLOCK_N + c, acc, xp, rpre[j], have_pre);
+            if (!(p.dbg_mode & 2)) epi_store(p, row0, lane, n_blk * BLOCK_N + c, acc, xp, rpre[j], have_pre);
           }
         }
       } else {
@@ -513,7 +515,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
           tmem_ld_32x32(t_row + c, acc);
           tmem_ld_wait();
           if constexpr (EPI == EPI_QKV) epi_qkv(p, row0, lane, n_blk * BLOCK_N + c, acc, sn, cs, xp);
-          else epi_store(p, row0, lane, n_blk * BLOCK_N + c, acc, xp, rpre[0], false);
+          else if (!(p.dbg_mode & 2)) epi_store(p, row0, lane, n_blk * BLOCK_N + c, acc, xp, rpre[0], false);
         }
       }
       tc_fence_before();
@@ -950,7 +952,9 @@ static int launch_tn(const GemmParams& p, const void* a, long long lda, const vo
   }
   const int tiles = ceil_div(p.M, BLOCK_M) * (EPI == EPI_PAIRSUM ? 1 : ceil_div(p.N, BLOCK_N));
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  cudaError_t le = launch_ex(gemm_tn_kernel<BLOCK_N, EPI>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, 0, true, p, tm_a, tm_b);
+  GemmParams pp = p;
+  pp.dbg_mode = g_gemm_dbg_mode;
+  cudaError_t le = launch_ex(gemm_tn_kernel<BLOCK_N, EPI>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, 0, true, pp, tm_a, tm_b);
   if (le != cudaSuccess) {
     set_error("launch gemm_tn_kernel: %s", cudaGetErrorString(le));
     return MPX_ERR_CUDA;
