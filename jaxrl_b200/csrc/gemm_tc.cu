@@ -190,8 +190,7 @@ __device__ __forceinline__ void epi_store(const GemmParams& p, int row0, int lan
         const uint4 bv = reinterpret_cast<const uint4*>(p.bias + col0)[i];
         const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          w[4 * i + e] = pack_bf16(bf16_lo(w[4 * i + e]) + bf16_lo(bw[e]), bf16_hi(w[4 * i + e]) + bf16_hi(bw[e]));
+        for (int e = 0; e < 4; ++e) w[4 * i + e] = bf16x2_add(w[4 * i + e], bw[e]);
       }
     } else {
 #pragma unroll
@@ -230,7 +229,7 @@ __device__ __forceinline__ void epi_store(const GemmParams& p, int row0, int lan
       }
       warp_rows_from_fetched(xp, c, rw, lane);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) w[i] = pack_bf16(bf16_lo(w[i]) + bf16_lo(rw[i]), bf16_hi(w[i]) + bf16_hi(rw[i]));
+      for (int i = 0; i < 16; ++i) w[i] = bf16x2_add(w[i], rw[i]);
     } else if (row < p.M) {
       const __nv_bfloat16* r = p.residual + (long long)row * p.ldr + col0;
 #pragma unroll
