@@ -417,6 +417,8 @@ static int launch_fwd(const mpx_attn_train_args* a, cudaStream_t s) {
   return check_launch("attn_fwd_kernel");
 }
 
+int attn_bwd_tc_launch(const mpx_attn_train_bwd_args* a, cudaStream_t stream);   // attn_train_bwd_tc.cu
+
 template <int G>
 static int launch_bwd(const mpx_attn_train_bwd_args* a, cudaStream_t s) {
   const long long M = (long long)a->B * a->T;
@@ -430,8 +432,11 @@ static int launch_bwd(const mpx_attn_train_bwd_args* a, cudaStream_t s) {
   int dgrid = (int)((nw + 7) / 8 < (long long)num_sms() * 16 ? (nw + 7) / 8 : (long long)num_sms() * 16);
   attn_bwd_delta_kernel<<<dgrid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(a->dout), a->lddo,
                                               reinterpret_cast<const __nv_bfloat16*>(a->o), a->ldo, a->delta, M, a->Nq);
+  const int tc = attn_bwd_tc_launch(a, s);          // tcgen05 / TMEM kernel when the layout allows (attn_train_bwd_tc.cu)
+  if (tc != MPX_OK && tc != MPX_ERR_UNSUPPORTED) return tc;
   dim3 grid(a->T / AT_TILE, a->Nkv, a->B);
-  attn_bwd_kernel<G><<<grid, 128, 0, s>>>(
+  if (tc == MPX_ERR_UNSUPPORTED)
+    attn_bwd_kernel<G><<<grid, 128, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(a->q), a->ldq, reinterpret_cast<const __nv_bfloat16*>(a->k), a->ldk,
       reinterpret_cast<const __nv_bfloat16*>(a->v), a->ldv, reinterpret_cast<const __nv_bfloat16*>(a->dout), a->lddo,
       a->lse, a->delta, a->dq_acc, reinterpret_cast<__nv_bfloat16*>(a->dk), a->lddk,

@@ -1,0 +1,305 @@
+// PPO-update attention BACKWARD on 5th-generation tensor cores: the five contractions of the flash-attention
+// transpose (autodiff of the training branch of AttentionBlock.__call__, reference mapox_trainer/model/attention.py:
+// 151-169) issued as tcgen05.mma with every accumulator in TMEM.  Same arithmetic as attn_bwd_kernel in
+// attn_train.cu (fp32 P and dS from the saved base-2 log-sum-exp and delta = rowsum(dO*O); P and dS rounded to bf16
+// before they feed the next contraction; fp32 accumulation).
+//
+// CTA = (batch row b, 128-key tile j); it owns dK_j and dV_j (accumulated in TMEM over the 4 query heads of the GQA
+// group and every 128-query tile i >= j) and adds its dQ contribution to the fp32 accumulator with red.add (finished
+// by attn_bwd_dq_kernel, which also applies the inverse RoPE).  Per (i, h) iteration:
+//   S  [q x k] = Q_h  . K_j^T        A = Q box  (K-major, K = 32)        B = [k|v] box (K-major, first half)
+//   dP [q x k] = dO_h . V_j^T        A = dO box (K-major, K = 32)        B = [k|v] box (K-major, +64 B: the v half)
+//   P = exp2(S*scale*log2e - lse), dS = P * (dP - delta) * scale         (128 threads, thread = query row)
+//   dV [k x d] += P^T  . dO_h        A = P  tile (MN-major: M = keys)    B = dO box (MN-major, N = 32)
+//   dK [k x d] += dS^T . Q_h         A = dS tile (MN-major)              B = Q box  (MN-major, N = 32)
+//   dQ [q x d]  = dS   . K_j         A = dS tile (K-major, K = 128 keys) B = [k|v] box (MN-major, N = 32: the k half)
+// Every global operand box is [128 rows x 64 columns] with the 128-byte swizzle (the head-dim-32 operand is the first
+// half of each row: the Q / dO boxes are loaded at column h*32 so that head h always comes first).
+// Roles (192 threads): warps 0-3 softmax + epilogue, warp 4 TMA producer, warp 5 MMA issuer / TMEM owner.
+// Requires Nkv == 1, packed q|k|v rows, head_dim 32, T % 128 == 0, T <= 1024.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.h"
+
+namespace mpx {
+
+extern int g_attn_train_impl;
+
+constexpr int BT = 128;            // queries per tile == keys per tile
+
+struct AttnBwdTcParams {
+  const float* lse;                // (M, Nq) base-2 log-sum-exp (scale folded in)
+  const float* delta;              // (M, Nq)
+  float* dq_acc;                   // (M, Nq*32) fp32
+  __nv_bfloat16* dk;
+  long long lddk;
+  __nv_bfloat16* dv;
+  long long lddv;
+  const int32_t* pos;
+  int pos_len;
+  const float* timescale;
+  int T, Nq, kv_col;
+  float scale, scale_log2;
+};
+
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap tm_qkv,
+                   const __grid_constant__ CUtensorMap tm_do) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sKV = smem;                       // 16 KB  [128 keys x (k | v)]
+  uint8_t* sQ = smem + 16384;                // 2 x 16 KB  (double buffered per iteration)
+  uint8_t* sDO = smem + 16384 * 3;           // 2 x 16 KB
+  uint8_t* sP = smem + 16384 * 5;            // 32 KB  [128 q x 128 keys] bf16: 2 boxes of 64 keys
+  uint8_t* sDS = smem + 16384 * 7;           // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 * 9);
+  uint64_t* kv_full = bars;
+  uint64_t* in_full = bars + 1;              // [2] Q + dO boxes of an iteration landed
+  uint64_t* in_empty = bars + 3;             // [2] all MMAs reading them are done
+  uint64_t* s_full = bars + 5;               // S and dP accumulators written
+  uint64_t* s_empty = bars + 6;              // ... and read by the softmax threads (4 warps)
+  uint64_t* p_full = bars + 7;               // P and dS tiles written (4 warps)
+  uint64_t* p_empty = bars + 8;              // dV/dK/dQ MMAs done: tiles reusable, dQ readable
+  uint64_t* dq_empty = bars + 9;             // dQ accumulator read (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = p.T / BT;
+  const int kt = (int)blockIdx.x;             // key tile; tile 0 has the most work (all query tiles see it)
+  const int b = blockIdx.y;
+  const long long tok0 = (long long)b * p.T;
+  const int n_iter = (nt - kt) * p.Nq;        // (query tile i = kt .. nt-1) x heads
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&in_full[s], 1);
+      mbar_init(&in_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(p_full, 4);
+    mbar_init(p_empty, 1);
+    mbar_init(dq_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 288, tDQ = tmem_base + 320;
+
+  if (warp == 4) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, 16384);
+      tma_load_2d(&tm_qkv, kv_full, sKV, p.kv_col, (int)(tok0 + kt * BT));
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it & 1;
+        const int i = kt + it / p.Nq, h = it % p.Nq;
+        mbar_wait(&in_empty[s], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&in_full[s], 32768);
+        tma_load_2d(&tm_qkv, &in_full[s], sQ + s * 16384, h * 32, (int)(tok0 + i * BT));
+        tma_load_2d(&tm_do, &in_full[s], sDO + s * 16384, h * 32, (int)(tok0 + i * BT));
+      }
+    }
+  } else if (warp == 5) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);    // K-major x K-major
+      constexpr uint32_t id_kd = umma_idesc_bf16(128, 32, 1, 1);    // MN-major x MN-major  (dV, dK)
+      constexpr uint32_t id_q = umma_idesc_bf16(128, 32, 0, 1);     // K-major x MN-major   (dQ)
+      mbar_wait(kv_full, 0);
+      const uint32_t kv = smem_u32(sKV);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it & 1;
+        const uint32_t q = smem_u32(sQ + s * 16384), d_o = smem_u32(sDO + s * 16384);
+        mbar_wait(&in_full[s], (it >> 1) & 1);
+        mbar_wait(s_empty, (it & 1) ^ 1);                    // softmax of the previous iteration has read S / dP
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          umma_bf16(tS, umma_smem_desc_sw128(q + 32 * k, 16, 1024), umma_smem_desc_sw128(kv + 32 * k, 16, 1024), id_s, k);
+          umma_bf16(tDP, umma_smem_desc_sw128(d_o + 32 * k, 16, 1024), umma_smem_desc_sw128(kv + 64 + 32 * k, 16, 1024),
+                    id_s, k);
+        }
+        umma_commit(s_full);
+        mbar_wait(p_full, it & 1);                           // P and dS tiles of this iteration are in smem
+        mbar_wait(dq_empty, (it & 1) ^ 1);                   // previous dQ has been drained
+        tc_fence_after();
+        const uint32_t pp = smem_u32(sP), ds = smem_u32(sDS);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {                        // contraction over the 128 queries: 16 rows per step
+          umma_bf16(tDV, umma_smem_desc_sw128(pp + 2048 * k, 16384, 1024), umma_smem_desc_sw128(d_o + 2048 * k, 8192, 1024),
+                    id_kd, (it | k) != 0 ? 1u : 0u);
+          umma_bf16(tDK, umma_smem_desc_sw128(ds + 2048 * k, 16384, 1024), umma_smem_desc_sw128(q + 2048 * k, 8192, 1024),
+                    id_kd, (it | k) != 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)                          // contraction over the 128 keys: two 64-key boxes
+          umma_bf16(tDQ, umma_smem_desc_sw128(ds + (k >> 2) * 16384 + 32 * (k & 3), 16, 1024),
+                    umma_smem_desc_sw128(kv + 2048 * k, 8192, 1024), id_q, k != 0 ? 1u : 0u);
+        umma_commit(&in_empty[s]);
+        umma_commit(p_empty);
+      }
+    }
+  } else {
+    // ================================ softmax / epilogue warps ================================
+    const int r = warp * 32 + lane;                          // query row of the tile == TMEM lane (also key row at the end)
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    for (int it = 0; it < n_iter; ++it) {
+      const int i = kt + it / p.Nq, h = it % p.Nq;
+      const long long qtok = tok0 + (long long)i * BT + r;
+      const float lse_r = p.lse[qtok * p.Nq + h];
+      const float dl_r = p.delta[qtok * p.Nq + h];
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      if (it > 0) {
+        // dQ of the previous iteration (its MMAs finished before this iteration's S): add to the fp32 accumulator
+        const int pi = kt + (it - 1) / p.Nq, ph = (it - 1) % p.Nq;
+        uint32_t dq[32];
+        tmem_ld_32x32(tDQ + lane_off, dq);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_empty);
+        float* dst = p.dq_acc + (tok0 + (long long)pi * BT + r) * (long long)(p.Nq * 32) + ph * 32;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) atomicAdd(dst + c, __uint_as_float(dq[c]));
+      }
+      mbar_wait(p_empty, (it & 1) ^ 1);                      // previous iteration's MMAs no longer read sP / sDS
+      const uint32_t prow = smem_u32(sP) + r * 128, dsrow = smem_u32(sDS) + r * 128;
+      const bool diag = (i == kt);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {                          // 32 keys at a time
+        uint32_t sv[32], dpv[32];
+        tmem_ld_32x32(tS + lane_off + 32 * c, sv);
+        tmem_ld_32x32(tDP + lane_off + 32 * c, dpv);
+        tmem_ld_wait();
+        uint32_t pw[16], dw[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float p0 = ex2_approx(__uint_as_float(sv[2 * e]) * p.scale_log2 - lse_r);
+          float p1 = ex2_approx(__uint_as_float(sv[2 * e + 1]) * p.scale_log2 - lse_r);
+          if (diag) {
+            if (32 * c + 2 * e > r) p0 = 0.f;
+            if (32 * c + 2 * e + 1 > r) p1 = 0.f;
+          }
+          pw[e] = pack_bf16(p0, p1);
+          dw[e] = pack_bf16(p0 * (__uint_as_float(dpv[2 * e]) - dl_r) * p.scale,
+                            p1 * (__uint_as_float(dpv[2 * e + 1]) - dl_r) * p.scale);
+        }
+        // key columns [32c, 32c+32): box c >> 1, 16-byte chunks 4*(c & 1) .. +3 of the row (128-byte swizzle)
+        const uint32_t boxo = (c >> 1) * 16384;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const uint32_t off = boxo + ((((c & 1) * 4 + ch) ^ (r & 7)) << 4);
+          sts_v4(prow + off, make_uint4(pw[4 * ch], pw[4 * ch + 1], pw[4 * ch + 2], pw[4 * ch + 3]));
+          sts_v4(dsrow + off, make_uint4(dw[4 * ch], dw[4 * ch + 1], dw[4 * ch + 2], dw[4 * ch + 3]));
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(s_empty);
+        mbar_arrive(p_full);
+      }
+    }
+    // ---- last dQ, then dK / dV of this key tile (thread = key row)
+    mbar_wait(p_empty, (n_iter & 1) ^ 1);
+    tc_fence_after();
+    {
+      const int pi = kt + (n_iter - 1) / p.Nq, ph = (n_iter - 1) % p.Nq;
+      uint32_t dq[32];
+      tmem_ld_32x32(tDQ + lane_off, dq);
+      tmem_ld_wait();
+      float* dst = p.dq_acc + (tok0 + (long long)pi * BT + r) * (long long)(p.Nq * 32) + ph * 32;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) atomicAdd(dst + c, __uint_as_float(dq[c]));
+    }
+    const long long ktok = tok0 + (long long)kt * BT + r;
+    uint32_t dkv[32], dvv[32];
+    tmem_ld_32x32(tDK + lane_off, dkv);
+    tmem_ld_32x32(tDV + lane_off, dvv);
+    tmem_ld_wait();
+    // inverse RoPE on dK (positional_embeddings.py:14-27 transposed): pairs (d, d + 16)
+    const float pf = (float)p.pos[ktok % p.pos_len];
+    uint32_t klo[8], khi[8], vw[16];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float o_lo[2], o_hi[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int d = 2 * e + u;
+        float sn, cs;
+        sincosf(pf / p.timescale[d], &sn, &cs);
+        const float a = __uint_as_float(dkv[d]), bb = __uint_as_float(dkv[d + 16]);
+        o_lo[u] = a * cs + bb * sn;
+        o_hi[u] = bb * cs - a * sn;
+      }
+      klo[e] = pack_bf16(o_lo[0], o_lo[1]);
+      khi[e] = pack_bf16(o_hi[0], o_hi[1]);
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) vw[e] = pack_bf16(__uint_as_float(dvv[2 * e]), __uint_as_float(dvv[2 * e + 1]));
+    uint4* dkr = reinterpret_cast<uint4*>(p.dk + ktok * p.lddk);
+    dkr[0] = make_uint4(klo[0], klo[1], klo[2], klo[3]);
+    dkr[1] = make_uint4(klo[4], klo[5], klo[6], klo[7]);
+    dkr[2] = make_uint4(khi[0], khi[1], khi[2], khi[3]);
+    dkr[3] = make_uint4(khi[4], khi[5], khi[6], khi[7]);
+    uint4* dvr = reinterpret_cast<uint4*>(p.dv + ktok * p.lddv);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dvr[c] = make_uint4(vw[4 * c], vw[4 * c + 1], vw[4 * c + 2], vw[4 * c + 3]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
+// Returns MPX_ERR_UNSUPPORTED (without setting an error) when the shape is not covered; the caller falls back.
+int attn_bwd_tc_launch(const mpx_attn_train_bwd_args* a, cudaStream_t stream) {
+  const long long QD = (long long)a->Nq * 32;
+  const bool packed = a->Nkv == 1 && a->D == 32 && a->T % BT == 0 && a->T <= 1024 && a->ldq == a->ldk && a->ldk == a->ldv &&
+                      a->k == a->q + QD && a->v == a->k + 32 && a->ldq >= QD + 64 && (a->ldq % 8) == 0 &&
+                      (a->lddo % 8) == 0 && a->lddo >= QD && (a->lddk % 8) == 0 && (a->lddv % 8) == 0 &&
+                      (reinterpret_cast<uintptr_t>(a->dk) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->dv) & 15) == 0;
+  if (!packed || g_attn_train_impl != 0) return MPX_ERR_UNSUPPORTED;
+  const long long M = (long long)a->B * a->T;
+  CUtensorMap tm_qkv, tm_do;
+  int rc = make_tmap_bf16_2d(&tm_qkv, a->q, (uint64_t)M, (uint64_t)a->ldq, (uint64_t)a->ldq, 64, 128);
+  if (rc) return rc;
+  // dO (M, Nq*32): boxes of 64 columns starting at h*32 - the last head's box runs 32 columns past the row end,
+  // which TMA zero-fills (and those columns are never used)
+  rc = make_tmap_bf16_2d(&tm_do, a->dout, (uint64_t)M, (uint64_t)QD, (uint64_t)a->lddo, 64, 128);
+  if (rc) return rc;
+  const int smem = 1024 + 16384 * 9 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(attn_bwd_tc): %s", cudaGetErrorString(e));
+      return MPX_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  AttnBwdTcParams p;
+  p.lse = a->lse; p.delta = a->delta; p.dq_acc = a->dq_acc;
+  p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.lddk = a->lddk;
+  p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv); p.lddv = a->lddv;
+  p.pos = a->pos; p.pos_len = a->pos_len; p.timescale = a->rope_timescale;
+  p.T = a->T; p.Nq = a->Nq; p.kv_col = (int)QD;
+  p.scale = 1.0f / sqrtf((float)a->D);
+  p.scale_log2 = p.scale * 1.4426950408889634f;
+  dim3 grid(a->T / BT, a->B);
+  attn_bwd_tc_kernel<<<grid, 192, smem, stream>>>(p, tm_qkv, tm_do);
+  return check_launch("attn_bwd_tc_kernel");
+}
+
+}  // namespace mpx

@@ -18,7 +18,7 @@ BF16 = torch.bfloat16
 @pytest.mark.parametrize("B,T,Nq,Nkv", [(2, 64, 4, 1), (3, 128, 4, 1), (1, 512, 4, 1), (5, 256, 4, 1), (2, 128, 4, 2),
                                         (2, 64, 4, 4)])
 def test_attn_train_fwd_bwd(B, T, Nq, Nkv, impl):
-    """impl 0: tcgen05/TMEM forward where the shape allows (Nkv == 1, T % 128 == 0), impl 1: mma.sync forward."""
+    """impl 0: tcgen05/TMEM forward AND backward where the shape allows (Nkv == 1, T % 128 == 0), impl 1: mma.sync."""
     from jaxrl_b200 import ops
     from jaxrl_b200._lib import lib
     lib.mpx_debug_set(2, impl)
@@ -39,8 +39,13 @@ def test_attn_train_fwd_bwd(B, T, Nq, Nkv, impl):
     (ref.float() * dout.float()).sum().backward()
 
     qkv = torch.cat([q.reshape(B * T, QD), k.reshape(B * T, KD), v.reshape(B * T, KD)], dim=1).detach().to(DEV).contiguous()
+    dqkv = torch.zeros(B * T, QKV, dtype=BF16, device=DEV)
     try:
         o, lse = ops.attn_train_fwd(qkv, qkv[:, QD:], qkv[:, QD + KD:], B, T, Nq, Nkv, D, QKV, QKV, QKV)
+        torch.cuda.synchronize()
+        ops.attn_train_bwd(qkv, qkv[:, QD:], qkv[:, QD + KD:], o, dout.reshape(B * T, QD).to(DEV).contiguous(), lse,
+                           pos.to(DEV), _rope_timescale(D).to(DEV), B, T, Nq, Nkv, D, QKV, QKV, QKV,
+                           dqkv, dqkv[:, QD:], dqkv[:, QD + KD:], QKV, QKV, QKV)
         torch.cuda.synchronize()
     finally:
         lib.mpx_debug_set(2, 0)
@@ -48,15 +53,10 @@ def test_attn_train_fwd_bwd(B, T, Nq, Nkv, impl):
     # reference's GPU implementation, does); the XLA path rounds after normalising -> up to 2 bf16 ulps apart.
     assert_close_bf16(o.reshape(B, T, Nq, D), ref, f"attn_train_fwd impl{impl} B{B} T{T} kv{Nkv}", rtol=1.7e-2, abs_floor_frac=1e-2,
                       allow_frac=5e-4, max_err_frac=0.25)
-    dqkv = torch.zeros(B * T, QKV, dtype=BF16, device=DEV)
-    ops.attn_train_bwd(qkv, qkv[:, QD:], qkv[:, QD + KD:], o, dout.reshape(B * T, QD).to(DEV).contiguous(), lse,
-                       pos.to(DEV), _rope_timescale(D).to(DEV), B, T, Nq, Nkv, D, QKV, QKV, QKV,
-                       dqkv, dqkv[:, QD:], dqkv[:, QD + KD:], QKV, QKV, QKV)
-    torch.cuda.synchronize()
     got = dqkv.float().cpu()
     for name, g, ref_g in (("dq", got[:, :QD], q0.grad.reshape(B * T, QD)),
                            ("dk", got[:, QD:QD + KD], k0.grad.reshape(B * T, KD)),
                            ("dv", got[:, QD + KD:], v0.grad.reshape(B * T, KD))):
         rel = (g - ref_g).norm().item() / (ref_g.norm().item() + 1e-9)
-        _log(f"attn_train_bwd B{B} T{T} kv{Nkv} {name}: rel_l2={rel:.4e}")
+        _log(f"attn_train_bwd impl{impl} B{B} T{T} kv{Nkv} {name}: rel_l2={rel:.4e}")
         assert rel < 3e-2, f"{name} rel l2 error {rel}"
