@@ -15,7 +15,9 @@
 //   dQ [q x d]  = dS   . K_j         A = dS tile (K-major, K = 128 keys) B = [k|v] box (MN-major, N = 32: the k half)
 // Every global operand box is [128 rows x 64 columns] with the 128-byte swizzle (the head-dim-32 operand is the first
 // half of each row: the Q / dO boxes are loaded at column h*32 so that head h always comes first).
-// Roles (192 threads): warps 0-3 softmax + epilogue, warp 4 TMA producer, warp 5 MMA issuer / TMEM owner.
+// Roles (320 threads): warps 0-7 softmax + epilogue (thread = query row; warps 0-3 take keys 0-63 of the tile, warps
+// 4-7 keys 64-127), warp 8 TMA producer, warp 9 MMA issuer / TMEM owner.  S/dP of iteration it+1 are issued as soon as
+// the softmax threads have pulled iteration it's S/dP out of TMEM, i.e. they overlap the second half of its math.
 // Requires Nkv == 1, packed q|k|v rows, head_dim 32, T % 128 == 0, T <= 1024.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -42,7 +44,10 @@ struct AttnBwdTcParams {
   float scale, scale_log2;
 };
 
-__global__ void __launch_bounds__(192, 1)
+constexpr int BWD_SM_WARPS = 8;
+constexpr int BWD_THREADS = (BWD_SM_WARPS + 2) * 32;
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap tm_qkv,
                    const __grid_constant__ CUtensorMap tm_do) {
   extern __shared__ uint8_t smem_raw[];
@@ -79,13 +84,13 @@ attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap 
       mbar_init(&in_empty[s], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_empty, 4);
-    mbar_init(p_full, 4);
+    mbar_init(s_empty, BWD_SM_WARPS);
+    mbar_init(p_full, BWD_SM_WARPS);
     mbar_init(p_empty, 1);
-    mbar_init(dq_empty, 4);
+    mbar_init(dq_empty, BWD_SM_WARPS);
     fence_barrier_init();
   }
-  if (warp == 5) {
+  if (warp == BWD_SM_WARPS + 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -95,7 +100,7 @@ attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap 
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 288, tDQ = tmem_base + 320;
 
-  if (warp == 4) {
+  if (warp == BWD_SM_WARPS) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       mbar_arrive_expect_tx(kv_full, 16384);
@@ -109,7 +114,7 @@ attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap 
         tma_load_2d(&tm_do, &in_full[s], sDO + s * 16384, h * 32, (int)(tok0 + i * BT));
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == BWD_SM_WARPS + 1) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
       constexpr uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);    // K-major x K-major
@@ -117,11 +122,11 @@ attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap 
       constexpr uint32_t id_q = umma_idesc_bf16(128, 32, 0, 1);     // K-major x MN-major   (dQ)
       mbar_wait(kv_full, 0);
       const uint32_t kv = smem_u32(sKV);
-      for (int it = 0; it < n_iter; ++it) {
+      auto mma_s = [&](int it) {                              // S and dP of iteration `it`
         const int s = it & 1;
         const uint32_t q = smem_u32(sQ + s * 16384), d_o = smem_u32(sDO + s * 16384);
         mbar_wait(&in_full[s], (it >> 1) & 1);
-        mbar_wait(s_empty, (it & 1) ^ 1);                    // softmax of the previous iteration has read S / dP
+        mbar_wait(s_empty, (it & 1) ^ 1);                     // iteration it-1's S / dP have been pulled out of TMEM
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -130,19 +135,25 @@ attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap 
                     id_s, k);
         }
         umma_commit(s_full);
-        mbar_wait(p_full, it & 1);                           // P and dS tiles of this iteration are in smem
-        mbar_wait(dq_empty, (it & 1) ^ 1);                   // previous dQ has been drained
+      };
+      mma_s(0);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it & 1;
+        const uint32_t q = smem_u32(sQ + s * 16384), d_o = smem_u32(sDO + s * 16384);
+        if (it + 1 < n_iter) mma_s(it + 1);                   // overlaps the second half of softmax(it)
+        mbar_wait(p_full, it & 1);                            // P and dS tiles of this iteration are in smem
+        mbar_wait(dq_empty, (it & 1) ^ 1);                    // previous dQ has been drained
         tc_fence_after();
         const uint32_t pp = smem_u32(sP), ds = smem_u32(sDS);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {                        // contraction over the 128 queries: 16 rows per step
+        for (int k = 0; k < 8; ++k) {                         // contraction over the 128 queries: 16 rows per step
           umma_bf16(tDV, umma_smem_desc_sw128(pp + 2048 * k, 16384, 1024), umma_smem_desc_sw128(d_o + 2048 * k, 8192, 1024),
                     id_kd, (it | k) != 0 ? 1u : 0u);
           umma_bf16(tDK, umma_smem_desc_sw128(ds + 2048 * k, 16384, 1024), umma_smem_desc_sw128(q + 2048 * k, 8192, 1024),
                     id_kd, (it | k) != 0 ? 1u : 0u);
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k)                          // contraction over the 128 keys: two 64-key boxes
+        for (int k = 0; k < 8; ++k)                           // contraction over the 128 keys: two 64-key boxes
           umma_bf16(tDQ, umma_smem_desc_sw128(ds + (k >> 2) * 16384 + 32 * (k & 3), 16, 1024),
                     umma_smem_desc_sw128(kv + 2048 * k, 8192, 1024), id_q, k != 0 ? 1u : 0u);
         umma_commit(&in_empty[s]);
@@ -151,38 +162,47 @@ attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap 
     }
   } else {
     // ================================ softmax / epilogue warps ================================
-    const int r = warp * 32 + lane;                          // query row of the tile == TMEM lane (also key row at the end)
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const int quarter = warp & 3, chalf = warp >> 2;
+    const int r = quarter * 32 + lane;                       // query row of the tile == TMEM lane (key row at the end)
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    auto drain_dq = [&](int it_done) {                       // my 16 columns of dQ(it_done) -> fp32 accumulator
+      const int pi = kt + it_done / p.Nq, ph = it_done % p.Nq;
+      uint32_t dq[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(dq[0]), "=r"(dq[1]), "=r"(dq[2]), "=r"(dq[3]), "=r"(dq[4]), "=r"(dq[5]), "=r"(dq[6]), "=r"(dq[7]),
+            "=r"(dq[8]), "=r"(dq[9]), "=r"(dq[10]), "=r"(dq[11]), "=r"(dq[12]), "=r"(dq[13]), "=r"(dq[14]), "=r"(dq[15])
+          : "r"(tDQ + lane_off + 16 * chalf)
+          : "memory");
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty);
+      float* dst = p.dq_acc + (tok0 + (long long)pi * BT + r) * (long long)(p.Nq * 32) + ph * 32 + 16 * chalf;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) atomicAdd(dst + c, __uint_as_float(dq[c]));
+    };
     for (int it = 0; it < n_iter; ++it) {
       const int i = kt + it / p.Nq, h = it % p.Nq;
       const long long qtok = tok0 + (long long)i * BT + r;
       const float lse_r = p.lse[qtok * p.Nq + h];
       const float dl_r = p.delta[qtok * p.Nq + h];
+      const bool diag = (i == kt);
       mbar_wait(s_full, it & 1);
       tc_fence_after();
-      if (it > 0) {
-        // dQ of the previous iteration (its MMAs finished before this iteration's S): add to the fp32 accumulator
-        const int pi = kt + (it - 1) / p.Nq, ph = (it - 1) % p.Nq;
-        uint32_t dq[32];
-        tmem_ld_32x32(tDQ + lane_off, dq);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(dq_empty);
-        float* dst = p.dq_acc + (tok0 + (long long)pi * BT + r) * (long long)(p.Nq * 32) + ph * 32;
+      uint32_t pw[2][16], dw[2][16];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) atomicAdd(dst + c, __uint_as_float(dq[c]));
-      }
-      mbar_wait(p_empty, (it & 1) ^ 1);                      // previous iteration's MMAs no longer read sP / sDS
-      const uint32_t prow = smem_u32(sP) + r * 128, dsrow = smem_u32(sDS) + r * 128;
-      const bool diag = (i == kt);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {                          // 32 keys at a time
+      for (int cc = 0; cc < 2; ++cc) {                       // my 64 keys, 32 at a time
+        const int c = 2 * chalf + cc;
         uint32_t sv[32], dpv[32];
         tmem_ld_32x32(tS + lane_off + 32 * c, sv);
         tmem_ld_32x32(tDP + lane_off + 32 * c, dpv);
         tmem_ld_wait();
-        uint32_t pw[16], dw[16];
+        if (cc == 1) {                                        // S / dP are in registers: the next S / dP may be issued
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_empty);
+        }
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           float p0 = ex2_approx(__uint_as_float(sv[2 * e]) * p.scale_log2 - lse_r);
@@ -191,76 +211,74 @@ attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap 
             if (32 * c + 2 * e > r) p0 = 0.f;
             if (32 * c + 2 * e + 1 > r) p1 = 0.f;
           }
-          pw[e] = pack_bf16(p0, p1);
-          dw[e] = pack_bf16(p0 * (__uint_as_float(dpv[2 * e]) - dl_r) * p.scale,
-                            p1 * (__uint_as_float(dpv[2 * e + 1]) - dl_r) * p.scale);
-        }
-        // key columns [32c, 32c+32): box c >> 1, 16-byte chunks 4*(c & 1) .. +3 of the row (128-byte swizzle)
-        const uint32_t boxo = (c >> 1) * 16384;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const uint32_t off = boxo + ((((c & 1) * 4 + ch) ^ (r & 7)) << 4);
-          sts_v4(prow + off, make_uint4(pw[4 * ch], pw[4 * ch + 1], pw[4 * ch + 2], pw[4 * ch + 3]));
-          sts_v4(dsrow + off, make_uint4(dw[4 * ch], dw[4 * ch + 1], dw[4 * ch + 2], dw[4 * ch + 3]));
+          pw[cc][e] = pack_bf16(p0, p1);
+          dw[cc][e] = pack_bf16(p0 * (__uint_as_float(dpv[2 * e]) - dl_r) * p.scale,
+                                p1 * (__uint_as_float(dpv[2 * e + 1]) - dl_r) * p.scale);
         }
       }
-      tc_fence_before();
+      mbar_wait(p_empty, (it & 1) ^ 1);                      // MMAs of iteration it-1 are done: tiles free, dQ(it-1) readable
+      tc_fence_after();
+      // key columns [64*chalf, +64) = box chalf, all 8 16-byte chunks of my row (128-byte swizzle)
+      const uint32_t prow = smem_u32(sP) + chalf * 16384 + r * 128, dsrow = smem_u32(sDS) + chalf * 16384 + r * 128;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const uint32_t off = (ch ^ (r & 7)) << 4;
+        const uint32_t* pq = &pw[ch >> 2][4 * (ch & 3)];
+        const uint32_t* dq4 = &dw[ch >> 2][4 * (ch & 3)];
+        sts_v4(prow + off, make_uint4(pq[0], pq[1], pq[2], pq[3]));
+        sts_v4(dsrow + off, make_uint4(dq4[0], dq4[1], dq4[2], dq4[3]));
+      }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(s_empty);
-        mbar_arrive(p_full);
-      }
+      if (lane == 0) mbar_arrive(p_full);
+      if (it > 0) drain_dq(it - 1);
     }
-    // ---- last dQ, then dK / dV of this key tile (thread = key row)
+    // ---- last dQ, then dK (warps 0-3) / dV (warps 4-7) of this key tile (thread = key row)
     mbar_wait(p_empty, (n_iter & 1) ^ 1);
     tc_fence_after();
-    {
-      const int pi = kt + (n_iter - 1) / p.Nq, ph = (n_iter - 1) % p.Nq;
-      uint32_t dq[32];
-      tmem_ld_32x32(tDQ + lane_off, dq);
-      tmem_ld_wait();
-      float* dst = p.dq_acc + (tok0 + (long long)pi * BT + r) * (long long)(p.Nq * 32) + ph * 32;
-#pragma unroll
-      for (int c = 0; c < 32; ++c) atomicAdd(dst + c, __uint_as_float(dq[c]));
-    }
+    drain_dq(n_iter - 1);
     const long long ktok = tok0 + (long long)kt * BT + r;
-    uint32_t dkv[32], dvv[32];
-    tmem_ld_32x32(tDK + lane_off, dkv);
-    tmem_ld_32x32(tDV + lane_off, dvv);
-    tmem_ld_wait();
-    // inverse RoPE on dK (positional_embeddings.py:14-27 transposed): pairs (d, d + 16)
-    const float pf = (float)p.pos[ktok % p.pos_len];
-    uint32_t klo[8], khi[8], vw[16];
+    if (chalf == 0) {
+      uint32_t dkv[32];
+      tmem_ld_32x32(tDK + lane_off, dkv);
+      tmem_ld_wait();
+      // inverse RoPE on dK (positional_embeddings.py:14-27 transposed): pairs (d, d + 16)
+      const float pf = (float)p.pos[ktok % p.pos_len];
+      uint32_t klo[8], khi[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float o_lo[2], o_hi[2];
+      for (int e = 0; e < 8; ++e) {
+        float o_lo[2], o_hi[2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int d = 2 * e + u;
-        float sn, cs;
-        sincosf(pf / p.timescale[d], &sn, &cs);
-        const float a = __uint_as_float(dkv[d]), bb = __uint_as_float(dkv[d + 16]);
-        o_lo[u] = a * cs + bb * sn;
-        o_hi[u] = bb * cs - a * sn;
+        for (int u = 0; u < 2; ++u) {
+          const int d = 2 * e + u;
+          float sn, cs;
+          sincosf(pf / p.timescale[d], &sn, &cs);
+          const float a = __uint_as_float(dkv[d]), bb = __uint_as_float(dkv[d + 16]);
+          o_lo[u] = a * cs + bb * sn;
+          o_hi[u] = bb * cs - a * sn;
+        }
+        klo[e] = pack_bf16(o_lo[0], o_lo[1]);
+        khi[e] = pack_bf16(o_hi[0], o_hi[1]);
       }
-      klo[e] = pack_bf16(o_lo[0], o_lo[1]);
-      khi[e] = pack_bf16(o_hi[0], o_hi[1]);
+      uint4* dkr = reinterpret_cast<uint4*>(p.dk + ktok * p.lddk);
+      dkr[0] = make_uint4(klo[0], klo[1], klo[2], klo[3]);
+      dkr[1] = make_uint4(klo[4], klo[5], klo[6], klo[7]);
+      dkr[2] = make_uint4(khi[0], khi[1], khi[2], khi[3]);
+      dkr[3] = make_uint4(khi[4], khi[5], khi[6], khi[7]);
+    } else {
+      uint32_t dvv[32], vw[16];
+      tmem_ld_32x32(tDV + lane_off, dvv);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) vw[e] = pack_bf16(__uint_as_float(dvv[2 * e]), __uint_as_float(dvv[2 * e + 1]));
+      uint4* dvr = reinterpret_cast<uint4*>(p.dv + ktok * p.lddv);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dvr[c] = make_uint4(vw[4 * c], vw[4 * c + 1], vw[4 * c + 2], vw[4 * c + 3]);
     }
-#pragma unroll
-    for (int e = 0; e < 16; ++e) vw[e] = pack_bf16(__uint_as_float(dvv[2 * e]), __uint_as_float(dvv[2 * e + 1]));
-    uint4* dkr = reinterpret_cast<uint4*>(p.dk + ktok * p.lddk);
-    dkr[0] = make_uint4(klo[0], klo[1], klo[2], klo[3]);
-    dkr[1] = make_uint4(klo[4], klo[5], klo[6], klo[7]);
-    dkr[2] = make_uint4(khi[0], khi[1], khi[2], khi[3]);
-    dkr[3] = make_uint4(khi[4], khi[5], khi[6], khi[7]);
-    uint4* dvr = reinterpret_cast<uint4*>(p.dv + ktok * p.lddv);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) dvr[c] = make_uint4(vw[4 * c], vw[4 * c + 1], vw[4 * c + 2], vw[4 * c + 3]);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, 512);
+  if (warp == BWD_SM_WARPS + 1) tmem_dealloc(tmem_base, 512);
 }
 
 // Returns MPX_ERR_UNSUPPORTED (without setting an error) when the shape is not covered; the caller falls back.
@@ -298,7 +316,7 @@ int attn_bwd_tc_launch(const mpx_attn_train_bwd_args* a, cudaStream_t stream) {
   p.scale = 1.0f / sqrtf((float)a->D);
   p.scale_log2 = p.scale * 1.4426950408889634f;
   dim3 grid(a->T / BT, a->B);
-  attn_bwd_tc_kernel<<<grid, 192, smem, stream>>>(p, tm_qkv, tm_do);
+  attn_bwd_tc_kernel<<<grid, BWD_THREADS, smem, stream>>>(p, tm_qkv, tm_do);
   return check_launch("attn_bwd_tc_kernel");
 }
 
