@@ -42,6 +42,7 @@ struct AttnBwdTcParams {
   const float* timescale;
   int T, Nq, kv_col;
   float scale, scale_log2;
+  unsigned long long* dbg;
 };
 
 constexpr int BWD_SM_WARPS = 8;
@@ -165,6 +166,8 @@ attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap 
     const int quarter = warp & 3, chalf = warp >> 2;
     const int r = quarter * 32 + lane;                       // query row of the tile == TMEM lane (key row at the end)
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    unsigned long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ? p.dbg : nullptr;
+    dbg_stamp(dbg, 0);
     auto drain_dq = [&](int it_done) {                       // my 16 columns of dQ(it_done) -> fp32 accumulator
       const int pi = kt + it_done / p.Nq, ph = it_done % p.Nq;
       uint32_t dq[16];
@@ -179,8 +182,14 @@ attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap 
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_empty);
       float* dst = p.dq_acc + (tok0 + (long long)pi * BT + r) * (long long)(p.Nq * 32) + ph * 32 + 16 * chalf;
+      // 16-byte vector reductions: 4 instructions per thread instead of 16 scalar ones (the scalar version made the
+      // drain - 4096 uncoalesced red.add per iteration - the longest phase of the loop)
 #pragma unroll
-      for (int c = 0; c < 16; ++c) atomicAdd(dst + c, __uint_as_float(dq[c]));
+      for (int c = 0; c < 4; ++c)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * c), "f"(__uint_as_float(dq[4 * c])),
+                     "f"(__uint_as_float(dq[4 * c + 1])), "f"(__uint_as_float(dq[4 * c + 2])),
+                     "f"(__uint_as_float(dq[4 * c + 3]))
+                     : "memory");
     };
     for (int it = 0; it < n_iter; ++it) {
       const int i = kt + it / p.Nq, h = it % p.Nq;
@@ -190,6 +199,7 @@ attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap 
       const bool diag = (i == kt);
       mbar_wait(s_full, it & 1);
       tc_fence_after();
+      if (it < 6) dbg_stamp(dbg, 1 + 5 * it);
       uint32_t pw[2][16], dw[2][16];
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {                       // my 64 keys, 32 at a time
@@ -216,8 +226,10 @@ attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap 
                                 p1 * (__uint_as_float(dpv[2 * e + 1]) - dl_r) * p.scale);
         }
       }
+      if (it < 6) dbg_stamp(dbg, 2 + 5 * it);
       mbar_wait(p_empty, (it & 1) ^ 1);                      // MMAs of iteration it-1 are done: tiles free, dQ(it-1) readable
       tc_fence_after();
+      if (it < 6) dbg_stamp(dbg, 3 + 5 * it);
       // key columns [64*chalf, +64) = box chalf, all 8 16-byte chunks of my row (128-byte swizzle)
       const uint32_t prow = smem_u32(sP) + chalf * 16384 + r * 128, dsrow = smem_u32(sDS) + chalf * 16384 + r * 128;
 #pragma unroll
@@ -231,7 +243,9 @@ attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap 
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (it < 6) dbg_stamp(dbg, 4 + 5 * it);
       if (it > 0) drain_dq(it - 1);
+      if (it < 6) dbg_stamp(dbg, 5 + 5 * it);
     }
     // ---- last dQ, then dK (warps 0-3) / dV (warps 4-7) of this key tile (thread = key row)
     mbar_wait(p_empty, (n_iter & 1) ^ 1);
@@ -315,6 +329,7 @@ int attn_bwd_tc_launch(const mpx_attn_train_bwd_args* a, cudaStream_t stream) {
   p.T = a->T; p.Nq = a->Nq; p.kv_col = (int)QD;
   p.scale = 1.0f / sqrtf((float)a->D);
   p.scale_log2 = p.scale * 1.4426950408889634f;
+  p.dbg = g_dbg_stamps;
   dim3 grid(a->T / BT, a->B);
   attn_bwd_tc_kernel<<<grid, BWD_THREADS, smem, stream>>>(p, tm_qkv, tm_do);
   return check_launch("attn_bwd_tc_kernel");

@@ -76,3 +76,19 @@ for kt in range(8):
 timeline("attn_fwd_tc (query tile 3, 8 key tiles)",
          lambda: ops.attn_train_fwd(qkv, qkv[:, QD:], qkv[:, QD + KD:], Bm, T, eng.Nq, eng.Nkv, eng.D, eng.QKV, eng.QKV, eng.QKV,
                                     o=o, lse=lse), lab)
+
+# training attention backward (tcgen05): CTA (key tile 0, batch row 0): 16 iterations, first 6 stamped
+dout = torch.randn(Bm * T, eng.QD, device=dev, generator=gen).to(torch.bfloat16)
+dqkv = torch.zeros(Bm * T, eng.QKV, dtype=torch.bfloat16, device=dev)
+pos_t = torch.arange(T, dtype=torch.int32, device=dev)
+lab = {0: "start (after setup)"}
+for it in range(6):
+    lab[1 + 5 * it] = f"it{it}: S/dP ready"
+    lab[2 + 5 * it] = f"it{it}: P/dS computed (regs)"
+    lab[3 + 5 * it] = f"it{it}: MMA2(it-1) done"
+    lab[4 + 5 * it] = f"it{it}: P/dS in smem, signalled"
+    lab[5 + 5 * it] = f"it{it}: dQ(it-1) drained"
+timeline("attn_bwd_tc (key tile 0)",
+         lambda: ops.attn_train_bwd(qkv, qkv[:, QD:], qkv[:, QD + KD:], o, dout, lse, pos_t, eng.timescale, Bm, T, eng.Nq, eng.Nkv,
+                                    eng.D, eng.QKV, eng.QKV, eng.QKV, dqkv, dqkv[:, QD:], dqkv[:, QD + KD:], eng.QKV, eng.QKV,
+                                    eng.QKV), lab)
