@@ -104,7 +104,9 @@ int mpx_linear_wgrad(const mpx_wgrad_args* a, mpx_stream_t stream);
  * wt_qkv rows: [q heads (Nq*D) | k heads (Nkv*D) | v heads (Nkv*D)], each row = H input features.
  * Row r uses position pos[r % pos_len] (decode: pos_len = M = B; train: pos_len = T).
  * If cache_S > 0, k/v are the cache bases (B,S,Nkv,D) and the rows are written at ring slot pos[0] % cache_S
- * (one scalar for the whole batch, exactly as attention.py:109). head_dim must be 32. */
+ * (one scalar for the whole batch, exactly as attention.py:109). head_dim must be 32.
+ * norm_scale (H) f32, when not NULL (H == 128 only), fuses the block's pre-norm (network.py:160, history_norm) in front:
+ * the rows of x are RMS-normalised in shared memory before they enter the tensor cores. */
 typedef struct {
   const mpx_bf16* x; long long ldx;          /* (M,H) */
   const mpx_bf16* wt_qkv;                    /* ((Nq+2Nkv)*D, H) */
@@ -115,6 +117,7 @@ typedef struct {
   mpx_bf16* v; long long v_row_stride;
   int cache_S;
   int M, H, Nq, Nkv, D;
+  const float* norm_scale; float norm_eps;   /* optional fused pre-norm */
 } mpx_qkv_rope_args;
 int mpx_qkv_rope(const mpx_qkv_rope_args* a, mpx_stream_t stream);
 

@@ -51,7 +51,8 @@ WgradArgs = _struct("mpx_wgrad_args", [
 QkvRopeArgs = _struct("mpx_qkv_rope_args", [
     ("x", c_p), ("ldx", c_ll), ("wt_qkv", c_p), ("pos", c_p), ("pos_len", c_i), ("rope_timescale", c_p),
     ("q", c_p), ("q_row_stride", c_ll), ("k", c_p), ("k_row_stride", c_ll), ("v", c_p), ("v_row_stride", c_ll),
-    ("cache_S", c_i), ("M", c_i), ("H", c_i), ("Nq", c_i), ("Nkv", c_i), ("D", c_i)])
+    ("cache_S", c_i), ("M", c_i), ("H", c_i), ("Nq", c_i), ("Nkv", c_i), ("D", c_i),
+    ("norm_scale", c_p), ("norm_eps", C.c_float)])
 
 GluUpArgs = _struct("mpx_glu_up_args", [
     ("x", c_p), ("ldx", c_ll), ("wt_ug", c_p), ("h", c_p), ("u_save", c_p), ("g_save", c_p),

@@ -46,6 +46,8 @@ struct GemmParams {
   int act;
   __nv_bfloat16* y_pre;      // optional: bf16 pre-activation (after bias), same pitch as y
   const float* bias_f32;     // EPI_PAIRSUM
+  const float* norm_scale;   // EPI_QKV, K == 128: RMSNorm(x; scale, eps) applied to the A tile in shared memory first
+  float norm_eps;
   int dbg_mode;              // mpx_debug_set(7, v) experiments: 1 = epilogue without global stores, 2 = no epilogue work
   // EPI_QKV
   const int32_t* pos;
@@ -73,7 +75,8 @@ struct SmemLayout {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int XPOSE_OFFSET = BAR_OFFSET + 256;   // 2 KB per epilogue warp: row-per-lane <-> coalesced transposes
-  static constexpr int TOTAL = XPOSE_OFFSET + 8 * 2048 + 1024;   // + 1 KB alignment slack
+  static constexpr int NORM_OFFSET = XPOSE_OFFSET + 8 * 2048;   // 2 x 128 partial sums of squares + 128 scales (pre-norm prologue)
+  static constexpr int TOTAL = NORM_OFFSET + 2048 + 1024;         // + 1 KB alignment slack
 };
 
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&f)[32]) {
@@ -353,6 +356,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* normed = bars + 2 * STAGES + 5;           // [EPI_QKV pre-norm] both K blocks of the A tile are normalised
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -375,6 +379,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], 8);
     }
+    mbar_init(normed, 8);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -418,6 +423,9 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        if constexpr (EPI == EPI_QKV) {
+          if (p.norm_scale) mbar_wait(normed, it & 1);      // the epilogue warps have normalised this tile's rows
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -451,6 +459,48 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
       const int row = row0 + lane;
       float sn[16], cs[16];
       if constexpr (EPI == EPI_QKV) {
+        if (p.norm_scale) {
+          // ---- pre-norm (network.py:160: history_norm) on the A tile, in place in the swizzled TMA layout: this warp
+          //      owns K block `half` of its 32 rows; the two halves of a row exchange their sums of squares via smem
+          float* sSq = reinterpret_cast<float*>(smem + L::NORM_OFFSET);
+          float* sScale = sSq + 256;
+          if (it == 0 && warp == 2) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sScale[lane + 32 * i] = p.norm_scale[lane + 32 * i];
+          }
+          const int lin = 2 * it + half;                       // running k-block counter of the producer (num_kb == 2)
+          mbar_wait(&full[lin % STAGES], (lin / STAGES) & 1);
+          const uint32_t xrow = smem_u32(smem + (lin % STAGES) * L::STAGE_BYTES + row_in_tile * 128);
+          uint4 xv[8];
+          float ss = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            xv[c] = lds_v4(xrow + ((c ^ (row_in_tile & 7)) << 4));
+            const uint32_t w4[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = bf16_lo(w4[e]), b2 = bf16_hi(w4[e]);
+              ss += a * a + b2 * b2;
+            }
+          }
+          sSq[half * 128 + row_in_tile] = ss;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const float inv = rsqrtf((sSq[row_in_tile] + sSq[128 + row_in_tile]) * (1.0f / 128.0f) + p.norm_eps);
+          const float4* sc4 = reinterpret_cast<const float4*>(sScale + half * 64);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1];
+            uint4 o;
+            o.x = pack_bf16(bf16_lo(xv[c].x) * (inv * s0.x), bf16_hi(xv[c].x) * (inv * s0.y));
+            o.y = pack_bf16(bf16_lo(xv[c].y) * (inv * s0.z), bf16_hi(xv[c].y) * (inv * s0.w));
+            o.z = pack_bf16(bf16_lo(xv[c].z) * (inv * s1.x), bf16_hi(xv[c].z) * (inv * s1.y));
+            o.w = pack_bf16(bf16_lo(xv[c].w) * (inv * s1.z), bf16_hi(xv[c].w) * (inv * s1.w));
+            sts_v4(xrow + ((c ^ (row_in_tile & 7)) << 4), o);
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 256;" ::: "memory");       // sSq may be rewritten by the next tile
+          if (lane == 0) mbar_arrive(normed);
+        }
         if (row < p.M) {
           const float pf = (float)p.pos[row % p.pos_len];
 #pragma unroll
@@ -1064,6 +1114,8 @@ extern "C" int mpx_qkv_rope(const mpx_qkv_rope_args* a, mpx_stream_t stream) {
   p.v = reinterpret_cast<__nv_bfloat16*>(a->v);
   p.q_row_stride = a->q_row_stride; p.k_row_stride = a->k_row_stride; p.v_row_stride = a->v_row_stride;
   p.cache_S = a->cache_S; p.Nq = a->Nq; p.Nkv = a->Nkv;
+  p.norm_scale = a->norm_scale; p.norm_eps = a->norm_eps;
+  MPX_REQUIRE(!a->norm_scale || a->H == 128, "mpx_qkv_rope: the fused pre-norm needs hidden_features == 128 (got %d)", a->H);
   MPX_REQUIRE((a->q_row_stride % 8) == 0 && (a->k_row_stride % 8) == 0 && (a->v_row_stride % 8) == 0,
               "mpx_qkv_rope: q/k/v row strides must be multiples of 8");
   cudaStream_t s = (cudaStream_t)stream;

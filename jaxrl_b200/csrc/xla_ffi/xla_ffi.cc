@@ -87,7 +87,7 @@ static ffi::Error QkvRopeDecodeImpl(mpx_stream_t stream, ffi::Buffer<ffi::BF16> 
   (void)kcache_in; (void)vcache_in;   // aliased with the results
   const auto kd = kcache->dimensions();
   const auto xd = x.dimensions();
-  mpx_qkv_rope_args a;
+  mpx_qkv_rope_args a{};
   a.M = static_cast<int>(kd[0]); a.H = static_cast<int>(xd[xd.size() - 1]);
   a.Nq = num_heads; a.Nkv = static_cast<int>(kd[2]); a.D = static_cast<int>(kd[3]);
   a.x = reinterpret_cast<const mpx_bf16*>(x.untyped_data()); a.ldx = a.H;

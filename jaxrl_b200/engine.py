@@ -372,10 +372,15 @@ class PolicyEngine:
         other = ws.xb
         for i in range(self.L):
             pre = f"layers.{i}."
-            ops.rmsnorm_fwd(x, p[pre + "history_norm.scale"], out=ws.xn)
-            ops.qkv_rope(ws.xn, w[pre + "wt_qkv"], pos, self.timescale, self.Nq, self.Nkv, self.D, q=ws.q,
-                         k=ws.kcache[i], v=ws.vcache[i], k_row_stride=S * self.KD, v_row_stride=S * self.KD,
-                         cache_S=S)
+            if self.H == 128:                                 # pre-norm fused into the q/k/v GEMM (shared-memory prologue)
+                ops.qkv_rope(x, w[pre + "wt_qkv"], pos, self.timescale, self.Nq, self.Nkv, self.D, q=ws.q,
+                             k=ws.kcache[i], v=ws.vcache[i], k_row_stride=S * self.KD, v_row_stride=S * self.KD,
+                             cache_S=S, norm_scale=p[pre + "history_norm.scale"])
+            else:
+                ops.rmsnorm_fwd(x, p[pre + "history_norm.scale"], out=ws.xn)
+                ops.qkv_rope(ws.xn, w[pre + "wt_qkv"], pos, self.timescale, self.Nq, self.Nkv, self.D, q=ws.q,
+                             k=ws.kcache[i], v=ws.vcache[i], k_row_stride=S * self.KD, v_row_stride=S * self.KD,
+                             cache_S=S)
             ops.attn_decode(ws.q, ws.kcache[i], ws.vcache[i], pos, self.Nq, self.Nkv, self.D, out=ws.ao)
             if hidden_out is not None and i == self.L - 1:
                 other = hidden_out                            # the block's output goes straight to the caller's buffer

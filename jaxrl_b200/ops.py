@@ -150,8 +150,10 @@ def linear_f32w(x, wt_hilo, bias, out, N: int):
 
 def qkv_rope(x, wt_qkv, pos, timescale, Nq: int, Nkv: int, D: int, q=None, k=None, v=None,
              q_row_stride: Optional[int] = None, k_row_stride: Optional[int] = None,
-             v_row_stride: Optional[int] = None, cache_S: int = 0, pos_len: Optional[int] = None):
-    """q/k/v projection + RoPE (+ ring-slot write when cache_S > 0).  Returns (q, k, v)."""
+             v_row_stride: Optional[int] = None, cache_S: int = 0, pos_len: Optional[int] = None, norm_scale=None,
+             eps: float = 1e-6):
+    """q/k/v projection + RoPE (+ ring-slot write when cache_S > 0), optionally preceded by RMSNorm(x; norm_scale).
+    Returns (q, k, v)."""
     _req(x, BF16, "x"); _req(wt_qkv, BF16, "wt_qkv"); _req(timescale, F32, "timescale")
     assert pos.dtype == I32 and pos.is_cuda
     H = x.shape[-1]
@@ -166,7 +168,7 @@ def qkv_rope(x, wt_qkv, pos, timescale, Nq: int, Nkv: int, D: int, q=None, k=Non
     v_row_stride = Nkv * D if v_row_stride is None else v_row_stride
     a = _lib.QkvRopeArgs(ptr(x), H, ptr(wt_qkv), ptr(pos), pos.numel() if pos_len is None else pos_len,
                          ptr(timescale), ptr(q), q_row_stride, ptr(k), k_row_stride, ptr(v), v_row_stride,
-                         cache_S, M, H, Nq, Nkv, D)
+                         cache_S, M, H, Nq, Nkv, D, ptr(norm_scale), eps)
     check(lib.mpx_qkv_rope(C.byref(a), stream()), "mpx_qkv_rope")
     return q, k, v
 

@@ -197,6 +197,29 @@ def test_qkv_rope_cache_slot(ops, step, S):
     assert (kc[:, mask] == 7.0).all() and (vc[:, mask] == -3.0).all()
 
 
+@pytest.mark.parametrize("Bb", [5, 300, 4096])
+def test_qkv_rope_fused_prenorm(ops, Bb):
+    """history_norm (network.py:160) folded into the q/k/v GEMM: same result as rms_norm -> qkv_rope."""
+    gen = g(Bb)
+    H, D, Nq, Nkv, S, step = 128, 32, 4, 1, 16, 5
+    x = (torch.randn(Bb, H, generator=gen) * 3).to(BF16)
+    scale = 1.0 + 0.2 * torch.randn(H, generator=gen)
+    w = (torch.randn((Nq + 2 * Nkv) * D, H, generator=gen) / math.sqrt(H)).to(BF16)
+    kc = torch.zeros((Bb, S, Nkv, D), dtype=BF16, device=DEV)
+    vc = torch.zeros((Bb, S, Nkv, D), dtype=BF16, device=DEV)
+    pos = torch.full((Bb,), step, dtype=torch.int32, device=DEV)
+    q, _, _ = ops.qkv_rope(x.to(DEV), w.to(DEV), pos, _rope_timescale(D).to(DEV), Nq, Nkv, D, k=kc, v=vc,
+                           k_row_stride=S * Nkv * D, v_row_stride=S * Nkv * D, cache_S=S, norm_scale=scale.to(DEV))
+    xn = O.rms_norm(x, scale)
+    posr = torch.full((Bb, 1), step)
+    q_ref = O.apply_rope(O.linear(xn, w[:Nq * D].t().float()).reshape(Bb, 1, Nq, D), posr, D)
+    k_ref = O.apply_rope(O.linear(xn, w[Nq * D:(Nq + Nkv) * D].t().float()).reshape(Bb, 1, Nkv, D), posr, D)
+    v_ref = O.linear(xn, w[(Nq + Nkv) * D:].t().float()).reshape(Bb, 1, Nkv, D)
+    assert_close_bf16(q.reshape(Bb, 1, Nq, D), q_ref, "prenorm q")
+    assert_close_bf16(kc[:, step % S], k_ref[:, 0], "prenorm k")
+    assert_close_bf16(vc[:, step % S], v_ref[:, 0], "prenorm v")
+
+
 def test_glu_up(ops):
     gen = g(21)
     M, K, F = 700, 128, 768
