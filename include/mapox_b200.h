@@ -141,10 +141,19 @@ int mpx_glu_up(const mpx_glu_up_args* a, mpx_stream_t stream);
  * the caller passes the un-normalised residual stream as both x and residual.
  * wt_o (H,H) = Wo^T, when not NULL (requires norm_scale), folds the attention output projection and its residual add
  * (network.py:163-165) in front: x is then the attention output and the kernel computes
- * x1 = residual + x @ Wo, out = x1 + GLU(RMSNorm(x1)); x1 never leaves shared memory. */
+ * x1 = residual + x @ Wo, out = x1 + GLU(RMSNorm(x1)); x1 never leaves shared memory.
+ * h_out (M,F), when not NULL, also receives h (bulk stores from the operand tiles): the training forward keeps it for
+ * dWdown = h^T dy, while u and g are recomputed by mpx_glu_bwd_fused. */
 int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const mpx_bf16* wt_d, const mpx_bf16* residual,
                   mpx_bf16* out, int M, int H, int F, const float* norm_scale, float eps, const mpx_bf16* wt_o,
-                  mpx_stream_t stream);
+                  mpx_bf16* h_out, mpx_stream_t stream);
+
+/* Backward of the same block in one kernel (jax.grad of feed_forward.py:73-78 inside train.py:180-230), for a forward
+ * that kept only xn = RMSNorm(x1): u, g, a = gelu(u) and dh = dy @ Wdown^T are recomputed on chip and never stored.
+ * Outputs dug (M,2F) = [du | dg], the operand of dWup/dWgate = xn^T dug, and dxn (M,H) = du @ Wup^T + dg @ Wgate^T
+ * (h for dWdown = h^T dy comes from the forward's h_out).  Same weight layouts as mpx_glu_fused. */
+int mpx_glu_bwd_fused(const mpx_bf16* xn, const mpx_bf16* dy, const mpx_bf16* wt_ug64, const mpx_bf16* wt_d,
+                      mpx_bf16* dug, mpx_bf16* dxn, int M, int H, int F, mpx_stream_t stream);
 
 /* Whole value path of a rollout step in one kernel (network.py:321,335-341 + values.py:40-45):
  * value = sum softmax(f32(pv) @ Wvh + b_vh) * centers, pv = bf16(gelu(bf16(bf16(xf @ Wvm) + b_vm))),

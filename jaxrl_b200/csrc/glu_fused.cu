@@ -21,7 +21,8 @@
 
 namespace mpx {
 
-constexpr int GF_STAGES = 4;
+constexpr int GF_STAGES = 4;        // weight ring depth of the cluster / projection variants
+constexpr int GF_MAX_STAGES = 10;   // single-CTA variant: the ring also takes the (then unused) partial and x1 regions
 constexpr int GF_STAGE_BYTES = 16384;   // [128 rows x 64 cols] bf16, SW128
 constexpr int GF_THREADS = 320;
 constexpr int GF_EPI_WARPS = 8;
@@ -36,6 +37,7 @@ struct GluFusedParams {
   const float* norm_scale;        // (128) fp32: RMSNorm applied to the x tile in shared memory before MMA1; or null
   float eps;
   int proj;                       // 1: x is the attention output; x1 = residual + x @ Wo^T is formed first
+  int h_out;                      // 1: the h chunks are also stored to global memory (tm_h) for the weight gradients
   unsigned long long* dbg;
 };
 
@@ -46,7 +48,7 @@ __device__ __forceinline__ void gf_bar_sync(int id, int nthreads) {
 __global__ void __launch_bounds__(GF_THREADS, 1)
 glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_x,
                  const __grid_constant__ CUtensorMap tm_wug, const __grid_constant__ CUtensorMap tm_wd,
-                 const __grid_constant__ CUtensorMap tm_wo) {
+                 const __grid_constant__ CUtensorMap tm_wo, const __grid_constant__ CUtensorMap tm_h) {
   extern __shared__ uint8_t smem_raw[];
   // the dynamic window starts at the same shared::cta offset in every CTA of the cluster, so the aligned
   // carve-up below is identical across the cluster (mapa relies on that)
@@ -57,9 +59,9 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
   uint8_t* sP = sW + GF_STAGES * GF_STAGE_BYTES;   // fp32 partial (cluster reduction staging)
   uint8_t* sX1 = sP + GF_PART_BYTES;          // 32 KB: x1 rows (bf16, 256 B each, 16-byte chunks XOR-swizzled by row) [proj]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sX1 + 32768);
-  uint64_t* w_full = bars;                    // [GF_STAGES]
-  uint64_t* w_empty = bars + GF_STAGES;       // [GF_STAGES]
-  uint64_t* x_full = bars + 2 * GF_STAGES;
+  uint64_t* w_full = bars;                    // [GF_MAX_STAGES]
+  uint64_t* w_empty = bars + GF_MAX_STAGES;   // [GF_MAX_STAGES]
+  uint64_t* x_full = bars + 2 * GF_MAX_STAGES;
   uint64_t* x_empty = x_full + 1;
   uint64_t* ug_full = x_full + 2;             // [2]
   uint64_t* ug_empty = x_full + 4;            // [2]
@@ -77,6 +79,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ncta = (int)cluster_nctarank(), krank = (int)cluster_ctarank();
+  const int nstages = (ncta == 1 && !p.proj) ? GF_MAX_STAGES : GF_STAGES;
   const int nchunks = p.F / 64 / ncta;        // chunks of the hidden dimension owned by this CTA
   const int chunk0 = krank * nchunks;
   const int m_tiles = (p.M + 127) / 128;
@@ -89,7 +92,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
     tma_prefetch_desc(&tm_wug);
     tma_prefetch_desc(&tm_wd);
     if (p.proj) tma_prefetch_desc(&tm_wo);
-    for (int s = 0; s < GF_STAGES; ++s) {
+    for (int s = 0; s < GF_MAX_STAGES; ++s) {
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
     }
@@ -134,7 +137,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         mbar_wait(&w_empty[stage], wphase ^ 1);
         mbar_arrive_expect_tx(&w_full[stage], GF_STAGE_BYTES);
         tma_load_2d(tm, &w_full[stage], sW + stage * GF_STAGE_BYTES, c0, c1);
-        if (++stage == GF_STAGES) { stage = 0; wphase ^= 1; }
+        if (++stage == nstages) { stage = 0; wphase ^= 1; }
       };
       for (int tile = blockIdx.y; tile < m_tiles; tile += gridDim.y) {
         mbar_wait(x_empty, xphase ^ 1);
@@ -179,7 +182,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
             umma_bf16(tUG[b], umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024),
                       idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&w_empty[stage]);
-          if (++stage == GF_STAGES) { stage = 0; wphase ^= 1; }
+          if (++stage == nstages) { stage = 0; wphase ^= 1; }
         }
         umma_commit(&ug_full[b]);
         if (last) umma_commit(x_empty);
@@ -198,7 +201,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
           umma_bf16(tD, umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024), idesc,
                     (c | k) != 0 ? 1u : 0u);
         umma_commit(&w_empty[stage]);
-        if (++stage == GF_STAGES) { stage = 0; wphase ^= 1; }
+        if (++stage == nstages) { stage = 0; wphase ^= 1; }
         umma_commit(&h_empty[b]);
         if (last) umma_commit(d_full);
       };
@@ -218,7 +221,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
               umma_bf16(tD, umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024),
                         idesc, (kb | k) != 0 ? 1u : 0u);
             umma_commit(&w_empty[stage]);
-            if (++stage == GF_STAGES) { stage = 0; wphase ^= 1; }
+            if (++stage == nstages) { stage = 0; wphase ^= 1; }
           }
           umma_commit(d0_full);
         }
@@ -342,7 +345,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         mbar_wait(&ug_full[b], ug_ph[b]);
         ug_ph[b] ^= 1;
         tc_fence_after();
-        dbg_stamp(dbg, 4 + 2 * c);
+        if (c < 8) dbg_stamp(dbg, 4 + 2 * c);
         uint32_t u[32], g[32];
         tmem_ld_32x32(tUG[b] + lane_off + 32 * half, u);
         tmem_ld_32x32(tUG[b] + lane_off + 64 + 32 * half, g);
@@ -360,6 +363,10 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         }
         mbar_wait(&h_empty[b], h_ph[b] ^ 1);                   // MMA2 of chunk c-2 no longer reads this buffer
         h_ph[b] ^= 1;
+        if (p.h_out) {                                         // ... and neither does its bulk store
+          if (half == 0 && lane == 0) bulk_wait_group_read1();
+          gf_bar_sync(2 + quarter, 64);
+        }
         const uint32_t hrow = smem_u32(sH + b * 16384 + r * 128);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -368,8 +375,20 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         }
         fence_proxy_async_smem();
         __syncwarp();
-        dbg_stamp(dbg, 5 + 2 * c);
+        if (c < 8) dbg_stamp(dbg, 5 + 2 * c);
         if (lane == 0) mbar_arrive(&h_full[b]);
+        if (p.h_out) {                                         // rows [32 quarter, +32) of h_c leave from the operand tile
+          gf_bar_sync(2 + quarter, 64);
+          if (half == 0 && lane == 0) {
+            tma_store_2d(&tm_h, sH + b * 16384 + quarter * 4096, (chunk0 + c) * 64, tile * 128 + quarter * 32);
+            bulk_commit_group();
+          }
+        }
+      }
+      uint4 rpre[8];                                           // single CTA: this thread's 64 residual columns, in flight
+      if (ncta == 1 && !p.proj && row < p.M) {                 // while the last chunks drain
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rpre[i] = *reinterpret_cast<const uint4*>(p.residual + row * 128 + 64 * half + 8 * i);
       }
       mbar_wait(d_full, dphase);
       dphase ^= 1;
@@ -383,11 +402,10 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
           tmem_ld_32x32(tD + lane_off + 64 * half + 32 * cc, acc);
           tmem_ld_wait();
           if (row < p.M) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + row * 128 + 64 * half + 32 * cc);
             uint4* o4 = reinterpret_cast<uint4*>(p.out + row * 128 + 64 * half + 32 * cc);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const uint4 rv = p.proj ? lds_v4(smem_u32(sX1 + r * 256) + (((8 * half + 4 * cc + i) ^ (r & 7)) << 4)) : r4[i];
+              const uint4 rv = p.proj ? lds_v4(smem_u32(sX1 + r * 256) + (((8 * half + 4 * cc + i) ^ (r & 7)) << 4)) : rpre[4 * cc + i];
               const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
               uint32_t ow[4];
 #pragma unroll
@@ -475,6 +493,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         }
       }
     }
+    if (p.h_out && half == 0 && lane == 0) bulk_wait_group0();   // shared memory must outlive the stores reading it
     // Exit protocol: a CTA leaves only after ITS receive barrier completed (all pushes into its shared memory have
     // landed) and nobody signals part_empty after the last tile, so no peer touches an exited CTA.
   }
@@ -490,12 +509,12 @@ using namespace mpx;
 
 extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const mpx_bf16* wt_d, const mpx_bf16* residual,
                              mpx_bf16* out, int M, int H, int F, const float* norm_scale, float eps, const mpx_bf16* wt_o,
-                             mpx_stream_t stream) {
+                             mpx_bf16* h_out, mpx_stream_t stream) {
   MPX_REQUIRE(x && wt_ug64 && wt_d && residual && out && M > 0, "mpx_glu_fused: bad arguments");
   MPX_REQUIRE(H == 128, "mpx_glu_fused: hidden_features=%d unsupported (128 only; use mpx_glu_up + mpx_linear)", H);
   MPX_REQUIRE(F > 0 && F % 64 == 0, "mpx_glu_fused: F=%d must be a positive multiple of 64", F);
   MPX_REQUIRE(!wt_o || norm_scale, "mpx_glu_fused: the projection prologue needs norm_scale");
-  CUtensorMap tm_x, tm_wug, tm_wd, tm_wo;
+  CUtensorMap tm_x, tm_wug, tm_wd, tm_wo, tm_h;
   int rc = make_tmap_bf16_2d(&tm_x, x, M, H, H, 64, 128);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_wug, wt_ug64, 2 * F, H, H, 64, 128);
@@ -504,7 +523,9 @@ extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const m
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_wo, wt_o ? wt_o : wt_d, H, H, wt_o ? H : F, 64, 128);
   if (rc) return rc;
-  const int smem = 1024 + 65536 + GF_STAGES * GF_STAGE_BYTES + GF_PART_BYTES + 32768 + 256 + 1024 + 512;
+  rc = h_out ? make_tmap_bf16_2d(&tm_h, h_out, M, F, F, 64, 32) : make_tmap_bf16_2d(&tm_h, wt_d, H, F, F, 64, 32);
+  if (rc) return rc;
+  const int smem = 1024 + 65536 + GF_STAGES * GF_STAGE_BYTES + GF_PART_BYTES + 32768 + 384 + 1024 + 512;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(glu_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -521,6 +542,7 @@ extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const m
   p.norm_scale = norm_scale;
   p.eps = eps;
   p.proj = wt_o ? 1 : 0;
+  p.h_out = h_out ? 1 : 0;
   p.dbg = g_dbg_stamps;
   MPX_REQUIRE(!norm_scale || (reinterpret_cast<uintptr_t>(norm_scale) & 15) == 0, "mpx_glu_fused: norm_scale must be 16-byte aligned");
   const int tiles = ceil_div(M, 128);
@@ -533,7 +555,7 @@ extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const m
     cl = g_glu_fused_cluster;
   int gy = num_sms() / cl;
   if (gy > tiles) gy = tiles;
-  cudaError_t le = launch_ex(glu_fused_kernel, dim3(cl, gy, 1), dim3(GF_THREADS), smem, (cudaStream_t)stream, cl, true, p, tm_x, tm_wug, tm_wd, tm_wo);
+  cudaError_t le = launch_ex(glu_fused_kernel, dim3(cl, gy, 1), dim3(GF_THREADS), smem, (cudaStream_t)stream, cl, true, p, tm_x, tm_wug, tm_wd, tm_wo, tm_h);
   if (le != cudaSuccess) {
     set_error("cudaLaunchKernelEx(glu_fused, cluster %d): %s", cl, cudaGetErrorString(le));
     return MPX_ERR_CUDA;

@@ -50,6 +50,8 @@ class PolicyEngine:
         self.QKV = self.QD + 2 * self.KD
         self.L = cfg.num_layers
         self.fused_glu = (H == 128 and cfg.ffn_size % 64 == 0)     # decode path: one kernel per GLU block
+        # training path: the same forward kernel (keeping h) and a one-kernel backward that recomputes u, g, dh on chip
+        self.fused_glu_train = self.fused_glu and os.environ.get("MPX_FUSED_GLU_TRAIN", "1") != "0"
         self.fused_value = (H == 128 and cfg.value_hidden_dim is not None and cfg.value_hidden_dim % 64 == 0
                             and cfg.value_n_logits <= 64)           # decode path: one kernel for the value path
         self.timescale = (torch.tensor(cfg.rope_max_wavelength, dtype=F32)
@@ -244,8 +246,9 @@ class PolicyEngine:
         ws.x1 = [e(M, H) for _ in range(L)]
         ws.xn2 = [e(M, H) for _ in range(L)]
         ws.h = [e(M, F) for _ in range(L)]
-        ws.u = [e(M, F) for _ in range(L)]
-        ws.g = [e(M, F) for _ in range(L)]
+        if not self.fused_glu_train:
+            ws.u = [e(M, F) for _ in range(L)]
+            ws.g = [e(M, F) for _ in range(L)]
         ws.xf, ws.zv, ws.pv = e(M, H), e(M, self.Vh), e(M, self.Vh)
         ws.logits, ws.vlogits = f(M, self.A), f(M, self.NL)
         ws.pos = torch.arange(T, dtype=I32, device=dev)
@@ -254,7 +257,7 @@ class PolicyEngine:
         ws.dvl = e(M, 64)
         ws.dpv = e(M, self.Vh)
         ws.dxa, ws.dxb, ws.dxn = e(M, H), e(M, H), e(M, H)
-        ws.dh, ws.dug = e(M, F), e(M, 2 * F)
+        ws.dh, ws.dug = (None if self.fused_glu_train else e(M, F)), e(M, 2 * F)
         ws.dqkv, ws.do = e(M, self.QKV), e(M, self.QD)
         ws.delta, ws.dq_acc = f(M, self.Nq), f(M, self.QD)
         ws.dca = [e(M * c.oh * c.ow, c.cout) for c in self.conv[:-1]]
@@ -467,8 +470,11 @@ class PolicyEngine:
                                QKV, o=ws.o[i], lse=ws.lse[i])
             ops.linear(ws.o[i], w[pre + "wt_o"], residual=ws.x[i], out=ws.x1[i])
             ops.rmsnorm_fwd(ws.x1[i], p[pre + "ffn_norm.scale"], out=ws.xn2[i])
-            ops.glu_up(ws.xn2[i], w[pre + "wt_ug"], self.F, save=True, h=ws.h[i], u=ws.u[i], g=ws.g[i])
-            ops.linear(ws.h[i], w[pre + "wt_d"], residual=ws.x1[i], out=ws.x[i + 1])
+            if self.fused_glu_train:
+                ops.glu_fused(ws.xn2[i], w[pre + "wt_ug64"], w[pre + "wt_d"], ws.x1[i], ws.x[i + 1], self.F, h_out=ws.h[i])
+            else:
+                ops.glu_up(ws.xn2[i], w[pre + "wt_ug"], self.F, save=True, h=ws.h[i], u=ws.u[i], g=ws.g[i])
+                ops.linear(ws.h[i], w[pre + "wt_d"], residual=ws.x1[i], out=ws.x[i + 1])
         self._heads_fwd(ws.x[self.L], action_mask, ws.xf, ws.logits, ws.pv, ws.zv, ws.vlogits)
         return ws.vlogits, ws.logits
 
@@ -532,11 +538,15 @@ class PolicyEngine:
         for i in reversed(range(self.L)):
             pre = f"layers.{i}."
             dx_in = dx
-            ops.linear(dx, w[pre + "w_d"], out=ws.dh)
+            if not self.fused_glu_train:
+                ops.linear(dx, w[pre + "w_d"], out=ws.dh)
             ev_down = self._side_run(lambda: ops.linear_wgrad(ws.h[i], dx_in, p.g(pre + "ffn.down_proj.kernel"), M=M, K=F,
                                                               N=H, ldx=F, ldy=H, lddw=H))
             self._wait(ev_updown)                    # dug is still being read by the previous layer's up/gate wgrads
-            ops.glu_bwd(ws.dh, ws.u[i], ws.g[i], out=ws.dug)
+            if self.fused_glu_train:
+                ops.glu_bwd_fused(ws.xn2[i], dx, w[pre + "wt_ug64"], w[pre + "wt_d"], self.F, dug=ws.dug, dxn=ws.dxn)
+            else:
+                ops.glu_bwd(ws.dh, ws.u[i], ws.g[i], out=ws.dug)
 
             def _wg_updown(i=i, pre=pre):
                 ops.linear_wgrad(ws.xn2[i], ws.dug, p.g(pre + "ffn.up_proj.kernel"), M=M, K=H, N=F, ldx=H, ldy=2 * F,
@@ -544,7 +554,8 @@ class PolicyEngine:
                 ops.linear_wgrad(ws.xn2[i], ws.dug[:, F:], p.g(pre + "ffn.up_gate.kernel"), M=M, K=H, N=F, ldx=H,
                                  ldy=2 * F, lddw=F)
             ev_updown = self._side_run(_wg_updown)
-            ops.linear(ws.dug, w[pre + "w_ug"], out=ws.dxn)
+            if not self.fused_glu_train:
+                ops.linear(ws.dug, w[pre + "w_ug"], out=ws.dxn)
             self._wait(ev_out)                       # `spare` was the d x1 the previous layer's out-proj wgrad reads
             ops.rmsnorm_bwd(ws.dxn, ws.x1[i], p[pre + "ffn_norm.scale"], dscale=p.g(pre + "ffn_norm.scale"), dres=dx,
                             out=spare)

@@ -187,15 +187,29 @@ def glu_up(x, wt_ug, F: int, save: bool = False, h=None, u=None, g=None):
     return (h, u, g) if save else h
 
 
-def glu_fused(x, wt_ug64, wt_d, residual, out, F: int, norm_scale=None, eps: float = 1e-6, wt_o=None):
+def glu_fused(x, wt_ug64, wt_d, residual, out, F: int, norm_scale=None, eps: float = 1e-6, wt_o=None, h_out=None):
     """out = residual + down(gelu(up(xn)) * gate(xn)) in one kernel (H = 128); xn = RMSNorm(x) when norm_scale is given.
-    With wt_o (Wo^T): x is the attention output, x1 = residual + x @ Wo, out = x1 + GLU(RMSNorm(x1))."""
+    With wt_o (Wo^T): x is the attention output, x1 = residual + x @ Wo, out = x1 + GLU(RMSNorm(x1)).
+    h_out (M,F), if given, also receives the hidden activation h (kept by the training forward for dWdown)."""
     _req(x, BF16, "x"); _req(wt_ug64, BF16, "wt_ug64"); _req(wt_d, BF16, "wt_d"); _req(residual, BF16, "residual")
     H = x.shape[-1]
     M = x.numel() // H
     check(lib.mpx_glu_fused(ptr(x), ptr(wt_ug64), ptr(wt_d), ptr(residual), ptr(out), M, H, F, ptr(norm_scale), eps,
-                            ptr(wt_o), stream()), "mpx_glu_fused")
+                            ptr(wt_o), ptr(h_out), stream()), "mpx_glu_fused")
     return out
+
+
+def glu_bwd_fused(xn, dy, wt_ug64, wt_d, F: int, dug=None, dxn=None):
+    """Backward of the GLU block for a forward that kept only xn (and h): recomputes u, g, dh on chip; returns
+    (dug, dxn) with dug = [du | dg] (M, 2F) - the operand of the up/gate weight gradients - and dxn (M, H).  H = 128."""
+    _req(xn, BF16, "xn"); _req(dy, BF16, "dy"); _req(wt_ug64, BF16, "wt_ug64"); _req(wt_d, BF16, "wt_d")
+    H = xn.shape[-1]
+    M = xn.numel() // H
+    dug = torch.empty(M, 2 * F, dtype=BF16, device=xn.device) if dug is None else dug
+    dxn = torch.empty(M, H, dtype=BF16, device=xn.device) if dxn is None else dxn
+    check(lib.mpx_glu_bwd_fused(ptr(xn), ptr(dy), ptr(wt_ug64), ptr(wt_d), ptr(dug), ptr(dxn), M, H, F, stream()),
+          "mpx_glu_bwd_fused")
+    return dug, dxn
 
 
 def value_head_fused(x, wt_vm, b_vm, wt_vh_hilo, b_vh, centers, value, vlogits=None, norm_scale=None,

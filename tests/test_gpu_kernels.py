@@ -634,6 +634,51 @@ def test_glu_fused_with_out_projection(ops, M, F, cluster):
                       max_err_frac=0.1)
 
 
+@pytest.mark.parametrize("M,F", [(128, 128), (77, 256), (1000, 768), (20000, 768), (131072, 768), (300, 384)])
+def test_glu_bwd_fused(ops, M, F):
+    """One-kernel GLU backward (u, g, dh recomputed in TMEM) vs the unfused kernel chain (glu_up(save) -> linear ->
+    glu_bwd -> linear), which test_glu_up / test_glu_bwd pin to the oracle, and vs fp32 autograd of the oracle block."""
+    gen = g(M + F + 3)
+    H = 128
+    xn = torch.randn(M, H, generator=gen).to(BF16)
+    dy = (torch.randn(M, H, generator=gen) * 0.5).to(BF16)
+    wu = torch.randn(H, F, generator=gen) / math.sqrt(H)
+    wg = torch.randn(H, F, generator=gen) / math.sqrt(H)
+    wd = torch.randn(F, H, generator=gen) / math.sqrt(F)
+    wt_ug64 = ops.pack_glu_weight64(wu, wg).to(DEV)
+    wt_d = wd.t().contiguous().to(BF16).to(DEV)
+    dug, dxn = ops.glu_bwd_fused(xn.to(DEV), dy.to(DEV), wt_ug64, wt_d, F)
+    # the training forward: same kernel as the rollout's, plus the h output kept for dWdown
+    res = torch.randn(M, H, generator=gen).to(BF16)
+    y = torch.empty(M, H, dtype=BF16, device=DEV)
+    h = torch.full((M, F), float("nan"), dtype=BF16, device=DEV)
+    ops.glu_fused(xn.to(DEV), wt_ug64, wt_d, res.to(DEV), y, F, h_out=h)
+    torch.cuda.synchronize()
+    # unfused chain on the same device
+    h_ref, u, gg = ops.glu_up(xn.to(DEV), ops.pack_glu_weight(wu, wg).to(DEV), F, save=True)
+    dh = ops.linear(dy.to(DEV), wd.to(BF16).to(DEV))                  # (M,H) @ (F,H)^T
+    dug_ref = torch.empty(M, 2 * F, dtype=BF16, device=DEV)
+    ops.glu_bwd(dh, u, gg, out=dug_ref)
+    w_ug = torch.cat([wu, wg], dim=1).to(BF16).to(DEV)                # (H, 2F)
+    dxn_ref = ops.linear(dug_ref, w_ug)
+    y_ref = ops.linear(h_ref, wt_d, residual=res.to(DEV))
+    torch.cuda.synchronize()
+    assert_close_bf16(y, y_ref.cpu(), f"glu_fused(h_out) y M={M}", rtol=1e-2, abs_floor_frac=1e-2, allow_frac=1e-3, max_err_frac=0.1)
+    assert_close_bf16(h, h_ref.cpu(), f"glu_bwd_fused h M={M}", rtol=1e-2, abs_floor_frac=1e-2, allow_frac=1e-3, max_err_frac=0.1)
+    assert_close_bf16(dug, dug_ref.cpu(), f"glu_bwd_fused dug M={M}", rtol=1e-2, abs_floor_frac=1e-2, allow_frac=1e-3, max_err_frac=0.1)
+    assert_close_bf16(dxn, dxn_ref.cpu(), f"glu_bwd_fused dxn M={M}", rtol=1e-2, abs_floor_frac=1e-2, allow_frac=1e-3, max_err_frac=0.1)
+    if M <= 1000:
+        # fp32 autograd of the oracle block: loose, it does not model the bf16 roundings of the backward intermediates
+        xf = xn.float().requires_grad_(True)
+        pdict = {"f.up_proj.kernel": wu.to(BF16).float(), "f.up_gate.kernel": wg.to(BF16).float(), "f.down_proj.kernel": wd.to(BF16).float()}
+        up = xf @ pdict["f.up_proj.kernel"]
+        gate = xf @ pdict["f.up_gate.kernel"]
+        y = (O.gelu_tanh(up) * gate) @ pdict["f.down_proj.kernel"]
+        (y * dy.float()).sum().backward()
+        err = (dxn.float().cpu() - xf.grad).abs().max().item()
+        assert err < 0.05 * xf.grad.abs().max().item() + 0.05, err
+
+
 @pytest.mark.parametrize("geom", [(5, 5, 16, 3, 3, 1, 1), (11, 11, 8, 3, 3, 2, 2), (6, 7, 8, 2, 3, 1, 2)])
 @pytest.mark.parametrize("with_z", [False, True])
 def test_col2im(ops, geom, with_z):
