@@ -179,6 +179,21 @@ typedef struct {
 } mpx_attn_decode_args;
 int mpx_attn_decode(const mpx_attn_decode_args* a, mpx_stream_t stream);
 
+/* Attention half of a block for one rollout step in one kernel (network.py:158-165, attention.py:96-150):
+ * history_norm -> q/k/v projection -> RoPE -> ring write at pos[0] % S -> the attention above, with the projection
+ * running under the start of the cache stream.  Replaces mpx_rmsnorm_fwd + mpx_qkv_rope + mpx_attn_decode for
+ * H == 128, Nq == 4, Nkv == 1, D == 32 (MPX_ERR_INVALID otherwise).  x (B,H) is the un-normalised residual stream;
+ * wt_qkv as in mpx_qkv_rope; kcache/vcache (B,S,1,D) are updated in place; out (B, Nq*D). */
+typedef struct {
+  const mpx_bf16* x; const float* norm_scale; float eps;
+  const mpx_bf16* wt_qkv;
+  const int32_t* pos; const float* rope_timescale;
+  mpx_bf16* kcache; mpx_bf16* vcache;
+  mpx_bf16* out;
+  int B, S, H, Nq, Nkv, D;
+} mpx_attn_decode_fused_args;
+int mpx_attn_decode_fused(const mpx_attn_decode_fused_args* a, mpx_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------- row-wise ops
  * flax nnx.RMSNorm (eps 1e-6) as used by TransformerBlock (network.py:158-172) and output_norm (:321):
  * y = bf16(x32 * (rsqrt(mean(x32^2)+eps) * scale)).  x,y (M,H) bf16, scale (H) f32; H in {128,256,384,512}. */

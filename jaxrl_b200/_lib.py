@@ -62,6 +62,11 @@ AttnDecodeArgs = _struct("mpx_attn_decode_args", [
     ("q", c_p), ("kcache", c_p), ("vcache", c_p), ("pos", c_p), ("out", c_p),
     ("B", c_i), ("S", c_i), ("Nq", c_i), ("Nkv", c_i), ("D", c_i)])
 
+AttnDecodeFusedArgs = _struct("mpx_attn_decode_fused_args", [
+    ("x", c_p), ("norm_scale", c_p), ("eps", C.c_float), ("wt_qkv", c_p), ("pos", c_p), ("rope_timescale", c_p),
+    ("kcache", c_p), ("vcache", c_p), ("out", c_p),
+    ("B", c_i), ("S", c_i), ("H", c_i), ("Nq", c_i), ("Nkv", c_i), ("D", c_i)])
+
 AttnTrainArgs = _struct("mpx_attn_train_args", [
     ("q", c_p), ("ldq", c_ll), ("k", c_p), ("ldk", c_ll), ("v", c_p), ("ldv", c_ll), ("o", c_p), ("ldo", c_ll),
     ("lse", c_p), ("B", c_i), ("T", c_i), ("Nq", c_i), ("Nkv", c_i), ("D", c_i)])
@@ -89,7 +94,7 @@ lib.mpx_hlgauss_loss_workspace_bytes.restype = C.c_size_t
 lib.mpx_hlgauss_loss_workspace_bytes.argtypes = [c_ll]
 lib.mpx_hlgauss_loss.argtypes = [c_p, c_p, c_ll, c_i, c_p, c_f, c_f, c_f, c_f, c_p, c_p, c_p, c_i, c_p, c_p]
 for _name in ("mpx_linear", "mpx_linear_wgrad", "mpx_qkv_rope", "mpx_glu_up", "mpx_attn_decode",
-              "mpx_attn_train_fwd", "mpx_attn_train_bwd"):
+              "mpx_attn_decode_fused", "mpx_attn_train_fwd", "mpx_attn_train_bwd"):
     getattr(lib, _name).argtypes = [c_p, c_p]
 lib.mpx_linear_wgrad_workspace_bytes.restype = C.c_size_t
 lib.mpx_linear_wgrad_workspace_bytes.argtypes = [c_i, c_i, c_i]

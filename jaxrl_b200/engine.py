@@ -50,6 +50,8 @@ class PolicyEngine:
         self.QKV = self.QD + 2 * self.KD
         self.L = cfg.num_layers
         self.fused_glu = (H == 128 and cfg.ffn_size % 64 == 0)     # decode path: one kernel per GLU block
+        self.fused_attn_decode = (H == 128 and self.Nq == 4 and self.Nkv == 1 and self.D == 32
+                                  and os.environ.get("MPX_FUSED_ATTN_DECODE", "1") != "0")
         # training path: the same forward kernel (keeping h) and a one-kernel backward that recomputes u, g, dh on chip
         self.fused_glu_train = self.fused_glu and os.environ.get("MPX_FUSED_GLU_TRAIN", "1") != "0"
         self.fused_value = (H == 128 and cfg.value_hidden_dim is not None and cfg.value_hidden_dim % 64 == 0
@@ -375,7 +377,10 @@ class PolicyEngine:
         other = ws.xb
         for i in range(self.L):
             pre = f"layers.{i}."
-            if self.H == 128:                                 # pre-norm fused into the q/k/v GEMM (shared-memory prologue)
+            if self.fused_attn_decode:                        # pre-norm, projection, RoPE, ring write and attention: one kernel
+                ops.attn_decode_fused(x, p[pre + "history_norm.scale"], w[pre + "wt_qkv"], pos, self.timescale,
+                                      ws.kcache[i], ws.vcache[i], self.Nq, self.Nkv, self.D, out=ws.ao)
+            elif self.H == 128:                               # pre-norm fused into the q/k/v GEMM (shared-memory prologue)
                 ops.qkv_rope(x, w[pre + "wt_qkv"], pos, self.timescale, self.Nq, self.Nkv, self.D, q=ws.q,
                              k=ws.kcache[i], v=ws.vcache[i], k_row_stride=S * self.KD, v_row_stride=S * self.KD,
                              cache_S=S, norm_scale=p[pre + "history_norm.scale"])
@@ -384,7 +389,8 @@ class PolicyEngine:
                 ops.qkv_rope(ws.xn, w[pre + "wt_qkv"], pos, self.timescale, self.Nq, self.Nkv, self.D, q=ws.q,
                              k=ws.kcache[i], v=ws.vcache[i], k_row_stride=S * self.KD, v_row_stride=S * self.KD,
                              cache_S=S)
-            ops.attn_decode(ws.q, ws.kcache[i], ws.vcache[i], pos, self.Nq, self.Nkv, self.D, out=ws.ao)
+            if not self.fused_attn_decode:
+                ops.attn_decode(ws.q, ws.kcache[i], ws.vcache[i], pos, self.Nq, self.Nkv, self.D, out=ws.ao)
             if hidden_out is not None and i == self.L - 1:
                 other = hidden_out                            # the block's output goes straight to the caller's buffer
             if self.fused_glu and self.QD == 128:

@@ -262,6 +262,52 @@ def test_attn_decode(ops, step, S, Nq, Nkv, Bb, impl):
                       rtol=1.7e-2 if impl == 0 else 1e-2, abs_floor_frac=1e-2 if impl == 0 else 4e-3)
 
 
+@pytest.mark.parametrize("step,S,Bb", [(0, 16, 3), (5, 16, 9), (31, 64, 14), (32, 64, 15), (100, 512, 33), (300, 512, 4096),
+                                       (511, 512, 130), (700, 512, 29), (1029, 512, 2100)])
+def test_attn_decode_fused(ops, step, S, Bb):
+    """history_norm + q/k/v + RoPE + ring write + attention in one kernel vs the oracle chain (network.py:158-165,
+    attention.py:96-150); the ring must change only at slot pos % S, there by exactly the new k,v."""
+    gen = g(step * 3 + S + Bb)
+    H, D, Nq, Nkv = 128, 32, 4, 1
+    x = (torch.randn(Bb, H, generator=gen) * 2).to(BF16)
+    scale = 1.0 + 0.2 * torch.randn(H, generator=gen)
+    w = (torch.randn((Nq + 2 * Nkv) * D, H, generator=gen) / math.sqrt(H)).to(BF16)
+    kc0 = torch.randn(Bb, S, Nkv, D, generator=gen).to(BF16)
+    vc0 = torch.randn(Bb, S, Nkv, D, generator=gen).to(BF16)
+    kc, vc = kc0.clone().to(DEV), vc0.clone().to(DEV)
+    pos = torch.full((Bb,), step, dtype=torch.int32, device=DEV)
+    out = ops.attn_decode_fused(x.to(DEV), scale.to(DEV), w.to(DEV), pos, _rope_timescale(D).to(DEV), kc, vc, Nq, Nkv, D)
+    torch.cuda.synchronize()
+    nb = min(Bb, 256)                      # oracle on the first and last agents
+    sel = torch.cat([torch.arange(nb // 2), torch.arange(Bb - (nb - nb // 2), Bb)]) if Bb > nb else torch.arange(Bb)
+    xn = O.rms_norm(x[sel], scale)
+    posr = torch.full((len(sel), 1), step)
+    q_ref = O.apply_rope(O.linear(xn, w[:Nq * D].t().float()).reshape(len(sel), 1, Nq, D), posr, D)
+    k_ref = O.apply_rope(O.linear(xn, w[Nq * D:(Nq + Nkv) * D].t().float()).reshape(len(sel), 1, Nkv, D), posr, D)
+    v_ref = O.linear(xn, w[(Nq + Nkv) * D:].t().float()).reshape(len(sel), 1, Nkv, D)
+    slot = step % S
+    kr, vr = kc0[sel].clone(), vc0[sel].clone()
+    kr[:, slot] = k_ref[:, 0]
+    vr[:, slot] = v_ref[:, 0]
+    ref = O.dot_product_attention(q_ref, kr, vr, kv_len=min(step + 1, S))[:, 0]
+    assert_close_bf16(kc[sel.to(DEV), slot], k_ref[:, 0], "fused decode: new k")
+    assert_close_bf16(vc[sel.to(DEV), slot], v_ref[:, 0], "fused decode: new v")
+    mask = torch.ones(S, dtype=torch.bool)
+    mask[slot] = False
+    assert torch.equal(kc.cpu()[:, mask], kc0[:, mask]) and torch.equal(vc.cpu()[:, mask], vc0[:, mask])
+    assert_close_bf16(out[sel.to(DEV)].reshape(len(sel), Nq, D), ref, f"attn_decode_fused step={step} S={S} B={Bb}", rtol=2e-2,
+                      abs_floor_frac=1.5e-2)
+    # and against the three-kernel path on the device, all agents
+    kc2, vc2 = kc0.clone().to(DEV), vc0.clone().to(DEV)
+    xn_d = ops.rmsnorm_fwd(x.to(DEV), scale.to(DEV))
+    q_d, _, _ = ops.qkv_rope(xn_d, w.to(DEV), pos, _rope_timescale(D).to(DEV), Nq, Nkv, D, k=kc2, v=vc2,
+                             k_row_stride=S * Nkv * D, v_row_stride=S * Nkv * D, cache_S=S)
+    out2 = ops.attn_decode(q_d, kc2, vc2, pos, Nq, Nkv, D)
+    torch.cuda.synchronize()
+    assert_close_bf16(out, out2.cpu(), "attn_decode_fused vs rmsnorm + qkv_rope + attn_decode", rtol=2e-2, abs_floor_frac=1.5e-2,
+                      allow_frac=1e-3, max_err_frac=0.1)
+
+
 def test_attn_decode_full_batch(ops):
     """Full-size shape (B=4096, S=512): persistent-warp striding covers every agent; bit-for-bit vs the SIMT kernel."""
     from jaxrl_b200._lib import lib
