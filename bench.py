@@ -184,40 +184,54 @@ def count_launches(trainer) -> int:
 
 
 def decode_attention_roofline(trainer, peaks):
-    """Dominant HBM-bound kernel: rollout decode attention.  Times the T launches of one rollout (positions
-    0..T-1, alternating layers so the 268 MB caches never sit in L2) back to back with CUDA events on the
-    launching stream; achieved = algorithmic KV bytes per launch / average launch duration."""
+    """Dominant HBM-bound kernel: rollout decode attention (with the q/k/v projection folded in front where the
+    shape allows).  Times the T launches of one rollout (positions 0..T-1, alternating layers so the 268 MB caches
+    never sit in L2) back to back with CUDA events on the launching stream; achieved = algorithmic bytes per launch /
+    average launch duration."""
     import torch
     from jaxrl_b200 import ops
     eng, r = trainer.engine, trainer.r
     ws = trainer.dws if trainer.n_chains == 1 else trainer.dws_chain[0]   # the launch shape the rollout really uses
     T, B, L = trainer.T, ws.B, eng.L
+    fused = eng.fused_attn_decode
+    x = torch.randn(B, eng.H, device=ws.ao.device).to(torch.bfloat16)
+
+    def launch(t, i):
+        if fused:
+            pre = f"layers.{i}."
+            ops.attn_decode_fused(x, eng.p[pre + "history_norm.scale"], eng.w[pre + "wt_qkv"], r.pos[t][:B], eng.timescale,
+                                  ws.kcache[i], ws.vcache[i], eng.Nq, eng.Nkv, eng.D, out=ws.ao)
+        else:
+            ops.attn_decode(ws.q, ws.kcache[i], ws.vcache[i], r.pos[t][:B], eng.Nq, eng.Nkv, eng.D, out=ws.ao)
+
     for t in range(0, T, 64):
-        ops.attn_decode(ws.q, ws.kcache[0], ws.vcache[0], r.pos[t][:B], eng.Nq, eng.Nkv, eng.D, out=ws.ao)
+        launch(t, 0)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for t in range(T):
-        i = t % L
-        ops.attn_decode(ws.q, ws.kcache[i], ws.vcache[i], r.pos[t][:B], eng.Nq, eng.Nkv, eng.D, out=ws.ao)
+        launch(t, t % L)
     e1.record()
     torch.cuda.synchronize()
     avg_s = e0.elapsed_time(e1) * 1e-3 / T
-    # SURVEY 8(d): per agent-step per layer (T+1)/2 * Nkv*D*2*2 bytes of KV read (+ the q/out rows)
+    # SURVEY 8(d): per agent-step per layer (T+1)/2 * Nkv*D*2*2 bytes of KV read + the rows in and out: q and out
+    # (unfused) or x, out and the new k,v ring rows (fused; the 48 KB of projection weights per CTA come from L2)
     kv_bytes = (T + 1) / 2 * eng.Nkv * eng.D * 2 * 2
-    io_bytes = 2 * eng.Nq * eng.D * 2
+    io_bytes = (eng.H * 2 + eng.Nq * eng.D * 2 + 2 * eng.Nkv * eng.D * 2) if fused else 2 * eng.Nq * eng.D * 2
     per_launch = B * (kv_bytes + io_bytes)
     achieved = per_launch / avg_s / 1e9
     peak = peaks.get("hbm_gbs", 6650.0)
     # DRAM traffic per launch: ncu measured (read + write) / algorithmic bytes for this kernel at one position
-    # (profiles/r01_attn_decode_traffic.json); scaled to the average launch of the rollout, like `achieved`.
+    # (profiles/r01_attn_decode*_traffic.json); scaled to the average launch of the rollout, like `achieved`.
     traffic = None
+    name = "attn_decode_fused_kernel" if fused else "attn_decode_online_kernel"
+    tfile = "r01_attn_decode_fused_traffic.json" if fused else "r01_attn_decode_traffic.json"
     try:
-        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_attn_decode_traffic.json")))
+        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", tfile)))
         traffic = tj["ratio"] * per_launch
     except Exception:
         pass
-    return {"kernel": "attn_decode_online_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    return {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": traffic, "avg_launch_us": avg_s * 1e6,
             "algorithmic_bytes_per_launch": per_launch, "agents_per_launch": B,
             "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"}

@@ -105,10 +105,10 @@ __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedP
     ts0 = p.timescale[8 * jp + 2 * t];
     ts1 = p.timescale[8 * jp + 2 * t + 1];
   }
+  const int pos0 = p.pos[0];                     // positions are step inputs, never produced by the preceding kernel
   griddep_launch();
   griddep_wait();                                // x and the rings are written by the previous kernels
 
-  const int pos0 = p.pos[0];
   const int kv_len = min(pos0 + 1, p.S);
   const int nchunks = (kv_len + AF_CHUNK - 1) / AF_CHUNK;
   int slot = pos0 % p.S;
@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedP
     const bool active = b < p.B;
     const __nv_bfloat16* kbase = p.kcache + (size_t)(active ? b : 0) * p.S * 32;
     const __nv_bfloat16* vbase = p.vcache + (size_t)(active ? b : 0) * p.S * 32;
+    float rsn[2][2], rcs[2][2];
     auto issue = [&](int c) {
       if (active && c < nchunks) {
         const uint32_t st = ring + (c % AF_STAGES) * AF_STAGE_BYTES;
@@ -147,11 +148,22 @@ __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedP
     for (int i = 0; i < AF_STAGES - 1; ++i) issue(i);
     // every warp has left the previous round's loop: stage 3 of rings 0-2 is free for the scratch rows
     if (round > 0) __syncthreads();
-    // ---- 2. RMSNorm of this agent's row -> xs[warp]
+    // ---- 2. RMSNorm of this agent's row -> xs[warp]; the rotation angles of the projection rows this lane will
+    //         finish (agents g, g + 8) are computed while the row is in flight
     {
+      uint2 xv = make_uint2(0u, 0u);
+      if (active) xv = *reinterpret_cast<const uint2*>(p.x + (size_t)b * 128 + 4 * lane);
+      if (warp < 10) {
+#pragma unroll
+        for (int rs = 0; rs < 2; ++rs) {
+          const int ab = cta_b0 + g + 8 * rs;
+          const float pf = (float)p.pos[ab < p.B ? ab : 0];
+          sincosf(pf / ts0, &rsn[rs][0], &rcs[rs][0]);
+          sincosf(pf / ts1, &rsn[rs][1], &rcs[rs][1]);
+        }
+      }
       uint32_t y0 = 0u, y1 = 0u;
       if (active) {
-        const uint2 xv = *reinterpret_cast<const uint2*>(p.x + (size_t)b * 128 + 4 * lane);
         const float x0 = bf16_lo(xv.x), x1 = bf16_hi(xv.x), x2 = bf16_lo(xv.y), x3 = bf16_hi(xv.y);
         const float ss = warp_sum(x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3);
         const float inv = rsqrtf(ss * (1.0f / 128.0f) + p.eps);
@@ -188,10 +200,7 @@ __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedP
           bf16_round2(lo0, lo1);                          // the projection output is bf16 (attention.py:100-107)
           bf16_round2(hi0, hi1);
           if (he < 5) {                                   // RoPE on q and k: (d, d + 16) pairs
-            const float pf = (float)p.pos[ab];
-            float s0, c0, s1, c1;
-            sincosf(pf / ts0, &s0, &c0);
-            sincosf(pf / ts1, &s1, &c1);
+            const float s0 = rsn[rs][0], c0 = rcs[rs][0], s1 = rsn[rs][1], c1 = rcs[rs][1];
             const float a0 = lo0 * c0 - hi0 * s0, b0 = hi0 * c0 + lo0 * s0;
             const float a1 = lo1 * c1 - hi1 * s1, b1 = hi1 * c1 + lo1 * s1;
             lo0 = a0; hi0 = b0; lo1 = a1; hi1 = b1;
