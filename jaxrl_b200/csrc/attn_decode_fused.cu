@@ -119,13 +119,31 @@ __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedP
   const int per_round = gridDim.x * warps;
   const int nrounds = (p.B + per_round - 1) / per_round;
 
+  // this warp's input row and the rotation angles of the projection rows it finishes (agents g, g + 8 of the CTA), for
+  // the round about to start: fetched one round ahead so that their latency hides behind the previous round's stream
+  uint2 xv = make_uint2(0u, 0u);
+  float rsn[2][2], rcs[2][2];
+  auto fetch_round = [&](int round) {
+    const int b0 = round * per_round + blockIdx.x * warps;
+    if (round < nrounds && b0 + warp < p.B) xv = *reinterpret_cast<const uint2*>(p.x + (size_t)(b0 + warp) * 128 + 4 * lane);
+    if (round < nrounds && warp < 10) {
+#pragma unroll
+      for (int rs = 0; rs < 2; ++rs) {
+        const int ab = b0 + g + 8 * rs;
+        const float pf = (float)p.pos[ab < p.B ? ab : 0];
+        sincosf(pf / ts0, &rsn[rs][0], &rcs[rs][0]);
+        sincosf(pf / ts1, &rsn[rs][1], &rcs[rs][1]);
+      }
+    }
+  };
+  fetch_round(0);
+
   for (int round = 0; round < nrounds; ++round) {
     const int cta_b0 = round * per_round + blockIdx.x * warps;      // first agent of this CTA in this round
     const int b = cta_b0 + warp;
     const bool active = b < p.B;
     const __nv_bfloat16* kbase = p.kcache + (size_t)(active ? b : 0) * p.S * 32;
     const __nv_bfloat16* vbase = p.vcache + (size_t)(active ? b : 0) * p.S * 32;
-    float rsn[2][2], rcs[2][2];
     auto issue = [&](int c) {
       if (active && c < nchunks) {
         const uint32_t st = ring + (c % AF_STAGES) * AF_STAGE_BYTES;
@@ -148,20 +166,8 @@ __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedP
     for (int i = 0; i < AF_STAGES - 1; ++i) issue(i);
     // every warp has left the previous round's loop: stage 3 of rings 0-2 is free for the scratch rows
     if (round > 0) __syncthreads();
-    // ---- 2. RMSNorm of this agent's row -> xs[warp]; the rotation angles of the projection rows this lane will
-    //         finish (agents g, g + 8) are computed while the row is in flight
+    // ---- 2. RMSNorm of this agent's row -> xs[warp] (the row and the rotation angles were fetched a round ahead)
     {
-      uint2 xv = make_uint2(0u, 0u);
-      if (active) xv = *reinterpret_cast<const uint2*>(p.x + (size_t)b * 128 + 4 * lane);
-      if (warp < 10) {
-#pragma unroll
-        for (int rs = 0; rs < 2; ++rs) {
-          const int ab = cta_b0 + g + 8 * rs;
-          const float pf = (float)p.pos[ab < p.B ? ab : 0];
-          sincosf(pf / ts0, &rsn[rs][0], &rcs[rs][0]);
-          sincosf(pf / ts1, &rsn[rs][1], &rcs[rs][1]);
-        }
-      }
       uint32_t y0 = 0u, y1 = 0u;
       if (active) {
         const float x0 = bf16_lo(xv.x), x1 = bf16_hi(xv.x), x2 = bf16_lo(xv.y), x3 = bf16_hi(xv.y);
@@ -232,6 +238,7 @@ __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedP
     }
     if (lane < 8) kvnew = lds_v4(kvs + warp * 128 + lane * 16);
     __syncthreads();                                       // scratch rows are dead: stage 3 may be refilled
+    fetch_round(round + 1);
 
     if (active) {
       float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;       // heads 2t, 2t+1 (log2 domain)

@@ -124,6 +124,69 @@ __global__ void __launch_bounds__(HLG_WARPS * 32) hlgauss_loss_kernel(
   }
 }
 
+// NL < 64: lane l owns bins 2l and 2l+1 (bin edges 2l, 2l+1 and, from lane l+1, 2l+2) - no shared memory, half the
+// instructions of the generic kernel above for the reference's 51 bins.
+__global__ void __launch_bounds__(HLG_WARPS * 32) hlgauss_loss2_kernel(
+    const float* __restrict__ logits, const float* __restrict__ targets, long long n, int NL,
+    const float* __restrict__ supports, float vmin, float vmax, float sigma, float gscale,
+    float* __restrict__ dlogits, __nv_bfloat16* __restrict__ dl_bf16, int ld_bf16, double* __restrict__ partials) {
+  __shared__ double s_part[HLG_WARPS];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  long long row = (long long)blockIdx.x * HLG_WARPS + warp;
+  const long long stride = (long long)gridDim.x * HLG_WARPS;
+  const int j0 = 2 * lane, j1 = 2 * lane + 1;
+  const float e0 = j0 <= NL ? supports[j0] : 0.f, e1 = j1 <= NL ? supports[j1] : 0.f;
+  const bool b0 = j0 < NL, b1 = j1 < NL;
+  double acc = 0.0;
+  for (; row < n; row += stride) {
+    const float* x = logits + row * NL;
+    const float v0 = b0 ? x[j0] : -INFINITY, v1 = b1 ? x[j1] : -INFINITY;
+    const float t = fminf(fmaxf(targets[row], vmin), vmax);
+    const float c0 = j0 <= NL ? ndtr_f32((e0 - t) / sigma) : 0.f;
+    const float c1 = j1 <= NL ? ndtr_f32((e1 - t) / sigma) : 0.f;
+    const float c2 = __shfl_down_sync(0xffffffffu, c0, 1);
+    const float cdf_lo = __shfl_sync(0xffffffffu, c0, 0);
+    const float cdf_hi = __shfl_sync(0xffffffffu, (NL & 1) ? c1 : c0, NL >> 1);
+    const float z = cdf_hi - cdf_lo;
+    const float p0 = b0 ? (c1 - c0) / z : 0.f, p1 = b1 ? (c2 - c1) / z : 0.f;
+    const float m = warp_max(fmaxf(v0, v1));
+    float s = (b0 ? expf(v0 - m) : 0.f) + (b1 ? expf(v1 - m) : 0.f);
+    float psum = p0 + p1;
+    s = warp_sum(s);
+    psum = warp_sum(psum);
+    const float lse = logf(s);
+    float l = 0.f;
+    if (b0) {
+      const float lsm = (v0 - m) - lse;
+      l -= p0 * lsm;
+      const float gr = gscale * (expf(lsm) * psum - p0);
+      if (dlogits) dlogits[row * NL + j0] = gr;
+      if (dl_bf16) dl_bf16[row * ld_bf16 + j0] = __float2bfloat16_rn(gr);
+    } else if (dl_bf16 && j0 < ld_bf16) {
+      dl_bf16[row * ld_bf16 + j0] = __float2bfloat16_rn(0.f);
+    }
+    if (b1) {
+      const float lsm = (v1 - m) - lse;
+      l -= p1 * lsm;
+      const float gr = gscale * (expf(lsm) * psum - p1);
+      if (dlogits) dlogits[row * NL + j1] = gr;
+      if (dl_bf16) dl_bf16[row * ld_bf16 + j1] = __float2bfloat16_rn(gr);
+    } else if (dl_bf16 && j1 < ld_bf16) {
+      dl_bf16[row * ld_bf16 + j1] = __float2bfloat16_rn(0.f);
+    }
+    l = warp_sum(l);
+    acc += (double)l;
+  }
+  if (lane == 0) s_part[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int w = 0; w < HLG_WARPS; ++w) a += s_part[w];
+    partials[blockIdx.x] = a;
+  }
+}
+
 __global__ void hlgauss_loss_finalize_kernel(const double* __restrict__ partials, int nparts, double inv_n,
                                              float* __restrict__ loss) {
   __shared__ double s[256];
@@ -172,9 +235,14 @@ extern "C" int mpx_hlgauss_loss(const float* logits, const float* targets, long 
   MPX_REQUIRE(loss && workspace, "mpx_hlgauss_loss: null pointer");
   const int grid = hlg_grid(n);
   double* partials = reinterpret_cast<double*>(workspace);
-  hlgauss_loss_kernel<<<grid, HLG_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      logits, targets, n, n_logits, supports, vmin, vmax, sigma, grad_scale / (float)n, dlogits,
-      reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), ld_bf16, partials);
+  if (n_logits < 64 && ld_bf16 <= 64)      // bin edge NL must live in lane NL >> 1 < 32
+    hlgauss_loss2_kernel<<<grid, HLG_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        logits, targets, n, n_logits, supports, vmin, vmax, sigma, grad_scale / (float)n, dlogits,
+        reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), ld_bf16, partials);
+  else
+    hlgauss_loss_kernel<<<grid, HLG_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        logits, targets, n, n_logits, supports, vmin, vmax, sigma, grad_scale / (float)n, dlogits,
+        reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), ld_bf16, partials);
   hlgauss_loss_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, grid, 1.0 / (double)n, loss);
   return check_launch("mpx_hlgauss_loss");
 }

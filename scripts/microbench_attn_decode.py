@@ -15,11 +15,27 @@ q = torch.randn(B, Nq * D, device=dev, generator=g).to(torch.bfloat16)
 caches = [(torch.randn(B, S, Nkv, D, device=dev, generator=g).to(torch.bfloat16),
            torch.randn(B, S, Nkv, D, device=dev, generator=g).to(torch.bfloat16)) for _ in range(2)]
 out = torch.empty_like(q)
-print(" pos    us/launch   GB/s (algorithmic)")
+H = 128
+x = torch.randn(B, H, device=dev, generator=g).to(torch.bfloat16)
+nscale = torch.ones(H, device=dev)
+wt_qkv = (torch.randn((Nq + 2 * Nkv) * D, H, device=dev, generator=g) / H ** 0.5).to(torch.bfloat16)
+half = D // 2
+timescale = (10000.0 ** (torch.arange(half, dtype=torch.float32) * 2.0 / D)).to(dev)
+fused = "--fused" in sys.argv
+
+
+def launch(i, pos):
+    if fused:
+        ops.attn_decode_fused(x, nscale, wt_qkv, pos, timescale, caches[i & 1][0], caches[i & 1][1], Nq, Nkv, D, out=out)
+    else:
+        ops.attn_decode(q, caches[i & 1][0], caches[i & 1][1], pos, Nq, Nkv, D, out=out)
+
+
+print(("fused norm+qkv+rope+attention" if fused else "attention only") + ": pos    us/launch   GB/s (algorithmic)")
 for pos_v in (0, 15, 31, 63, 127, 191, 255, 319, 383, 447, 511):
     pos = torch.full((B,), pos_v, dtype=torch.int32, device=dev)
     for i in range(4):
-        ops.attn_decode(q, caches[i & 1][0], caches[i & 1][1], pos, Nq, Nkv, D, out=out)
+        launch(i, pos)
     torch.cuda.synchronize()
     n = 40
     gr = torch.cuda.CUDAGraph()
@@ -27,7 +43,7 @@ for pos_v in (0, 15, 31, 63, 127, 191, 255, 319, 383, 447, 511):
     with torch.cuda.stream(st):
         with torch.cuda.graph(gr, stream=st):
             for i in range(n):
-                ops.attn_decode(q, caches[i & 1][0], caches[i & 1][1], pos, Nq, Nkv, D, out=out)   # alternate caches: no L2 reuse
+                launch(i, pos)   # alternate caches: no L2 reuse
     torch.cuda.synchronize()
     gr.replay()
     torch.cuda.synchronize()

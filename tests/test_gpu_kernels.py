@@ -64,7 +64,8 @@ def test_gae_known_answers(ops):
 
 # ---------------------------------------------------------------------------------------------- HL-Gauss
 @pytest.mark.parametrize("n,NL,vmin,vmax,sigma", [(7, 51, -10.0, 10.0, 0.1038127), (5000, 51, -10.0, 10.0, 0.1038127),
-                                                  (300, 51, -5.0, 5.0, 0.75), (64, 10, -1.0, 1.0, 0.5)])
+                                                  (300, 51, -5.0, 5.0, 0.75), (64, 10, -1.0, 1.0, 0.5),
+                                                  (200, 100, -10.0, 10.0, 0.3), (33, 64, -2.0, 2.0, 0.2)])
 def test_hlgauss(ops, n, NL, vmin, vmax, sigma):
     gen = g(n + NL)
     logits = torch.randn(n, NL, generator=gen) * 2.0
