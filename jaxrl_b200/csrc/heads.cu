@@ -106,12 +106,18 @@ __global__ void embed_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const flo
 __global__ void __launch_bounds__(HD_WARPS * 32) policy_logits_kernel(
     const __nv_bfloat16* __restrict__ x, const float* __restrict__ table, const uint8_t* __restrict__ mask,
     float* __restrict__ logits, long long M, int H, int A) {
-  extern __shared__ float s_table[];   // [A][H]
-  for (int i = threadIdx.x; i < A * H; i += blockDim.x) s_table[i] = table[i];
+  // [A][8 lane slots][per + 4]: the 4-float pad puts the 8 lanes of a token group on disjoint banks for the 16-byte
+  // reads below (unpadded, per = 16 floats = 64 B makes slots 0,2,4,6 collide: 4-way conflicts on every read)
+  extern __shared__ float s_table[];
+  const int per = H / 8;                                               // features per lane (multiple of 8)
+  const int pstride = per + 4, astride = 8 * pstride;
+  for (int i = threadIdx.x; i < A * H; i += blockDim.x) {
+    const int a = i / H, h = i % H;
+    s_table[a * astride + (h / per) * pstride + (h % per)] = table[i];
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int sub = lane & 7, rsel = lane >> 3;
-  const int per = H / 8;                                               // features per lane (multiple of 8)
   long long row = ((long long)blockIdx.x * HD_WARPS + (threadIdx.x >> 5)) * 4 + rsel;
   const long long stride = (long long)gridDim.x * HD_WARPS * 4;
   for (long long base = row - rsel; base < M; base += stride) {
@@ -127,9 +133,12 @@ __global__ void __launch_bounds__(HD_WARPS * 32) policy_logits_kernel(
 #pragma unroll
         for (int a = 0; a < MAX_A; ++a) {
           if (a < A) {
-            const float* tr = s_table + a * H + sub * per + c;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) part[a] = fmaf(xf[e], tr[e], part[a]);
+            const float4* tr = reinterpret_cast<const float4*>(s_table + a * astride + sub * pstride + c);
+            const float4 t0 = tr[0], t1 = tr[1];
+            part[a] = fmaf(xf[0], t0.x, part[a]); part[a] = fmaf(xf[1], t0.y, part[a]);
+            part[a] = fmaf(xf[2], t0.z, part[a]); part[a] = fmaf(xf[3], t0.w, part[a]);
+            part[a] = fmaf(xf[4], t1.x, part[a]); part[a] = fmaf(xf[5], t1.y, part[a]);
+            part[a] = fmaf(xf[6], t1.z, part[a]); part[a] = fmaf(xf[7], t1.w, part[a]);
           }
         }
       }
@@ -221,12 +230,16 @@ __global__ void __launch_bounds__(HD_WARPS * 32) policy_head_sample_kernel(
   extern __shared__ float s_table[];   // [A][H]
   griddep_launch();
   griddep_wait();
-  for (int i = threadIdx.x; i < A * H; i += blockDim.x) s_table[i] = table[i];
+  const int per = H / 8;
+  const int pstride = per + 4, astride = 8 * pstride;     // padded like policy_logits_kernel: conflict-free 16-byte reads
+  for (int i = threadIdx.x; i < A * H; i += blockDim.x) {
+    const int a = i / H, h = i % H;
+    s_table[a * astride + (h / per) * pstride + (h % per)] = table[i];
+  }
   __syncthreads();
   if (stream_off) stream_id += stream_off[0];
   const int lane = threadIdx.x & 31;
   const int sub = lane & 7, rsel = lane >> 3;
-  const int per = H / 8;
   const long long stride = (long long)gridDim.x * HD_WARPS * 4;
   for (long long base = ((long long)blockIdx.x * HD_WARPS + (threadIdx.x >> 5)) * 4; base < M; base += stride) {
     const long long row = base + rsel;
@@ -269,10 +282,15 @@ __global__ void __launch_bounds__(HD_WARPS * 32) policy_head_sample_kernel(
     for (int a = 0; a < MAX_A; ++a) {
       part[a] = 0.f;
       if (a < A) {
-        const float* tr = s_table + a * H + sub * per;
+        const float4* tr = reinterpret_cast<const float4*>(s_table + a * astride + sub * pstride);
 #pragma unroll
-        for (int c = 0; c < PH_MAX_PER; ++c)
-          if (c < per) part[a] = fmaf(xv[c], tr[c], part[a]);
+        for (int c = 0; c < PH_MAX_PER; c += 4) {
+          if (c < per) {
+            const float4 tv = tr[c >> 2];
+            part[a] = fmaf(xv[c], tv.x, part[a]); part[a] = fmaf(xv[c + 1], tv.y, part[a]);
+            part[a] = fmaf(xv[c + 2], tv.z, part[a]); part[a] = fmaf(xv[c + 3], tv.w, part[a]);
+          }
+        }
         part[a] += __shfl_xor_sync(0xffffffffu, part[a], 1);
         part[a] += __shfl_xor_sync(0xffffffffu, part[a], 2);
         part[a] += __shfl_xor_sync(0xffffffffu, part[a], 4);
@@ -444,14 +462,30 @@ __global__ void __launch_bounds__(HD_WARPS * 32) policy_head_bwd_kernel(
     for (int j = 0; j < HPL; ++j) dt[a][j] = 0.f;
   long long row = (long long)blockIdx.x * HD_WARPS + (threadIdx.x >> 5);
   const long long stride = (long long)gridDim.x * HD_WARPS;
+  // the next row's operands are fetched while the current row is multiplied (the loop is otherwise a chain of
+  // dependent global loads: one row of latency per iteration)
+  float xn[HPL], on[HPL], dn = 0.f;
+  auto fetch = [&](long long r) {
+    if (r < M) {
+#pragma unroll
+      for (int j = 0; j < HPL; ++j) {
+        xn[j] = __bfloat162float(x[r * H + j * 32 + lane]);
+        on[j] = dx_other ? __bfloat162float(dx_other[r * H + j * 32 + lane]) : 0.f;
+      }
+      dn = lane < A ? dlogits[r * A + lane] : 0.f;
+    }
+  };
+  fetch(row);
   for (; row < M; row += stride) {
-    float xv[HPL], acc[HPL];
+    float xv[HPL], ov[HPL], acc[HPL];
 #pragma unroll
     for (int j = 0; j < HPL; ++j) {
-      xv[j] = __bfloat162float(x[row * H + j * 32 + lane]);
+      xv[j] = xn[j];
+      ov[j] = on[j];
       acc[j] = 0.f;
     }
-    const float dl_mine = lane < A ? dlogits[row * A + lane] : 0.f;
+    const float dl_mine = dn;
+    fetch(row + stride);
 #pragma unroll
     for (int a = 0; a < AMAX; ++a) {
       if (a < A) {
@@ -466,7 +500,7 @@ __global__ void __launch_bounds__(HD_WARPS * 32) policy_head_bwd_kernel(
 #pragma unroll
     for (int j = 0; j < HPL; ++j) {
       float o = bf16_round(acc[j]);
-      if (dx_other) o += __bfloat162float(dx_other[row * H + j * 32 + lane]);
+      if (dx_other) o += ov[j];
       dx[row * H + j * 32 + lane] = __float2bfloat16_rn(o);
     }
   }
@@ -525,7 +559,7 @@ extern "C" int mpx_policy_logits(const mpx_bf16* x, const float* table, const ui
   MPX_REQUIRE(x && table && logits && M > 0 && H > 0, "mpx_policy_logits: bad arguments");
   MPX_REQUIRE(A > 0 && A <= MAX_A, "mpx_policy_logits: A=%d not in [1,%d]", A, MAX_A);
   MPX_REQUIRE(H % 64 == 0, "mpx_policy_logits: H=%d must be a multiple of 64", H);
-  const size_t smem = (size_t)A * H * sizeof(float);
+  const size_t smem = (size_t)A * (H + 32) * sizeof(float);      // 4-float pad per lane slot
   MPX_REQUIRE(smem <= 48 * 1024, "mpx_policy_logits: table too large for shared memory");
   policy_logits_kernel<<<grid_for(M, HD_WARPS * 4, 8), HD_WARPS * 32, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), table, action_mask, logits, M, H, A);
@@ -608,7 +642,7 @@ extern "C" int mpx_policy_head_sample(const mpx_bf16* x, const float* norm_scale
   MPX_REQUIRE(A > 0 && A <= MAX_A, "mpx_policy_head_sample: A=%d not in [1,%d]", A, MAX_A);
   MPX_REQUIRE(H % 64 == 0 && H <= 8 * PH_MAX_PER, "mpx_policy_head_sample: H=%d must be a multiple of 64, <= %d", H,
               8 * PH_MAX_PER);
-  const size_t smem = (size_t)A * H * sizeof(float);
+  const size_t smem = (size_t)A * (H + 32) * sizeof(float);      // 4-float pad per lane slot
   MPX_REQUIRE(smem <= 48 * 1024, "mpx_policy_head_sample: table too large for shared memory");
   cudaError_t le = launch_ex(policy_head_sample_kernel, dim3(grid_for(M, HD_WARPS * 4, 8)), dim3(HD_WARPS * 32), smem,
                              (cudaStream_t)stream, 0, true, reinterpret_cast<const __nv_bfloat16*>(x), norm_scale, eps, table,
