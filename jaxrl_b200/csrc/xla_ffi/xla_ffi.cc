@@ -117,6 +117,48 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(MpxQkvRopeDecode, QkvRopeDecodeImpl,
                                   .Ret<ffi::Buffer<ffi::BF16>>(),
                               {xla::ffi::Traits::kCmdBufferCompatible});
 
+// ---------------------------------------------------------------------------------------------- attention half, one kernel
+// network.py:158-165 + attention.py:96-150 for one rollout step: history_norm, q/k/v, RoPE, ring write, attention.
+// x is the un-normalised residual stream; the caches are aliased in -> out as above.
+static ffi::Error AttnBlockDecodeImpl(mpx_stream_t stream, ffi::Buffer<ffi::BF16> x, ffi::Buffer<ffi::F32> norm_scale,
+                                      ffi::Buffer<ffi::BF16> wt_qkv, ffi::Buffer<ffi::S32> seq_pos,
+                                      ffi::Buffer<ffi::F32> timescale, ffi::Buffer<ffi::BF16> kcache_in,
+                                      ffi::Buffer<ffi::BF16> vcache_in, int32_t num_heads, float eps,
+                                      ffi::ResultBuffer<ffi::BF16> out, ffi::ResultBuffer<ffi::BF16> kcache,
+                                      ffi::ResultBuffer<ffi::BF16> vcache) {
+  (void)kcache_in; (void)vcache_in;
+  const auto kd = kcache->dimensions();
+  const auto xd = x.dimensions();
+  mpx_attn_decode_fused_args a{};
+  a.x = reinterpret_cast<const mpx_bf16*>(x.untyped_data());
+  a.norm_scale = norm_scale.typed_data(); a.eps = eps;
+  a.wt_qkv = reinterpret_cast<const mpx_bf16*>(wt_qkv.untyped_data());
+  a.pos = seq_pos.typed_data(); a.rope_timescale = timescale.typed_data();
+  a.kcache = reinterpret_cast<mpx_bf16*>(kcache->untyped_data());
+  a.vcache = reinterpret_cast<mpx_bf16*>(vcache->untyped_data());
+  a.out = reinterpret_cast<mpx_bf16*>(out->untyped_data());
+  a.B = static_cast<int>(kd[0]); a.S = static_cast<int>(kd[1]); a.Nkv = static_cast<int>(kd[2]);
+  a.D = static_cast<int>(kd[3]); a.Nq = num_heads; a.H = static_cast<int>(xd[xd.size() - 1]);
+  if (mpx_attn_decode_fused(&a, stream)) return Fail("mpx_attn_decode_fused");
+  return ffi::Error::Success();
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(MpxAttnBlockDecode, AttnBlockDecodeImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<Stream>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Attr<int32_t>("num_heads")
+                                  .Attr<float>("eps")
+                                  .Ret<ffi::Buffer<ffi::BF16>>()
+                                  .Ret<ffi::Buffer<ffi::BF16>>()
+                                  .Ret<ffi::Buffer<ffi::BF16>>(),
+                              {xla::ffi::Traits::kCmdBufferCompatible});
+
 // ---------------------------------------------------------------------------------------------- HL-Gauss
 static ffi::Error HlGaussValueImpl(mpx_stream_t stream, ffi::Buffer<ffi::F32> logits, ffi::Buffer<ffi::F32> centers,
                                    ffi::ResultBuffer<ffi::F32> value) {
