@@ -77,7 +77,9 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
   float* sSq = reinterpret_cast<float*>(x_full + 18);   // 2 x 128 partial sums of squares (RMSNorm prologue)
   float* sScale = sSq + 256;                            // norm scale (128)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // shfl from a constant lane makes the warp index provably warp-uniform for the compiler: the role branches below and
+  // everything computed inside them can live on the uniform datapath (UTCHMMA takes uniform-register descriptors)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int ncta = (int)cluster_nctarank(), krank = (int)cluster_ctarank();
   const int nstages = (ncta == 1 && !p.proj) ? GF_MAX_STAGES : GF_STAGES;
   const int nchunks = p.F / 64 / ncta;        // chunks of the hidden dimension owned by this CTA
@@ -124,7 +126,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
   if (ncta > 1) cluster_sync_all();            // remote CTAs' barriers are initialised before anyone arrives on them
   tc_fence_after();
   dbg_stamp(dbg, 1);
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t tUG[2] = {tmem_base, tmem_base + 128};
   const uint32_t tD = tmem_base + 256;
 
@@ -163,7 +165,9 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    // The whole warp runs the control flow (waits, ring cursors, descriptor arithmetic stay warp-uniform); one elected
+    // lane issues each tcgen05.mma / commit.
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
       int stage = 0;
       uint32_t wphase = 0, xphase = 0, dphase = 0;
@@ -179,13 +183,13 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
           const uint32_t sb = smem_u32(sW + stage * GF_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tUG[b], umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024),
+            umma_bf16_1(tUG[b], umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024),
                       idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&w_empty[stage]);
+          umma_commit_1(&w_empty[stage]);
           if (++stage == nstages) { stage = 0; wphase ^= 1; }
         }
-        umma_commit(&ug_full[b]);
-        if (last) umma_commit(x_empty);
+        umma_commit_1(&ug_full[b]);
+        if (last) umma_commit_1(x_empty);
         ug_ph[b] ^= 1;
       };
       auto mma2 = [&](int c, bool last) {     // acc_d += h_c . Wd_c^T
@@ -198,13 +202,14 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         const uint32_t sb = smem_u32(sW + stage * GF_STAGE_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tD, umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024), idesc,
+          umma_bf16_1(tD, umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024), idesc,
                     (c | k) != 0 ? 1u : 0u);
-        umma_commit(&w_empty[stage]);
+        umma_commit_1(&w_empty[stage]);
         if (++stage == nstages) { stage = 0; wphase ^= 1; }
-        umma_commit(&h_empty[b]);
-        if (last) umma_commit(d_full);
+        umma_commit_1(&h_empty[b]);
+        if (last) umma_commit_1(d_full);
       };
+      unsigned long long* mdbg = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) ? p.dbg : nullptr;   // MMA-thread stamps: slots 32..63
       for (int tile = blockIdx.y; tile < m_tiles; tile += gridDim.y) {
         if (p.proj) {
           // x1 accumulator = ao . Wo^T in the tD columns (free: the previous tile's output has been drained)
@@ -218,12 +223,12 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
             const uint32_t sb = smem_u32(sW + stage * GF_STAGE_BYTES);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(tD, umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024),
+              umma_bf16_1(tD, umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024),
                         idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit(&w_empty[stage]);
+            umma_commit_1(&w_empty[stage]);
             if (++stage == nstages) { stage = 0; wphase ^= 1; }
           }
-          umma_commit(d0_full);
+          umma_commit_1(d0_full);
         }
         mbar_wait(xn_ready, xphase);
         xphase ^= 1;
@@ -232,8 +237,11 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         tc_fence_after();
         mma1(0, nchunks == 1);
         for (int c = 0; c < nchunks; ++c) {
+          if (c < 8) dbg_stamp(mdbg, 32 + 3 * c);             // about to issue MMA1(c+1)
           if (c + 1 < nchunks) mma1(c + 1, c + 2 == nchunks);
+          if (c < 8) dbg_stamp(mdbg, 33 + 3 * c);             // MMA1(c+1) issued; waiting for h(c)
           mma2(c, c + 1 == nchunks);
+          if (c < 8) dbg_stamp(mdbg, 34 + 3 * c);             // MMA2(c) issued
         }
       }
     }

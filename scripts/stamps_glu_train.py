@@ -45,6 +45,10 @@ lab = {0: "start", 1: "setup done", 2: "x tile landed", 3: "xn ready", 20: "D re
 for c in range(8):
     lab[4 + 2 * c] = f"ug{c} ready"
     lab[5 + 2 * c] = f"h{c} written"
+for c in range(8):
+    lab[32 + 3 * c] = f"[mma thread] before MMA1({c + 1})"
+    lab[33 + 3 * c] = f"[mma thread] MMA1({c + 1}) issued"
+    lab[34 + 3 * c] = f"[mma thread] h{c} seen, MMA2({c}) issued"
 timeline("glu_fused fwd M=131072 (last tile of CTA 0)", lambda: ops.glu_fused(xn, wt_ug64, wt_d, xn, out, F, h_out=h), lab)
 lab = {0: "start", 1: "setup done", 30: "chunks done", 31: "dxn ready", 32: "dxn stored"}
 for c in range(8):
