@@ -17,15 +17,19 @@
 // Weights stream from L2 through two rings: Wug_c lives until MMA3(c) (3 x 32 KB, so that the load of chunk c+2
 // starts one whole chunk before it is needed), Wdown_c only until MMA2(c) (2 x 16 KB).
 //
-// Roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, warps 2-9 activation warps (two per TMEM
-// lane quarter; thread = row, each warp 32 of the chunk's 64 hidden columns).  H must be 128, F % 64 == 0.
+// Roles (352 threads): warp 0 TMA producer, warp 1 issues MMA1/MMA2 (and owns TMEM), warp 10 issues MMA3, warps 2-9
+// are the activation warps (two per TMEM lane quarter; thread = row, each warp 32 of the chunk's 64 hidden columns).
+// Two issuing warps because one thread's program order would chain MMA1/MMA2 of chunk c+1 behind "du|dg of chunk c-1
+// are written", although they only need the TMEM buffer that chunk c-1's activation warps drained at their START.
+// Both issuers run warp-uniform control flow with one elected lane per tcgen05 instruction, so descriptor arithmetic
+// stays on the uniform datapath.  H must be 128, F % 64 == 0.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tmap.h"
 
 namespace mpx {
 
-constexpr int GB_THREADS = 320;
+constexpr int GB_THREADS = 352;
 constexpr int GB_EPI_WARPS = 8;
 constexpr int GB_UG_STAGES = 3;
 constexpr int GB_UG_BYTES = 32768;  // Wug_c: K blocks 0 and 1, 16 KB each
@@ -63,7 +67,7 @@ glu_bwd_fused_kernel(const GluBwdParams p, const __grid_constant__ CUtensorMap t
   uint64_t* dx_empty = bars + 19;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int nchunks = p.F / 64;
   const int m_tiles = (p.M + 127) / 128;
 
@@ -101,7 +105,7 @@ glu_bwd_fused_kernel(const GluBwdParams p, const __grid_constant__ CUtensorMap t
   __syncthreads();
   tc_fence_after();
   dbg_stamp(dbg, 1);
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   auto tUG = [&](int b) { return tmem_base + 128u * b; };
   auto tDH = [&](int b) { return tmem_base + 256u + 64u * b; };
   const uint32_t tDX = tmem_base + 384;
@@ -133,63 +137,65 @@ glu_bwd_fused_kernel(const GluBwdParams p, const __grid_constant__ CUtensorMap t
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    if (lane == 0) {
+    // ================================ MMA1 / MMA2 issuer ================================
+    {
       constexpr uint32_t id_ug = umma_idesc_bf16(128, 128, 0, 0);   // K-major x K-major
       constexpr uint32_t id_dh = umma_idesc_bf16(128, 64, 0, 1);    // K-major x MN-major
-      constexpr uint32_t id_dx = umma_idesc_bf16(128, 128, 0, 1);   // K-major x MN-major
-      uint32_t xphase = 0, dxphase = 0, dug_ph = 0, acc_ph[2] = {0, 0};
-      uint32_t ugphase = 0, dphase = 0;
-      int us = 0, ds = 0, us3 = 0;            // ring cursors: Wug for MMA1, Wdown for MMA2, Wug for MMA3
-      auto mma12 = [&](int c, bool last) {
-        const int b = c & 1;
-        mbar_wait(&ug_full[us], ugphase);
-        mbar_wait(&wd_full[ds], dphase);
-        mbar_wait(&acc_empty[b], acc_ph[b] ^ 1);
-        acc_ph[b] ^= 1;
-        tc_fence_after();
-        const uint32_t w = smem_u32(sWug + us * GB_UG_BYTES);
-        const uint32_t wd = smem_u32(sWd + ds * GB_D_BYTES);
-        const uint32_t xa = smem_u32(sX), da = smem_u32(sDY);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)       // [u | g] = xn . Wug_c^T
-          umma_bf16(tUG(b), umma_smem_desc_sw128(xa + (k >> 2) * 16384 + 32 * (k & 3), 16, 1024),
-                    umma_smem_desc_sw128(w + (k >> 2) * 16384 + 32 * (k & 3), 16, 1024), id_ug, k != 0 ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)       // dh = dy . Wdown_c : B[n = feature, k = hidden] from the (hidden x feature) tile
-          umma_bf16(tDH(b), umma_smem_desc_sw128(da + (k >> 2) * 16384 + 32 * (k & 3), 16, 1024),
-                    umma_smem_desc_sw128(wd + 2048 * k, 8192, 1024), id_dh, k != 0 ? 1u : 0u);
-        umma_commit(&wd_empty[ds]);
-        umma_commit(&acc_full[b]);
-        if (last) umma_commit(x_empty);
-        if (++us == GB_UG_STAGES) { us = 0; ugphase ^= 1; }
-        if (++ds == 2) { ds = 0; dphase ^= 1; }
-      };
-      auto mma3 = [&](int c, bool last) {   // dxn += [du | dg] . Wug_c : B[n = hidden, k = feature]
-        mbar_wait(dug_full, dug_ph);
-        dug_ph ^= 1;
-        tc_fence_after();
-        const uint32_t w = smem_u32(sWug + us3 * GB_UG_BYTES);
-        const uint32_t a = smem_u32(sDUG);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tDX, umma_smem_desc_sw128(a + (k >> 2) * 16384 + 32 * (k & 3), 16, 1024),
-                    umma_smem_desc_sw128(w + 2048 * k, 16384, 1024), id_dx, (c | k) != 0 ? 1u : 0u);
-        umma_commit(&ug_empty[us3]);
-        umma_commit(dug_empty);
-        if (last) umma_commit(dx_full);
-        if (++us3 == GB_UG_STAGES) us3 = 0;
-      };
+      uint32_t xphase = 0, acc_ph0 = 0, acc_ph1 = 0, ugphase = 0, dphase = 0;
+      int us = 0, ds = 0;                     // ring cursors: Wug for MMA1, Wdown for MMA2
+      const uint32_t xa = smem_u32(sX), da = smem_u32(sDY);
       for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
         mbar_wait(x_full, xphase);
         xphase ^= 1;
+        for (int c = 0; c < nchunks; ++c) {
+          const int b = c & 1;
+          mbar_wait(&ug_full[us], ugphase);
+          mbar_wait(&wd_full[ds], dphase);
+          if (b) { mbar_wait(&acc_empty[1], acc_ph1 ^ 1); acc_ph1 ^= 1; }
+          else   { mbar_wait(&acc_empty[0], acc_ph0 ^ 1); acc_ph0 ^= 1; }
+          tc_fence_after();
+          const uint32_t w = smem_u32(sWug + us * GB_UG_BYTES);
+          const uint32_t wd = smem_u32(sWd + ds * GB_D_BYTES);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)       // [u | g] = xn . Wug_c^T
+            umma_bf16_1(tUG(b), umma_smem_desc_sw128(xa + (k >> 2) * 16384 + 32 * (k & 3), 16, 1024),
+                        umma_smem_desc_sw128(w + (k >> 2) * 16384 + 32 * (k & 3), 16, 1024), id_ug, k != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)       // dh = dy . Wdown_c : B[n = feature, k = hidden] from the (hidden x feature) tile
+            umma_bf16_1(tDH(b), umma_smem_desc_sw128(da + (k >> 2) * 16384 + 32 * (k & 3), 16, 1024),
+                        umma_smem_desc_sw128(wd + 2048 * k, 8192, 1024), id_dh, k != 0 ? 1u : 0u);
+          umma_commit_1(&wd_empty[ds]);
+          umma_commit_1(&acc_full[b]);
+          if (c + 1 == nchunks) umma_commit_1(x_empty);
+          if (++us == GB_UG_STAGES) { us = 0; ugphase ^= 1; }
+          if (++ds == 2) { ds = 0; dphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ================================ MMA3 issuer ================================
+    {
+      constexpr uint32_t id_dx = umma_idesc_bf16(128, 128, 0, 1);   // K-major x MN-major
+      uint32_t dxphase = 0, dug_ph = 0, ugphase = 0;
+      int us3 = 0;                            // ring cursor: Wug for MMA3
+      const uint32_t a = smem_u32(sDUG);
+      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
         mbar_wait(dx_empty, dxphase ^ 1);    // previous tile's dxn accumulator has been drained
         dxphase ^= 1;
-        tc_fence_after();
-        mma12(0, nchunks == 1);
-        for (int c = 0; c < nchunks; ++c) {
-          if (c + 1 < nchunks) mma12(c + 1, c + 2 == nchunks);
-          mma3(c, c + 1 == nchunks);
+        for (int c = 0; c < nchunks; ++c) {  // dxn += [du | dg] . Wug_c : B[n = hidden, k = feature]
+          mbar_wait(&ug_full[us3], ugphase); // (long since complete: MMA1 of this chunk read the same tile)
+          mbar_wait(dug_full, dug_ph);
+          dug_ph ^= 1;
+          tc_fence_after();
+          const uint32_t w = smem_u32(sWug + us3 * GB_UG_BYTES);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16_1(tDX, umma_smem_desc_sw128(a + (k >> 2) * 16384 + 32 * (k & 3), 16, 1024),
+                        umma_smem_desc_sw128(w + 2048 * k, 16384, 1024), id_dx, (c | k) != 0 ? 1u : 0u);
+          umma_commit_1(&ug_empty[us3]);
+          umma_commit_1(dug_empty);
+          if (c + 1 == nchunks) umma_commit_1(dx_full);
+          if (++us3 == GB_UG_STAGES) { us3 = 0; ugphase ^= 1; }
         }
       }
     }

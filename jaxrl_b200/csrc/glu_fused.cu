@@ -6,8 +6,10 @@
 // turn it into the bf16 h_c tile in shared memory (SW128 K-major, the A operand of MMA2), MMA2 accumulates
 // h_c @ Wdown_c^T into a second TMEM accumulator.  MMA1 of chunk c+1 overlaps the activation math of chunk c.
 //
-// Roles (320 threads): warp 0 TMA producer (x tile + weight ring), warp 1 MMA issuer / TMEM owner, warps 2-9
-// activation + output epilogue (two warps per TMEM lane quarter; thread = row, each warp half of the columns).
+// Roles (352 threads): warp 0 TMA producer (x tile + weight ring), warp 1 issues MMA1 (and owns TMEM), warp 10 issues
+// MMA2, warps 2-9 activation + output epilogue (two warps per TMEM lane quarter; thread = row, each warp half of the
+// columns).  Two issuing warps: in one thread's program order MMA1 of chunk c+1 would queue behind "h of chunk c-1 is
+// written", although it only needs the TMEM buffer that chunk c-1's activation warps drained at their start.
 // H (model width) must be 128; F % 64 == 0.
 //
 // Rollout batches are small (M = agents, 32 row tiles at 4096 agents), so one CTA per row tile would leave most
@@ -24,7 +26,7 @@ namespace mpx {
 constexpr int GF_STAGES = 4;        // weight ring depth of the cluster / projection variants
 constexpr int GF_MAX_STAGES = 10;   // single-CTA variant: the ring also takes the (then unused) partial and x1 regions
 constexpr int GF_STAGE_BYTES = 16384;   // [128 rows x 64 cols] bf16, SW128
-constexpr int GF_THREADS = 320;
+constexpr int GF_THREADS = 352;
 constexpr int GF_EPI_WARPS = 8;
 constexpr int GF_PART_BYTES = 65536;    // fp32 partial of the 128 x 128 output tile, [32 float4 columns][128 rows]
 
@@ -163,85 +165,89 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    // The whole warp runs the control flow (waits, ring cursors, descriptor arithmetic stay warp-uniform); one elected
-    // lane issues each tcgen05.mma / commit.
-    {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
-      int stage = 0;
-      uint32_t wphase = 0, xphase = 0, dphase = 0;
-      uint32_t ug_ph[2] = {0, 0}, h_ph[2] = {0, 0};
-      auto mma1 = [&](int c, bool last) {     // [u_c | g_c] = x . Wug_c^T
-        const int b = c & 1;
-        mbar_wait(&ug_empty[b], ug_ph[b] ^ 1);
-        tc_fence_after();
-        for (int kb = 0; kb < 2; ++kb) {
-          mbar_wait(&w_full[stage], wphase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(sX + kb * 16384);
-          const uint32_t sb = smem_u32(sW + stage * GF_STAGE_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_1(tUG[b], umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024),
-                      idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_1(&w_empty[stage]);
-          if (++stage == nstages) { stage = 0; wphase ^= 1; }
-        }
-        umma_commit_1(&ug_full[b]);
-        if (last) umma_commit_1(x_empty);
-        ug_ph[b] ^= 1;
-      };
-      auto mma2 = [&](int c, bool last) {     // acc_d += h_c . Wd_c^T
-        const int b = c & 1;
-        mbar_wait(&h_full[b], h_ph[b]);
-        h_ph[b] ^= 1;
-        mbar_wait(&w_full[stage], wphase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(sH + b * 16384);
-        const uint32_t sb = smem_u32(sW + stage * GF_STAGE_BYTES);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_1(tD, umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024), idesc,
-                    (c | k) != 0 ? 1u : 0u);
-        umma_commit_1(&w_empty[stage]);
-        if (++stage == nstages) { stage = 0; wphase ^= 1; }
-        umma_commit_1(&h_empty[b]);
-        if (last) umma_commit_1(d_full);
-      };
-      unsigned long long* mdbg = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) ? p.dbg : nullptr;   // MMA-thread stamps: slots 32..63
-      for (int tile = blockIdx.y; tile < m_tiles; tile += gridDim.y) {
+  } else if (warp == 1 || warp == 10) {
+    // ================================ MMA issuers ================================
+    // The whole warp runs the control flow (waits, ring positions, descriptor arithmetic stay warp-uniform); one elected
+    // lane issues each tcgen05.mma / commit.  Weight tiles are consumed in the producer's order: per tile
+    // [Wo a, Wo b], UG_0 a, b, then for each c: UG_{c+1} a, b (if any), D_c - both warps derive ring positions from that.
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+    const int P = p.proj ? 2 : 0;
+    const int per_tile = P + 3 * nchunks;
+    auto w_wait = [&](int n) -> uint32_t {    // wait for weight tile number n (running count) and return its address
+      const int st = n % nstages;
+      mbar_wait(&w_full[st], (uint32_t)(n / nstages) & 1u);
+      return smem_u32(sW + st * GF_STAGE_BYTES);
+    };
+    auto w_release = [&](int n) { umma_commit_1(&w_empty[n % nstages]); };
+    if (warp == 1) {
+      uint32_t xphase = 0, dphase = 0, ug_ph0 = 0, ug_ph1 = 0;
+      unsigned long long* mdbg = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) ? p.dbg : nullptr;   // slots 32..63
+      int base = 0;
+      for (int tile = blockIdx.y; tile < m_tiles; tile += gridDim.y, base += per_tile) {
         if (p.proj) {
           // x1 accumulator = ao . Wo^T in the tD columns (free: the previous tile's output has been drained)
           mbar_wait(x_full, xphase);
           mbar_wait(d_empty, dphase ^ 1);
           tc_fence_after();
           for (int kb = 0; kb < 2; ++kb) {
-            mbar_wait(&w_full[stage], wphase);
+            const uint32_t sb = w_wait(base + kb);
             tc_fence_after();
             const uint32_t sa = smem_u32(sX + kb * 16384);
-            const uint32_t sb = smem_u32(sW + stage * GF_STAGE_BYTES);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16_1(tD, umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024),
-                        idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit_1(&w_empty[stage]);
-            if (++stage == nstages) { stage = 0; wphase ^= 1; }
+                          idesc, (kb | k) != 0 ? 1u : 0u);
+            w_release(base + kb);
           }
           umma_commit_1(d0_full);
         }
+        dphase ^= 1;
         mbar_wait(xn_ready, xphase);
         xphase ^= 1;
-        if (!p.proj) mbar_wait(d_empty, dphase ^ 1);   // previous tile's output accumulator has been drained
-        dphase ^= 1;
         tc_fence_after();
-        mma1(0, nchunks == 1);
-        for (int c = 0; c < nchunks; ++c) {
-          if (c < 8) dbg_stamp(mdbg, 32 + 3 * c);             // about to issue MMA1(c+1)
-          if (c + 1 < nchunks) mma1(c + 1, c + 2 == nchunks);
-          if (c < 8) dbg_stamp(mdbg, 33 + 3 * c);             // MMA1(c+1) issued; waiting for h(c)
-          mma2(c, c + 1 == nchunks);
-          if (c < 8) dbg_stamp(mdbg, 34 + 3 * c);             // MMA2(c) issued
+        for (int c = 0; c < nchunks; ++c) {   // [u_c | g_c] = x . Wug_c^T
+          const int b = c & 1;
+          if (c < 8) dbg_stamp(mdbg, 32 + 2 * c);
+          if (b) { mbar_wait(&ug_empty[1], ug_ph1 ^ 1); ug_ph1 ^= 1; }
+          else   { mbar_wait(&ug_empty[0], ug_ph0 ^ 1); ug_ph0 ^= 1; }
+          tc_fence_after();
+          const int n0 = base + (c == 0 ? P : P + 3 * c - 1);
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint32_t sb = w_wait(n0 + kb);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(sX + kb * 16384);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_1(tUG[b], umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024),
+                          idesc, (kb | k) != 0 ? 1u : 0u);
+            w_release(n0 + kb);
+          }
+          umma_commit_1(&ug_full[b]);
+          if (c + 1 == nchunks) umma_commit_1(x_empty);
+          if (c < 8) dbg_stamp(mdbg, 33 + 2 * c);
+        }
+      }
+    } else {
+      uint32_t dphase = 0, h_ph0 = 0, h_ph1 = 0;
+      int base = 0;
+      for (int tile = blockIdx.y; tile < m_tiles; tile += gridDim.y, base += per_tile) {
+        mbar_wait(d_empty, dphase ^ 1);       // previous tile's output accumulator has been drained
+        dphase ^= 1;
+        for (int c = 0; c < nchunks; ++c) {   // acc_d += h_c . Wd_c^T
+          const int b = c & 1;
+          if (b) { mbar_wait(&h_full[1], h_ph1); h_ph1 ^= 1; }
+          else   { mbar_wait(&h_full[0], h_ph0); h_ph0 ^= 1; }
+          const int n = base + (c + 1 < nchunks ? P + 4 + 3 * c : P + 2 + 3 * c);
+          const uint32_t sb = w_wait(n);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(sH + b * 16384);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_1(tD, umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024), idesc,
+                        (c | k) != 0 ? 1u : 0u);
+          w_release(n);
+          umma_commit_1(&h_empty[b]);
+          if (c + 1 == nchunks) umma_commit_1(d_full);
         }
       }
     }
