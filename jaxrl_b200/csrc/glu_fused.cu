@@ -354,27 +354,33 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
       __syncwarp();
       dbg_stamp(dbg, 3);
       if (lane == 0) mbar_arrive(xn_ready);
-      for (int c = 0; c < nchunks; ++c) {
-        const int b = c & 1;
-        mbar_wait(&ug_full[b], ug_ph[b]);
-        ug_ph[b] ^= 1;
-        tc_fence_after();
-        if (c < 8) dbg_stamp(dbg, 4 + 2 * c);
-        uint32_t u[32], g[32];
-        tmem_ld_32x32(tUG[b] + lane_off + 32 * half, u);
-        tmem_ld_32x32(tUG[b] + lane_off + 64 + 32 * half, g);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ug_empty[b]);
-        uint32_t hw[16];                                       // 32 bf16 = this warp's half of the row's h chunk
+      // Half-chunk software pipeline: while the 16 columns in registers are turned into h, the TMEM load of the next
+      // 16 (second half of this chunk, or first half of the next chunk) is in flight - TMEM reads (64 B/clk per SM) and
+      // the activation math of a warp overlap instead of alternating.
+      uint32_t uA[16], gA[16], uB[16], gB[16];
+      auto act16 = [&](const uint32_t (&u)[16], const uint32_t (&g)[16], uint32_t (&hw)[8]) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
           const uint32_t uw = pack_bf16(__uint_as_float(u[2 * i]), __uint_as_float(u[2 * i + 1]));
           const uint32_t gw = pack_bf16(__uint_as_float(g[2 * i]), __uint_as_float(g[2 * i + 1]));
           const uint32_t aw = pack_bf16(gelu_tanh(bf16_lo(uw)), gelu_tanh(bf16_hi(uw)));
           hw[i] = pack_bf16(bf16_lo(aw) * bf16_lo(gw), bf16_hi(aw) * bf16_hi(gw));
         }
+      };
+      mbar_wait(&ug_full[0], ug_ph[0]);
+      ug_ph[0] ^= 1;
+      tc_fence_after();
+      tmem_ld_32x16(tUG[0] + lane_off + 32 * half, uA);
+      tmem_ld_32x16(tUG[0] + lane_off + 64 + 32 * half, gA);
+      tmem_ld_wait16(uA);
+      tmem_ld_wait16(gA);
+      for (int c = 0; c < nchunks; ++c) {
+        const int b = c & 1;
+        if (c < 8) dbg_stamp(dbg, 4 + 2 * c);
+        tmem_ld_32x16(tUG[b] + lane_off + 32 * half + 16, uB);
+        tmem_ld_32x16(tUG[b] + lane_off + 64 + 32 * half + 16, gB);
+        uint32_t hw[8];
+        act16(uA, gA, hw);
         mbar_wait(&h_empty[b], h_ph[b] ^ 1);                   // MMA2 of chunk c-2 no longer reads this buffer
         h_ph[b] ^= 1;
         if (p.h_out) {                                         // ... and neither does its bulk store
@@ -382,11 +388,23 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
           gf_bar_sync(2 + quarter, 64);
         }
         const uint32_t hrow = smem_u32(sH + b * 16384 + r * 128);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int pc = 4 * half + i;
-          sts_v4(hrow + ((pc ^ (r & 7)) << 4), make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]));
+        sts_v4(hrow + (((4 * half) ^ (r & 7)) << 4), make_uint4(hw[0], hw[1], hw[2], hw[3]));
+        sts_v4(hrow + (((4 * half + 1) ^ (r & 7)) << 4), make_uint4(hw[4], hw[5], hw[6], hw[7]));
+        tmem_ld_wait16(uB);
+        tmem_ld_wait16(gB);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ug_empty[b]);              // both halves of chunk c are in registers
+        if (c + 1 < nchunks) {
+          mbar_wait(&ug_full[b ^ 1], ug_ph[b ^ 1]);
+          ug_ph[b ^ 1] ^= 1;
+          tc_fence_after();
+          tmem_ld_32x16(tUG[b ^ 1] + lane_off + 32 * half, uA);
+          tmem_ld_32x16(tUG[b ^ 1] + lane_off + 64 + 32 * half, gA);
         }
+        act16(uB, gB, hw);
+        sts_v4(hrow + (((4 * half + 2) ^ (r & 7)) << 4), make_uint4(hw[0], hw[1], hw[2], hw[3]));
+        sts_v4(hrow + (((4 * half + 3) ^ (r & 7)) << 4), make_uint4(hw[4], hw[5], hw[6], hw[7]));
         fence_proxy_async_smem();
         __syncwarp();
         if (c < 8) dbg_stamp(dbg, 5 + 2 * c);
@@ -397,6 +415,10 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
             tma_store_2d(&tm_h, sH + b * 16384 + quarter * 4096, (chunk0 + c) * 64, tile * 128 + quarter * 32);
             bulk_commit_group();
           }
+        }
+        if (c + 1 < nchunks) {
+          tmem_ld_wait16(uA);
+          tmem_ld_wait16(gA);
         }
       }
       uint4 rpre[8];                                           // single CTA: this thread's 64 residual columns, in flight
