@@ -69,7 +69,7 @@ attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap 
   uint64_t* dq_empty = bars + 9;             // dQ accumulator read (4 warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int nt = p.T / BT;
   const int kt = (int)blockIdx.x;             // key tile; tile 0 has the most work (all query tiles see it)
   const int b = blockIdx.y;
@@ -98,7 +98,7 @@ attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 288, tDQ = tmem_base + 320;
 
   if (warp == BWD_SM_WARPS) {
@@ -117,7 +117,10 @@ attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap 
     }
   } else if (warp == BWD_SM_WARPS + 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    // warp-uniform control flow, one elected lane per tcgen05 instruction: waits, descriptor arithmetic and loop state
+    // stay on the uniform datapath (a single divergent lane pays ~15 dependent instructions per MMA to move its
+    // descriptors into uniform registers - 28 MMAs per iteration made that the critical path)
+    {
       constexpr uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);    // K-major x K-major
       constexpr uint32_t id_kd = umma_idesc_bf16(128, 32, 1, 1);    // MN-major x MN-major  (dV, dK)
       constexpr uint32_t id_q = umma_idesc_bf16(128, 32, 0, 1);     // K-major x MN-major   (dQ)
@@ -131,11 +134,11 @@ attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap 
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-          umma_bf16(tS, umma_smem_desc_sw128(q + 32 * k, 16, 1024), umma_smem_desc_sw128(kv + 32 * k, 16, 1024), id_s, k);
-          umma_bf16(tDP, umma_smem_desc_sw128(d_o + 32 * k, 16, 1024), umma_smem_desc_sw128(kv + 64 + 32 * k, 16, 1024),
+          umma_bf16_1(tS, umma_smem_desc_sw128(q + 32 * k, 16, 1024), umma_smem_desc_sw128(kv + 32 * k, 16, 1024), id_s, k);
+          umma_bf16_1(tDP, umma_smem_desc_sw128(d_o + 32 * k, 16, 1024), umma_smem_desc_sw128(kv + 64 + 32 * k, 16, 1024),
                     id_s, k);
         }
-        umma_commit(s_full);
+        umma_commit_1(s_full);
       };
       mma_s(0);
       for (int it = 0; it < n_iter; ++it) {
@@ -148,17 +151,17 @@ attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap 
         const uint32_t pp = smem_u32(sP), ds = smem_u32(sDS);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {                         // contraction over the 128 queries: 16 rows per step
-          umma_bf16(tDV, umma_smem_desc_sw128(pp + 2048 * k, 16384, 1024), umma_smem_desc_sw128(d_o + 2048 * k, 8192, 1024),
+          umma_bf16_1(tDV, umma_smem_desc_sw128(pp + 2048 * k, 16384, 1024), umma_smem_desc_sw128(d_o + 2048 * k, 8192, 1024),
                     id_kd, (it | k) != 0 ? 1u : 0u);
-          umma_bf16(tDK, umma_smem_desc_sw128(ds + 2048 * k, 16384, 1024), umma_smem_desc_sw128(q + 2048 * k, 8192, 1024),
+          umma_bf16_1(tDK, umma_smem_desc_sw128(ds + 2048 * k, 16384, 1024), umma_smem_desc_sw128(q + 2048 * k, 8192, 1024),
                     id_kd, (it | k) != 0 ? 1u : 0u);
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k)                           // contraction over the 128 keys: two 64-key boxes
-          umma_bf16(tDQ, umma_smem_desc_sw128(ds + (k >> 2) * 16384 + 32 * (k & 3), 16, 1024),
+          umma_bf16_1(tDQ, umma_smem_desc_sw128(ds + (k >> 2) * 16384 + 32 * (k & 3), 16, 1024),
                     umma_smem_desc_sw128(kv + 2048 * k, 8192, 1024), id_q, k != 0 ? 1u : 0u);
-        umma_commit(&in_empty[s]);
-        umma_commit(p_empty);
+        umma_commit_1(&in_empty[s]);
+        umma_commit_1(p_empty);
       }
     }
   } else {

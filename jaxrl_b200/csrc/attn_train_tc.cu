@@ -56,7 +56,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
   uint64_t* bar_o = bars + 1 + 8 + 2;  // MMA2 finished (O updated, P tile free)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp index, provably uniform
   const long long tok0 = (long long)b * T;
   unsigned long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 32) ? dbg_buf : nullptr;
   dbg_stamp(dbg, 0);
@@ -78,21 +78,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
   __syncthreads();
   tc_fence_after();
   dbg_stamp(dbg, 1);
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t tS[2] = {tmem_base, tmem_base + 64};
   const uint32_t tO = tmem_base + 128;
 
   constexpr uint32_t idesc1 = umma_idesc_bf16(128, 64, 0, 0);   // Q (K-major) x K (K-major)
   constexpr uint32_t idesc2 = umma_idesc_bf16(128, 64, 0, 1);   // P (K-major) x [K|V] (MN-major)
 
-  auto issue_mma1 = [&](int kt) {   // S[kt & 1] = Q . K_kt^T     (thread 0 only)
+  // MMAs are issued by warp 0 as a whole (uniform control flow, one elected lane per instruction) so that the
+  // descriptors stay in uniform registers
+  auto issue_mma1 = [&](int kt) {   // S[kt & 1] = Q . K_kt^T     (warp 0)
     const uint32_t a = smem_u32(sQ);
     const uint32_t bb = smem_u32(sKV) + kt * (TC_KT * 128);
 #pragma unroll
     for (int k = 0; k < 2; ++k)
-      umma_bf16(tS[kt & 1], umma_smem_desc_sw128(a + 32 * k, 16, 1024), umma_smem_desc_sw128(bb + 32 * k, 16, 1024),
-                idesc1, k);
-    umma_commit(&bar_s[kt & 1]);
+      umma_bf16_1(tS[kt & 1], umma_smem_desc_sw128(a + 32 * k, 16, 1024), umma_smem_desc_sw128(bb + 32 * k, 16, 1024),
+                  idesc1, k);
+    umma_commit_1(&bar_s[kt & 1]);
   };
 
   if (tid == 0) {
@@ -102,6 +104,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
       mbar_arrive_expect_tx(&bar_kv[j], 16384);
       tma_load_2d(&tm_qkv, &bar_kv[j], sKV + j * 16384, kv_col, (int)(tok0 + j * 128));
     }
+  }
+  if (warp == 0) {
     mbar_wait(bar_q, 0);
     mbar_wait(&bar_kv[0], 0);
     tc_fence_after();
@@ -113,7 +117,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
   float m = -INFINITY, l = 0.f;
 
   for (int kt = 0; kt < nkt; ++kt) {
-    if (tid == 0 && kt + 1 < nkt) {
+    if (warp == 0 && kt + 1 < nkt) {
       if (((kt + 1) & 1) == 0) mbar_wait(&bar_kv[(kt + 1) >> 1], 0);   // first use of a new [k|v] box
       tc_fence_after();
       issue_mma1(kt + 1);
@@ -171,15 +175,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
     tc_fence_before();
     __syncthreads();
     if (kt < 8) dbg_stamp(dbg, 4 + 3 * kt);
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       const uint32_t a = smem_u32(sP);
       const uint32_t bb = smem_u32(sKV) + kt * (TC_KT * 128);
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        umma_bf16(tO, umma_smem_desc_sw128(a + 32 * k, 16, 1024), umma_smem_desc_sw128(bb + 2048 * k, 8192, 1024),
-                  idesc2, (kt | k) != 0 ? 1u : 0u);
-      umma_commit(bar_o);
+        umma_bf16_1(tO, umma_smem_desc_sw128(a + 32 * k, 16, 1024), umma_smem_desc_sw128(bb + 2048 * k, 8192, 1024),
+                    idesc2, (kt | k) != 0 ? 1u : 0u);
+      umma_commit_1(bar_o);
     }
   }
   mbar_wait(bar_o, (nkt - 1) & 1);

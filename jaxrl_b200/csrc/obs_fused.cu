@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
   float* sOut = reinterpret_cast<float*>(sA1);               // conv3 accumulator staging, aliases a1 (dead by then)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int tid = threadIdx.x;
   const int n_tiles = (int)((p.M + OF_AG - 1) / OF_AG);
   const int cell_bytes = OF_IH * OF_IW * p.K;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
   __syncthreads();
   tc_fence_after();
   dbg_stamp(dbg, 1);
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t tD2 = tmem_base;            // 3 x 32 columns
   const uint32_t tD3 = tmem_base + 128;      // 128 columns
   const uint32_t lboA = p.swap ? 256u : 128u, sboA1 = p.swap ? 128u : 256u;
@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
 
   if (warp == OF_WORKERS) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    // the whole warp runs the (uniform) control flow; one elected lane issues each of the 45 MMAs of a tile
+    {
       constexpr uint32_t idesc2 = umma_idesc_bf16(128, OF_C2, 0, 0);
       constexpr uint32_t idesc3 = umma_idesc_bf16(128, OF_H, 0, 0);
       uint32_t ph = 0;
@@ -193,19 +194,19 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             const int q0 = (j + tap / 3) * OF_P1 + (tap % 3);
-            umma_bf16(tD2 + j * OF_C2, umma_smem_desc_nosw(a1 + q0 * 1024, lboA, sboA1),
+            umma_bf16_1(tD2 + j * OF_C2, umma_smem_desc_nosw(a1 + q0 * 1024, lboA, sboA1),
                       umma_smem_desc_nosw(w2 + tap * 1024, lboA, sboA1), idesc2, tap != 0 ? 1u : 0u);
           }
         }
-        umma_commit(c2_full);
+        umma_commit_1(c2_full);
         mbar_wait(a2_ready, ph);
         tc_fence_after();
         const uint32_t a2 = smem_u32(sA2), w3 = smem_u32(sW3);
 #pragma unroll
         for (int s = 0; s < OF_K3 / 16; ++s)
-          umma_bf16(tD3, umma_smem_desc_nosw(a2 + s * 256, p.swap ? sbo3 : 128u, p.swap ? 128u : sbo3),
+          umma_bf16_1(tD3, umma_smem_desc_nosw(a2 + s * 256, p.swap ? sbo3 : 128u, p.swap ? 128u : sbo3),
                     umma_smem_desc_nosw(w3 + s * 256, p.swap ? sbo3 : 128u, p.swap ? 128u : sbo3), idesc3, s != 0 ? 1u : 0u);
-        umma_commit(c3_full);
+        umma_commit_1(c3_full);
         ph ^= 1;
       }
     }

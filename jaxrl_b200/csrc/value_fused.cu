@@ -72,7 +72,7 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
   uint64_t* part_empty = x_full + 14;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 15);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int ncta = (int)cluster_nctarank(), krank = (int)cluster_ctarank();
   const int nchunks = p.Vh / 64 / ncta;
   const int chunk0 = krank * nchunks;
@@ -122,7 +122,7 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
   if (ncta > 1) cluster_sync_all();
   tc_fence_after();
   dbg_stamp(dbg, 1);
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t tZ[2] = {tmem_base, tmem_base + 64};
   const uint32_t tD = tmem_base + 128;
 
@@ -159,7 +159,8 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    // warp-uniform control flow, one elected lane per tcgen05 instruction (descriptors stay in uniform registers)
+    {
       constexpr uint32_t idesc1 = umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc2 = umma_idesc_bf16(128, 128, 0, 0);
       int stage = 0;
@@ -176,13 +177,13 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
           const uint32_t sa = smem_u32(sX + kb * 16384);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tZ[b], umma_smem_desc_sw128(sa + 32 * k, 16, 1024),
+            umma_bf16_1(tZ[b], umma_smem_desc_sw128(sa + 32 * k, 16, 1024),
                       umma_smem_desc_sw128(sb + kb * 8192 + 32 * k, 16, 1024), idesc1, (kb | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&w_empty[stage]);
+        umma_commit_1(&w_empty[stage]);
         if (++stage == VF_STAGES) { stage = 0; wphase ^= 1; }
-        umma_commit(&z_full[b]);
-        if (last) umma_commit(x_empty);
+        umma_commit_1(&z_full[b]);
+        if (last) umma_commit_1(x_empty);
         z_ph[b] ^= 1;
       };
       auto mma2 = [&](int c, bool last) {     // [hi | lo] += pv_c . Whl_c^T
@@ -195,12 +196,12 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
         const uint32_t sb = smem_u32(sW + stage * VF_STAGE_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tD, umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024), idesc2,
+          umma_bf16_1(tD, umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024), idesc2,
                     (c | k) != 0 ? 1u : 0u);
-        umma_commit(&w_empty[stage]);
+        umma_commit_1(&w_empty[stage]);
         if (++stage == VF_STAGES) { stage = 0; wphase ^= 1; }
-        umma_commit(&h_empty[b]);
-        if (last) umma_commit(d_full);
+        umma_commit_1(&h_empty[b]);
+        if (last) umma_commit_1(d_full);
       };
       for (int tile = blockIdx.y; tile < m_tiles; tile += gridDim.y) {
         mbar_wait(xn_ready, xnphase);          // x tile landed and (optionally) normalised in place
