@@ -48,7 +48,8 @@ struct GemmParams {
   const float* bias_f32;     // EPI_PAIRSUM
   const float* norm_scale;   // EPI_QKV, K == 128: RMSNorm(x; scale, eps) applied to the A tile in shared memory first
   float norm_eps;
-  int dbg_mode;              // mpx_debug_set(7, v) experiments: 1 = epilogue without global stores, 2 = no epilogue work
+  int tma_store;             // EPI_STORE: bf16 outputs (y, y_pre) leave through per-warp TMA bulk stores (tm_y, tm_ypre)
+  int dbg_mode;              // mpx_debug_set(7, v) experiments: 1 = epilogue without global stores, 2 = no epilogue work, 4 = no TMA stores
   // EPI_QKV
   const int32_t* pos;
   int pos_len;
@@ -74,9 +75,10 @@ struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int XPOSE_OFFSET = BAR_OFFSET + 256;   // 2 KB per epilogue warp: row-per-lane <-> coalesced transposes
-  static constexpr int NORM_OFFSET = XPOSE_OFFSET + 8 * 2048;   // 2 x 128 partial sums of squares + 128 scales (pre-norm prologue)
-  static constexpr int TOTAL = NORM_OFFSET + 2048 + 1024;         // + 1 KB alignment slack
+  static constexpr int NORM_OFFSET = BAR_OFFSET + 256;    // 2 x 128 partial sums of squares + 128 scales (pre-norm prologue)
+  static constexpr int XPOSE_OFFSET = BAR_OFFSET + 2048;  // 2 x 2 KB per epilogue warp: row-per-lane <-> coalesced transposes,
+                                                          // and the (SWIZZLE_64B) source tiles of the TMA output stores
+  static constexpr int TOTAL = XPOSE_OFFSET + 8 * 4096 + 1024;    // + 1 KB alignment slack
 };
 
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&f)[32]) {
@@ -127,6 +129,26 @@ __device__ __forceinline__ void warp_store_tile(uint32_t xp, __nv_bfloat16* tile
   }
   __syncwarp();
 }
+// The same tile through a TMA bulk store: the row-per-lane write above IS the SWIZZLE_64B layout of a 32-column box
+// (16-byte chunk index XOR address bits 7-8), so the 4 shared loads + 4 global stores per lane become one instruction
+// per warp.  Two buffers per warp; a buffer is rewritten only after the store issued from it two tiles ago has read it.
+__device__ __forceinline__ void warp_store_tile_tma(uint32_t xp, uint32_t& sel, const CUtensorMap* tm, int col0, int row0,
+                                                    const uint32_t (&w)[16], int lane) {
+  const uint32_t buf = xp + sel * 2048;
+  sel ^= 1;
+  if (lane == 0) bulk_wait_group_read1();
+  __syncwarp();
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    sts_v4(buf + lane * 64 + ((j ^ sw) << 4), make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]));
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d_s(tm, buf, col0, row0);
+    bulk_commit_group();
+  }
+}
 // coalesced global read of the warp's 32 x 32 tile into registers (lane = (r8, j) layout) ...
 __device__ __forceinline__ void warp_fetch_tile(const __nv_bfloat16* tile, long long ld, int rows_valid, uint4 (&c)[4],
                                                 int lane) {
@@ -166,7 +188,8 @@ __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
 // rpre: this chunk's residual already fetched with warp_fetch_tile (when use_pre).
 // Values are carried as packed bf16 pairs between the rounding points (one F2FP per pair).
 __device__ __forceinline__ void epi_store(const GemmParams& p, int row0, int lane, int col0, const uint32_t (&acc)[32],
-                                          uint32_t xp, const uint4 (&rpre)[4], bool use_pre) {
+                                          uint32_t xp, const uint4 (&rpre)[4], bool use_pre, const CUtensorMap* tm_y,
+                                          const CUtensorMap* tm_ypre, uint32_t& sel) {
   if (row0 >= p.M || col0 >= p.N) return;                 // warp-uniform
   const int row = row0 + lane;
   const int rows_valid = (p.dbg_mode & 1) ? 0 : min(32, p.M - row0);
@@ -207,7 +230,9 @@ __device__ __forceinline__ void epi_store(const GemmParams& p, int row0, int lan
   // 16-byte pieces everywhere: pitches are multiples of 8 elements and the bases 16-byte aligned
   const bool vec_y = full && ((p.ldy & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
   if (p.y_pre) {
-    if (vec_y && ((reinterpret_cast<uintptr_t>(p.y_pre) & 15) == 0)) {
+    if (p.tma_store) {
+      warp_store_tile_tma(xp, sel, tm_ypre, col0, row0, w, lane);
+    } else if (vec_y && ((reinterpret_cast<uintptr_t>(p.y_pre) & 15) == 0)) {
       warp_store_tile(xp, p.y_pre + (long long)row0 * p.ldy + col0, p.ldy, rows_valid, w, lane);
     } else if (row < p.M) {
       __nv_bfloat16* dp = p.y_pre + (long long)row * p.ldy + col0;
@@ -243,7 +268,9 @@ __device__ __forceinline__ void epi_store(const GemmParams& p, int row0, int lan
       }
     }
   }
-  if (vec_y) {
+  if (p.tma_store) {
+    warp_store_tile_tma(xp, sel, tm_y, col0, row0, w, lane);
+  } else if (vec_y) {
     warp_store_tile(xp, p.y + (long long)row0 * p.ldy + col0, p.ldy, rows_valid, w, lane);
   } else if (row < p.M) {
     __nv_bfloat16* d = p.y + (long long)row * p.ldy + col0;
@@ -346,7 +373,8 @@ __device__ __forceinline__ void epi_pairsum(const GemmParams& p, int row, int co
 // ------------------------------------------------------------------------------------------------ kernel
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b) {
+gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+               const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_ypre) {
   using L = SmemLayout<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -450,7 +478,8 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;        // which of the two warps of this quarter: takes chunks with (c/32)&1 == half
     const int row_in_tile = quarter * 32 + lane;
-    const uint32_t xp = smem_u32(smem + L::XPOSE_OFFSET + (warp - 2) * 2048);
+    const uint32_t xp = smem_u32(smem + L::XPOSE_OFFSET + (warp - 2) * 4096);
+    uint32_t xsel = 0;                      // which of the warp's two 2 KB buffers the next TMA store tile takes
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
@@ -555,7 +584,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
             uint32_t acc[32];
             tmem_ld_32x32(t_row + c, acc);
             tmem_ld_wait();
-            if (!(p.dbg_mode & 2)) epi_store(p, row0, lane, n_blk * BLOCK_N + c, acc, xp, rpre[j], have_pre);
+            if (!(p.dbg_mode & 2)) epi_store(p, row0, lane, n_blk * BLOCK_N + c, acc, xp, rpre[j], have_pre, &tm_y, &tm_ypre, xsel);
           }
         }
       } else {
@@ -565,13 +594,14 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
           tmem_ld_32x32(t_row + c, acc);
           tmem_ld_wait();
           if constexpr (EPI == EPI_QKV) epi_qkv(p, row0, lane, n_blk * BLOCK_N + c, acc, sn, cs, xp);
-          else if (!(p.dbg_mode & 2)) epi_store(p, row0, lane, n_blk * BLOCK_N + c, acc, xp, rpre[0], false);
+          else if (!(p.dbg_mode & 2)) epi_store(p, row0, lane, n_blk * BLOCK_N + c, acc, xp, rpre[0], false, &tm_y, &tm_ypre, xsel);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
     }
+    if (p.tma_store && lane == 0) bulk_wait_group0();       // shared memory must outlive the stores reading it
   }
   tc_fence_before();
   __syncthreads();
@@ -954,8 +984,14 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+static int make_tmap_bf16_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                                uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz);
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_cols, uint32_t box_rows) {
+  return make_tmap_bf16_2d_sw(out, base, rows, cols, ld, box_cols, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+static int make_tmap_bf16_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                                uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -971,7 +1007,7 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%ux%u)", (int)r,
@@ -1004,7 +1040,21 @@ static int launch_tn(const GemmParams& p, const void* a, long long lda, const vo
   const int grid = tiles < num_sms() ? tiles : num_sms();
   GemmParams pp = p;
   pp.dbg_mode = g_gemm_dbg_mode;
-  cudaError_t le = launch_ex(gemm_tn_kernel<BLOCK_N, EPI>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, 0, true, pp, tm_a, tm_b);
+  // bf16 outputs through TMA stores (32 x 32 boxes, SWIZZLE_64B) when nothing else needs the per-warp transposer
+  CUtensorMap tm_y = tm_a, tm_ypre = tm_a;
+  pp.tma_store = 0;
+  if (EPI == EPI_STORE && p.y && !p.residual && !p.y_f32 && !(g_gemm_dbg_mode & 4) && (p.ldy & 7) == 0 &&
+      (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 && (!p.y_pre || (reinterpret_cast<uintptr_t>(p.y_pre) & 15) == 0)) {
+    rc = make_tmap_bf16_2d_sw(&tm_y, p.y, p.M, p.N, p.ldy, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    if (p.y_pre) {
+      rc = make_tmap_bf16_2d_sw(&tm_ypre, p.y_pre, p.M, p.N, p.ldy, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    }
+    pp.tma_store = 1;
+  }
+  cudaError_t le = launch_ex(gemm_tn_kernel<BLOCK_N, EPI>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, 0, true, pp, tm_a, tm_b,
+                             tm_y, tm_ypre);
   if (le != cudaSuccess) {
     set_error("launch gemm_tn_kernel: %s", cudaGetErrorString(le));
     return MPX_ERR_CUDA;
