@@ -615,7 +615,7 @@ static int launch_attn_decode_online(const mpx_attn_decode_args* a, cudaStream_t
   }
   const int grid = ceil_div(total, best_w) < sms ? ceil_div(total, best_w) : sms;
   const float scale_log2 = (1.0f / sqrtf((float)a->D)) * 1.4426950408889634f;
-  cudaError_t le = launch_ex(attn_decode_online_kernel<G>, dim3(grid), dim3(best_w * 32), smem, stream, 0, true,
+  cudaError_t le = launch_ex(attn_decode_online_kernel<G>, dim3(grid), dim3(best_w * 32), smem, stream, 0, 4,
                              reinterpret_cast<const __nv_bfloat16*>(a->q), reinterpret_cast<const __nv_bfloat16*>(a->kcache),
                              reinterpret_cast<const __nv_bfloat16*>(a->vcache), a->pos,
                              reinterpret_cast<__nv_bfloat16*>(a->out), a->B, a->S, a->Nkv, scale_log2);

@@ -388,7 +388,7 @@ extern "C" int mpx_attn_decode_fused(const mpx_attn_decode_fused_args* a, mpx_st
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.B = a->B; p.S = a->S;
   p.scale_log2 = (1.0f / sqrtf((float)a->D)) * 1.4426950408889634f;
-  cudaError_t le = launch_ex(attn_decode_fused_kernel, dim3(grid), dim3(best_w * 32), smem, (cudaStream_t)stream, 0, true, p);
+  cudaError_t le = launch_ex(attn_decode_fused_kernel, dim3(grid), dim3(best_w * 32), smem, (cudaStream_t)stream, 0, 4, p);
   if (le != cudaSuccess) {
     set_error("launch attn_decode_fused_kernel: %s", cudaGetErrorString(le));
     return MPX_ERR_CUDA;

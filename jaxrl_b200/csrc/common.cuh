@@ -33,11 +33,12 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 int num_sms();   // abi.cu (cached cudaDevAttrMultiProcessorCount of the current device)
 
 // Launch with optional thread-block cluster (x dimension) and programmatic dependent launch (see ptx.cuh).
-extern int g_use_pdl;   // mpx_debug_set(6, 0|1); default 0 (measured gain on the whole rollout step: <1%)
+extern int g_use_pdl;   // mpx_debug_set(6, mask); default 0.  Bit per kernel family (the `pdl` argument of launch_ex):
+                        // 1 = everything else, 2 = obs encoder, 4 = decode attention, 8 = fused GLU, 16 = policy head
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                             int cluster_x, bool pdl, Args&&... args) {
+                             int cluster_x, int pdl, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -52,7 +53,7 @@ inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
     attr[n].val.clusterDim.z = 1;
     ++n;
   }
-  if (pdl && g_use_pdl) {
+  if (pdl & g_use_pdl) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;

@@ -591,7 +591,7 @@ extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const m
     cl = g_glu_fused_cluster;
   int gy = num_sms() / cl;
   if (gy > tiles) gy = tiles;
-  cudaError_t le = launch_ex(glu_fused_kernel, dim3(cl, gy, 1), dim3(GF_THREADS), smem, (cudaStream_t)stream, cl, true, p, tm_x, tm_wug, tm_wd, tm_wo, tm_h);
+  cudaError_t le = launch_ex(glu_fused_kernel, dim3(cl, gy, 1), dim3(GF_THREADS), smem, (cudaStream_t)stream, cl, 8, p, tm_x, tm_wug, tm_wd, tm_wo, tm_h);
   if (le != cudaSuccess) {
     set_error("cudaLaunchKernelEx(glu_fused, cluster %d): %s", cl, cudaGetErrorString(le));
     return MPX_ERR_CUDA;

@@ -645,7 +645,7 @@ extern "C" int mpx_policy_head_sample(const mpx_bf16* x, const float* norm_scale
   const size_t smem = (size_t)A * (H + 32) * sizeof(float);      // 4-float pad per lane slot
   MPX_REQUIRE(smem <= 48 * 1024, "mpx_policy_head_sample: table too large for shared memory");
   cudaError_t le = launch_ex(policy_head_sample_kernel, dim3(grid_for(M, HD_WARPS * 4, 8)), dim3(HD_WARPS * 32), smem,
-                             (cudaStream_t)stream, 0, true, reinterpret_cast<const __nv_bfloat16*>(x), norm_scale, eps, table,
+                             (cudaStream_t)stream, 0, 16, reinterpret_cast<const __nv_bfloat16*>(x), norm_scale, eps, table,
                              action_mask, gumbel_in, seed, stream_id, stream_offset, logits_out,
                              reinterpret_cast<__nv_bfloat16*>(xf_out), action, log_prob, M, H, A);
   if (le != cudaSuccess) {

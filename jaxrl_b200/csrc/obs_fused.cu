@@ -525,7 +525,7 @@ extern "C" int mpx_obs_embed_fused(const uint8_t* obs, const int* sizes, int K, 
   }
   const long long tiles = (M + OF_AG - 1) / OF_AG;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  cudaError_t le = launch_ex(obs_fused_kernel, dim3(grid), dim3(OF_THREADS), OF_SMEM, (cudaStream_t)stream, 0, true, p);
+  cudaError_t le = launch_ex(obs_fused_kernel, dim3(grid), dim3(OF_THREADS), OF_SMEM, (cudaStream_t)stream, 0, 2, p);
   if (le != cudaSuccess) {
     set_error("launch obs_fused_kernel: %s", cudaGetErrorString(le));
     return MPX_ERR_CUDA;
