@@ -80,7 +80,9 @@ typedef struct {
   mpx_bf16* y;              long long ldy;    /* (M,N) or NULL */
   float* y_f32;             long long ldy32;  /* optional raw fp32 accumulator output (M,N) */
   int M, N, K;
-  int act;                                    /* 0 none, 1 gelu (tanh approximation, jax.nn.gelu default) */
+  int act;                                    /* 0 none, 1 gelu (tanh approximation, jax.nn.gelu default),
+                                               * 2 gelu TRANSPOSE for data gradients: y = bf16(bf16(x @ wt^T) * gelu'(z))
+                                               *   with z = the saved pre-activation passed in `residual` (no add) */
   mpx_bf16* y_pre;                            /* optional (M,N), pitch ldy: bf16 pre-activation saved for backward */
 } mpx_linear_args;
 int mpx_linear(const mpx_linear_args* a, mpx_stream_t stream);
@@ -372,6 +374,17 @@ int mpx_muon_step(float* params, const float* grads, float* mu, float* nu, float
                   int max_c, float* ns_ws, int* step, float lr0, float total_steps, float adam_b1, float adam_b2,
                   float eps, float weight_decay, float muon_beta, int ns_steps, float max_norm, float grad_scale,
                   float* update_norm_out, void* workspace, mpx_stream_t stream);
+/* The same step in two enqueue phases (phases = 1 | 2; 3 = mpx_muon_step): 1 = the Muon-labelled matrices only
+ * (momentum, Newton-Schulz, their update and squared-norm partials - touches neither params nor the step counter),
+ * 2 = the AdamW-labelled leaves, the global-norm clip over both partitions, the parameter write, step += 1.  The
+ * matrices' gradients (layer weights, optimizer.py:51-69) are complete before the observation-encoder backward
+ * starts, so a caller runs phase 1 (after its own all-reduce of grads[n_adam:]) on a second stream under that
+ * backward and joins before phase 2.  Same arguments in both calls. */
+int mpx_muon_step_phased(float* params, const float* grads, float* mu, float* nu, float* update_scratch, long long n,
+                         long long n_adam, const void* mats, int nmat, long long x_total, long long a_total,
+                         int max_r, int max_c, float* ns_ws, int* step, float lr0, float total_steps, float adam_b1,
+                         float adam_b2, float eps, float weight_decay, float muon_beta, int ns_steps, float max_norm,
+                         float grad_scale, float* update_norm_out, void* workspace, int phases, mpx_stream_t stream);
 /* fp32 master weights -> bf16 GEMM operand copies. descs is a DEVICE array; each entry casts (and optionally
  * transposes) a (rows, cols) fp32 block with pitch src_ld into a bf16 destination with pitch dst_ld. */
 typedef struct {

@@ -256,15 +256,22 @@ __device__ __forceinline__ void epi_store(const GemmParams& p, int row0, int lan
         warp_fetch_tile(p.residual + (long long)row0 * p.ldr + col0, p.ldr, rows_valid, c, lane);
       }
       warp_rows_from_fetched(xp, c, rw, lane);
+      if (p.act == 2) {                                   // gelu transpose: `residual` is the saved pre-activation z
 #pragma unroll
-      for (int i = 0; i < 16; ++i) w[i] = bf16x2_add(w[i], rw[i]);
+        for (int i = 0; i < 16; ++i)
+          w[i] = pack_bf16(bf16_lo(w[i]) * gelu_tanh_grad(bf16_lo(rw[i])), bf16_hi(w[i]) * gelu_tanh_grad(bf16_hi(rw[i])));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = bf16x2_add(w[i], rw[i]);
+      }
     } else if (row < p.M) {
       const __nv_bfloat16* r = p.residual + (long long)row * p.ldr + col0;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float r0 = (col0 + 2 * i < p.N) ? __bfloat162float(r[2 * i]) : 0.f;
         const float r1 = (col0 + 2 * i + 1 < p.N) ? __bfloat162float(r[2 * i + 1]) : 0.f;
-        w[i] = pack_bf16(bf16_lo(w[i]) + r0, bf16_hi(w[i]) + r1);
+        if (p.act == 2) w[i] = pack_bf16(bf16_lo(w[i]) * gelu_tanh_grad(r0), bf16_hi(w[i]) * gelu_tanh_grad(r1));
+        else w[i] = pack_bf16(bf16_lo(w[i]) + r0, bf16_hi(w[i]) + r1);
       }
     }
   }
@@ -554,6 +561,15 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
           have_pre = true;
         }
       }
+      // wide tiles (BLOCK_N > 128): the residual / pre-activation tile of a chunk is fetched one chunk ahead instead
+      uint4 rnext[4];
+      bool pre_wide = false;
+      if constexpr (EPI == EPI_STORE && BLOCK_N > 128) {
+        pre_wide = p.residual && p.y && row0 < p.M && (p.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0;
+        if (pre_wide && n_blk * BLOCK_N + 32 * half + 32 <= p.N)
+          warp_fetch_tile(p.residual + (long long)row0 * p.ldr + n_blk * BLOCK_N + 32 * half, p.ldr, min(32, p.M - row0),
+                          rnext, lane);
+      }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BLOCK_N;
@@ -587,14 +603,28 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
             if (!(p.dbg_mode & 2)) epi_store(p, row0, lane, n_blk * BLOCK_N + c, acc, xp, rpre[j], have_pre, &tm_y, &tm_ypre, xsel);
           }
         }
+      } else if constexpr (EPI == EPI_STORE) {
+#pragma unroll 1
+        for (int c = 32 * half; c < BLOCK_N; c += 64) {
+          const int col0 = n_blk * BLOCK_N + c;
+          const bool have = pre_wide && col0 + 32 <= p.N;
+          uint4 rcur[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
+          if (pre_wide && c + 64 < BLOCK_N && col0 + 96 <= p.N)
+            warp_fetch_tile(p.residual + (long long)row0 * p.ldr + col0 + 64, p.ldr, min(32, p.M - row0), rnext, lane);
+          uint32_t acc[32];
+          tmem_ld_32x32(t_row + c, acc);
+          tmem_ld_wait();
+          if (!(p.dbg_mode & 2)) epi_store(p, row0, lane, col0, acc, xp, rcur, have, &tm_y, &tm_ypre, xsel);
+        }
       } else {
 #pragma unroll 1
         for (int c = 32 * half; c < BLOCK_N; c += 64) {
           uint32_t acc[32];
           tmem_ld_32x32(t_row + c, acc);
           tmem_ld_wait();
-          if constexpr (EPI == EPI_QKV) epi_qkv(p, row0, lane, n_blk * BLOCK_N + c, acc, sn, cs, xp);
-          else if (!(p.dbg_mode & 2)) epi_store(p, row0, lane, n_blk * BLOCK_N + c, acc, xp, rpre[0], false, &tm_y, &tm_ypre, xsel);
+          epi_qkv(p, row0, lane, n_blk * BLOCK_N + c, acc, sn, cs, xp);
         }
       }
       tc_fence_before();
@@ -1107,7 +1137,9 @@ using namespace mpx;
 extern "C" int mpx_linear(const mpx_linear_args* a, mpx_stream_t stream) {
   MPX_REQUIRE(a && a->x && a->wt && (a->y || a->y_f32), "mpx_linear: null pointer");
   MPX_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "mpx_linear: empty shape M=%d N=%d K=%d", a->M, a->N, a->K);
-  MPX_REQUIRE(a->act == 0 || a->act == 1, "mpx_linear: unknown activation %d", a->act);
+  MPX_REQUIRE(a->act == 0 || a->act == 1 || a->act == 2, "mpx_linear: unknown activation %d", a->act);
+  MPX_REQUIRE(a->act != 2 || (a->residual && a->y && !a->bias && !a->y_pre),
+              "mpx_linear: act 2 (gelu transpose) needs y and the pre-activation in `residual`, and takes no bias / y_pre");
   GemmParams p = {};
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.bias = reinterpret_cast<const __nv_bfloat16*>(a->bias);

@@ -357,23 +357,28 @@ extern "C" size_t mpx_muon_workspace_bytes(long long n, int nmat) {
   return (size_t)(opt_grid(n > 0 ? n : 1) + (size_t)nmat * 32) * sizeof(double);
 }
 
-extern "C" int mpx_muon_step(float* params, const float* grads, float* mu, float* nu, float* update_scratch,
-                             long long n, long long n_adam, const void* mats, int nmat, long long x_total,
-                             long long a_total, int max_r, int max_c, float* ns_ws, int* step, float lr0,
-                             float total_steps, float adam_b1, float adam_b2, float eps, float weight_decay,
-                             float muon_beta, int ns_steps, float max_norm, float grad_scale, float* update_norm_out,
-                             void* workspace, mpx_stream_t stream) {
+// phases: bit 0 = the Muon-labelled matrices (momentum, Newton-Schulz, update + its squared-norm partials); bit 1 = the
+// AdamW-labelled leaves, the post-update global-norm clip over BOTH partitions, the parameter write and the step
+// counter.  A caller that has the matrices' gradients early (the layer weight gradients are complete long before the
+// observation-encoder backward ends) runs phase 1 on a second stream and joins before phase 2.
+extern "C" int mpx_muon_step_phased(float* params, const float* grads, float* mu, float* nu, float* update_scratch,
+                                    long long n, long long n_adam, const void* mats, int nmat, long long x_total,
+                                    long long a_total, int max_r, int max_c, float* ns_ws, int* step, float lr0,
+                                    float total_steps, float adam_b1, float adam_b2, float eps, float weight_decay,
+                                    float muon_beta, int ns_steps, float max_norm, float grad_scale,
+                                    float* update_norm_out, void* workspace, int phases, mpx_stream_t stream) {
   MPX_REQUIRE(params && grads && mu && nu && update_scratch && step && workspace && n > 0, "mpx_muon_step: bad arguments");
   MPX_REQUIRE(n_adam >= 0 && n_adam <= n && (nmat == 0 || (mats && ns_ws)), "mpx_muon_step: bad partition");
   MPX_REQUIRE(total_steps > 0.f && ns_steps >= 1, "mpx_muon_step: bad schedule");
+  MPX_REQUIRE(phases >= 1 && phases <= 3, "mpx_muon_step_phased: phases must be 1, 2 or 3");
   cudaStream_t s = (cudaStream_t)stream;
   double* partials = reinterpret_cast<double*>(workspace);
   const int agrid = n_adam > 0 ? opt_grid(n_adam) : 0;
-  if (n_adam > 0)
+  if (n_adam > 0 && (phases & 2))
     adamw_update_kernel<<<agrid, 256, 0, s>>>(params, grads, mu, nu, update_scratch, n_adam, step, lr0, total_steps,
                                               adam_b1, adam_b2, eps, weight_decay, grad_scale, 1, partials);
-  int nparts = agrid;
-  if (nmat > 0) {
+  int nparts = agrid + (nmat > 0 ? 32 * nmat : 0);
+  if (nmat > 0 && (phases & 1)) {
     const MuonMat* mm = reinterpret_cast<const MuonMat*>(mats);
     float* X0 = ns_ws;
     float* X1 = X0 + x_total;
@@ -396,10 +401,22 @@ extern "C" int mpx_muon_step(float* params, const float* grads, float* mu, float
     }
     muon_finish_kernel<<<dim3(32, nmat), 256, 0, s>>>(mm, xin, params, update_scratch, step, lr0, total_steps,
                                                      weight_decay, partials + agrid);
-    nparts += 32 * nmat;
   }
-  const int pgrid = opt_grid(n);
-  apply_update_kernel<<<pgrid, 256, 0, s>>>(params, update_scratch, n, partials, nparts, max_norm, step, update_norm_out);
-  step_inc_kernel<<<1, 1, 0, s>>>(step);
+  if (phases & 2) {
+    const int pgrid = opt_grid(n);
+    apply_update_kernel<<<pgrid, 256, 0, s>>>(params, update_scratch, n, partials, nparts, max_norm, step, update_norm_out);
+    step_inc_kernel<<<1, 1, 0, s>>>(step);
+  }
   return check_launch("mpx_muon_step");
+}
+
+extern "C" int mpx_muon_step(float* params, const float* grads, float* mu, float* nu, float* update_scratch,
+                             long long n, long long n_adam, const void* mats, int nmat, long long x_total,
+                             long long a_total, int max_r, int max_c, float* ns_ws, int* step, float lr0,
+                             float total_steps, float adam_b1, float adam_b2, float eps, float weight_decay,
+                             float muon_beta, int ns_steps, float max_norm, float grad_scale, float* update_norm_out,
+                             void* workspace, mpx_stream_t stream) {
+  return mpx_muon_step_phased(params, grads, mu, nu, update_scratch, n, n_adam, mats, nmat, x_total, a_total, max_r, max_c,
+                              ns_ws, step, lr0, total_steps, adam_b1, adam_b2, eps, weight_decay, muon_beta, ns_steps,
+                              max_norm, grad_scale, update_norm_out, workspace, 3, stream);
 }

@@ -316,12 +316,16 @@ class PolicyEngine:
                           t_table, out=out)
         return out
 
-    def _embed_bwd(self, ws, M: int, dx0, reward, last_action, task_ids, obs):
+    def _embed_bwd(self, ws, M: int, dx0, reward, last_action, task_ids, obs, matrices_ready=None):
         p, w = self.p, self.w
         gt = p.gviews.get("task_embedder.embedding_table") if task_ids is not None else None
         ops.embed_bwd(dx0, reward, last_action, task_ids if gt is not None else None, self.A, self.cfg.task_count,
                       p.g("reward_encoder.kernel"), p.g("reward_encoder.bias"),
                       p.g("action_embedder.embedding_table"), gt)
+        # Every 2-D leaf outside obs_encoder / reward_encoder / value_head (the Muon partition, optimizer.py:42-69) now
+        # has its complete gradient; only the observation encoder's backward is left.  The caller's hook (gradient
+        # all-reduce of that partition + the Newton-Schulz phase of the optimizer) runs on the side stream under it.
+        self.matrices_event = self._side_run(matrices_ready) if matrices_ready is not None else None
         if self.flat:
             ops.colsum(dx0, p.g("obs_encoder.dense.bias"), M=M, N=self.H, ld=self.H)
             ops.linear_wgrad(ws.fe, dx0, p.g("obs_encoder.dense.kernel"), M=M, K=self.fk, N=self.H, ldx=self.fkp,
@@ -351,8 +355,10 @@ class PolicyEngine:
                              N=c.cout, ldx=c.kp, ldy=c.cout, lddw=c.cout)
             if c.j == 0:
                 break
-            if last:
-                ops.linear(dy, w[f"w_c{c.j}"], out=ws.dca[c.j - 1].view(M, c.k), M=rows)
+            if last:       # the layer below is never the last one: its gelu transpose rides in the GEMM epilogue
+                ops.linear(dy, w[f"w_c{c.j}"], out=ws.dca[c.j - 1].view(M, c.k), M=rows,
+                           residual=ws.cz[c.j - 1].view(M, c.k), act=2)
+                fused_gelu = True
             else:
                 ops.linear(dy, w[f"w_c{c.j}"], out=ws.dcx[c.j], M=rows)
                 # the layer below is never the last one: its gelu transpose rides along with the scatter-sum
@@ -511,9 +517,11 @@ class PolicyEngine:
             torch.cuda.current_stream().wait_event(ev)
 
     # ------------------------------------------------------------------------------------------ loss + backward
-    def loss_and_backward(self, ws, batch: dict, hyp, progress: float, entropy_coef_dev=None):
+    def loss_and_backward(self, ws, batch: dict, hyp, progress: float, entropy_coef_dev=None, matrices_ready=None):
         """ppo_loss (train.py:162-222) on the activations left by forward_train, and its full transpose.
-        Gradients are ACCUMULATED into self.p.grad (zero it first).  ws.losses = (value, actor, entropy_loss)."""
+        Gradients are ACCUMULATED into self.p.grad (zero it first).  ws.losses = (value, actor, entropy_loss).
+        matrices_ready: optional callable enqueued on the side stream as soon as the gradients of the Muon-labelled
+        matrices (p.grad[p.n_adam:]) are final; self.matrices_event then holds its completion event (wait on it)."""
         p, w, M = self.p, self.w, ws.M
         cfg = self.cfg
         H, F, QD, KD, QKV, NL, Vh = self.H, self.F, self.QD, self.KD, self.QKV, self.NL, self.Vh
@@ -528,8 +536,7 @@ class PolicyEngine:
         self._side_run(lambda: ops.linear_wgrad(ws.pv, ws.dvl, p.g("value_head.dense.kernel"), M=M, K=Vh, N=NL, ldx=Vh,
                                                 ldy=64, lddw=NL))             # dvl / dpv are not rewritten in this pass
         ops.colsum(ws.dvl, p.g("value_head.dense.bias"), M=M, N=NL, ld=64)
-        ops.linear(ws.dvl, w["w_vh_pad"], out=ws.dpv)
-        ops.gelu_bwd(ws.dpv, ws.zv, out=ws.dpv)
+        ops.linear(ws.dvl, w["w_vh_pad"], out=ws.dpv, residual=ws.zv, act=2)      # gelu' rides in the GEMM epilogue
         self._side_run(lambda: ops.linear_wgrad(ws.xf, ws.dpv, p.g("value_mlp.kernel"), M=M, K=H, N=Vh, ldx=H, ldy=Vh,
                                                 lddw=Vh))
         ops.colsum(ws.dpv, p.g("value_mlp.bias"), M=M, N=Vh, ld=Vh)
@@ -591,5 +598,6 @@ class PolicyEngine:
             dx, spare = spare, dx                                       # dx = d x[i]
         # the embedding backward uses the same split-K workspace and overwrites `spare`: join the side stream first
         self._wait(ev_qkv)
-        self._embed_bwd(ws, M, dx, batch["last_rewards"], batch["last_actions"], batch.get("task_ids"), batch["obs"])
+        self._embed_bwd(ws, M, dx, batch["last_rewards"], batch["last_actions"], batch.get("task_ids"), batch["obs"],
+                        matrices_ready=matrices_ready)
         return ws.losses

@@ -533,14 +533,18 @@ def adamw_step(params, grads, mu, nu, scratch, step, lr0, total_steps, b1, b2, e
 
 def muon_step(params, grads, mu, nu, scratch, n_adam: int, table, nmat: int, x_total: int, a_total: int, max_r: int,
               max_c: int, ns_ws, step, lr0, total_steps, b1, b2, eps, wd, max_norm, grad_scale=1.0, muon_beta=0.95,
-              ns_steps=5, norm_out=None, ws=None):
-    """optax.contrib.muon partition (optimizer.py:25-37): Muon on the labelled matrices, AdamW(nesterov) elsewhere."""
+              ns_steps=5, norm_out=None, ws=None, phases: int = 3):
+    """optax.contrib.muon partition (optimizer.py:25-37): Muon on the labelled matrices, AdamW(nesterov) elsewhere.
+    phases: 1 = matrices only (enqueue early, e.g. on a side stream), 2 = AdamW leaves + clip + apply, 3 = both."""
     n = params.numel()
     if ws is None:
+        if phases != 3:
+            raise _lib.MpxError("muon_step: the two phases must share one caller-provided workspace")
         ws = torch.empty(lib.mpx_muon_workspace_bytes(n, nmat), dtype=torch.uint8, device=params.device)
-    check(lib.mpx_muon_step(ptr(params), ptr(grads), ptr(mu), ptr(nu), ptr(scratch), n, n_adam, ptr(table), nmat, x_total,
-                            a_total, max_r, max_c, ptr(ns_ws), ptr(step), lr0, float(total_steps), b1, b2, eps, wd,
-                            muon_beta, ns_steps, max_norm, grad_scale, ptr(norm_out), ptr(ws), stream()), "mpx_muon_step")
+    check(lib.mpx_muon_step_phased(ptr(params), ptr(grads), ptr(mu), ptr(nu), ptr(scratch), n, n_adam, ptr(table), nmat,
+                                   x_total, a_total, max_r, max_c, ptr(ns_ws), ptr(step), lr0, float(total_steps), b1, b2,
+                                   eps, wd, muon_beta, ns_steps, max_norm, grad_scale, ptr(norm_out), ptr(ws), phases,
+                                   stream()), "mpx_muon_step")
 
 
 def prep_weights(descs_device, ndesc: int):

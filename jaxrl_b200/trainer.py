@@ -245,17 +245,34 @@ class PPOTrainer:
                      obs=b.obs[sl])
         eng.p.grad.zero_()
         eng.forward_train(tws, b.obs[sl], batch["last_rewards"], batch["last_actions"])
-        eng.loss_and_backward(tws, batch, self.hyp, 0.0, entropy_coef_dev=self.ent_coef)
+        o, opt = self.o, self.opt
+        total = self.run.update_steps * self.hyp.minibatch_count * self.hyp.epoch_count
+        n_adam = eng.p.n_adam
+
+        def muon(phases: int, gscale: float):   # optimizer.py:25-37 (muon's own eps/beta defaults; adam_b1/b2 from the config)
+            m = o.muon
+            ops.muon_step(eng.p.flat, eng.p.grad, o.mu, o.nu, o.scratch, n_adam, m.table, m.nmat, m.x_total,
+                          m.a_total, m.max_r, m.max_c, m.ns_ws, o.step, opt.learning_rate, total, opt.beta1, opt.beta2,
+                          1e-8, opt.weight_decay, opt.max_norm, grad_scale=gscale, norm_out=o.norm, ws=m.ws, phases=phases)
+
+        # The Muon-labelled matrices (everything but the encoders / value head) have their gradients before the
+        # observation-encoder backward starts: their all-reduce and Newton-Schulz iterations run under it on the side
+        # stream; the AdamW leaves, the global-norm clip and the parameter write follow the rest of the backward.
+        early = self.run_optimizer and opt.type == "muon" and o.muon.nmat > 0 and 0 < n_adam < eng.p.numel and \
+            os.environ.get("MPX_MUON_OVERLAP", "1") == "1"
+        hook = (lambda: muon(1, mdist.allreduce_gradients(eng.p.grad[n_adam:]))) if early else None
+        eng.loss_and_backward(tws, batch, self.hyp, 0.0, entropy_coef_dev=self.ent_coef, matrices_ready=hook)
         self.log_acc[:3] += tws.losses[:3]
+        if early:
+            gscale = mdist.allreduce_gradients(eng.p.grad[:n_adam])
+            eng._wait(eng.matrices_event)
+            muon(2, gscale)
+            eng.stage_weights(rollout=False)
+            return
         gscale = mdist.allreduce_gradients(eng.p.grad)
         if self.run_optimizer:
-            o, opt = self.o, self.opt
-            total = self.run.update_steps * self.hyp.minibatch_count * self.hyp.epoch_count
-            if opt.type == "muon":        # optimizer.py:25-37 (muon's own eps/beta defaults; adam_b1/b2 from the config)
-                m = o.muon
-                ops.muon_step(eng.p.flat, eng.p.grad, o.mu, o.nu, o.scratch, eng.p.n_adam, m.table, m.nmat, m.x_total,
-                              m.a_total, m.max_r, m.max_c, m.ns_ws, o.step, opt.learning_rate, total, opt.beta1, opt.beta2,
-                              1e-8, opt.weight_decay, opt.max_norm, grad_scale=gscale, norm_out=o.norm, ws=m.ws)
+            if opt.type == "muon":
+                muon(3, gscale)
             else:                         # optimizer.py:12-23
                 ops.adamw_step(eng.p.flat, eng.p.grad, o.mu, o.nu, o.scratch, o.step, opt.learning_rate, total, opt.beta1,
                                opt.beta2, opt.eps, opt.weight_decay, opt.max_norm, grad_scale=gscale,

@@ -131,6 +131,22 @@ def test_linear_epilogues(ops):
     torch.testing.assert_close(out32.cpu(), x.float() @ wt.float().t(), rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("M,K,N", [(1000, 64, 768), (777, 128, 288), (333, 128, 96), (4096, 64, 768), (130, 128, 136)])
+def test_linear_gelu_transpose_epilogue(ops, M, K, N):
+    """act=2: dz = bf16(bf16(dy @ W) * gelu'(z)) in the GEMM epilogue == mpx_linear followed by mpx_gelu_bwd, bit for
+    bit (wide tiles fetch z one chunk ahead; narrow tiles before the accumulator wait), and a residual add with a
+    wide tile (the same prefetch path)."""
+    gen = g(M + N)
+    x = torch.randn(M, K, generator=gen).to(BF16).to(DEV)
+    wt = (torch.randn(N, K, generator=gen) / math.sqrt(K)).to(BF16).to(DEV)
+    z = (torch.randn(M, N, generator=gen) * 1.5).to(BF16).to(DEV)
+    two = ops.gelu_bwd(ops.linear(x, wt), z)
+    one = ops.linear(x, wt, residual=z, act=2)
+    assert torch.equal(one, two), "fused gelu transpose differs from linear + gelu_bwd"
+    y = ops.linear(x, wt, residual=z)
+    assert_close_bf16(y, _lin_ref(x.cpu(), wt.cpu(), residual=z.cpu()), "linear residual (wide tile)")
+
+
 @pytest.mark.parametrize("M,K,N", [(64, 128, 64), (1000, 128, 192), (131072, 128, 1536), (5000, 768, 128), (333, 128, 128)])
 def test_linear_wgrad(ops, M, K, N):
     gen = g(M + 3 * K + N)

@@ -203,6 +203,57 @@ def test_optimizer_step_matches_oracle(opt_type):
     assert step.item() == 3
 
 
+def test_muon_step_phased_matches_single_call():
+    """mpx_muon_step_phased: phase 1 (matrices, on a second stream) then phase 2 == the single-call step."""
+    from jaxrl_b200 import ops
+    from jaxrl_b200.config import OptimizerConfig
+    from jaxrl_b200.params import ParamStore
+    cfg = replace(CFG, num_layers=2)
+    ocfg = OptimizerConfig(type="muon")
+    gen = torch.Generator().manual_seed(3)
+    results = []
+    for phased in (False, True):
+        ps = ParamStore(cfg, DEV, seed=12, bias_noise=0.02)
+        n = ps.numel
+        z = lambda: torch.zeros(n, device=DEV)
+        mu, nu, scratch = z(), z(), z()
+        step = torch.zeros(1, dtype=torch.int32, device=DEV)
+        norm = torch.zeros(1, device=DEV)
+        tab, nmat, xt, at, mr, mc = ps.muon_table()
+        ns_ws = torch.zeros(2 * xt + 2 * at + nmat, device=DEV)
+        ws = torch.empty(_lib_bytes(n, nmat), dtype=torch.uint8, device=DEV)
+        gen.manual_seed(3)
+        side = torch.cuda.Stream()
+        for t in range(3):
+            ps.grad.copy_((torch.randn(n, generator=gen) * 0.01).to(DEV))
+            args = (ps.flat, ps.grad, mu, nu, scratch, ps.n_adam, tab, nmat, xt, at, mr, mc, ns_ws, step,
+                    ocfg.learning_rate, 100, ocfg.beta1, ocfg.beta2, 1e-8, ocfg.weight_decay, ocfg.max_norm)
+            if phased:
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    ops.muon_step(*args, norm_out=norm, ws=ws, phases=1)
+                torch.cuda.current_stream().wait_stream(side)
+                ops.muon_step(*args, norm_out=norm, ws=ws, phases=2)
+            else:
+                ops.muon_step(*args, norm_out=norm, ws=ws)
+        torch.cuda.synchronize()
+        assert step.item() == 3
+        results.append((ps.flat.clone(), mu.clone(), nu.clone(), norm.clone()))
+    (p0, mu0, nu0, n0), (p1, mu1, nu1, n1) = results
+    assert torch.equal(mu0, mu1) and torch.equal(nu0, nu1)          # momenta: no reduction-order freedom
+    # Newton-Schulz accumulates its split-K Gram matrices with fp32 atomics: equal up to summation order
+    init = ParamStore(cfg, DEV, seed=12, bias_noise=0.02).flat
+    d0, d1 = (p0 - init).double(), (p1 - init).double()
+    assert d0.norm().item() > 0
+    assert ((d1 - d0).norm() / d0.norm()).item() < 1e-4
+    torch.testing.assert_close(n1, n0, rtol=1e-4, atol=0)
+
+
+def _lib_bytes(n, nmat):
+    from jaxrl_b200 import _lib
+    return _lib.lib.mpx_muon_workspace_bytes(n, nmat)
+
+
 def test_flattened_encoder_forward_backward_match_oracle():
     """grid_flattened observation encoder (FlattenedObsEncoder, observation.py:98-145; the blog_32_layers config):
     training forward, losses and every gradient vs the oracle, plus a few decode steps."""
