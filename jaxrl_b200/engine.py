@@ -93,6 +93,10 @@ class PolicyEngine:
         self.obs_image = ops.obs_fused_image(self.dev) if self.fused_obs else None
         self.overlap_wgrad = os.environ.get("MPX_WGRAD_OVERLAP", "1") != "0"
         self.side = torch.cuda.Stream(device=self.dev) if (self.overlap_wgrad and self.dev.type == "cuda") else None
+        self.side2 = torch.cuda.Stream(device=self.dev) if self.side is not None else None     # early optimizer phase
+        # trip 79: the encoder's weight gradients next to its data-gradient chain gain nothing (both HBM-bound,
+        # 15.66 M vs 15.69 M env-steps/s), unlike the latency-bound Newton-Schulz launches: off by default
+        self.overlap_enc_wgrad = os.environ.get("MPX_ENC_WGRAD_OVERLAP", "0") == "1"
         c0 = self.conv[0] if self.conv else None
         self.onehot_wgrad = (c0 is not None and c0.k <= 128 and (c0.kh, c0.kw) == (3, 3) and c0.cout <= 64
                              and c0.cout % 8 == 0 and len(cfg.obs_max_value) <= 4)
@@ -325,7 +329,7 @@ class PolicyEngine:
         # Every 2-D leaf outside obs_encoder / reward_encoder / value_head (the Muon partition, optimizer.py:42-69) now
         # has its complete gradient; only the observation encoder's backward is left.  The caller's hook (gradient
         # all-reduce of that partition + the Newton-Schulz phase of the optimizer) runs on the side stream under it.
-        self.matrices_event = self._side_run(matrices_ready) if matrices_ready is not None else None
+        self.matrices_event = self._side_run(matrices_ready, self.side2) if matrices_ready is not None else None
         if self.flat:
             ops.colsum(dx0, p.g("obs_encoder.dense.bias"), M=M, N=self.H, ld=self.H)
             ops.linear_wgrad(ws.fe, dx0, p.g("obs_encoder.dense.kernel"), M=M, K=self.fk, N=self.H, ldx=self.fkp,
@@ -334,25 +338,34 @@ class PolicyEngine:
             ops.flat_embed_bwd(obs, ws.dfe, p.g("obs_encoder.embedding.kernel"), p.g("obs_encoder.embedding.bias"), M,
                                self.cells)
             return
+        # The data-gradient chain (GEMM -> col2im -> GEMM ...) stays on this stream; each layer's bias / weight
+        # gradients only feed the optimizer and go to the side stream as soon as that layer's dz exists (the side
+        # stream's program order protects the shared split-K workspace).  Every buffer they read is written once per
+        # minibatch; the join at the end precedes the optimizer and the next minibatch.
         n = len(self.conv)
         dy = dx0                      # cotangent of the last conv's output (M, H)
         fused_gelu = False
+        ev = None
+        run = self._side_run if self.overlap_enc_wgrad else (lambda fn: (fn(), None)[1])
         for c in reversed(self.conv):
             last = c.j == n - 1
             rows = M * c.oh * c.ow
             if not last and not fused_gelu:
                 ops.gelu_bwd(dy, ws.cz[c.j], out=dy)          # dz in place
             fused_gelu = False
-            ops.colsum(dy, p.g(f"obs_encoder.layers.{c.j}.bias"), M=rows, N=c.cout, ld=c.cout)
-            if c.j == 0 and self.onehot_wgrad:     # one-hot operand tiles are generated inside the wgrad kernel
-                ops.conv1_onehot_wgrad(obs, dy, p.g("obs_encoder.layers.0.kernel").view(c.k, c.cout), M, c.ih, c.iw,
-                                       self.cfg.obs_max_value, c.kh, c.kw, c.sh, c.sw, c.cout)
-                break
-            if c.j == 0:      # one-hot im2col rows are only needed here, for the weight gradient
-                ops.obs_onehot_im2col(obs, ws.cx[0], M, c.ih, c.iw, self.cfg.obs_max_value, c.kh, c.kw, c.sh, c.sw)
-            xin = ws.ca[c.j - 1].view(M, c.kp) if last else ws.cx[c.j]
-            ops.linear_wgrad(xin, dy, p.g(f"obs_encoder.layers.{c.j}.kernel").view(c.k, c.cout), M=rows, K=c.k,
-                             N=c.cout, ldx=c.kp, ldy=c.cout, lddw=c.cout)
+
+            def _wg(c=c, dy=dy, last=last, rows=rows):
+                ops.colsum(dy, p.g(f"obs_encoder.layers.{c.j}.bias"), M=rows, N=c.cout, ld=c.cout)
+                if c.j == 0 and self.onehot_wgrad:     # one-hot operand tiles are generated inside the wgrad kernel
+                    ops.conv1_onehot_wgrad(obs, dy, p.g("obs_encoder.layers.0.kernel").view(c.k, c.cout), M, c.ih, c.iw,
+                                           self.cfg.obs_max_value, c.kh, c.kw, c.sh, c.sw, c.cout)
+                    return
+                if c.j == 0:      # one-hot im2col rows are only needed here, for the weight gradient
+                    ops.obs_onehot_im2col(obs, ws.cx[0], M, c.ih, c.iw, self.cfg.obs_max_value, c.kh, c.kw, c.sh, c.sw)
+                xin = ws.ca[c.j - 1].view(M, c.kp) if last else ws.cx[c.j]
+                ops.linear_wgrad(xin, dy, p.g(f"obs_encoder.layers.{c.j}.kernel").view(c.k, c.cout), M=rows, K=c.k,
+                                 N=c.cout, ldx=c.kp, ldy=c.cout, lddw=c.cout)
+            ev = run(_wg)
             if c.j == 0:
                 break
             if last:       # the layer below is never the last one: its gelu transpose rides in the GEMM epilogue
@@ -365,6 +378,7 @@ class PolicyEngine:
                 ops.col2im(ws.dcx[c.j], ws.dca[c.j - 1], M, c.ih, c.iw, c.cin, c.kh, c.kw, c.sh, c.sw, z=ws.cz[c.j - 1])
                 fused_gelu = True
             dy = ws.dca[c.j - 1]
+        self._wait(ev)
 
     # ------------------------------------------------------------------------------------------ decode step
     def decode_step(self, ws, obs, reward, last_action, pos, action_mask=None, task_ids=None, value_out=None,
@@ -495,20 +509,21 @@ class PolicyEngine:
     # (HBM-bound wgrads overlap the compute-bound attention backward and the epilogue-bound dgrad GEMMs).  They share
     # one split-K workspace, which the side stream's program order protects.  Every buffer a pending wgrad reads is
     # guarded by an event the main stream waits on before the next kernel that overwrites it.
-    def _side_run(self, fn):
-        """Enqueue fn on the side stream, ordered after everything already on the current stream; returns an event
-        recorded on the side stream after fn."""
+    def _side_run(self, fn, stream=None):
+        """Enqueue fn on the side stream (or `stream`), ordered after everything already on the current stream;
+        returns an event recorded on that stream after fn."""
         if not self.overlap_wgrad:
             fn()
             return None
+        side = self.side if stream is None else stream
         main = torch.cuda.current_stream()
         ready = torch.cuda.Event()
         ready.record(main)
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(ready)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
             fn()
             done = torch.cuda.Event()
-            done.record(self.side)
+            done.record(side)
         return done
 
     @staticmethod
@@ -533,13 +548,16 @@ class PolicyEngine:
                             losses=ws.losses[1:3], dlogits=ws.dlogits, ws=ws.loss_ws,
                             entropy_coef_dev=entropy_coef_dev)
         # ---- value head (values.py:34,40-41) and value MLP (network.py:335-338)
-        self._side_run(lambda: ops.linear_wgrad(ws.pv, ws.dvl, p.g("value_head.dense.kernel"), M=M, K=Vh, N=NL, ldx=Vh,
-                                                ldy=64, lddw=NL))             # dvl / dpv are not rewritten in this pass
-        ops.colsum(ws.dvl, p.g("value_head.dense.bias"), M=M, N=NL, ld=64)
+        def _wg_vhead():                          # dvl / dpv are not rewritten in this pass
+            ops.linear_wgrad(ws.pv, ws.dvl, p.g("value_head.dense.kernel"), M=M, K=Vh, N=NL, ldx=Vh, ldy=64, lddw=NL)
+            ops.colsum(ws.dvl, p.g("value_head.dense.bias"), M=M, N=NL, ld=64)
+        self._side_run(_wg_vhead)
         ops.linear(ws.dvl, w["w_vh_pad"], out=ws.dpv, residual=ws.zv, act=2)      # gelu' rides in the GEMM epilogue
-        self._side_run(lambda: ops.linear_wgrad(ws.xf, ws.dpv, p.g("value_mlp.kernel"), M=M, K=H, N=Vh, ldx=H, ldy=Vh,
-                                                lddw=Vh))
-        ops.colsum(ws.dpv, p.g("value_mlp.bias"), M=M, N=Vh, ld=Vh)
+
+        def _wg_vmlp():
+            ops.linear_wgrad(ws.xf, ws.dpv, p.g("value_mlp.kernel"), M=M, K=H, N=Vh, ldx=H, ldy=Vh, lddw=Vh)
+            ops.colsum(ws.dpv, p.g("value_mlp.bias"), M=M, N=Vh, ld=Vh)
+        self._side_run(_wg_vmlp)
         ops.linear(ws.dpv, w["w_vm"], out=ws.dxn)                      # d xf from the value path
         # ---- tied policy head (network.py:323) and output norm (:321)
         ops.policy_head_bwd(ws.dlogits, ws.xf, p["action_embedder.embedding_table"],
