@@ -488,6 +488,22 @@ def test_transpose_tb(ops):
     assert torch.equal(fd.cpu(), f.t())
 
 
+@pytest.mark.parametrize("T,B,shape", [(512, 9, (11, 11, 2)), (136, 5, (11, 11, 2)), (64, 33, (5, 5, 2)), (8, 3, (11, 11, 2)),
+                                       (256, 4, (7, 7, 3))])
+def test_transpose_tb_row_assembler(ops, T, B, shape):
+    """Even item sizes that are not 4-byte multiples (uint8 observations) go through the shared-memory row assembler
+    (full and ragged 128-step segments); odd sizes keep the byte kernel.  Bit exact against torch indexing."""
+    gen = g(T + B)
+    src = torch.randint(0, 255, (T, B) + shape, generator=gen).to(torch.uint8)
+    perm = torch.randperm(B, generator=gen).to(torch.int32)
+    dst = torch.full((B, T) + shape, 7, dtype=torch.uint8, device=DEV)
+    ops.transpose_tb(src.to(DEV), dst, perm.to(DEV), T, B)
+    assert torch.equal(dst.cpu(), src[:, perm.long()].transpose(0, 1))
+    dst.fill_(9)
+    ops.transpose_tb(src.to(DEV), dst, None, T, B)
+    assert torch.equal(dst.cpu(), src.transpose(0, 1))
+
+
 @pytest.mark.parametrize("norm", [False, True])
 @pytest.mark.parametrize("M,F,cluster", [(77, 768, 0), (4096, 768, 0), (4096, 768, 1), (4096, 768, 2), (1000, 512, 4),
                                          (5000, 768, 4), (20000, 768, 0), (20000, 640, 2), (300, 192, 0)])
