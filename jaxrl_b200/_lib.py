@@ -163,6 +163,7 @@ def stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
 
-# Tuning knob for A/B runs: MPX_PDL=0 launches the rollout-chain kernels without programmatic dependent launch.
+# Tuning knob for A/B runs: MPX_PDL=<mask> selects the kernel families launched with programmatic dependent launch
+# (library default 12 = decode attention + fused GLU; 0 = none; bits in csrc/common.cuh).
 if os.environ.get("MPX_PDL") is not None:
     lib.mpx_debug_set(6, int(os.environ["MPX_PDL"]))

@@ -26,7 +26,7 @@ int num_sms() {
 }
 
 unsigned long long* g_dbg_stamps = nullptr;
-int g_use_pdl = 0;
+int g_use_pdl = 12;   // decode attention + fused GLU (trip 81: +1.5 % on the whole step; the encoder / policy-head bits lose)
 extern int g_debug_swap_lbo_sbo;
 extern int g_attn_decode_impl;
 extern int g_attn_train_impl;
