@@ -200,7 +200,8 @@ def decode_attention_roofline(trainer, peaks):
         if fused:
             pre = f"layers.{i}."
             ops.attn_decode_fused(x, eng.p[pre + "history_norm.scale"], eng.w[pre + "wt_qkv"], r.pos[t][:B], eng.timescale,
-                                  ws.kcache[i], ws.vcache[i], eng.Nq, eng.Nkv, eng.D, out=ws.ao)
+                                  ws.kcache[i], ws.vcache[i], eng.Nq, eng.Nkv, eng.D, out=ws.ao,
+                                  stable_history=eng.early_kv_stream)    # as the rollout launches it
         else:
             ops.attn_decode(ws.q, ws.kcache[i], ws.vcache[i], r.pos[t][:B], eng.Nq, eng.Nkv, eng.D, out=ws.ao)
 

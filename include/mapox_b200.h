@@ -193,6 +193,9 @@ typedef struct {
   mpx_bf16* kcache; mpx_bf16* vcache;
   mpx_bf16* out;
   int B, S, H, Nq, Nkv, D;
+  int flags;   /* bit 0: every ring slot except pos[0] % S was written by kernels that had COMPLETED before this launch
+                * could begin (in a rollout: earlier decode steps, with at least one fully serialised launch in between),
+                * so under programmatic dependent launch their stream may start before griddepcontrol.wait.  0 = safe. */
 } mpx_attn_decode_fused_args;
 int mpx_attn_decode_fused(const mpx_attn_decode_fused_args* a, mpx_stream_t stream);
 

@@ -65,7 +65,7 @@ AttnDecodeArgs = _struct("mpx_attn_decode_args", [
 AttnDecodeFusedArgs = _struct("mpx_attn_decode_fused_args", [
     ("x", c_p), ("norm_scale", c_p), ("eps", C.c_float), ("wt_qkv", c_p), ("pos", c_p), ("rope_timescale", c_p),
     ("kcache", c_p), ("vcache", c_p), ("out", c_p),
-    ("B", c_i), ("S", c_i), ("H", c_i), ("Nq", c_i), ("Nkv", c_i), ("D", c_i)])
+    ("B", c_i), ("S", c_i), ("H", c_i), ("Nq", c_i), ("Nkv", c_i), ("D", c_i), ("flags", c_i)])
 
 AttnTrainArgs = _struct("mpx_attn_train_args", [
     ("q", c_p), ("ldq", c_ll), ("k", c_p), ("ldk", c_ll), ("v", c_p), ("ldv", c_ll), ("o", c_p), ("ldo", c_ll),
@@ -165,5 +165,7 @@ def stream() -> int:
 
 # Tuning knob for A/B runs: MPX_PDL=<mask> selects the kernel families launched with programmatic dependent launch
 # (library default 12 = decode attention + fused GLU; 0 = none; bits in csrc/common.cuh).
+PDL_MASK = 12
 if os.environ.get("MPX_PDL") is not None:
-    lib.mpx_debug_set(6, int(os.environ["MPX_PDL"]))
+    PDL_MASK = int(os.environ["MPX_PDL"])
+    lib.mpx_debug_set(6, PDL_MASK)

@@ -70,7 +70,28 @@ struct AttnFusedParams {
   __nv_bfloat16* out;              // (B,128)
   int B, S;
   float scale_log2;
+  int early_stream;                // 1: ring slots other than pos % S are stable - their stream may start before griddepcontrol.wait
 };
+
+// one 32-position chunk of an agent's K and V rings -> stage (c % 4) of the warp's shared-memory ring (one commit group)
+__device__ __forceinline__ void af_issue_chunk(uint32_t ring, const __nv_bfloat16* kbase, const __nv_bfloat16* vbase, int c,
+                                               int nchunks, int kv_len, bool active, int lane) {
+  if (active && c < nchunks) {
+    const uint32_t st = ring + (c % AF_STAGES) * AF_STAGE_BYTES;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int pi = lane + 32 * (i & 3);
+      const int r = pi >> 2, j = pi & 3;
+      const int pp = c * AF_CHUNK + r;
+      const bool valid = pp < kv_len;
+      const __nv_bfloat16* gp = (i < 4 ? kbase : vbase) + (size_t)(valid ? pp : 0) * 32 + j * 8;
+      const uint32_t n = valid ? 16u : 0u;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                   ::"r"(st + (i < 4 ? 0 : AF_HALF) + af_off64(r, j)), "l"(gp), "r"(n) : "memory");
+    }
+  }
+  af_commit();
+}
 
 __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -107,12 +128,23 @@ __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedP
   }
   const int pos0 = p.pos[0];                     // positions are step inputs, never produced by the preceding kernel
   griddep_launch();
-  griddep_wait();                                // x and the rings are written by the previous kernels
-
   const int kv_len = min(pos0 + 1, p.S);
   const int nchunks = (kv_len + AF_CHUNK - 1) / AF_CHUNK;
   int slot = pos0 % p.S;
   if (slot < 0) slot += p.S;
+  // The caller vouches (early_stream) that every ring slot except pos % S was written by kernels that completed
+  // before this one could start (the rollout: earlier decode steps, with fully serialised launches in between).  Round
+  // 0's first chunks then leave for shared memory while the preceding kernel is still draining; the slot this step
+  // writes is patched into its stage below, whatever the early load brought for it.
+  if (p.early_stream) {
+    const int b = blockIdx.x * warps + warp;
+    const bool active = b < p.B;
+    const __nv_bfloat16* kbase = p.kcache + (size_t)(active ? b : 0) * p.S * 32;
+    const __nv_bfloat16* vbase = p.vcache + (size_t)(active ? b : 0) * p.S * 32;
+#pragma unroll
+    for (int i = 0; i < AF_STAGES - 1; ++i) af_issue_chunk(ring, kbase, vbase, i, nchunks, kv_len, active, lane);
+  }
+  griddep_wait();                                // x and the rings are written by the previous kernels
   const int c_new = slot >> 5, r_new = slot & 31;
   const bool head_lane = (2 * t) < G;
   const bool head1 = (2 * t + 1) < G;
@@ -144,26 +176,12 @@ __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedP
     const bool active = b < p.B;
     const __nv_bfloat16* kbase = p.kcache + (size_t)(active ? b : 0) * p.S * 32;
     const __nv_bfloat16* vbase = p.vcache + (size_t)(active ? b : 0) * p.S * 32;
-    auto issue = [&](int c) {
-      if (active && c < nchunks) {
-        const uint32_t st = ring + (c % AF_STAGES) * AF_STAGE_BYTES;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int pi = lane + 32 * (i & 3);
-          const int r = pi >> 2, j = pi & 3;
-          const int pp = c * AF_CHUNK + r;
-          const bool valid = pp < kv_len;
-          const __nv_bfloat16* gp = (i < 4 ? kbase : vbase) + (size_t)(valid ? pp : 0) * 32 + j * 8;
-          const uint32_t n = valid ? 16u : 0u;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
-                       ::"r"(st + (i < 4 ? 0 : AF_HALF) + af_off64(r, j)), "l"(gp), "r"(n) : "memory");
-        }
-      }
-      af_commit();
-    };
+    auto issue = [&](int c) { af_issue_chunk(ring, kbase, vbase, c, nchunks, kv_len, active, lane); };
     // ---- 1. the cache stream starts first: chunks 0..2 (the stale row at slot pos % S is patched below)
+    if (!(round == 0 && p.early_stream)) {
 #pragma unroll
-    for (int i = 0; i < AF_STAGES - 1; ++i) issue(i);
+      for (int i = 0; i < AF_STAGES - 1; ++i) issue(i);
+    }
     // every warp has left the previous round's loop: stage 3 of rings 0-2 is free for the scratch rows
     if (round > 0) __syncthreads();
     // ---- 2. RMSNorm of this agent's row -> xs[warp] (the row and the rotation angles were fetched a round ahead)
@@ -388,6 +406,7 @@ extern "C" int mpx_attn_decode_fused(const mpx_attn_decode_fused_args* a, mpx_st
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.B = a->B; p.S = a->S;
   p.scale_log2 = (1.0f / sqrtf((float)a->D)) * 1.4426950408889634f;
+  p.early_stream = (a->flags & 1) ? 1 : 0;
   cudaError_t le = launch_ex(attn_decode_fused_kernel, dim3(grid), dim3(best_w * 32), smem, (cudaStream_t)stream, 0, 4, p);
   if (le != cudaSuccess) {
     set_error("launch attn_decode_fused_kernel: %s", cudaGetErrorString(le));

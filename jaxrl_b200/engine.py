@@ -93,6 +93,9 @@ class PolicyEngine:
         self.obs_image = ops.obs_fused_image(self.dev) if self.fused_obs else None
         self.overlap_wgrad = os.environ.get("MPX_WGRAD_OVERLAP", "1") != "0"
         self.side = torch.cuda.Stream(device=self.dev) if (self.overlap_wgrad and self.dev.type == "cuda") else None
+        # trip 83: starting the cache stream before griddepcontrol.wait is correct (tested) but loses 0.5 ms of rollout
+        # (the early loads compete with the tail of the preceding GLU kernel): opt-in only
+        self.early_kv_stream = (_lib.PDL_MASK & ~12) == 0 and os.environ.get("MPX_EARLY_KV", "0") == "1"
         self.side2 = torch.cuda.Stream(device=self.dev) if self.side is not None else None     # early optimizer phase
         # trip 79: the encoder's weight gradients next to its data-gradient chain gain nothing (both HBM-bound,
         # 15.66 M vs 15.69 M env-steps/s), unlike the latency-bound Newton-Schulz launches: off by default
@@ -398,8 +401,12 @@ class PolicyEngine:
         for i in range(self.L):
             pre = f"layers.{i}."
             if self.fused_attn_decode:                        # pre-norm, projection, RoPE, ring write and attention: one kernel
+                # Only the attention / GLU kernels launch programmatically (default mask): the encoder and head kernels
+                # of every step are full stream barriers, so the ring slots of earlier steps are complete and visible
+                # before this launch can begin - their stream may start under the previous kernel's tail.
                 ops.attn_decode_fused(x, p[pre + "history_norm.scale"], w[pre + "wt_qkv"], pos, self.timescale,
-                                      ws.kcache[i], ws.vcache[i], self.Nq, self.Nkv, self.D, out=ws.ao)
+                                      ws.kcache[i], ws.vcache[i], self.Nq, self.Nkv, self.D, out=ws.ao,
+                                      stable_history=self.early_kv_stream)
             elif self.H == 128:                               # pre-norm fused into the q/k/v GEMM (shared-memory prologue)
                 ops.qkv_rope(x, w[pre + "wt_qkv"], pos, self.timescale, self.Nq, self.Nkv, self.D, q=ws.q,
                              k=ws.kcache[i], v=ws.vcache[i], k_row_stride=S * self.KD, v_row_stride=S * self.KD,

@@ -311,9 +311,11 @@ def attn_decode(q, kcache, vcache, pos, Nq: int, Nkv: int, D: int, out=None):
 
 
 def attn_decode_fused(x, norm_scale, wt_qkv, pos, timescale, kcache, vcache, Nq: int, Nkv: int, D: int, out=None,
-                      eps: float = 1e-6):
+                      eps: float = 1e-6, stable_history: bool = False):
     """history_norm + q/k/v projection + RoPE + ring write + decode attention in one kernel (H=128, Nq=4, Nkv=1, D=32).
-    kcache/vcache (B,S,Nkv,D) are updated in place at slot pos[0] % S; returns out (B, Nq*D)."""
+    kcache/vcache (B,S,Nkv,D) are updated in place at slot pos[0] % S; returns out (B, Nq*D).
+    stable_history: the caller guarantees that the other ring slots were written by kernels that completed before this
+    launch could start (flags bit 0 of the C ABI) - lets the cache stream start under the previous kernel's tail."""
     _req(x, BF16, "x"); _req(wt_qkv, BF16, "wt_qkv"); _req(kcache, BF16, "kcache"); _req(vcache, BF16, "vcache")
     _req(norm_scale, F32, "norm_scale"); _req(timescale, F32, "timescale")
     assert pos.dtype == I32 and pos.is_cuda
@@ -322,7 +324,7 @@ def attn_decode_fused(x, norm_scale, wt_qkv, pos, timescale, kcache, vcache, Nq:
     if out is None:
         out = torch.empty(B, Nq * D, dtype=BF16, device=x.device)
     a = _lib.AttnDecodeFusedArgs(ptr(x), ptr(norm_scale), eps, ptr(wt_qkv), ptr(pos), ptr(timescale), ptr(kcache),
-                                 ptr(vcache), ptr(out), B, S, H, Nq, Nkv, D)
+                                 ptr(vcache), ptr(out), B, S, H, Nq, Nkv, D, 1 if stable_history else 0)
     check(lib.mpx_attn_decode_fused(C.byref(a), stream()), "mpx_attn_decode_fused")
     return out
 

@@ -325,6 +325,31 @@ def test_attn_decode_fused(ops, step, S, Bb):
                       allow_frac=1e-3, max_err_frac=0.1)
 
 
+@pytest.mark.parametrize("step,S,Bb", [(0, 16, 3), (40, 64, 15), (300, 512, 4096), (511, 512, 130), (1029, 512, 2100)])
+def test_attn_decode_fused_early_stream(ops, step, S, Bb):
+    """flags bit 0 (ring history declared stable: its stream starts before griddepcontrol.wait) changes neither the
+    output nor the ring, bit for bit, also right behind a kernel that has just rewritten x."""
+    gen = g(step + S + Bb)
+    H, D, Nq, Nkv = 128, 32, 4, 1
+    x = (torch.randn(Bb, H, generator=gen) * 2).to(BF16).to(DEV)
+    scale = (1.0 + 0.2 * torch.randn(H, generator=gen)).to(DEV)
+    w = (torch.randn((Nq + 2 * Nkv) * D, H, generator=gen) / math.sqrt(H)).to(BF16).to(DEV)
+    kc0 = torch.randn(Bb, S, Nkv, D, generator=gen).to(BF16).to(DEV)
+    vc0 = torch.randn(Bb, S, Nkv, D, generator=gen).to(BF16).to(DEV)
+    pos = torch.full((Bb,), step, dtype=torch.int32, device=DEV)
+    ts = _rope_timescale(D).to(DEV)
+    res = []
+    for early in (False, True):
+        kc, vc = kc0.clone(), vc0.clone()
+        xin = torch.zeros_like(x)
+        xin.copy_(x)                                     # the producer of x is the kernel right before the launch
+        out = ops.attn_decode_fused(xin, scale, w, pos, ts, kc, vc, Nq, Nkv, D, stable_history=early)
+        torch.cuda.synchronize()
+        res.append((out.clone(), kc, vc))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
 def test_attn_decode_full_batch(ops):
     """Full-size shape (B=4096, S=512): persistent-warp striding covers every agent; bit-for-bit vs the SIMT kernel."""
     from jaxrl_b200._lib import lib
