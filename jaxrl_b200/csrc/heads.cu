@@ -47,6 +47,64 @@ __global__ void __launch_bounds__(256) embed_combine_kernel(
   }
 }
 
+// Same arithmetic, eight consecutive features per thread (H % 8 == 0, 16-byte aligned rows): one 16-byte load / store
+// of the activation row piece, the per-token scalars read once per thread, the fp32 parameter rows as float4 pairs.
+__global__ void __launch_bounds__(256) embed_combine8_kernel(
+    const __nv_bfloat16* __restrict__ obs_emb, const float* __restrict__ reward, const int32_t* __restrict__ last_action,
+    const int32_t* __restrict__ task_ids, const float* __restrict__ w_r, const float* __restrict__ b_r,
+    const float* __restrict__ a_table, int A, const float* __restrict__ t_table, int n_tasks,
+    __nv_bfloat16* __restrict__ x, long long M, int H) {
+  const float sq = bf16_round(sqrtf((float)H));
+  const unsigned per_row = (unsigned)H >> 3;
+  const unsigned total = (unsigned)(M * per_row);
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const unsigned m = i / per_row;
+    const int h = (int)(i % per_row) << 3;
+    const uint4 ov = *reinterpret_cast<const uint4*>(obs_emb + (size_t)m * H + h);
+    const float r = bf16_round(reward[m]);
+    int a = last_action[m];
+    if (a < 0) a += A;
+    const bool a_ok = a >= 0 && a < A;
+    int tk = -1;
+    if (task_ids && t_table) {
+      tk = task_ids[m];
+      if (tk < 0) tk += n_tasks;
+      if (tk >= n_tasks) tk = -1;
+    }
+    float o[8], wr[8], br[8], ar[8], tr[8];
+    o[0] = bf16_lo(ov.x); o[1] = bf16_hi(ov.x); o[2] = bf16_lo(ov.y); o[3] = bf16_hi(ov.y);
+    o[4] = bf16_lo(ov.z); o[5] = bf16_hi(ov.z); o[6] = bf16_lo(ov.w); o[7] = bf16_hi(ov.w);
+    *reinterpret_cast<float4*>(wr) = *reinterpret_cast<const float4*>(w_r + h);
+    *reinterpret_cast<float4*>(wr + 4) = *reinterpret_cast<const float4*>(w_r + h + 4);
+    *reinterpret_cast<float4*>(br) = *reinterpret_cast<const float4*>(b_r + h);
+    *reinterpret_cast<float4*>(br + 4) = *reinterpret_cast<const float4*>(b_r + h + 4);
+    if (a_ok) {
+      *reinterpret_cast<float4*>(ar) = *reinterpret_cast<const float4*>(a_table + (size_t)a * H + h);
+      *reinterpret_cast<float4*>(ar + 4) = *reinterpret_cast<const float4*>(a_table + (size_t)a * H + h + 4);
+    }
+    if (tk >= 0) {
+      *reinterpret_cast<float4*>(tr) = *reinterpret_cast<const float4*>(t_table + (size_t)tk * H + h);
+      *reinterpret_cast<float4*>(tr + 4) = *reinterpret_cast<const float4*>(t_table + (size_t)tk * H + h + 4);
+    }
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float re = bf16_round(r * bf16_round(wr[k]));
+      re = bf16_round(re + bf16_round(br[k]));
+      const float ae = bf16_round((a_ok ? bf16_round(ar[k]) : 0.f) * sq);
+      float t = bf16_round(o[k] + re);
+      t = bf16_round(t + ae);
+      if (task_ids && t_table) t = bf16_round(t + bf16_round((tk >= 0 ? bf16_round(tr[k]) : 0.f) * sq));
+      v[k] = t;
+    }
+    uint4 out;
+    out.x = pack_bf16(v[0], v[1]); out.y = pack_bf16(v[2], v[3]);
+    out.z = pack_bf16(v[4], v[5]); out.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(x + (size_t)m * H + h) = out;
+  }
+}
+
 // Transpose of embed_combine.  Each block reduces `rows_per_block` token rows; thread = feature column.
 // d_wr[h] += sum bf16(r) * dx ; d_br[h] += sum dx ; d_a_table[a][h] += sqrt(H) * dx ; same for tasks.
 __global__ void embed_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const float* __restrict__ reward,
@@ -441,7 +499,7 @@ __global__ void ppo_loss_finalize_kernel(const double* __restrict__ partials, in
 // One warp per token row, lane owns HPL = H/32 feature columns; dtable partials live in registers (AMAX x HPL),
 // meet in shared memory per block, one atomic per table entry per block.
 template <int AMAX, int HPL>
-__global__ void __launch_bounds__(HD_WARPS * 32) policy_head_bwd_kernel(
+__global__ void __launch_bounds__(HD_WARPS * 32, 3) policy_head_bwd_kernel(
     const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ x, const float* __restrict__ table,
     const __nv_bfloat16* __restrict__ dx_other, __nv_bfloat16* __restrict__ dx, float* __restrict__ dtable, long long M,
     int A) {
@@ -531,9 +589,18 @@ extern "C" int mpx_embed_combine(const mpx_bf16* obs_emb, const float* reward, c
   MPX_REQUIRE(obs_emb && reward && last_action && w_reward && b_reward && action_table && x && M > 0 && H > 0 && A > 0,
               "mpx_embed_combine: bad arguments");
   MPX_REQUIRE(M * H < (1LL << 31), "mpx_embed_combine: too many elements for 32-bit indexing");
-  embed_combine_kernel<<<grid_for(M * H, 256), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(obs_emb), reward, last_action, task_ids, w_reward, b_reward, action_table,
-      A, task_table, n_tasks, reinterpret_cast<__nv_bfloat16*>(x), M, H);
+  const bool vec8 = (H % 8 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(obs_emb) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_reward) |
+                      reinterpret_cast<uintptr_t>(b_reward) | reinterpret_cast<uintptr_t>(action_table) |
+                      reinterpret_cast<uintptr_t>(task_table)) & 15) == 0;
+  if (vec8)
+    embed_combine8_kernel<<<grid_for(M * (H / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(obs_emb), reward, last_action, task_ids, w_reward, b_reward, action_table,
+        A, task_table, n_tasks, reinterpret_cast<__nv_bfloat16*>(x), M, H);
+  else
+    embed_combine_kernel<<<grid_for(M * H, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(obs_emb), reward, last_action, task_ids, w_reward, b_reward, action_table,
+        A, task_table, n_tasks, reinterpret_cast<__nv_bfloat16*>(x), M, H);
   return check_launch("mpx_embed_combine");
 }
 
