@@ -161,6 +161,7 @@ __global__ void embed_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const flo
 // 8 lanes per token (4 tokens per warp): logits[a] = sum_h f32(x[h]) * table[a][h]; masked entries -> finfo(f32).min.
 // Each lane owns H/8 consecutive features (16-byte loads); the A partial sums are reduced over the 8 lanes with 3
 // xor-shuffles each.
+template <int AMAX>
 __global__ void __launch_bounds__(HD_WARPS * 32) policy_logits_kernel(
     const __nv_bfloat16* __restrict__ x, const float* __restrict__ table, const uint8_t* __restrict__ mask,
     float* __restrict__ logits, long long M, int H, int A) {
@@ -176,46 +177,61 @@ __global__ void __launch_bounds__(HD_WARPS * 32) policy_logits_kernel(
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int sub = lane & 7, rsel = lane >> 3;
-  long long row = ((long long)blockIdx.x * HD_WARPS + (threadIdx.x >> 5)) * 4 + rsel;
-  const long long stride = (long long)gridDim.x * HD_WARPS * 4;
-  for (long long base = row - rsel; base < M; base += stride) {
-    row = base + rsel;
-    float part[MAX_A];
+  // two tokens per 8-lane group and iteration (rows base + rsel and base + 4 + rsel): every table float4 read from
+  // shared memory feeds both (the kernel is bound by those reads)
+  const long long stride = (long long)gridDim.x * HD_WARPS * 8;
+  for (long long base = ((long long)blockIdx.x * HD_WARPS + (threadIdx.x >> 5)) * 8; base < M; base += stride) {
+    const long long row0 = base + rsel, row1 = base + 4 + rsel;
+    float p0[AMAX], p1[AMAX];
 #pragma unroll
-    for (int a = 0; a < MAX_A; ++a) part[a] = 0.f;
-    if (row < M) {
-      for (int c = 0; c < per; c += 8) {
-        const uint4 v = *reinterpret_cast<const uint4*>(x + row * H + sub * per + c);
-        const float xf[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
-                             bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+    for (int a = 0; a < AMAX; ++a) p0[a] = p1[a] = 0.f;
+    for (int c = 0; c < per; c += 8) {
+      const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+      const uint4 v0 = row0 < M ? *reinterpret_cast<const uint4*>(x + row0 * H + sub * per + c) : z4;
+      const uint4 v1 = row1 < M ? *reinterpret_cast<const uint4*>(x + row1 * H + sub * per + c) : z4;
+      const float xa[8] = {bf16_lo(v0.x), bf16_hi(v0.x), bf16_lo(v0.y), bf16_hi(v0.y),
+                           bf16_lo(v0.z), bf16_hi(v0.z), bf16_lo(v0.w), bf16_hi(v0.w)};
+      const float xb[8] = {bf16_lo(v1.x), bf16_hi(v1.x), bf16_lo(v1.y), bf16_hi(v1.y),
+                           bf16_lo(v1.z), bf16_hi(v1.z), bf16_lo(v1.w), bf16_hi(v1.w)};
 #pragma unroll
-        for (int a = 0; a < MAX_A; ++a) {
-          if (a < A) {
-            const float4* tr = reinterpret_cast<const float4*>(s_table + a * astride + sub * pstride + c);
-            const float4 t0 = tr[0], t1 = tr[1];
-            part[a] = fmaf(xf[0], t0.x, part[a]); part[a] = fmaf(xf[1], t0.y, part[a]);
-            part[a] = fmaf(xf[2], t0.z, part[a]); part[a] = fmaf(xf[3], t0.w, part[a]);
-            part[a] = fmaf(xf[4], t1.x, part[a]); part[a] = fmaf(xf[5], t1.y, part[a]);
-            part[a] = fmaf(xf[6], t1.z, part[a]); part[a] = fmaf(xf[7], t1.w, part[a]);
-          }
+      for (int a = 0; a < AMAX; ++a) {
+        if (a < A) {
+          const float4* tr = reinterpret_cast<const float4*>(s_table + a * astride + sub * pstride + c);
+          const float4 t0 = tr[0], t1 = tr[1];
+          p0[a] = fmaf(xa[0], t0.x, p0[a]); p0[a] = fmaf(xa[1], t0.y, p0[a]);
+          p0[a] = fmaf(xa[2], t0.z, p0[a]); p0[a] = fmaf(xa[3], t0.w, p0[a]);
+          p0[a] = fmaf(xa[4], t1.x, p0[a]); p0[a] = fmaf(xa[5], t1.y, p0[a]);
+          p0[a] = fmaf(xa[6], t1.z, p0[a]); p0[a] = fmaf(xa[7], t1.w, p0[a]);
+          p1[a] = fmaf(xb[0], t0.x, p1[a]); p1[a] = fmaf(xb[1], t0.y, p1[a]);
+          p1[a] = fmaf(xb[2], t0.z, p1[a]); p1[a] = fmaf(xb[3], t0.w, p1[a]);
+          p1[a] = fmaf(xb[4], t1.x, p1[a]); p1[a] = fmaf(xb[5], t1.y, p1[a]);
+          p1[a] = fmaf(xb[6], t1.z, p1[a]); p1[a] = fmaf(xb[7], t1.w, p1[a]);
         }
       }
     }
 #pragma unroll
-    for (int a = 0; a < MAX_A; ++a) {
+    for (int a = 0; a < AMAX; ++a) {
       if (a < A) {
-        part[a] += __shfl_xor_sync(0xffffffffu, part[a], 1);
-        part[a] += __shfl_xor_sync(0xffffffffu, part[a], 2);
-        part[a] += __shfl_xor_sync(0xffffffffu, part[a], 4);
+        p0[a] += __shfl_xor_sync(0xffffffffu, p0[a], 1);
+        p1[a] += __shfl_xor_sync(0xffffffffu, p1[a], 1);
+        p0[a] += __shfl_xor_sync(0xffffffffu, p0[a], 2);
+        p1[a] += __shfl_xor_sync(0xffffffffu, p1[a], 2);
+        p0[a] += __shfl_xor_sync(0xffffffffu, p0[a], 4);
+        p1[a] += __shfl_xor_sync(0xffffffffu, p1[a], 4);
       }
     }
-    if (row < M) {
 #pragma unroll
-      for (int a = 0; a < MAX_A; ++a) {
-        if (a < A && (a & 7) == sub) {
-          float v = part[a];
-          if (mask && !mask[row * A + a]) v = -3.4028234663852886e38f;
-          logits[row * A + a] = v;
+    for (int a = 0; a < AMAX; ++a) {
+      if (a < A && (a & 7) == sub) {
+        if (row0 < M) {
+          float v = p0[a];
+          if (mask && !mask[row0 * A + a]) v = -3.4028234663852886e38f;
+          logits[row0 * A + a] = v;
+        }
+        if (row1 < M) {
+          float v = p1[a];
+          if (mask && !mask[row1 * A + a]) v = -3.4028234663852886e38f;
+          logits[row1 * A + a] = v;
         }
       }
     }
@@ -499,7 +515,7 @@ __global__ void ppo_loss_finalize_kernel(const double* __restrict__ partials, in
 // One warp per token row, lane owns HPL = H/32 feature columns; dtable partials live in registers (AMAX x HPL),
 // meet in shared memory per block, one atomic per table entry per block.
 template <int AMAX, int HPL>
-__global__ void __launch_bounds__(HD_WARPS * 32, 3) policy_head_bwd_kernel(
+__global__ void __launch_bounds__(HD_WARPS * 32, (AMAX * HPL <= 32) ? 3 : 1) policy_head_bwd_kernel(
     const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ x, const float* __restrict__ table,
     const __nv_bfloat16* __restrict__ dx_other, __nv_bfloat16* __restrict__ dx, float* __restrict__ dtable, long long M,
     int A) {
@@ -520,53 +536,106 @@ __global__ void __launch_bounds__(HD_WARPS * 32, 3) policy_head_bwd_kernel(
     for (int j = 0; j < HPL; ++j) dt[a][j] = 0.f;
   long long row = (long long)blockIdx.x * HD_WARPS + (threadIdx.x >> 5);
   const long long stride = (long long)gridDim.x * HD_WARPS;
-  // the next row's operands are fetched while the current row is multiplied (the loop is otherwise a chain of
-  // dependent global loads: one row of latency per iteration)
-  float xn[HPL], on[HPL], dn = 0.f;
-  auto fetch = [&](long long r) {
-    if (r < M) {
-#pragma unroll
-      for (int j = 0; j < HPL; ++j) {
-        xn[j] = __bfloat162float(x[r * H + j * 32 + lane]);
-        on[j] = dx_other ? __bfloat162float(dx_other[r * H + j * 32 + lane]) : 0.f;
+  if constexpr (HPL == 4) {
+    // H = 128: lane owns the 4 CONSECUTIVE columns [4 lane, 4 lane + 4) - one 8-byte load per operand row, one 8-byte
+    // store, the table as one float4 per action.  The operands of the next TWO rows are in flight while the current
+    // row is multiplied (the loop is otherwise one row of global-load latency per iteration).
+    uint2 xq[2], oq[2];
+    float dq[2];
+    auto fetch = [&](long long r, int slot) {
+      xq[slot] = make_uint2(0u, 0u); oq[slot] = make_uint2(0u, 0u); dq[slot] = 0.f;
+      if (r < M) {
+        xq[slot] = *reinterpret_cast<const uint2*>(x + r * H + 4 * lane);
+        if (dx_other) oq[slot] = *reinterpret_cast<const uint2*>(dx_other + r * H + 4 * lane);
+        dq[slot] = lane < A ? dlogits[r * A + lane] : 0.f;
       }
-      dn = lane < A ? dlogits[r * A + lane] : 0.f;
-    }
-  };
-  fetch(row);
-  for (; row < M; row += stride) {
-    float xv[HPL], ov[HPL], acc[HPL];
+    };
+    fetch(row, 0);
+    fetch(row + stride, 1);
+    for (; row < M; row += 2 * stride) {
 #pragma unroll
-    for (int j = 0; j < HPL; ++j) {
-      xv[j] = xn[j];
-      ov[j] = on[j];
-      acc[j] = 0.f;
-    }
-    const float dl_mine = dn;
-    fetch(row + stride);
+      for (int ph = 0; ph < 2; ++ph) {
+        const long long r = row + ph * stride;
+        const uint2 xw = xq[ph], ow = oq[ph];
+        const float dl_mine = dq[ph];
+        fetch(r + 2 * stride, ph);
+        if (r < M) {
+          const float xv[4] = {bf16_lo(xw.x), bf16_hi(xw.x), bf16_lo(xw.y), bf16_hi(xw.y)};
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int a = 0; a < AMAX; ++a) {
-      if (a < A) {
-        const float d = __shfl_sync(0xffffffffu, dl_mine, a);
+          for (int a = 0; a < AMAX; ++a) {
+            if (a < A) {
+              const float d = __shfl_sync(0xffffffffu, dl_mine, a);
+              const float4 tv = *reinterpret_cast<const float4*>(s_table + a * H + 4 * lane);
+              acc[0] = fmaf(d, tv.x, acc[0]); acc[1] = fmaf(d, tv.y, acc[1]);
+              acc[2] = fmaf(d, tv.z, acc[2]); acc[3] = fmaf(d, tv.w, acc[3]);
 #pragma unroll
-        for (int j = 0; j < HPL; ++j) {
-          acc[j] = fmaf(d, s_table[a * H + j * 32 + lane], acc[j]);
-          dt[a][j] = fmaf(d, xv[j], dt[a][j]);
+              for (int j = 0; j < 4; ++j) dt[a][j] = fmaf(d, xv[j], dt[a][j]);
+            }
+          }
+          float o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = bf16_round(acc[j]);
+          if (dx_other) {
+            o[0] += bf16_lo(ow.x); o[1] += bf16_hi(ow.x); o[2] += bf16_lo(ow.y); o[3] += bf16_hi(ow.y);
+          }
+          *reinterpret_cast<uint2*>(dx + r * H + 4 * lane) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
         }
       }
     }
 #pragma unroll
-    for (int j = 0; j < HPL; ++j) {
-      float o = bf16_round(acc[j]);
-      if (dx_other) o += ov[j];
-      dx[row * H + j * 32 + lane] = __float2bfloat16_rn(o);
+    for (int a = 0; a < AMAX; ++a)
+      if (a < A)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(&s_red[a * H + 4 * lane + j], dt[a][j]);
+  } else {
+    // the next row's operands are fetched while the current row is multiplied
+    float xn[HPL], on[HPL], dn = 0.f;
+    auto fetch = [&](long long r) {
+      if (r < M) {
+#pragma unroll
+        for (int j = 0; j < HPL; ++j) {
+          xn[j] = __bfloat162float(x[r * H + j * 32 + lane]);
+          on[j] = dx_other ? __bfloat162float(dx_other[r * H + j * 32 + lane]) : 0.f;
+        }
+        dn = lane < A ? dlogits[r * A + lane] : 0.f;
+      }
+    };
+    fetch(row);
+    for (; row < M; row += stride) {
+      float xv[HPL], ov[HPL], acc[HPL];
+#pragma unroll
+      for (int j = 0; j < HPL; ++j) {
+        xv[j] = xn[j];
+        ov[j] = on[j];
+        acc[j] = 0.f;
+      }
+      const float dl_mine = dn;
+      fetch(row + stride);
+#pragma unroll
+      for (int a = 0; a < AMAX; ++a) {
+        if (a < A) {
+          const float d = __shfl_sync(0xffffffffu, dl_mine, a);
+#pragma unroll
+          for (int j = 0; j < HPL; ++j) {
+            acc[j] = fmaf(d, s_table[a * H + j * 32 + lane], acc[j]);
+            dt[a][j] = fmaf(d, xv[j], dt[a][j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < HPL; ++j) {
+        float o = bf16_round(acc[j]);
+        if (dx_other) o += ov[j];
+        dx[row * H + j * 32 + lane] = __float2bfloat16_rn(o);
+      }
     }
+#pragma unroll
+    for (int a = 0; a < AMAX; ++a)
+      if (a < A)
+#pragma unroll
+        for (int j = 0; j < HPL; ++j) atomicAdd(&s_red[a * H + j * 32 + lane], dt[a][j]);
   }
-#pragma unroll
-  for (int a = 0; a < AMAX; ++a)
-    if (a < A)
-#pragma unroll
-      for (int j = 0; j < HPL; ++j) atomicAdd(&s_red[a * H + j * 32 + lane], dt[a][j]);
   __syncthreads();
   for (int i = threadIdx.x; i < A * H; i += blockDim.x) atomicAdd(dtable + i, s_red[i]);
 }
@@ -628,8 +697,12 @@ extern "C" int mpx_policy_logits(const mpx_bf16* x, const float* table, const ui
   MPX_REQUIRE(H % 64 == 0, "mpx_policy_logits: H=%d must be a multiple of 64", H);
   const size_t smem = (size_t)A * (H + 32) * sizeof(float);      // 4-float pad per lane slot
   MPX_REQUIRE(smem <= 48 * 1024, "mpx_policy_logits: table too large for shared memory");
-  policy_logits_kernel<<<grid_for(M, HD_WARPS * 4, 8), HD_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), table, action_mask, logits, M, H, A);
+  if (A <= 8)
+    policy_logits_kernel<8><<<grid_for(M, HD_WARPS * 8, 8), HD_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), table, action_mask, logits, M, H, A);
+  else
+    policy_logits_kernel<MAX_A><<<grid_for(M, HD_WARPS * 8, 8), HD_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), table, action_mask, logits, M, H, A);
   return check_launch("mpx_policy_logits");
 }
 

@@ -452,6 +452,17 @@ def test_rope_inverse_is_transpose(ops):
     assert_close_bf16(xd[:, :nh * D], x[:, :nh * D], "rope inverse(rope(x)) == x", rtol=2e-2, abs_floor_frac=1e-2)
 
 
+@pytest.mark.parametrize("M,A", [(3003, 8), (5, 3), (4097, 12), (131072, 8)])
+def test_policy_logits_shapes(ops, M, A):
+    """Two tokens per lane group and iteration: ragged tails, the A <= 8 and generic instantiations, no mask."""
+    gen = g(M + A)
+    H = 128
+    x = torch.randn(M, H, generator=gen).to(BF16)
+    table = torch.randn(A, H, generator=gen) * 0.1
+    logits = ops.policy_logits(x.to(DEV), table.to(DEV), None)
+    torch.testing.assert_close(logits.cpu(), x.float() @ table.t(), rtol=1e-4, atol=1e-4)
+
+
 def test_policy_logits_and_ppo_loss(ops):
     gen = g(31)
     M, H, A = 3000, 128, 6
@@ -479,6 +490,22 @@ def test_policy_logits_and_ppo_loss(ops):
     dx = ops.policy_head_bwd(dl, x.to(DEV), table.to(DEV), dtable)
     assert_close_bf16(dx, dl.cpu() @ table, "policy_head_bwd dx", rtol=2e-2, abs_floor_frac=1e-2)
     torch.testing.assert_close(dtable.cpu(), dl.cpu().t() @ x.float(), rtol=1e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("M,H,A", [(3001, 128, 8), (7, 128, 5), (70001, 128, 8), (2000, 256, 6), (1500, 128, 12)])
+def test_policy_head_bwd_shapes(ops, M, H, A):
+    """Tied-table transpose with the value path's cotangent added (dx_other): H = 128 takes the 4-consecutive-column
+    path with two rows in flight (ragged M), other widths the strided path."""
+    gen = g(M + H + A)
+    x = torch.randn(M, H, generator=gen).to(BF16)
+    table = torch.randn(A, H, generator=gen) * 0.1
+    dl = torch.randn(M, A, generator=gen) * 0.01
+    other = (torch.randn(M, H, generator=gen) * 0.01).to(BF16)
+    dtable = torch.zeros(A, H, dtype=torch.float32, device=DEV)
+    dx = ops.policy_head_bwd(dl.to(DEV), x.to(DEV), table.to(DEV), dtable, dx_other=other.to(DEV))
+    ref = ((dl @ table).to(BF16).float() + other.float()).to(BF16)
+    assert_close_bf16(dx, ref, f"policy_head_bwd dx M={M} H={H} A={A}", rtol=2e-2, abs_floor_frac=1e-2)
+    torch.testing.assert_close(dtable.cpu(), dl.t() @ x.float(), rtol=2e-3, atol=2e-5)
 
 
 def test_value_head_hilo(ops):
