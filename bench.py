@@ -165,8 +165,9 @@ def reference_arm(args, run):
 def count_launches(trainer) -> int:
     """Kernel launches of OUR library in one PPO update (counted from the C-ABI calls of one eager pass)."""
     from jaxrl_b200 import _lib
-    per_call = {"mpx_gae": 2, "mpx_hlgauss_loss": 2, "mpx_ppo_policy_loss": 2, "mpx_adamw_step": 3,
-                "mpx_attn_train_bwd": 3, "mpx_muon_step": 21}
+    # muon: prepare + 3 x 5 Newton-Schulz GEMMs + finish (phase 1), AdamW leaves + clip/apply (phase 2)
+    per_call = {"mpx_gae": 2, "mpx_hlgauss_loss": 2, "mpx_ppo_policy_loss": 2, "mpx_adamw_step": 2,
+                "mpx_attn_train_bwd": 3, "mpx_muon_step:1": 17, "mpx_muon_step:2": 2, "mpx_muon_step:3": 19}
     counts = {"n": 0}
     orig = _lib.check
 

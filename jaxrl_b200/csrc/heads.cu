@@ -157,6 +157,93 @@ __global__ void embed_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const flo
       if (s_tab[A * H + i] != 0.f) atomicAdd(d_t_table + i, s_tab[A * H + i]);
 }
 
+// H % 8 == 0: thread = (row group, 8 consecutive feature columns).  One 16-byte load per row piece, the per-token
+// scalars once per 8 features, four rows in flight per thread; every row group accumulates the table rows in its own
+// shared-memory copy (no races, no shared atomics), the copies meet at the end.
+constexpr int EB_THREADS = 128;
+__global__ void __launch_bounds__(EB_THREADS) embed_bwd8_kernel(
+    const __nv_bfloat16* __restrict__ dx, const float* __restrict__ reward, const int32_t* __restrict__ last_action,
+    const int32_t* __restrict__ task_ids, int A, int n_tasks, float* __restrict__ d_wr, float* __restrict__ d_br,
+    float* __restrict__ d_a_table, float* __restrict__ d_t_table, long long M, int H, int rows_per_block) {
+  extern __shared__ __align__(16) float s_tab8[];   // [nrg][ntab][H] then [nrg][2][H] for the reward kernel / bias
+  const int ncg = H >> 3, nrg = EB_THREADS / ncg;
+  const int ntab = A + (d_t_table ? n_tasks : 0);
+  const int cg = threadIdx.x % ncg, rg = threadIdx.x / ncg;
+  float* tab = s_tab8 + (size_t)rg * ntab * H + 8 * cg;
+  for (int i = threadIdx.x; i < nrg * (ntab + 2) * H; i += EB_THREADS) s_tab8[i] = 0.f;
+  __syncthreads();
+  const float sq = bf16_round(sqrtf((float)H));
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(M, r0 + (long long)rows_per_block);
+  float awr[8], abr[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) awr[k] = abr[k] = 0.f;
+  if (rg < nrg) {
+    for (long long m0 = r0 + rg; m0 < r1; m0 += 4 * nrg) {
+      uint4 gv[4];
+      float rv[4];
+      int av[4], tv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                          // independent loads first
+        const long long m = m0 + (long long)u * nrg;
+        const bool ok = m < r1;
+        gv[u] = ok ? *reinterpret_cast<const uint4*>(dx + m * H + 8 * cg) : make_uint4(0u, 0u, 0u, 0u);
+        rv[u] = ok ? reward[m] : 0.f;
+        av[u] = ok ? last_action[m] : A;                     // A = out of range: no table row
+        tv[u] = (ok && d_t_table) ? task_ids[m] : n_tasks;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float g[8] = {bf16_lo(gv[u].x), bf16_hi(gv[u].x), bf16_lo(gv[u].y), bf16_hi(gv[u].y),
+                            bf16_lo(gv[u].z), bf16_hi(gv[u].z), bf16_lo(gv[u].w), bf16_hi(gv[u].w)};
+        const float rb = bf16_round(rv[u]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          awr[k] = fmaf(rb, g[k], awr[k]);
+          abr[k] += g[k];
+        }
+        int a = av[u];
+        if (a < 0) a += A;
+        if (a >= 0 && a < A) {
+          float4* t4 = reinterpret_cast<float4*>(tab + a * H);
+          float4 t0 = t4[0], t1 = t4[1];
+          t0.x = fmaf(g[0], sq, t0.x); t0.y = fmaf(g[1], sq, t0.y); t0.z = fmaf(g[2], sq, t0.z); t0.w = fmaf(g[3], sq, t0.w);
+          t1.x = fmaf(g[4], sq, t1.x); t1.y = fmaf(g[5], sq, t1.y); t1.z = fmaf(g[6], sq, t1.z); t1.w = fmaf(g[7], sq, t1.w);
+          t4[0] = t0; t4[1] = t1;
+        }
+        if (d_t_table) {
+          int tk = tv[u];
+          if (tk < 0) tk += n_tasks;
+          if (tk >= 0 && tk < n_tasks) {
+            float4* t4 = reinterpret_cast<float4*>(tab + (A + tk) * H);
+            float4 t0 = t4[0], t1 = t4[1];
+            t0.x = fmaf(g[0], sq, t0.x); t0.y = fmaf(g[1], sq, t0.y); t0.z = fmaf(g[2], sq, t0.z); t0.w = fmaf(g[3], sq, t0.w);
+            t1.x = fmaf(g[4], sq, t1.x); t1.y = fmaf(g[5], sq, t1.y); t1.z = fmaf(g[6], sq, t1.z); t1.w = fmaf(g[7], sq, t1.w);
+            t4[0] = t0; t4[1] = t1;
+          }
+        }
+      }
+    }
+    float* wb = s_tab8 + (size_t)nrg * ntab * H + (size_t)rg * 2 * H + 8 * cg;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      wb[k] = awr[k];
+      wb[H + k] = abr[k];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ntab * H; i += EB_THREADS) {
+    float v = 0.f;
+    for (int r = 0; r < nrg; ++r) v += s_tab8[(size_t)r * ntab * H + i];
+    if (v != 0.f) atomicAdd((i < A * H ? d_a_table : d_t_table - A * H) + i, v);
+  }
+  for (int i = threadIdx.x; i < 2 * H; i += EB_THREADS) {
+    float v = 0.f;
+    for (int r = 0; r < nrg; ++r) v += s_tab8[(size_t)nrg * ntab * H + (size_t)r * 2 * H + i];
+    atomicAdd((i < H ? d_wr : d_br - H) + i, v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ policy logits
 // 8 lanes per token (4 tokens per warp): logits[a] = sum_h f32(x[h]) * table[a][h]; masked entries -> finfo(f32).min.
 // Each lane owns H/8 consecutive features (16-byte loads); the A partial sums are reduced over the 8 lanes with 3
@@ -679,6 +766,20 @@ extern "C" int mpx_embed_bwd(const mpx_bf16* dx, const float* reward, const int3
   MPX_REQUIRE(dx && reward && last_action && d_w_reward && d_b_reward && d_action_table && M > 0 && H > 0 && A > 0,
               "mpx_embed_bwd: bad arguments");
   MPX_REQUIRE(!d_task_table || task_ids, "mpx_embed_bwd: task table gradient requested without task ids");
+  {
+    const int ntab = A + (d_task_table ? n_tasks : 0);
+    const int ncg = H / 8;
+    const size_t smem8 = (H % 8 == 0 && ncg <= EB_THREADS && EB_THREADS % ncg == 0)
+                             ? (size_t)(EB_THREADS / ncg) * (ntab + 2) * H * sizeof(float) : 0;
+    if (smem8 > 0 && smem8 <= 48 * 1024 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
+      int rows8 = (int)((M + (long long)num_sms() * 4 - 1) / ((long long)num_sms() * 4));
+      if (rows8 < 128) rows8 = 128;
+      embed_bwd8_kernel<<<(int)((M + rows8 - 1) / rows8), EB_THREADS, smem8, (cudaStream_t)stream>>>(
+          reinterpret_cast<const __nv_bfloat16*>(dx), reward, last_action, task_ids, A, n_tasks, d_w_reward, d_b_reward,
+          d_action_table, d_task_table, M, H, rows8);
+      return check_launch("mpx_embed_bwd");
+    }
+  }
   int rows = (int)((M + (long long)num_sms() * 8 - 1) / ((long long)num_sms() * 8));
   if (rows < 64) rows = 64;
   const int grid = (int)((M + rows - 1) / rows);

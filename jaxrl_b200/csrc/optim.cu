@@ -65,9 +65,9 @@ __global__ void __launch_bounds__(256) apply_update_kernel(float* __restrict__ p
   for (; i < n; i += stride) p[i] += upd[i] * scale;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (norm_out) norm_out[0] = norm;
+    step[0] += 1;          // nothing in this kernel reads the counter; the update kernels before it already have
   }
 }
-__global__ void step_inc_kernel(int* step) { step[0] += 1; }
 
 // ------------------------------------------------------------------------------------------------ weight staging
 __global__ void prep_weights_kernel(const mpx_prep_desc* __restrict__ descs, int ndesc) {
@@ -398,7 +398,6 @@ extern "C" int mpx_adamw_step(float* params, const float* grads, float* mu, floa
   adamw_update_kernel<<<grid, 256, 0, s>>>(params, grads, mu, nu, update_scratch, n, step, lr0, total_steps, b1, b2, eps,
                                            weight_decay, grad_scale, 0, partials);
   apply_update_kernel<<<grid, 256, 0, s>>>(params, update_scratch, n, partials, grid, max_norm, step, update_norm_out);
-  step_inc_kernel<<<1, 1, 0, s>>>(step);
   return check_launch("mpx_adamw_step");
 }
 
@@ -464,8 +463,7 @@ extern "C" int mpx_muon_step_phased(float* params, const float* grads, float* mu
   if (phases & 2) {
     const int pgrid = opt_grid(n);
     apply_update_kernel<<<pgrid, 256, 0, s>>>(params, update_scratch, n, partials, nparts, max_norm, step, update_norm_out);
-    step_inc_kernel<<<1, 1, 0, s>>>(step);
-  }
+    }
   return check_launch("mpx_muon_step");
 }
 

@@ -546,7 +546,7 @@ def muon_step(params, grads, mu, nu, scratch, n_adam: int, table, nmat: int, x_t
     check(lib.mpx_muon_step_phased(ptr(params), ptr(grads), ptr(mu), ptr(nu), ptr(scratch), n, n_adam, ptr(table), nmat,
                                    x_total, a_total, max_r, max_c, ptr(ns_ws), ptr(step), lr0, float(total_steps), b1, b2,
                                    eps, wd, muon_beta, ns_steps, max_norm, grad_scale, ptr(norm_out), ptr(ws), phases,
-                                   stream()), "mpx_muon_step")
+                                   stream()), f"mpx_muon_step:{phases}")
 
 
 def prep_weights(descs_device, ndesc: int):

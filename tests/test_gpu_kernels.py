@@ -508,6 +508,39 @@ def test_policy_head_bwd_shapes(ops, M, H, A):
     torch.testing.assert_close(dtable.cpu(), dl.t() @ x.float(), rtol=2e-3, atol=2e-5)
 
 
+@pytest.mark.parametrize("M,H,A,NT", [(5000, 128, 8, 0), (131, 128, 6, 3), (70003, 128, 8, 0), (900, 256, 8, 4), (333, 64, 5, 2)])
+def test_embed_bwd(ops, M, H, A, NT):
+    """Transpose of the embedding sum (network.py:303-309): reward kernel / bias and the action / task table rows, with
+    wrapped negative and out-of-range indices (jnp.take mode=fill), accumulated INTO the gradient buffers.  H = 128 and
+    64 take the 8-columns-per-thread kernel, H = 256 with task rows the column-per-thread one."""
+    gen = g(M + H + A + NT)
+    dx = (torch.randn(M, H, generator=gen) * 0.1).to(BF16)
+    reward = torch.randn(M, generator=gen)
+    act = torch.randint(-2, A + 2, (M,), generator=gen).to(torch.int32)
+    task = torch.randint(-1, NT + 1, (M,), generator=gen).to(torch.int32) if NT else None
+    d_wr = torch.full((H,), 0.5, device=DEV)
+    d_br = torch.full((H,), -0.25, device=DEV)
+    d_at = torch.full((A, H), 1.0, device=DEV)
+    d_tt = torch.full((NT, H), 2.0, device=DEV) if NT else None
+    ops.embed_bwd(dx.to(DEV), reward.to(DEV), act.to(DEV), task.to(DEV) if NT else None, A, NT, d_wr, d_br, d_at, d_tt)
+    g32 = dx.double()
+    sq = float(torch.tensor(math.sqrt(H)).to(BF16))
+    rb = reward.to(BF16).double()
+    torch.testing.assert_close(d_wr.cpu().double(), 0.5 + (rb[:, None] * g32).sum(0), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(d_br.cpu().double(), -0.25 + g32.sum(0), rtol=1e-4, atol=1e-4)
+
+    def table_ref(idx, n, base):
+        idx = idx.long()
+        idx = torch.where(idx < 0, idx + n, idx)
+        ref = torch.full((n, H), base, dtype=torch.float64)
+        ok = (idx >= 0) & (idx < n)
+        ref.index_add_(0, idx[ok], g32[ok] * sq)
+        return ref
+    torch.testing.assert_close(d_at.cpu().double(), table_ref(act, A, 1.0), rtol=1e-4, atol=1e-4)
+    if NT:
+        torch.testing.assert_close(d_tt.cpu().double(), table_ref(task, NT, 2.0), rtol=1e-4, atol=1e-4)
+
+
 def test_value_head_hilo(ops):
     """fp32-weight Linear emulated with a bf16 hi/lo split (values.py:34): ~fp32 accuracy on bf16 activations."""
     gen = g(41)
