@@ -96,6 +96,10 @@ class PolicyEngine:
         # trip 83: starting the cache stream before griddepcontrol.wait is correct (tested) but loses 0.5 ms of rollout
         # (the early loads compete with the tail of the preceding GLU kernel): opt-in only
         self.early_kv_stream = (_lib.PDL_MASK & ~12) == 0 and os.environ.get("MPX_EARLY_KV", "0") == "1"
+        # mpx_linear act=2 (gelu transpose in the dgrad GEMM epilogue) is bit-identical to linear + gelu_bwd but its
+        # epilogue cannot use the TMA-store path (the pre-activation tile shares the transposer's shared memory): under ncu
+        # the fused launches cost 184 + 124 us against 51 + 93 and 44 + 35 us for the pairs (trip 89) - off by default
+        self.fuse_gelu_t = os.environ.get("MPX_FUSE_GELU_T", "0") == "1"
         self.side2 = torch.cuda.Stream(device=self.dev) if self.side is not None else None     # early optimizer phase
         # trip 79: the encoder's weight gradients next to its data-gradient chain gain nothing (both HBM-bound,
         # 15.66 M vs 15.69 M env-steps/s), unlike the latency-bound Newton-Schulz launches: off by default
@@ -371,10 +375,12 @@ class PolicyEngine:
             ev = run(_wg)
             if c.j == 0:
                 break
-            if last:       # the layer below is never the last one: its gelu transpose rides in the GEMM epilogue
+            if last and self.fuse_gelu_t:   # the layer below is never the last one: gelu transpose in the GEMM epilogue
                 ops.linear(dy, w[f"w_c{c.j}"], out=ws.dca[c.j - 1].view(M, c.k), M=rows,
                            residual=ws.cz[c.j - 1].view(M, c.k), act=2)
                 fused_gelu = True
+            elif last:
+                ops.linear(dy, w[f"w_c{c.j}"], out=ws.dca[c.j - 1].view(M, c.k), M=rows)
             else:
                 ops.linear(dy, w[f"w_c{c.j}"], out=ws.dcx[c.j], M=rows)
                 # the layer below is never the last one: its gelu transpose rides along with the scatter-sum
@@ -559,7 +565,11 @@ class PolicyEngine:
             ops.linear_wgrad(ws.pv, ws.dvl, p.g("value_head.dense.kernel"), M=M, K=Vh, N=NL, ldx=Vh, ldy=64, lddw=NL)
             ops.colsum(ws.dvl, p.g("value_head.dense.bias"), M=M, N=NL, ld=64)
         self._side_run(_wg_vhead)
-        ops.linear(ws.dvl, w["w_vh_pad"], out=ws.dpv, residual=ws.zv, act=2)      # gelu' rides in the GEMM epilogue
+        if self.fuse_gelu_t:
+            ops.linear(ws.dvl, w["w_vh_pad"], out=ws.dpv, residual=ws.zv, act=2)  # gelu' rides in the GEMM epilogue
+        else:
+            ops.linear(ws.dvl, w["w_vh_pad"], out=ws.dpv)
+            ops.gelu_bwd(ws.dpv, ws.zv, out=ws.dpv)
 
         def _wg_vmlp():
             ops.linear_wgrad(ws.xf, ws.dpv, p.g("value_mlp.kernel"), M=M, K=H, N=Vh, ldx=H, ldy=Vh, lddw=Vh)
