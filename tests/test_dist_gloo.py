@@ -44,6 +44,12 @@ def _worker(rank, world, port, q):
         g_local = (2 * (x @ w)[:, None] * x).mean(0)           # d/dw mean((x.w)^2) over the shard
         g = g_local.clone()
         scale = mdist.allreduce_gradients(g)
+        # the trainer reduces the flat gradient as two partitions (Muon matrices early, AdamW leaves late): same result
+        g2 = g_local.clone()
+        n_adam = 1
+        s_hi = mdist.allreduce_gradients(g2[n_adam:])
+        s_lo = mdist.allreduce_gradients(g2[:n_adam])
+        assert s_hi == s_lo == scale and torch.equal(g2, g)
         p = torch.zeros(3) if rank else torch.ones(3)
         mdist.broadcast_params(p)
         q.put((rank, lo, hi, adv_n, (g * scale).numpy(), p.numpy(), count))
