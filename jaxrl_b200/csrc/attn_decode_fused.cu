@@ -128,6 +128,27 @@ __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedP
   }
   const int pos0 = p.pos[0];                     // positions are step inputs, never produced by the preceding kernel
   griddep_launch();
+  const int per_round = gridDim.x * warps;
+  const int nrounds = (p.B + per_round - 1) / per_round;
+  uint2 xv = make_uint2(0u, 0u);
+  float rsn[2][2], rcs[2][2];
+  auto fetch_x = [&](int round) {
+    const int b0 = round * per_round + blockIdx.x * warps;
+    if (round < nrounds && b0 + warp < p.B) xv = *reinterpret_cast<const uint2*>(p.x + (size_t)(b0 + warp) * 128 + 4 * lane);
+  };
+  auto fetch_angles = [&](int round) {
+    const int b0 = round * per_round + blockIdx.x * warps;
+    if (round < nrounds && warp < 10) {
+#pragma unroll
+      for (int rs = 0; rs < 2; ++rs) {
+        const int ab = b0 + g + 8 * rs;
+        const float pf = (float)p.pos[ab < p.B ? ab : 0];
+        sincosf(pf / ts0, &rsn[rs][0], &rcs[rs][0]);
+        sincosf(pf / ts1, &rsn[rs][1], &rcs[rs][1]);
+      }
+    }
+  };
+  fetch_angles(0);                               // positions only: runs under the preceding kernel's tail
   const int kv_len = min(pos0 + 1, p.S);
   const int nchunks = (kv_len + AF_CHUNK - 1) / AF_CHUNK;
   int slot = pos0 % p.S;
@@ -148,27 +169,10 @@ __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedP
   const int c_new = slot >> 5, r_new = slot & 31;
   const bool head_lane = (2 * t) < G;
   const bool head1 = (2 * t + 1) < G;
-  const int per_round = gridDim.x * warps;
-  const int nrounds = (p.B + per_round - 1) / per_round;
 
   // this warp's input row and the rotation angles of the projection rows it finishes (agents g, g + 8 of the CTA), for
   // the round about to start: fetched one round ahead so that their latency hides behind the previous round's stream
-  uint2 xv = make_uint2(0u, 0u);
-  float rsn[2][2], rcs[2][2];
-  auto fetch_round = [&](int round) {
-    const int b0 = round * per_round + blockIdx.x * warps;
-    if (round < nrounds && b0 + warp < p.B) xv = *reinterpret_cast<const uint2*>(p.x + (size_t)(b0 + warp) * 128 + 4 * lane);
-    if (round < nrounds && warp < 10) {
-#pragma unroll
-      for (int rs = 0; rs < 2; ++rs) {
-        const int ab = b0 + g + 8 * rs;
-        const float pf = (float)p.pos[ab < p.B ? ab : 0];
-        sincosf(pf / ts0, &rsn[rs][0], &rcs[rs][0]);
-        sincosf(pf / ts1, &rsn[rs][1], &rcs[rs][1]);
-      }
-    }
-  };
-  fetch_round(0);
+  fetch_x(0);
 
   for (int round = 0; round < nrounds; ++round) {
     const int cta_b0 = round * per_round + blockIdx.x * warps;      // first agent of this CTA in this round
@@ -256,7 +260,8 @@ __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedP
     }
     if (lane < 8) kvnew = lds_v4(kvs + warp * 128 + lane * 16);
     __syncthreads();                                       // scratch rows are dead: stage 3 may be refilled
-    fetch_round(round + 1);
+    fetch_x(round + 1);
+    fetch_angles(round + 1);
 
     if (active) {
       float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;       // heads 2t, 2t+1 (log2 domain)
