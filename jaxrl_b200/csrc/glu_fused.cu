@@ -120,13 +120,15 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  griddep_wait();                              // everything read from global memory below may come from earlier kernels
+  // the norm scale is a parameter (written by the optimizer / weight staging, never by the kernel right before this
+  // one), so it and the CTA / cluster set-up barriers run under the preceding kernel's tail
   if (p.norm_scale && threadIdx.x >= 64 && threadIdx.x < 96)
     reinterpret_cast<float4*>(sScale)[threadIdx.x - 64] = reinterpret_cast<const float4*>(p.norm_scale)[threadIdx.x - 64];
   tc_fence_before();
   __syncthreads();
   if (ncta > 1) cluster_sync_all();            // remote CTAs' barriers are initialised before anyone arrives on them
   tc_fence_after();
+  griddep_wait();                              // activations read from global memory below may come from earlier kernels
   dbg_stamp(dbg, 1);
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t tUG[2] = {tmem_base, tmem_base + 128};
