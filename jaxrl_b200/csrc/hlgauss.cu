@@ -148,35 +148,37 @@ __global__ void __launch_bounds__(HLG_WARPS * 32) hlgauss_loss2_kernel(
     const float c2 = __shfl_down_sync(0xffffffffu, c0, 1);
     const float cdf_lo = __shfl_sync(0xffffffffu, c0, 0);
     const float cdf_hi = __shfl_sync(0xffffffffu, (NL & 1) ? c1 : c0, NL >> 1);
-    const float z = cdf_hi - cdf_lo;
-    const float p0 = b0 ? (c1 - c0) / z : 0.f, p1 = b1 ? (c2 - c1) / z : 0.f;
+    const float rz = 1.0f / (cdf_hi - cdf_lo);                        // one reciprocal per row (all lanes hold it)
+    const float p0 = b0 ? (c1 - c0) * rz : 0.f, p1 = b1 ? (c2 - c1) * rz : 0.f;
     const float m = warp_max(fmaxf(v0, v1));
-    float s = (b0 ? expf(v0 - m) : 0.f) + (b1 ? expf(v1 - m) : 0.f);
-    float psum = p0 + p1;
-    s = warp_sum(s);
-    psum = warp_sum(psum);
+    const float d0 = v0 - m, d1 = v1 - m;
+    const float ex0 = b0 ? expf(d0) : 0.f, ex1 = b1 ? expf(d1) : 0.f;
+    // three independent butterflies in one pass: sum exp, sum p, sum p * (v - m);
+    // loss row = -sum p * ((v - m) - lse) = lse * sum p - sum p * (v - m)
+    float s = ex0 + ex1, psum = p0 + p1, pd = (b0 ? p0 * d0 : 0.f) + (b1 ? p1 * d1 : 0.f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      psum += __shfl_xor_sync(0xffffffffu, psum, o);
+      pd += __shfl_xor_sync(0xffffffffu, pd, o);
+    }
     const float lse = logf(s);
-    float l = 0.f;
-    if (b0) {
-      const float lsm = (v0 - m) - lse;
-      l -= p0 * lsm;
-      const float gr = gscale * (expf(lsm) * psum - p0);
-      if (dlogits) dlogits[row * NL + j0] = gr;
-      if (dl_bf16) dl_bf16[row * ld_bf16 + j0] = __float2bfloat16_rn(gr);
-    } else if (dl_bf16 && j0 < ld_bf16) {
-      dl_bf16[row * ld_bf16 + j0] = __float2bfloat16_rn(0.f);
+    const float rs = 1.0f / s;
+    const float g0 = gscale * (ex0 * rs * psum - p0), g1 = gscale * (ex1 * rs * psum - p1);   // softmax = exp(v - m) / s
+    if (dlogits) {
+      if (b0) dlogits[row * NL + j0] = g0;
+      if (b1) dlogits[row * NL + j1] = g1;
     }
-    if (b1) {
-      const float lsm = (v1 - m) - lse;
-      l -= p1 * lsm;
-      const float gr = gscale * (expf(lsm) * psum - p1);
-      if (dlogits) dlogits[row * NL + j1] = gr;
-      if (dl_bf16) dl_bf16[row * ld_bf16 + j1] = __float2bfloat16_rn(gr);
-    } else if (dl_bf16 && j1 < ld_bf16) {
-      dl_bf16[row * ld_bf16 + j1] = __float2bfloat16_rn(0.f);
+    if (dl_bf16) {
+      if ((ld_bf16 & 1) == 0) {                                       // j0 even: one 4-byte store per lane, zero padded
+        if (j0 < ld_bf16)
+          *reinterpret_cast<uint32_t*>(dl_bf16 + row * ld_bf16 + j0) = pack_bf16(b0 ? g0 : 0.f, b1 ? g1 : 0.f);
+      } else {
+        if (j0 < ld_bf16) dl_bf16[row * ld_bf16 + j0] = __float2bfloat16_rn(b0 ? g0 : 0.f);
+        if (j1 < ld_bf16) dl_bf16[row * ld_bf16 + j1] = __float2bfloat16_rn(b1 ? g1 : 0.f);
+      }
     }
-    l = warp_sum(l);
-    acc += (double)l;
+    if (lane == 0) acc += (double)(lse * psum - pd);
   }
   if (lane == 0) s_part[warp] = acc;
   __syncthreads();
