@@ -6,9 +6,15 @@ steps for B agents (KV-cache decode + sampling + value), GAE, and minibatch_coun
 gradient all-reduce and the optimizer step - i.e. the reference's `train()` (mapox_trainer/train.py:225-309).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--config return_2_layers] [--impl ours|reference]
+                  [--scaling weak|strong]
 
-N > 1 is launched by torchrun (one rank per GPU, NCCL); agents are sharded across ranks (weak scaling: B per GPU
-is fixed).  Rank 0 prints ONE JSON line.
+N > 1 is launched by torchrun (one rank per GPU, NCCL); agents are sharded across ranks.  `--scaling weak` (default):
+B per GPU is the config's 4096; `--scaling strong`: the config's 4096 agents in total, 4096/N per GPU.  The default
+(weak) line of an N > 1 run also carries a `strong_scaling` object measured in the same process.  Rank 0 prints ONE
+JSON line.
+
+`--impl reference` times the CPU restatement of the reference (oracle/, torch-CPU, all host threads) on a bounded
+sample of the same workload; it imports nothing from `jaxrl_b200` (the CUDA library is never loaded on that arm).
 """
 
 from __future__ import annotations
@@ -28,6 +34,7 @@ if ROOT not in sys.path:
 
 METRIC = "ppo_env_steps_per_sec"
 UNIT = "env-steps/s"
+CPU_SAMPLE_AGENTS = 64          # bounded CPU sample (both `cpu_baseline` and `--impl reference`)
 
 
 def parse():
@@ -37,15 +44,31 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="return_2_layers")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true",
+                    help="no other_configs / strong_scaling / in-graph roofline legs (quick A/B runs)")
     ap.add_argument("--cpu-agents", type=int, default=None)
     ap.add_argument("--ncu", action="store_true", help="profiling run: one eager warm pass + ONE eager update, no extras")
     ap.add_argument("--ncu-decode-step", action="store_true", help="profiling run: one decode step (t=300) between profiler start/stop")
     ap.add_argument("--ncu-minibatch", action="store_true",
                     help="profiling run: eager warm pass, then ONE training minibatch (fwd+bwd+optimizer) between NVTX-free markers")
     return ap.parse_args()
+
+
+def workload_config(name: str, cfg, hyp, B: int, world: int, optimizer: str, scaling: str, graphs: bool) -> dict:
+    """`config` of the JSON line - identical for both arms (the CPU arm's bounded sample is described in its
+    `cpu_baseline.sample`, not here)."""
+    T = cfg.max_seq_length
+    return {"workload": f"{name}: PPO update = rollout of T={T} decode steps for B={B} agents/GPU + GAE + "
+                        f"{hyp.minibatch_count} minibatch fwd/bwd + optimizer, L={cfg.num_layers} "
+                        f"H={cfg.hidden_features} GQA {cfg.num_heads}:{cfg.num_kv_heads}",
+            "agents_per_gpu": B, "trajectory": T, "layers": cfg.num_layers,
+            "parallelism": f"env-sharded dp{world}", "optimizer": optimizer, "scaling": scaling,
+            "l2": "working set (KV caches + activations, >2 GB) larger than the 126 MB L2; no flush",
+            "cuda_graphs": graphs}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -98,64 +121,22 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_baseline(run, agents: int, steps: int = 1, warmup: int = 0):
-    """The oracle (torch-CPU restatement of the reference path; JAX cannot be installed here) timed on the host
-    cores for the same unit of work on a bounded sample: `agents` agents x T steps, same L/H/minibatch structure."""
-    import torch
-    from oracle import oracle as O
-    from jaxrl_b200.params import param_specs, _init
-
-    cfg, hyp = run.model, run.ppo
-    T = cfg.max_seq_length
-    torch.set_num_threads(os.cpu_count() or 1)
-    gen = torch.Generator().manual_seed(0)
-    p = {name: _init(shape, kind, gen) for name, shape, kind in param_specs(cfg)}
-    vw, vh = cfg.obs_shape[0], cfg.obs_shape[1]
-    comps = [torch.randint(0, n, (T + 1, agents, vw, vh), generator=gen) for n in cfg.obs_max_value]
-    obs = (comps[0] if cfg.obs_type == "grid_flattened" else torch.stack(comps, -1)).to(torch.uint8)
-    reward = (torch.rand(T + 1, agents, generator=gen) < 0.02).float() * 0.05
-    u = torch.rand(T, agents, cfg.action_dim, generator=gen).clamp(1e-6, 1 - 1e-6)
-    gumbel = -torch.log(-torch.log(u))
-    m = max(1, min(hyp.minibatch_count, agents))
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        with torch.no_grad():
-            ro = O.rollout_decode(p, cfg, obs, reward, gumbel)
-        term = torch.zeros(agents, T, dtype=torch.bool); term[:, -1] = True
-        adv, tgt = O.calculate_advantage(ro["rewards"].numpy(), ro["values"].numpy(), term.numpy(), hyp.discount,
-                                         hyp.gae_lambda, hyp.normalize_advantage)
-        adv, tgt = torch.from_numpy(adv), torch.from_numpy(tgt)
-        pg = {k: v.clone().requires_grad_(True) for k, v in p.items()}
-        bm = agents // m
-        for i in range(m):
-            sl = slice(i * bm, (i + 1) * bm)
-            batch = dict(obs=obs[:T].transpose(0, 1)[sl], action_mask=None, actions=ro["actions"][sl],
-                         last_actions=ro["last_actions"][sl], last_rewards=ro["last_rewards"][sl],
-                         terminated=torch.zeros(bm, T, dtype=torch.bool), log_prob=ro["log_prob"][sl],
-                         advantages=adv[sl], targets=tgt[sl])
-            total, _ = O.ppo_loss(pg, cfg, hyp, batch, 0.0)
-            total.backward()
-        times.append(time.perf_counter() - t0)
-    dt = statistics.median(times[warmup:])
-    return dict(value=agents * T / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port",
-                sample=f"{agents} agents x {T} steps x {cfg.num_layers} layers, {m} minibatches, torch-CPU oracle "
-                       f"(restatement of the reference; JAX CPU backend not installable here), {dt:.2f} s per update"), dt
-
-
-def reference_arm(args, run):
+# ------------------------------------------------------------------------------------------------ CPU arm
+def reference_arm(args):
+    """The reference's CPU implementation of the path - here its torch-CPU restatement (oracle/; the JAX CPU backend
+    cannot be installed in this image) - on all host threads, on a bounded sample of the SAME workload as our arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    args.cpu_agents = args.cpu_agents or 16
-    cb, dt = cpu_baseline(run, args.cpu_agents, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    from oracle import synth
+    cfg, hyp, B = synth.WORKLOADS[args.config]
+    agents = args.cpu_agents or CPU_SAMPLE_AGENTS
+    cb, dt = synth.time_cpu_update(args.config, agents, steps=max(1, args.steps), warmup=min(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{run.name}: PPO update (rollout T={run.model.max_seq_length} + GAE + "
-                                   f"{run.ppo.minibatch_count} minibatch fwd/bwd), L={run.model.num_layers}, "
-                                   f"bounded CPU sample of {args.cpu_agents} agents"},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args.config, cfg, hyp, B if args.scaling == "weak" else B // args.gpus, args.gpus,
+                                      "muon", args.scaling, True),
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -164,10 +145,8 @@ def reference_arm(args, run):
 # ------------------------------------------------------------------------------------------------ ours
 def count_launches(trainer) -> int:
     """Kernel launches of OUR library in one PPO update (counted from the C-ABI calls of one eager pass)."""
-    from jaxrl_b200 import _lib
-    # muon: prepare + 3 x 5 Newton-Schulz GEMMs + finish (phase 1), AdamW leaves + clip/apply (phase 2)
-    per_call = {"mpx_gae": 2, "mpx_hlgauss_loss": 2, "mpx_ppo_policy_loss": 2, "mpx_adamw_step": 2,
-                "mpx_attn_train_bwd": 3, "mpx_muon_step:1": 17, "mpx_muon_step:2": 2, "mpx_muon_step:3": 19}
+    from jaxrl_b200 import _lib, ops
+    per_call = dict(ops.LAUNCHES_PER_CALL)
     counts = {"n": 0}
     orig = _lib.check
 
@@ -175,24 +154,38 @@ def count_launches(trainer) -> int:
         counts["n"] += per_call.get(what, 1)
         return orig(rc, what)
 
-    from jaxrl_b200 import ops
     ops.check = counting_check
+    state = trainer.snapshot_state()
     try:
         trainer._rollout_body(); trainer._postprocess_body(); trainer._normalize(); trainer._update_body()
     finally:
         ops.check = orig
+        trainer.restore_state(state)
     return counts["n"]
 
 
-def decode_attention_roofline(trainer, peaks):
+def _decode_attention_bytes(eng, B: int, T: int) -> float:
+    """per agent-step per layer (T+1)/2 * Nkv*D*2*2 bytes of KV read + the rows in and out: x, out and
+    the new k,v ring rows (fused; the projection weights come from L2) or q and out (unfused)."""
+    kv_bytes = (T + 1) / 2 * eng.Nkv * eng.D * 2 * 2
+    fused = eng.fused_attn_decode
+    io_bytes = (eng.H * 2 + eng.Nq * eng.D * 2 + 2 * eng.Nkv * eng.D * 2) if fused else 2 * eng.Nq * eng.D * 2
+    return B * (kv_bytes + io_bytes)
+
+
+def decode_attention_roofline(trainer, peaks, in_graph: bool):
     """Dominant HBM-bound kernel: rollout decode attention (with the q/k/v projection folded in front where the
-    shape allows).  Times the T launches of one rollout (positions 0..T-1, alternating layers so the 268 MB caches
-    never sit in L2) back to back with CUDA events on the launching stream; achieved = algorithmic bytes per launch /
-    average launch duration."""
+    shape allows).
+
+    `frac` (in-graph): the kernel's time INSIDE the rollout graph = (replay time of the rollout graph - replay time of
+    the same graph captured without the attention launches) / (T*L launches); everything else (encoder, feed-forward
+    halves, policy head, value pass, programmatic dependent launches) is identical in both graphs.
+    `frac_isolated`: the T launches of one rollout timed back to back with CUDA events on the launching stream
+    (alternating layers so the 268 MB caches never sit in L2) - the kernel behind itself, the round-1 figure."""
     import torch
     from jaxrl_b200 import ops
     eng, r = trainer.engine, trainer.r
-    ws = trainer.dws if trainer.n_chains == 1 else trainer.dws_chain[0]   # the launch shape the rollout really uses
+    ws = trainer.dws
     T, B, L = trainer.T, ws.B, eng.L
     fused = eng.fused_attn_decode
     x = torch.randn(B, eng.H, device=ws.ao.device).to(torch.bfloat16)
@@ -201,8 +194,7 @@ def decode_attention_roofline(trainer, peaks):
         if fused:
             pre = f"layers.{i}."
             ops.attn_decode_fused(x, eng.p[pre + "history_norm.scale"], eng.w[pre + "wt_qkv"], r.pos[t][:B], eng.timescale,
-                                  ws.kcache[i], ws.vcache[i], eng.Nq, eng.Nkv, eng.D, out=ws.ao,
-                                  stable_history=eng.early_kv_stream)    # as the rollout launches it
+                                  ws.kcache[i], ws.vcache[i], eng.Nq, eng.Nkv, eng.D, out=ws.ao)
         else:
             ops.attn_decode(ws.q, ws.kcache[i], ws.vcache[i], r.pos[t][:B], eng.Nq, eng.Nkv, eng.D, out=ws.ao)
 
@@ -215,42 +207,103 @@ def decode_attention_roofline(trainer, peaks):
         launch(t, t % L)
     e1.record()
     torch.cuda.synchronize()
-    avg_s = e0.elapsed_time(e1) * 1e-3 / T
-    # per agent-step per layer (T+1)/2 * Nkv*D*2*2 bytes of KV read + the rows in and out: q and out
-    # (unfused) or x, out and the new k,v ring rows (fused; the 48 KB of projection weights per CTA come from L2)
-    kv_bytes = (T + 1) / 2 * eng.Nkv * eng.D * 2 * 2
-    io_bytes = (eng.H * 2 + eng.Nq * eng.D * 2 + 2 * eng.Nkv * eng.D * 2) if fused else 2 * eng.Nq * eng.D * 2
-    per_launch = B * (kv_bytes + io_bytes)
-    achieved = per_launch / avg_s / 1e9
+    iso_s = e0.elapsed_time(e1) * 1e-3 / T
+    per_launch = _decode_attention_bytes(eng, B, T)
     peak = peaks.get("hbm_gbs", 6650.0)
-    # DRAM traffic per launch: ncu measured (read + write) / algorithmic bytes for this kernel at one position
-    # (profiles/r01_attn_decode*_traffic.json); scaled to the average launch of the rollout, like `achieved`.
-    traffic = None
     name = "attn_decode_fused_kernel" if fused else "attn_decode_online_kernel"
-    tfile = "r01_attn_decode_fused_traffic.json" if fused else "r01_attn_decode_traffic.json"
-    try:
-        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", tfile)))
-        traffic = tj["ratio"] * per_launch
+    out = {"kernel": name, "bound": "hbm", "peak": peak, "unit": "GB/s",
+           "algorithmic_bytes_per_launch": per_launch, "agents_per_launch": B,
+           "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
+           "frac_isolated": per_launch / iso_s / 1e9 / peak, "isolated_launch_us": iso_s * 1e6}
+    avg_s = iso_s
+    if in_graph and trainer.rollout_graph is not None:
+        def replay_ms(g, n=3):
+            g.replay()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                g.replay()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+        full_ms = replay_ms(trainer.rollout_graph)
+        key = "attn_decode_fused" if fused else "attn_decode"
+        orig = getattr(ops, key)
+        setattr(ops, key, lambda *a, **k: k.get("out"))           # bench-only: the same graph minus the attention launches
+        try:
+            g0 = trainer._capture(trainer._rollout_body)
+        finally:
+            setattr(ops, key, orig)
+        without_ms = replay_ms(g0)
+        del g0
+        n_launch = (T + 1) * L
+        avg_s = max(full_ms - without_ms, 1e-6) * 1e-3 / n_launch
+        # the bootstrap step (position 0) moves no history: T*L launches carry the bytes
+        out.update({"rollout_graph_ms": full_ms, "rollout_graph_without_kernel_ms": without_ms,
+                    "timing": "in-graph marginal: (rollout graph - same graph without this kernel) / launches"})
+        per_launch_graph = per_launch * T / (T + 1)
+        out["achieved"] = per_launch_graph / avg_s / 1e9
+    else:
+        out["timing"] = "isolated back-to-back launches"
+        out["achieved"] = per_launch / avg_s / 1e9
+    out["frac"] = out["achieved"] / peak
+    out["avg_launch_us"] = avg_s * 1e6
+    # DRAM traffic per launch: ncu (dram__bytes_read.sum + dram__bytes_write.sum) / algorithmic bytes for this kernel at
+    # one position, from the newest --set full capture under profiles/; scaled to the average launch like `achieved`.
+    out["traffic"] = None
+    for tfile in ("r02_attn_decode_fused_traffic.json", "r01_attn_decode_fused_traffic.json") if fused else ("r01_attn_decode_traffic.json",):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", tfile)))
+            out["traffic"] = tj["ratio"] * per_launch
+            out["traffic_source"] = f"profiles/{tfile} (ncu capture, ratio {tj['ratio']:.3f} of algorithmic)"
+            break
+        except Exception:
+            continue
+    return out
+
+
+def train_flops_per_token(cfg) -> float:
+    """per token, forward + backward: GEMMs 6 * params per layer, causal attention 3.5 * 4*Nq*D*(T+1)/2
+    per layer, heads 6 * (H*Vh + Vh*NL + H*A) (the observation encoder is not counted)."""
+    H, F, T = cfg.hidden_features, cfg.ffn_size, cfg.max_seq_length
+    QD, KD = cfg.num_heads * cfg.head_dim, cfg.num_kv_heads * cfg.head_dim
+    layer = 6.0 * (H * QD + 2 * H * KD + QD * H + 3 * H * F) + 3.5 * (4 * cfg.num_heads * cfg.head_dim * (T + 1) / 2)
+    Vh = cfg.value_hidden_dim or 0
+    heads = 6.0 * (H * Vh + (Vh or H) * cfg.value_n_logits + H * cfg.action_dim)
+    return cfg.num_layers * layer + heads
+
+
+def train_roofline(cfg, B: int, update_ms: float, peaks) -> dict:
+    T = cfg.max_seq_length
+    flops = train_flops_per_token(cfg) * B * T
+    peak = peaks.get("bf16_tflops_sustained", 1355.0)
+    achieved = flops / (update_ms * 1e-3) / 1e12
+    out = {"phase": "PPO update (all minibatch fwd/bwd + optimizer)", "bound": "tensor", "achieved": achieved,
+           "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "flops_per_update": flops,
+           "flops_per_token": train_flops_per_token(cfg), "update_ms": update_ms,
+           "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback 1355"}
+    try:      # per-kernel tensor-pipe % of the newest ncu minibatch capture (profiles/, cold-cache, serialised)
+        tp = json.load(open(os.path.join(ROOT, "profiles", "train_tensor_pct.json")))
+        out["tensor_pipe_pct"] = tp["kernels"]
+        out["tensor_pipe_source"] = tp["source"]
     except Exception:
         pass
-    return {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": traffic, "avg_launch_us": avg_s * 1e6,
-            "algorithmic_bytes_per_launch": per_launch, "agents_per_launch": B,
-            "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"}
+    return out
 
 
 def main():
     args = parse()
-    from jaxrl_b200.config import NAMED
-    run = NAMED[args.config]
     if args.impl == "reference":
-        reference_arm(args, run)
+        reference_arm(args)
         return
     import torch
     import torch.distributed as dist
     from dataclasses import replace
+    from jaxrl_b200.config import NAMED
     from jaxrl_b200.trainer import PPOTrainer
 
+    run = NAMED[args.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -258,15 +311,17 @@ def main():
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
-    # weak scaling: B agents per GPU fixed (the config's 4096), total = world * B
-    run_w = replace(run, num_agents=run.num_agents * world)
-    B, T = run.num_agents, run.model.max_seq_length
+    T = run.model.max_seq_length
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             peaks = json.load(f)
     except Exception:
         pass
+
+    def sized(r, scaling):
+        # weak: the config's agents on every GPU; strong: the config's agents in total
+        return replace(r, num_agents=r.num_agents * world) if scaling == "weak" else r
 
     def barrier():
         if world > 1:
@@ -295,18 +350,21 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
+    run_w = sized(run, args.scaling)
+    B = run_w.num_agents // world
+
     if args.ncu_decode_step:
         trainer = PPOTrainer(run_w, rank=rank, world=world, use_graphs=False)
         trainer.warmup()
-        from jaxrl_b200 import ops as _ops
         t, r, env, eng = 300, trainer.r, trainer.env, trainer.engine
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        dws = trainer.dws if trainer.n_chains == 1 else trainer.dws_chain[0]
+        dws = trainer.dws
         rows = slice(0, dws.B)
         eng.decode_step(dws, env.obs[t][rows], env.reward[t][rows], r.actions_ext[t][rows], r.pos[t][rows],
-                        value_out=r.values[t][rows],
-                        sample=dict(action=r.actions_ext[t + 1][rows], log_prob=r.log_prob[t][rows], seed=trainer.seed,
+                        hidden_out=r.hidden[t][rows] if trainer.defer_value else None,
+                        value_out=None if trainer.defer_value else r.values[t][rows],
+                        sample=dict(action=r.actions_ext[t + 1][rows], log_prob=r.log_prob[t][rows], seed=trainer.sample_seed,
                                     stream_id=t, stream_offset=trainer.noise_off, want_logits=False))
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
@@ -315,6 +373,7 @@ def main():
     if args.ncu_minibatch:
         trainer = PPOTrainer(run_w, rank=rank, world=world, use_graphs=False)
         trainer.warmup()
+        trainer.train_step()
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
         trainer._minibatch_body(1)
@@ -332,28 +391,32 @@ def main():
         torch.cuda.profiler.stop()
         print(json.dumps({"ncu_run": True, "losses": trainer.logs()}), flush=True)
         return
+
     # ---- device-resident arm (value)
-    trainer = PPOTrainer(run_w, rank=rank, world=world, use_graphs=not args.no_graphs)
+    graphs = not args.no_graphs
+    trainer = PPOTrainer(run_w, rank=rank, world=world, use_graphs=graphs)
     trainer.warmup()
     launches = count_launches(trainer)      # every rank: the pass contains the collectives of one update
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    secs = timed(trainer, args.steps, max(3, args.warmup), sync_logs=False)
+    wu = max(3, args.warmup)
+    secs = timed(trainer, args.steps, wu, sync_logs=False)
     clocks = sampler.stop() if rank == 0 else None
     logs = trainer.logs()
     value = world * B * T * args.steps / secs
-    roof = decode_attention_roofline(trainer, peaks) if rank == 0 else None
     phases = trainer.timed_phases()
+    roof = decode_attention_roofline(trainer, peaks, in_graph=not args.skip_extras) if rank == 0 else None
+    roof_train = train_roofline(run.model, B, phases["update_ms"], peaks)
     del trainer
     torch.cuda.empty_cache()
 
     # ---- end-to-end arm: host (pinned) observations copied every decode step, losses read back every update
     e2e = None
     if not args.skip_e2e:
-        tr2 = PPOTrainer(run_w, rank=rank, world=world, use_graphs=not args.no_graphs, e2e_host_inputs=True)
+        tr2 = PPOTrainer(run_w, rank=rank, world=world, use_graphs=graphs, e2e_host_inputs=True)
         tr2.warmup()
-        secs2 = timed(tr2, args.steps, max(3, args.warmup), sync_logs=True)
+        secs2 = timed(tr2, args.steps, wu, sync_logs=True)
         obs_bytes = tr2.env.obs_host[0].numel() * tr2.env.obs_host[0].element_size()
         rew_bytes = tr2.env.reward_host[0].numel() * 4
         e2e = {"value": world * B * T * args.steps / secs2, "unit": UNIT,
@@ -361,23 +424,43 @@ def main():
         del tr2
         torch.cuda.empty_cache()
 
+    # ---- extras: strong scaling in the same run (N > 1), the other BASELINE.json configs (N = 1)
+    strong = None
+    other = None
+    if not args.skip_extras:
+        def quick(r, steps=3, warm=3):
+            tr = PPOTrainer(r, rank=rank, world=world, use_graphs=graphs)
+            tr.warmup()
+            s = timed(tr, steps, warm, sync_logs=False)
+            ph = tr.timed_phases()
+            Bq = r.num_agents // world
+            del tr
+            torch.cuda.empty_cache()
+            return {"value": world * Bq * r.model.max_seq_length * steps / s, "unit": UNIT,
+                    "ms_per_step": s / steps * 1e3, "agents_per_gpu": Bq, "steps": steps, "warmup": warm,
+                    "phases_ms": ph}
+        if world > 1 and args.scaling == "weak":
+            strong = {}
+            for name in (args.config, "return_8_layers"):
+                r = NAMED[name]
+                if r.num_agents % (world * r.ppo.minibatch_count) == 0:
+                    strong[name] = quick(r)
+        if world == 1 and args.config == "return_2_layers":
+            other = {name: quick(NAMED[name]) for name in ("return_8_layers", "multitask", "blog_32_layers")}
+
     if rank == 0:
         cb = None
         if world == 1 and not args.skip_cpu:
-            cb, _ = cpu_baseline(run, args.cpu_agents or 64)
+            from oracle import synth
+            cb, _ = synth.time_cpu_update(args.config, args.cpu_agents or CPU_SAMPLE_AGENTS)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{run.name}: PPO update = rollout of T={T} decode steps for B={B} agents/GPU + GAE + "
-                                   f"{run.ppo.minibatch_count} minibatch fwd/bwd + optimizer, L={run.model.num_layers} "
-                                   f"H={run.model.hidden_features} GQA {run.model.num_heads}:{run.model.num_kv_heads}",
-                       "agents_per_gpu": B, "trajectory": T, "layers": run.model.num_layers,
-                       "parallelism": f"env-sharded dp{world}", "optimizer": run.optimizer.type,
-                       "l2": "working set (KV caches + activations, >2 GB) larger than the 126 MB L2; no flush",
-                       "cuda_graphs": not args.no_graphs},
+            "warmup": wu, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(run.name, run.model, run.ppo, B, world, run.optimizer.type, args.scaling, graphs),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
-            "roofline": roof, "cpu_baseline": cb, "losses": logs, "phases_ms": phases,
+            "roofline": roof, "roofline_train": roof_train, "cpu_baseline": cb, "losses": logs, "phases_ms": phases,
+            "strong_scaling": strong, "other_configs": other,
             "published_reference": "3.8M+ steps/s on 1x RTX 5090 (README.md:10), other hardware",
         }
         print(json.dumps(line), flush=True)

@@ -33,11 +33,9 @@ int mpx_version(void);
  * key 1: decode attention implementation (0 = mma.sync online softmax, default; 1 = SIMT exact two-pass;
  * 2 = mma.sync exact two-pass).  key 2: training attention forward (0 = tcgen05/TMEM when q,k,v are packed and
  * Nkv == 1, default; 1 = mma.sync everywhere).  key 3: mpx_glu_fused cluster size (0 = auto; 1, 2 or 4 = force).
- * key 4: mpx_value_head_fused cluster size, same values.  key 5: swap LBO/SBO in mpx_obs_embed_fused's no-swizzle
- * UMMA descriptors (bring-up).  key 6: programmatic dependent launch, one bit per kernel family (1 = GEMM / elementwise
- * / value head, 2 = observation encoder, 4 = decode attention, 8 = fused GLU, 16 = policy head; default 12).
- * key 7: GEMM epilogue experiments (bit 0: no global stores, bit 1: no epilogue work at all) - results are then WRONG;
- * used only by scripts/microbench_gemm.py to attribute time. */
+ * key 4: mpx_value_head_fused cluster size, same values.  key 6: programmatic dependent launch, one bit per kernel
+ * family (1 = GEMM / elementwise / value head, 2 = observation encoder, 4 = decode attention, 8 = fused GLU,
+ * 16 = policy head; default 12).  No key changes results beyond the documented choice of an equivalent kernel. */
 int mpx_debug_set(int key, int value);
 /* Bring-up aid: device buffer of >= 32 uint64 slots in which CTA 0 of the fused rollout kernels records %globaltimer at
  * its phase boundaries (NULL switches it off, the default). */

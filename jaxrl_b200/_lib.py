@@ -7,7 +7,6 @@ raises if the CUDA call fails (e.g. no sm_100 device).
 from __future__ import annotations
 
 import ctypes as C
-import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
@@ -162,10 +161,3 @@ def ptr(t) -> int | None:
 def stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
-
-# Tuning knob for A/B runs: MPX_PDL=<mask> selects the kernel families launched with programmatic dependent launch
-# (library default 12 = decode attention + fused GLU; 0 = none; bits in csrc/common.cuh).
-PDL_MASK = 12
-if os.environ.get("MPX_PDL") is not None:
-    PDL_MASK = int(os.environ["MPX_PDL"])
-    lib.mpx_debug_set(6, PDL_MASK)

@@ -82,6 +82,13 @@ class RunConfig:
     update_steps: int = 5000
     seed: int = 42
 
+    @property
+    def optimizer_total_steps(self) -> int:
+        """Horizon of the linear LR schedule: the reference passes update_steps * minibatch_count * epoch_count to
+        create_optimizer (train.py:360-365) and calls optimizer.update once per minibatch (train.py:244), so the
+        schedule reaches 0 exactly at the end of training."""
+        return self.update_steps * self.ppo.minibatch_count * self.ppo.epoch_count
+
 
 def from_reference_json(path: str, *, obs_components: Tuple[int, ...] = (5, 5), action_dim: int = 8,
                         agents_per_env: Optional[int] = None, task_count: int = 1) -> RunConfig:
@@ -93,8 +100,10 @@ def from_reference_json(path: str, *, obs_components: Tuple[int, ...] = (5, 5), 
     enc = m["obs_encoder"]
     env = j["environment"]
     val = m["value"]
-    if val["type"] != "hl_gauss":
-        raise ValueError("only the hl_gauss value head is on the B200 path (mse is craftax-only)")
+    unsupported = _unsupported_model_options(m)
+    if unsupported:
+        raise ValueError("reference config options outside the B200 hot path (the engine would run a different "
+                         "network): " + "; ".join(unsupported))
     model = ModelConfig(
         hidden_features=m["hidden_features"], num_layers=m["num_layers"], num_heads=hist["num_heads"],
         num_kv_heads=hist["num_kv_heads"], head_dim=hist["head_dim"],
@@ -115,9 +124,57 @@ def from_reference_json(path: str, *, obs_components: Tuple[int, ...] = (5, 5), 
     o = j["learner"]["optimizer"]
     opt = OptimizerConfig(type=o["type"], learning_rate=o["learning_rate"], weight_decay=o["weight_decay"],
                           eps=o["eps"], beta1=o["beta1"], beta2=o["beta2"], max_norm=o["max_norm"])
-    apn = agents_per_env if agents_per_env is not None else env.get("num_agents", 1)
-    return RunConfig(name=path, model=model, ppo=ppo, optimizer=opt, num_agents=j.get("num_envs", 1) * apn,
+    if env.get("env_type") == "multi":
+        # MultiTaskConfig (mapox, third party): one task id per sub-environment, agents = sum(num * agents per env);
+        # envs whose per-env agent count lives in mapox (scouts) take `agents_per_env`
+        def _agents(e):
+            if "num_agents" in e:
+                return e["num_agents"]
+            if "num_sneakers" in e:
+                return e["num_sneakers"] + e.get("num_chasers", 0)
+            if agents_per_env is None:
+                raise ValueError(f"agents per env of {e.get('env_type')!r} lives in mapox: pass agents_per_env")
+            return agents_per_env
+        total_agents = sum(e["num"] * _agents(e["env"]) for e in env["envs"])
+        model = replace(model, task_count=len(env["envs"]))
+    else:
+        apn = agents_per_env if agents_per_env is not None else env.get("num_agents", 1)
+        total_agents = j.get("num_envs", 1) * apn
+    return RunConfig(name=path, model=model, ppo=ppo, optimizer=opt, num_agents=total_agents,
                      update_steps=j["update_steps"], seed=j["seed"] if isinstance(j["seed"], int) else 42)
+
+
+def _unsupported_model_options(m: dict) -> list:
+    """The engine hardcodes what every config BASELINE.json names uses: tanh-GELU GLU blocks,
+    RMSNorm, attention history without qk-norm / post-norms, bf16 compute over fp32 parameters, an HL-Gauss head.
+    Anything else must be rejected, not silently run as a different network (TransformerActorCriticConfig,
+    mapox_trainer/config.py:80-101 with its defaults)."""
+    layer = m.get("layer", {})
+    hist = layer.get("history") or {}
+    bad = []
+    if m.get("value", {}).get("type") != "hl_gauss":
+        bad.append("value.type != hl_gauss (mse is craftax-only)")
+    if m.get("activation") != "gelu":
+        bad.append(f"activation={m.get('activation')!r} (gelu only)")
+    if m.get("norm") != "rms_norm":
+        bad.append(f"norm={m.get('norm')!r} (rms_norm only)")
+    if m.get("dtype", "float32") != "bfloat16":
+        bad.append(f"dtype={m.get('dtype', 'float32')!r} (bfloat16 only)")
+    if m.get("param_dtype", "float32") != "float32":
+        bad.append(f"param_dtype={m.get('param_dtype')!r} (float32 only)")
+    if m.get("kernel_init", "glorot_uniform") != "glorot_uniform":
+        bad.append(f"kernel_init={m.get('kernel_init')!r} (glorot_uniform only; affects initialisation, not kernels)")
+    if hist.get("type", "attention") != "attention" or not hist:
+        bad.append(f"layer.history.type={hist.get('type')!r} (attention only)")
+    if hist.get("use_qk_norm", False):
+        bad.append("layer.history.use_qk_norm=true")
+    if layer.get("use_post_attn_norm", False) or layer.get("use_post_ffw_norm", False):
+        bad.append("layer.use_post_attn_norm / use_post_ffw_norm")
+    if not layer.get("feed_forward", {}).get("glu", True):
+        bad.append("layer.feed_forward.glu=false")
+    if m.get("obs_encoder", {}).get("obs_type") not in ("grid_cnn", "grid_flattened"):
+        bad.append(f"obs_encoder.obs_type={m.get('obs_encoder', {}).get('obs_type')!r}")
+    return bad
 
 
 _BASE = ModelConfig()
@@ -128,9 +185,11 @@ NAMED = {
     "return_2_layers": RunConfig("return_2_layers", _BASE),
     "return_8_layers": RunConfig("return_8_layers", replace(_BASE, num_layers=8)),
     "multitask": RunConfig("multitask", replace(_BASE, hidden_features=256, num_layers=16, task_count=4),
-                           ppo=PPOConfig(minibatch_count=32, discount=0.99, gae_lambda=0.91)),
+                           ppo=PPOConfig(minibatch_count=32, discount=0.99, gae_lambda=0.91),
+                           optimizer=OptimizerConfig(learning_rate=0.003)),
     "blog_32_layers": RunConfig("blog_32_layers",
                                 replace(_BASE, num_layers=32, obs_type="grid_flattened", obs_shape=(5, 5),
                                         obs_max_value=(8,)),
-                                ppo=PPOConfig(normalize_advantage=False)),
+                                ppo=PPOConfig(normalize_advantage=False, entropy_coef=8.270466882977551e-05),
+                                update_steps=3800),
 }

@@ -32,8 +32,6 @@ extern int g_attn_decode_impl;
 extern int g_attn_train_impl;
 extern int g_glu_fused_cluster;
 extern int g_value_fused_cluster;
-extern int g_obs_fused_swap;
-extern int g_gemm_dbg_mode;
 
 }  // namespace mpx
 
@@ -64,16 +62,8 @@ extern "C" int mpx_debug_set(int key, int value) {
     mpx::g_value_fused_cluster = value;
     return MPX_OK;
   }
-  if (key == 5) {
-    mpx::g_obs_fused_swap = value;
-    return MPX_OK;
-  }
   if (key == 6) {
     mpx::g_use_pdl = value;
-    return MPX_OK;
-  }
-  if (key == 7) {
-    mpx::g_gemm_dbg_mode = value;
     return MPX_OK;
   }
   mpx::set_error("mpx_debug_set: unknown key %d", key);

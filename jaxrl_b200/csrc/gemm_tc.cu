@@ -22,7 +22,6 @@
 namespace mpx {
 
 int g_debug_swap_lbo_sbo = 0;
-int g_gemm_dbg_mode = 0;
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
@@ -49,7 +48,6 @@ struct GemmParams {
   const float* norm_scale;   // EPI_QKV, K == 128: RMSNorm(x; scale, eps) applied to the A tile in shared memory first
   float norm_eps;
   int tma_store;             // EPI_STORE: bf16 outputs (y, y_pre) leave through per-warp TMA bulk stores (tm_y, tm_ypre)
-  int dbg_mode;              // mpx_debug_set(7, v) experiments: 1 = epilogue without global stores, 2 = no epilogue work, 4 = no TMA stores
   // EPI_QKV
   const int32_t* pos;
   int pos_len;
@@ -192,7 +190,7 @@ __device__ __forceinline__ void epi_store(const GemmParams& p, int row0, int lan
                                           const CUtensorMap* tm_ypre, uint32_t& sel) {
   if (row0 >= p.M || col0 >= p.N) return;                 // warp-uniform
   const int row = row0 + lane;
-  const int rows_valid = (p.dbg_mode & 1) ? 0 : min(32, p.M - row0);
+  const int rows_valid = min(32, p.M - row0);
   const bool full = (col0 + 32 <= p.N);
   if (p.y_f32 && row < p.M) {
     float* d = p.y_f32 + (long long)row * p.ldy32 + col0;
@@ -348,7 +346,7 @@ __device__ __forceinline__ void epi_qkv(const GemmParams& p, int row0, int lane,
 __device__ __forceinline__ void epi_glu(const GemmParams& p, int row0, int lane, int hcol0, const uint32_t (&u)[32],
                                         const uint32_t (&g)[32], uint32_t xp) {
   if (row0 >= p.M || hcol0 >= p.F) return;
-  const int rows_valid = (p.dbg_mode & 1) ? 0 : min(32, p.M - row0);
+  const int rows_valid = min(32, p.M - row0);
   uint32_t uw[16], gw[16], hw[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -581,7 +579,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
           tmem_ld_32x32(t_row + c, u);
           tmem_ld_32x32(t_row + 128 + c, g);
           tmem_ld_wait();
-          if (!(p.dbg_mode & 2)) epi_glu(p, row0, lane, n_blk * 128 + c, u, g, xp);
+          epi_glu(p, row0, lane, n_blk * 128 + c, u, g, xp);
         }
       } else if constexpr (EPI == EPI_PAIRSUM) {
         {
@@ -600,7 +598,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
             uint32_t acc[32];
             tmem_ld_32x32(t_row + c, acc);
             tmem_ld_wait();
-            if (!(p.dbg_mode & 2)) epi_store(p, row0, lane, n_blk * BLOCK_N + c, acc, xp, rpre[j], have_pre, &tm_y, &tm_ypre, xsel);
+            epi_store(p, row0, lane, n_blk * BLOCK_N + c, acc, xp, rpre[j], have_pre, &tm_y, &tm_ypre, xsel);
           }
         }
       } else if constexpr (EPI == EPI_STORE) {
@@ -616,7 +614,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
           uint32_t acc[32];
           tmem_ld_32x32(t_row + c, acc);
           tmem_ld_wait();
-          if (!(p.dbg_mode & 2)) epi_store(p, row0, lane, col0, acc, xp, rcur, have, &tm_y, &tm_ypre, xsel);
+          epi_store(p, row0, lane, col0, acc, xp, rcur, have, &tm_y, &tm_ypre, xsel);
         }
       } else {
 #pragma unroll 1
@@ -1069,11 +1067,10 @@ static int launch_tn(const GemmParams& p, const void* a, long long lda, const vo
   const int tiles = ceil_div(p.M, BLOCK_M) * (EPI == EPI_PAIRSUM ? 1 : ceil_div(p.N, BLOCK_N));
   const int grid = tiles < num_sms() ? tiles : num_sms();
   GemmParams pp = p;
-  pp.dbg_mode = g_gemm_dbg_mode;
   // bf16 outputs through TMA stores (32 x 32 boxes, SWIZZLE_64B) when nothing else needs the per-warp transposer
   CUtensorMap tm_y = tm_a, tm_ypre = tm_a;
   pp.tma_store = 0;
-  if (EPI == EPI_STORE && p.y && !p.residual && !p.y_f32 && !(g_gemm_dbg_mode & 4) && (p.ldy & 7) == 0 &&
+  if (EPI == EPI_STORE && p.y && !p.residual && !p.y_f32 && (p.ldy & 7) == 0 &&
       (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 && (!p.y_pre || (reinterpret_cast<uintptr_t>(p.y_pre) & 15) == 0)) {
     rc = make_tmap_bf16_2d_sw(&tm_y, p.y, p.M, p.N, p.ldy, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;

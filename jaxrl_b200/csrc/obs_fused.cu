@@ -21,7 +21,6 @@
 
 namespace mpx {
 
-int g_obs_fused_swap = 0;   // mpx_debug_set(5, 1): swap LBO/SBO of the no-swizzle descriptors (bring-up knob)
 
 constexpr int OF_AG = 32;              // agents per tile
 constexpr int OF_WORKERS = 8;          // worker warps
@@ -67,7 +66,6 @@ struct ObsFusedParams {
   __nv_bfloat16* x;               // (M, H)
   __nv_bfloat16* obs_emb;         // (M, H) or null: conv3 output before the embedding sum (tests)
   long long M;
-  int swap;
   unsigned long long* dbg;
 };
 
@@ -174,7 +172,7 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t tD2 = tmem_base;            // 3 x 32 columns
   const uint32_t tD3 = tmem_base + 128;      // 128 columns
-  const uint32_t lboA = p.swap ? 256u : 128u, sboA1 = p.swap ? 128u : 256u;
+  const uint32_t lboA = 128u, sboA1 = 256u;
   const uint32_t sbo3 = (OF_K3 / 8) * 128;   // 4608
 
   if (warp == OF_WORKERS) {
@@ -204,8 +202,8 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
         const uint32_t a2 = smem_u32(sA2), w3 = smem_u32(sW3);
 #pragma unroll
         for (int s = 0; s < OF_K3 / 16; ++s)
-          umma_bf16_1(tD3, umma_smem_desc_nosw(a2 + s * 256, p.swap ? sbo3 : 128u, p.swap ? 128u : sbo3),
-                    umma_smem_desc_nosw(w3 + s * 256, p.swap ? sbo3 : 128u, p.swap ? 128u : sbo3), idesc3, s != 0 ? 1u : 0u);
+          umma_bf16_1(tD3, umma_smem_desc_nosw(a2 + s * 256, 128u, sbo3),
+                    umma_smem_desc_nosw(w3 + s * 256, 128u, sbo3), idesc3, s != 0 ? 1u : 0u);
         umma_commit_1(c3_full);
         ph ^= 1;
       }
@@ -512,7 +510,6 @@ extern "C" int mpx_obs_embed_fused(const uint8_t* obs, const int* sizes, int K, 
   p.x = reinterpret_cast<__nv_bfloat16*>(x);
   p.obs_emb = reinterpret_cast<__nv_bfloat16*>(obs_emb);
   p.M = M;
-  p.swap = g_obs_fused_swap;
   p.dbg = g_dbg_stamps;
   static bool attr_set = false;
   if (!attr_set) {

@@ -12,7 +12,6 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-import os
 from types import SimpleNamespace
 from typing import Dict, List, Optional
 
@@ -33,7 +32,9 @@ def _round_up(n: int, m: int) -> int:
 
 class PolicyEngine:
     def __init__(self, cfg: ModelConfig, device="cuda", seed: int = 0, params: Optional[ParamStore] = None,
-                 bias_noise: float = 0.0):
+                 bias_noise: float = 0.0, fused_rollout: bool = True):
+        """fused_rollout=False runs the rollout step through the general (per-op) kernel chain even where the
+        one-kernel-per-half-block kernels apply - the chain every shape without a fused kernel takes (tests)."""
         if cfg.head_dim != 32:
             raise _lib.MpxError("head_dim must be 32 on the B200 path")
         if cfg.obs_type not in ("grid_cnn", "grid_flattened"):
@@ -49,13 +50,13 @@ class PolicyEngine:
         self.QD, self.KD = self.Nq * D, self.Nkv * D
         self.QKV = self.QD + 2 * self.KD
         self.L = cfg.num_layers
-        self.fused_glu = (H == 128 and cfg.ffn_size % 64 == 0)     # decode path: one kernel per GLU block
-        self.fused_attn_decode = (H == 128 and self.Nq == 4 and self.Nkv == 1 and self.D == 32
-                                  and os.environ.get("MPX_FUSED_ATTN_DECODE", "1") != "0")
+        glu_ok = (H == 128 and cfg.ffn_size % 64 == 0)
+        self.fused_glu = glu_ok and fused_rollout                  # decode path: one kernel per GLU block
+        self.fused_attn_decode = (H == 128 and self.Nq == 4 and self.Nkv == 1 and self.D == 32 and fused_rollout)
         # training path: the same forward kernel (keeping h) and a one-kernel backward that recomputes u, g, dh on chip
-        self.fused_glu_train = self.fused_glu and os.environ.get("MPX_FUSED_GLU_TRAIN", "1") != "0"
+        self.fused_glu_train = glu_ok
         self.fused_value = (H == 128 and cfg.value_hidden_dim is not None and cfg.value_hidden_dim % 64 == 0
-                            and cfg.value_n_logits <= 64)           # decode path: one kernel for the value path
+                            and cfg.value_n_logits <= 64 and fused_rollout)   # decode path: one kernel for the value path
         self.timescale = (torch.tensor(cfg.rope_max_wavelength, dtype=F32)
                           ** (2.0 * torch.arange(0, D // 2, dtype=F32) / D)).to(self.dev)
         sup = torch.linspace(cfg.value_min, cfg.value_max, cfg.value_n_logits + 1, dtype=F32)
@@ -85,25 +86,16 @@ class PolicyEngine:
             if c.cin % 8 != 0:
                 raise _lib.MpxError("hidden conv channels must be multiples of 8")
         # rollout path: the standard geometry (11x11 view, 3x3/2 -> 16, 3x3/1 -> 32, 3x3/1 -> 128) runs as one kernel
-        self.fused_obs = (not self.flat and H == 128 and tuple(cfg.obs_shape[:2]) == (11, 11) and len(self.conv) == 3
+        self.fused_obs = (fused_rollout and not self.flat and H == 128 and tuple(cfg.obs_shape[:2]) == (11, 11) and len(self.conv) == 3
                           and all((c.kh, c.kw) == (3, 3) for c in self.conv)
                           and [(c.sh, c.sw) for c in self.conv] == [(2, 2), (1, 1), (1, 1)]
                           and [c.cout for c in self.conv] == [16, 32, 128] and len(cfg.obs_max_value) <= 4
                           and math.prod(n + 1 for n in cfg.obs_max_value) <= 48)
         self.obs_image = ops.obs_fused_image(self.dev) if self.fused_obs else None
-        self.overlap_wgrad = os.environ.get("MPX_WGRAD_OVERLAP", "1") != "0"
-        self.side = torch.cuda.Stream(device=self.dev) if (self.overlap_wgrad and self.dev.type == "cuda") else None
-        # trip 83: starting the cache stream before griddepcontrol.wait is correct (tested) but loses 0.5 ms of rollout
-        # (the early loads compete with the tail of the preceding GLU kernel): opt-in only
-        self.early_kv_stream = (_lib.PDL_MASK & ~12) == 0 and os.environ.get("MPX_EARLY_KV", "0") == "1"
-        # mpx_linear act=2 (gelu transpose in the dgrad GEMM epilogue) is bit-identical to linear + gelu_bwd but its
-        # epilogue cannot use the TMA-store path (the pre-activation tile shares the transposer's shared memory): under ncu
-        # the fused launches cost 184 + 124 us against 51 + 93 and 44 + 35 us for the pairs (trip 89) - off by default
-        self.fuse_gelu_t = os.environ.get("MPX_FUSE_GELU_T", "0") == "1"
-        self.side2 = torch.cuda.Stream(device=self.dev) if self.side is not None else None     # early optimizer phase
-        # trip 79: the encoder's weight gradients next to its data-gradient chain gain nothing (both HBM-bound,
-        # 15.66 M vs 15.69 M env-steps/s), unlike the latency-bound Newton-Schulz launches: off by default
-        self.overlap_enc_wgrad = os.environ.get("MPX_ENC_WGRAD_OVERLAP", "0") == "1"
+        # weight-gradient GEMMs run on a side stream next to the data-gradient chain; a second one carries the early
+        # optimizer phase (Muon partition) under the observation-encoder backward
+        self.side = torch.cuda.Stream(device=self.dev)
+        self.side2 = torch.cuda.Stream(device=self.dev)
         c0 = self.conv[0] if self.conv else None
         self.onehot_wgrad = (c0 is not None and c0.k <= 128 and (c0.kh, c0.kw) == (3, 3) and c0.cout <= 64
                              and c0.cout % 8 == 0 and len(cfg.obs_max_value) <= 4)
@@ -345,15 +337,11 @@ class PolicyEngine:
             ops.flat_embed_bwd(obs, ws.dfe, p.g("obs_encoder.embedding.kernel"), p.g("obs_encoder.embedding.bias"), M,
                                self.cells)
             return
-        # The data-gradient chain (GEMM -> col2im -> GEMM ...) stays on this stream; each layer's bias / weight
-        # gradients only feed the optimizer and go to the side stream as soon as that layer's dz exists (the side
-        # stream's program order protects the shared split-K workspace).  Every buffer they read is written once per
-        # minibatch; the join at the end precedes the optimizer and the next minibatch.
+        # Data-gradient chain (GEMM -> col2im -> GEMM ...) and each layer's bias / weight gradients, all on this stream:
+        # both are HBM-bound, so running the weight gradients on the side stream gained nothing (round 1, trip 79).
         n = len(self.conv)
         dy = dx0                      # cotangent of the last conv's output (M, H)
         fused_gelu = False
-        ev = None
-        run = self._side_run if self.overlap_enc_wgrad else (lambda fn: (fn(), None)[1])
         for c in reversed(self.conv):
             last = c.j == n - 1
             rows = M * c.oh * c.ow
@@ -372,14 +360,10 @@ class PolicyEngine:
                 xin = ws.ca[c.j - 1].view(M, c.kp) if last else ws.cx[c.j]
                 ops.linear_wgrad(xin, dy, p.g(f"obs_encoder.layers.{c.j}.kernel").view(c.k, c.cout), M=rows, K=c.k,
                                  N=c.cout, ldx=c.kp, ldy=c.cout, lddw=c.cout)
-            ev = run(_wg)
+            _wg()        # on this stream: both sides of the encoder backward are HBM-bound, overlapping them gained nothing
             if c.j == 0:
                 break
-            if last and self.fuse_gelu_t:   # the layer below is never the last one: gelu transpose in the GEMM epilogue
-                ops.linear(dy, w[f"w_c{c.j}"], out=ws.dca[c.j - 1].view(M, c.k), M=rows,
-                           residual=ws.cz[c.j - 1].view(M, c.k), act=2)
-                fused_gelu = True
-            elif last:
+            if last:
                 ops.linear(dy, w[f"w_c{c.j}"], out=ws.dca[c.j - 1].view(M, c.k), M=rows)
             else:
                 ops.linear(dy, w[f"w_c{c.j}"], out=ws.dcx[c.j], M=rows)
@@ -387,7 +371,6 @@ class PolicyEngine:
                 ops.col2im(ws.dcx[c.j], ws.dca[c.j - 1], M, c.ih, c.iw, c.cin, c.kh, c.kw, c.sh, c.sw, z=ws.cz[c.j - 1])
                 fused_gelu = True
             dy = ws.dca[c.j - 1]
-        self._wait(ev)
 
     # ------------------------------------------------------------------------------------------ decode step
     def decode_step(self, ws, obs, reward, last_action, pos, action_mask=None, task_ids=None, value_out=None,
@@ -411,8 +394,7 @@ class PolicyEngine:
                 # of every step are full stream barriers, so the ring slots of earlier steps are complete and visible
                 # before this launch can begin - their stream may start under the previous kernel's tail.
                 ops.attn_decode_fused(x, p[pre + "history_norm.scale"], w[pre + "wt_qkv"], pos, self.timescale,
-                                      ws.kcache[i], ws.vcache[i], self.Nq, self.Nkv, self.D, out=ws.ao,
-                                      stable_history=self.early_kv_stream)
+                                      ws.kcache[i], ws.vcache[i], self.Nq, self.Nkv, self.D, out=ws.ao)
             elif self.H == 128:                               # pre-norm fused into the q/k/v GEMM (shared-memory prologue)
                 ops.qkv_rope(x, w[pre + "wt_qkv"], pos, self.timescale, self.Nq, self.Nkv, self.D, q=ws.q,
                              k=ws.kcache[i], v=ws.vcache[i], k_row_stride=S * self.KD, v_row_stride=S * self.KD,
@@ -525,9 +507,6 @@ class PolicyEngine:
     def _side_run(self, fn, stream=None):
         """Enqueue fn on the side stream (or `stream`), ordered after everything already on the current stream;
         returns an event recorded on that stream after fn."""
-        if not self.overlap_wgrad:
-            fn()
-            return None
         side = self.side if stream is None else stream
         main = torch.cuda.current_stream()
         ready = torch.cuda.Event()
@@ -565,11 +544,8 @@ class PolicyEngine:
             ops.linear_wgrad(ws.pv, ws.dvl, p.g("value_head.dense.kernel"), M=M, K=Vh, N=NL, ldx=Vh, ldy=64, lddw=NL)
             ops.colsum(ws.dvl, p.g("value_head.dense.bias"), M=M, N=NL, ld=64)
         self._side_run(_wg_vhead)
-        if self.fuse_gelu_t:
-            ops.linear(ws.dvl, w["w_vh_pad"], out=ws.dpv, residual=ws.zv, act=2)  # gelu' rides in the GEMM epilogue
-        else:
-            ops.linear(ws.dvl, w["w_vh_pad"], out=ws.dpv)
-            ops.gelu_bwd(ws.dpv, ws.zv, out=ws.dpv)
+        ops.linear(ws.dvl, w["w_vh_pad"], out=ws.dpv)
+        ops.gelu_bwd(ws.dpv, ws.zv, out=ws.dpv)
 
         def _wg_vmlp():
             ops.linear_wgrad(ws.xf, ws.dpv, p.g("value_mlp.kernel"), M=M, K=H, N=Vh, ldx=H, ldy=Vh, lddw=Vh)

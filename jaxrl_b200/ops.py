@@ -18,6 +18,12 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 I32 = torch.int32
 
+# kernels launched per C-ABI call where it is not one (bench.py counts `gpu_launches` from the calls of one eager update);
+# muon: prepare + 3 x 5 Newton-Schulz GEMMs + finish (phase 1), AdamW leaves + clip/apply (phase 2)
+LAUNCHES_PER_CALL = {"mpx_gae": 2, "mpx_hlgauss_loss": 2, "mpx_ppo_policy_loss": 2, "mpx_adamw_step": 2,
+                     "mpx_attn_train_bwd": 3, "mpx_muon_step:1": 17, "mpx_muon_step:2": 2, "mpx_muon_step:3": 19,
+                     "mpx_linear_wgrad": 2}
+
 
 def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     if not t.is_cuda:

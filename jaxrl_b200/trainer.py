@@ -10,8 +10,6 @@ minibatch one gradient all-reduce over NCCL and, once per rollout, an all-reduce
 
 from __future__ import annotations
 
-import os
-
 from types import SimpleNamespace
 from typing import Optional
 
@@ -66,6 +64,7 @@ class PPOTrainer:
         self.Bm = self.B // m
         seed = run.seed if seed is None else seed
         self.seed = seed
+        self.sample_seed = seed + 104729 * rank
         self.engine = PolicyEngine(self.cfg, self.dev, seed=seed)          # same seed on every rank: replicated weights
         mdist.broadcast_params(self.engine.p.flat)
         self.engine.stage_weights()
@@ -78,16 +77,7 @@ class PPOTrainer:
     def _alloc(self):
         dev, B, T, cfg = self.dev, self.B, self.T, self.cfg
         A = cfg.action_dim
-        # Rollout chains: agents are independent during the rollout, so the batch is split into `n_chains` row ranges
-        # whose decode-step chains run on separate streams inside the same CUDA graph - the latency-bound kernels of
-        # one chain fill the SMs that the other chain leaves idle (the HBM-bound attention kernels still alternate).
-        self.n_chains = int(os.environ.get("MPX_ROLLOUT_CHAINS", "1"))   # measured: 2 chains gained <2% before, and LOSE 16 ms of rollout with programmatic dependent launch on (trip 97)
-        if self.n_chains < 1 or B % (self.n_chains * 128) != 0:
-            self.n_chains = 1
-        self.Bc = B // self.n_chains
-        self.dws = self.engine.alloc_decode(B) if self.n_chains == 1 else None
-        self.dws_chain = [self.engine.alloc_decode(self.Bc) for _ in range(self.n_chains)] if self.n_chains > 1 else []
-        self.chain_streams = [torch.cuda.Stream(device=dev) for _ in range(self.n_chains - 1)]
+        self.dws = self.engine.alloc_decode(B)
         self.tws = self.engine.alloc_train(self.Bm, T)
         f = lambda *s: torch.zeros(*s, dtype=F32, device=dev)
         r = SimpleNamespace()
@@ -99,7 +89,7 @@ class PPOTrainer:
         r.pos = torch.arange(T, dtype=I32, device=dev)[:, None].repeat(1, B).contiguous()   # ts.time per step
         # The value of step t is not an input of step t+1: the rollout only keeps the trunk output of every step and
         # evaluates the value path ONCE for all (T+1)*B rows afterwards (same arithmetic, off the per-step chain).
-        self.defer_value = self.engine.fused_value and os.environ.get("MPX_DEFER_VALUE", "1") == "1"
+        self.defer_value = self.engine.fused_value
         r.hidden = torch.empty(T + 1, B, cfg.hidden_features, dtype=torch.bfloat16, device=dev) if self.defer_value else None
         # end-to-end mode: double-buffered device staging of the per-step host inputs
         r.obs_stage = [torch.empty_like(self.env.obs[0]) for _ in range(2)] if self.e2e else None
@@ -187,25 +177,9 @@ class PPOTrainer:
 
     def _rollout_body(self):
         self.engine.stage_rollout_weights()                 # weights are fixed for the whole rollout
-        if self.n_chains == 1:
-            self._rollout_chain(self.dws, slice(0, self.B), self.seed)
-            self._deferred_values()
-            return
-        main = torch.cuda.current_stream()
-        fork = torch.cuda.Event()
-        fork.record(main)
-        joins = []
-        for c in range(1, self.n_chains):
-            st = self.chain_streams[c - 1]
-            with torch.cuda.stream(st):
-                st.wait_event(fork)
-                self._rollout_chain(self.dws_chain[c], slice(c * self.Bc, (c + 1) * self.Bc), self.seed + 7919 * c)
-                ev = torch.cuda.Event()
-                ev.record(st)
-                joins.append(ev)
-        self._rollout_chain(self.dws_chain[0], slice(0, self.Bc), self.seed)
-        for ev in joins:
-            main.wait_event(ev)
+        # the sampling key is per rank: the Philox counter is the LOCAL row, so equal seeds would hand agent i of every
+        # shard the same Gumbel noise (perfectly correlated sampling across shards instead of i.i.d.)
+        self._rollout_chain(self.dws, slice(0, self.B), self.sample_seed)
         self._deferred_values()
 
     def _deferred_values(self):
@@ -246,7 +220,7 @@ class PPOTrainer:
         eng.p.grad.zero_()
         eng.forward_train(tws, b.obs[sl], batch["last_rewards"], batch["last_actions"])
         o, opt = self.o, self.opt
-        total = self.run.update_steps * self.hyp.minibatch_count * self.hyp.epoch_count
+        total = self.run.optimizer_total_steps        # train.py:360-365
         n_adam = eng.p.n_adam
 
         def muon(phases: int, gscale: float):   # optimizer.py:25-37 (muon's own eps/beta defaults; adam_b1/b2 from the config)
@@ -258,8 +232,7 @@ class PPOTrainer:
         # The Muon-labelled matrices (everything but the encoders / value head) have their gradients before the
         # observation-encoder backward starts: their all-reduce and Newton-Schulz iterations run under it on the side
         # stream; the AdamW leaves, the global-norm clip and the parameter write follow the rest of the backward.
-        early = self.run_optimizer and opt.type == "muon" and o.muon.nmat > 0 and 0 < n_adam < eng.p.numel and \
-            os.environ.get("MPX_MUON_OVERLAP", "1") == "1"
+        early = self.run_optimizer and opt.type == "muon" and o.muon.nmat > 0 and 0 < n_adam < eng.p.numel
         hook = (lambda: muon(1, mdist.allreduce_gradients(eng.p.grad[n_adam:]))) if early else None
         eng.loss_and_backward(tws, batch, self.hyp, 0.0, entropy_coef_dev=self.ent_coef, matrices_ready=hook)
         self.log_acc[:3] += tws.losses[:3]
@@ -291,7 +264,11 @@ class PPOTrainer:
         return g
 
     def warmup(self):
-        """One eager pass (sets kernel attributes, fills caches), then CUDA-graph capture of the three phases."""
+        """One eager pass (sets kernel attributes, fills caches), then CUDA-graph capture of the three phases.
+        The pass is a throw-away: parameters, optimizer moments and the device step counter are restored afterwards,
+        so training starts from the seeded initial state (LR schedule and bias correction at step 0) and the first
+        real rollout draws Gumbel stream 0."""
+        keep = self.snapshot_state()
         self._rollout_body()
         self._postprocess_body()
         self._normalize()
@@ -300,11 +277,23 @@ class PPOTrainer:
         if self.use_graphs:
             self.rollout_graph = self._capture(self._rollout_body)
             self.post_graph = self._capture(self._postprocess_body)
-            # world > 1: the update graph then contains the NCCL gradient all-reduces (MPX_GRAPH_NCCL=0 keeps it eager)
-            if self.world == 1 or os.environ.get("MPX_GRAPH_NCCL", "1") == "1":
-                self.update_graph = self._capture(self._update_body)
+            # world > 1: the update graph contains the NCCL gradient all-reduces
+            self.update_graph = self._capture(self._update_body)
             torch.cuda.synchronize()
+        self.restore_state(keep)
         self.log_acc.zero_()
+        torch.cuda.synchronize()
+
+    def snapshot_state(self):
+        """Copies of everything an update mutates: parameters, optimizer moments, the device step counter."""
+        o, p = self.o, self.engine.p
+        return [t.clone() for t in (p.flat, o.mu, o.nu, o.step)]
+
+    def restore_state(self, keep):
+        o, p = self.o, self.engine.p
+        for dst, src in zip((p.flat, o.mu, o.nu, o.step), keep):
+            dst.copy_(src)
+        self.engine.stage_weights()
 
     def train_step(self):
         """One outer PPO update (train.py:_global_step): returns the device tensor of summed minibatch losses."""

@@ -401,7 +401,7 @@ def rollout_decode(p: dict, cfg, obs_seq: torch.Tensor, reward_seq: torch.Tensor
     centers = calculate_supports(cfg.value_min, cfg.value_max, cfg.value_n_logits)[1]
     carry = initialize_carry(cfg, B, dtype)
     last_action = torch.zeros(B, dtype=torch.int32)
-    out = dict(actions=[], log_prob=[], values=[], last_actions=[], last_rewards=[], rewards=[])
+    out = dict(actions=[], log_prob=[], values=[], last_actions=[], last_rewards=[], rewards=[], logits=[])
 
     def mk(t, la):
         am = None if action_mask_seq is None else action_mask_seq[t][:, None]
@@ -417,6 +417,7 @@ def rollout_decode(p: dict, cfg, obs_seq: torch.Tensor, reward_seq: torch.Tensor
         lp = categorical_log_prob(logits[:, 0], action)
         value = hlgauss_get_value(vlogits[:, 0], centers)
         out["actions"].append(action); out["log_prob"].append(lp); out["values"].append(value)
+        out["logits"].append(logits[:, 0])
         out["last_actions"].append(last_action.clone()); out["last_rewards"].append(reward_seq[t])
         out["rewards"].append(reward_seq[t + 1])
         last_action = action

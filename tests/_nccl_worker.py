@@ -1,0 +1,91 @@
+"""Worker of tests/test_gpu_nccl.py: launched by torchrun with 2 ranks, one per GPU (NCCL).
+
+Checks, on real GPUs, what the env-sharded data-parallel design relies on:
+  1. averaging the all-reduced shard gradients of 2 x (B/2) rows equals the 1 x B gradient (every loss term is a mean
+     over equal shards, train.py:204-212, values.py:63);
+  2. after a PPOTrainer.train_step() with the gradient all-reduce inside the CUDA graph, parameters stay bit-identical
+     across ranks, while the shards sample with different Gumbel streams (per-rank sampling key).
+Exit code 0 = pass; any assertion failure propagates through torchrun.
+"""
+
+import datetime
+import os
+import sys
+from dataclasses import replace
+
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
+    from jaxrl_b200 import dist as mdist, ops
+    from jaxrl_b200.config import NAMED, ModelConfig, PPOConfig
+    from jaxrl_b200.engine import PolicyEngine
+    from jaxrl_b200.trainer import PPOTrainer
+    from _parity import make_batch
+
+    dev = "cuda"
+    # ---- 1. sharded gradient == full-batch gradient
+    cfg = ModelConfig(num_layers=2, max_seq_length=128, action_dim=6)
+    hyp = PPOConfig()
+    B, T = 8, 128
+    batch = make_batch(cfg, T, B, seed=77)               # same on both ranks
+
+    def grads_of(rows):
+        eng = PolicyEngine(cfg, dev, seed=3, bias_noise=0.05)
+        ws = eng.alloc_train(rows.stop - rows.start, T)
+        d = {k: v[rows].contiguous().to(dev) for k, v in batch.items()}
+        eng.forward_train(ws, d["obs"], d["last_rewards"].reshape(-1), d["last_actions"].reshape(-1),
+                          action_mask=d["action_mask"])
+        eng.p.grad.zero_()
+        flat = {k: (v.reshape(-1) if v.dim() == 2 else v) for k, v in d.items()}
+        eng.loss_and_backward(ws, flat, hyp, progress=0.0)
+        torch.cuda.synchronize()
+        return eng
+
+    per = B // world
+    eng = grads_of(slice(rank * per, (rank + 1) * per))
+    scale = mdist.allreduce_gradients(eng.p.grad)
+    assert scale == 1.0 / world
+    sharded = eng.p.grad * scale
+    full = grads_of(slice(0, B)).p.grad
+    for name, (off, shape) in eng.p.offsets.items():
+        n = 1
+        for s in shape:
+            n *= s
+        a, b = sharded[off:off + n], full[off:off + n]
+        rel = ((a - b).norm() / (b.norm() + 1e-12)).item()
+        assert rel < 2e-3, f"rank {rank}: sharded vs full gradient of {name}: rel l2 {rel}"
+    # ---- 2. trainer: replicated parameters stay identical, sampling streams differ
+    run = replace(NAMED["test"], num_agents=32, seed=9)
+    tr = PPOTrainer(run, rank=rank, world=world, use_graphs=True)
+    tr.warmup()
+    for _ in range(2):
+        tr.train_step()
+    torch.cuda.synchronize()
+    flat = tr.engine.p.flat
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    assert all(torch.equal(gathered[0], g) for g in gathered[1:]), "parameters diverged across ranks"
+    assert torch.isfinite(flat).all()
+    noise = ops.gumbel_noise(torch.empty(16, cfg.action_dim, device=dev), tr.sample_seed, 0)
+    ng = [torch.empty_like(noise) for _ in range(world)]
+    dist.all_gather(ng, noise)
+    assert not torch.equal(ng[0], ng[1]), "ranks must not share Gumbel noise"
+    logs = tr.logs()
+    assert all(abs(v) < 1e3 for v in logs.values())
+    dist.barrier()
+    if rank == 0:
+        print("NCCL_WORKER_OK", logs, flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

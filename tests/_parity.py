@@ -1,0 +1,152 @@
+"""Model-level parity drivers shared by the GPU tests: the engine's rollout decode loop and its training
+forward / loss / backward against the CPU oracle (oracle/oracle.py) for an arbitrary ModelConfig.
+
+Tolerances: BASELINE.json's north star - indices bit exact, bf16 logits / values <= 1e-2 relative, fp32 GAE <= 1e-5.
+"Relative" for a bf16 tensor means |got - ref| <= rtol * |ref| + floor * rms(ref): entries near zero are compared on
+the scale of the tensor.  A deep stack amplifies single bf16 rounding flips (1 ulp = 2^-8 relative) of the layers
+below, so for tensors downstream of k > 1 blocks a small fraction `allow_frac` of entries may leave the band, with a
+hard cap on the largest error; tensors produced by the first block are compared with allow_frac = 0.
+"""
+
+import torch
+
+from oracle import oracle as O
+from _util import assert_close_bf16, log as _log
+
+DEV = "cuda"
+FMIN = torch.finfo(torch.float32).min
+
+
+def synth(cfg, T, B, seed, masked=True):
+    """Observation / reward / Gumbel / action-mask / task-id streams: (T+1,B,...) time-major."""
+    gen = torch.Generator().manual_seed(seed)
+    vw, vh = cfg.obs_shape[0], cfg.obs_shape[1]
+    comps = [torch.randint(0, n, (T + 1, B, vw, vh), generator=gen) for n in cfg.obs_max_value]
+    obs = (comps[0] if cfg.obs_type == "grid_flattened" else torch.stack(comps, dim=-1)).to(torch.uint8)
+    reward = (torch.rand(T + 1, B, generator=gen) < 0.1).float() * 0.5 + torch.randn(T + 1, B, generator=gen) * 0.05
+    u = torch.rand(T, B, cfg.action_dim, generator=gen).clamp(1e-6, 1 - 1e-6)
+    gumbel = -torch.log(-torch.log(u))
+    mask = torch.rand(T + 1, B, cfg.action_dim, generator=gen) < (0.8 if masked else 2.0)
+    mask[..., 0] = True
+    tasks = torch.randint(0, cfg.task_count, (B,), generator=gen).to(torch.int32) if cfg.task_count > 1 else None
+    return obs, reward, gumbel, mask, tasks
+
+
+def decode_parity(cfg, eng, steps, B, seed, name, value_atol=2e-2, logp_atol=2e-2, min_agree=0.97,
+                  deep_allow=2e-2):
+    """`steps` rollout decode steps (teacher-forced on the oracle's actions) vs O.rollout_decode: sampled actions,
+    log-probs, values per step and the KV rings of every layer at the end."""
+    from jaxrl_b200 import ops
+    obs, reward, gumbel, mask, tasks = synth(cfg, steps, B, seed)
+    p = eng.p.oracle_dict()
+    ref = O.rollout_decode(p, cfg, obs, reward, gumbel, action_mask_seq=mask, task_ids=tasks)
+    ws = eng.alloc_decode(B)
+    eng.reset_carry(ws)
+    obs_d, rew_d, gum_d, mask_d = obs.to(DEV), reward.to(DEV), gumbel.to(DEV), mask.to(DEV)
+    tasks_d = None if tasks is None else tasks.to(DEV)
+    la = torch.zeros(B, dtype=torch.int32, device=DEV)
+    agree = 0
+    worst_v = worst_lp = 0.0
+    for t in range(steps):
+        pos = torch.full((B,), t, dtype=torch.int32, device=DEV)
+        val = torch.empty(B, dtype=torch.float32, device=DEV)
+        logits, vlogits = eng.decode_step(ws, obs_d[t].contiguous(), rew_d[t].contiguous(), la, pos,
+                                          action_mask=mask_d[t].contiguous(), task_ids=tasks_d, value_out=val)
+        act, lp = ops.policy_sample(logits, gum_d[t].contiguous())
+        torch.testing.assert_close(val, ops.hlgauss_value(vlogits, eng.centers), rtol=1e-5, atol=1e-5)
+        assert (logits.cpu()[~mask[t]] == FMIN).all(), "masked logits must be finfo(f32).min"
+        same = act.cpu() == ref["actions"][:, t]
+        agree += same.sum().item()
+        dlp = (lp.cpu()[same] - ref["log_prob"][:, t][same]).abs().max().item() if same.any() else 0.0
+        dv = (val.cpu() - ref["values"][:, t]).abs().max().item()
+        worst_lp, worst_v = max(worst_lp, dlp), max(worst_v, dv)
+        la = ref["actions"][:, t].to(DEV)
+    frac = agree / (steps * B)
+    _log(f"{name}: decode {steps} steps B={B}: action agreement {frac:.4f} max|dlogp|={worst_lp:.3e} max|dvalue|={worst_v:.3e}")
+    assert frac >= min_agree, f"{name}: sampled-action agreement {frac}"
+    assert worst_lp <= logp_atol, f"{name}: log-prob error {worst_lp}"
+    assert worst_v <= value_atol, f"{name}: value error {worst_v}"
+    S = cfg.max_seq_length
+    n = min(steps, S)
+    for i in range(cfg.num_layers):
+        kw = dict(rtol=1e-2, abs_floor_frac=1e-2, allow_frac=deep_allow if i > 0 else 0.0, max_err_frac=8e-2)
+        assert_close_bf16(ws.kcache[i][:, :n], ref["carry"][i].key[:, :n], f"{name} kcache layer {i}", **kw)
+        assert_close_bf16(ws.vcache[i][:, :n], ref["carry"][i].value[:, :n], f"{name} vcache layer {i}", **kw)
+        if n < S:
+            assert (ws.kcache[i][:, n:] == 0).all() and (ws.vcache[i][:, n:] == 0).all()
+    return frac
+
+
+def make_batch(cfg, T, B, seed, masked=True):
+    obs, reward, gumbel, mask, tasks = synth(cfg, T, B, seed, masked=masked)
+    gen = torch.Generator().manual_seed(seed + 100)
+    perm = (1, 0) + tuple(range(2, obs.dim()))
+    batch = dict(
+        obs=obs[:T].permute(*perm).contiguous(), action_mask=mask[:T].permute(1, 0, 2).contiguous(),
+        last_rewards=reward[:T].t().contiguous(),
+        last_actions=torch.randint(0, cfg.action_dim, (B, T), generator=gen).to(torch.int32),
+        terminated=torch.zeros(B, T, dtype=torch.bool),
+        log_prob=-torch.rand(B, T, generator=gen) * 2 - 0.2, advantages=torch.randn(B, T, generator=gen),
+        targets=torch.randn(B, T, generator=gen) * 2)
+    # actions must be unmasked
+    score = batch["action_mask"].float() * torch.rand(B, T, cfg.action_dim, generator=gen)
+    batch["actions"] = torch.argmax(score, dim=-1).to(torch.int32)
+    if tasks is not None:
+        batch["task_ids"] = tasks[:, None].expand(B, T).contiguous()
+    return batch
+
+
+def train_parity(cfg, eng, hyp, T, B, seed, name, progress=0.3, logits_allow=2e-3, grad_rel=2.5e-2, grad_cos=0.9995,
+                 loss_rtol=1e-2):
+    """forward_train + loss_and_backward vs O.ppo_loss and torch autograd: logits, value logits, values, the three
+    losses and every parameter gradient."""
+    from jaxrl_b200 import ops
+    batch = make_batch(cfg, T, B, seed)
+    p = {k: v.clone().requires_grad_(True) for k, v in eng.p.oracle_dict().items()}
+    total, logs = O.ppo_loss(p, cfg, hyp, batch, progress=progress)
+    total.backward()
+    with torch.no_grad():
+        vl_ref, lg_ref, _ = O.model_forward({k: v.detach() for k, v in p.items()}, cfg,
+                                            O.TimeStep(obs=batch["obs"], time=torch.arange(T, dtype=torch.int32)[None],
+                                                       terminated=batch["terminated"], last_action=batch["last_actions"],
+                                                       reward=batch["last_rewards"], action_mask=batch["action_mask"],
+                                                       task_ids=batch.get("task_ids")))
+    ws = eng.alloc_train(B, T)
+    d = {k: v.to(DEV) for k, v in batch.items()}
+    tasks_flat = d["task_ids"].reshape(-1) if "task_ids" in d else None
+    vlogits, logits = eng.forward_train(ws, d["obs"], d["last_rewards"].reshape(-1), d["last_actions"].reshape(-1),
+                                        action_mask=d["action_mask"], task_ids=tasks_flat)
+    A = cfg.action_dim
+    lg = logits.cpu().reshape(B, T, A)
+    live = batch["action_mask"]
+    assert (lg[~live] == FMIN).all()
+    assert_close_bf16(lg[live], lg_ref[live], f"{name} train logits", rtol=1e-2, abs_floor_frac=2e-2, allow_frac=logits_allow,
+                      max_err_frac=6e-2)
+    assert_close_bf16(vlogits.cpu().reshape(B, T, -1), vl_ref, f"{name} train vlogits", rtol=1e-2, abs_floor_frac=2e-2,
+                      allow_frac=logits_allow, max_err_frac=6e-2)
+    centers = O.calculate_supports(cfg.value_min, cfg.value_max, cfg.value_n_logits)[1]
+    val = ops.hlgauss_value(vlogits, eng.centers).cpu().reshape(B, T)
+    torch.testing.assert_close(val, O.hlgauss_get_value(vl_ref, centers), rtol=1e-2, atol=2e-2)
+    eng.p.grad.zero_()
+    flat = {k: (v.reshape(-1) if v.dim() == 2 else v) for k, v in d.items()}
+    losses = eng.loss_and_backward(ws, flat, hyp, progress=progress)
+    torch.cuda.synchronize()
+    l = losses.cpu()
+    _log(f"{name}: losses gpu value={l[0]:.5f} actor={l[1]:.5f} ent={l[2]:.5f} | ref value={logs['value_loss']:.5f} "
+         f"actor={logs['actor_loss']:.5f} ent={logs['entropy_loss']:.5f}")
+    for got, key, floor in ((l[0], "value_loss", 1e-3), (l[1], "actor_loss", 2e-3), (l[2], "entropy_loss", 1e-3)):
+        want = logs[key].item()
+        assert abs(got.item() - want) <= loss_rtol * abs(want) + floor, f"{name} {key}: {got.item()} vs {want}"
+    grads = eng.p.grad_dict()
+    worst = 0.0
+    for pname, gref in ((k, v.grad) for k, v in p.items()):
+        gg = grads[pname]
+        denom = gref.norm().item() + 1e-8
+        rel = (gg - gref).norm().item() / denom
+        cos = (gg * gref).sum().item() / (gg.norm().item() * gref.norm().item() + 1e-12)
+        _log(f"{name} grad {pname}: rel_l2={rel:.4f} cos={cos:.5f} |ref|={denom:.3e}")
+        worst = max(worst, rel)
+        assert cos > grad_cos, f"{name}: gradient direction mismatch for {pname}: cos={cos}"
+        assert rel < grad_rel, f"{name}: gradient mismatch for {pname}: rel l2 {rel}"
+    _log(f"{name}: worst gradient rel_l2 {worst:.4f}")
+    return worst

@@ -4,6 +4,11 @@ import os
 
 import torch
 
+# Flash-style (online-softmax) attention rounds the UN-normalised probabilities to bf16 - as cuDNN's fused SDPA, the
+# reference's GPU implementation, does - while the XLA restatement rounds after normalising: outputs may differ by up
+# to 2 bf16 ulps (2 * 2^-7 relative at the bottom of a binade).  Every other bf16 result is held to 1e-2.
+ULP2 = 2.0 ** -6
+
 
 def log(msg):
     os.makedirs("gpurun_out", exist_ok=True)

@@ -8,7 +8,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import oracle as O  # noqa: E402
-from _util import assert_close_bf16, log as _log, rope_timescale as _rope_timescale  # noqa: E402
+from _util import ULP2, assert_close_bf16, log as _log, rope_timescale as _rope_timescale  # noqa: E402
 
 DEV = "cuda"
 BF16 = torch.bfloat16
@@ -51,12 +51,12 @@ def test_attn_train_fwd_bwd(B, T, Nq, Nkv, impl):
         lib.mpx_debug_set(2, 0)
     # flash-style online softmax rounds the UN-normalised probabilities to bf16 (as cuDNN's fused SDPA, the
     # reference's GPU implementation, does); the XLA path rounds after normalising -> up to 2 bf16 ulps apart.
-    assert_close_bf16(o.reshape(B, T, Nq, D), ref, f"attn_train_fwd impl{impl} B{B} T{T} kv{Nkv}", rtol=1.7e-2, abs_floor_frac=1e-2,
-                      allow_frac=5e-4, max_err_frac=0.25)
+    assert_close_bf16(o.reshape(B, T, Nq, D), ref, f"attn_train_fwd impl{impl} B{B} T{T} kv{Nkv}", rtol=ULP2, abs_floor_frac=1e-2,
+                      allow_frac=2e-4, max_err_frac=0.15)
     got = dqkv.float().cpu()
     for name, g, ref_g in (("dq", got[:, :QD], q0.grad.reshape(B * T, QD)),
                            ("dk", got[:, QD:QD + KD], k0.grad.reshape(B * T, KD)),
                            ("dv", got[:, QD + KD:], v0.grad.reshape(B * T, KD))):
         rel = (g - ref_g).norm().item() / (ref_g.norm().item() + 1e-9)
         _log(f"attn_train_bwd impl{impl} B{B} T{T} kv{Nkv} {name}: rel_l2={rel:.4e}")
-        assert rel < 3e-2, f"{name} rel l2 error {rel}"
+        assert rel < 8e-3, f"{name} rel l2 error {rel}"

@@ -10,7 +10,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from _util import assert_close_bf16, rope_timescale  # noqa: E402
+from _util import ULP2, assert_close_bf16, rope_timescale  # noqa: E402
 
 DEV = "cuda"
 BF16 = torch.bfloat16
@@ -87,7 +87,7 @@ def test_decode_attention_fixture(ops, impl):
             out = ops.attn_decode(q.reshape(B, Nq * D).to(DEV), kc, vc, pos, Nq, kc.shape[2], D)
             torch.cuda.synchronize()
             assert_close_bf16(out.reshape(B, Nq, D), torch.from_numpy(z[f"decode_out_len{kv_len}"])[:, 0],
-                              f"decode attention fixture impl={impl} kv_len={kv_len}", rtol=1.7e-2 if impl == 0 else 1e-2,
+                              f"decode attention fixture impl={impl} kv_len={kv_len}", rtol=ULP2 if impl == 0 else 1e-2,
                               abs_floor_frac=1e-2 if impl == 0 else 4e-3)
     finally:
         lib.mpx_debug_set(1, 0)
@@ -110,7 +110,7 @@ def test_train_attention_fixture(ops, impl):
     finally:
         lib.mpx_debug_set(2, 0)
     assert_close_bf16(o.reshape(B, T, Nq, D), torch.from_numpy(z["train_out"]), f"train attention fixture impl={impl}",
-                      rtol=1.7e-2, abs_floor_frac=1e-2)
+                      rtol=ULP2, abs_floor_frac=1e-2)
 
 
 def test_model_forward_fixture(ops):

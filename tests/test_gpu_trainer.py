@@ -1,8 +1,7 @@
-"""GPU: the PPO trainer end to end on the tiny `test` config - CUDA-graph capture of the three phases, the
-end-to-end mode whose observations arrive from pinned host memory through the double-buffered copy stream, and
-multi-chain rollouts.  Same seeds => the rollout (actions, log-probs, values) must be bit-identical across modes."""
-
-import os
+"""GPU: the PPO trainer end to end on the tiny `test` config - CUDA-graph capture of the three phases and the
+end-to-end mode whose observations arrive from pinned host memory through the double-buffered copy stream.
+Same seeds => the rollout (actions, log-probs, values) must be bit-identical across modes.  Parity of the whole step
+against the oracle pipeline is in test_gpu_composed.py."""
 
 import pytest
 import torch
@@ -57,21 +56,3 @@ def test_trainer_updates_parameters_and_is_deterministic():
     # orthogonalisation amplifies such last-bit differences on small-gradient matrices, hence the loose band)
     assert (outs[0][1] == outs[1][1]).float().mean().item() >= 0.98
     torch.testing.assert_close(outs[0][0], outs[1][0], rtol=0, atol=2e-3)
-
-
-def test_rollout_chains_match_single_chain():
-    from jaxrl_b200.trainer import PPOTrainer
-    from dataclasses import replace
-    run = replace(NAMED["test"], num_agents=256)
-    os.environ["MPX_ROLLOUT_CHAINS"] = "2"
-    try:
-        two = PPOTrainer(run, use_graphs=True, seed=3)
-    finally:
-        os.environ.pop("MPX_ROLLOUT_CHAINS", None)
-    assert two.n_chains == 2
-    two.warmup()
-    two.train_step()
-    torch.cuda.synchronize()
-    v = two.r.values
-    assert torch.isfinite(v).all() and torch.isfinite(two.r.log_prob).all()
-    assert (two.r.actions_ext[1:] >= 0).all() and (two.r.actions_ext[1:] < run.model.action_dim).all()
