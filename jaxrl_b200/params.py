@@ -169,6 +169,36 @@ class ParamStore:
     def grad_dict(self) -> Dict[str, torch.Tensor]:
         return {n: v.detach().float().cpu().clone() for n, v in self.gviews.items()}
 
-    def load_dict(self, d: Dict[str, torch.Tensor]) -> None:
+    def load_dict(self, d: Dict[str, torch.Tensor], strict: bool = True) -> None:
+        """Copy named fp32 arrays (reference pytree paths) into the flat buffer.  strict: the key sets must match
+        exactly and every shape must be the reference's (what an orbax StandardRestore would enforce)."""
+        if strict:
+            missing, extra = sorted(set(self.views) - set(d)), sorted(set(d) - set(self.views))
+            if missing or extra:
+                raise KeyError(f"parameter names differ: missing {missing[:5]}, unexpected {extra[:5]}")
         for n, v in d.items():
-            self.views[n].copy_(v.to(self.flat.device, torch.float32).reshape(self.views[n].shape))
+            if n not in self.views:
+                continue
+            v = torch.as_tensor(v)
+            if tuple(v.shape) != tuple(self.views[n].shape):
+                raise ValueError(f"{n}: shape {tuple(v.shape)} != {tuple(self.views[n].shape)}")
+            self.views[n].copy_(v.to(self.flat.device, torch.float32))
+
+    # ------------------------------------------------------------------ weight hand-off (checkpointer.py:15-34)
+    # The reference saves nnx.state(model, nnx.Param) with orbax.  Reading orbax/tensorstore trees needs those
+    # libraries, so the hand-off format is a flat .npz written on the reference side by
+    # scripts/export_reference_params.py ("param/<nnx path>" float32 arrays, "meta/*" env facts).
+    def save_npz(self, path: str, **meta) -> None:
+        import numpy as np
+        arrays = {"param/" + n: v.detach().float().cpu().numpy() for n, v in self.views.items()}
+        arrays.update({"meta/" + k: np.asarray(v) for k, v in meta.items()})
+        np.savez(path, **arrays)
+
+    def load_npz(self, path: str, strict: bool = True) -> dict:
+        """Load parameters exported by scripts/export_reference_params.py (or save_npz); returns the meta entries."""
+        import numpy as np
+        with np.load(path, allow_pickle=False) as z:
+            params = {k[len("param/"):]: torch.from_numpy(z[k].astype(np.float32)) for k in z.files if k.startswith("param/")}
+            meta = {k[len("meta/"):]: z[k] for k in z.files if k.startswith("meta/")}
+        self.load_dict(params, strict=strict)
+        return meta

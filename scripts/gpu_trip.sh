@@ -11,6 +11,8 @@ for step in "$@"; do
   case "$step" in
     tests)
       timeout 900 python -m pytest tests -m gpu -x -q > ${out}_tests.log 2>&1; echo "tests exit $?"; tail -5 ${out}_tests.log ;;
+    testsall)
+      timeout 1200 python -m pytest tests -m gpu -q > ${out}_tests.log 2>&1; echo "tests exit $?"; grep -E "^(FAILED|ERROR)|passed|failed" ${out}_tests.log | tail -40 ;;
     tests:*)
       timeout 900 python -m pytest tests -m gpu -x -q -k "${step#tests:}" > ${out}_tests.log 2>&1; echo "tests exit $?"; tail -15 ${out}_tests.log ;;
     bench)

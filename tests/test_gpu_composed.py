@@ -82,7 +82,7 @@ def test_rollout_matches_oracle(stepped):
     dv = (tr.r.values[:T].t().cpu() - ref["values"][:, :T]).abs()[lead].max().item()
     dl = (tr.r.log_prob.t().cpu() - ref["log_prob"]).abs()[lead].max().item()
     _log(f"composed rollout: max|dvalue|={dv:.3e} max|dlogp|={dl:.3e} (steps before divergence)")
-    assert dv <= 2e-2 and dl <= 2e-2
+    assert dv <= 2.5e-2 and dl <= 1e-2
     # bootstrap value (train.py:142-148 quirk: initial timestep, empty carry) - independent of the sampled actions
     db = (tr.r.values[T].cpu() - ref["values"][:, T]).abs().max().item()
     assert db <= 2e-2, f"bootstrap value error {db}"
@@ -137,7 +137,7 @@ def test_minibatch_gradient_matches_oracle(stepped):
     for name, t in p.items():
         rel = (grads[name] - t.grad).norm().item() / (t.grad.norm().item() + 1e-8)
         _log(f"composed minibatch grad {name}: rel_l2={rel:.4f}")
-        assert rel < 2.5e-2, f"{name}: rel l2 {rel}"
+        assert rel < 1.2e-2, f"{name}: rel l2 {rel}"
     got = tr.tws.losses.cpu()
     assert abs(got[0].item() - logs["value_loss"].item()) <= 1e-2 * abs(logs["value_loss"].item()) + 1e-3
     assert abs(got[1].item() - logs["actor_loss"].item()) <= 1e-2 * abs(logs["actor_loss"].item()) + 2e-3
@@ -149,7 +149,8 @@ def test_full_step_parameter_update_matches_oracle(opt_type):
     """The whole step with the optimizer on: the oracle repeats the m sequential (ppo_loss -> autograd -> optimizer)
     steps on the trainer's own batch-major arrays; compared: averaged minibatch losses and the parameter update.
     Both optimizers normalise the gradient (Newton-Schulz orthogonalisation / sign-like first Adam steps), which maps a
-    0.5 % bf16 gradient error onto a few per cent of the update - hence direction + norm, not 1e-2 elementwise."""
+    0.5 % bf16 gradient error onto a few per cent of the update (measured: rel l2 4.2 % muon / 3.8 % adamw, cosine
+    0.9993, norm ratio 1.000) - hence direction + norm + 8 % rel l2, not 1e-2 elementwise."""
     from jaxrl_b200.trainer import PPOTrainer
     run = replace(RUN, optimizer=replace(RUN.optimizer, type=opt_type))
     tr = PPOTrainer(run, use_graphs=True)
@@ -182,4 +183,4 @@ def test_full_step_parameter_update_matches_oracle(opt_type):
     cos = ((d_got * d_ref).sum() / (d_got.norm() * d_ref.norm())).item()
     nrm = (d_got.norm() / d_ref.norm()).item()
     _log(f"composed full step ({opt_type}): update rel_l2={rel:.4f} cos={cos:.5f} norm ratio={nrm:.4f}")
-    assert cos > 0.97 and abs(nrm - 1) < 3e-2 and rel < 0.25
+    assert cos > 0.998 and abs(nrm - 1) < 1e-2 and rel < 8e-2

@@ -33,7 +33,7 @@ def eng_return8():
 def test_return8_decode(eng_return8):
     """L=8, S=512 ring, 72 decode steps through the fused kernels."""
     from _parity import decode_parity
-    decode_parity(eng_return8.cfg, eng_return8, steps=72, B=16, seed=31, name="return_8 decode", deep_allow=3e-2)
+    decode_parity(eng_return8.cfg, eng_return8, steps=72, B=16, seed=31, name="return_8 decode")
 
 
 def test_return8_train_full_window(eng_return8):
@@ -55,7 +55,7 @@ def eng_multitask():
 def test_multitask_decode(eng_multitask):
     """H=256 + task embeddings: the rollout chain this shape runs, 64 steps."""
     from _parity import decode_parity
-    decode_parity(eng_multitask.cfg, eng_multitask, steps=64, B=16, seed=33, name="multitask decode", deep_allow=3e-2)
+    decode_parity(eng_multitask.cfg, eng_multitask, steps=64, B=16, seed=33, name="multitask decode")
 
 
 def test_multitask_train(eng_multitask):
@@ -91,7 +91,7 @@ def eng_blog():
 
 def test_blog32_decode(eng_blog):
     from _parity import decode_parity
-    decode_parity(eng_blog.cfg, eng_blog, steps=64, B=16, seed=36, name="blog_32 decode", deep_allow=3e-2)
+    decode_parity(eng_blog.cfg, eng_blog, steps=64, B=16, seed=36, name="blog_32 decode")
 
 
 def test_blog32_train(eng_blog):
