@@ -111,8 +111,8 @@ def make_batch(cfg, T, B, seed, masked=True):
     return batch
 
 
-def train_parity(cfg, eng, hyp, T, B, seed, name, progress=0.3, logits_allow=2e-3, grad_rel=2.5e-2, grad_cos=0.9995,
-                 loss_rtol=1e-2):
+def train_parity(cfg, eng, hyp, T, B, seed, name, progress=0.3, logits_allow=2e-3, logits_rel=1e-2, grad_rel=2.5e-2,
+                 grad_cos=0.9995, loss_rtol=1e-2):
     """forward_train + loss_and_backward vs O.ppo_loss and torch autograd: logits, value logits, values, the three
     losses and every parameter gradient."""
     from jaxrl_b200 import ops
@@ -139,6 +139,8 @@ def train_parity(cfg, eng, hyp, T, B, seed, name, progress=0.3, logits_allow=2e-
                       max_err_frac=6e-2)
     assert_close_bf16(vlogits.cpu().reshape(B, T, -1), vl_ref, f"{name} train vlogits", rtol=1e-2, abs_floor_frac=2e-2,
                       allow_frac=logits_allow, max_err_frac=6e-2)
+    _assert_rel_l2(lg[live], lg_ref[live], f"{name} train logits (l2)", logits_rel, 6e-2)
+    _assert_rel_l2(vlogits.cpu().reshape(B, T, -1), vl_ref, f"{name} train vlogits (l2)", logits_rel, 6e-2)
     centers = O.calculate_supports(cfg.value_min, cfg.value_max, cfg.value_n_logits)[1]
     val = ops.hlgauss_value(vlogits, eng.centers).cpu().reshape(B, T)
     torch.testing.assert_close(val, O.hlgauss_get_value(vl_ref, centers), rtol=1e-2, atol=2e-2)
