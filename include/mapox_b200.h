@@ -31,8 +31,9 @@ const char* mpx_last_error(void);
 int mpx_version(void);
 /* Debug/tuning knobs (tests only). key 0: swap LBO/SBO in MN-major UMMA descriptors.
  * key 1: decode attention implementation (0 = mma.sync online softmax, default; 1 = SIMT exact two-pass;
- * 2 = mma.sync exact two-pass).  key 2: training attention forward (0 = tcgen05/TMEM when q,k,v are packed and
- * Nkv == 1, default; 1 = mma.sync everywhere).  key 3: mpx_glu_fused cluster size (0 = auto; 1, 2 or 4 = force).
+ * 2 = mma.sync exact two-pass).  key 2: training attention (0 = tcgen05/TMEM forward and backward when q,k,v are packed
+ * and Nkv == 1 - forward with the four heads of a GQA group per CTA when Nq == 4 - default; 1 = mma.sync everywhere;
+ * 2 = tcgen05 forward with one head per CTA, mma.sync backward).  key 3: mpx_glu_fused cluster size (0 = auto; 1, 2 or 4 = force).
  * key 4: mpx_value_head_fused cluster size, same values.  key 6: programmatic dependent launch, one bit per kernel
  * family (1 = GEMM / elementwise / value head, 2 = observation encoder, 4 = decode attention, 8 = fused GLU,
  * 16 = policy head; default 12).  No key changes results beyond the documented choice of an equivalent kernel. */

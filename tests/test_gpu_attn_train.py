@@ -14,11 +14,12 @@ DEV = "cuda"
 BF16 = torch.bfloat16
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 @pytest.mark.parametrize("B,T,Nq,Nkv", [(2, 64, 4, 1), (3, 128, 4, 1), (1, 512, 4, 1), (5, 256, 4, 1), (2, 128, 4, 2),
                                         (2, 64, 4, 4)])
 def test_attn_train_fwd_bwd(B, T, Nq, Nkv, impl):
-    """impl 0: tcgen05/TMEM forward AND backward where the shape allows (Nkv == 1, T % 128 == 0), impl 1: mma.sync."""
+    """impl 0: tcgen05/TMEM forward (four heads per CTA when Nq == 4) AND backward where the shape allows (Nkv == 1,
+    T % 128 == 0), impl 1: mma.sync, impl 2: tcgen05 forward with one head per CTA."""
     from jaxrl_b200 import ops
     from jaxrl_b200._lib import lib
     lib.mpx_debug_set(2, impl)
