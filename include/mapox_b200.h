@@ -388,6 +388,15 @@ int mpx_muon_step_phased(float* params, const float* grads, float* mu, float* nu
                          int max_r, int max_c, float* ns_ws, int* step, float lr0, float total_steps, float adam_b1,
                          float adam_b2, float eps, float weight_decay, float muon_beta, int ns_steps, float max_norm,
                          float grad_scale, float* update_norm_out, void* workspace, int phases, mpx_stream_t stream);
+/* Sharded Muon (reduce-scatter -> Newton-Schulz on 1/world of the matrices -> all-gather; new: the reference is single
+ * device): after phase 1 on the LOCAL matrices (mpx_muon_step_phased, phases = 1, local table) and an all-gather of
+ * update_scratch[n_adam:], this call runs the AdamW-labelled leaves [0, n_adam), the global-norm clip over the whole
+ * update (a fixed-order sum of the gathered data: bit-identical on every rank), the parameter write and step += 1.
+ * workspace >= mpx_muon_workspace_bytes(n, 1). */
+int mpx_muon_apply_sharded(float* params, const float* grads, float* mu, float* nu, float* update_scratch, long long n,
+                           long long n_adam, int* step, float lr0, float total_steps, float adam_b1, float adam_b2,
+                           float eps, float weight_decay, float max_norm, float grad_scale, float* update_norm_out,
+                           void* workspace, mpx_stream_t stream);
 /* fp32 master weights -> bf16 GEMM operand copies. descs is a DEVICE array; each entry casts (and optionally
  * transposes) a (rows, cols) fp32 block with pitch src_ld into a bf16 destination with pitch dst_ld. */
 typedef struct {

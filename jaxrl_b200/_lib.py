@@ -143,6 +143,8 @@ lib.mpx_muon_step.argtypes = [c_p, c_p, c_p, c_p, c_p, c_ll, c_ll, c_p, c_i, c_l
                               c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_p, c_p, c_p]
 lib.mpx_muon_step_phased.argtypes = [c_p, c_p, c_p, c_p, c_p, c_ll, c_ll, c_p, c_i, c_ll, c_ll, c_i, c_i, c_p, c_p, c_f, c_f,
                                      c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_p, c_p, c_i, c_p]
+lib.mpx_muon_apply_sharded.argtypes = [c_p, c_p, c_p, c_p, c_p, c_ll, c_ll, c_p, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_p,
+                                       c_p, c_p]
 lib.mpx_prep_weights.argtypes = [c_p, c_i, c_p]
 lib.mpx_transpose_tb.argtypes = [c_p, c_p, c_p, c_i, c_i, c_i, c_p]
 

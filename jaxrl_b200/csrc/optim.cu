@@ -342,6 +342,25 @@ __global__ void __launch_bounds__(256) muon_finish_kernel(const MuonMat* __restr
   if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = s_sum[0];
 }
 
+// partials[blockIdx.x] = sum of squares of this block's grid-stride share of x (fixed order: identical on every rank that
+// holds the same data)
+__global__ void __launch_bounds__(256) sumsq_partials_kernel(const float* __restrict__ x, long long n,
+                                                             double* __restrict__ partials) {
+  __shared__ double s_sum[256];
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const double v = (double)x[i];
+    acc += v * v;
+  }
+  s_sum[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[blockIdx.x] = s_sum[0];
+}
+
 }  // namespace mpx
 
 using namespace mpx;
@@ -465,6 +484,33 @@ extern "C" int mpx_muon_step_phased(float* params, const float* grads, float* mu
     apply_update_kernel<<<pgrid, 256, 0, s>>>(params, update_scratch, n, partials, nparts, max_norm, step, update_norm_out);
     }
   return check_launch("mpx_muon_step");
+}
+
+// Second half of the SHARDED Muon step (data-parallel ranks each own 1/world of the Muon-labelled matrices): phase 1
+// (mpx_muon_step_phased, phases = 1, with the table of the LOCAL matrices) has written this rank's slice of
+// update_scratch[n_adam:], the caller has all-gathered that partition; this call updates the AdamW-labelled leaves
+// [0, n_adam), takes the global norm over the WHOLE update (every rank sums the same gathered data in the same order, so
+// the clip factor is bit-identical everywhere), applies it and increments the step counter.
+extern "C" int mpx_muon_apply_sharded(float* params, const float* grads, float* mu, float* nu, float* update_scratch,
+                                      long long n, long long n_adam, int* step, float lr0, float total_steps, float adam_b1,
+                                      float adam_b2, float eps, float weight_decay, float max_norm, float grad_scale,
+                                      float* update_norm_out, void* workspace, mpx_stream_t stream) {
+  MPX_REQUIRE(params && grads && mu && nu && update_scratch && step && workspace && n > 0 && n_adam >= 0 && n_adam <= n,
+              "mpx_muon_apply_sharded: bad arguments");
+  MPX_REQUIRE(total_steps > 0.f, "mpx_muon_apply_sharded: total_steps must be positive");
+  cudaStream_t s = (cudaStream_t)stream;
+  double* partials = reinterpret_cast<double*>(workspace);
+  const int agrid = n_adam > 0 ? opt_grid(n_adam) : 0;
+  if (n_adam > 0)
+    adamw_update_kernel<<<agrid, 256, 0, s>>>(params, grads, mu, nu, update_scratch, n_adam, step, lr0, total_steps,
+                                              adam_b1, adam_b2, eps, weight_decay, grad_scale, 1, partials);
+  int nparts = agrid;
+  if (n > n_adam) {
+    sumsq_partials_kernel<<<32, 256, 0, s>>>(update_scratch + n_adam, n - n_adam, partials + agrid);
+    nparts += 32;
+  }
+  apply_update_kernel<<<opt_grid(n), 256, 0, s>>>(params, update_scratch, n, partials, nparts, max_norm, step, update_norm_out);
+  return check_launch("mpx_muon_apply_sharded");
 }
 
 extern "C" int mpx_muon_step(float* params, const float* grads, float* mu, float* nu, float* update_scratch,

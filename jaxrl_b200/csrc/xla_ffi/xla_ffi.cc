@@ -702,6 +702,28 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(MpxMuonStep, MuonStepImpl,
                                   .Ret<F32>().Ret<F32>().Ret<F32>().Ret<S32>().Ret<F32>().Ret<F32>().Ret<F32>().Ret<U8>(),
                               MPX_TRAITS);
 
+// Second half of the sharded Muon step (after the all-gather of the Muon partition of `scratch`).
+// aliases: params(0) -> 0, mu(2) -> 1, nu(3) -> 2, step(4) -> 3, scratch(5) -> 5
+static ffi::Error MuonApplyShardedImpl(mpx_stream_t stream, F32 params_in, F32 grads, F32 mu_in, F32 nu_in, S32 step_in,
+                                       F32 scratch_in, int64_t n_adam, float lr0, float total_steps, float adam_b1,
+                                       float adam_b2, float eps, float weight_decay, float max_norm, float grad_scale,
+                                       RF32 params, RF32 mu, RF32 nu, RS32 step, RF32 update_norm, RF32 scratch,
+                                       RU8 workspace) {
+  (void)params_in; (void)mu_in; (void)nu_in; (void)step_in; (void)scratch_in;
+  MPX_CALL(mpx_muon_apply_sharded(params->typed_data(), grads.typed_data(), mu->typed_data(), nu->typed_data(),
+                                  scratch->typed_data(), static_cast<long long>(params->element_count()), n_adam,
+                                  step->typed_data(), lr0, total_steps, adam_b1, adam_b2, eps, weight_decay, max_norm,
+                                  grad_scale, update_norm->typed_data(), workspace->untyped_data(), stream),
+           "mpx_muon_apply_sharded");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(MpxMuonApplySharded, MuonApplyShardedImpl,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<S32>().Arg<F32>()
+                                  .Attr<int64_t>("n_adam").Attr<float>("lr0").Attr<float>("total_steps")
+                                  .Attr<float>("adam_b1").Attr<float>("adam_b2").Attr<float>("eps").Attr<float>("weight_decay")
+                                  .Attr<float>("max_norm").Attr<float>("grad_scale")
+                                  .Ret<F32>().Ret<F32>().Ret<F32>().Ret<S32>().Ret<F32>().Ret<F32>().Ret<U8>(),
+                              MPX_TRAITS);
+
 // fp32 master weights -> bf16 GEMM operand copies.  The descriptor table holds DEVICE pointers into XLA buffers and is
 // therefore only valid while those buffers do not move: the JAX side builds it per call from the operand addresses, or
 // (simpler) stages weights with jnp casts/transposes and skips this entry point.  Bound for completeness.

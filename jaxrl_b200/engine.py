@@ -32,7 +32,7 @@ def _round_up(n: int, m: int) -> int:
 
 class PolicyEngine:
     def __init__(self, cfg: ModelConfig, device="cuda", seed: int = 0, params: Optional[ParamStore] = None,
-                 bias_noise: float = 0.0, fused_rollout: bool = True):
+                 bias_noise: float = 0.0, fused_rollout: bool = True, world: int = 1):
         """fused_rollout=False runs the rollout step through the general (per-op) kernel chain even where the
         one-kernel-per-half-block kernels apply - the chain every shape without a fused kernel takes (tests)."""
         if cfg.head_dim != 32:
@@ -43,7 +43,7 @@ class PolicyEngine:
             raise _lib.MpxError("value_hidden_dim=None is not on the B200 path yet")
         self.cfg = cfg
         self.dev = torch.device(device)
-        self.p = params if params is not None else ParamStore(cfg, self.dev, seed, bias_noise)
+        self.p = params if params is not None else ParamStore(cfg, self.dev, seed, bias_noise, world=world)
         H, D = cfg.hidden_features, cfg.head_dim
         self.H, self.F, self.Vh, self.NL, self.A = H, cfg.ffn_size, cfg.value_hidden_dim, cfg.value_n_logits, cfg.action_dim
         self.Nq, self.Nkv, self.D = cfg.num_heads, cfg.num_kv_heads, D

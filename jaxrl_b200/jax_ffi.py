@@ -46,7 +46,8 @@ TARGETS = (
     "MpxGeluBwd", "MpxColSum", "MpxAddBf16", "MpxEmbedCombine", "MpxEmbedBwd", "MpxObsFusedPrep", "MpxObsEmbedFused",
     "MpxConv1OnehotFwd", "MpxConv1OnehotWgrad", "MpxObsOnehotIm2col", "MpxIm2col", "MpxCol2im", "MpxFlatEmbedFwd",
     "MpxFlatEmbedBwd", "MpxPolicyLogits", "MpxPolicySample", "MpxPolicyHeadSample", "MpxGumbelNoise", "MpxPpoPolicyLoss",
-    "MpxPolicyHeadBwd", "MpxValueHeadFused", "MpxAdamwStep", "MpxMuonStep", "MpxPrepWeights", "MpxTransposeTb",
+    "MpxPolicyHeadBwd", "MpxValueHeadFused", "MpxAdamwStep", "MpxMuonStep", "MpxMuonApplySharded", "MpxPrepWeights",
+    "MpxTransposeTb",
 )
 for _t in TARGETS:
     jax.ffi.register_ffi_target(_t, jax.ffi.pycapsule(getattr(_XLA_LIB, _t)), platform="CUDA")

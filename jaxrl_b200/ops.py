@@ -22,6 +22,7 @@ I32 = torch.int32
 # muon: prepare + 3 x 5 Newton-Schulz GEMMs + finish (phase 1), AdamW leaves + clip/apply (phase 2)
 LAUNCHES_PER_CALL = {"mpx_gae": 2, "mpx_hlgauss_loss": 2, "mpx_ppo_policy_loss": 2, "mpx_adamw_step": 2,
                      "mpx_attn_train_bwd": 3, "mpx_muon_step:1": 17, "mpx_muon_step:2": 2, "mpx_muon_step:3": 19,
+                     "mpx_muon_apply_sharded": 3,
                      "mpx_linear_wgrad": 2}
 
 
@@ -553,6 +554,15 @@ def muon_step(params, grads, mu, nu, scratch, n_adam: int, table, nmat: int, x_t
                                    x_total, a_total, max_r, max_c, ptr(ns_ws), ptr(step), lr0, float(total_steps), b1, b2,
                                    eps, wd, muon_beta, ns_steps, max_norm, grad_scale, ptr(norm_out), ptr(ws), phases,
                                    stream()), f"mpx_muon_step:{phases}")
+
+
+def muon_apply_sharded(params, grads, mu, nu, scratch, n_adam: int, step, lr0, total_steps, b1, b2, eps, wd, max_norm,
+                       grad_scale=1.0, norm_out=None, ws=None):
+    """Second half of the sharded Muon step: AdamW leaves + global-norm clip over the all-gathered update + apply."""
+    n = params.numel()
+    check(lib.mpx_muon_apply_sharded(ptr(params), ptr(grads), ptr(mu), ptr(nu), ptr(scratch), n, n_adam, ptr(step), lr0,
+                                     float(total_steps), b1, b2, eps, wd, max_norm, grad_scale, ptr(norm_out), ptr(ws),
+                                     stream()), "mpx_muon_apply_sharded")
 
 
 def prep_weights(descs_device, ndesc: int):

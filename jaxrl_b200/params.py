@@ -94,32 +94,55 @@ def _init(shape, kind: str, gen: torch.Generator) -> torch.Tensor:
     return torch.randn(shape, generator=gen) * math.sqrt(1.0 / fan_in)
 
 
+def assign_muon_owners(sizes: List[int], world: int) -> List[int]:
+    """Owner rank of every Muon matrix: longest-processing-time greedy (largest matrix first to the least loaded rank;
+    ties to the lowest rank), so the Newton-Schulz work and the shard sizes are balanced."""
+    load = [0] * world
+    owner = [0] * len(sizes)
+    for i in sorted(range(len(sizes)), key=lambda i: (-sizes[i], i)):
+        r = min(range(world), key=lambda r: (load[r], r))
+        owner[i] = r
+        load[r] += sizes[i]
+    return owner
+
+
 class ParamStore:
     ALIGN = 4   # floats (16 bytes): kernels read fp32 params with float4 loads
 
-    def __init__(self, cfg: ModelConfig, device, seed: int = 0, bias_noise: float = 0.0):
+    def __init__(self, cfg: ModelConfig, device, seed: int = 0, bias_noise: float = 0.0, world: int = 1):
+        """world > 1 lays the Muon-labelled matrices out in `world` equal-sized shards, one per data-parallel rank (the
+        matrices a rank owns are contiguous, the shard is zero-padded to the common size): the optimizer reduce-scatters
+        the gradient of that partition, runs Newton-Schulz on the local shard only and all-gathers the updates
+        (optimizer.py:25-37,51-69 sharded ZeRO-1 style).  Parameter VALUES do not depend on `world`."""
         self.cfg = cfg
+        self.world = world
         specs = param_specs(cfg)
-        # AdamW-labelled leaves first, Muon-labelled matrices last: the optimizer kernels partition the flat buffer
-        self.specs = [sp for sp in specs if not is_muon_param(sp[0], sp[1])] + \
-                     [sp for sp in specs if is_muon_param(sp[0], sp[1])]
+        adam = [sp for sp in specs if not is_muon_param(sp[0], sp[1])]
+        muon = [sp for sp in specs if is_muon_param(sp[0], sp[1])]
+        numel = lambda shape: math.prod(shape)
+        pad = lambda n: (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        owners = assign_muon_owners([pad(numel(sp[1])) for sp in muon], world)
+        self.muon_owner: Dict[str, int] = {sp[0]: o for sp, o in zip(muon, owners)}
+        # AdamW-labelled leaves first, then the Muon-labelled matrices grouped by owner rank
+        self.specs = adam + [sp for r in range(world) for sp, o in zip(muon, owners) if o == r]
         self.offsets: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
         off = 0
-        self.n_adam = None
-        for name, shape, _ in self.specs:
-            if self.n_adam is None and is_muon_param(name, shape):
-                self.n_adam = off
-            n = 1
-            for s in shape:
-                n *= s
+        for name, shape, _ in adam:
             self.offsets[name] = (off, shape)
-            off += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
-        self.numel = off
-        if self.n_adam is None:
-            self.n_adam = off
+            off += pad(numel(shape))
+        self.n_adam = off
+        loads = [sum(pad(numel(sp[1])) for sp, o in zip(muon, owners) if o == r) for r in range(world)]
+        self.muon_shard = max(loads) if muon else 0           # floats per rank shard (equal on every rank)
+        for r in range(world):
+            o = self.n_adam + r * self.muon_shard
+            for sp, ow in zip(muon, owners):
+                if ow == r:
+                    self.offsets[sp[0]] = (o, sp[1])
+                    o += pad(numel(sp[1]))
+        self.numel = off = self.n_adam + world * self.muon_shard
         gen = torch.Generator().manual_seed(seed)
         host = torch.zeros(off, dtype=torch.float32)
-        for name, shape, kind in self.specs:
+        for name, shape, kind in adam + muon:    # fixed draw order: the values do not depend on the shard layout
             o, _ = self.offsets[name]
             t = _init(shape, kind, gen)
             if kind == "zeros" and bias_noise > 0:
@@ -130,12 +153,13 @@ class ParamStore:
         self.views = {n: self._view(self.flat, n) for n, _, _ in self.specs}
         self.gviews = {n: self._view(self.grad, n) for n, _, _ in self.specs}
 
-    def muon_table(self):
-        """-> (device uint8 tensor of MuonMat records, nmat, x_total, a_total, max_r, max_c) for mpx_muon_step."""
+    def muon_table(self, rank: int = None):
+        """-> (device uint8 tensor of MuonMat records, nmat, x_total, a_total, max_r, max_c) for mpx_muon_step.
+        rank: only the matrices that rank owns (the sharded optimizer); None = all of them."""
         import struct
         recs, xoff, aoff, max_r, max_c = [], 0, 0, 1, 1
         for name, shape, _ in self.specs:
-            if not is_muon_param(name, shape):
+            if not is_muon_param(name, shape) or (rank is not None and self.muon_owner[name] != rank):
                 continue
             off, _ = self.offsets[name]
             rows, cols = shape

@@ -45,13 +45,15 @@ class SyntheticEnv:
 
 class PPOTrainer:
     def __init__(self, run: RunConfig, device="cuda", rank: int = 0, world: int = 1, use_graphs: bool = True,
-                 e2e_host_inputs: bool = False, seed: Optional[int] = None, run_optimizer: bool = True):
+                 e2e_host_inputs: bool = False, seed: Optional[int] = None, run_optimizer: bool = True,
+                 shard_optimizer: bool = True):
         self.run, self.cfg, self.hyp, self.opt = run, run.model, run.ppo, run.optimizer
         self.dev = torch.device(device)
         self.rank, self.world = rank, world
         self.use_graphs = use_graphs
         self.e2e = e2e_host_inputs
         self.run_optimizer = run_optimizer
+        self.shard_optimizer = shard_optimizer            # world > 1: Muon sharded over the ranks (False: every rank repeats it)
         if run.num_agents % world != 0:
             raise ValueError("num_agents must divide evenly across ranks")
         self.B = run.num_agents // world
@@ -65,7 +67,8 @@ class PPOTrainer:
         seed = run.seed if seed is None else seed
         self.seed = seed
         self.sample_seed = seed + 104729 * rank
-        self.engine = PolicyEngine(self.cfg, self.dev, seed=seed)          # same seed on every rank: replicated weights
+        # same seed on every rank: replicated weights; world > 1 lays the Muon matrices out in per-rank shards
+        self.engine = PolicyEngine(self.cfg, self.dev, seed=seed, world=world if shard_optimizer else 1)
         mdist.broadcast_params(self.engine.p.flat)
         self.engine.stage_weights()
         self.env = SyntheticEnv(self.cfg, self.B, self.T, self.dev, seed=seed + 1000 * (rank + 1), host=self.e2e)
@@ -113,12 +116,17 @@ class PPOTrainer:
         o = SimpleNamespace(mu=f(n), nu=f(n), scratch=f(n), step=torch.zeros(1, dtype=I32, device=dev),
                             norm=f(1), ws=torch.empty(_lib.lib.mpx_adamw_workspace_bytes(n), dtype=torch.uint8, device=dev))
         if self.opt.type == "muon":
-            tab, nmat, xt, at, mr, mc = self.engine.p.muon_table()
+            # world > 1: sharded Muon - this rank runs Newton-Schulz on the matrices it owns only (optimizer.py:25-37,51-69)
+            self.sharded = self.world > 1 and self.shard_optimizer and self.engine.p.muon_shard > 0
+            tab, nmat, xt, at, mr, mc = self.engine.p.muon_table(self.rank if self.sharded else None)
             o.muon = SimpleNamespace(table=tab, nmat=nmat, x_total=xt, a_total=at, max_r=mr, max_c=mc,
                                      ns_ws=f(2 * xt + 2 * at + max(nmat, 1)),
-                                     ws=torch.empty(_lib.lib.mpx_muon_workspace_bytes(n, nmat), dtype=torch.uint8, device=dev))
+                                     ws=torch.empty(_lib.lib.mpx_muon_workspace_bytes(n, max(nmat, 1)), dtype=torch.uint8,
+                                                    device=dev))
         elif self.opt.type != "adamw":
             raise ValueError(f"Unknown optimizer type: {self.opt.type}")
+        else:
+            self.sharded = False
         self.o = o
         self.noise_off = torch.zeros(1, dtype=torch.int64, device=dev)      # Gumbel stream offset, += T per rollout
         self.ent_coef = torch.full((1,), self.hyp.entropy_coef, dtype=F32, device=dev)
@@ -232,18 +240,41 @@ class PPOTrainer:
         # The Muon-labelled matrices (everything but the encoders / value head) have their gradients before the
         # observation-encoder backward starts: their all-reduce and Newton-Schulz iterations run under it on the side
         # stream; the AdamW leaves, the global-norm clip and the parameter write follow the rest of the backward.
-        early = self.run_optimizer and opt.type == "muon" and o.muon.nmat > 0 and 0 < n_adam < eng.p.numel
-        hook = (lambda: muon(1, mdist.allreduce_gradients(eng.p.grad[n_adam:]))) if early else None
+        early = self.run_optimizer and opt.type == "muon" and 0 < n_adam < eng.p.numel and \
+            (o.muon.nmat > 0 or self.sharded)
+        shard = eng.p.muon_shard
+
+        def sharded_phase1():
+            # reduce-scatter the Muon partition (each rank receives the summed gradient of ITS matrices), Newton-Schulz on
+            # the local shard, all-gather the updates: 1/world of the orthogonalisation work and of the gradient traffic
+            gs = mdist.reduce_scatter_shard(eng.p.grad[n_adam:], shard)
+            if o.muon.nmat > 0:
+                muon(1, gs)
+            mdist.all_gather_shards(o.scratch[n_adam:], shard)
+
+        if early and self.sharded:
+            hook = sharded_phase1
+        elif early:
+            hook = lambda: muon(1, mdist.allreduce_gradients(eng.p.grad[n_adam:]))
+        else:
+            hook = None
         eng.loss_and_backward(tws, batch, self.hyp, 0.0, entropy_coef_dev=self.ent_coef, matrices_ready=hook)
         self.log_acc[:3] += tws.losses[:3]
         if early:
             gscale = mdist.allreduce_gradients(eng.p.grad[:n_adam])
             eng._wait(eng.matrices_event)
-            muon(2, gscale)
+            if self.sharded:
+                ops.muon_apply_sharded(eng.p.flat, eng.p.grad, o.mu, o.nu, o.scratch, n_adam, o.step, opt.learning_rate,
+                                       total, opt.beta1, opt.beta2, 1e-8, opt.weight_decay, opt.max_norm, grad_scale=gscale,
+                                       norm_out=o.norm, ws=o.muon.ws)
+            else:
+                muon(2, gscale)
             eng.stage_weights(rollout=False)
             return
         gscale = mdist.allreduce_gradients(eng.p.grad)
         if self.run_optimizer:
+            if self.sharded:
+                raise _lib.MpxError("sharded Muon needs both an AdamW and a Muon partition")
             if opt.type == "muon":
                 muon(3, gscale)
             else:                         # optimizer.py:12-23

@@ -63,13 +63,26 @@ def main():
         a, b = sharded[off:off + n], full[off:off + n]
         rel = ((a - b).norm() / (b.norm() + 1e-12)).item()
         assert rel < 2e-3, f"rank {rank}: sharded vs full gradient of {name}: rel l2 {rel}"
-    # ---- 2. trainer: replicated parameters stay identical, sampling streams differ
+    # ---- 2. trainer: replicated parameters stay identical, sampling streams differ; the sharded Muon step (reduce-scatter
+    #         -> Newton-Schulz on the local matrices -> all-gather) equals the replicated one up to fp32 summation order
     run = replace(NAMED["test"], num_agents=32, seed=9)
-    tr = PPOTrainer(run, rank=rank, world=world, use_graphs=True)
-    tr.warmup()
-    for _ in range(2):
-        tr.train_step()
-    torch.cuda.synchronize()
+    finals = {}
+    for shard in (False, True):
+        tr = PPOTrainer(run, rank=rank, world=world, use_graphs=True, shard_optimizer=shard)
+        assert tr.sharded == shard
+        init = tr.engine.p.oracle_dict()
+        tr.warmup()
+        for _ in range(2):
+            tr.train_step()
+        torch.cuda.synchronize()
+        finals[shard] = (tr.engine.p.oracle_dict(), init)
+    num = den = 0.0
+    for k, v in finals[True][0].items():
+        d_sh, d_rep = v - finals[True][1][k], finals[False][0][k] - finals[False][1][k]
+        num += float((d_sh - d_rep).double().pow(2).sum())
+        den += float(d_rep.double().pow(2).sum())
+    rel = (num / den) ** 0.5
+    assert den > 0 and rel < 2e-3, f"sharded vs replicated optimizer: update differs by rel l2 {rel}"
     flat = tr.engine.p.flat
     gathered = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
