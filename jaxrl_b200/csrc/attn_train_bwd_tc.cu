@@ -194,11 +194,18 @@ attn_bwd_tc_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap 
                      "f"(__uint_as_float(dq[4 * c + 3]))
                      : "memory");
     };
+    // lse / delta of the row for the NEXT iteration are fetched while the current one computes: their L2 latency used to
+    // sit between the S / dP wait and the first exponential of every iteration
+    float lse_n = p.lse[(tok0 + (long long)kt * BT + r) * p.Nq], dl_n = p.delta[(tok0 + (long long)kt * BT + r) * p.Nq];
     for (int it = 0; it < n_iter; ++it) {
       const int i = kt + it / p.Nq, h = it % p.Nq;
-      const long long qtok = tok0 + (long long)i * BT + r;
-      const float lse_r = p.lse[qtok * p.Nq + h];
-      const float dl_r = p.delta[qtok * p.Nq + h];
+      const float lse_r = lse_n, dl_r = dl_n;
+      if (it + 1 < n_iter) {
+        const int i2 = kt + (it + 1) / p.Nq, h2 = (it + 1) % p.Nq;
+        const long long q2 = tok0 + (long long)i2 * BT + r;
+        lse_n = p.lse[q2 * p.Nq + h2];
+        dl_n = p.delta[q2 * p.Nq + h2];
+      }
       const bool diag = (i == kt);
       mbar_wait(s_full, it & 1);
       tc_fence_after();

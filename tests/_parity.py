@@ -112,7 +112,7 @@ def make_batch(cfg, T, B, seed, masked=True):
 
 
 def train_parity(cfg, eng, hyp, T, B, seed, name, progress=0.3, logits_allow=2e-3, logits_rel=1e-2, grad_rel=2.5e-2,
-                 grad_cos=0.9995, loss_rtol=1e-2):
+                 grad_cos=0.9995, loss_rtol=1e-2, value_atol=2e-2):
     """forward_train + loss_and_backward vs O.ppo_loss and torch autograd: logits, value logits, values, the three
     losses and every parameter gradient."""
     from jaxrl_b200 import ops
@@ -143,7 +143,8 @@ def train_parity(cfg, eng, hyp, T, B, seed, name, progress=0.3, logits_allow=2e-
     _assert_rel_l2(vlogits.cpu().reshape(B, T, -1), vl_ref, f"{name} train vlogits (l2)", logits_rel, 6e-2)
     centers = O.calculate_supports(cfg.value_min, cfg.value_max, cfg.value_n_logits)[1]
     val = ops.hlgauss_value(vlogits, eng.centers).cpu().reshape(B, T)
-    torch.testing.assert_close(val, O.hlgauss_get_value(vl_ref, centers), rtol=1e-2, atol=2e-2)
+    # HL-Gauss expectation over a support of width 20: 1e-2 relative + value_atol (0.1-0.2 % of the support range)
+    torch.testing.assert_close(val, O.hlgauss_get_value(vl_ref, centers), rtol=1e-2, atol=value_atol)
     eng.p.grad.zero_()
     flat = {k: (v.reshape(-1) if v.dim() == 2 else v) for k, v in d.items()}
     losses = eng.loss_and_backward(ws, flat, hyp, progress=progress)

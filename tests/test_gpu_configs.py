@@ -40,7 +40,7 @@ def test_return8_train_full_window(eng_return8):
     """L=8 at the full T=512 window (tcgen05 attention fwd/bwd at their bench shape, 4 query tiles per row)."""
     from _parity import train_parity
     train_parity(eng_return8.cfg, eng_return8, NAMED["return_8_layers"].ppo, T=512, B=2, seed=32, name="return_8 T512",
-                 logits_allow=4e-2, logits_rel=1.5e-2, grad_rel=4e-2, grad_cos=0.999)
+                 logits_allow=4e-2, logits_rel=1.5e-2, grad_rel=4e-2, grad_cos=0.999, value_atol=4e-2)
 
 
 # ---------------------------------------------------------------------------------------------- multitask (H=256)
@@ -61,7 +61,7 @@ def test_multitask_decode(eng_multitask):
 def test_multitask_train(eng_multitask):
     from _parity import train_parity
     train_parity(eng_multitask.cfg, eng_multitask, NAMED["multitask"].ppo, T=128, B=4, seed=34, name="multitask T128",
-                 logits_allow=5e-3, grad_rel=4e-2, grad_cos=0.999)
+                 logits_allow=5e-3, grad_rel=4e-2, grad_cos=0.999, value_atol=4e-2)
 
 
 def test_multitask_task_embedding_matters(eng_multitask):
@@ -97,4 +97,4 @@ def test_blog32_decode(eng_blog):
 def test_blog32_train(eng_blog):
     from _parity import train_parity
     train_parity(eng_blog.cfg, eng_blog, NAMED["blog_32_layers"].ppo, T=128, B=4, seed=37, name="blog_32 T128",
-                 logits_allow=5e-3, grad_rel=4e-2, grad_cos=0.999)
+                 logits_allow=5e-3, grad_rel=4e-2, grad_cos=0.999, value_atol=4e-2)
