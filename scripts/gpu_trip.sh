@@ -30,12 +30,12 @@ for step in "$@"; do
     minibatch)
       timeout 600 python bench.py --ncu-minibatch > ${out}_plain_mb.log 2>&1 && \
       timeout 1500 ncu --profile-from-start off --clock-control none --csv --metrics \
-gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,sm__inst_issued.avg.pct_of_peak_sustained_active \
+gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread \
         --log-file ${out}_minibatch.csv python bench.py --ncu-minibatch > ${out}_ncu_mb.log 2>&1; echo "minibatch exit $?" ;;
     decodestep)
       timeout 600 python bench.py --ncu-decode-step > ${out}_plain_ds.log 2>&1 && \
       timeout 1500 ncu --profile-from-start off --clock-control none --csv --metrics \
-gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,sm__inst_issued.avg.pct_of_peak_sustained_active \
+gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread \
         --log-file ${out}_decodestep.csv python bench.py --ncu-decode-step > ${out}_ncu_ds.log 2>&1; echo "decodestep exit $?" ;;
     ncu:*)
       timeout 600 python bench.py --ncu-minibatch > ${out}_plain_full.log 2>&1 && \
