@@ -290,6 +290,34 @@ int mpx_obs_embed_fused(const uint8_t* obs, const int* sizes, int K, const void*
                         const int32_t* last_action, const int32_t* task_ids, const float* w_reward, const float* b_reward,
                         const float* action_table, int A, const float* task_table, int n_tasks, mpx_bf16* x,
                         mpx_bf16* obs_emb, long long M, int IH, int IW, int H, mpx_stream_t stream);
+/* Training-side observation encoder (observation.py:84-96 + network.py:303-309 as nnx.grad(ppo_loss) evaluates and
+ * differentiates them, train.py:180-192,236-238) for the geometry, image and embedding arguments of
+ * mpx_obs_embed_fused; one tile = 128 tokens, no im2col matrix exists anywhere.
+ *   mpx_obs_train_supported(sizes, K) = 1 when the joint table of these one-hot sizes fits next to the operand tiles in
+ *     shared memory (prod(sizes[k]+1) <= 39); mpx_obs_train_tiles(M) = ceil(M / 128).
+ *   mpx_obs_train_fwd: x (M,H) [+ obs_emb (M,H), nullable] and what the backward needs: a2 (M,288) = gelu(z2) row-major
+ *     (operand of the conv3 weight gradient) and, in layouts private to these kernels (TILE layouts, buffers sized for
+ *     mpx_obs_train_tiles(M) whole tiles): z1t / a1t [tile][25 positions][2][128 rows][8 ch] = the bf16 pre-activation
+ *     (+bias) of conv1 and its gelu, z2t [tile][9][4][128][8] = the pre-activation of conv2.
+ *   mpx_obs_train_bwd: data gradients given dx0 (M,H) = d loss / d (encoder output): dz2t (tile layout, operand of
+ *     mpx_obs_conv2_wgrad), dz1 (M*25,16) row-major (operand of mpx_conv1_onehot_wgrad); db1 (16) / db2 (32) fp32 +=
+ *     the conv1 / conv2 bias gradients (fixed summation order).  The conv3 weight / bias gradients are
+ *     mpx_linear_wgrad(a2, dx0) / mpx_colsum(dx0).
+ *   mpx_obs_conv2_wgrad: dw (144,32) fp32 += sum_p a1[p + tap]^T dz2[p] (kernel layout (kh,kw,cin,cout) flattened).
+ * workspace: mpx_obs_train_bwd_workspace_bytes() bytes, shared by the two backward calls of a stream. */
+int mpx_obs_train_supported(const int* sizes, int K);
+long long mpx_obs_train_tiles(long long M);
+int mpx_obs_train_fwd(const uint8_t* obs, const int* sizes, int K, const void* image, const float* reward,
+                      const int32_t* last_action, const int32_t* task_ids, const float* w_reward, const float* b_reward,
+                      const float* action_table, int A, const float* task_table, int n_tasks, mpx_bf16* z1t, mpx_bf16* a1t,
+                      mpx_bf16* z2t, mpx_bf16* a2, mpx_bf16* x, mpx_bf16* obs_emb, long long M, int IH, int IW, int H,
+                      mpx_stream_t stream);
+size_t mpx_obs_train_bwd_workspace_bytes(void);
+int mpx_obs_train_bwd(const mpx_bf16* dx0, const mpx_bf16* z1t, const mpx_bf16* z2t, const void* image, mpx_bf16* dz2t,
+                      mpx_bf16* dz1, float* db1, float* db2, long long M, void* workspace, size_t workspace_bytes,
+                      mpx_stream_t stream);
+int mpx_obs_conv2_wgrad(const mpx_bf16* a1t, const mpx_bf16* dz2t, float* dw, long long M, void* workspace,
+                        size_t workspace_bytes, mpx_stream_t stream);
 /* Weight gradient of the first observation conv without materialising the one-hot im2col matrix:
  * dw ((kh*kw*C), cout) f32 += onehot_im2col(obs)^T @ dz, dz (M*OH*OW, cout) bf16 contiguous.  The one-hot operand
  * tiles are generated in shared memory from the uint8 observation.  kh*kw*C <= 128, kh*kw*K <= 32, cout <= 64. */

@@ -123,6 +123,15 @@ lib.mpx_obs_fused_image_bytes.argtypes = []
 lib.mpx_obs_fused_prep.argtypes = [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]
 lib.mpx_obs_embed_fused.argtypes = [c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_p, c_p, c_ll, c_i, c_i,
                                     c_i, c_p]
+lib.mpx_obs_train_supported.argtypes = [c_p, c_i]
+lib.mpx_obs_train_tiles.restype = c_ll
+lib.mpx_obs_train_tiles.argtypes = [c_ll]
+lib.mpx_obs_train_fwd.argtypes = [c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p,
+                                  c_ll, c_i, c_i, c_i, c_p]
+lib.mpx_obs_train_bwd_workspace_bytes.restype = C.c_size_t
+lib.mpx_obs_train_bwd_workspace_bytes.argtypes = []
+lib.mpx_obs_train_bwd.argtypes = [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, C.c_size_t, c_p]
+lib.mpx_obs_conv2_wgrad.argtypes = [c_p, c_p, c_p, c_ll, c_p, C.c_size_t, c_p]
 lib.mpx_policy_head_sample.argtypes = [c_p, c_p, C.c_float, c_p, c_p, c_p, C.c_ulonglong, C.c_ulonglong, c_p, c_p, c_p, c_p,
                                        c_p, c_ll, c_i, c_i, c_p]
 lib.mpx_ppo_policy_loss_workspace_bytes.restype = C.c_size_t

@@ -16,8 +16,7 @@
 // stands for an out-of-range value = all-zero one-hot), so a 3x3 receptive field costs 9 lookups of a 16-channel fp32 row.
 // The joint table and the core-matrix images of W2 / W3 are built once per weight update by obs_fused_prep_kernel into
 // one contiguous device buffer, which each CTA pulls into shared memory with a single bulk copy.
-#include "common.cuh"
-#include "ptx.cuh"
+#include "obs_common.cuh"
 
 namespace mpx {
 
@@ -25,18 +24,9 @@ namespace mpx {
 constexpr int OF_AG = 32;              // agents per tile
 constexpr int OF_WORKERS = 8;          // worker warps
 constexpr int OF_THREADS = (OF_WORKERS + 1) * 32;
-constexpr int OF_IH = 11, OF_IW = 11, OF_P1 = 5, OF_C1 = 16, OF_C2 = 32, OF_H = 128;
-constexpr int OF_K3 = 9 * OF_C2;       // 288
-constexpr int OF_MAXK = 4;             // observation components per cell
 
 constexpr int OF_A1_BYTES = 26 * 1024;                 // 25 position tiles [32 agents x 16 ch] + 1 tile of slack
 constexpr int OF_A2_BYTES = 16 * (OF_K3 / 8) * 128;    // 128 rows x 576 B = 73728
-constexpr int OF_W3_BYTES = 16 * (OF_K3 / 8) * 128;    // 128 n x 576 B
-constexpr int OF_W2_BYTES = 9 * 1024;
-constexpr int OF_MAXJ = 48;                            // joint one-hot codes per cell (product of (size_k + 1))
-constexpr int OF_T1_BYTES = 9 * OF_MAXJ * 2 * OF_C1 * 4;   // conv1 joint table, fp32, two bank-disjoint copies: 55296
-constexpr int OF_BIAS_BYTES = 512;                     // b1[16] b2[32] b3[128] bf16
-constexpr int OF_IMG_BYTES = OF_W3_BYTES + OF_W2_BYTES + OF_T1_BYTES + OF_BIAS_BYTES;   // one bulk copy
 constexpr int OF_OBS_BYTES = OF_AG * OF_IH * OF_IW * OF_MAXK;   // 15488
 constexpr int OF_CODE_BYTES = OF_AG * OF_IH * OF_IW;            // 3872: one joint code per cell
 // Only rows 0..31 of the conv3 A operand are agents; the other 96 rows of the M=128 MMA are don't-care, so a1, the
@@ -69,21 +59,7 @@ struct ObsFusedParams {
   unsigned long long* dbg;
 };
 
-__device__ __forceinline__ uint64_t umma_smem_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;                                                  // layout type 0: no swizzle
-}
-__device__ __forceinline__ void of_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-// Image layout (bytes): [W3 core-matrix image 73728][W2 tap images 9216][conv1 joint table fp32 27648][biases bf16 512]
-//   W3: element (n, k) at (n/8)*4608 + (k/8)*128 + (n%8)*16 + (k%8)*2        (k = pos*32 + cin)
-//   W2: element (tap, n, c) at tap*1024 + (n/8)*256 + (c/8)*128 + (n%8)*16 + (c%8)*2
-//   T1: [tap][code][copy 0|1][16] fp32 = sum over components k with digit_k < sizes[k] of W1[tap*C + off_k + digit_k][:]
-//       (row pitch 128 B: copy 0 sits in banks 0-15, copy 1 in banks 16-31, so two lookups never collide)
+// Builds the weight image (layout: obs_common.cuh)
 __global__ void __launch_bounds__(256) obs_fused_prep_kernel(const __nv_bfloat16* __restrict__ w1, const __nv_bfloat16* __restrict__ b1,
                                                              const __nv_bfloat16* __restrict__ wt2, const __nv_bfloat16* __restrict__ b2,
                                                              const __nv_bfloat16* __restrict__ wt3, const __nv_bfloat16* __restrict__ b3,
@@ -454,23 +430,19 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
 using namespace mpx;
 
 static int of_fill_spec(ObsFusedParams& p, const int* sizes, int K) {
-  MPX_REQUIRE(sizes && K >= 1 && K <= OF_MAXK, "mpx_obs_embed_fused: K=%d components unsupported", K);
-  p.K = K;
-  int nj = 1;
+  ObsCodeSpec s;
+  int rc = obs_fill_spec(s, sizes, K, "mpx_obs_embed_fused");
+  if (rc) return rc;
+  p.K = s.K;
+  p.NJ = s.NJ;
   for (int i = 0; i < OF_MAXK; ++i) {
-    p.sizes[i] = i < K ? sizes[i] : 0;
-    p.radix[i] = i < K ? nj : 0;
-    if (i < K) {
-      MPX_REQUIRE(sizes[i] > 0 && sizes[i] < 255, "mpx_obs_embed_fused: bad one-hot size %d", sizes[i]);
-      nj *= sizes[i] + 1;
-    }
+    p.sizes[i] = s.sizes[i];
+    p.radix[i] = s.radix[i];
   }
-  MPX_REQUIRE(nj <= OF_MAXJ, "mpx_obs_embed_fused: %d joint one-hot codes per cell > %d (use the unfused encoder)", nj, OF_MAXJ);
-  p.NJ = nj;
   return MPX_OK;
 }
 
-extern "C" size_t mpx_obs_fused_image_bytes(void) { return (size_t)OF_IMG_BYTES; }
+extern "C" size_t mpx_obs_fused_image_bytes(void) { return (size_t)OF_IMG_BYTES + obs_train_bwd_image_bytes(); }
 
 extern "C" int mpx_obs_fused_prep(const int* sizes, int K, const mpx_bf16* w1, const mpx_bf16* b1, const mpx_bf16* wt2,
                                   const mpx_bf16* b2, const mpx_bf16* wt3, const mpx_bf16* b3, void* image,
@@ -487,7 +459,10 @@ extern "C" int mpx_obs_fused_prep(const int* sizes, int K, const mpx_bf16* w1, c
       reinterpret_cast<const __nv_bfloat16*>(wt2), reinterpret_cast<const __nv_bfloat16*>(b2),
       reinterpret_cast<const __nv_bfloat16*>(wt3), reinterpret_cast<const __nv_bfloat16*>(b3), p,
       reinterpret_cast<uint8_t*>(image));
-  return check_launch("obs_fused_prep_kernel");
+  rc = check_launch("obs_fused_prep_kernel");
+  if (rc) return rc;
+  return obs_train_prep_bwd(reinterpret_cast<const __nv_bfloat16*>(wt2), reinterpret_cast<const __nv_bfloat16*>(wt3),
+                            reinterpret_cast<uint8_t*>(image) + OF_IMG_BYTES, (cudaStream_t)stream);
 }
 
 extern "C" int mpx_obs_embed_fused(const uint8_t* obs, const int* sizes, int K, const void* image, const float* reward,

@@ -458,6 +458,58 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(MpxObsEmbedFused, ObsEmbedFusedImpl,
                                   .Arg<F32>().Arg<F32>().Arg<F32>().Attr<ffi::Span<const int32_t>>("sizes").Ret<BF>(),
                               MPX_TRAITS);
 
+// Training-side observation encoder in one kernel (observation.py:84-96 + network.py:303-309 under nnx.grad): x plus the
+// saved activations - z1t / a1t / z2t in the kernels' private tile layouts (flat, sized by the Python side from
+// mpx_obs_train_tiles) and a2 (M,288) row-major
+static ffi::Error ObsTrainFwdImpl(mpx_stream_t stream, U8 obs, U8 image, F32 reward, S32 last_action, S32 task_ids,
+                                  F32 w_reward, F32 b_reward, F32 action_table, F32 task_table,
+                                  ffi::Span<const int32_t> sizes, RBF x, RBF z1t, RBF a1t, RBF z2t, RBF a2) {
+  int sz[8] = {0};
+  const int K = static_cast<int>(sizes.size());
+  if (K > 8) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "MpxObsTrainFwd: at most 8 observation components");
+  for (int i = 0; i < K; ++i) sz[i] = sizes[i];
+  const auto od = obs.dimensions();
+  const int n = static_cast<int>(od.size());
+  const int IH = static_cast<int>(od[n - 3]), IW = static_cast<int>(od[n - 2]);
+  const long long M = static_cast<long long>(obs.element_count()) / (static_cast<long long>(IH) * IW * K);
+  const bool tasks = task_ids.element_count() && task_table.element_count();
+  MPX_CALL(mpx_obs_train_fwd(obs.typed_data(), sz, K, image.untyped_data(), reward.typed_data(), last_action.typed_data(),
+                             tasks ? task_ids.typed_data() : nullptr, w_reward.typed_data(), b_reward.typed_data(),
+                             action_table.typed_data(), static_cast<int>(action_table.dimensions()[0]),
+                             tasks ? task_table.typed_data() : nullptr,
+                             tasks ? static_cast<int>(task_table.dimensions()[0]) : 0, rbf(z1t), rbf(a1t), rbf(z2t), rbf(a2),
+                             rbf(x), nullptr, M, IH, IW, last_dim(*x), stream), "mpx_obs_train_fwd");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(MpxObsTrainFwd, ObsTrainFwdImpl,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<U8>().Arg<U8>().Arg<F32>().Arg<S32>().Arg<S32>().Arg<F32>()
+                                  .Arg<F32>().Arg<F32>().Arg<F32>().Attr<ffi::Span<const int32_t>>("sizes").Ret<BF>()
+                                  .Ret<BF>().Ret<BF>().Ret<BF>().Ret<BF>(),
+                              MPX_TRAITS);
+
+// Its data gradients: dz2t (tile layout), dz1 (M*25,16); db1 / db2 accumulate.  aliases: db1_in(4) -> 2, db2_in(5) -> 3
+static ffi::Error ObsTrainBwdImpl(mpx_stream_t stream, BF dx0, BF z1t, BF z2t, U8 image, F32 db1_in, F32 db2_in, RBF dz2t,
+                                  RBF dz1, RF32 db1, RF32 db2, RU8 workspace) {
+  (void)db1_in; (void)db2_in;
+  MPX_CALL(mpx_obs_train_bwd(bf(dx0), bf(z1t), bf(z2t), image.untyped_data(), rbf(dz2t), rbf(dz1), db1->typed_data(),
+                             db2->typed_data(), rows_of(dx0), workspace->untyped_data(), workspace->element_count(), stream),
+           "mpx_obs_train_bwd");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(MpxObsTrainBwd, ObsTrainBwdImpl,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<BF>().Arg<BF>().Arg<BF>().Arg<U8>().Arg<F32>().Arg<F32>()
+                                  .Ret<BF>().Ret<BF>().Ret<F32>().Ret<F32>().Ret<U8>(),
+                              MPX_TRAITS);
+
+// Tap-wise conv2 weight gradient from the position tiles, M = token count.  aliases: dw_in(2) -> 0 (accumulated)
+static ffi::Error ObsConv2WgradImpl(mpx_stream_t stream, BF a1t, BF dz2t, F32 dw_in, int64_t M, RF32 dw, RU8 workspace) {
+  (void)dw_in;
+  MPX_CALL(mpx_obs_conv2_wgrad(bf(a1t), bf(dz2t), dw->typed_data(), static_cast<long long>(M), workspace->untyped_data(),
+                               workspace->element_count(), stream), "mpx_obs_conv2_wgrad");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(MpxObsConv2Wgrad, ObsConv2WgradImpl,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<BF>().Arg<BF>().Arg<F32>().Attr<int64_t>("M").Ret<F32>()
+                                  .Ret<U8>(),
+                              MPX_TRAITS);
+
 // conv1 straight from the uint8 observation: a_out (M*OH*OW, cout), z_out (0 elements => not kept)
 static ffi::Error Conv1OnehotFwdImpl(mpx_stream_t stream, U8 obs, BF w, BF bias, ffi::Span<const int32_t> sizes, int32_t kh,
                                      int32_t kw, int32_t sh, int32_t sw, int32_t apply_gelu, RBF a_out, RBF z_out) {

@@ -32,9 +32,10 @@ def _round_up(n: int, m: int) -> int:
 
 class PolicyEngine:
     def __init__(self, cfg: ModelConfig, device="cuda", seed: int = 0, params: Optional[ParamStore] = None,
-                 bias_noise: float = 0.0, fused_rollout: bool = True, world: int = 1):
+                 bias_noise: float = 0.0, fused_rollout: bool = True, world: int = 1, fused_obs_train: bool = True):
         """fused_rollout=False runs the rollout step through the general (per-op) kernel chain even where the
-        one-kernel-per-half-block kernels apply - the chain every shape without a fused kernel takes (tests)."""
+        one-kernel-per-half-block kernels apply - the chain every shape without a fused kernel takes (tests);
+        fused_obs_train=False does the same for the training-side observation encoder (im2col + GEMM chain)."""
         if cfg.head_dim != 32:
             raise _lib.MpxError("head_dim must be 32 on the B200 path")
         if cfg.obs_type not in ("grid_cnn", "grid_flattened"):
@@ -86,19 +87,22 @@ class PolicyEngine:
             if c.cin % 8 != 0:
                 raise _lib.MpxError("hidden conv channels must be multiples of 8")
         # rollout path: the standard geometry (11x11 view, 3x3/2 -> 16, 3x3/1 -> 32, 3x3/1 -> 128) runs as one kernel
-        self.fused_obs = (fused_rollout and not self.flat and H == 128 and tuple(cfg.obs_shape[:2]) == (11, 11) and len(self.conv) == 3
-                          and all((c.kh, c.kw) == (3, 3) for c in self.conv)
-                          and [(c.sh, c.sw) for c in self.conv] == [(2, 2), (1, 1), (1, 1)]
-                          and [c.cout for c in self.conv] == [16, 32, 128] and len(cfg.obs_max_value) <= 4
-                          and math.prod(n + 1 for n in cfg.obs_max_value) <= 48)
-        self.obs_image = ops.obs_fused_image(self.dev) if self.fused_obs else None
+        std_geom = (not self.flat and H == 128 and tuple(cfg.obs_shape[:2]) == (11, 11) and len(self.conv) == 3
+                    and all((c.kh, c.kw) == (3, 3) for c in self.conv)
+                    and [(c.sh, c.sw) for c in self.conv] == [(2, 2), (1, 1), (1, 1)]
+                    and [c.cout for c in self.conv] == [16, 32, 128] and len(cfg.obs_max_value) <= 4)
+        self.fused_obs = fused_rollout and std_geom and math.prod(n + 1 for n in cfg.obs_max_value) <= 48
+        # training path: the same geometry as one forward kernel + one data-gradient kernel (obs_train.cu)
+        c0 = self.conv[0] if self.conv else None
+        self.onehot_wgrad = (c0 is not None and c0.k <= 128 and (c0.kh, c0.kw) == (3, 3) and c0.cout <= 64
+                             and c0.cout % 8 == 0 and len(cfg.obs_max_value) <= 4)
+        self.fused_obs_train = bool(fused_obs_train and std_geom and self.onehot_wgrad
+                                    and ops.obs_train_supported(cfg.obs_max_value))
+        self.obs_image = ops.obs_fused_image(self.dev) if (self.fused_obs or self.fused_obs_train) else None
         # weight-gradient GEMMs run on a side stream next to the data-gradient chain; a second one carries the early
         # optimizer phase (Muon partition) under the observation-encoder backward
         self.side = torch.cuda.Stream(device=self.dev)
         self.side2 = torch.cuda.Stream(device=self.dev)
-        c0 = self.conv[0] if self.conv else None
-        self.onehot_wgrad = (c0 is not None and c0.k <= 128 and (c0.kh, c0.kw) == (3, 3) and c0.cout <= 64
-                             and c0.cout % 8 == 0 and len(cfg.obs_max_value) <= 4)
         self._alloc_staged()
         self.stage_weights()
 
@@ -186,11 +190,11 @@ class PolicyEngine:
         """fp32 master params -> bf16 GEMM operand copies (one launch).  rollout=True also rebuilds the weight image of
         the fused observation encoder, which only the rollout path reads (so once per update is enough)."""
         ops.prep_weights(self._desc_dev, self._ndesc)
-        if rollout:
+        if rollout or self.fused_obs_train:                   # the fused training encoder reads the same image
             self.stage_rollout_weights()
 
     def stage_rollout_weights(self):
-        if self.fused_obs:
+        if self.obs_image is not None:
             w = self.w
             ops.obs_fused_prep(self.cfg.obs_max_value, w["w_c0"], w["b_c0"], w["wt_c1"], w["b_c1"], w["wt_c2"], w["b_c2"],
                                self.obs_image)
@@ -205,14 +209,17 @@ class PolicyEngine:
             ws.fe = e(M, self.fkp)                                # flattened cell embeddings (dense input)
             ws.oe = e(M, self.H)                                  # encoder output
             ws.dfe = e(M, self.fkp) if train else None
+        fused_t = train and self.fused_obs_train
+        if fused_t:
+            ws.obs_t = ops.obs_train_buffers(M, dev)              # z1t, a1t, z2t, dz2t (tile layouts) + workspace
         for c in self.conv:
             rows = M * c.oh * c.ow
             # the last conv covers the whole remaining map: its im2col is the flattened previous activation;
             # the first conv reads the uint8 observation directly (its one-hot im2col is only built for the
-            # weight gradient, in training)
-            ws.cx.append(e(rows, c.kp) if (c.j < n - 1 and (c.j > 0 or train)) else None)
-            ws.cz.append(e(rows, c.cout) if (train and c.j < n - 1) else None)
-            ws.ca.append(e(rows, c.cout))
+            # weight gradient, in training); the fused training encoder keeps only a2 = ca[1] in row-major form
+            ws.cx.append(e(rows, c.kp) if (c.j < n - 1 and (c.j > 0 or train) and not fused_t) else None)
+            ws.cz.append(e(rows, c.cout) if (train and c.j < n - 1 and not fused_t) else None)
+            ws.ca.append(e(rows, c.cout) if not (fused_t and c.j != 1) else None)
         ws.x0 = e(M, self.H)
 
     def alloc_decode(self, B: int) -> SimpleNamespace:
@@ -265,8 +272,12 @@ class PolicyEngine:
         ws.dh, ws.dug = (None if self.fused_glu_train else e(M, F)), e(M, 2 * F)
         ws.dqkv, ws.do = e(M, self.QKV), e(M, self.QD)
         ws.delta, ws.dq_acc = f(M, self.Nq), f(M, self.QD)
-        ws.dca = [e(M * c.oh * c.ow, c.cout) for c in self.conv[:-1]]
-        ws.dcx = [e(M * c.oh * c.ow, c.kp) if c.j > 0 else None for c in self.conv[:-1]]
+        if self.fused_obs_train:                       # only dz1 (operand of the one-hot weight gradient) is row-major
+            ws.dca = [e(M * c.oh * c.ow, c.cout) if c.j == 0 else None for c in self.conv[:-1]]
+            ws.dcx = [None for c in self.conv[:-1]]
+        else:
+            ws.dca = [e(M * c.oh * c.ow, c.cout) for c in self.conv[:-1]]
+            ws.dcx = [e(M * c.oh * c.ow, c.kp) if c.j > 0 else None for c in self.conv[:-1]]
         ws.losses = f(4)          # value_loss, actor_loss, entropy_loss, (spare)
         ws.loss_ws = torch.empty(max(_lib.lib.mpx_hlgauss_loss_workspace_bytes(M),
                                      _lib.lib.mpx_ppo_policy_loss_workspace_bytes(M)), dtype=torch.uint8, device=dev)
@@ -292,6 +303,13 @@ class PolicyEngine:
                                        task_ids if t_table is not None else None, p["reward_encoder.kernel"],
                                        p["reward_encoder.bias"], p["action_embedder.embedding_table"], t_table, out, M,
                                        c0.ih, c0.iw)
+        if train and self.fused_obs_train:        # training: one kernel, z1 / a1 / z2 / a2 saved for the backward
+            t_table = p.views.get("task_embedder.embedding_table") if task_ids is not None else None
+            c0, t = self.conv[0], ws.obs_t
+            return ops.obs_train_fwd(obs, cfg.obs_max_value, self.obs_image, reward, last_action,
+                                     task_ids if t_table is not None else None, p["reward_encoder.kernel"],
+                                     p["reward_encoder.bias"], p["action_embedder.embedding_table"], t_table,
+                                     t["z1t"], t["a1t"], t["z2t"], ws.ca[1], out, M, c0.ih, c0.iw)
         prev = None
         for c in self.conv:
             last = c.j == n - 1
@@ -336,6 +354,19 @@ class PolicyEngine:
             ops.linear(dx0, w["w_fd"], out=ws.dfe)
             ops.flat_embed_bwd(obs, ws.dfe, p.g("obs_encoder.embedding.kernel"), p.g("obs_encoder.embedding.bias"), M,
                                self.cells)
+            return
+        if self.fused_obs_train:
+            # conv3: bias / weight gradient from dx0 and the saved a2; one kernel for both data gradients (+ the conv1 /
+            # conv2 bias gradients); tap-wise conv2 weight gradient; one-hot conv1 weight gradient.  No im2col / col2im.
+            c0, c1, c2, t = self.conv[0], self.conv[1], self.conv[2], ws.obs_t
+            ops.colsum(dx0, p.g("obs_encoder.layers.2.bias"), M=M, N=c2.cout, ld=c2.cout)
+            ops.linear_wgrad(ws.ca[1].view(M, c2.kp), dx0, p.g("obs_encoder.layers.2.kernel").view(c2.k, c2.cout), M=M,
+                             K=c2.k, N=c2.cout, ldx=c2.kp, ldy=c2.cout, lddw=c2.cout)
+            ops.obs_train_bwd(dx0, t["z1t"], t["z2t"], self.obs_image, t["dz2t"], ws.dca[0],
+                              p.g("obs_encoder.layers.0.bias"), p.g("obs_encoder.layers.1.bias"), M, t["ws"])
+            ops.obs_conv2_wgrad(t["a1t"], t["dz2t"], p.g("obs_encoder.layers.1.kernel"), M, t["ws"])
+            ops.conv1_onehot_wgrad(obs, ws.dca[0], p.g("obs_encoder.layers.0.kernel").view(c0.k, c0.cout), M, c0.ih, c0.iw,
+                                   self.cfg.obs_max_value, c0.kh, c0.kw, c0.sh, c0.sw, c0.cout)
             return
         # Data-gradient chain (GEMM -> col2im -> GEMM ...) and each layer's bias / weight gradients, all on this stream:
         # both are HBM-bound, so running the weight gradients on the side stream gained nothing (round 1, trip 79).

@@ -34,7 +34,7 @@ for _n, _args in (("mpx_gae_workspace_bytes", [ctypes.c_int, ctypes.c_int]),
                   ("mpx_conv1_onehot_wgrad_workspace_bytes", [ctypes.c_longlong] + [ctypes.c_int] * 6),
                   ("mpx_adamw_workspace_bytes", [ctypes.c_longlong]),
                   ("mpx_muon_workspace_bytes", [ctypes.c_longlong, ctypes.c_int]),
-                  ("mpx_obs_fused_image_bytes", [])):
+                  ("mpx_obs_fused_image_bytes", []), ("mpx_obs_train_bwd_workspace_bytes", [])):
     getattr(_CORE, _n).restype = ctypes.c_size_t
     getattr(_CORE, _n).argtypes = _args
 
@@ -47,7 +47,7 @@ TARGETS = (
     "MpxConv1OnehotFwd", "MpxConv1OnehotWgrad", "MpxObsOnehotIm2col", "MpxIm2col", "MpxCol2im", "MpxFlatEmbedFwd",
     "MpxFlatEmbedBwd", "MpxPolicyLogits", "MpxPolicySample", "MpxPolicyHeadSample", "MpxGumbelNoise", "MpxPpoPolicyLoss",
     "MpxPolicyHeadBwd", "MpxValueHeadFused", "MpxAdamwStep", "MpxMuonStep", "MpxMuonApplySharded", "MpxPrepWeights",
-    "MpxTransposeTb",
+    "MpxTransposeTb", "MpxObsTrainFwd", "MpxObsTrainBwd", "MpxObsConv2Wgrad",
 )
 for _t in TARGETS:
     jax.ffi.register_ffi_target(_t, jax.ffi.pycapsule(getattr(_XLA_LIB, _t)), platform="CUDA")
@@ -298,6 +298,39 @@ def obs_embed_fused(obs, image, reward, last_action, task_ids, w_reward, b_rewar
     return _call("MpxObsEmbedFused", _sds((B, H), BF16), obs, image, reward, last_action,
                  none_i if task_ids is None else task_ids, w_reward, b_reward, action_table,
                  _EMPTY_F32() if task_table is None else task_table, sizes=np.asarray(sizes, np.int32))
+
+
+# ------------------------------------------------------------------------------------------------ training encoder
+def _obs_tiles(M: int) -> int:
+    return (M + 127) // 128
+
+
+def obs_train_fwd(obs, image, reward, last_action, task_ids, w_reward, b_reward, action_table, task_table, sizes, H: int = 128):
+    """GridCnnObsEncoder + embedding sum under nnx.grad (observation.py:84-96, network.py:303-309) in one kernel.
+    Returns x (M,H) and the residuals (z1t, a1t, z2t, a2) the backward consumes."""
+    M = math.prod(obs.shape[:-3])
+    nt = _obs_tiles(M)
+    none_i = jnp.zeros((0,), I32)
+    return _call("MpxObsTrainFwd", (_sds((M, H), BF16), _sds((nt * 25 * 2048,), BF16), _sds((nt * 25 * 2048,), BF16),
+                                    _sds((nt * 9 * 4096,), BF16), _sds((M, 288), BF16)),
+                 obs, image, reward, last_action, none_i if task_ids is None else task_ids, w_reward, b_reward, action_table,
+                 _EMPTY_F32() if task_table is None else task_table, sizes=np.asarray(sizes, np.int32))
+
+
+def obs_train_bwd(dx0, z1t, z2t, image, db1, db2):
+    """Data gradients of the encoder given dx0 = d loss / d (encoder output): (dz2t, dz1, db1 + d b1, db2 + d b2)."""
+    M = dx0.shape[0]
+    dz2t, dz1, db1, db2, _ = _call("MpxObsTrainBwd", (_sds(z2t.shape, BF16), _sds((M * 25, 16), BF16), _sds((16,), F32),
+                                                      _sds((32,), F32), _sds((_CORE.mpx_obs_train_bwd_workspace_bytes(),), U8)),
+                                   dx0, z1t, z2t, image, db1, db2, aliases={4: 2, 5: 3})
+    return dz2t, dz1, db1, db2
+
+
+def obs_conv2_wgrad(a1t, dz2t, dw, M: int):
+    """dw (3,3,16,32) f32 += the tap-wise conv2 weight gradient (no im2col)."""
+    dw, _ = _call("MpxObsConv2Wgrad", (_sds(dw.shape, F32), _sds((_CORE.mpx_obs_train_bwd_workspace_bytes(),), U8)),
+                  a1t, dz2t, dw, aliases={2: 0}, M=np.int64(M))
+    return dw
 
 
 def policy_head_sample(x, norm_scale, table, action_mask, gumbel, eps: float = 1e-6):

@@ -518,6 +518,63 @@ def obs_embed_fused(obs, sizes: Sequence[int], image, reward, last_action, task_
     return out
 
 
+def obs_train_supported(sizes: Sequence[int]) -> bool:
+    K = len(sizes)
+    return bool(lib.mpx_obs_train_supported((C.c_int * K)(*sizes), K))
+
+
+def obs_train_buffers(M: int, device) -> dict:
+    """Saved activations / cotangents of the fused training encoder: tile layouts sized for whole 128-token tiles."""
+    nt = int(lib.mpx_obs_train_tiles(M))
+    e = lambda *s: torch.empty(*s, dtype=BF16, device=device)
+    return dict(z1t=e(nt, 25, 2, 128, 8), a1t=e(nt, 25, 2, 128, 8), z2t=e(nt, 9, 4, 128, 8), dz2t=e(nt, 9, 4, 128, 8),
+                ws=torch.empty(lib.mpx_obs_train_bwd_workspace_bytes(), dtype=torch.uint8, device=device))
+
+
+def obs_tile_to_rows(t, M: int):
+    """Tile layout [tile][pos][piece][row][8] -> row-major (M, pos, piece*8) (tests / inspection)."""
+    nt, P, Q = t.shape[0], t.shape[1], t.shape[2]
+    return t.permute(0, 3, 1, 2, 4).reshape(nt * 128, P, Q * 8)[:M]
+
+
+def obs_train_fwd(obs, sizes: Sequence[int], image, reward, last_action, task_ids, w_r, b_r, a_table, t_table, z1t, a1t,
+                  z2t, a2, out, M: int, IH: int, IW: int, obs_emb=None):
+    """Training forward of the observation encoder + embedding sum in one kernel; saves z1t, a1t, z2t (tile layouts)
+    and a2 (M, 288) for the backward."""
+    for t, n in ((out, "out"), (z1t, "z1t"), (a1t, "a1t"), (z2t, "z2t"), (a2, "a2")):
+        _req(t, BF16, n)
+    _req(image, torch.uint8, "image")
+    nt = int(lib.mpx_obs_train_tiles(M))
+    if z1t.numel() < nt * 25 * 2048 or a1t.numel() < nt * 25 * 2048 or z2t.numel() < nt * 9 * 4096:
+        raise _lib.MpxError("obs_train_fwd: tile-layout buffers too small (see obs_train_buffers)")
+    K = len(sizes)
+    arr = (C.c_int * K)(*sizes)
+    check(lib.mpx_obs_train_fwd(ptr(obs), arr, K, ptr(image), ptr(reward), ptr(last_action), ptr(task_ids), ptr(w_r),
+                                ptr(b_r), ptr(a_table), a_table.shape[0], ptr(t_table),
+                                0 if t_table is None else t_table.shape[0], ptr(z1t), ptr(a1t), ptr(z2t), ptr(a2), ptr(out),
+                                ptr(obs_emb), M, IH, IW, out.shape[-1], stream()), "mpx_obs_train_fwd")
+    return out
+
+
+def obs_train_bwd(dx0, z1t, z2t, image, dz2t, dz1, db1, db2, M: int, ws):
+    """Data gradients of the fused training encoder: dz2t (tile layout), dz1 (M*25, 16); db1 / db2 (fp32) +=."""
+    _req(dx0, BF16, "dx0"); _req(dz1, BF16, "dz1"); _req(db1, F32, "db1"); _req(db2, F32, "db2")
+    nt = int(lib.mpx_obs_train_tiles(M))
+    if z1t.numel() < nt * 25 * 2048 or z2t.numel() < nt * 9 * 4096 or dz2t.numel() < nt * 9 * 4096 or dz1.numel() < M * 400:
+        raise _lib.MpxError("obs_train_bwd: buffers too small")
+    check(lib.mpx_obs_train_bwd(ptr(dx0), ptr(z1t), ptr(z2t), ptr(image), ptr(dz2t), ptr(dz1), ptr(db1), ptr(db2), M,
+                                ptr(ws), ws.numel() * ws.element_size(), stream()), "mpx_obs_train_bwd")
+
+
+def obs_conv2_wgrad(a1t, dz2t, dw, M: int, ws):
+    """dw (144, 32) f32 += tap-wise conv2 weight gradient from the position tiles (no im2col)."""
+    _req(dw, F32, "dw")
+    if dw.numel() != 144 * 32 or not dw.is_contiguous():
+        raise _lib.MpxError("obs_conv2_wgrad: dw must be the contiguous (3,3,16,32) kernel gradient")
+    check(lib.mpx_obs_conv2_wgrad(ptr(a1t), ptr(dz2t), ptr(dw), M, ptr(ws), ws.numel() * ws.element_size(), stream()),
+          "mpx_obs_conv2_wgrad")
+
+
 def im2col(a, out, M: int, IH: int, IW: int, Cc: int, kh, kw, sh, sw):
     check(lib.mpx_im2col(ptr(a), ptr(out), M, IH, IW, Cc, kh, kw, sh, sw, stream()), "mpx_im2col")
     return out

@@ -23,7 +23,8 @@ HDR = os.path.join(ROOT, "include", "mapox_b200.h")
 PY = os.path.join(ROOT, "jaxrl_b200", "jax_ffi.py")
 
 # not compute entry points: queries, error string, test knobs
-NON_COMPUTE = {"mpx_last_error", "mpx_version", "mpx_debug_set", "mpx_debug_set_stamps"}
+NON_COMPUTE = {"mpx_last_error", "mpx_version", "mpx_debug_set", "mpx_debug_set_stamps", "mpx_obs_train_supported",
+               "mpx_obs_train_tiles"}
 # mpx_muon_step == mpx_muon_step_phased(phases=3): one handler (MpxMuonStep) serves both
 SERVED_BY = {"mpx_muon_step": "mpx_muon_step_phased"}
 
