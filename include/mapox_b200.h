@@ -157,6 +157,18 @@ int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const mpx_bf16* wt
 int mpx_glu_bwd_fused(const mpx_bf16* xn, const mpx_bf16* dy, const mpx_bf16* wt_ug64, const mpx_bf16* wt_d,
                       mpx_bf16* dug, mpx_bf16* dxn, int M, int H, int F, mpx_stream_t stream);
 
+/* Backward of the value path in one kernel (network.py:335-341 + values.py:34,40-41 under nnx.grad, train.py:236-238):
+ * given xf (M,H) = the normalised trunk output and dvl (M,64) bf16 = d loss / d value logits (columns >= NL zero), it
+ * recomputes z = bf16(bf16(xf @ Wvm) + b_vm) on chip and writes pv (M,Vh) = bf16(gelu(z)) and dz (M,Vh) =
+ * bf16(bf16(dvl @ Wvh^T) * gelu'(z)) (operands of dWvh = pv^T dvl and dWvm = xf^T dz), dxf (M,H) = bf16(dz @ Wvm^T),
+ * and db_vm (Vh) fp32 += column sums of dz (fixed order).  The forward therefore keeps nothing of the value MLP
+ * (mpx_value_head_fused with vlogits).  wt_vm (Vh,H) = Wvm^T and w_vh_pad (Vh,64) = Wvh zero-padded to 64 columns, bf16
+ * (mpx_prep_weights).  H must be 128, Vh % 64 == 0, Vh <= 1024.  workspace: mpx_value_bwd_fused_workspace_bytes(Vh). */
+size_t mpx_value_bwd_fused_workspace_bytes(int Vh);
+int mpx_value_bwd_fused(const mpx_bf16* xf, const mpx_bf16* dvl, const mpx_bf16* wt_vm, const mpx_bf16* b_vm,
+                        const mpx_bf16* w_vh_pad, mpx_bf16* pv, mpx_bf16* dz, mpx_bf16* dxf, float* db_vm, int M, int H,
+                        int Vh, void* workspace, size_t workspace_bytes, mpx_stream_t stream);
+
 /* Whole value path of a rollout step in one kernel (network.py:321,335-341 + values.py:40-45):
  * value = sum softmax(f32(pv) @ Wvh + b_vh) * centers, pv = bf16(gelu(bf16(bf16(xf @ Wvm) + b_vm))),
  * xf = RMSNorm(x; norm_scale, eps) when norm_scale != NULL, else xf = x (rows already normalised).

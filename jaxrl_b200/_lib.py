@@ -101,6 +101,9 @@ lib.mpx_linear_f32w.argtypes = [c_p, c_ll, c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c
 lib.mpx_glu_fused.argtypes = [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, C.c_float, c_p, c_p, c_p]
 lib.mpx_glu_bwd_fused.argtypes = [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p]
 lib.mpx_value_head_fused.argtypes = [c_p, c_p, C.c_float, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]
+lib.mpx_value_bwd_fused_workspace_bytes.restype = C.c_size_t
+lib.mpx_value_bwd_fused_workspace_bytes.argtypes = [c_i]
+lib.mpx_value_bwd_fused.argtypes = [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, C.c_size_t, c_p]
 lib.mpx_rmsnorm_fwd.argtypes = [c_p, c_p, c_f, c_p, c_ll, c_i, c_p]
 lib.mpx_rmsnorm_bwd.argtypes = [c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_ll, c_i, c_p]
 lib.mpx_glu_bwd.argtypes = [c_p, c_p, c_p, c_p, c_ll, c_i, c_p]

@@ -696,6 +696,20 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(MpxPolicyHeadBwd, PolicyHeadBwdImpl,
                               ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<BF>().Arg<F32>().Arg<BF>().Arg<F32>().Ret<BF>().Ret<F32>(),
                               MPX_TRAITS);
 
+// Backward of the value MLP + fp32 head in one kernel (network.py:335-341, values.py:34,40-41 under nnx.grad): pv, dz
+// (weight-gradient operands), d xf; the value-MLP bias gradient accumulates.  aliases: db_in(5) -> 3
+static ffi::Error ValueBwdFusedImpl(mpx_stream_t stream, BF xf, BF dvl, BF wt_vm, BF b_vm, BF w_vh_pad, F32 db_in, RBF pv,
+                                    RBF dz, RBF dxf, RF32 db, RU8 workspace) {
+  (void)db_in;
+  MPX_CALL(mpx_value_bwd_fused(bf(xf), bf(dvl), bf(wt_vm), bf(b_vm), bf(w_vh_pad), rbf(pv), rbf(dz), rbf(dxf), db->typed_data(),
+                               static_cast<int>(rows_of(xf)), last_dim(xf), static_cast<int>(wt_vm.dimensions()[0]),
+                               workspace->untyped_data(), workspace->element_count(), stream), "mpx_value_bwd_fused");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(MpxValueBwdFused, ValueBwdFusedImpl,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<BF>().Arg<BF>().Arg<BF>().Arg<BF>().Arg<BF>().Arg<F32>()
+                                  .Ret<BF>().Ret<BF>().Ret<BF>().Ret<F32>().Ret<U8>(),
+                              MPX_TRAITS);
+
 // Whole value path of a rollout step (network.py:321,335-341 + values.py:40-45).  norm_scale: 0 elements => x is xf.
 static ffi::Error ValueHeadFusedImpl(mpx_stream_t stream, BF x, F32 norm_scale, BF wt_vm, BF b_vm, BF wt_vh_hilo, F32 b_vh,
                                      F32 centers, float eps, RF32 value, RF32 vlogits) {

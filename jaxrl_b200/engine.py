@@ -32,10 +32,12 @@ def _round_up(n: int, m: int) -> int:
 
 class PolicyEngine:
     def __init__(self, cfg: ModelConfig, device="cuda", seed: int = 0, params: Optional[ParamStore] = None,
-                 bias_noise: float = 0.0, fused_rollout: bool = True, world: int = 1, fused_obs_train: bool = True):
+                 bias_noise: float = 0.0, fused_rollout: bool = True, world: int = 1, fused_obs_train: bool = True,
+                 fused_value_train: bool = True):
         """fused_rollout=False runs the rollout step through the general (per-op) kernel chain even where the
         one-kernel-per-half-block kernels apply - the chain every shape without a fused kernel takes (tests);
-        fused_obs_train=False does the same for the training-side observation encoder (im2col + GEMM chain)."""
+        fused_obs_train=False does the same for the training-side observation encoder (im2col + GEMM chain),
+        fused_value_train=False for the training-side value path (GEMM + gelu_bwd chain)."""
         if cfg.head_dim != 32:
             raise _lib.MpxError("head_dim must be 32 on the B200 path")
         if cfg.obs_type not in ("grid_cnn", "grid_flattened"):
@@ -58,6 +60,9 @@ class PolicyEngine:
         self.fused_glu_train = glu_ok
         self.fused_value = (H == 128 and cfg.value_hidden_dim is not None and cfg.value_hidden_dim % 64 == 0
                             and cfg.value_n_logits <= 64 and fused_rollout)   # decode path: one kernel for the value path
+        # training path: forward = the same kernel writing the logits, backward = one kernel (value_bwd_fused.cu)
+        self.fused_value_train = bool(fused_value_train and H == 128 and cfg.value_hidden_dim % 64 == 0
+                                      and cfg.value_hidden_dim <= 1024 and cfg.value_n_logits <= 64)
         self.timescale = (torch.tensor(cfg.rope_max_wavelength, dtype=F32)
                           ** (2.0 * torch.arange(0, D // 2, dtype=F32) / D)).to(self.dev)
         sup = torch.linspace(cfg.value_min, cfg.value_max, cfg.value_n_logits + 1, dtype=F32)
@@ -261,7 +266,12 @@ class PolicyEngine:
         if not self.fused_glu_train:
             ws.u = [e(M, F) for _ in range(L)]
             ws.g = [e(M, F) for _ in range(L)]
-        ws.xf, ws.zv, ws.pv = e(M, H), e(M, self.Vh), e(M, self.Vh)
+        ws.xf, ws.pv = e(M, H), e(M, self.Vh)
+        if self.fused_value_train:
+            ws.zv, ws.vval = None, f(M)
+            ws.vb_ws = torch.empty(_lib.lib.mpx_value_bwd_fused_workspace_bytes(self.Vh), dtype=torch.uint8, device=dev)
+        else:
+            ws.zv = e(M, self.Vh)
         ws.logits, ws.vlogits = f(M, self.A), f(M, self.NL)
         ws.pos = torch.arange(T, dtype=I32, device=dev)
         # backward scratch
@@ -497,11 +507,15 @@ class PolicyEngine:
         ops.value_head_fused(hidden, w["wt_vm"], w["b_vm"], w["wt_vh_hilo"], p["value_head.dense.bias"], self.centers,
                              value_out, norm_scale=p["output_norm.scale"])
 
-    def _heads_fwd(self, x, action_mask, xf, logits, pv, zv, vlogits):
-        """network.py:321-341."""
+    def _heads_fwd(self, x, action_mask, xf, logits, pv, zv, vlogits, vval=None):
+        """network.py:321-341.  vval (M,) f32: take the one-kernel value path (training; nothing kept for the backward)."""
         p, w = self.p, self.w
         ops.rmsnorm_fwd(x, p["output_norm.scale"], out=xf)
         ops.policy_logits(xf, p["action_embedder.embedding_table"], action_mask, out=logits)
+        if vval is not None:                           # value MLP + fp32 head in one kernel
+            ops.value_head_fused(xf, w["wt_vm"], w["b_vm"], w["wt_vh_hilo"], p["value_head.dense.bias"], self.centers,
+                                 vval, vlogits=vlogits)
+            return
         ops.linear(xf, w["wt_vm"], bias=w["b_vm"], act=1, out=pv, y_pre=zv)
         ops.linear_f32w(pv, w["wt_vh_hilo"], p["value_head.dense.bias"], vlogits, self.NL)
 
@@ -527,7 +541,10 @@ class PolicyEngine:
             else:
                 ops.glu_up(ws.xn2[i], w[pre + "wt_ug"], self.F, save=True, h=ws.h[i], u=ws.u[i], g=ws.g[i])
                 ops.linear(ws.h[i], w[pre + "wt_d"], residual=ws.x1[i], out=ws.x[i + 1])
-        self._heads_fwd(ws.x[self.L], action_mask, ws.xf, ws.logits, ws.pv, ws.zv, ws.vlogits)
+        if self.fused_value_train:
+            self._heads_fwd(ws.x[self.L], action_mask, ws.xf, ws.logits, None, None, ws.vlogits, vval=ws.vval)
+        else:
+            self._heads_fwd(ws.x[self.L], action_mask, ws.xf, ws.logits, ws.pv, ws.zv, ws.vlogits)
         return ws.vlogits, ws.logits
 
     # ------------------------------------------------------------------------------------------ side stream
@@ -574,15 +591,23 @@ class PolicyEngine:
         def _wg_vhead():                          # dvl / dpv are not rewritten in this pass
             ops.linear_wgrad(ws.pv, ws.dvl, p.g("value_head.dense.kernel"), M=M, K=Vh, N=NL, ldx=Vh, ldy=64, lddw=NL)
             ops.colsum(ws.dvl, p.g("value_head.dense.bias"), M=M, N=NL, ld=64)
-        self._side_run(_wg_vhead)
-        ops.linear(ws.dvl, w["w_vh_pad"], out=ws.dpv)
-        ops.gelu_bwd(ws.dpv, ws.zv, out=ws.dpv)
+        if self.fused_value_train:
+            # one kernel: recompute the pre-activation, pv / dz for the weight gradients, d xf, value-MLP bias gradient
+            ops.value_bwd_fused(ws.xf, ws.dvl, w["wt_vm"], w["b_vm"], w["w_vh_pad"], ws.pv, ws.dpv, ws.dxn,
+                                p.g("value_mlp.bias"), ws=ws.vb_ws)
+            self._side_run(_wg_vhead)
+            self._side_run(lambda: ops.linear_wgrad(ws.xf, ws.dpv, p.g("value_mlp.kernel"), M=M, K=H, N=Vh, ldx=H, ldy=Vh,
+                                                    lddw=Vh))
+        else:
+            self._side_run(_wg_vhead)
+            ops.linear(ws.dvl, w["w_vh_pad"], out=ws.dpv)
+            ops.gelu_bwd(ws.dpv, ws.zv, out=ws.dpv)
 
-        def _wg_vmlp():
-            ops.linear_wgrad(ws.xf, ws.dpv, p.g("value_mlp.kernel"), M=M, K=H, N=Vh, ldx=H, ldy=Vh, lddw=Vh)
-            ops.colsum(ws.dpv, p.g("value_mlp.bias"), M=M, N=Vh, ld=Vh)
-        self._side_run(_wg_vmlp)
-        ops.linear(ws.dpv, w["w_vm"], out=ws.dxn)                      # d xf from the value path
+            def _wg_vmlp():
+                ops.linear_wgrad(ws.xf, ws.dpv, p.g("value_mlp.kernel"), M=M, K=H, N=Vh, ldx=H, ldy=Vh, lddw=Vh)
+                ops.colsum(ws.dpv, p.g("value_mlp.bias"), M=M, N=Vh, ld=Vh)
+            self._side_run(_wg_vmlp)
+            ops.linear(ws.dpv, w["w_vm"], out=ws.dxn)                  # d xf from the value path
         # ---- tied policy head (network.py:323) and output norm (:321)
         ops.policy_head_bwd(ws.dlogits, ws.xf, p["action_embedder.embedding_table"],
                             p.g("action_embedder.embedding_table"), dx_other=ws.dxn, out=ws.dxa)

@@ -34,7 +34,8 @@ for _n, _args in (("mpx_gae_workspace_bytes", [ctypes.c_int, ctypes.c_int]),
                   ("mpx_conv1_onehot_wgrad_workspace_bytes", [ctypes.c_longlong] + [ctypes.c_int] * 6),
                   ("mpx_adamw_workspace_bytes", [ctypes.c_longlong]),
                   ("mpx_muon_workspace_bytes", [ctypes.c_longlong, ctypes.c_int]),
-                  ("mpx_obs_fused_image_bytes", []), ("mpx_obs_train_bwd_workspace_bytes", [])):
+                  ("mpx_obs_fused_image_bytes", []), ("mpx_obs_train_bwd_workspace_bytes", []),
+                  ("mpx_value_bwd_fused_workspace_bytes", [ctypes.c_int])):
     getattr(_CORE, _n).restype = ctypes.c_size_t
     getattr(_CORE, _n).argtypes = _args
 
@@ -47,7 +48,7 @@ TARGETS = (
     "MpxConv1OnehotFwd", "MpxConv1OnehotWgrad", "MpxObsOnehotIm2col", "MpxIm2col", "MpxCol2im", "MpxFlatEmbedFwd",
     "MpxFlatEmbedBwd", "MpxPolicyLogits", "MpxPolicySample", "MpxPolicyHeadSample", "MpxGumbelNoise", "MpxPpoPolicyLoss",
     "MpxPolicyHeadBwd", "MpxValueHeadFused", "MpxAdamwStep", "MpxMuonStep", "MpxMuonApplySharded", "MpxPrepWeights",
-    "MpxTransposeTb", "MpxObsTrainFwd", "MpxObsTrainBwd", "MpxObsConv2Wgrad",
+    "MpxTransposeTb", "MpxObsTrainFwd", "MpxObsTrainBwd", "MpxObsConv2Wgrad", "MpxValueBwdFused",
 )
 for _t in TARGETS:
     jax.ffi.register_ffi_target(_t, jax.ffi.pycapsule(getattr(_XLA_LIB, _t)), platform="CUDA")
@@ -350,3 +351,14 @@ def value_head_fused(x, norm_scale, wt_vm, b_vm, wt_vh_hilo, b_vh, centers, eps:
     B, NL = x.shape[0], centers.shape[0]
     return _call("MpxValueHeadFused", (_sds((B,), F32), _sds((B, NL), F32)), x, norm_scale, wt_vm, b_vm, wt_vh_hilo, b_vh,
                  centers, eps=np.float32(eps))
+
+
+def value_bwd_fused(xf, dvl, wt_vm, b_vm, w_vh_pad, db_vm):
+    """Backward of value_mlp + value_head in one kernel (network.py:335-341, values.py:34,40-41): returns
+    (pv, dz, dxf, db_vm + d b_vm); dWvh = pv^T dvl and dWvm = xf^T dz are linear_wgrad calls on pv / dz."""
+    M, H = xf.shape
+    Vh = wt_vm.shape[0]
+    pv, dz, dxf, db, _ = _call("MpxValueBwdFused", (_sds((M, Vh), BF16), _sds((M, Vh), BF16), _sds((M, H), BF16),
+                                                    _sds((Vh,), F32), _sds((_CORE.mpx_value_bwd_fused_workspace_bytes(Vh),), U8)),
+                               xf, dvl, wt_vm, b_vm, w_vh_pad, db_vm, aliases={5: 3})
+    return pv, dz, dxf, db

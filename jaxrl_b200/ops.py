@@ -234,6 +234,27 @@ def value_head_fused(x, wt_vm, b_vm, wt_vh_hilo, b_vh, centers, value, vlogits=N
     return value
 
 
+def value_bwd_fused(xf, dvl, wt_vm, b_vm, w_vh_pad, pv, dz, dxf, db_vm, ws=None):
+    """Backward of the value MLP + head in one kernel: recomputes the pre-activation, writes pv / dz (weight-gradient
+    operands), dxf, and accumulates the value-MLP bias gradient."""
+    for t, n in ((xf, "xf"), (dvl, "dvl"), (wt_vm, "wt_vm"), (b_vm, "b_vm"), (w_vh_pad, "w_vh_pad"), (pv, "pv"), (dz, "dz"),
+                 (dxf, "dxf")):
+        _req(t, BF16, n)
+    _req(db_vm, F32, "db_vm")
+    H = xf.shape[-1]
+    M = xf.numel() // H
+    Vh = wt_vm.shape[0]
+    if dvl.shape[-1] != 64 or w_vh_pad.shape[-1] != 64:
+        raise _lib.MpxError("value_bwd_fused: dvl / w_vh_pad must have 64 (padded) logit columns")
+    need = lib.mpx_value_bwd_fused_workspace_bytes(Vh)
+    if ws is None:
+        ws = torch.empty(need, dtype=torch.uint8, device=xf.device)
+    check(lib.mpx_value_bwd_fused(ptr(xf), ptr(dvl), ptr(wt_vm), ptr(b_vm), ptr(w_vh_pad), ptr(pv), ptr(dz), ptr(dxf),
+                                  ptr(db_vm), M, H, Vh, ptr(ws), ws.numel() * ws.element_size(), stream()),
+          "mpx_value_bwd_fused")
+    return dxf
+
+
 def pack_glu_weight64(w_up: torch.Tensor, w_gate: torch.Tensor) -> torch.Tensor:
     """(K,F) flax kernels -> (2F,K) bf16, 128-row tiles [64 up rows | 64 gate rows] (see mpx_glu_fused)."""
     K, F = w_up.shape

@@ -204,3 +204,97 @@ def test_engine_encoder_gradients_fused_vs_unfused():
         got = res[True][1][k]
         r = (got - ref).norm().item() / (ref.norm().item() + 1e-12)
         assert r < 1e-2, f"{k}: rel l2 {r}"
+
+
+# ---------------------------------------------------------------------------------------------- value path backward
+@pytest.mark.parametrize("M,Vh,NL", [(128, 768, 51), (1, 64, 64), (300, 768, 51), (128 * 150 + 37, 768, 51), (77, 128, 17),
+                                     (128 * 297 + 5, 192, 51)])
+def test_value_bwd_fused(ops, M, Vh, NL):
+    """One-kernel backward of the value MLP + fp32 head vs autograd through the oracle (network.py:335-341, values.py:34,
+    40-41): pv, dz, d xf, the bias gradient, and bit-identity with the GEMM + gelu_bwd chain it replaces."""
+    import math
+    gen = g(M + Vh + NL)
+    H = 128
+    xf = torch.randn(M, H, generator=gen).to(BF16)
+    wvm = torch.randn(H, Vh, generator=gen) / math.sqrt(H)
+    bvm = torch.randn(Vh, generator=gen) * 0.1
+    wvh = torch.randn(Vh, NL, generator=gen) / math.sqrt(Vh)
+    dvl = torch.zeros(M, 64, dtype=BF16)
+    dvl[:, :NL] = (torch.randn(M, NL, generator=gen) * 0.02).to(BF16)
+    # oracle: z -> pv -> logits (fp32 head), cotangent dvl on the logits
+    xr = xf.clone().requires_grad_(True)
+    bvr = bvm.clone().requires_grad_(True)
+    z = O.linear(xr, wvm, bvr)
+    z.retain_grad()
+    pv_ref = O.gelu_tanh(z)
+    vl = O.linear(pv_ref, wvh, None, dtype=None)
+    (vl * dvl[:, :NL].float()).sum().backward()
+    # kernel
+    d = lambda t: t.to(DEV)
+    wt_vm = d(wvm.t().contiguous().to(BF16))
+    w_vh_pad = torch.zeros(Vh, 64, dtype=BF16)
+    w_vh_pad[:, :NL] = wvh.to(BF16)
+    pv = torch.full((M, Vh), float("nan"), dtype=BF16, device=DEV)
+    dz = torch.full((M, Vh), float("nan"), dtype=BF16, device=DEV)
+    dxf = torch.full((M, H), float("nan"), dtype=BF16, device=DEV)
+    db = torch.full((Vh,), 0.5, device=DEV)
+    ops.value_bwd_fused(d(xf), d(dvl), wt_vm, d(bvm.to(BF16)), d(w_vh_pad), pv, dz, dxf, db)
+    torch.cuda.synchronize()
+    kw = dict(rtol=2e-2, abs_floor_frac=2e-2, allow_frac=2e-3, max_err_frac=0.2)
+    assert_close_bf16(pv, pv_ref, f"value_bwd_fused pv M={M}", rtol=1e-2, abs_floor_frac=1e-2, allow_frac=2e-3, max_err_frac=0.1)
+    assert_close_bf16(dz, z.grad, f"value_bwd_fused dz M={M}", **kw)
+    assert_close_bf16(dxf, xr.grad, f"value_bwd_fused dxf M={M}", **kw)
+    rel = ((db - 0.5).cpu() - bvr.grad).norm().item() / (bvr.grad.norm().item() + 1e-12)
+    assert rel < 1e-2, f"value-MLP bias gradient rel l2 {rel}"
+    # the chain it replaces: GEMM (+bias, gelu, pre-activation) / dpv GEMM / gelu_bwd / dxf GEMM - same rounding points
+    pv2 = torch.empty(M, Vh, dtype=BF16, device=DEV)
+    zv2 = torch.empty(M, Vh, dtype=BF16, device=DEV)
+    dpv2 = torch.empty(M, Vh, dtype=BF16, device=DEV)
+    dxf2 = torch.empty(M, H, dtype=BF16, device=DEV)
+    ops.linear(d(xf), wt_vm, bias=d(bvm.to(BF16)), act=1, out=pv2, y_pre=zv2)
+    ops.linear(d(dvl), d(w_vh_pad), out=dpv2)
+    ops.gelu_bwd(dpv2, zv2, out=dpv2)
+    ops.linear(dpv2, d(wvm.to(BF16)), out=dxf2)
+    torch.cuda.synchronize()
+    assert torch.equal(pv, pv2), "pv differs from the unfused chain"
+    assert torch.equal(dz, dpv2), "dz differs from the unfused chain"
+    assert_close_bf16(dxf, dxf2, f"value_bwd_fused dxf vs chain M={M}", rtol=1e-2, abs_floor_frac=4e-3)
+    # deterministic
+    db2 = torch.full((Vh,), 0.5, device=DEV)
+    ops.value_bwd_fused(d(xf), d(dvl), wt_vm, d(bvm.to(BF16)), d(w_vh_pad), pv2, dpv2, dxf2, db2)
+    torch.cuda.synchronize()
+    assert torch.equal(db, db2) and torch.equal(dxf, dxf2)
+
+
+def test_engine_value_path_fused_vs_unfused():
+    """forward_train + loss_and_backward with the one-kernel value path (forward and backward) against the GEMM chain:
+    losses and every gradient agree."""
+    from jaxrl_b200.config import ModelConfig, PPOConfig
+    from jaxrl_b200.engine import PolicyEngine
+    cfg = ModelConfig(num_layers=1, max_seq_length=64, action_dim=6)
+    hyp = PPOConfig()
+    Bm, T = 5, 64
+    M = Bm * T
+    gen = g(9)
+    obs = torch.stack([torch.randint(0, n, (Bm, T, 11, 11), generator=gen) for n in cfg.obs_max_value], -1).to(torch.uint8).to(DEV)
+    batch = dict(last_rewards=torch.randn(M, generator=gen) * 0.1, last_actions=torch.randint(0, 6, (M,), generator=gen).to(torch.int32),
+                 actions=torch.randint(0, 6, (M,), generator=gen).to(torch.int32), log_prob=-torch.rand(M, generator=gen) * 2 - 0.2,
+                 advantages=torch.randn(M, generator=gen), targets=torch.randn(M, generator=gen) * 2)
+    batch = {k: v.to(DEV) for k, v in batch.items()}
+    batch["obs"] = obs
+    res = {}
+    for fused in (False, True):
+        eng = PolicyEngine(cfg, DEV, seed=3, bias_noise=0.05, fused_value_train=fused)
+        assert eng.fused_value_train == fused
+        ws = eng.alloc_train(Bm, T)
+        eng.forward_train(ws, obs, batch["last_rewards"], batch["last_actions"])
+        eng.p.grad.zero_()
+        losses = eng.loss_and_backward(ws, batch, hyp, progress=0.0).clone()
+        torch.cuda.synchronize()
+        res[fused] = (losses.cpu(), ws.vlogits.clone(), eng.p.grad_dict())
+    torch.testing.assert_close(res[True][0][:3], res[False][0][:3], rtol=1e-4, atol=1e-5)     # [3] is a spare slot
+    torch.testing.assert_close(res[True][1], res[False][1], rtol=1e-3, atol=1e-3)
+    for k, ref in res[False][2].items():
+        got = res[True][2][k]
+        r = (got - ref).norm().item() / (ref.norm().item() + 1e-12)
+        assert r < 2e-2, f"{k}: rel l2 {r}"
