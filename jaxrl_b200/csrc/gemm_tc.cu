@@ -1018,6 +1018,10 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
                       uint32_t box_cols, uint32_t box_rows) {
   return make_tmap_bf16_2d_sw(out, base, rows, cols, ld, box_cols, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
+int make_tmap_bf16_2d_sw64(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                           uint32_t box_cols, uint32_t box_rows) {
+  return make_tmap_bf16_2d_sw(out, base, rows, cols, ld, box_cols, box_rows, CU_TENSOR_MAP_SWIZZLE_64B);
+}
 static int make_tmap_bf16_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                                 uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = get_encode_fn();

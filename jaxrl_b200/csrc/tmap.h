@@ -12,5 +12,8 @@ namespace mpx {
 // Returns 0 on success.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_cols, uint32_t box_rows);
+// The same with the 64-byte swizzle (box_cols * 2 bytes must be <= 64).
+int make_tmap_bf16_2d_sw64(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                           uint32_t box_cols, uint32_t box_rows);
 
 }  // namespace mpx
