@@ -32,6 +32,7 @@ extern int g_attn_decode_impl;
 extern int g_attn_train_impl;
 extern int g_glu_fused_cluster;
 extern int g_value_fused_cluster;
+extern int g_muon_ns_impl;
 
 }  // namespace mpx
 
@@ -60,6 +61,10 @@ extern "C" int mpx_debug_set(int key, int value) {
   }
   if (key == 4) {
     mpx::g_value_fused_cluster = value;
+    return MPX_OK;
+  }
+  if (key == 5) {
+    mpx::g_muon_ns_impl = value;
     return MPX_OK;
   }
   if (key == 6) {

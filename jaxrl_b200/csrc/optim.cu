@@ -5,6 +5,7 @@
 //   whole minibatch step is CUDA-graph replayable.
 //   prep_weights: fp32 master weights -> bf16 operand copies (optionally transposed / re-tiled) for the GEMMs.
 #include "common.cuh"
+#include "muon.h"
 #include "ptx.cuh"
 
 namespace mpx {
@@ -192,16 +193,13 @@ __global__ void __launch_bounds__(256) transpose_tb_rows_kernel(const uint16_t* 
 //   X = mu_hat oriented rows <= cols ; X /= (||X||_F + eps) ; 5 x Newton-Schulz: A = X X^T, B = c1 A + c2 A A,
 //   X = c0 X + B X ; update = -lr * ( sqrt(max(1, out/in)) * X + weight_decay * p )
 // everything else goes through AdamW(nesterov=True); clip_by_global_norm then acts on the combined update.
-// Newton-Schulz runs in fp32 (as optax does) on small matrices: batched SIMT GEMM, one grid.z slice per matrix.
-struct MuonMat {
-  long long off;       // offset of the parameter in the flat buffers
-  int rows, cols;      // parameter shape (in, out)
-  int r, c;            // oriented shape, r <= c
-  int transposed;      // 1 if the oriented matrix is the transpose of the parameter
-  int _pad;
-  long long xoff;      // offset of this matrix in the X / X' workspaces (r*c floats)
-  long long aoff;      // offset in the A / B workspaces (r*r floats)
-};
+// Newton-Schulz runs on fp32 matrices (as optax does).  Two implementations of its contractions: the tensor-core one with
+// bf16 hi/lo operand pairs (muon_ns_tc.cu) and the batched SIMT fp32 GEMM below.  The chain is 15 dependent launches; with a
+// handful of 128-row matrices (return_2_layers: 8) it is pure latency and the lighter SIMT CTAs finish sooner (244 vs 306 us
+// per step, and they do not take 129 KB of shared memory from the kernels they overlap with), from a few dozen matrices on
+// the tensor cores win (blog_32_layers 1314 -> 756 us, multitask 2418 -> 1176 us).  mpx_debug_set(5, v): 0 = by table
+// size, 1 = SIMT, 2 = tensor cores.
+int g_muon_ns_impl = 0;
 
 __global__ void __launch_bounds__(256) muon_prepare_kernel(const MuonMat* __restrict__ mats, const float* __restrict__ g,
                                                            float* __restrict__ mu, float* __restrict__ X,
@@ -469,11 +467,16 @@ extern "C" int mpx_muon_step_phased(float* params, const float* grads, float* mu
     float* xout = X1;
     for (int it = 0; it < ns_steps; ++it) {
       const int first = it == 0;
-      const int tr = ceil_div(max_r, 64), tc = ceil_div(max_c, 64), nks = ceil_div(max_c, NS_KSPLIT);
-      cudaMemsetAsync(Ab, 0, (size_t)a_total * sizeof(float), s);
-      muon_ns_gemm_kernel<<<dim3(tr * nks, tr, nmat), 256, 0, s>>>(mm, xin, xout, Ab, Bb, norm2, 0, first, tr, c0, c1, c2, eps);
-      muon_ns_gemm_kernel<<<dim3(tr, tr, nmat), 256, 0, s>>>(mm, xin, xout, Ab, Bb, norm2, 1, 0, tr, c0, c1, c2, eps);
-      muon_ns_gemm_kernel<<<dim3(tc, tr, nmat), 256, 0, s>>>(mm, xin, xout, Ab, Bb, norm2, 2, first, tc, c0, c1, c2, eps);
+      if (g_muon_ns_impl == 2 || (g_muon_ns_impl == 0 && (nmat > 12 || max_r > 128))) {
+        const int rc = muon_ns_tc_iteration(mm, nmat, max_r, max_c, xin, xout, Ab, Bb, norm2, first, c0, c1, c2, eps, s);
+        if (rc) return rc;
+      } else {
+        const int tr = ceil_div(max_r, 64), tc = ceil_div(max_c, 64), nks = ceil_div(max_c, NS_KSPLIT);
+        cudaMemsetAsync(Ab, 0, (size_t)a_total * sizeof(float), s);
+        muon_ns_gemm_kernel<<<dim3(tr * nks, tr, nmat), 256, 0, s>>>(mm, xin, xout, Ab, Bb, norm2, 0, first, tr, c0, c1, c2, eps);
+        muon_ns_gemm_kernel<<<dim3(tr, tr, nmat), 256, 0, s>>>(mm, xin, xout, Ab, Bb, norm2, 1, 0, tr, c0, c1, c2, eps);
+        muon_ns_gemm_kernel<<<dim3(tc, tr, nmat), 256, 0, s>>>(mm, xin, xout, Ab, Bb, norm2, 2, first, tc, c0, c1, c2, eps);
+      }
       float* tmp = xin; xin = xout; xout = tmp;
     }
     muon_finish_kernel<<<dim3(32, nmat), 256, 0, s>>>(mm, xin, params, update_scratch, step, lr0, total_steps,

@@ -102,6 +102,50 @@ def test_optimizer_step_matches_oracle(opt_type):
     assert step.item() == 3
 
 
+@pytest.mark.parametrize("hidden", [128, 256])
+def test_muon_newton_schulz_tensor_core_matches_simt(hidden):
+    """The tcgen05 Newton-Schulz path (bf16 hi/lo operand pairs, muon_ns_tc.cu) against the SIMT fp32 GEMM path
+    (mpx_debug_set(5, 2) / (5, 1)) on the same gradients: r = 128 / 256 matrices, K and N tails (288 = 4.5 x 64), and bit-identical
+    repeats (no split-K atomics)."""
+    from jaxrl_b200 import ops
+    from jaxrl_b200._lib import lib
+    from jaxrl_b200.config import OptimizerConfig
+    from jaxrl_b200.params import ParamStore
+    cfg = replace(CFG, num_layers=1, hidden_features=hidden)
+    ocfg = OptimizerConfig(type="muon")
+    outs = []
+    for impl in (2, 1, 2):
+        lib.mpx_debug_set(5, impl)
+        try:
+            ps = ParamStore(cfg, DEV, seed=21, bias_noise=0.02)
+            n = ps.numel
+            z = lambda: torch.zeros(n, device=DEV)
+            mu, nu, scratch = z(), z(), z()
+            step = torch.zeros(1, dtype=torch.int32, device=DEV)
+            norm = torch.zeros(1, device=DEV)
+            tab, nmat, xt, at, mr, mc = ps.muon_table()
+            assert mr == hidden
+            ns_ws = torch.zeros(2 * xt + 2 * at + nmat, device=DEV)
+            gen = torch.Generator().manual_seed(5)
+            for t in range(2):
+                ps.grad.copy_((torch.randn(n, generator=gen) * 0.01).to(DEV))
+                ops.muon_step(ps.flat, ps.grad, mu, nu, scratch, ps.n_adam, tab, nmat, xt, at, mr, mc, ns_ws, step,
+                              ocfg.learning_rate, 100, ocfg.beta1, ocfg.beta2, 1e-8, ocfg.weight_decay, ocfg.max_norm,
+                              norm_out=norm)
+            torch.cuda.synchronize()
+            outs.append((scratch[ps.n_adam:].clone(), norm.clone()))
+        finally:
+            lib.mpx_debug_set(5, 0)
+    (u_tc, n_tc), (u_simt, n_simt), (u_tc2, _) = outs
+    assert u_simt.norm().item() > 0
+    rel = ((u_tc - u_simt).double().norm() / u_simt.double().norm()).item()
+    _log(f"muon NS tcgen05 vs SIMT (H={hidden}): update rel_l2={rel:.3e}")
+    assert rel < 2e-4, rel
+    torch.testing.assert_close(n_tc, n_simt, rtol=1e-4, atol=0)
+    # same inputs twice: the Frobenius norm still comes from atomics (summation order), everything after it is fixed-order
+    assert ((u_tc2 - u_tc).double().norm() / u_tc.double().norm()).item() < 1e-4
+
+
 def test_muon_step_phased_matches_single_call():
     """mpx_muon_step_phased: phase 1 (matrices, on a second stream) then phase 2 == the single-call step."""
     from jaxrl_b200 import ops
