@@ -367,28 +367,29 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(
   }
 }
 
-// dq (bf16, inverse RoPE) from the fp32 accumulator: one thread per (token, head, rotation pair-of-2).
+// dq (bf16, inverse RoPE) from the fp32 accumulator: one thread per (token, two rotation pairs); the rotation angles
+// depend on the token only, so one sincosf pair serves all Nq heads (the kernel was issue-bound on sincosf, not on HBM).
 __global__ void attn_bwd_dq_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dq, long long lddq,
                                    const int32_t* __restrict__ pos, int pos_len, const float* __restrict__ timescale,
                                    long long M, int Nq) {
-  const long long total = M * Nq * 8;
+  const long long total = M * 8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
     const int sub = (int)(i & 7);
-    const long long th = i >> 3;
-    const int head = (int)(th % Nq);
-    const long long tok = th / Nq;
+    const long long tok = i >> 3;
     const float pf = (float)pos[tok % pos_len];
-    const float* src = dq_acc + tok * (long long)(Nq * 32) + head * 32 + sub * 2;
-    const float2 a = *reinterpret_cast<const float2*>(src);
-    const float2 bb = *reinterpret_cast<const float2*>(src + 16);
     float s0, c0, s1, c1;
     sincosf(pf / timescale[sub * 2], &s0, &c0);
     sincosf(pf / timescale[sub * 2 + 1], &s1, &c1);
-    __nv_bfloat16* d = dq + tok * lddq + head * 32 + sub * 2;
-    *reinterpret_cast<uint32_t*>(d) = pack_bf16(a.x * c0 + bb.x * s0, a.y * c1 + bb.y * s1);
-    *reinterpret_cast<uint32_t*>(d + 16) = pack_bf16(bb.x * c0 - a.x * s0, bb.y * c1 - a.y * s1);
+    const float* src = dq_acc + tok * (long long)(Nq * 32) + sub * 2;
+    __nv_bfloat16* d = dq + tok * lddq + sub * 2;
+    for (int head = 0; head < Nq; ++head, src += 32, d += 32) {
+      const float2 a = *reinterpret_cast<const float2*>(src);
+      const float2 bb = *reinterpret_cast<const float2*>(src + 16);
+      *reinterpret_cast<uint32_t*>(d) = pack_bf16(a.x * c0 + bb.x * s0, a.y * c1 + bb.y * s1);
+      *reinterpret_cast<uint32_t*>(d + 16) = pack_bf16(bb.x * c0 - a.x * s0, bb.y * c1 - a.y * s1);
+    }
   }
 }
 
@@ -442,7 +443,7 @@ static int launch_bwd(const mpx_attn_train_bwd_args* a, cudaStream_t s) {
       a->lse, a->delta, a->dq_acc, reinterpret_cast<__nv_bfloat16*>(a->dk), a->lddk,
       reinterpret_cast<__nv_bfloat16*>(a->dv), a->lddv, a->pos, a->pos_len, a->rope_timescale, a->T, a->Nkv, scale,
       scale * 1.4426950408889634f);
-  const long long tot = M * a->Nq * 8;
+  const long long tot = M * 8;
   int qgrid = (int)((tot + 255) / 256 < (long long)num_sms() * 16 ? (tot + 255) / 256 : (long long)num_sms() * 16);
   attn_bwd_dq_kernel<<<qgrid, 256, 0, s>>>(a->dq_acc, reinterpret_cast<__nv_bfloat16*>(a->dq), a->lddq, a->pos,
                                            a->pos_len, a->rope_timescale, M, a->Nq);
