@@ -150,6 +150,29 @@ int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const mpx_bf16* wt
                   mpx_bf16* out, int M, int H, int F, const float* norm_scale, float eps, const mpx_bf16* wt_o,
                   mpx_bf16* h_out, mpx_stream_t stream);
 
+/* The same block for the LAST layer of a rollout step with the policy head folded in (network.py:321-333 + sample_actions,
+ * network.py:345-351 / train.py:97-98): after out = x1 + GLU(RMSNorm(x1)) the kernel applies the output RMSNorm to the
+ * finished rows, forms the tied fp32 action logits (masked), draws the Gumbel arg-max action (Philox counters as
+ * mpx_gumbel_noise / mpx_policy_head_sample) and its log-probability - bit-identical to mpx_glu_fused followed by
+ * mpx_policy_head_sample, one launch less per step.  Needs wt_o (the projection prologue); the fused epilogue runs when
+ * the launch is a cluster of four (M <= 32 * 148 / 4 rows per SM wave) and A <= 8, otherwise the call issues the two
+ * kernels itself.  logits_out (M,A), xf_out (M,H), action_mask (M,A), gumbel_in (M,A), stream_offset may be NULL. */
+typedef struct {
+  const float* norm_scale; float eps;             /* output_norm.scale (H) */
+  const float* table; int A;                      /* action_embedder.embedding_table (A,H) f32 */
+  const uint8_t* action_mask;
+  const float* gumbel_in;
+  unsigned long long seed, stream_id;
+  const unsigned long long* stream_offset;
+  float* logits_out;
+  mpx_bf16* xf_out;
+  int32_t* action;                                /* (M) */
+  float* log_prob;                                /* (M) */
+} mpx_policy_head_args;
+int mpx_glu_fused_head(const mpx_bf16* x, const mpx_bf16* wt_ug64, const mpx_bf16* wt_d, const mpx_bf16* residual,
+                       mpx_bf16* out, int M, int H, int F, const float* norm_scale, float eps, const mpx_bf16* wt_o,
+                       const mpx_policy_head_args* head, mpx_stream_t stream);
+
 /* Backward of the same block in one kernel (jax.grad of feed_forward.py:73-78 inside train.py:180-230), for a forward
  * that kept only xn = RMSNorm(x1): u, g, a = gelu(u) and dh = dy @ Wdown^T are recomputed on chip and never stored.
  * Outputs dug (M,2F) = [du | dg], the operand of dWup/dWgate = xn^T dug, and dxn (M,H) = du @ Wup^T + dg @ Wgate^T

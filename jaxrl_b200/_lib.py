@@ -77,6 +77,11 @@ AttnTrainBwdArgs = _struct("mpx_attn_train_bwd_args", [
     ("pos", c_p), ("pos_len", c_i), ("rope_timescale", c_p),
     ("B", c_i), ("T", c_i), ("Nq", c_i), ("Nkv", c_i), ("D", c_i)])
 
+PolicyHeadArgs = _struct("mpx_policy_head_args", [
+    ("norm_scale", c_p), ("eps", C.c_float), ("table", c_p), ("A", c_i), ("action_mask", c_p), ("gumbel_in", c_p),
+    ("seed", C.c_ulonglong), ("stream_id", C.c_ulonglong), ("stream_offset", c_p), ("logits_out", c_p), ("xf_out", c_p),
+    ("action", c_p), ("log_prob", c_p)])
+
 PrepDesc = _struct("mpx_prep_desc", [
     ("src", c_p), ("src_ld", c_ll), ("dst", c_p), ("dst_ld", c_ll), ("rows", c_i), ("cols", c_i),
     ("transpose", c_i), ("_pad", c_i)])
@@ -99,6 +104,7 @@ lib.mpx_linear_wgrad_workspace_bytes.restype = C.c_size_t
 lib.mpx_linear_wgrad_workspace_bytes.argtypes = [c_i, c_i, c_i]
 lib.mpx_linear_f32w.argtypes = [c_p, c_ll, c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_p]
 lib.mpx_glu_fused.argtypes = [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, C.c_float, c_p, c_p, c_p]
+lib.mpx_glu_fused_head.argtypes = [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, C.c_float, c_p, C.POINTER(PolicyHeadArgs), c_p]
 lib.mpx_glu_bwd_fused.argtypes = [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p]
 lib.mpx_value_head_fused.argtypes = [c_p, c_p, C.c_float, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]
 lib.mpx_value_bwd_fused_workspace_bytes.restype = C.c_size_t

@@ -17,7 +17,13 @@
 // kernel therefore runs as a thread-block cluster of CL CTAs per row tile: CTA k of the cluster owns chunks
 // [k*F/64/CL, (k+1)*F/64/CL), leaves its fp32 partial of the output tile in its own shared memory, and the CL
 // partials are summed over distributed shared memory - CTA k finishes output columns [k*128/CL, (k+1)*128/CL).
+//
+// Last layer of a rollout step (mpx_glu_fused_head): the cluster of 4 reduces BY ROWS instead - CTA k receives the four
+// partials of rows [32k, 32k+32) with all 128 columns, adds x1 (every CTA holds the whole x1 tile), stores the block output
+// and, holding complete rows, runs the policy head on them (output RMSNorm, tied logits, mask, Gumbel arg-max, log-prob:
+// policy_head.cuh, 8 lanes per row = the 256 epilogue threads) - the separate policy_head_sample launch disappears.
 #include "common.cuh"
+#include "policy_head.cuh"
 #include "ptx.cuh"
 #include "tmap.h"
 
@@ -40,6 +46,8 @@ struct GluFusedParams {
   float eps;
   int proj;                       // 1: x is the attention output; x1 = residual + x @ Wo^T is formed first
   int h_out;                      // 1: the h chunks are also stored to global memory (tm_h) for the weight gradients
+  int head_on;                    // 1: cluster of 4 with the projection prologue; the partials are reduced BY ROWS and the owner
+  PolicyHeadDev head;             //    of a row finishes it and runs the policy head on it (last layer of a rollout step)
   unsigned long long* dbg;
 };
 
@@ -260,6 +268,8 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
     const int r = quarter * 32 + lane;                       // row within the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     uint32_t ug_ph[2] = {0, 0}, h_ph[2] = {0, 0}, dphase = 0, pf_phase = 0, pe_phase = 0, xphase = 0;
+    unsigned long long head_sid = 0;
+    if (p.head_on) head_sid = p.head.stream_id + (p.head.stream_off ? p.head.stream_off[0] : 0ull);
     // output columns this thread finishes: single CTA -> its half of the row; cluster -> its half of the CTA's slice
     const int slice = 128 / ncta;                            // 128, 64 or 32 columns per CTA
     const int ocol0 = krank * slice + half * (slice / 2);
@@ -459,6 +469,98 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(d_empty);
+      } else if (p.head_on) {
+        // 1'. PUSH my fp32 partial BY ROWS: CTA j finishes rows [32 j, 32 j + 32) and receives them from every CTA of the
+        //     cluster into recv[src][row][32 float4 columns] (st.async completes the owner's transaction barrier)
+        const bool last_tile = tile + (int)gridDim.y >= m_tiles;
+        if (tile != (int)blockIdx.y) mbar_wait_cluster(part_empty, pe_phase ^ 1);   // owners consumed the previous tile
+        pe_phase ^= 1;
+        const uint32_t sp = smem_u32(sP);
+        // the h-chunk buffers are free once the last MMA2 has completed (d_full): the policy head's parameters (action table,
+        // padded per lane slot like policy_head_sample_kernel's; output norm scale) are staged there while the partials travel
+        float* sT = reinterpret_cast<float*>(sH);
+        {
+          const int t = (int)threadIdx.x - 64;
+          for (int i = t; i < p.head.A * 32; i += GF_EPI_WARPS * 32) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.head.table) + i);
+            *reinterpret_cast<float4*>(sT + (i >> 5) * 160 + ((i & 31) >> 2) * 20 + (i & 3) * 4) = v;
+          }
+          if (t < 32) *reinterpret_cast<float4*>(sT + 8 * 160 + 4 * t) = __ldg(reinterpret_cast<const float4*>(p.head.norm_scale) + t);
+        }
+        {
+          uint32_t acc0[32], acc1[32];
+          tmem_ld_32x32(tD + lane_off + 64 * half, acc0);
+          tmem_ld_32x32(tD + lane_off + 64 * half + 32, acc1);
+          tmem_ld_wait();
+          // recv[src][float4 column c4][row slot]: the 32 lanes of a warp (consecutive rows, same owner = r / 32) write 512
+          // contiguous bytes per instruction; the row slot is XOR-ed with (c4 / 4) & 7 so that the 8 lanes that later read one
+          // row's 8 column groups hit 8 different bank groups
+          const uint32_t dst = mapa_u32(sp + (uint32_t)((krank * 32 + 16 * half) * 32) * 16u, quarter);
+          const uint32_t bar = mapa_u32(smem_u32(part_full), quarter);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t* a4 = (i < 8) ? &acc0[4 * i] : &acc1[4 * (i - 8)];
+            const int c4 = 16 * half + i;
+            st_async_v4(dst + (uint32_t)(i * 32 + (lane ^ ((c4 >> 2) & 7))) * 16u, make_uint4(a4[0], a4[1], a4[2], a4[3]), bar);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d_empty);                   // TMEM accumulator drained
+        dbg_stamp(dbg, 21);
+        mbar_wait(part_full, pf_phase);                        // async-proxy completion, like a TMA load
+        pf_phase ^= 1;
+        gf_bar_sync(1, GF_EPI_WARPS * 32);                     // the staged head parameters are visible to every warp
+        dbg_stamp(dbg, 22);
+        {
+          // 2'. my 32 rows, 8 lanes per row: lane `sub` sums columns [16 sub, +16) in CTA-rank order, adds x1, stores the
+          //     block output and feeds the policy head
+          const int rl = (warp - 2) * 4 + (lane >> 3), sub = lane & 7;
+          const int rt = krank * 32 + rl;                      // row inside the 128-row tile
+          float4 sm[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) sm[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 a = lds_v4(sp + (uint32_t)(((j * 32 + 4 * sub + q) * 32 + (rl ^ sub)) * 16));
+              sm[q].x += __uint_as_float(a.x); sm[q].y += __uint_as_float(a.y);
+              sm[q].z += __uint_as_float(a.z); sm[q].w += __uint_as_float(a.w);
+            }
+          const uint32_t x1row = smem_u32(sX1 + rt * 256);
+          const uint4 rv0 = lds_v4(x1row + (((2 * sub) ^ (rt & 7)) << 4)), rv1 = lds_v4(x1row + (((2 * sub + 1) ^ (rt & 7)) << 4));
+          uint32_t xw[8];
+          xw[0] = pack_bf16(bf16_round(sm[0].x) + bf16_lo(rv0.x), bf16_round(sm[0].y) + bf16_hi(rv0.x));
+          xw[1] = pack_bf16(bf16_round(sm[0].z) + bf16_lo(rv0.y), bf16_round(sm[0].w) + bf16_hi(rv0.y));
+          xw[2] = pack_bf16(bf16_round(sm[1].x) + bf16_lo(rv0.z), bf16_round(sm[1].y) + bf16_hi(rv0.z));
+          xw[3] = pack_bf16(bf16_round(sm[1].z) + bf16_lo(rv0.w), bf16_round(sm[1].w) + bf16_hi(rv0.w));
+          xw[4] = pack_bf16(bf16_round(sm[2].x) + bf16_lo(rv1.x), bf16_round(sm[2].y) + bf16_hi(rv1.x));
+          xw[5] = pack_bf16(bf16_round(sm[2].z) + bf16_lo(rv1.y), bf16_round(sm[2].w) + bf16_hi(rv1.y));
+          xw[6] = pack_bf16(bf16_round(sm[3].x) + bf16_lo(rv1.z), bf16_round(sm[3].y) + bf16_hi(rv1.z));
+          xw[7] = pack_bf16(bf16_round(sm[3].z) + bf16_lo(rv1.w), bf16_round(sm[3].w) + bf16_hi(rv1.w));
+          const long long grow = (long long)tile * 128 + rt;
+          const bool live = grow < p.M;
+          if (live) {
+            uint4* o4 = reinterpret_cast<uint4*>(p.out + grow * 128 + 16 * sub);
+            o4[0] = make_uint4(xw[0], xw[1], xw[2], xw[3]);
+            o4[1] = make_uint4(xw[4], xw[5], xw[6], xw[7]);
+          }
+          float xv[16];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            xv[2 * e] = bf16_lo(xw[e]);
+            xv[2 * e + 1] = bf16_hi(xw[e]);
+          }
+          dbg_stamp(dbg, 25);
+          policy_head_row16(xv, live, grow, sub, p.head, head_sid, sT, 160, 20, sT + 8 * 160, dbg);
+        }
+        __syncwarp();
+        dbg_stamp(dbg, 23);
+        if (lane == 0 && !last_tile) {                         // my receive buffer may be overwritten by the next tile
+          const uint32_t pe = smem_u32(part_empty);
+          for (int j = 0; j < ncta; ++j) mbar_arrive_cluster(mapa_u32(pe, j));
+        }
       } else {
         // 1. PUSH my fp32 partial to its owners: CTA j finishes output columns [j*slice, (j+1)*slice) and receives, from
         //    every CTA of the cluster, those columns into recv[src][c4 local][row] (st.async: the data itself completes
@@ -545,9 +647,11 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
 
 using namespace mpx;
 
-extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const mpx_bf16* wt_d, const mpx_bf16* residual,
-                             mpx_bf16* out, int M, int H, int F, const float* norm_scale, float eps, const mpx_bf16* wt_o,
-                             mpx_bf16* h_out, mpx_stream_t stream) {
+// head != nullptr: fold the policy head in when the launch is a cluster of 4 with the projection prologue and A <= 8;
+// *head_done tells the caller whether that happened.
+static int glu_fused_launch(const mpx_bf16* x, const mpx_bf16* wt_ug64, const mpx_bf16* wt_d, const mpx_bf16* residual,
+                            mpx_bf16* out, int M, int H, int F, const float* norm_scale, float eps, const mpx_bf16* wt_o,
+                            mpx_bf16* h_out, const PolicyHeadDev* head, bool* head_done, mpx_stream_t stream) {
   MPX_REQUIRE(x && wt_ug64 && wt_d && residual && out && M > 0, "mpx_glu_fused: bad arguments");
   MPX_REQUIRE(H == 128, "mpx_glu_fused: hidden_features=%d unsupported (128 only; use mpx_glu_up + mpx_linear)", H);
   MPX_REQUIRE(F > 0 && F % 64 == 0, "mpx_glu_fused: F=%d must be a positive multiple of 64", F);
@@ -593,10 +697,40 @@ extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const m
     cl = g_glu_fused_cluster;
   int gy = num_sms() / cl;
   if (gy > tiles) gy = tiles;
+  p.head_on = 0;
+  if (head && cl == 4 && p.proj && !p.h_out && head->A <= 8) {
+    p.head = *head;
+    p.head_on = 1;
+  }
+  if (head_done) *head_done = p.head_on != 0;
   cudaError_t le = launch_ex(glu_fused_kernel, dim3(cl, gy, 1), dim3(GF_THREADS), smem, (cudaStream_t)stream, cl, 8, p, tm_x, tm_wug, tm_wd, tm_wo, tm_h);
   if (le != cudaSuccess) {
     set_error("cudaLaunchKernelEx(glu_fused, cluster %d): %s", cl, cudaGetErrorString(le));
     return MPX_ERR_CUDA;
   }
   return check_launch("glu_fused_kernel");
+}
+
+extern "C" int mpx_glu_fused(const mpx_bf16* x, const mpx_bf16* wt_ug64, const mpx_bf16* wt_d, const mpx_bf16* residual,
+                             mpx_bf16* out, int M, int H, int F, const float* norm_scale, float eps, const mpx_bf16* wt_o,
+                             mpx_bf16* h_out, mpx_stream_t stream) {
+  return glu_fused_launch(x, wt_ug64, wt_d, residual, out, M, H, F, norm_scale, eps, wt_o, h_out, nullptr, nullptr, stream);
+}
+
+extern "C" int mpx_glu_fused_head(const mpx_bf16* x, const mpx_bf16* wt_ug64, const mpx_bf16* wt_d, const mpx_bf16* residual,
+                                  mpx_bf16* out, int M, int H, int F, const float* norm_scale, float eps, const mpx_bf16* wt_o,
+                                  const mpx_policy_head_args* h, mpx_stream_t stream) {
+  MPX_REQUIRE(h && h->norm_scale && h->table && h->action && h->log_prob && h->A > 0, "mpx_glu_fused_head: bad head arguments");
+  MPX_REQUIRE((reinterpret_cast<uintptr_t>(h->norm_scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(h->table) & 15) == 0,
+              "mpx_glu_fused_head: norm_scale and table must be 16-byte aligned");
+  PolicyHeadDev d;
+  d.norm_scale = h->norm_scale; d.eps = h->eps; d.table = h->table; d.mask = h->action_mask; d.gumbel_in = h->gumbel_in;
+  d.seed = h->seed; d.stream_id = h->stream_id; d.stream_off = h->stream_offset; d.logits_out = h->logits_out;
+  d.xf_out = reinterpret_cast<__nv_bfloat16*>(h->xf_out); d.action = h->action; d.log_prob = h->log_prob; d.A = h->A;
+  bool done = false;
+  const int rc = glu_fused_launch(x, wt_ug64, wt_d, residual, out, M, H, F, norm_scale, eps, wt_o, nullptr, &d, &done, stream);
+  if (rc || done) return rc;
+  // shapes the fused epilogue does not cover (other cluster sizes, A > 8): the same arithmetic as two launches
+  return mpx_policy_head_sample(out, h->norm_scale, h->eps, h->table, h->action_mask, h->gumbel_in, h->seed, h->stream_id,
+                                h->stream_offset, h->logits_out, h->xf_out, h->action, h->log_prob, M, H, h->A, stream);
 }

@@ -328,6 +328,38 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(MpxGluFused, GluFusedImpl,
                                   .Attr<float>("eps").Ret<BF>().Ret<BF>(),
                               MPX_TRAITS);
 
+// The last layer's feed-forward half with the policy head folded in (network.py:163-170 + 321-333, train.py:97-98): one
+// launch instead of MpxGluFused + MpxPolicyHeadSample, bit-identical results.  action_mask / gumbel / stream_offset /
+// logits / xf: 0 elements => absent.
+static ffi::Error GluFusedHeadImpl(mpx_stream_t stream, BF x, BF wt_ug64, BF wt_d, BF residual, F32 norm_scale, BF wt_o,
+                                   F32 head_norm_scale, F32 table, PRED action_mask, F32 gumbel, U64 stream_offset, float eps,
+                                   float head_eps, int64_t seed, int64_t stream_id, RBF out, RS32 action, RF32 log_prob,
+                                   RF32 logits, RBF xf) {
+  const int H = last_dim(x);
+  const int F = static_cast<int>(wt_ug64.dimensions()[0]) / 2;
+  mpx_policy_head_args a{};
+  a.norm_scale = head_norm_scale.typed_data(); a.eps = head_eps;
+  a.table = table.typed_data(); a.A = static_cast<int>(table.dimensions()[0]);
+  a.action_mask = action_mask.element_count() ? u8(action_mask) : nullptr;
+  a.gumbel_in = gumbel.element_count() ? gumbel.typed_data() : nullptr;
+  a.seed = static_cast<unsigned long long>(seed); a.stream_id = static_cast<unsigned long long>(stream_id);
+  a.stream_offset = stream_offset.element_count()
+                        ? reinterpret_cast<const unsigned long long*>(stream_offset.untyped_data()) : nullptr;
+  a.logits_out = logits->element_count() ? logits->typed_data() : nullptr;
+  a.xf_out = xf->element_count() ? rbf(xf) : nullptr;
+  a.action = action->typed_data();
+  a.log_prob = log_prob->typed_data();
+  MPX_CALL(mpx_glu_fused_head(bf(x), bf(wt_ug64), bf(wt_d), bf(residual), rbf(out), static_cast<int>(rows_of(x)), H, F,
+                              norm_scale.typed_data(), eps, bf(wt_o), &a, stream),
+           "mpx_glu_fused_head");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(MpxGluFusedHead, GluFusedHeadImpl,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<BF>().Arg<BF>().Arg<BF>().Arg<BF>().Arg<F32>().Arg<BF>()
+                                  .Arg<F32>().Arg<F32>().Arg<PRED>().Arg<F32>().Arg<U64>()
+                                  .Attr<float>("eps").Attr<float>("head_eps").Attr<int64_t>("seed").Attr<int64_t>("stream_id")
+                                  .Ret<BF>().Ret<S32>().Ret<F32>().Ret<F32>().Ret<BF>(),
+                              MPX_TRAITS);
+
 // Its backward in one kernel (u, g, dh recomputed on chip): dug (M,2F) = [du | dg], dxn (M,H)
 static ffi::Error GluBwdFusedImpl(mpx_stream_t stream, BF xn, BF dy, BF wt_ug64, BF wt_d, RBF dug, RBF dxn) {
   const int H = last_dim(xn);

@@ -451,6 +451,16 @@ class PolicyEngine:
                 other = hidden_out                            # the block's output goes straight to the caller's buffer
             if self.fused_glu and self.QD == 128:
                 # out projection + residual, ffn_norm, GLU and its residual in ONE kernel (x1 stays in shared memory)
+                if hidden_out is not None and sample is not None and i == self.L - 1:
+                    # ... and, on the last layer of a rollout step, the policy head on the finished rows (one launch less)
+                    ops.glu_fused_head(ws.ao, w[pre + "wt_ug64"], w[pre + "wt_d"], x, other, self.F,
+                                       p[pre + "ffn_norm.scale"], w[pre + "wt_o"], p["output_norm.scale"],
+                                       p["action_embedder.embedding_table"], sample["action"], sample["log_prob"],
+                                       seed=sample.get("seed", 0), stream_id=sample.get("stream_id", 0),
+                                       stream_offset=sample.get("stream_offset"), mask=action_mask,
+                                       gumbel_in=sample.get("gumbel_in"),
+                                       logits_out=ws.logits if sample.get("want_logits", True) else None)
+                    return ws.logits, None
                 ops.glu_fused(ws.ao, w[pre + "wt_ug64"], w[pre + "wt_d"], x, other, self.F,
                               norm_scale=p[pre + "ffn_norm.scale"], wt_o=w[pre + "wt_o"])
                 x, other = other, x

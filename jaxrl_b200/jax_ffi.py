@@ -43,7 +43,7 @@ for _n, _args in (("mpx_gae_workspace_bytes", [ctypes.c_int, ctypes.c_int]),
 TARGETS = (
     "MpxGae", "MpxAdvNormalize", "MpxHlGaussValue", "MpxHlGaussLoss", "MpxLinear", "MpxLinearWgrad", "MpxLinearF32w",
     "MpxQkvRopeDecode", "MpxQkvRopeTrain", "MpxRope", "MpxAttnDecode", "MpxAttnBlockDecode", "MpxAttnTrainFwd",
-    "MpxAttnTrainBwd", "MpxGluUp", "MpxGluFused", "MpxGluBwdFused", "MpxGluBwd", "MpxRmsNormFwd", "MpxRmsNormBwd",
+    "MpxAttnTrainBwd", "MpxGluUp", "MpxGluFused", "MpxGluFusedHead", "MpxGluBwdFused", "MpxGluBwd", "MpxRmsNormFwd", "MpxRmsNormBwd",
     "MpxGeluBwd", "MpxColSum", "MpxAddBf16", "MpxEmbedCombine", "MpxEmbedBwd", "MpxObsFusedPrep", "MpxObsEmbedFused",
     "MpxConv1OnehotFwd", "MpxConv1OnehotWgrad", "MpxObsOnehotIm2col", "MpxIm2col", "MpxCol2im", "MpxFlatEmbedFwd",
     "MpxFlatEmbedBwd", "MpxPolicyLogits", "MpxPolicySample", "MpxPolicyHeadSample", "MpxGumbelNoise", "MpxPpoPolicyLoss",
@@ -285,6 +285,19 @@ def ffn_half_decode(attn_out, x, norm_scale, wt_ug64, wt_d, wt_o, eps: float = 1
     out, _ = _call("MpxGluFused", (_sds(x.shape, BF16), _sds((0,), BF16)), attn_out, wt_ug64, wt_d, x, norm_scale, wt_o,
                    eps=np.float32(eps))
     return out
+
+
+def ffn_half_decode_with_policy_head(attn_out, x, norm_scale, wt_ug64, wt_d, wt_o, out_norm_scale, table, action_mask, gumbel,
+                                     eps: float = 1e-6):
+    """Last layer of a rollout step: ffn_half_decode + policy_head_sample in one launch (bit-identical results).
+    -> (block output, action, log_prob, logits)."""
+    B, A = x.shape[0], table.shape[0]
+    mask = jnp.zeros((0,), jnp.bool_) if action_mask is None else action_mask
+    out, action, log_prob, logits, _ = _call(
+        "MpxGluFusedHead", (_sds(x.shape, BF16), _sds((B,), I32), _sds((B,), F32), _sds((B, A), F32), _sds((0,), BF16)),
+        attn_out, wt_ug64, wt_d, x, norm_scale, wt_o, out_norm_scale, table, mask, gumbel, jnp.zeros((0,), jnp.uint64),
+        eps=np.float32(eps), head_eps=np.float32(eps), seed=np.int64(0), stream_id=np.int64(0))
+    return out, action, log_prob, logits
 
 
 # ------------------------------------------------------------------------------------------------ rollout heads

@@ -206,6 +206,23 @@ def glu_fused(x, wt_ug64, wt_d, residual, out, F: int, norm_scale=None, eps: flo
     return out
 
 
+def glu_fused_head(x, wt_ug64, wt_d, residual, out, F: int, norm_scale, wt_o, head_norm_scale, table, action, log_prob,
+                   seed: int = 0, stream_id: int = 0, stream_offset=None, mask=None, gumbel_in=None, logits_out=None,
+                   xf_out=None, eps: float = 1e-6, head_eps: float = 1e-6):
+    """The last layer's feed-forward half with the policy head folded in: glu_fused(..., wt_o=wt_o) followed by
+    policy_head_sample(out, ...) as ONE launch (bit-identical results; the library issues the two kernels itself for shapes
+    the fused epilogue does not cover)."""
+    _req(x, BF16, "x"); _req(wt_ug64, BF16, "wt_ug64"); _req(wt_d, BF16, "wt_d"); _req(residual, BF16, "residual")
+    _req(table, F32, "table"); _req(head_norm_scale, F32, "head_norm_scale")
+    H = x.shape[-1]
+    M = x.numel() // H
+    h = _lib.PolicyHeadArgs(ptr(head_norm_scale), head_eps, ptr(table), table.shape[0], ptr(_u8(mask)), ptr(gumbel_in), seed,
+                            stream_id, ptr(stream_offset), ptr(logits_out), ptr(xf_out), ptr(action), ptr(log_prob))
+    check(lib.mpx_glu_fused_head(ptr(x), ptr(wt_ug64), ptr(wt_d), ptr(residual), ptr(out), M, H, F, ptr(norm_scale), eps,
+                                 ptr(wt_o), C.byref(h), stream()), "mpx_glu_fused_head")
+    return out
+
+
 def glu_bwd_fused(xn, dy, wt_ug64, wt_d, F: int, dug=None, dxn=None):
     """Backward of the GLU block for a forward that kept only xn (and h): recomputes u, g, dh on chip; returns
     (dug, dxn) with dug = [du | dg] (M, 2F) - the operand of the up/gate weight gradients - and dxn (M, H).  H = 128."""

@@ -74,6 +74,16 @@ variants = {
     "glu_fused (norm inside)": lambda: ops.glu_fused(x, w[pre + "wt_ug64"], w[pre + "wt_d"], x, x2, eng.F,
                                                      norm_scale=p[pre + "ffn_norm.scale"]),
     "glu_fused (pre-normalised)": lambda: ops.glu_fused(ws.xn, w[pre + "wt_ug64"], w[pre + "wt_d"], x, x2, eng.F),
+    "glu_fused + out projection (the rollout's feed-forward half)": lambda: ops.glu_fused(
+        ws.ao, w[pre + "wt_ug64"], w[pre + "wt_d"], x, x2, eng.F, norm_scale=p[pre + "ffn_norm.scale"], wt_o=w[pre + "wt_o"]),
+    "glu_fused + out projection, then policy_head_sample (2 launches)": lambda: (
+        ops.glu_fused(ws.ao, w[pre + "wt_ug64"], w[pre + "wt_d"], x, x2, eng.F, norm_scale=p[pre + "ffn_norm.scale"],
+                      wt_o=w[pre + "wt_o"]),
+        ops.policy_head_sample(x2, p["action_embedder.embedding_table"], act, lp, seed=1, stream_id=2,
+                               norm_scale=p["output_norm.scale"])),
+    "glu_fused_head (feed-forward half + policy head, 1 launch)": lambda: ops.glu_fused_head(
+        ws.ao, w[pre + "wt_ug64"], w[pre + "wt_d"], x, x2, eng.F, p[pre + "ffn_norm.scale"], w[pre + "wt_o"],
+        p["output_norm.scale"], p["action_embedder.embedding_table"], act, lp, seed=1, stream_id=2),
     "heads (unfused: norm, logits, vmlp, vhead, value, gumbel, sample)": heads_unfused,
     "policy_head_sample (fused)": lambda: ops.policy_head_sample(x, p["action_embedder.embedding_table"], act, lp, seed=1,
                                                                  stream_id=2, norm_scale=p["output_norm.scale"]),

@@ -92,3 +92,15 @@ timeline("attn_bwd_tc (key tile 0)",
          lambda: ops.attn_train_bwd(qkv, qkv[:, QD:], qkv[:, QD + KD:], o, dout, lse, pos_t, eng.timescale, Bm, T, eng.Nq, eng.Nkv,
                                     eng.D, eng.QKV, eng.QKV, eng.QKV, dqkv, dqkv[:, QD:], dqkv[:, QD + KD:], eng.QKV, eng.QKV,
                                     eng.QKV), lab)
+act = torch.empty(B, dtype=torch.int32, device=dev)
+lp = torch.empty(B, dtype=torch.float32, device=dev)
+ao = torch.randn(B, eng.H, device=dev, generator=gen).to(torch.bfloat16)
+glu_labels = {0: "start", 1: "setup done (barriers, tmem, cluster sync)", 2: "x1 accumulator ready", 3: "x1 + norm done", 4: "ug0 ready",
+              5: "h0 written", 6: "ug1 ready", 7: "h1 written", 8: "ug2 ready", 9: "h2 written", 20: "D ready", 21: "partial pushed",
+              22: "all partials in", 23: "output stored (+ policy head)", 24: "exit sync", 25: "head: rows summed, block output stored",
+              26: "head: output norm done", 27: "head: logits reduced", 28: "head: noise + arg-max done"}
+timeline("glu_fused + out projection", lambda: ops.glu_fused(ao, w[pre + "wt_ug64"], w[pre + "wt_d"], x, x2, eng.F,
+                                                             norm_scale=p[pre + "ffn_norm.scale"], wt_o=w[pre + "wt_o"]), glu_labels)
+timeline("glu_fused_head", lambda: ops.glu_fused_head(ao, w[pre + "wt_ug64"], w[pre + "wt_d"], x, x2, eng.F, p[pre + "ffn_norm.scale"],
+                                                      w[pre + "wt_o"], p["output_norm.scale"], p["action_embedder.embedding_table"],
+                                                      act, lp, seed=1, stream_id=2), glu_labels)

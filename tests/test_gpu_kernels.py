@@ -796,6 +796,50 @@ def test_glu_fused_with_out_projection(ops, M, F, cluster):
                       max_err_frac=0.1)
 
 
+@pytest.mark.parametrize("M,F,A,masked,philox", [(4096, 768, 6, True, True), (77, 768, 8, False, False), (4000, 512, 3, True, False),
+                                                 (20000, 768, 6, True, True), (300, 192, 19, False, True), (1, 256, 2, True, True)])
+def test_glu_fused_head_matches_separate_kernels(ops, M, F, A, masked, philox):
+    """mpx_glu_fused_head (last feed-forward half + policy head in one launch; by-rows cluster reduction) is bit-identical to
+    mpx_glu_fused followed by mpx_policy_head_sample: block output, normalised rows, logits, sampled action, log-prob.
+    Covers the fused epilogue (cluster of 4, A <= 8) and the shapes where the library issues the two kernels itself
+    (M = 20000: no cluster of 4; A = 19)."""
+    gen = g(M + F + A)
+    H = 128
+    ao = torch.randn(M, H, generator=gen).to(BF16).to(DEV)
+    x = torch.randn(M, H, generator=gen).to(BF16).to(DEV)
+    wo = (torch.randn(H, H, generator=gen) / math.sqrt(H)).t().contiguous().to(BF16).to(DEV)
+    wu = torch.randn(H, F, generator=gen) / math.sqrt(H)
+    wg = torch.randn(H, F, generator=gen) / math.sqrt(H)
+    wug = ops.pack_glu_weight64(wu, wg).to(DEV)
+    wd = (torch.randn(F, H, generator=gen) / math.sqrt(F)).t().contiguous().to(BF16).to(DEV)
+    scale = (1.0 + 0.1 * torch.randn(H, generator=gen)).to(DEV)
+    oscale = (1.0 + 0.1 * torch.randn(H, generator=gen)).to(DEV)
+    table = (torch.randn(A, H, generator=gen) * 0.1).to(DEV)
+    mask = None
+    if masked:
+        mask = torch.rand(M, A, generator=gen) < 0.8
+        mask[:, 0] = True
+        mask = mask.to(DEV)
+    gum = None if philox else (-torch.log(-torch.log(torch.rand(M, A, generator=gen).clamp(1e-6, 1 - 1e-6)))).to(DEV)
+    off = torch.tensor([5], dtype=torch.int64, device=DEV) if philox else None
+
+    def outs():
+        return dict(out=torch.full((M + 2, H), 7.0, dtype=BF16, device=DEV), xf=torch.empty(M, H, dtype=BF16, device=DEV),
+                    logits=torch.empty(M, A, dtype=torch.float32, device=DEV), act=torch.full((M + 2,), -9, dtype=torch.int32, device=DEV),
+                    lp=torch.full((M + 2,), -9.0, dtype=torch.float32, device=DEV))
+    a, b = outs(), outs()
+    ops.glu_fused(ao, wug, wd, x, a["out"][:M], F, norm_scale=scale, wt_o=wo)
+    ops.policy_head_sample(a["out"][:M], table, a["act"][:M], a["lp"][:M], seed=99, stream_id=11, stream_offset=off, mask=mask,
+                           gumbel_in=gum, norm_scale=oscale, logits_out=a["logits"], xf_out=a["xf"])
+    ops.glu_fused_head(ao, wug, wd, x, b["out"][:M], F, scale, wo, oscale, table, b["act"][:M], b["lp"][:M], seed=99, stream_id=11,
+                       stream_offset=off, mask=mask, gumbel_in=gum, logits_out=b["logits"], xf_out=b["xf"])
+    torch.cuda.synchronize()
+    for k in a:
+        assert torch.equal(a[k], b[k]), f"glu_fused_head differs from the two-kernel path in {k} (M={M} F={F} A={A})"
+    assert (b["act"][M:] == -9).all() and (b["out"][M:] == 7.0).all()        # nothing written past row M
+    assert ((b["act"][:M] >= 0) & (b["act"][:M] < A)).all()
+
+
 @pytest.mark.parametrize("M,F", [(128, 128), (77, 256), (1000, 768), (20000, 768), (131072, 768), (300, 384)])
 def test_glu_bwd_fused(ops, M, F):
     """One-kernel GLU backward (u, g, dh recomputed in TMEM) vs the unfused kernel chain (glu_up(save) -> linear ->
