@@ -257,10 +257,33 @@ __global__ void __launch_bounds__(OT_THREADS, 1) obs_train_fwd_kernel(const ObsT
     const int erow = wtid >> 3, ecg = wtid & 7;
     uint32_t ph = 0;
     unsigned long long* dbg = (blockIdx.x == 0 && tid == 0) ? p.dbg : nullptr;
+    // reward projection of this thread's 16 columns (tile-invariant)
+    uint32_t wr_p[8], br_p[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 wv = reinterpret_cast<const float4*>(p.w_r + ecg * 16)[i], bq = reinterpret_cast<const float4*>(p.b_r + ecg * 16)[i];
+      wr_p[2 * i] = pack_bf16(wv.x, wv.y); wr_p[2 * i + 1] = pack_bf16(wv.z, wv.w);
+      br_p[2 * i] = pack_bf16(bq.x, bq.y); br_p[2 * i + 1] = pack_bf16(bq.z, bq.w);
+    }
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long m0 = (long long)tile * OT_TOK;
       const int nag = (int)min((long long)OT_TOK, p.M - m0);
       dbg_stamp(dbg, 0);
+      // reward / last action / task id of this thread's 4 embedding rows: fetched now, used after conv2 - two dependent
+      // L2 round trips per row (index, then table row) used to sit in front of the conv3 epilogue
+      float rw_r[4];
+      int ea_r[4], et_r[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int er = erow + 32 * r;
+        rw_r[r] = 0.f; ea_r[r] = -1; et_r[r] = -1;
+        if (er < nag) {
+          const long long m = m0 + er;
+          rw_r[r] = p.reward[m];
+          ea_r[r] = p.last_action[m];
+          if (has_task) et_r[r] = p.task_ids[m];
+        }
+      }
       {
         const int ncell = nag * OF_IH * OF_IW;
         const uint8_t* src = p.obs + m0 * cell_bytes;
@@ -373,47 +396,66 @@ __global__ void __launch_bounds__(OT_THREADS, 1) obs_train_fwd_kernel(const ObsT
           if (r < nag) *reinterpret_cast<uint4*>(p.a2 + (m0 + r) * OF_K3 + (pb * 4 + pc) * 8) = v;
         }
       }
-      // ---- embedding addends of this thread's 4 (row, 16 columns) items (network.py:304-309)
-      uint32_t ae_w[4][8], te_w[4][8], wr_p[8], br_p[8];
-      float rw_r[4];
+      // ---- embedding addends of this thread's 4 (row, 16 columns) items (network.py:304-309): the table rows of all four
+      //      rows are requested before the first one is packed (one round trip, not four)
+      uint32_t ae_w[4][8], te_w[4][8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 wv = reinterpret_cast<const float4*>(p.w_r + ecg * 16)[i], bq = reinterpret_cast<const float4*>(p.b_r + ecg * 16)[i];
-        wr_p[2 * i] = pack_bf16(wv.x, wv.y); wr_p[2 * i + 1] = pack_bf16(wv.z, wv.w);
-        br_p[2 * i] = pack_bf16(bq.x, bq.y); br_p[2 * i + 1] = pack_bf16(bq.z, bq.w);
-      }
+      for (int r0 = 0; r0 < 4; r0 += 2) {                      // two rows per batch: 8 table loads in flight
+        float4 av[2][4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int er = erow + 32 * r;
-        float rw = 0.f;
-        int a = -1, tk = -1;
-        if (er < nag) {
-          const long long m = m0 + er;
-          rw = bf16_round(p.reward[m]);
-          a = p.last_action[m];
-          if (a < 0) a += p.A;
-          if (a >= p.A) a = -1;
-          if (has_task) {
-            tk = p.task_ids[m];
-            if (tk < 0) tk += p.n_tasks;
-            if (tk >= p.n_tasks) tk = -1;
+        for (int u = 0; u < 2; ++u) {
+          int a = ea_r[r0 + u];
+          if (erow + 32 * (r0 + u) >= nag) a = -1;
+          else {
+            if (a < 0) a += p.A;
+            if (a >= p.A) a = -1;
           }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            av[u][i] = a >= 0 ? reinterpret_cast<const float4*>(p.a_table + (long long)a * OF_H + ecg * 16)[i]
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float4 av = make_float4(0.f, 0.f, 0.f, 0.f), tv = av;
-          if (a >= 0) av = reinterpret_cast<const float4*>(p.a_table + (long long)a * OF_H + ecg * 16)[i];
-          if (tk >= 0) tv = reinterpret_cast<const float4*>(p.t_table + (long long)tk * OF_H + ecg * 16)[i];
-          const float avv[4] = {av.x, av.y, av.z, av.w}, tvv[4] = {tv.x, tv.y, tv.z, tv.w};
+        for (int u = 0; u < 2; ++u)
 #pragma unroll
-          for (int e = 0; e < 4; e += 2) {
-            const int h = (4 * i + e) >> 1;
-            ae_w[r][h] = pack_bf16(bf16_round(avv[e]) * sqH, bf16_round(avv[e + 1]) * sqH);
-            te_w[r][h] = pack_bf16(bf16_round(tvv[e]) * sqH, bf16_round(tvv[e + 1]) * sqH);
+          for (int i = 0; i < 4; ++i) {
+            ae_w[r0 + u][2 * i] = pack_bf16(bf16_round(av[u][i].x) * sqH, bf16_round(av[u][i].y) * sqH);
+            ae_w[r0 + u][2 * i + 1] = pack_bf16(bf16_round(av[u][i].z) * sqH, bf16_round(av[u][i].w) * sqH);
           }
-        }
-        rw_r[r] = rw;
       }
+      if (has_task) {
+#pragma unroll
+        for (int r0 = 0; r0 < 4; r0 += 2) {
+          float4 tv[2][4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            int tk = et_r[r0 + u];
+            if (erow + 32 * (r0 + u) >= nag) tk = -1;
+            else {
+              if (tk < 0) tk += p.n_tasks;
+              if (tk >= p.n_tasks) tk = -1;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              tv[u][i] = tk >= 0 ? reinterpret_cast<const float4*>(p.t_table + (long long)tk * OF_H + ecg * 16)[i]
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              te_w[r0 + u][2 * i] = pack_bf16(bf16_round(tv[u][i].x) * sqH, bf16_round(tv[u][i].y) * sqH);
+              te_w[r0 + u][2 * i + 1] = pack_bf16(bf16_round(tv[u][i].z) * sqH, bf16_round(tv[u][i].w) * sqH);
+            }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int h = 0; h < 8; ++h) te_w[r][h] = 0u;
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) rw_r[r] = bf16_round(rw_r[r]);
       // ---- conv3 accumulator -> fp32 staging (aliases a1 / a2, both dead once c3_full fires and the copy-out is done)
       dbg_stamp(dbg, 5);
       mbar_wait(c3_full, ph);
