@@ -44,8 +44,6 @@ struct GluFusedParams {
   __nv_bfloat16* out;
   const float* norm_scale;        // (128) fp32: RMSNorm applied to the x tile in shared memory before MMA1; or null
   float eps;
-  int proj;                       // 1: x is the attention output; x1 = residual + x @ Wo^T is formed first
-  int h_out;                      // 1: the h chunks are also stored to global memory (tm_h) for the weight gradients
   int head_on;                    // 1: cluster of 4 with the projection prologue; the partials are reduced BY ROWS and the owner
   PolicyHeadDev head;             //    of a row finishes it and runs the policy head on it (last layer of a rollout step)
   unsigned long long* dbg;
@@ -55,6 +53,12 @@ __device__ __forceinline__ void gf_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// One instantiation per mode - PROJ: out-projection prologue; CLUSTER: F split over a cluster of 2 or 4 CTAs; HOUT: h kept
+// for the weight gradients (training); HEAD: policy-head epilogue (last layer of a rollout step).  The single runtime-mode
+// kernel was 87 KB of SASS: a latency-bound launch pays for every instruction line it has to fetch (the rollout alternates
+// five kernels, so little of it stays in the instruction caches) - measured 1.3 us per launch between the kernel with and
+// without the head code compiled in.
+template <bool PROJ, bool CLUSTER, bool HOUT, bool HEAD>
 __global__ void __launch_bounds__(GF_THREADS, 1)
 glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_x,
                  const __grid_constant__ CUtensorMap tm_wug, const __grid_constant__ CUtensorMap tm_wd,
@@ -90,8 +94,9 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
   // shfl from a constant lane makes the warp index provably warp-uniform for the compiler: the role branches below and
   // everything computed inside them can live on the uniform datapath (UTCHMMA takes uniform-register descriptors)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int ncta = (int)cluster_nctarank(), krank = (int)cluster_ctarank();
-  const int nstages = (ncta == 1 && !p.proj) ? GF_MAX_STAGES : GF_STAGES;
+  const int ncta = CLUSTER ? (int)cluster_nctarank() : 1, krank = CLUSTER ? (int)cluster_ctarank() : 0;
+  if (CLUSTER) __builtin_assume(ncta > 1);
+  const int nstages = (ncta == 1 && !PROJ) ? GF_MAX_STAGES : GF_STAGES;
   const int nchunks = p.F / 64 / ncta;        // chunks of the hidden dimension owned by this CTA
   const int chunk0 = krank * nchunks;
   const int m_tiles = (p.M + 127) / 128;
@@ -103,7 +108,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_wug);
     tma_prefetch_desc(&tm_wd);
-    if (p.proj) tma_prefetch_desc(&tm_wo);
+    if (PROJ) tma_prefetch_desc(&tm_wo);
     for (int s = 0; s < GF_MAX_STAGES; ++s) {
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
@@ -160,7 +165,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         tma_load_2d(&tm_x, x_full, sX + 16384, 64, tile * 128);
         xphase ^= 1;
         // weight order == MMA issue order: [Wo K blocks], UG_0, then for each c: UG_{c+1} (if any), D_c
-        if (p.proj) {
+        if (PROJ) {
           load_w(&tm_wo, 0, 0);
           load_w(&tm_wo, 64, 0);
         }
@@ -181,7 +186,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
     // lane issues each tcgen05.mma / commit.  Weight tiles are consumed in the producer's order: per tile
     // [Wo a, Wo b], UG_0 a, b, then for each c: UG_{c+1} a, b (if any), D_c - both warps derive ring positions from that.
     constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
-    const int P = p.proj ? 2 : 0;
+    const int P = PROJ ? 2 : 0;
     const int per_tile = P + 3 * nchunks;
     auto w_wait = [&](int n) -> uint32_t {    // wait for weight tile number n (running count) and return its address
       const int st = n % nstages;
@@ -194,7 +199,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
       unsigned long long* mdbg = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) ? p.dbg : nullptr;   // slots 32..63
       int base = 0;
       for (int tile = blockIdx.y; tile < m_tiles; tile += gridDim.y, base += per_tile) {
-        if (p.proj) {
+        if (PROJ) {
           // x1 accumulator = ao . Wo^T in the tD columns (free: the previous tile's output has been drained)
           mbar_wait(x_full, xphase);
           mbar_wait(d_empty, dphase ^ 1);
@@ -269,7 +274,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     uint32_t ug_ph[2] = {0, 0}, h_ph[2] = {0, 0}, dphase = 0, pf_phase = 0, pe_phase = 0, xphase = 0;
     unsigned long long head_sid = 0;
-    if (p.head_on) head_sid = p.head.stream_id + (p.head.stream_off ? p.head.stream_off[0] : 0ull);
+    if constexpr (HEAD) head_sid = p.head.stream_id + (p.head.stream_off ? p.head.stream_off[0] : 0ull);
     // output columns this thread finishes: single CTA -> its half of the row; cluster -> its half of the CTA's slice
     const int slice = 128 / ncta;                            // 128, 64 or 32 columns per CTA
     const int ocol0 = krank * slice + half * (slice / 2);
@@ -278,7 +283,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
       const long long row = (long long)tile * 128 + r;
       if (ncta > 1 && warp == 2 && lane == 0) mbar_arrive_expect_tx(part_full, GF_PART_BYTES);   // 128 rows x slice x 4 B x CL
       // ---- optional RMSNorm of the x tile, in place in the swizzled layout (this warp: K block `half` of its rows)
-      if (p.proj) {
+      if (PROJ) {
         // ---- x1 = bf16(bf16(ao @ Wo) + x): kept in smem for the final residual; RMSNorm(x1) becomes the MMA1 operand
         if (tile != (int)blockIdx.y) gf_bar_sync(1, GF_EPI_WARPS * 32);   // every reader of the previous tile's x1 rows is done
         uint4 rx[8];
@@ -395,7 +400,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         act16(uA, gA, hw);
         mbar_wait(&h_empty[b], h_ph[b] ^ 1);                   // MMA2 of chunk c-2 no longer reads this buffer
         h_ph[b] ^= 1;
-        if (p.h_out) {                                         // ... and neither does its bulk store
+        if (HOUT) {                                         // ... and neither does its bulk store
           if (half == 0 && lane == 0) bulk_wait_group_read1();
           gf_bar_sync(2 + quarter, 64);
         }
@@ -421,7 +426,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         __syncwarp();
         if (c < 8) dbg_stamp(dbg, 5 + 2 * c);
         if (lane == 0) mbar_arrive(&h_full[b]);
-        if (p.h_out) {                                         // rows [32 quarter, +32) of h_c leave from the operand tile
+        if (HOUT) {                                         // rows [32 quarter, +32) of h_c leave from the operand tile
           gf_bar_sync(2 + quarter, 64);
           if (half == 0 && lane == 0) {
             tma_store_2d(&tm_h, sH + b * 16384 + quarter * 4096, (chunk0 + c) * 64, tile * 128 + quarter * 32);
@@ -434,7 +439,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         }
       }
       uint4 rpre[8];                                           // single CTA: this thread's 64 residual columns, in flight
-      if (ncta == 1 && !p.proj && row < p.M) {                 // while the last chunks drain
+      if (ncta == 1 && !PROJ && row < p.M) {                 // while the last chunks drain
 #pragma unroll
         for (int i = 0; i < 8; ++i) rpre[i] = *reinterpret_cast<const uint4*>(p.residual + row * 128 + 64 * half + 8 * i);
       }
@@ -453,7 +458,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
             uint4* o4 = reinterpret_cast<uint4*>(p.out + row * 128 + 64 * half + 32 * cc);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const uint4 rv = p.proj ? lds_v4(smem_u32(sX1 + r * 256) + (((8 * half + 4 * cc + i) ^ (r & 7)) << 4)) : rpre[4 * cc + i];
+              const uint4 rv = PROJ ? lds_v4(smem_u32(sX1 + r * 256) + (((8 * half + 4 * cc + i) ^ (r & 7)) << 4)) : rpre[4 * cc + i];
               const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
               uint32_t ow[4];
 #pragma unroll
@@ -469,7 +474,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(d_empty);
-      } else if (p.head_on) {
+      } else if constexpr (HEAD) {
         // 1'. PUSH my fp32 partial BY ROWS: CTA j finishes rows [32 j, 32 j + 32) and receives them from every CTA of the
         //     cluster into recv[src][row][32 float4 columns] (st.async completes the owner's transaction barrier)
         const bool last_tile = tile + (int)gridDim.y >= m_tiles;
@@ -572,7 +577,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         const int per_owner = slice / 4;                       // float4 column groups per owner: 8 (CL 4) or 16 (CL 2)
         // residual of my output slice: in flight while the partials are exchanged
         uint4 rres[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (ncta == 4 && row < p.M && !p.proj) {
+        if (ncta == 4 && row < p.M && !PROJ) {
           rres[0] = *reinterpret_cast<const uint4*>(p.residual + row * 128 + ocol0);
           rres[1] = *reinterpret_cast<const uint4*>(p.residual + row * 128 + ocol0 + 8);
         }
@@ -615,7 +620,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
           }
           if (row < p.M) {
             const long long o = row * 128 + ocol0 + 4 * i;
-            const uint4 rv = p.proj ? lds_v4(smem_u32(sX1 + r * 256) + ((((ocol0 + 4 * i) >> 3) ^ (r & 7)) << 4))
+            const uint4 rv = PROJ ? lds_v4(smem_u32(sX1 + r * 256) + ((((ocol0 + 4 * i) >> 3) ^ (r & 7)) << 4))
                                     : (ncta == 4) ? rres[(i >> 1) & 1] : *reinterpret_cast<const uint4*>(p.residual + o);
             uint4 ov;
             ov.x = pack_bf16(bf16_round(s0.x) + bf16_lo(rv.x), bf16_round(s0.y) + bf16_hi(rv.x));
@@ -633,7 +638,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         }
       }
     }
-    if (p.h_out && half == 0 && lane == 0) bulk_wait_group0();   // shared memory must outlive the stores reading it
+    if (HOUT && half == 0 && lane == 0) bulk_wait_group0();   // shared memory must outlive the stores reading it
     // Exit protocol: a CTA leaves only after ITS receive barrier completed (all pushes into its shared memory have
     // landed) and nobody signals part_empty after the last tile, so no peer touches an exited CTA.
   }
@@ -668,23 +673,12 @@ static int glu_fused_launch(const mpx_bf16* x, const mpx_bf16* wt_ug64, const mp
   rc = h_out ? make_tmap_bf16_2d(&tm_h, h_out, M, F, F, 64, 32) : make_tmap_bf16_2d(&tm_h, wt_d, H, F, F, 64, 32);
   if (rc) return rc;
   const int smem = 1024 + 65536 + GF_STAGES * GF_STAGE_BYTES + GF_PART_BYTES + 32768 + 384 + 1024 + 512;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(glu_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(glu_fused): %s", cudaGetErrorString(e));
-      return MPX_ERR_CUDA;
-    }
-    attr_set = true;
-  }
   GluFusedParams p;
   p.M = M; p.F = F;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.norm_scale = norm_scale;
   p.eps = eps;
-  p.proj = wt_o ? 1 : 0;
-  p.h_out = h_out ? 1 : 0;
   p.dbg = g_dbg_stamps;
   MPX_REQUIRE(!norm_scale || (reinterpret_cast<uintptr_t>(norm_scale) & 15) == 0, "mpx_glu_fused: norm_scale must be 16-byte aligned");
   const int tiles = ceil_div(M, 128);
@@ -698,12 +692,30 @@ static int glu_fused_launch(const mpx_bf16* x, const mpx_bf16* wt_ug64, const mp
   int gy = num_sms() / cl;
   if (gy > tiles) gy = tiles;
   p.head_on = 0;
-  if (head && cl == 4 && p.proj && !p.h_out && head->A <= 8) {
+  if (head && cl == 4 && wt_o && !h_out && head->A <= 8) {
     p.head = *head;
     p.head_on = 1;
   }
   if (head_done) *head_done = p.head_on != 0;
-  cudaError_t le = launch_ex(glu_fused_kernel, dim3(cl, gy, 1), dim3(GF_THREADS), smem, (cudaStream_t)stream, cl, 8, p, tm_x, tm_wug, tm_wd, tm_wo, tm_h);
+  using Kern = void (*)(GluFusedParams, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap);
+  static const Kern kerns[9] = {
+      glu_fused_kernel<false, false, false, false>, glu_fused_kernel<true, false, false, false>,
+      glu_fused_kernel<false, true, false, false>,  glu_fused_kernel<true, true, false, false>,
+      glu_fused_kernel<false, false, true, false>,  glu_fused_kernel<true, false, true, false>,
+      glu_fused_kernel<false, true, true, false>,   glu_fused_kernel<true, true, true, false>,
+      glu_fused_kernel<true, true, false, true>};
+  const int ki = p.head_on ? 8 : (wt_o ? 1 : 0) + (cl > 1 ? 2 : 0) + (h_out ? 4 : 0);
+  static bool attr_set[9] = {};
+  if (!attr_set[ki]) {
+    cudaError_t e = cudaFuncSetAttribute(kerns[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(glu_fused): %s", cudaGetErrorString(e));
+      return MPX_ERR_CUDA;
+    }
+    attr_set[ki] = true;
+  }
+  cudaError_t le = launch_ex(kerns[ki], dim3(cl, gy, 1), dim3(GF_THREADS), smem, (cudaStream_t)stream, cl, 8, p, tm_x, tm_wug, tm_wd,
+                             tm_wo, tm_h);
   if (le != cudaSuccess) {
     set_error("cudaLaunchKernelEx(glu_fused, cluster %d): %s", cl, cudaGetErrorString(le));
     return MPX_ERR_CUDA;
