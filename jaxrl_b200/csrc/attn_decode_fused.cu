@@ -143,8 +143,8 @@ __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedP
       for (int rs = 0; rs < 2; ++rs) {
         const int ab = b0 + g + 8 * rs;
         const float pf = (float)p.pos[ab < p.B ? ab : 0];
-        sincosf(pf / ts0, &rsn[rs][0], &rcs[rs][0]);
-        sincosf(pf / ts1, &rsn[rs][1], &rcs[rs][1]);
+        rope_sincos(pf / ts0, &rsn[rs][0], &rcs[rs][0]);
+        rope_sincos(pf / ts1, &rsn[rs][1], &rcs[rs][1]);
       }
     }
   };

@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(
       for (int e = 0; e < 2; ++e) {
         const int i = nt * 8 + 2 * t + e;   // rotation index 0..15
         float sn, cs;
-        sincosf(pf / timescale[i], &sn, &cs);
+        rope_sincos(pf / timescale[i], &sn, &cs);
         const float a = dkacc[nt][half * 2 + e], bb = dkacc[nt + 2][half * 2 + e];
         o_lo[e] = a * cs + bb * sn;
         o_hi[e] = bb * cs - a * sn;
@@ -380,8 +380,8 @@ __global__ void attn_bwd_dq_kernel(const float* __restrict__ dq_acc, __nv_bfloat
     const long long tok = i >> 3;
     const float pf = (float)pos[tok % pos_len];
     float s0, c0, s1, c1;
-    sincosf(pf / timescale[sub * 2], &s0, &c0);
-    sincosf(pf / timescale[sub * 2 + 1], &s1, &c1);
+    rope_sincos(pf / timescale[sub * 2], &s0, &c0);
+    rope_sincos(pf / timescale[sub * 2 + 1], &s1, &c1);
     const float* src = dq_acc + tok * (long long)(Nq * 32) + sub * 2;
     __nv_bfloat16* d = dq + tok * lddq + sub * 2;
     for (int head = 0; head < Nq; ++head, src += 32, d += 32) {

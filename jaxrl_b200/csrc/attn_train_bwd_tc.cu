@@ -295,7 +295,7 @@ attn_bwd_tc2_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap
         for (int u = 0; u < 2; ++u) {
           const int d = 2 * e + u;
           float sn, cs;
-          sincosf(pf / p.timescale[d], &sn, &cs);
+          rope_sincos(pf / p.timescale[d], &sn, &cs);
           const float a = __uint_as_float(dkv[d]), bb = __uint_as_float(dkv[d + 16]);
           o_lo[u] = a * cs + bb * sn;
           o_hi[u] = bb * cs - a * sn;

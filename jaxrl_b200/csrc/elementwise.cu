@@ -270,7 +270,7 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ x, long long ld, const i
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       float sn, cs;
-      sincosf(pf / timescale[sub * 2 + k], &sn, &cs);
+      rope_sincos(pf / timescale[sub * 2 + k], &sn, &cs);
       if (inverse) sn = -sn;
       oa[k] = a[k] * cs - b[k] * sn;
       ob[k] = b[k] * cs + a[k] * sn;

@@ -539,7 +539,7 @@ gemm_tn_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
         if (row < p.M) {
           const float pf = (float)p.pos[row % p.pos_len];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) sincosf(pf / p.timescale[i], &sn[i], &cs[i]);
+          for (int i = 0; i < 16; ++i) rope_sincos(pf / p.timescale[i], &sn[i], &cs[i]);
         }
       }
       // residual rows of this tile are fetched BEFORE waiting for the accumulator (hides the global-load latency)
