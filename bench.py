@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--ncu-decode-step", action="store_true", help="profiling run: one decode step (t=300) between profiler start/stop")
     ap.add_argument("--ncu-minibatch", action="store_true",
                     help="profiling run: eager warm pass, then ONE training minibatch (fwd+bwd+optimizer) between NVTX-free markers")
+    ap.add_argument("--pdl", type=int, default=None,
+                    help="experiment: programmatic-dependent-launch family mask (mpx_debug_set(6, mask); library default 12)")
     return ap.parse_args()
 
 
@@ -303,6 +305,9 @@ def main():
     from jaxrl_b200.config import NAMED
     from jaxrl_b200.trainer import PPOTrainer
 
+    if args.pdl is not None:
+        from jaxrl_b200 import _lib
+        _lib.lib.mpx_debug_set(6, args.pdl)
     run = NAMED[args.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -7,12 +7,14 @@
 // projection of the CTA's agents runs underneath it - one m16 x n192 x k128 mma.sync GEMM per round, the weight
 // fragments held in registers for the whole kernel.  The new k,v go to the ring in global memory (for later steps)
 // AND are patched into the shared-memory stage of the chunk that holds slot pos % S, so this step attends to them
-// without a round trip.  Shapes: hidden 128, 4 query heads on 1 kv head, head_dim 32 (the rollout configs of
-// return_*_layers); everything else takes mpx_qkv_rope + mpx_attn_decode.
+// without a round trip.  Shapes: hidden 128 (return_*_layers, blog_32_layers) or 256 (multitask), 4 query heads on 1 kv
+// head, head_dim 32; everything else takes mpx_qkv_rope + mpx_attn_decode.  At hidden 256 the weight fragments (64
+// registers per lane) are re-read from L2 at the top of every round (a launch has two rounds at 4096 agents) and are dead
+// before the cache loop begins, so the CTA keeps its 14 warps.
 //
 // One warp per agent, W (12..14) agents per CTA per round.  Shared memory = W rings of 4 stages x 4 KB (K chunk |
-// V chunk of 32 positions).  Stage 3 of the first three rings doubles as the projection scratch (normalised x rows,
-// q rows, new k|v rows) while only stages 0-2 are in flight.
+// V chunk of 32 positions).  Stage 3 of the first rings doubles as the projection scratch (normalised x rows - 4 KB at
+// hidden 128, 8 KB over two rings at hidden 256 -, q rows, new k|v rows) while only stages 0-2 are in flight.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -59,10 +61,10 @@ __device__ __forceinline__ void af_sts64(uint32_t addr, uint32_t v0, uint32_t v1
 }
 
 struct AttnFusedParams {
-  const __nv_bfloat16* x;          // (B,128) block input (residual stream)
-  const float* norm_scale;         // (128) history_norm
+  const __nv_bfloat16* x;          // (B,H) block input (residual stream), H = 16 HK
+  const float* norm_scale;         // (H) history_norm
   float eps;
-  const __nv_bfloat16* wt_qkv;     // (192,128): rows = [4 q heads x 32 | k 32 | v 32] output features
+  const __nv_bfloat16* wt_qkv;     // (192,H): rows = [4 q heads x 32 | k 32 | v 32] output features
   const int32_t* pos;              // (B)
   const float* timescale;          // (16)
   __nv_bfloat16* kcache;           // (B,S,1,32)
@@ -93,34 +95,52 @@ __device__ __forceinline__ void af_issue_chunk(uint32_t ring, const __nv_bfloat1
   af_commit();
 }
 
+// HK = hidden / 16 (k-steps of the projection): 8 or 16
+template <int HK>
 __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int H = 16 * HK;
+  constexpr int XROW = 2 * H;                   // bytes of a normalised x row
+  constexpr int XRINGS = HK / 8;                // rings whose stage 3 holds x rows (8 rows of 512 B or 16 rows of 256 B each)
+  constexpr int XROWS_PER_RING = AF_STAGE_BYTES / XROW;
   const int warps = blockDim.x >> 5;            // 12..14
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = smem_u32(smem_raw);
   const uint32_t ring = smem0 + warp * AF_RING;
-  const uint32_t xs = smem0 + 0 * AF_RING + 3 * AF_STAGE_BYTES;    // 16 rows x 256 B (normalised x, words XOR 4*(row&7))
-  const uint32_t qs = smem0 + 1 * AF_RING + 3 * AF_STAGE_BYTES;    // W rows x 256 B (q, 4 heads x 32)
-  const uint32_t kvs = smem0 + 2 * AF_RING + 3 * AF_STAGE_BYTES;   // W rows x 128 B (new k | new v)
+  // normalised x: 16 rows x XROW bytes, 16-byte chunk c of row r at chunk position c ^ xs_swz(r): the 8 lanes of a
+  // quarter warp (rows 2q, 2q+1; 4 chunks each) of the A-fragment loads hit 8 different bank groups
+  auto xs_swz = [](int r) { return ((r & 1) << 2) | ((r >> 1) & 3); };
+  auto xs_row = [&](int r) { return smem0 + (r / XROWS_PER_RING) * AF_RING + 3 * AF_STAGE_BYTES + (r % XROWS_PER_RING) * XROW; };
+  const uint32_t qs = smem0 + XRINGS * AF_RING + 3 * AF_STAGE_BYTES;          // W rows x 256 B (q, 4 heads x 32)
+  const uint32_t kvs = smem0 + (XRINGS + 1) * AF_RING + 3 * AF_STAGE_BYTES;   // W rows x 128 B (new k | new v)
   const int g = lane >> 2, t = lane & 3, mi = lane >> 3, r8 = lane & 7;
   constexpr int G = 4;
 
   // ---- projection weights: warp w < 12 owns output columns [n0, n0+8) and [n0+16, n0+24) of head-slot w/2 (the two
   //      halves of a RoPE pair live in the same lane).  B fragments stay in registers for the whole kernel.
   const int he = warp >> 1, jp = warp & 1;      // head slot: 0-3 q heads, 4 k, 5 v
-  uint32_t bw[2][8][2];
-  if (warp < 12) {
+  // B fragments as 16-byte loads: lane (g,t) holds W[n][32 kb + 8t .. +7] per 32-wide k block kb - words 0,1 are the
+  // fragment of the block's first m16n8k16 step, words 2,3 of its second.  That is a permutation of k inside the block
+  // (logical k 2t+i -> 8t+i, 2t+8+i -> 8t+2+i; second step +4); the A fragments below read x under the same permutation
+  // (one 16-byte shared load per row and block), and a contraction does not care.
+  uint4 bw[2][HK / 2];
+  auto load_w = [&]() {
+    if (warp < 12) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const __nv_bfloat16* wrow = p.wt_qkv + (size_t)(he * 32 + 8 * jp + 16 * j + g) * 128 + 2 * t;
+      for (int j = 0; j < 2; ++j) {
+        const __nv_bfloat16* wrow = p.wt_qkv + (size_t)(he * 32 + 8 * jp + 16 * j + g) * H + 8 * t;
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        bw[j][ks][0] = *reinterpret_cast<const uint32_t*>(wrow + 16 * ks);
-        bw[j][ks][1] = *reinterpret_cast<const uint32_t*>(wrow + 16 * ks + 8);
+        for (int kb = 0; kb < HK / 2; ++kb) bw[j][kb] = __ldg(reinterpret_cast<const uint4*>(wrow + 32 * kb));
       }
     }
+  };
+  load_w();                                      // weights are parameters: never produced by the preceding kernel
+  float nscale[HK / 2];                          // this lane's HK/2 consecutive features
+#pragma unroll
+  for (int i = 0; i < HK / 8; ++i) {
+    const float4 v4 = *reinterpret_cast<const float4*>(p.norm_scale + (HK / 2) * lane + 4 * i);
+    nscale[4 * i] = v4.x; nscale[4 * i + 1] = v4.y; nscale[4 * i + 2] = v4.z; nscale[4 * i + 3] = v4.w;
   }
-  const float4 nscale = *reinterpret_cast<const float4*>(p.norm_scale + 4 * lane);
   float ts0 = 0.f, ts1 = 0.f;
   if (warp < 10) {                               // q and k columns: rotation frequencies 8 jp + 2t, +1
     ts0 = p.timescale[8 * jp + 2 * t];
@@ -130,11 +150,22 @@ __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedP
   griddep_launch();
   const int per_round = gridDim.x * warps;
   const int nrounds = (p.B + per_round - 1) / per_round;
-  uint2 xv = make_uint2(0u, 0u);
+  uint32_t xv[HK / 4];                           // HK/2 bf16 of this warp's row
+#pragma unroll
+  for (int i = 0; i < HK / 4; ++i) xv[i] = 0u;
   float rsn[2][2], rcs[2][2];
   auto fetch_x = [&](int round) {
     const int b0 = round * per_round + blockIdx.x * warps;
-    if (round < nrounds && b0 + warp < p.B) xv = *reinterpret_cast<const uint2*>(p.x + (size_t)(b0 + warp) * 128 + 4 * lane);
+    if (round < nrounds && b0 + warp < p.B) {
+      const __nv_bfloat16* xp = p.x + (size_t)(b0 + warp) * H + (HK / 2) * lane;
+      if constexpr (HK == 8) {
+        const uint2 v = *reinterpret_cast<const uint2*>(xp);
+        xv[0] = v.x; xv[1] = v.y;
+      } else {
+        const uint4 v = *reinterpret_cast<const uint4*>(xp);
+        xv[0] = v.x; xv[1] = v.y; xv[2] = v.z; xv[3] = v.w;
+      }
+    }
   };
   auto fetch_angles = [&](int round) {
     const int b0 = round * per_round + blockIdx.x * warps;
@@ -186,19 +217,28 @@ __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedP
 #pragma unroll
       for (int i = 0; i < AF_STAGES - 1; ++i) issue(i);
     }
-    // every warp has left the previous round's loop: stage 3 of rings 0-2 is free for the scratch rows
+    // every warp has left the previous round's loop: stage 3 of the first rings is free for the scratch rows
     if (round > 0) __syncthreads();
     // ---- 2. RMSNorm of this agent's row -> xs[warp] (the row and the rotation angles were fetched a round ahead)
     {
-      uint32_t y0 = 0u, y1 = 0u;
+      uint32_t y[HK / 4];
+#pragma unroll
+      for (int i = 0; i < HK / 4; ++i) y[i] = 0u;
       if (active) {
-        const float x0 = bf16_lo(xv.x), x1 = bf16_hi(xv.x), x2 = bf16_lo(xv.y), x3 = bf16_hi(xv.y);
-        const float ss = warp_sum(x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3);
-        const float inv = rsqrtf(ss * (1.0f / 128.0f) + p.eps);
-        y0 = pack_bf16(x0 * (inv * nscale.x), x1 * (inv * nscale.y));
-        y1 = pack_bf16(x2 * (inv * nscale.z), x3 * (inv * nscale.w));
+        float ssl = 0.f;
+#pragma unroll
+        for (int i = 0; i < HK / 4; ++i) {
+          const float a = bf16_lo(xv[i]), b = bf16_hi(xv[i]);
+          ssl += a * a + b * b;
+        }
+        const float ss = warp_sum(ssl);
+        const float inv = rsqrtf(ss * (1.0f / (float)H) + p.eps);
+#pragma unroll
+        for (int i = 0; i < HK / 4; ++i)
+          y[i] = pack_bf16(bf16_lo(xv[i]) * (inv * nscale[2 * i]), bf16_hi(xv[i]) * (inv * nscale[2 * i + 1]));
       }
-      af_sts64(xs + warp * 256 + (((2 * lane) ^ (4 * (warp & 7))) << 2), y0, y1);
+      if constexpr (HK == 8) af_sts64(xs_row(warp) + (((lane >> 1) ^ xs_swz(warp)) << 4) + 8 * (lane & 1), y[0], y[1]);
+      else sts_v4(xs_row(warp) + ((lane ^ xs_swz(warp)) << 4), make_uint4(y[0], y[1], y[2], y[3]));
     }
     __syncthreads();
     // ---- 3. q,k,v of the CTA's agents: C[16 agents, 16 columns] per warp
@@ -207,17 +247,18 @@ __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedP
 #pragma unroll
       for (int j = 0; j < 2; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
       const bool row_hi_ok = g + 8 < warps;
-      const uint32_t xr0 = xs + g * 256, xr1 = xs + (g + 8) * 256;
+      const uint32_t xr0 = xs_row(g), xr1 = xs_row(g + 8);
+      const int fg = xs_swz(g);                           // == xs_swz(g + 8)
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        uint32_t a[4];
-        const uint32_t w0 = (uint32_t)(((8 * ks + t) ^ (4 * g)) << 2), w1 = (uint32_t)(((8 * ks + 4 + t) ^ (4 * g)) << 2);
-        a[0] = af_lds32(xr0 + w0);
-        a[1] = row_hi_ok ? af_lds32(xr1 + w0) : 0u;
-        a[2] = af_lds32(xr0 + w1);
-        a[3] = row_hi_ok ? af_lds32(xr1 + w1) : 0u;
-        af_mma(acc[0], a, bw[0][ks][0], bw[0][ks][1]);
-        af_mma(acc[1], a, bw[1][ks][0], bw[1][ks][1]);
+      for (int kb = 0; kb < HK / 2; ++kb) {
+        const uint32_t c = (uint32_t)(((4 * kb + t) ^ fg) << 4);
+        const uint4 lo = lds_v4(xr0 + c);
+        const uint4 hi = row_hi_ok ? lds_v4(xr1 + c) : make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t a0[4] = {lo.x, hi.x, lo.y, hi.y}, a1[4] = {lo.z, hi.z, lo.w, hi.w};
+        af_mma(acc[0], a0, bw[0][kb].x, bw[0][kb].y);
+        af_mma(acc[1], a0, bw[1][kb].x, bw[1][kb].y);
+        af_mma(acc[0], a1, bw[0][kb].z, bw[0][kb].w);
+        af_mma(acc[1], a1, bw[1][kb].z, bw[1][kb].w);
       }
 #pragma unroll
       for (int rs = 0; rs < 2; ++rs) {                    // agent rows g and g + 8
@@ -361,6 +402,9 @@ __global__ void __launch_bounds__(448) attn_decode_fused_kernel(const AttnFusedP
     } else {
       af_wait<0>();
     }
+    // hidden 256: the weight fragments do not stay in registers across the cache loop - re-read them (L2) for the next
+    // round; unconditional, so that nothing of the previous copy is live inside the loop above
+    if (HK > 8) load_w();
   }
 }
 
@@ -373,12 +417,12 @@ extern "C" int mpx_attn_decode_fused(const mpx_attn_decode_fused_args* a, mpx_st
   MPX_REQUIRE(a && a->x && a->norm_scale && a->wt_qkv && a->pos && a->rope_timescale && a->kcache && a->vcache && a->out,
               "mpx_attn_decode_fused: null pointer");
   MPX_REQUIRE(a->B > 0 && a->S > 0, "mpx_attn_decode_fused: bad shape");
-  MPX_REQUIRE(a->H == 128 && a->Nq == 4 && a->Nkv == 1 && a->D == 32,
-              "mpx_attn_decode_fused: only hidden 128, 4 query heads on 1 kv head, head_dim 32 (got H=%d Nq=%d Nkv=%d D=%d); "
+  MPX_REQUIRE((a->H == 128 || a->H == 256) && a->Nq == 4 && a->Nkv == 1 && a->D == 32,
+              "mpx_attn_decode_fused: only hidden 128 / 256, 4 query heads on 1 kv head, head_dim 32 (got H=%d Nq=%d Nkv=%d D=%d); "
               "use mpx_qkv_rope + mpx_attn_decode", a->H, a->Nq, a->Nkv, a->D);
-  MPX_REQUIRE((reinterpret_cast<uintptr_t>(a->x) & 7) == 0 && (reinterpret_cast<uintptr_t>(a->norm_scale) & 15) == 0 &&
+  MPX_REQUIRE((reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->norm_scale) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(a->kcache) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->vcache) & 15) == 0 &&
-              (reinterpret_cast<uintptr_t>(a->wt_qkv) & 3) == 0, "mpx_attn_decode_fused: misaligned pointer");
+              (reinterpret_cast<uintptr_t>(a->wt_qkv) & 15) == 0, "mpx_attn_decode_fused: misaligned pointer");
   const int sms = num_sms();
   int best_w = 14;
   double best_eff = -1.0;
@@ -389,14 +433,16 @@ extern "C" int mpx_attn_decode_fused(const mpx_attn_decode_fused_args* a, mpx_st
     if (eff > best_eff + 1e-9) { best_eff = eff; best_w = w; }
   }
   const size_t smem = (size_t)AF_RING * best_w;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(attn_decode_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int wide = a->H == 256 ? 1 : 0;
+  static size_t attr_smem[2] = {0, 0};
+  if (smem > attr_smem[wide]) {
+    cudaError_t e = wide ? cudaFuncSetAttribute(attn_decode_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                         : cudaFuncSetAttribute(attn_decode_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(attn_decode_fused): %s", cudaGetErrorString(e));
       return MPX_ERR_CUDA;
     }
-    attr_smem = smem;
+    attr_smem[wide] = smem;
   }
   const int grid = ceil_div(a->B, best_w) < sms ? ceil_div(a->B, best_w) : sms;
   AttnFusedParams p;
@@ -412,7 +458,8 @@ extern "C" int mpx_attn_decode_fused(const mpx_attn_decode_fused_args* a, mpx_st
   p.B = a->B; p.S = a->S;
   p.scale_log2 = (1.0f / sqrtf((float)a->D)) * 1.4426950408889634f;
   p.early_stream = (a->flags & 1) ? 1 : 0;
-  cudaError_t le = launch_ex(attn_decode_fused_kernel, dim3(grid), dim3(best_w * 32), smem, (cudaStream_t)stream, 0, 4, p);
+  cudaError_t le = wide ? launch_ex(attn_decode_fused_kernel<16>, dim3(grid), dim3(best_w * 32), smem, (cudaStream_t)stream, 0, 4, p)
+                        : launch_ex(attn_decode_fused_kernel<8>, dim3(grid), dim3(best_w * 32), smem, (cudaStream_t)stream, 0, 4, p);
   if (le != cudaSuccess) {
     set_error("launch attn_decode_fused_kernel: %s", cudaGetErrorString(le));
     return MPX_ERR_CUDA;

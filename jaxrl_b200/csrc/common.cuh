@@ -34,7 +34,8 @@ int num_sms();   // abi.cu (cached cudaDevAttrMultiProcessorCount of the current
 
 // Launch with optional thread-block cluster (x dimension) and programmatic dependent launch (see ptx.cuh).
 extern int g_use_pdl;   // mpx_debug_set(6, mask); default 12.  Bit per kernel family (the `pdl` argument of launch_ex):
-                        // 1 = everything else, 2 = obs encoder, 4 = decode attention, 8 = fused GLU, 16 = policy head.
+                        // 1 = everything else, 2 = obs encoder, 4 = decode attention (+ rollout-sized GEMM / rmsnorm launches, M <= 8192),
+                        // 8 = fused GLU, 16 = policy head.
                         // Measured on the whole PPO step (trips 76 / 81, 10 timed steps, +-0.03 ms run to run): 4 -> -1.4 ms
                         // of rollout, 4|8 -> -2.0 ms, 2 -> +3.5 ms, 16 -> +3.1 ms (their early CTAs take the SM slots the
                         // predecessor's tail needs).

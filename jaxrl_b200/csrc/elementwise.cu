@@ -369,11 +369,12 @@ extern "C" int mpx_rmsnorm_fwd(const mpx_bf16* x, const float* scale, float eps,
   auto X = reinterpret_cast<const __nv_bfloat16*>(x);
   auto Y = reinterpret_cast<__nv_bfloat16*>(y);
   cudaStream_t s = (cudaStream_t)stream;
+  const int fam = M <= 8192 ? 4 : 1;      // rollout-sized rows: programmatic launch like the decode kernels (gemm_tc.cu)
   switch (H / 128) {
-    case 1: launch_ex(rmsnorm_fwd_kernel<1>, dim3(grid), dim3(EW_WARPS * 32), 0, s, 0, true, X, scale, eps, Y, M, H); break;
-    case 2: launch_ex(rmsnorm_fwd_kernel<2>, dim3(grid), dim3(EW_WARPS * 32), 0, s, 0, true, X, scale, eps, Y, M, H); break;
-    case 3: launch_ex(rmsnorm_fwd_kernel<3>, dim3(grid), dim3(EW_WARPS * 32), 0, s, 0, true, X, scale, eps, Y, M, H); break;
-    default: launch_ex(rmsnorm_fwd_kernel<4>, dim3(grid), dim3(EW_WARPS * 32), 0, s, 0, true, X, scale, eps, Y, M, H); break;
+    case 1: launch_ex(rmsnorm_fwd_kernel<1>, dim3(grid), dim3(EW_WARPS * 32), 0, s, 0, fam, X, scale, eps, Y, M, H); break;
+    case 2: launch_ex(rmsnorm_fwd_kernel<2>, dim3(grid), dim3(EW_WARPS * 32), 0, s, 0, fam, X, scale, eps, Y, M, H); break;
+    case 3: launch_ex(rmsnorm_fwd_kernel<3>, dim3(grid), dim3(EW_WARPS * 32), 0, s, 0, fam, X, scale, eps, Y, M, H); break;
+    default: launch_ex(rmsnorm_fwd_kernel<4>, dim3(grid), dim3(EW_WARPS * 32), 0, s, 0, fam, X, scale, eps, Y, M, H); break;
   }
   return check_launch("mpx_rmsnorm_fwd");
 }

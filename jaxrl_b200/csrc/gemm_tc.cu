@@ -1084,8 +1084,11 @@ static int launch_tn(const GemmParams& p, const void* a, long long lda, const vo
     }
     pp.tma_store = 1;
   }
-  cudaError_t le = launch_ex(gemm_tn_kernel<BLOCK_N, EPI>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, 0, true, pp, tm_a, tm_b,
-                             tm_y, tm_ypre);
+  // rollout-sized GEMMs (one decode step of the per-op chain, hidden 256) launch programmatically like the fused decode
+  // kernels (family 4): -3 us per layer of a multitask step; training-sized ones stay in the "everything else" family
+  const int pdl_family = p.M <= 8192 ? 4 : 1;
+  cudaError_t le = launch_ex(gemm_tn_kernel<BLOCK_N, EPI>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, 0, pdl_family, pp, tm_a,
+                             tm_b, tm_y, tm_ypre);
   if (le != cudaSuccess) {
     set_error("launch gemm_tn_kernel: %s", cudaGetErrorString(le));
     return MPX_ERR_CUDA;

@@ -55,7 +55,7 @@ class PolicyEngine:
         self.L = cfg.num_layers
         glu_ok = (H == 128 and cfg.ffn_size % 64 == 0)
         self.fused_glu = glu_ok and fused_rollout                  # decode path: one kernel per GLU block
-        self.fused_attn_decode = (H == 128 and self.Nq == 4 and self.Nkv == 1 and self.D == 32 and fused_rollout)
+        self.fused_attn_decode = (H in (128, 256) and self.Nq == 4 and self.Nkv == 1 and self.D == 32 and fused_rollout)
         # training path: the same forward kernel (keeping h) and a one-kernel backward that recomputes u, g, dh on chip
         self.fused_glu_train = glu_ok
         self.fused_value = (H == 128 and cfg.value_hidden_dim is not None and cfg.value_hidden_dim % 64 == 0

@@ -15,7 +15,7 @@ q = torch.randn(B, Nq * D, device=dev, generator=g).to(torch.bfloat16)
 caches = [(torch.randn(B, S, Nkv, D, device=dev, generator=g).to(torch.bfloat16),
            torch.randn(B, S, Nkv, D, device=dev, generator=g).to(torch.bfloat16)) for _ in range(2)]
 out = torch.empty_like(q)
-H = 128
+H = int(sys.argv[sys.argv.index("--hidden") + 1]) if "--hidden" in sys.argv else 128
 x = torch.randn(B, H, device=dev, generator=g).to(torch.bfloat16)
 nscale = torch.ones(H, device=dev)
 wt_qkv = (torch.randn((Nq + 2 * Nkv) * D, H, device=dev, generator=g) / H ** 0.5).to(torch.bfloat16)

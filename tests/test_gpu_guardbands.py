@@ -38,11 +38,12 @@ def _g(seed):
 
 
 @pytest.mark.parametrize("B,step,S", [(1, 0, 16), (13, 5, 16), (15, 40, 64), (29, 700, 512), (2075, 300, 512)])
-def test_attn_decode_fused_guard(B, step, S):
+@pytest.mark.parametrize("H", [128, 256])
+def test_attn_decode_fused_guard(B, step, S, H):
     from jaxrl_b200 import ops
     from _util import rope_timescale
-    gen = _g(B + step)
-    H, D, Nq, Nkv = 128, 32, 4, 1
+    gen = _g(B + step + H)
+    D, Nq, Nkv = 32, 4, 1
     x = Guarded((B, H), BF16, (torch.randn(B, H, generator=gen)).to(BF16))
     kc = Guarded((B, S, Nkv, D), BF16, torch.randn(B, S, Nkv, D, generator=gen).to(BF16))
     vc = Guarded((B, S, Nkv, D), BF16, torch.randn(B, S, Nkv, D, generator=gen).to(BF16))

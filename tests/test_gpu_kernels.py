@@ -281,11 +281,13 @@ def test_attn_decode(ops, step, S, Nq, Nkv, Bb, impl):
 
 @pytest.mark.parametrize("step,S,Bb", [(0, 16, 3), (5, 16, 9), (31, 64, 14), (32, 64, 15), (100, 512, 33), (300, 512, 4096),
                                        (511, 512, 130), (700, 512, 29), (1029, 512, 2100)])
-def test_attn_decode_fused(ops, step, S, Bb):
+@pytest.mark.parametrize("H", [128, 256])
+def test_attn_decode_fused(ops, step, S, Bb, H):
     """history_norm + q/k/v + RoPE + ring write + attention in one kernel vs the oracle chain (network.py:158-165,
-    attention.py:96-150); the ring must change only at slot pos % S, there by exactly the new k,v."""
-    gen = g(step * 3 + S + Bb)
-    H, D, Nq, Nkv = 128, 32, 4, 1
+    attention.py:96-150); the ring must change only at slot pos % S, there by exactly the new k,v.  H = 256 is the
+    multitask width (config/multitask.json:31)."""
+    gen = g(step * 3 + S + Bb + H)
+    D, Nq, Nkv = 32, 4, 1
     x = (torch.randn(Bb, H, generator=gen) * 2).to(BF16)
     scale = 1.0 + 0.2 * torch.randn(H, generator=gen)
     w = (torch.randn((Nq + 2 * Nkv) * D, H, generator=gen) / math.sqrt(H)).to(BF16)
@@ -325,11 +327,12 @@ def test_attn_decode_fused(ops, step, S, Bb):
 
 
 @pytest.mark.parametrize("step,S,Bb", [(0, 16, 3), (40, 64, 15), (300, 512, 4096), (511, 512, 130), (1029, 512, 2100)])
-def test_attn_decode_fused_early_stream(ops, step, S, Bb):
+@pytest.mark.parametrize("H", [128, 256])
+def test_attn_decode_fused_early_stream(ops, step, S, Bb, H):
     """flags bit 0 (ring history declared stable: its stream starts before griddepcontrol.wait) changes neither the
     output nor the ring, bit for bit, also right behind a kernel that has just rewritten x."""
-    gen = g(step + S + Bb)
-    H, D, Nq, Nkv = 128, 32, 4, 1
+    gen = g(step + S + Bb + H)
+    D, Nq, Nkv = 32, 4, 1
     x = (torch.randn(Bb, H, generator=gen) * 2).to(BF16).to(DEV)
     scale = (1.0 + 0.2 * torch.randn(H, generator=gen)).to(DEV)
     w = (torch.randn((Nq + 2 * Nkv) * D, H, generator=gen) / math.sqrt(H)).to(BF16).to(DEV)
