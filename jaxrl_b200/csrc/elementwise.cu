@@ -52,6 +52,51 @@ __global__ void __launch_bounds__(EW_WARPS * 32) rmsnorm_fwd_kernel(
   }
 }
 
+// H == 128 specialisation (every shipped config but multitask): 16 lanes per row with 16-byte accesses (two rows per warp
+// instruction), two row pairs in flight per iteration and a 4-step instead of a 5-step reduction - the generic kernel keeps
+// one 256-byte row per warp in flight and measured 1.9 TB/s on the training tensors (17 us per 131072 rows).
+__global__ void __launch_bounds__(EW_WARPS * 32) rmsnorm_fwd128_kernel(
+    const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, float eps, __nv_bfloat16* __restrict__ y,
+    long long M) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & 15, rsel = lane >> 4;
+  float sc[8];
+  {
+    const float4 a = reinterpret_cast<const float4*>(scale + sub * 8)[0], b = reinterpret_cast<const float4*>(scale + sub * 8)[1];
+    sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
+  }
+  griddep_launch();
+  griddep_wait();
+  const long long stride = (long long)gridDim.x * EW_WARPS * 4;
+  for (long long base = ((long long)blockIdx.x * EW_WARPS + warp) * 4; base < M; base += stride) {
+    uint4 xq[2];
+    bool live[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long row = base + 2 * u + rsel;
+      live[u] = row < M;
+      xq[u] = live[u] ? *reinterpret_cast<const uint4*>(x + row * 128 + sub * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t xw[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w};
+      float ss = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ss += bf16_lo(xw[e]) * bf16_lo(xw[e]) + bf16_hi(xw[e]) * bf16_hi(xw[e]);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rstd = rsqrtf(ss * (1.0f / 128.0f) + eps);
+      uint4 o;
+      o.x = pack_bf16(bf16_lo(xw[0]) * (rstd * sc[0]), bf16_hi(xw[0]) * (rstd * sc[1]));
+      o.y = pack_bf16(bf16_lo(xw[1]) * (rstd * sc[2]), bf16_hi(xw[1]) * (rstd * sc[3]));
+      o.z = pack_bf16(bf16_lo(xw[2]) * (rstd * sc[4]), bf16_hi(xw[2]) * (rstd * sc[5]));
+      o.w = pack_bf16(bf16_lo(xw[3]) * (rstd * sc[6]), bf16_hi(xw[3]) * (rstd * sc[7]));
+      const long long row = base + 2 * u + rsel;
+      if (live[u]) *reinterpret_cast<uint4*>(y + row * 128 + sub * 8) = o;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ RMSNorm bwd
 // a = dy * scale ; dx = rstd * a - x * rstd^3 / H * sum(a * x) ; dscale += sum_rows dy * x * rstd
 // out = bf16(dx) (+ dres in bf16 if given: the residual branch's cotangent).
@@ -370,6 +415,13 @@ extern "C" int mpx_rmsnorm_fwd(const mpx_bf16* x, const float* scale, float eps,
   auto Y = reinterpret_cast<__nv_bfloat16*>(y);
   cudaStream_t s = (cudaStream_t)stream;
   const int fam = M <= 8192 ? 4 : 1;      // rollout-sized rows: programmatic launch like the decode kernels (gemm_tc.cu)
+  if (H == 128 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(scale) & 15) == 0) {
+    const long long cap = (long long)num_sms() * 8;
+    const long long g4 = (M + EW_WARPS * 4 - 1) / (EW_WARPS * 4);
+    launch_ex(rmsnorm_fwd128_kernel, dim3((unsigned)(g4 < cap ? g4 : cap)), dim3(EW_WARPS * 32), 0, s, 0, fam, X, scale, eps, Y, M);
+    return check_launch("mpx_rmsnorm_fwd");
+  }
   switch (H / 128) {
     case 1: launch_ex(rmsnorm_fwd_kernel<1>, dim3(grid), dim3(EW_WARPS * 32), 0, s, 0, fam, X, scale, eps, Y, M, H); break;
     case 2: launch_ex(rmsnorm_fwd_kernel<2>, dim3(grid), dim3(EW_WARPS * 32), 0, s, 0, fam, X, scale, eps, Y, M, H); break;
