@@ -23,6 +23,12 @@ constexpr int VF_STAGES = 4;
 constexpr int VF_STAGE_BYTES = 16384;
 constexpr int VF_THREADS = 320;
 constexpr int VF_EPI_WARPS = 8;
+#ifndef VF_X_TMEM
+#define VF_X_TMEM 1             // 1: the (normalised) x tile, A operand of every MMA1 of the tile, is copied to TMEM once per tile
+#endif
+#ifndef VF_H_TMEM
+#define VF_H_TMEM 1             // 1: the pv chunk (A operand of MMA2) goes registers -> TMEM (tcgen05.st), never through shared memory
+#endif
 
 int g_value_fused_cluster = 0;   // mpx_debug_set(4, v): 0 = auto, 1/2/4 = force that cluster size (tests)
 
@@ -103,7 +109,7 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, (VF_H_TMEM || VF_X_TMEM) ? 512 : 256);
     tmem_relinquish();
   }
   griddep_wait();                              // everything read from global memory below may come from earlier kernels
@@ -125,6 +131,8 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t tZ[2] = {tmem_base, tmem_base + 64};
   const uint32_t tD = tmem_base + 128;
+  const uint32_t tX = tmem_base + 320;                         // [VF_X_TMEM] x tile: 128 lanes x 64 columns (K = 128 as bf16 pairs)
+  const uint32_t tH[2] = {tmem_base + 256, tmem_base + 288};   // [VF_H_TMEM] pv chunk double buffer: 128 lanes x 32 columns (bf16 pairs)
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -174,11 +182,18 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
         const uint32_t sb = smem_u32(sW + stage * VF_STAGE_BYTES);
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
+#if VF_X_TMEM
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ts_1(tZ[b], tX + 32 * kb + 8 * k, umma_smem_desc_sw128(sb + kb * 8192 + 32 * k, 16, 1024), idesc1,
+                           (kb | k) != 0 ? 1u : 0u);
+#else
           const uint32_t sa = smem_u32(sX + kb * 16384);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16_1(tZ[b], umma_smem_desc_sw128(sa + 32 * k, 16, 1024),
                       umma_smem_desc_sw128(sb + kb * 8192 + 32 * k, 16, 1024), idesc1, (kb | k) != 0 ? 1u : 0u);
+#endif
         }
         umma_commit_1(&w_empty[stage]);
         if (++stage == VF_STAGES) { stage = 0; wphase ^= 1; }
@@ -192,12 +207,18 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
         h_ph[b] ^= 1;
         mbar_wait(&w_full[stage], wphase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(sH + b * 16384);
         const uint32_t sb = smem_u32(sW + stage * VF_STAGE_BYTES);
+#if VF_H_TMEM
+#pragma unroll
+        for (int k = 0; k < 4; ++k)                            // 16 bf16 of K = 8 TMEM columns per step
+          umma_bf16_ts_1(tD, tH[b] + 8 * k, umma_smem_desc_sw128(sb + 32 * k, 16, 1024), idesc2, (c | k) != 0 ? 1u : 0u);
+#else
+        const uint32_t sa = smem_u32(sH + b * 16384);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16_1(tD, umma_smem_desc_sw128(sa + 32 * k, 16, 1024), umma_smem_desc_sw128(sb + 32 * k, 16, 1024), idesc2,
                     (c | k) != 0 ? 1u : 0u);
+#endif
         umma_commit_1(&w_empty[stage]);
         if (++stage == VF_STAGES) { stage = 0; wphase ^= 1; }
         umma_commit_1(&h_empty[b]);
@@ -230,6 +251,41 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
       mbar_wait(x_full, xphase);
       xphase ^= 1;
       dbg_stamp(dbg, 2);
+#if VF_X_TMEM
+      {
+        // my row's 64 features of K block `half` (8 swizzled 16-byte chunks) -> registers -> (RMSNorm) -> TMEM columns
+        // [32 half, +32) of the x operand; MMA1 of the previous tile finished with tX before x_full could complete again
+        const uint32_t xrow = smem_u32(sX + half * 16384 + r * 128);
+        uint32_t xw[32];
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 v = lds_v4(xrow + ((c ^ (r & 7)) << 4));
+          xw[4 * c] = v.x; xw[4 * c + 1] = v.y; xw[4 * c + 2] = v.z; xw[4 * c + 3] = v.w;
+        }
+        if (p.norm_scale) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float a = bf16_lo(xw[i]), b = bf16_hi(xw[i]);
+            ss += a * a + b * b;
+          }
+          sSq[half * 128 + r] = ss;
+          named_bar_sync(1, VF_EPI_WARPS * 32);
+          const float inv = rsqrtf((sSq[r] + sSq[128 + r]) * (1.0f / 128.0f) + p.eps);
+          const float2* sc2 = reinterpret_cast<const float2*>(sScale + half * 64);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float2 s2 = sc2[i];
+            xw[i] = pack_bf16(bf16_lo(xw[i]) * inv * s2.x, bf16_hi(xw[i]) * inv * s2.y);
+          }
+        }
+        tc_fence_after();
+        tmem_st_32x32(tX + lane_off + 32 * half, xw);
+        tmem_st_wait_all();
+        tc_fence_before();
+        if (p.norm_scale) named_bar_sync(1, VF_EPI_WARPS * 32);   // sSq may be rewritten by the next tile
+      }
+#else
       if (p.norm_scale) {
         const uint32_t xrow = smem_u32(sX + half * 16384 + r * 128);
         uint4 xv[8];
@@ -261,6 +317,7 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
         fence_proxy_async_smem();
         named_bar_sync(1, VF_EPI_WARPS * 32);                 // sSq may be rewritten by the next tile
       }
+#endif
       __syncwarp();
       dbg_stamp(dbg, 3);
       if (lane == 0) mbar_arrive(xn_ready);
@@ -295,6 +352,13 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
         }
         mbar_wait(&h_empty[b], h_ph[b] ^ 1);
         h_ph[b] ^= 1;
+#if VF_H_TMEM
+        tc_fence_after();                                     // MMA2 of chunk c-2 (the buffer's last reader) has completed
+        tmem_st_32x16(tH[b] + lane_off + 16 * half, hw);        // my row, K columns [32 half, +32) as 16 bf16 pairs
+        tmem_st_wait_all();
+        tc_fence_before();
+        __syncwarp();
+#else
         const uint32_t hrow = smem_u32(sH + b * 16384 + r * 128);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -303,6 +367,7 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
         }
         fence_proxy_async_smem();
         __syncwarp();
+#endif
         dbg_stamp(dbg, 5 + 2 * c);
         if (lane == 0) mbar_arrive(&h_full[b]);
       }
@@ -412,7 +477,7 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
   tc_fence_before();
   __syncthreads();
   dbg_stamp(dbg, 25);
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, (VF_H_TMEM || VF_X_TMEM) ? 512 : 256);
 }
 
 }  // namespace mpx
