@@ -357,7 +357,7 @@ def attn_decode(q, kcache, vcache, pos, Nq: int, Nkv: int, D: int, out=None):
 
 def attn_decode_fused(x, norm_scale, wt_qkv, pos, timescale, kcache, vcache, Nq: int, Nkv: int, D: int, out=None,
                       eps: float = 1e-6, stable_history: bool = False):
-    """history_norm + q/k/v projection + RoPE + ring write + decode attention in one kernel (H=128, Nq=4, Nkv=1, D=32).
+    """history_norm + q/k/v projection + RoPE + ring write + decode attention in one kernel (H in {128, 256}, Nq=4, Nkv=1, D=32).
     kcache/vcache (B,S,Nkv,D) are updated in place at slot pos[0] % S; returns out (B, Nq*D).
     stable_history: the caller guarantees that the other ring slots were written by kernels that completed before this
     launch could start (flags bit 0 of the C ABI) - lets the cache stream start under the previous kernel's tail."""
