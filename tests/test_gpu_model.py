@@ -236,7 +236,7 @@ def test_flattened_encoder_forward_backward_match_oracle():
         rel = (gg - gref).norm().item() / (gref.norm().item() + 1e-8)
         cos = (gg * gref).sum().item() / (gg.norm().item() * gref.norm().item() + 1e-12)
         _log(f"flat-encoder grad {name}: rel_l2={rel:.4f} cos={cos:.5f}")
-        assert cos > 0.99 and rel < 0.1, f"gradient mismatch for {name}: rel {rel} cos {cos}"
+        assert cos > 0.999 and rel < 3e-2, f"gradient mismatch for {name}: rel {rel} cos {cos}"   # measured <= 1.1e-2
     # decode: embedding of the first step equals the training embedding of token 0 of each row
     dws = eng.alloc_decode(B)
     eng.reset_carry(dws)
