@@ -220,8 +220,8 @@ int mpx_attn_decode(const mpx_attn_decode_args* a, mpx_stream_t stream);
  * history_norm -> q/k/v projection -> RoPE -> ring write at pos[0] % S -> the attention above, with the projection
  * running under the start of the cache stream.  Replaces mpx_rmsnorm_fwd + mpx_qkv_rope + mpx_attn_decode for
  * H in {128, 256}, Nq == 4, Nkv == 1, D == 32 (MPX_ERR_INVALID otherwise).  x (B,H) is the un-normalised residual
- * stream, 16-byte aligned like wt_qkv ((Nq+2*Nkv)*D, H) - laid out as in mpx_qkv_rope; kcache/vcache (B,S,1,D) are
- * updated in place; out (B, Nq*D). */
+ * stream (8-byte aligned, 16 at H == 256); wt_qkv ((Nq+2*Nkv)*D, H) as in mpx_qkv_rope, 16-byte aligned; kcache/vcache
+ * (B,S,1,D) are updated in place; out (B, Nq*D). */
 typedef struct {
   const mpx_bf16* x; const float* norm_scale; float eps;
   const mpx_bf16* wt_qkv;

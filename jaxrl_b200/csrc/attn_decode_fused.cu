@@ -420,7 +420,7 @@ extern "C" int mpx_attn_decode_fused(const mpx_attn_decode_fused_args* a, mpx_st
   MPX_REQUIRE((a->H == 128 || a->H == 256) && a->Nq == 4 && a->Nkv == 1 && a->D == 32,
               "mpx_attn_decode_fused: only hidden 128 / 256, 4 query heads on 1 kv head, head_dim 32 (got H=%d Nq=%d Nkv=%d D=%d); "
               "use mpx_qkv_rope + mpx_attn_decode", a->H, a->Nq, a->Nkv, a->D);
-  MPX_REQUIRE((reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->norm_scale) & 15) == 0 &&
+  MPX_REQUIRE((reinterpret_cast<uintptr_t>(a->x) & (a->H == 256 ? 15 : 7)) == 0 && (reinterpret_cast<uintptr_t>(a->norm_scale) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(a->kcache) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->vcache) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(a->wt_qkv) & 15) == 0, "mpx_attn_decode_fused: misaligned pointer");
   const int sms = num_sms();
