@@ -52,14 +52,16 @@ __global__ void __launch_bounds__(EW_WARPS * 32) rmsnorm_fwd_kernel(
   }
 }
 
-// H == 128 specialisation (every shipped config but multitask): 16 lanes per row with 16-byte accesses (two rows per warp
-// instruction), two row pairs in flight per iteration and a 4-step instead of a 5-step reduction - the generic kernel keeps
-// one 256-byte row per warp in flight and measured 1.9 TB/s on the training tensors (17 us per 131072 rows).
-__global__ void __launch_bounds__(EW_WARPS * 32) rmsnorm_fwd128_kernel(
+// H == 128 / 256 specialisation (every shipped config): 16 or 32 lanes per row with 16-byte accesses (two rows or one per warp
+// instruction), two of them in flight per iteration - the generic kernel keeps one row per warp in flight with 8-byte accesses
+// and measured 1.9 TB/s on the training tensors (17 us per 131072 rows of 128).
+template <int LPR>   // lanes per row: 16 (hidden 128, two rows per warp instruction) or 32 (hidden 256)
+__global__ void __launch_bounds__(EW_WARPS * 32) rmsnorm_fwdw_kernel(
     const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, float eps, __nv_bfloat16* __restrict__ y,
     long long M) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane & 15, rsel = lane >> 4;
+  constexpr int H = 8 * LPR, RPW = 32 / LPR;
+  const int sub = lane & (LPR - 1), rsel = lane / LPR;
   float sc[8];
   {
     const float4 a = reinterpret_cast<const float4*>(scale + sub * 8)[0], b = reinterpret_cast<const float4*>(scale + sub * 8)[1];
@@ -67,15 +69,15 @@ __global__ void __launch_bounds__(EW_WARPS * 32) rmsnorm_fwd128_kernel(
   }
   griddep_launch();
   griddep_wait();
-  const long long stride = (long long)gridDim.x * EW_WARPS * 4;
-  for (long long base = ((long long)blockIdx.x * EW_WARPS + warp) * 4; base < M; base += stride) {
+  const long long stride = (long long)gridDim.x * EW_WARPS * 2 * RPW;
+  for (long long base = ((long long)blockIdx.x * EW_WARPS + warp) * 2 * RPW; base < M; base += stride) {
     uint4 xq[2];
     bool live[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const long long row = base + 2 * u + rsel;
+      const long long row = base + RPW * u + rsel;
       live[u] = row < M;
-      xq[u] = live[u] ? *reinterpret_cast<const uint4*>(x + row * 128 + sub * 8) : make_uint4(0, 0, 0, 0);
+      xq[u] = live[u] ? *reinterpret_cast<const uint4*>(x + row * H + sub * 8) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -84,15 +86,15 @@ __global__ void __launch_bounds__(EW_WARPS * 32) rmsnorm_fwd128_kernel(
 #pragma unroll
       for (int e = 0; e < 4; ++e) ss += bf16_lo(xw[e]) * bf16_lo(xw[e]) + bf16_hi(xw[e]) * bf16_hi(xw[e]);
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      const float rstd = rsqrtf(ss * (1.0f / 128.0f) + eps);
+      for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rstd = rsqrtf(ss * (1.0f / (float)H) + eps);
       uint4 o;
       o.x = pack_bf16(bf16_lo(xw[0]) * (rstd * sc[0]), bf16_hi(xw[0]) * (rstd * sc[1]));
       o.y = pack_bf16(bf16_lo(xw[1]) * (rstd * sc[2]), bf16_hi(xw[1]) * (rstd * sc[3]));
       o.z = pack_bf16(bf16_lo(xw[2]) * (rstd * sc[4]), bf16_hi(xw[2]) * (rstd * sc[5]));
       o.w = pack_bf16(bf16_lo(xw[3]) * (rstd * sc[6]), bf16_hi(xw[3]) * (rstd * sc[7]));
-      const long long row = base + 2 * u + rsel;
-      if (live[u]) *reinterpret_cast<uint4*>(y + row * 128 + sub * 8) = o;
+      const long long row = base + RPW * u + rsel;
+      if (live[u]) *reinterpret_cast<uint4*>(y + row * H + sub * 8) = o;
     }
   }
 }
@@ -170,34 +172,36 @@ __global__ void __launch_bounds__(EW_WARPS * 32) rmsnorm_bwd_kernel(
   }
 }
 
-// H == 128 specialisation: 16 lanes per row with 16-byte accesses (two rows per warp instruction) and two row pairs in
+// H == 128 / 256 specialisation: 16 / 32 lanes per row with 16-byte accesses (two rows / one per warp instruction), two of them in
 // flight per iteration - the generic kernel above is latency bound at this width (8-byte accesses, one row per warp).
-__global__ void __launch_bounds__(EW_WARPS * 32) rmsnorm_bwd128_kernel(
+template <int LPR>   // lanes per row: 16 (hidden 128) or 32 (hidden 256)
+__global__ void __launch_bounds__(EW_WARPS * 32) rmsnorm_bwdw_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
     float eps, const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ dscale,
     long long M) {
-  __shared__ float s_ds[EW_WARPS * 2][128];
+  constexpr int H = 8 * LPR, RPW = 32 / LPR;
+  __shared__ float s_ds[EW_WARPS * RPW][H];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane & 15, rsel = lane >> 4;
+  const int sub = lane & (LPR - 1), rsel = lane / LPR;
   float sc[8];
   {
     const float4 a = reinterpret_cast<const float4*>(scale + sub * 8)[0], b = reinterpret_cast<const float4*>(scale + sub * 8)[1];
     sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
   }
   float ds[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const long long stride = (long long)gridDim.x * EW_WARPS * 4;
-  for (long long base = ((long long)blockIdx.x * EW_WARPS + warp) * 4; base < M; base += stride) {
+  const long long stride = (long long)gridDim.x * EW_WARPS * 2 * RPW;
+  for (long long base = ((long long)blockIdx.x * EW_WARPS + warp) * 2 * RPW; base < M; base += stride) {
     uint4 xq[2], gq[2], rq[2];
     bool live[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const long long row = base + 2 * u + rsel;
+      const long long row = base + RPW * u + rsel;
       live[u] = row < M;
       xq[u] = gq[u] = rq[u] = make_uint4(0, 0, 0, 0);
       if (live[u]) {
-        xq[u] = *reinterpret_cast<const uint4*>(x + row * 128 + sub * 8);
-        gq[u] = *reinterpret_cast<const uint4*>(dy + row * 128 + sub * 8);
-        if (dres) rq[u] = *reinterpret_cast<const uint4*>(dres + row * 128 + sub * 8);
+        xq[u] = *reinterpret_cast<const uint4*>(x + row * H + sub * 8);
+        gq[u] = *reinterpret_cast<const uint4*>(dy + row * H + sub * 8);
+        if (dres) rq[u] = *reinterpret_cast<const uint4*>(dres + row * H + sub * 8);
       }
     }
 #pragma unroll
@@ -213,8 +217,8 @@ __global__ void __launch_bounds__(EW_WARPS * 32) rmsnorm_bwd128_kernel(
         ss += xv[2 * e] * xv[2 * e] + xv[2 * e + 1] * xv[2 * e + 1];
       }
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      const float rstd = rsqrtf(ss * (1.0f / 128.0f) + eps);
+      for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rstd = rsqrtf(ss * (1.0f / (float)H) + eps);
       float dot = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -223,8 +227,8 @@ __global__ void __launch_bounds__(EW_WARPS * 32) rmsnorm_bwd128_kernel(
         ds[i] += gv[i] * xv[i] * rstd;
       }
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-      const float c = rstd * rstd * rstd * dot * (1.0f / 128.0f);
+      for (int o = LPR / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      const float c = rstd * rstd * rstd * dot * (1.0f / (float)H);
       uint32_t ow[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -236,17 +240,17 @@ __global__ void __launch_bounds__(EW_WARPS * 32) rmsnorm_bwd128_kernel(
         }
         ow[e] = pack_bf16(o0, o1);
       }
-      if (live[u]) *reinterpret_cast<uint4*>(dx + (base + 2 * u + rsel) * 128 + sub * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      if (live[u]) *reinterpret_cast<uint4*>(dx + (base + RPW * u + rsel) * H + sub * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
   }
   if (dscale) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s_ds[warp * 2 + rsel][sub * 8 + i] = ds[i];
+    for (int i = 0; i < 8; ++i) s_ds[warp * RPW + rsel][sub * 8 + i] = ds[i];
     __syncthreads();
-    for (int j = threadIdx.x; j < 128; j += EW_WARPS * 32) {
+    for (int j = threadIdx.x; j < H; j += EW_WARPS * 32) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < EW_WARPS * 2; ++w) t += s_ds[w][j];
+      for (int w = 0; w < EW_WARPS * RPW; ++w) t += s_ds[w][j];
       atomicAdd(dscale + j, t);
     }
   }
@@ -415,11 +419,14 @@ extern "C" int mpx_rmsnorm_fwd(const mpx_bf16* x, const float* scale, float eps,
   auto Y = reinterpret_cast<__nv_bfloat16*>(y);
   cudaStream_t s = (cudaStream_t)stream;
   const int fam = M <= 8192 ? 4 : 1;      // rollout-sized rows: programmatic launch like the decode kernels (gemm_tc.cu)
-  if (H == 128 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+  if ((H == 128 || H == 256) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(scale) & 15) == 0) {
     const long long cap = (long long)num_sms() * 8;
-    const long long g4 = (M + EW_WARPS * 4 - 1) / (EW_WARPS * 4);
-    launch_ex(rmsnorm_fwd128_kernel, dim3((unsigned)(g4 < cap ? g4 : cap)), dim3(EW_WARPS * 32), 0, s, 0, fam, X, scale, eps, Y, M);
+    const int rows = H == 128 ? EW_WARPS * 4 : EW_WARPS * 2;          // rows per block and iteration
+    const long long g4 = (M + rows - 1) / rows;
+    const dim3 grid4((unsigned)(g4 < cap ? g4 : cap));
+    if (H == 128) launch_ex(rmsnorm_fwdw_kernel<16>, grid4, dim3(EW_WARPS * 32), 0, s, 0, fam, X, scale, eps, Y, M);
+    else launch_ex(rmsnorm_fwdw_kernel<32>, grid4, dim3(EW_WARPS * 32), 0, s, 0, fam, X, scale, eps, Y, M);
     return check_launch("mpx_rmsnorm_fwd");
   }
   switch (H / 128) {
@@ -444,12 +451,14 @@ extern "C" int mpx_rmsnorm_bwd(const mpx_bf16* dy, const mpx_bf16* x, const floa
   auto DR = reinterpret_cast<const __nv_bfloat16*>(dres);
   auto DX = reinterpret_cast<__nv_bfloat16*>(dx);
   cudaStream_t s = (cudaStream_t)stream;
-  if (H == 128 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+  if ((H == 128 || H == 256) && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(dx) & 15) == 0 && (!dres || (reinterpret_cast<uintptr_t>(dres) & 15) == 0) &&
       (reinterpret_cast<uintptr_t>(scale) & 15) == 0) {
-    long long g4 = (M + EW_WARPS * 4 - 1) / (EW_WARPS * 4);
+    const int rows = H == 128 ? EW_WARPS * 4 : EW_WARPS * 2;          // rows per block and iteration
+    long long g4 = (M + rows - 1) / rows;
     const int grid4 = (int)(g4 < cap ? g4 : cap);
-    rmsnorm_bwd128_kernel<<<grid4, EW_WARPS * 32, 0, s>>>(DY, X, scale, eps, DR, DX, dscale, M);
+    if (H == 128) rmsnorm_bwdw_kernel<16><<<grid4, EW_WARPS * 32, 0, s>>>(DY, X, scale, eps, DR, DX, dscale, M);
+    else rmsnorm_bwdw_kernel<32><<<grid4, EW_WARPS * 32, 0, s>>>(DY, X, scale, eps, DR, DX, dscale, M);
     return check_launch("mpx_rmsnorm_bwd");
   }
   switch (H / 128) {
