@@ -23,6 +23,9 @@ namespace mpx {
 
 constexpr int OF_AG = 32;              // agents per tile
 constexpr int OF_WORKERS = 8;          // worker warps
+#ifndef OF_NU
+#define OF_NU 2                        // conv1 task groups (8 tasks x 4 channel quads) in flight per warp and iteration
+#endif
 constexpr int OF_THREADS = (OF_WORKERS + 1) * 32;
 
 constexpr int OF_A1_BYTES = 26 * 1024;                 // 25 position tiles [32 agents x 16 ch] + 1 tile of slack
@@ -220,37 +223,6 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
           for (int i = wtid; i < nbytes; i += OF_WORKERS * 32) sObs[i] = src[i];
         }
       }
-      // ---- this thread's embedding addends (network.py:304-309), in flight while the encoder runs
-      uint32_t re_w[8], ae_w[8], te_w[8];
-      {
-        const float rw = bf16_round(e_rw);
-        int a = e_a, tk = e_tk;
-        if (eag < nag) {
-          if (a < 0) a += p.A;
-          if (a >= p.A) a = -1;
-          if (p.task_ids && p.t_table) {
-            if (tk < 0) tk += p.n_tasks;
-            if (tk >= p.n_tasks) tk = -1;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float4 av = make_float4(0.f, 0.f, 0.f, 0.f), tv = av;
-          if (a >= 0) av = reinterpret_cast<const float4*>(p.a_table + (long long)a * OF_H + ecg * 16)[i];
-          if (tk >= 0) tv = reinterpret_cast<const float4*>(p.t_table + (long long)tk * OF_H + ecg * 16)[i];
-          const float4 wv = reinterpret_cast<const float4*>(p.w_r + ecg * 16)[i], bq = reinterpret_cast<const float4*>(p.b_r + ecg * 16)[i];
-          const float avv[4] = {av.x, av.y, av.z, av.w}, tvv[4] = {tv.x, tv.y, tv.z, tv.w};
-          const float wr[4] = {bf16_round(wv.x), bf16_round(wv.y), bf16_round(wv.z), bf16_round(wv.w)};
-          const float br[4] = {bf16_round(bq.x), bf16_round(bq.y), bf16_round(bq.z), bf16_round(bq.w)};
-#pragma unroll
-          for (int e = 0; e < 4; e += 2) {
-            const int h = 4 * i + e;
-            re_w[h >> 1] = pack_bf16(bf16_round(rw * wr[e]) + br[e], bf16_round(rw * wr[e + 1]) + br[e + 1]);
-            ae_w[h >> 1] = pack_bf16(bf16_round(avv[e]) * sqH, bf16_round(avv[e + 1]) * sqH);
-            te_w[h >> 1] = pack_bf16(bf16_round(tvv[e]) * sqH, bf16_round(tvv[e + 1]) * sqH);
-          }
-        }
-      }
       of_bar_sync(1, OF_WORKERS * 32);
       dbg_stamp(dbg, 2);
       // ---- one joint code per cell: sum_k min(value_k, size_k) * radix_k  (size_k = "out of range" digit); 4 cells / thread
@@ -279,16 +251,39 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
       if (tile == (int)blockIdx.x) mbar_wait(img_full, 0);   // tables and weights have landed
       of_bar_sync(1, OF_WORKERS * 32);
       dbg_stamp(dbg, 3);
+      // ---- this thread's embedding addends (network.py:304-309): the table rows are REQUESTED here - after the observation
+      //      tile and the cell codes, so that the dependent round trip (last action -> table row) is off the start-up path -
+      //      and consumed after conv1, whose gather they fly under
+      float4 e_av[4], e_tv[4], e_wv[4], e_bq[4];
+      {
+        int a = e_a, tk = e_tk;
+        if (eag < nag) {
+          if (a < 0) a += p.A;
+          if (a >= p.A) a = -1;
+          if (p.task_ids && p.t_table) {
+            if (tk < 0) tk += p.n_tasks;
+            if (tk >= p.n_tasks) tk = -1;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          e_av[i] = e_tv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a >= 0) e_av[i] = reinterpret_cast<const float4*>(p.a_table + (long long)a * OF_H + ecg * 16)[i];
+          if (tk >= 0) e_tv[i] = reinterpret_cast<const float4*>(p.t_table + (long long)tk * OF_H + ecg * 16)[i];
+          e_wv[i] = reinterpret_cast<const float4*>(p.w_r + ecg * 16)[i];
+          e_bq[i] = reinterpret_cast<const float4*>(p.b_r + ecg * 16)[i];
+        }
+      }
       // ---- conv1: lane = (task tsub of 8, channel quad v); 9 conflict-free float4 lookups per task
       {
         const int tsub = lane >> 2, v = lane & 3;
         const float* tbase = sT1 + (tsub & 1) * OF_C1 + 4 * v;
         const uint2 bv = *reinterpret_cast<const uint2*>(sB + 4 * v);
-        for (int g0 = warp; g0 < OF_AG * 25 / 8; g0 += 2 * OF_WORKERS) {      // two task groups in flight per iteration
-          float4 acc[2];
-          int agq[2][2];
+        for (int g0 = warp; g0 < OF_AG * 25 / 8; g0 += OF_NU * OF_WORKERS) {  // OF_NU task groups in flight per iteration
+          float4 acc[OF_NU];
+          int agq[OF_NU][2];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
+          for (int u = 0; u < OF_NU; ++u) {
             const int g = g0 + u * OF_WORKERS;
             const int task = g * 8 + tsub;
             const int ag = task & 31, q = task >> 5;
@@ -306,7 +301,7 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
             }
           }
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
+          for (int u = 0; u < OF_NU; ++u) {
             if (g0 + u * OF_WORKERS < OF_AG * 25 / 8) {
               const int ag = agq[u][0], q = agq[u][1];
               const uint32_t z0 = pack_bf16(acc[u].x, acc[u].y), z1 = pack_bf16(acc[u].z, acc[u].w);
@@ -324,6 +319,25 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
       __syncwarp();
       dbg_stamp(dbg, 4);
       if (lane == 0) mbar_arrive(a1_ready);
+      // ---- the embedding addends, packed (their loads were issued in front of the conv1 gather)
+      uint32_t re_w[8], ae_w[8], te_w[8];
+      {
+        const float rw = bf16_round(e_rw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 av = e_av[i], tv = e_tv[i], wv = e_wv[i], bq = e_bq[i];
+          const float avv[4] = {av.x, av.y, av.z, av.w}, tvv[4] = {tv.x, tv.y, tv.z, tv.w};
+          const float wr[4] = {bf16_round(wv.x), bf16_round(wv.y), bf16_round(wv.z), bf16_round(wv.w)};
+          const float br[4] = {bf16_round(bq.x), bf16_round(bq.y), bf16_round(bq.z), bf16_round(bq.w)};
+#pragma unroll
+          for (int e = 0; e < 4; e += 2) {
+            const int h = 4 * i + e;
+            re_w[h >> 1] = pack_bf16(bf16_round(rw * wr[e]) + br[e], bf16_round(rw * wr[e + 1]) + br[e + 1]);
+            ae_w[h >> 1] = pack_bf16(bf16_round(avv[e]) * sqH, bf16_round(avv[e + 1]) * sqH);
+            te_w[h >> 1] = pack_bf16(bf16_round(tvv[e]) * sqH, bf16_round(tvv[e + 1]) * sqH);
+          }
+        }
+      }
       // ---- conv2 epilogue: rows (px = quarter, agent = lane), this warp's 16 of the 32 channels -> a2
       mbar_wait(c2_full, ph);
       tc_fence_after();
