@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(256) conv1_onehot_joint_kernel(
           if (z_out) *reinterpret_cast<uint2*>(z_out + o) = zz;
           uint2 aa = zz;
           if (apply_gelu) {
-            aa.x = pack_bf16(gelu_tanh(bf16_lo(zz.x)), gelu_tanh(bf16_hi(zz.x)));
-            aa.y = pack_bf16(gelu_tanh(bf16_lo(zz.y)), gelu_tanh(bf16_hi(zz.y)));
+            aa.x = gelu_tanh_bf16x2(zz.x);
+            aa.y = gelu_tanh_bf16x2(zz.y);
           }
           *reinterpret_cast<uint2*>(a_out + o) = aa;
         }

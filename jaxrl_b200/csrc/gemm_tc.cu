@@ -240,7 +240,7 @@ __device__ __forceinline__ void epi_store(const GemmParams& p, int row0, int lan
   }
   if (p.act == 1) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) w[i] = pack_bf16(gelu_tanh(bf16_lo(w[i])), gelu_tanh(bf16_hi(w[i])));
+    for (int i = 0; i < 16; ++i) w[i] = gelu_tanh_bf16x2(w[i]);
   }
   if (p.residual) {
     const bool vec_r = full && ((p.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
@@ -352,7 +352,7 @@ __device__ __forceinline__ void epi_glu(const GemmParams& p, int row0, int lane,
   for (int i = 0; i < 16; ++i) {
     uw[i] = pack_bf16(__uint_as_float(u[2 * i]), __uint_as_float(u[2 * i + 1]));
     gw[i] = pack_bf16(__uint_as_float(g[2 * i]), __uint_as_float(g[2 * i + 1]));
-    const uint32_t aw = pack_bf16(gelu_tanh(bf16_lo(uw[i])), gelu_tanh(bf16_hi(uw[i])));
+    const uint32_t aw = gelu_tanh_bf16x2(uw[i]);
     hw[i] = pack_bf16(bf16_lo(aw) * bf16_lo(gw[i]), bf16_hi(aw) * bf16_hi(gw[i]));
   }
   const long long o = (long long)row0 * p.F + hcol0;

@@ -21,6 +21,19 @@
 namespace mpx {
 
 
+// Shared-space loads for the conv1 gather: through the generic pointers derived from the aligned dynamic window the compiler
+// emits generic LD.E (address-space check per access, lower rate); volatile keeps them behind the named barriers.
+__device__ __forceinline__ uint32_t of_lds_u8(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float4 of_lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
 constexpr int OF_AG = 32;              // agents per tile
 constexpr int OF_WORKERS = 8;          // worker warps
 #ifndef OF_NU
@@ -277,26 +290,42 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
       // ---- conv1: lane = (task tsub of 8, channel quad v); 9 conflict-free float4 lookups per task
       {
         const int tsub = lane >> 2, v = lane & 3;
-        const float* tbase = sT1 + (tsub & 1) * OF_C1 + 4 * v;
+        const uint32_t tbase = smem_u32(sT1) + ((tsub & 1) * OF_C1 + 4 * v) * 4;
+        const uint32_t code_s = smem_u32(sCode);
+        const int NJ = p.NJ;
         const uint2 bv = *reinterpret_cast<const uint2*>(sB + 4 * v);
         for (int g0 = warp; g0 < OF_AG * 25 / 8; g0 += OF_NU * OF_WORKERS) {  // OF_NU task groups in flight per iteration
+          // all code bytes first, then all table rows, then the sums: the loads are volatile (ordered), so a tap-by-tap
+          // code -> row -> add sequence would serialise 18 dependent shared-memory round trips per iteration
           float4 acc[OF_NU];
           int agq[OF_NU][2];
+          uint32_t codes[OF_NU][9];
+          bool on[OF_NU];
 #pragma unroll
           for (int u = 0; u < OF_NU; ++u) {
             const int g = g0 + u * OF_WORKERS;
             const int task = g * 8 + tsub;
             const int ag = task & 31, q = task >> 5;
             agq[u][0] = ag; agq[u][1] = q;
+            on[u] = g < OF_AG * 25 / 8 && ag < nag;
+            const int oy = q / OF_P1, ox = q % OF_P1;
+            const uint32_t c0 = code_s + (on[u] ? ag * (OF_IH * OF_IW) + (oy * 2) * OF_IW + ox * 2 : 0);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) codes[u][tap] = of_lds_u8(c0 + (tap / 3) * OF_IW + (tap % 3));
+          }
+          float4 wrow[OF_NU][9];
+#pragma unroll
+          for (int u = 0; u < OF_NU; ++u)
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap)
+              wrow[u][tap] = of_lds_f4(tbase + (uint32_t)(tap * NJ + (on[u] ? (int)codes[u][tap] : 0)) * (2 * OF_C1 * 4));
+#pragma unroll
+          for (int u = 0; u < OF_NU; ++u) {
             acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g < OF_AG * 25 / 8 && ag < nag) {
-              const int oy = q / OF_P1, ox = q % OF_P1;
-              const uint8_t* c0 = sCode + ag * (OF_IH * OF_IW) + (oy * 2) * OF_IW + ox * 2;
+            if (on[u]) {
 #pragma unroll
               for (int tap = 0; tap < 9; ++tap) {
-                const int code = c0[(tap / 3) * OF_IW + (tap % 3)];
-                const float4 w = *reinterpret_cast<const float4*>(tbase + (tap * p.NJ + code) * (2 * OF_C1));
-                acc[u].x += w.x; acc[u].y += w.y; acc[u].z += w.z; acc[u].w += w.w;
+                acc[u].x += wrow[u][tap].x; acc[u].y += wrow[u][tap].y; acc[u].z += wrow[u][tap].z; acc[u].w += wrow[u][tap].w;
               }
             }
           }
@@ -308,8 +337,8 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
               const uint32_t y0 = pack_bf16(bf16_lo(z0) + bf16_lo(bv.x), bf16_hi(z0) + bf16_hi(bv.x));
               const uint32_t y1 = pack_bf16(bf16_lo(z1) + bf16_lo(bv.y), bf16_hi(z1) + bf16_hi(bv.y));
               uint2 o;
-              o.x = pack_bf16(gelu_tanh(bf16_lo(y0)), gelu_tanh(bf16_hi(y0)));
-              o.y = pack_bf16(gelu_tanh(bf16_lo(y1)), gelu_tanh(bf16_hi(y1)));
+              o.x = gelu_tanh_bf16x2(y0);
+              o.y = gelu_tanh_bf16x2(y1);
               *reinterpret_cast<uint2*>(sA1 + q * 1024 + (ag >> 3) * 256 + (v >> 1) * 128 + (ag & 7) * 16 + (v & 1) * 8) = o;
             }
           }
@@ -364,7 +393,7 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
             for (int e = 0; e < 4; ++e) {
               const uint32_t zw = pack_bf16(__uint_as_float(d[8 * hh + 2 * e]), __uint_as_float(d[8 * hh + 2 * e + 1]));
               const uint32_t zb = pack_bf16(bf16_lo(zw) + bf16_lo(bw[e]), bf16_hi(zw) + bf16_hi(bw[e]));
-              o[e] = pack_bf16(gelu_tanh(bf16_lo(zb)), gelu_tanh(bf16_hi(zb)));
+              o[e] = gelu_tanh_bf16x2(zb);
             }
             const int kk = pos * 4 + chalf * 2 + hh;        // 8-wide K core matrix index: k = pos*32 + chalf*16 + hh*8
             *reinterpret_cast<uint4*>(sA2 + (lane >> 3) * sbo3 + kk * 128 + (lane & 7) * 16) = make_uint4(o[0], o[1], o[2], o[3]);

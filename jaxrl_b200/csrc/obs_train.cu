@@ -335,8 +335,8 @@ __global__ void __launch_bounds__(OT_THREADS, 1) obs_train_fwd_kernel(const ObsT
               zz.x = pack_bf16(bf16_lo(z0) + bf16_lo(bv.x), bf16_hi(z0) + bf16_hi(bv.x));
               zz.y = pack_bf16(bf16_lo(z1) + bf16_lo(bv.y), bf16_hi(z1) + bf16_hi(bv.y));
               uint2 o;
-              o.x = pack_bf16(gelu_tanh(bf16_lo(zz.x)), gelu_tanh(bf16_hi(zz.x)));
-              o.y = pack_bf16(gelu_tanh(bf16_lo(zz.y)), gelu_tanh(bf16_hi(zz.y)));
+              o.x = gelu_tanh_bf16x2(zz.x);
+              o.y = gelu_tanh_bf16x2(zz.y);
               sts_v2(sA_s + q * 4096 + (ag >> 3) * 256 + (v >> 1) * 128 + (ag & 7) * 16 + (v & 1) * 8, o.x, o.y);
               const int go = q * 2048 + ag * 8;                // [q][half][row][8]: 8 tokens x 16 B contiguous per half
               *reinterpret_cast<uint2*>(z1_tile + go) = zz;
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(OT_THREADS, 1) obs_train_fwd_kernel(const ObsT
           for (int e = 0; e < 8; ++e) {
             const uint32_t zw = pack_bf16(__uint_as_float(d[pos & 1][2 * e]), __uint_as_float(d[pos & 1][2 * e + 1]));
             zb[e] = pack_bf16(bf16_lo(zw) + bf16_lo(bw[e]), bf16_hi(zw) + bf16_hi(bw[e]));
-            o[e] = pack_bf16(gelu_tanh(bf16_lo(zb[e])), gelu_tanh(bf16_hi(zb[e])));
+            o[e] = gelu_tanh_bf16x2(zb[e]);
           }
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
