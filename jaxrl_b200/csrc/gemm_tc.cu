@@ -353,7 +353,7 @@ __device__ __forceinline__ void epi_glu(const GemmParams& p, int row0, int lane,
     uw[i] = pack_bf16(__uint_as_float(u[2 * i]), __uint_as_float(u[2 * i + 1]));
     gw[i] = pack_bf16(__uint_as_float(g[2 * i]), __uint_as_float(g[2 * i + 1]));
     const uint32_t aw = gelu_tanh_bf16x2(uw[i]);
-    hw[i] = pack_bf16(bf16_lo(aw) * bf16_lo(gw[i]), bf16_hi(aw) * bf16_hi(gw[i]));
+    hw[i] = bf16x2_mul(aw, gw[i]);
   }
   const long long o = (long long)row0 * p.F + hcol0;
   warp_store_tile(xp, p.h + o, p.F, rows_valid, hw, lane);

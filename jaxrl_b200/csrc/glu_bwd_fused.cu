@@ -230,21 +230,10 @@ glu_bwd_fused_kernel(const GluBwdParams p, const __grid_constant__ CUtensorMap t
           const uint32_t gw = pack_bf16(__uint_as_float(g[2 * i]), __uint_as_float(g[2 * i + 1]));
           const uint32_t dw = pack_bf16(__uint_as_float(dh[2 * i]), __uint_as_float(dh[2 * i + 1]));
           float av[2], gr[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {                       // gelu (tanh form) and its derivative share one sigmoid
-            constexpr float cc = 0.7978845608028654f;
-            constexpr float k1 = -2.0f * cc * 1.4426950408889634f;
-            constexpr float k2 = k1 * 0.044715f;
-            const float x = e ? bf16_hi(uw) : bf16_lo(uw);
-            const float x2 = x * x;
-            const float s = rcp_approx(1.0f + ex2_approx(x * fmaf(k2, x2, k1)));
-            const float dy2 = 2.0f * cc * fmaf(3.0f * 0.044715f, x2, 1.0f);
-            av[e] = x * s;
-            gr[e] = fmaf(x * s * (1.0f - s), dy2, s);
-          }
+          gelu_tanh_val_grad_bf16x2(uw, av, gr);                // gelu and its derivative share one sigmoid
           const uint32_t aw = pack_bf16(av[0], av[1]);
-          dgw[i] = pack_bf16(bf16_lo(dw) * bf16_lo(aw), bf16_hi(dw) * bf16_hi(aw));
-          const uint32_t tw = pack_bf16(bf16_lo(dw) * bf16_lo(gw), bf16_hi(dw) * bf16_hi(gw));
+          dgw[i] = bf16x2_mul(dw, aw);
+          const uint32_t tw = bf16x2_mul(dw, gw);
           duw[i] = pack_bf16(bf16_lo(tw) * gr[0], bf16_hi(tw) * gr[1]);
         }
         if (c < 8) dbg_stamp(dbg, 3 + 3 * c);

@@ -381,7 +381,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
           const uint32_t uw = pack_bf16(__uint_as_float(u[2 * i]), __uint_as_float(u[2 * i + 1]));
           const uint32_t gw = pack_bf16(__uint_as_float(g[2 * i]), __uint_as_float(g[2 * i + 1]));
           const uint32_t aw = gelu_tanh_bf16x2(uw);
-          hw[i] = pack_bf16(bf16_lo(aw) * bf16_lo(gw), bf16_hi(aw) * bf16_hi(gw));
+          hw[i] = bf16x2_mul(aw, gw);
         }
       };
       mbar_wait(&ug_full[0], ug_ph[0]);

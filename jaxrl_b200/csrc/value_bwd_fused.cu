@@ -260,18 +260,7 @@ value_bwd_fused_kernel(const ValueBwdParams p, const __grid_constant__ CUtensorM
           const uint32_t zb = pack_bf16(bf16_lo(zw) + bf16_lo(bw), bf16_hi(zw) + bf16_hi(bw));
           const uint32_t dw = pack_bf16(__uint_as_float(dp[2 * i]), __uint_as_float(dp[2 * i + 1]));
           float av[2], gr[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {                       // gelu (tanh form) and its derivative share one sigmoid
-            constexpr float cc = 0.7978845608028654f;
-            constexpr float k1 = -2.0f * cc * 1.4426950408889634f;
-            constexpr float k2 = k1 * 0.044715f;
-            const float x = e ? bf16_hi(zb) : bf16_lo(zb);
-            const float x2 = x * x;
-            const float s = rcp_approx(1.0f + ex2_approx(x * fmaf(k2, x2, k1)));
-            const float dy2 = 2.0f * cc * fmaf(3.0f * 0.044715f, x2, 1.0f);
-            av[e] = x * s;
-            gr[e] = fmaf(x * s * (1.0f - s), dy2, s);
-          }
+          gelu_tanh_val_grad_bf16x2(zb, av, gr);                // gelu and its derivative share one sigmoid
           pvw[i] = pack_bf16(av[0], av[1]);
           dzw[i] = pack_bf16(bf16_lo(dw) * gr[0], bf16_hi(dw) * gr[1]);
         }
