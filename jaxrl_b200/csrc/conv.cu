@@ -220,8 +220,8 @@ __global__ void __launch_bounds__(256) conv1_onehot_joint_kernel(
         if (g0 + 8 * u < C1J_AG * 25 / 8 && ag < nag) {
           const uint32_t z0 = pack_bf16(acc[u].x, acc[u].y), z1 = pack_bf16(acc[u].z, acc[u].w);
           uint2 zz;
-          zz.x = pack_bf16(bf16_lo(z0) + bf16_lo(bv.x), bf16_hi(z0) + bf16_hi(bv.x));
-          zz.y = pack_bf16(bf16_lo(z1) + bf16_lo(bv.y), bf16_hi(z1) + bf16_hi(bv.y));
+          zz.x = bf16x2_add(z0, bv.x);
+          zz.y = bf16x2_add(z1, bv.y);
           const long long o = (m0 * 25 + task[u]) * 16 + 4 * v;         // row = (m0 + ag)*25 + q == m0*25 + task
           if (z_out) *reinterpret_cast<uint2*>(z_out + o) = zz;
           uint2 aa = zz;

@@ -306,7 +306,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
           const int j = i & 15;
           const uint32_t yw = pack_bf16(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
           const uint32_t rw = (i & 3) == 0 ? rx[i >> 2].x : (i & 3) == 1 ? rx[i >> 2].y : (i & 3) == 2 ? rx[i >> 2].z : rx[i >> 2].w;
-          xw[i] = pack_bf16(bf16_lo(yw) + bf16_lo(rw), bf16_hi(yw) + bf16_hi(rw));
+          xw[i] = bf16x2_add(yw, rw);
           const float a = bf16_lo(xw[i]), b2 = bf16_hi(xw[i]);
           ss += a * a + b2 * b2;
         }

@@ -334,8 +334,8 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
             if (g0 + u * OF_WORKERS < OF_AG * 25 / 8) {
               const int ag = agq[u][0], q = agq[u][1];
               const uint32_t z0 = pack_bf16(acc[u].x, acc[u].y), z1 = pack_bf16(acc[u].z, acc[u].w);
-              const uint32_t y0 = pack_bf16(bf16_lo(z0) + bf16_lo(bv.x), bf16_hi(z0) + bf16_hi(bv.x));
-              const uint32_t y1 = pack_bf16(bf16_lo(z1) + bf16_lo(bv.y), bf16_hi(z1) + bf16_hi(bv.y));
+              const uint32_t y0 = bf16x2_add(z0, bv.x);
+              const uint32_t y1 = bf16x2_add(z1, bv.y);
               uint2 o;
               o.x = gelu_tanh_bf16x2(y0);
               o.y = gelu_tanh_bf16x2(y1);
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const uint32_t zw = pack_bf16(__uint_as_float(d[8 * hh + 2 * e]), __uint_as_float(d[8 * hh + 2 * e + 1]));
-              const uint32_t zb = pack_bf16(bf16_lo(zw) + bf16_lo(bw[e]), bf16_hi(zw) + bf16_hi(bw[e]));
+              const uint32_t zb = bf16x2_add(zw, bw[e]);
               o[e] = gelu_tanh_bf16x2(zb);
             }
             const int kk = pos * 4 + chalf * 2 + hh;        // 8-wide K core matrix index: k = pos*32 + chalf*16 + hh*8
@@ -436,16 +436,16 @@ __global__ void __launch_bounds__(OF_THREADS, 1) obs_fused_kernel(const ObsFused
           const float4 vq = *reinterpret_cast<const float4*>(sOut + eag * OF_H + blk * 32 + 4 * (i ^ (eag & 7)));
           const uint2 b3 = *reinterpret_cast<const uint2*>(sB + 48 + c4 * 4);
           const uint32_t c0 = pack_bf16(vq.x, vq.y), c1 = pack_bf16(vq.z, vq.w);              // conv3 output -> bf16
-          const uint32_t e0 = pack_bf16(bf16_lo(c0) + bf16_lo(b3.x), bf16_hi(c0) + bf16_hi(b3.x));   // + bias
-          const uint32_t e1 = pack_bf16(bf16_lo(c1) + bf16_lo(b3.y), bf16_hi(c1) + bf16_hi(b3.y));
+          const uint32_t e0 = bf16x2_add(c0, b3.x);   // + bias
+          const uint32_t e1 = bf16x2_add(c1, b3.y);
           ew[2 * i4] = e0; ew[2 * i4 + 1] = e1;
-          uint32_t x0 = pack_bf16(bf16_lo(e0) + bf16_lo(re_w[2 * i4]), bf16_hi(e0) + bf16_hi(re_w[2 * i4]));
-          uint32_t x1 = pack_bf16(bf16_lo(e1) + bf16_lo(re_w[2 * i4 + 1]), bf16_hi(e1) + bf16_hi(re_w[2 * i4 + 1]));
-          x0 = pack_bf16(bf16_lo(x0) + bf16_lo(ae_w[2 * i4]), bf16_hi(x0) + bf16_hi(ae_w[2 * i4]));
-          x1 = pack_bf16(bf16_lo(x1) + bf16_lo(ae_w[2 * i4 + 1]), bf16_hi(x1) + bf16_hi(ae_w[2 * i4 + 1]));
+          uint32_t x0 = bf16x2_add(e0, re_w[2 * i4]);
+          uint32_t x1 = bf16x2_add(e1, re_w[2 * i4 + 1]);
+          x0 = bf16x2_add(x0, ae_w[2 * i4]);
+          x1 = bf16x2_add(x1, ae_w[2 * i4 + 1]);
           if (p.task_ids && p.t_table) {
-            x0 = pack_bf16(bf16_lo(x0) + bf16_lo(te_w[2 * i4]), bf16_hi(x0) + bf16_hi(te_w[2 * i4]));
-            x1 = pack_bf16(bf16_lo(x1) + bf16_lo(te_w[2 * i4 + 1]), bf16_hi(x1) + bf16_hi(te_w[2 * i4 + 1]));
+            x0 = bf16x2_add(x0, te_w[2 * i4]);
+            x1 = bf16x2_add(x1, te_w[2 * i4 + 1]);
           }
           ow[2 * i4] = x0; ow[2 * i4 + 1] = x1;
         }

@@ -332,8 +332,8 @@ __global__ void __launch_bounds__(OT_THREADS, 1) obs_train_fwd_kernel(const ObsT
             if (g0 + u * OT_WORKERS < NG && ag < nag) {
               const uint32_t z0 = pack_bf16(acc[u].x, acc[u].y), z1 = pack_bf16(acc[u].z, acc[u].w);
               uint2 zz;
-              zz.x = pack_bf16(bf16_lo(z0) + bf16_lo(bv.x), bf16_hi(z0) + bf16_hi(bv.x));
-              zz.y = pack_bf16(bf16_lo(z1) + bf16_lo(bv.y), bf16_hi(z1) + bf16_hi(bv.y));
+              zz.x = bf16x2_add(z0, bv.x);
+              zz.y = bf16x2_add(z1, bv.y);
               uint2 o;
               o.x = gelu_tanh_bf16x2(zz.x);
               o.y = gelu_tanh_bf16x2(zz.y);
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(OT_THREADS, 1) obs_train_fwd_kernel(const ObsT
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const uint32_t zw = pack_bf16(__uint_as_float(d[pos & 1][2 * e]), __uint_as_float(d[pos & 1][2 * e + 1]));
-            zb[e] = pack_bf16(bf16_lo(zw) + bf16_lo(bw[e]), bf16_hi(zw) + bf16_hi(bw[e]));
+            zb[e] = bf16x2_add(zw, bw[e]);
             o[e] = gelu_tanh_bf16x2(zb[e]);
           }
 #pragma unroll
@@ -489,21 +489,21 @@ __global__ void __launch_bounds__(OT_THREADS, 1) obs_train_fwd_kernel(const ObsT
             const float4 vq = lds_f4(sA_s + (er * OF_H + blk * 32 + 4 * (i ^ (er & 7))) * 4);
             const uint2 b3 = lds_v2(sB_s + 96 + c4 * 8);
             const uint32_t c0 = pack_bf16(vq.x, vq.y), c1 = pack_bf16(vq.z, vq.w);              // conv3 output -> bf16
-            const uint32_t e0 = pack_bf16(bf16_lo(c0) + bf16_lo(b3.x), bf16_hi(c0) + bf16_hi(b3.x));   // + bias
-            const uint32_t e1 = pack_bf16(bf16_lo(c1) + bf16_lo(b3.y), bf16_hi(c1) + bf16_hi(b3.y));
+            const uint32_t e0 = bf16x2_add(c0, b3.x);   // + bias
+            const uint32_t e1 = bf16x2_add(c1, b3.y);
             ew[2 * i4] = e0; ew[2 * i4 + 1] = e1;
             const float rw = rw_r[r];
             const uint32_t re0 = pack_bf16(bf16_round(rw * bf16_lo(wr_p[2 * i4])) + bf16_lo(br_p[2 * i4]),
                                            bf16_round(rw * bf16_hi(wr_p[2 * i4])) + bf16_hi(br_p[2 * i4]));
             const uint32_t re1 = pack_bf16(bf16_round(rw * bf16_lo(wr_p[2 * i4 + 1])) + bf16_lo(br_p[2 * i4 + 1]),
                                            bf16_round(rw * bf16_hi(wr_p[2 * i4 + 1])) + bf16_hi(br_p[2 * i4 + 1]));
-            uint32_t x0 = pack_bf16(bf16_lo(e0) + bf16_lo(re0), bf16_hi(e0) + bf16_hi(re0));
-            uint32_t x1 = pack_bf16(bf16_lo(e1) + bf16_lo(re1), bf16_hi(e1) + bf16_hi(re1));
-            x0 = pack_bf16(bf16_lo(x0) + bf16_lo(ae_w[r][2 * i4]), bf16_hi(x0) + bf16_hi(ae_w[r][2 * i4]));
-            x1 = pack_bf16(bf16_lo(x1) + bf16_lo(ae_w[r][2 * i4 + 1]), bf16_hi(x1) + bf16_hi(ae_w[r][2 * i4 + 1]));
+            uint32_t x0 = bf16x2_add(e0, re0);
+            uint32_t x1 = bf16x2_add(e1, re1);
+            x0 = bf16x2_add(x0, ae_w[r][2 * i4]);
+            x1 = bf16x2_add(x1, ae_w[r][2 * i4 + 1]);
             if (has_task) {
-              x0 = pack_bf16(bf16_lo(x0) + bf16_lo(te_w[r][2 * i4]), bf16_hi(x0) + bf16_hi(te_w[r][2 * i4]));
-              x1 = pack_bf16(bf16_lo(x1) + bf16_lo(te_w[r][2 * i4 + 1]), bf16_hi(x1) + bf16_hi(te_w[r][2 * i4 + 1]));
+              x0 = bf16x2_add(x0, te_w[r][2 * i4]);
+              x1 = bf16x2_add(x1, te_w[r][2 * i4 + 1]);
             }
             ow[2 * i4] = x0; ow[2 * i4 + 1] = x1;
           }

@@ -257,7 +257,7 @@ value_bwd_fused_kernel(const ValueBwdParams p, const __grid_constant__ CUtensorM
         for (int i = 0; i < 16; ++i) {
           const uint32_t bw = i & 3 ? (i & 3) == 1 ? bv[i >> 2].y : (i & 3) == 2 ? bv[i >> 2].z : bv[i >> 2].w : bv[i >> 2].x;
           const uint32_t zw = pack_bf16(__uint_as_float(z[2 * i]), __uint_as_float(z[2 * i + 1]));
-          const uint32_t zb = pack_bf16(bf16_lo(zw) + bf16_lo(bw), bf16_hi(zw) + bf16_hi(bw));
+          const uint32_t zb = bf16x2_add(zw, bw);
           const uint32_t dw = pack_bf16(__uint_as_float(dp[2 * i]), __uint_as_float(dp[2 * i + 1]));
           float av[2], gr[2];
           gelu_tanh_val_grad_bf16x2(zb, av, gr);                // gelu and its derivative share one sigmoid

@@ -346,7 +346,7 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const uint32_t zw = pack_bf16(__uint_as_float(z[8 * i + 2 * e]), __uint_as_float(z[8 * i + 2 * e + 1]));
-            const uint32_t zb = pack_bf16(bf16_lo(zw) + bf16_lo(bw[e]), bf16_hi(zw) + bf16_hi(bw[e]));
+            const uint32_t zb = bf16x2_add(zw, bw[e]);
             hw[4 * i + e] = gelu_tanh_bf16x2(zb);
           }
         }
