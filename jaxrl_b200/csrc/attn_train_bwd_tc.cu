@@ -240,19 +240,25 @@ attn_bwd_tc2_kernel(const AttnBwdTcParams p, const __grid_constant__ CUtensorMap
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty);                  // S / dP are in registers: the next half may be issued
         uint32_t pw[32], dw[32];
+        // packed f32x2 arithmetic, two keys per instruction: x = fma(s, scale_log2, -lse), dS = (P * (dP - delta)) * scale
+        const unsigned long long sc2 = f32x2_pack(p.scale_log2, p.scale_log2), nl2 = f32x2_pack(-lse_r, -lse_r);
+        const unsigned long long nd2 = f32x2_pack(-dl_r, -dl_r), s2 = f32x2_pack(p.scale, p.scale);
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc)
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            float p0 = ex2_approx(__uint_as_float(sv[cc][2 * e]) * p.scale_log2 - lse_r);
-            float p1 = ex2_approx(__uint_as_float(sv[cc][2 * e + 1]) * p.scale_log2 - lse_r);
+            float x0, x1;
+            f32x2_unpack(f32x2_fma(f32x2_pack(__uint_as_float(sv[cc][2 * e]), __uint_as_float(sv[cc][2 * e + 1])), sc2, nl2), x0, x1);
+            float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
             if (diag) {
               if (64 * half + 32 * cc + 2 * e > r) p0 = 0.f;
               if (64 * half + 32 * cc + 2 * e + 1 > r) p1 = 0.f;
             }
             pw[16 * cc + e] = pack_bf16(p0, p1);
-            dw[16 * cc + e] = pack_bf16(p0 * (__uint_as_float(dpv[cc][2 * e]) - dl_r) * p.scale,
-                                        p1 * (__uint_as_float(dpv[cc][2 * e + 1]) - dl_r) * p.scale);
+            const unsigned long long t = f32x2_add(f32x2_pack(__uint_as_float(dpv[cc][2 * e]), __uint_as_float(dpv[cc][2 * e + 1])), nd2);
+            float d0, d1;
+            f32x2_unpack(f32x2_mul(f32x2_mul(f32x2_pack(p0, p1), t), s2), d0, d1);
+            dw[16 * cc + e] = pack_bf16(d0, d1);
           }
         if (it < 6) dbg_stamp(dbg, 2 + 10 * it + 5 * half);
         if (half == 0) {

@@ -315,9 +315,10 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       for (int j = 0; j < 64; ++j)
         if (kt * TC_KT + j > qrow) sraw[j >> 5][j & 31] = 0xff800000u;   // -inf
     }
-    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};       // four independent chains (fixed-latency stalls)
-#pragma unroll
-    for (int j = 0; j < 64; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(sraw[j >> 5][j & 31]));
+    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};       // four independent chains (fixed-latency stalls),
+#pragma unroll                                                          // two scores per FMNMX3
+    for (int j = 0; j < 64; j += 2)
+      mx4[(j >> 1) & 3] = fmax3(mx4[(j >> 1) & 3], __uint_as_float(sraw[j >> 5][j & 31]), __uint_as_float(sraw[j >> 5][(j & 31) + 1]));
     const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
     const float mn = fmaxf(m, mx * scale_log2);
     const float alpha = ex2_approx(m - mn);
@@ -337,27 +338,39 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       }
     }
     const float neg_m = -m;
-    float l4[4] = {0.f, 0.f, 0.f, 0.f};
+    // packed f32x2 arithmetic: one FFMA2 scales two scores and subtracts the maximum, one FADD2 adds two probabilities to a
+    // pair of partial row sums (four independent pair chains)
+    const unsigned long long sc2 = f32x2_pack(scale_log2, scale_log2), nm2 = f32x2_pack(neg_m, neg_m);
+    unsigned long long l4[4] = {0ull, 0ull, 0ull, 0ull};
     uint8_t* prow = sP + wt * 128;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       float pv[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
+      for (int e = 0; e < 8; e += 2) {
         const int j = c * 8 + e;
-        const float x = fmaf(__uint_as_float(sraw[j >> 5][j & 31]), scale_log2, neg_m);
-        // every 4th exponential runs as a polynomial on the FMA pipe (the MUFU pipe is the busiest unit of this loop)
-        pv[e] = (e & 3) == 3 ? ex2_poly3(x) : ex2_approx(x);
+        float x0, x1;
+        f32x2_unpack(f32x2_fma(f32x2_pack(__uint_as_float(sraw[j >> 5][j & 31]), __uint_as_float(sraw[j >> 5][(j & 31) + 1])), sc2, nm2),
+                     x0, x1);
+        // every 4th exponential runs as a polynomial on the FMA pipe (the MUFU pipe is the busiest unit of this loop);
+        // evaluating the two of a group together as f32x2 costs registers the 128-register budget does not have (spills:
+        // 102 instead of 94 us)
+        pv[e] = ex2_approx(x0);
+        pv[e + 1] = (e & 3) == 2 ? ex2_poly3(x1) : ex2_approx(x1);
       }
       uint32_t w[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         w[e] = pack_bf16(pv[2 * e], pv[2 * e + 1]);
-        l4[e] += pv[2 * e] + pv[2 * e + 1];
+        l4[e] = f32x2_add(l4[e], f32x2_pack(pv[2 * e], pv[2 * e + 1]));
       }
       *reinterpret_cast<uint4*>(prow + ((c ^ (wt & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+    {
+      float a0, a1;
+      f32x2_unpack(f32x2_add(f32x2_add(l4[0], l4[1]), f32x2_add(l4[2], l4[3])), a0, a1);
+      l += a0 + a1;
+    }
     fence_proxy_async_smem();
     tc_fence_before();
     wg_sync(wg);
