@@ -317,16 +317,17 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
         sSq[half * 128 + r] = ss;
         gf_bar_sync(1, GF_EPI_WARPS * 32);
         const float inv = rsqrtf((sSq[r] + sSq[128 + r]) * (1.0f / 128.0f) + p.eps);
+        const unsigned long long inv2 = f32x2_pack(inv, inv);
         const float4* sc4 = reinterpret_cast<const float4*>(sScale + half * 64);
         const uint32_t xrow = smem_u32(sX + half * 16384 + r * 128);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1];
           uint4 o;
-          o.x = pack_bf16(bf16_lo(xw[4 * c]) * inv * s0.x, bf16_hi(xw[4 * c]) * inv * s0.y);
-          o.y = pack_bf16(bf16_lo(xw[4 * c + 1]) * inv * s0.z, bf16_hi(xw[4 * c + 1]) * inv * s0.w);
-          o.z = pack_bf16(bf16_lo(xw[4 * c + 2]) * inv * s1.x, bf16_hi(xw[4 * c + 2]) * inv * s1.y);
-          o.w = pack_bf16(bf16_lo(xw[4 * c + 3]) * inv * s1.z, bf16_hi(xw[4 * c + 3]) * inv * s1.w);
+          o.x = bf16x2_norm_scale(xw[4 * c], inv2, s0.x, s0.y);
+          o.y = bf16x2_norm_scale(xw[4 * c + 1], inv2, s0.z, s0.w);
+          o.z = bf16x2_norm_scale(xw[4 * c + 2], inv2, s1.x, s1.y);
+          o.w = bf16x2_norm_scale(xw[4 * c + 3], inv2, s1.z, s1.w);
           sts_v4(xrow + ((c ^ (r & 7)) << 4), o);
         }
         fence_proxy_async_smem();

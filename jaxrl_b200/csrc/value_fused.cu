@@ -54,7 +54,9 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sX = smem;                         // 2 x 16 KB: x tile, K blocks 0 and 1
-  uint8_t* sH = smem + 32768;                 // 2 x 16 KB: pv chunk double buffer
+#if !VF_H_TMEM
+  uint8_t* sH = smem + 32768;                 // 2 x 16 KB: pv chunk double buffer (the TMEM form leaves this region unused)
+#endif
   uint8_t* sW = smem + 65536;                 // VF_STAGES x 16 KB weight ring
   uint8_t* sP = sW + VF_STAGES * VF_STAGE_BYTES;   // 32 KB: fp32 partial logits [16 float4 columns][128 rows]
   uint8_t* sR = sP + 32768;                   // 8 KB: summed logits of one 32-row group [16 float4 columns][32 rows]
@@ -272,11 +274,12 @@ value_fused_kernel(const ValueFusedParams p, const __grid_constant__ CUtensorMap
           sSq[half * 128 + r] = ss;
           named_bar_sync(1, VF_EPI_WARPS * 32);
           const float inv = rsqrtf((sSq[r] + sSq[128 + r]) * (1.0f / 128.0f) + p.eps);
+          const unsigned long long inv2 = f32x2_pack(inv, inv);
           const float2* sc2 = reinterpret_cast<const float2*>(sScale + half * 64);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float2 s2 = sc2[i];
-            xw[i] = pack_bf16(bf16_lo(xw[i]) * inv * s2.x, bf16_hi(xw[i]) * inv * s2.y);
+            xw[i] = bf16x2_norm_scale(xw[i], inv2, s2.x, s2.y);
           }
         }
         tc_fence_after();
