@@ -464,9 +464,7 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
               uint32_t ow[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float y0 = bf16_round(__uint_as_float(acc[8 * i + 2 * e]));
-                const float y1 = bf16_round(__uint_as_float(acc[8 * i + 2 * e + 1]));
-                ow[e] = pack_bf16(y0 + bf16_lo(rw[e]), y1 + bf16_hi(rw[e]));
+                ow[e] = bf16x2_add(pack_bf16(__uint_as_float(acc[8 * i + 2 * e]), __uint_as_float(acc[8 * i + 2 * e + 1])), rw[e]);
               }
               o4[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }
@@ -537,14 +535,14 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
           const uint32_t x1row = smem_u32(sX1 + rt * 256);
           const uint4 rv0 = lds_v4(x1row + (((2 * sub) ^ (rt & 7)) << 4)), rv1 = lds_v4(x1row + (((2 * sub + 1) ^ (rt & 7)) << 4));
           uint32_t xw[8];
-          xw[0] = pack_bf16(bf16_round(sm[0].x) + bf16_lo(rv0.x), bf16_round(sm[0].y) + bf16_hi(rv0.x));
-          xw[1] = pack_bf16(bf16_round(sm[0].z) + bf16_lo(rv0.y), bf16_round(sm[0].w) + bf16_hi(rv0.y));
-          xw[2] = pack_bf16(bf16_round(sm[1].x) + bf16_lo(rv0.z), bf16_round(sm[1].y) + bf16_hi(rv0.z));
-          xw[3] = pack_bf16(bf16_round(sm[1].z) + bf16_lo(rv0.w), bf16_round(sm[1].w) + bf16_hi(rv0.w));
-          xw[4] = pack_bf16(bf16_round(sm[2].x) + bf16_lo(rv1.x), bf16_round(sm[2].y) + bf16_hi(rv1.x));
-          xw[5] = pack_bf16(bf16_round(sm[2].z) + bf16_lo(rv1.y), bf16_round(sm[2].w) + bf16_hi(rv1.y));
-          xw[6] = pack_bf16(bf16_round(sm[3].x) + bf16_lo(rv1.z), bf16_round(sm[3].y) + bf16_hi(rv1.z));
-          xw[7] = pack_bf16(bf16_round(sm[3].z) + bf16_lo(rv1.w), bf16_round(sm[3].w) + bf16_hi(rv1.w));
+          xw[0] = bf16x2_add(pack_bf16(sm[0].x, sm[0].y), rv0.x);
+          xw[1] = bf16x2_add(pack_bf16(sm[0].z, sm[0].w), rv0.y);
+          xw[2] = bf16x2_add(pack_bf16(sm[1].x, sm[1].y), rv0.z);
+          xw[3] = bf16x2_add(pack_bf16(sm[1].z, sm[1].w), rv0.w);
+          xw[4] = bf16x2_add(pack_bf16(sm[2].x, sm[2].y), rv1.x);
+          xw[5] = bf16x2_add(pack_bf16(sm[2].z, sm[2].w), rv1.y);
+          xw[6] = bf16x2_add(pack_bf16(sm[3].x, sm[3].y), rv1.z);
+          xw[7] = bf16x2_add(pack_bf16(sm[3].z, sm[3].w), rv1.w);
           const long long grow = (long long)tile * 128 + rt;
           const bool live = grow < p.M;
           if (live) {
@@ -624,10 +622,10 @@ glu_fused_kernel(const GluFusedParams p, const __grid_constant__ CUtensorMap tm_
             const uint4 rv = PROJ ? lds_v4(smem_u32(sX1 + r * 256) + ((((ocol0 + 4 * i) >> 3) ^ (r & 7)) << 4))
                                     : (ncta == 4) ? rres[(i >> 1) & 1] : *reinterpret_cast<const uint4*>(p.residual + o);
             uint4 ov;
-            ov.x = pack_bf16(bf16_round(s0.x) + bf16_lo(rv.x), bf16_round(s0.y) + bf16_hi(rv.x));
-            ov.y = pack_bf16(bf16_round(s0.z) + bf16_lo(rv.y), bf16_round(s0.w) + bf16_hi(rv.y));
-            ov.z = pack_bf16(bf16_round(s1.x) + bf16_lo(rv.z), bf16_round(s1.y) + bf16_hi(rv.z));
-            ov.w = pack_bf16(bf16_round(s1.z) + bf16_lo(rv.w), bf16_round(s1.w) + bf16_hi(rv.w));
+            ov.x = bf16x2_add(pack_bf16(s0.x, s0.y), rv.x);
+            ov.y = bf16x2_add(pack_bf16(s0.z, s0.w), rv.y);
+            ov.z = bf16x2_add(pack_bf16(s1.x, s1.y), rv.z);
+            ov.w = bf16x2_add(pack_bf16(s1.z, s1.w), rv.w);
             *reinterpret_cast<uint4*>(p.out + o) = ov;
           }
         }
